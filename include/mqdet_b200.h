@@ -1,0 +1,141 @@
+/* mqdet_b200 — C ABI of the B200-native MQ-Det hot path.
+ *
+ * Every entry point takes DEVICE pointers + explicit sizes/strides + a cudaStream_t (passed as
+ * void*), allocates nothing, never synchronises the device, and returns 0 on success or a
+ * negative error code (the text is available from mqdet_last_error(), thread-local).
+ *
+ * What each group replaces in the reference (paths relative to the MQ-Det repository root):
+ *   - mqdet_gemm_f16 / mqdet_layernorm / mqdet_softmax_rows: the ATen Linear/LayerNorm/softmax
+ *     chains of maskrcnn_benchmark/modeling/language_backbone/modeling_bert_new.py:196-248,347-374,
+ *     maskrcnn_benchmark/utils/fuse_helper.py:218-303 and
+ *     maskrcnn_benchmark/modeling/rpn/modeling_bert.py:39-270.
+ *   - mqdet_gcp_sparse_attn / mqdet_gcp_gate_residual_ln: MaskedCrossAttention.forward (sparse)
+ *     modeling_bert_new.py:162-248 and GatedCrossAttentionBlock.forward :347-374.
+ *   - mqdet_ml_nms: maskrcnn_benchmark._C.ml_nms (maskrcnn_benchmark/csrc/ml_nms.h:11-27,
+ *     csrc/cuda/ml_nms.cu:79-149).
+ *   - mqdet_dcnv2_im2col: maskrcnn_benchmark._C.modulated_deform_conv_forward
+ *     (csrc/cuda/deform_conv_cuda.cu:496-575, deform_conv_kernel_cuda.cu:578-641).
+ *   - mqdet_anchors / mqdet_atss_*: modeling/rpn/anchor_generator.py:72-137 and
+ *     modeling/rpn/inference.py:620-769.
+ */
+#ifndef MQDET_B200_H_
+#define MQDET_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MQDET_F16 0
+#define MQDET_F32 1
+
+#define MQDET_ACT_NONE 0
+#define MQDET_ACT_GELU 1 /* exact erf GELU */
+#define MQDET_ACT_RELU 2
+
+#define MQDET_VEC_NONE 0
+#define MQDET_VEC_SCALAR 1  /* one device float */
+#define MQDET_VEC_PER_COL 2 /* length N */
+#define MQDET_VEC_PER_ROW 3 /* length M */
+
+#define MQDET_GEMM_IMPL_TCGEN05 0 /* TMA + tcgen05.mma + TMEM (product path) */
+#define MQDET_GEMM_IMPL_SIMT 1    /* plain shared-memory tiled fp32-FMA kernel (validation only) */
+
+const char* mqdet_last_error(void);
+int mqdet_version(void);
+
+/* D[z] = epilogue( A[z] (M x K, fp16, K contiguous) * B[z]^T (N x K, fp16, K contiguous) ), fp32 accumulate.
+ *   v = alpha*acc + bias            (scale_after_bias == 0)
+ *   v = alpha*(acc + bias)          (scale_after_bias != 0)
+ *   v = act(v); v = clamp(v, -clamp, +clamp) if clamp > 0
+ *   v = gate * v   (gate optionally passed through tanh);  v += residual;  D = v
+ * z = z1 + nb1*z2 ranges over nb1*nb2 batches; a batch stride of 0 broadcasts that operand.
+ * B laid out [N, K] is exactly an nn.Linear weight, so y = x W^T needs no transposition.
+ * Requirements: K % 8 == 0, lda/ldb and batch strides % 8 == 0, A/B 16-byte aligned. */
+typedef struct mqdet_gemm_args {
+  const void* A;
+  const void* B;
+  int64_t M, N, K;
+  int64_t lda, ldb;
+  int64_t nb1, nb2;
+  int64_t a_b1, a_b2, b_b1, b_b2;
+  void* C;
+  int32_t c_dtype; /* MQDET_F16 / MQDET_F32 */
+  int64_t ldc, c_b1, c_b2;
+  float alpha;
+  int32_t scale_after_bias;
+  const float* bias;
+  int32_t bias_mode; /* MQDET_VEC_NONE / PER_COL / PER_ROW */
+  int64_t bias_b1, bias_b2;
+  int32_t act;
+  float clamp;
+  const float* gate;
+  int32_t gate_mode; /* MQDET_VEC_* */
+  int32_t gate_tanh;
+  const void* R; /* residual, same logical shape as D */
+  int32_t r_dtype;
+  int64_t ldr, r_b1, r_b2;
+} mqdet_gemm_args;
+
+int mqdet_gemm_f16(const mqdet_gemm_args* args, int impl, void* stream);
+
+/* Row-wise LayerNorm over the last dim D (biased variance, eps inside sqrt).
+ * x: [rows, D] in_dtype with row stride ldx; out16 (fp16) and/or out32 (fp32) may be NULL.
+ * If zero_row_period > 0, rows r with (r % zero_row_period) == zero_row_period-1 are treated as an
+ * all-zero input row (the GCP padding vision slot, modeling_bert_new.py:176-180) and x is not read. */
+int mqdet_layernorm(const void* x, int in_dtype, int64_t ldx, const float* gamma, const float* beta,
+                    float eps, int64_t rows, int64_t D, void* out16, void* out32, int64_t ldo,
+                    int64_t zero_row_period, void* stream);
+
+/* residual add + LayerNorm:  y = LN(a + b).  a,b fp32 [rows, D]; writes fp32 and/or fp16. */
+int mqdet_add_layernorm(const float* a, const float* b, const float* gamma, const float* beta, float eps,
+                        int64_t rows, int64_t D, float* out32, void* out16, float clamp, void* stream);
+
+/* Sparse GCP attention (modeling_bert_new.py:162-248 with K/V de-duplicated per unique query):
+ *   q   [B*T, H*Dh] fp16 (already scaled),  kv [B, V+1, 2*H*Dh] fp16 (row V = padding slot; K | V halves)
+ *   idx [B*T, S] int32 in [0, V] (V = padding);  out [B*T, H*Dh] fp16.
+ * sim = q.k (+ -1e4 on padding) -> softmax over S -> zero padding probs -> sum p*v. */
+int mqdet_gcp_sparse_attn(const void* q, const void* kv, const int32_t* idx, void* out, int64_t B, int64_t T,
+                          int64_t V, int64_t S, int64_t H, int64_t Dh, void* stream);
+
+/* GCP gate + residual + FFN pre-norm (modeling_bert_new.py:359-372):
+ *   g = tanh(h1[r,:] . w2);  x1 = s*g + x;  writes x1 (fp32) and LN(x1; gamma,beta) (fp16).
+ *   h1 [rows, Dg] fp16, w2 [Dg] fp32, s/x [rows, D] fp32.  gate_out (optional) receives g[r]. */
+int mqdet_gcp_gate_residual_ln(const void* h1, const float* w2, int64_t Dg, const float* s, const float* x,
+                               const float* gamma, const float* beta, float eps, int64_t rows, int64_t D,
+                               float* x1_out, void* ln_out16, float* gate_out, void* stream);
+
+/* Build the [B*T, S] index table from a 0/1 mask [B, V, T] (fp32): ascending v with mask != 0,
+ * padded with V (get_index_with_padding_batch, modeling_bert_new.py:40-63). counts_out[B*T] optional. */
+int mqdet_gcp_build_index(const float* mask, int64_t B, int64_t V, int64_t T, int64_t S, int32_t* idx,
+                          int32_t* counts_out, void* stream);
+
+/* Row softmax over the last dim with optional additive column mask (warp per row, fp32 math).
+ *   x [rows, n] fp16/fp32 (row stride ldx) -> y fp16 [rows, n_pad] (row stride ldy); columns [n, n_pad) := 0.
+ *   v = x*scale + (colmask[batch, c] == 0 ? mask_value : keep_add);  batch = row / rows_per_batch.
+ *   BERT self-attention: mask_value -10000, keep_add 0.  BiAttention (fuse_helper.py:270-283): -9e15 / +1. */
+int mqdet_softmax_rows(const void* x, int in_dtype, int64_t ldx, void* y, int64_t ldy, int64_t rows, int64_t n,
+                       int64_t n_pad, float scale, const float* colmask, int64_t rows_per_batch, float mask_value,
+                       float keep_add, void* stream);
+
+/* fp32 -> fp16 cast (n elements), and fp16 -> fp32. */
+int mqdet_cast_f32_f16(const float* x, void* y, int64_t n, void* stream);
+int mqdet_cast_f16_f32(const void* x, float* y, int64_t n, void* stream);
+
+/* Stable descending argsort of n <= 16384 fp32 scores (ties: lower index first), single CTA bitonic sort. */
+int mqdet_argsort_desc(const float* scores, int64_t n, int64_t* order, void* stream);
+
+/* Multi-label NMS, same arithmetic as maskrcnn_benchmark/csrc/cuda/ml_nms.cu (bit-identical kept set):
+ *   boxes [n,4] f32 xyxy, scores [n] f32, labels [n] f32, order int64 [n] = indices by score descending.
+ *   keep_out int64 [n] receives the kept ORIGINAL indices ascending, *num_keep (device int32) the count.
+ *   max_det > 0 additionally applies the `score >= kth-largest kept score` cut of rpn/inference.py:757-767.
+ *   workspace: mqdet_ml_nms_workspace_bytes(n) bytes.  No host sync, no D2H.  n <= 16384. */
+int64_t mqdet_ml_nms_workspace_bytes(int64_t n);
+int mqdet_ml_nms(const float* boxes, const float* scores, const float* labels, const int64_t* order, int64_t n,
+                 float thresh, int64_t max_det, int64_t* keep_out, int32_t* num_keep, void* workspace, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MQDET_B200_H_ */

@@ -1,0 +1,91 @@
+"""ctypes binding of libmqdet_b200.so (the C-ABI boundary, see include/mqdet_b200.h).
+
+The library is built in-tree by ``__graft_entry__.build()`` (``make -C mqdet_b200/csrc``).  There is no
+CPU or PyTorch fallback: if the shared object is missing, loading raises.
+"""
+import ctypes
+import os
+from ctypes import POINTER, c_char_p, c_float, c_int, c_int32, c_int64, c_void_p
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libmqdet_b200.so")
+
+F16, F32 = 0, 1
+ACT_NONE, ACT_GELU, ACT_RELU = 0, 1, 2
+VEC_NONE, VEC_SCALAR, VEC_PER_COL, VEC_PER_ROW = 0, 1, 2, 3
+IMPL_TCGEN05, IMPL_SIMT = 0, 1
+
+
+class GemmArgs(ctypes.Structure):
+    """Mirror of ``mqdet_gemm_args`` (include/mqdet_b200.h)."""
+
+    _fields_ = [
+        ("A", c_void_p), ("B", c_void_p),
+        ("M", c_int64), ("N", c_int64), ("K", c_int64),
+        ("lda", c_int64), ("ldb", c_int64),
+        ("nb1", c_int64), ("nb2", c_int64),
+        ("a_b1", c_int64), ("a_b2", c_int64), ("b_b1", c_int64), ("b_b2", c_int64),
+        ("C", c_void_p), ("c_dtype", c_int32),
+        ("ldc", c_int64), ("c_b1", c_int64), ("c_b2", c_int64),
+        ("alpha", c_float), ("scale_after_bias", c_int32),
+        ("bias", c_void_p), ("bias_mode", c_int32), ("bias_b1", c_int64), ("bias_b2", c_int64),
+        ("act", c_int32), ("clamp", c_float),
+        ("gate", c_void_p), ("gate_mode", c_int32), ("gate_tanh", c_int32),
+        ("R", c_void_p), ("r_dtype", c_int32), ("ldr", c_int64), ("r_b1", c_int64), ("r_b2", c_int64),
+    ]
+
+
+# name -> (restype, argtypes); every symbol include/mqdet_b200.h declares must appear here
+# (tests/test_abi.py checks the two lists against each other).
+SIGNATURES = {
+    "mqdet_last_error": (c_char_p, []),
+    "mqdet_version": (c_int, []),
+    "mqdet_gemm_f16": (c_int, [POINTER(GemmArgs), c_int, c_void_p]),
+    "mqdet_layernorm": (c_int, [c_void_p, c_int, c_int64, c_void_p, c_void_p, c_float, c_int64, c_int64, c_void_p,
+                                c_void_p, c_int64, c_int64, c_void_p]),
+    "mqdet_add_layernorm": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_int64, c_int64, c_void_p,
+                                    c_void_p, c_float, c_void_p]),
+    "mqdet_gcp_sparse_attn": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64,
+                                      c_int64, c_int64, c_void_p]),
+    "mqdet_gcp_gate_residual_ln": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p,
+                                           c_float, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "mqdet_gcp_build_index": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_int64, c_void_p, c_void_p, c_void_p]),
+    "mqdet_softmax_rows": (c_int, [c_void_p, c_int, c_int64, c_void_p, c_int64, c_int64, c_int64, c_int64, c_float,
+                                   c_void_p, c_int64, c_float, c_float, c_void_p]),
+    "mqdet_cast_f32_f16": (c_int, [c_void_p, c_void_p, c_int64, c_void_p]),
+    "mqdet_cast_f16_f32": (c_int, [c_void_p, c_void_p, c_int64, c_void_p]),
+    "mqdet_argsort_desc": (c_int, [c_void_p, c_int64, c_void_p, c_void_p]),
+    "mqdet_ml_nms_workspace_bytes": (c_int64, [c_int64]),
+    "mqdet_ml_nms": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_float, c_int64, c_void_p, c_void_p,
+                             c_void_p, c_void_p]),
+}
+
+_lib = None
+
+
+class MqdetError(RuntimeError):
+    """Raised when a C-ABI call returns a negative code (mirrors the reference's AT_ERROR -> RuntimeError)."""
+
+
+def load():
+    """Load the shared library and bind every declared symbol (raises if the build is missing)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise MqdetError(
+            f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(there is no CPU / PyTorch fallback for the mqdet_b200 hot path)")
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the symbol is not exported
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(rc, what=""):
+    if rc != 0:
+        msg = load().mqdet_last_error()
+        raise MqdetError(f"{what} failed ({rc}): {msg.decode() if msg else ''}")

@@ -1,0 +1,397 @@
+// mqdet_b200 — fp16 x fp16 -> fp32-accumulate GEMM with fused epilogue, hand-written for sm_100a.
+//
+//   D[z][m,n] = epi( sum_k A[z][m,k] * B[z][n,k] )      (both operands K-contiguous: "TN")
+//
+// Product kernel (gemm_tc_kernel): warp-specialised, one 128 x BLOCK_N output tile per CTA.
+//   warp 0   : TMA producer  — cp.async.bulk.tensor (4-D maps, 128B swizzle) into a STAGES-deep ring
+//   warp 1   : MMA issuer    — one lane issues tcgen05.mma.cta_group::1.kind::f16 (M=128,N=BLOCK_N,K=16),
+//                              tcgen05.commit releases ring slots / signals the epilogue
+//   warp 2   : TMEM allocator (BLOCK_N fp32 columns)
+//   warps 4-7: epilogue      — tcgen05.ld (lane == output row) -> bias/act/gate/residual -> 16B stores
+// Two CTAs fit per SM (<=~100 KB smem, <=256 TMEM columns each) so one CTA's epilogue overlaps the
+// other's main loop; the grid runs n-tiles fastest so the A row-panel is shared through L2.
+//
+// Validation kernel (gemm_simt_kernel): plain 64x64 shared-memory tiled FMA kernel with the same
+// epilogue, used by the tests to cross-check the tensor-core path (never by the product path).
+#include "common.cuh"
+#include "../../include/mqdet_b200.h"
+
+namespace mqdet {
+
+struct GemmP {
+  const __half* A;
+  const __half* B;
+  long M, N, K, lda, ldb;
+  int nb1, nb2;
+  long a_b1, a_b2, b_b1, b_b2;
+  void* C;
+  int c_dtype;
+  long ldc, c_b1, c_b2;
+  float alpha;
+  int scale_after_bias;
+  const float* bias;
+  int bias_mode;
+  long bias_b1, bias_b2;
+  int act;
+  float clamp;
+  const float* gate;
+  int gate_mode, gate_tanh;
+  const void* R;
+  int r_dtype;
+  long ldr, r_b1, r_b2;
+  int a_bcast1, a_bcast2, b_bcast1, b_bcast2;  // 1 -> TMA coordinate pinned to 0
+};
+
+// One output element's epilogue (shared by both kernels).
+__device__ __forceinline__ float epi_one(const GemmP& p, float acc, long row, long col, int z1, int z2,
+                                         float gate_scalar) {
+  float v = acc;
+  float b = 0.f;
+  if (p.bias_mode == MQDET_VEC_PER_COL)
+    b = p.bias[z1 * p.bias_b1 + z2 * p.bias_b2 + col];
+  else if (p.bias_mode == MQDET_VEC_PER_ROW)
+    b = p.bias[z1 * p.bias_b1 + z2 * p.bias_b2 + row];
+  v = p.scale_after_bias ? p.alpha * (v + b) : p.alpha * v + b;
+  if (p.act == MQDET_ACT_GELU)
+    v = gelu_erf(v);
+  else if (p.act == MQDET_ACT_RELU)
+    v = fmaxf(v, 0.f);
+  if (p.clamp > 0.f) v = fminf(fmaxf(v, -p.clamp), p.clamp);
+  if (p.gate_mode == MQDET_VEC_SCALAR) {
+    v *= gate_scalar;
+  } else if (p.gate_mode == MQDET_VEC_PER_COL) {
+    float g = p.gate[col];
+    v *= p.gate_tanh ? tanhf(g) : g;
+  } else if (p.gate_mode == MQDET_VEC_PER_ROW) {
+    float g = p.gate[row];
+    v *= p.gate_tanh ? tanhf(g) : g;
+  }
+  if (p.R) {
+    long off = z1 * p.r_b1 + z2 * p.r_b2 + row * p.ldr + col;
+    v += (p.r_dtype == MQDET_F32) ? reinterpret_cast<const float*>(p.R)[off]
+                                  : __half2float(reinterpret_cast<const __half*>(p.R)[off]);
+  }
+  return v;
+}
+
+__device__ __forceinline__ void store_one(const GemmP& p, float v, long row, long col, int z1, int z2) {
+  long off = z1 * p.c_b1 + z2 * p.c_b2 + row * p.ldc + col;
+  if (p.c_dtype == MQDET_F32)
+    reinterpret_cast<float*>(p.C)[off] = v;
+  else
+    reinterpret_cast<__half*>(p.C)[off] = __float2half_rn(v);
+}
+
+// ---------------------------------------------------------------------------------------------
+// tcgen05 kernel
+// ---------------------------------------------------------------------------------------------
+constexpr int BM = 128;
+constexpr int BK = 64;  // 64 fp16 = 128 B = one swizzle row
+
+template <int BN, int STAGES>
+struct TcCfg {
+  static constexpr int A_BYTES = BM * BK * 2;
+  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(256) gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a,
+                                                      const __grid_constant__ CUtensorMap tma_b,
+                                                      const GemmP p) {
+  using Cfg = TcCfg<BN, STAGES>;
+  extern __shared__ uint8_t smem_raw[];
+  // 128B-swizzled tiles need 1024-byte alignment.
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + STAGES * Cfg::A_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + STAGES;
+  uint64_t* tmem_full_bar = bars + 2 * STAGES;
+  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int n_tile = blockIdx.x, m_tile = blockIdx.y;
+  const int z1 = blockIdx.z % p.nb1, z2 = blockIdx.z / p.nb1;
+  const int num_kb = (int)((p.K + BK - 1) / BK);
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tma_a);
+    tma_prefetch_desc(&tma_b);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(tmem_full_bar, 1);
+    fence_mbar_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_base_slot, BN);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_base_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      const int az1 = p.a_bcast1 ? 0 : z1, az2 = p.a_bcast2 ? 0 : z2;
+      const int bz1 = p.b_bcast1 ? 0 : z1, bz2 = p.b_bcast2 ? 0 : z2;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb % STAGES;
+        const uint32_t ph = (kb / STAGES) & 1;
+        mbar_wait(&empty_bar[s], ph ^ 1);
+        mbar_expect_tx(&full_bar[s], Cfg::STAGE_BYTES);
+        tma_load_4d(smem_a + s * Cfg::A_BYTES, &tma_a, &full_bar[s], kb * BK, m_tile * BM, az1, az2);
+        tma_load_4d(smem_b + s * Cfg::B_BYTES, &tma_b, &full_bar[s], kb * BK, n_tile * BN, bz1, bz2);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_f16(BM, BN, 0);
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb % STAGES;
+        const uint32_t ph = (kb / STAGES) & 1;
+        mbar_wait(&full_bar[s], ph);
+        tc_fence_after();
+        const uint32_t a_addr = smem_u32(smem_a + s * Cfg::A_BYTES);
+        const uint32_t b_addr = smem_u32(smem_b + s * Cfg::B_BYTES);
+#pragma unroll
+        for (int k = 0; k < BK / 16; ++k) {
+          // advance 16 fp16 = 32 B along K inside the 128B swizzle row
+          const uint64_t da = umma_desc_k_sw128(a_addr + k * 32);
+          const uint64_t db = umma_desc_k_sw128(b_addr + k * 32);
+          tc_mma_f16(tmem_base, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+        }
+        tc_commit(&empty_bar[s]);  // slot reusable once these MMAs have read it
+      }
+      tc_commit(tmem_full_bar);  // accumulator complete
+    }
+  } else if (warp >= 4) {
+    const int ew = warp - 4;  // == warp % 4 -> TMEM lane quarter this warp may access
+    mbar_wait(tmem_full_bar, 0);
+    tc_fence_after();
+    const long row = (long)m_tile * BM + ew * 32 + lane;
+    const bool row_ok = row < p.M;
+    float gate_scalar = 1.f;
+    if (p.gate_mode == MQDET_VEC_SCALAR) {
+      gate_scalar = p.gate[0];
+      if (p.gate_tanh) gate_scalar = tanhf(gate_scalar);
+    }
+    const bool vec_ok = ((p.ldc & 7) == 0) && ((p.c_b1 & 7) == 0) && ((p.c_b2 & 7) == 0) &&
+                        ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0);
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+      uint32_t r[32];
+      tmem_ld_32x32(tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)c0, r);
+      tmem_ld_wait();
+      const long col0 = (long)n_tile * BN + c0;
+      if (row_ok && col0 < p.N) {
+        float v[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const long col = col0 + i;
+          v[i] = (col < p.N) ? epi_one(p, __uint_as_float(r[i]), row, col, z1, z2, gate_scalar) : 0.f;
+        }
+        if (vec_ok && col0 + 32 <= p.N) {
+          const long off = z1 * p.c_b1 + z2 * p.c_b2 + row * p.ldc + col0;
+          if (p.c_dtype == MQDET_F32) {
+            float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.C) + off);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) dst[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+          } else {
+            uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__half*>(p.C) + off);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              __half2 h0 = __floats2half2_rn(v[8 * i + 0], v[8 * i + 1]);
+              __half2 h1 = __floats2half2_rn(v[8 * i + 2], v[8 * i + 3]);
+              __half2 h2 = __floats2half2_rn(v[8 * i + 4], v[8 * i + 5]);
+              __half2 h3 = __floats2half2_rn(v[8 * i + 6], v[8 * i + 7]);
+              uint4 u;
+              u.x = *reinterpret_cast<uint32_t*>(&h0);
+              u.y = *reinterpret_cast<uint32_t*>(&h1);
+              u.z = *reinterpret_cast<uint32_t*>(&h2);
+              u.w = *reinterpret_cast<uint32_t*>(&h3);
+              dst[i] = u;
+            }
+          }
+        } else {
+#pragma unroll 1
+          for (int i = 0; i < 32; ++i)
+            if (col0 + i < p.N) store_one(p, v[i], row, col0 + i, z1, z2);
+        }
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, BN);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// SIMT validation kernel: 64x64 tile, 16x16 threads, 4x4 micro-tile.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) gemm_simt_kernel(const GemmP p) {
+  __shared__ float sa[16][64 + 1];
+  __shared__ float sb[16][64 + 1];
+  const int z1 = blockIdx.z % p.nb1, z2 = blockIdx.z / p.nb1;
+  const __half* A = p.A + z1 * p.a_b1 + z2 * p.a_b2;
+  const __half* B = p.B + z1 * p.b_b1 + z2 * p.b_b2;
+  const long m0 = (long)blockIdx.y * 64, n0 = (long)blockIdx.x * 64;
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  float acc[4][4] = {};
+  for (long k0 = 0; k0 < p.K; k0 += 16) {
+    for (int i = threadIdx.x; i < 64 * 16; i += 256) {
+      const int r = i >> 4, k = i & 15;
+      const long gm = m0 + r, gn = n0 + r, gk = k0 + k;
+      sa[k][r] = (gm < p.M && gk < p.K) ? __half2float(A[gm * p.lda + gk]) : 0.f;
+      sb[k][r] = (gn < p.N && gk < p.K) ? __half2float(B[gn * p.ldb + gk]) : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      float a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a[i] = sa[k][ty * 4 + i];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) b[j] = sb[k][tx * 4 + j];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+  float gate_scalar = 1.f;
+  if (p.gate_mode == MQDET_VEC_SCALAR) {
+    gate_scalar = p.gate[0];
+    if (p.gate_tanh) gate_scalar = tanhf(gate_scalar);
+  }
+  for (int i = 0; i < 4; ++i)
+    for (int j = 0; j < 4; ++j) {
+      const long row = m0 + ty * 4 + i, col = n0 + tx * 4 + j;
+      if (row < p.M && col < p.N) store_one(p, epi_one(p, acc[i][j], row, col, z1, z2, gate_scalar), row, col, z1, z2);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode_fn() {
+  static PFN_encodeTiled fn = nullptr;
+  if (!fn) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres);
+    if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !ptr) {
+      set_error("cudaGetDriverEntryPoint(cuTensorMapEncodeTiled) failed: %s", cudaGetErrorString(e));
+      return nullptr;
+    }
+    fn = reinterpret_cast<PFN_encodeTiled>(ptr);
+  }
+  return fn;
+}
+
+// 4-D map over an fp16 operand viewed as [b2][b1][rows][K]; box = [1][1][box_rows][64].
+static int make_operand_map(CUtensorMap* map, const void* ptr, long rows, long K, long ld, int nb1, long s1, int nb2,
+                            long s2, int box_rows, int* bcast1, int* bcast2) {
+  PFN_encodeTiled enc = get_encode_fn();
+  if (!enc) return MQDET_ERR_CUDA;
+  *bcast1 = (s1 == 0 || nb1 == 1);
+  *bcast2 = (s2 == 0 || nb2 == 1);
+  cuuint64_t dims[4] = {(cuuint64_t)K, (cuuint64_t)rows, (cuuint64_t)(*bcast1 ? 1 : nb1),
+                        (cuuint64_t)(*bcast2 ? 1 : nb2)};
+  // strides (bytes) of dims 1..3; unused batch dims get a harmless non-zero stride
+  cuuint64_t strides[3] = {(cuuint64_t)ld * 2, (cuuint64_t)((*bcast1 ? ld * rows : s1) * 2),
+                           (cuuint64_t)((*bcast2 ? ld * rows : s2) * 2)};
+  if (strides[1] == 0) strides[1] = 16;
+  if (strides[2] == 0) strides[2] = 16;
+  cuuint32_t box[4] = {(cuuint32_t)BK, (cuuint32_t)box_rows, 1, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed (%d): rows=%ld K=%ld ld=%ld nb1=%d s1=%ld nb2=%d s2=%ld ptr=%p", (int)r,
+              rows, K, ld, nb1, s1, nb2, s2, ptr);
+    return MQDET_ERR_CUDA;
+  }
+  return MQDET_OK;
+}
+
+template <int BN, int STAGES>
+static int launch_tc(const GemmP& p0, cudaStream_t st) {
+  using Cfg = TcCfg<BN, STAGES>;
+  GemmP p = p0;
+  CUtensorMap ma, mb;
+  int rc = make_operand_map(&ma, p.A, p.M, p.K, p.lda, p.nb1, p.a_b1, p.nb2, p.a_b2, BM, &p.a_bcast1, &p.a_bcast2);
+  if (rc) return rc;
+  rc = make_operand_map(&mb, p.B, p.N, p.K, p.ldb, p.nb1, p.b_b1, p.nb2, p.b_b2, BN, &p.b_bcast1, &p.b_bcast2);
+  if (rc) return rc;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         Cfg::SMEM_BYTES);
+    if (e != cudaSuccess) {
+      set_error("cudaFuncSetAttribute(smem=%d) failed: %s", Cfg::SMEM_BYTES, cudaGetErrorString(e));
+      return MQDET_ERR_CUDA;
+    }
+    attr_set = true;
+  }
+  dim3 grid(cdiv(p.N, BN), cdiv(p.M, BM), p.nb1 * p.nb2);
+  gemm_tc_kernel<BN, STAGES><<<grid, 256, Cfg::SMEM_BYTES, st>>>(ma, mb, p);
+  return check_launch("gemm_tc_kernel");
+}
+
+}  // namespace mqdet
+
+using namespace mqdet;
+
+extern "C" int mqdet_gemm_f16(const mqdet_gemm_args* a, int impl, void* stream) {
+  MQ_REQUIRE(a && a->A && a->B && a->C, "gemm: null pointer");
+  MQ_REQUIRE(a->M > 0 && a->N > 0 && a->K > 0, "gemm: empty problem M=%ld N=%ld K=%ld", (long)a->M, (long)a->N,
+             (long)a->K);
+  MQ_REQUIRE(a->nb1 >= 1 && a->nb2 >= 1 && a->nb1 * a->nb2 <= 65535, "gemm: bad batch %ld x %ld", (long)a->nb1,
+             (long)a->nb2);
+  MQ_REQUIRE(a->c_dtype == MQDET_F16 || a->c_dtype == MQDET_F32, "gemm: bad c_dtype");
+  GemmP p;
+  memset(&p, 0, sizeof(p));
+  p.A = (const __half*)a->A;
+  p.B = (const __half*)a->B;
+  p.M = a->M; p.N = a->N; p.K = a->K; p.lda = a->lda; p.ldb = a->ldb;
+  p.nb1 = (int)a->nb1; p.nb2 = (int)a->nb2;
+  p.a_b1 = a->a_b1; p.a_b2 = a->a_b2; p.b_b1 = a->b_b1; p.b_b2 = a->b_b2;
+  p.C = a->C; p.c_dtype = a->c_dtype; p.ldc = a->ldc; p.c_b1 = a->c_b1; p.c_b2 = a->c_b2;
+  p.alpha = a->alpha; p.scale_after_bias = a->scale_after_bias;
+  p.bias = a->bias; p.bias_mode = a->bias ? a->bias_mode : MQDET_VEC_NONE;
+  p.bias_b1 = a->bias_b1; p.bias_b2 = a->bias_b2;
+  p.act = a->act; p.clamp = a->clamp;
+  p.gate = a->gate; p.gate_mode = a->gate ? a->gate_mode : MQDET_VEC_NONE; p.gate_tanh = a->gate_tanh;
+  p.R = a->R; p.r_dtype = a->r_dtype; p.ldr = a->ldr; p.r_b1 = a->r_b1; p.r_b2 = a->r_b2;
+  cudaStream_t st = (cudaStream_t)stream;
+
+  if (impl == MQDET_GEMM_IMPL_SIMT) {
+    dim3 grid(cdiv(p.N, 64), cdiv(p.M, 64), p.nb1 * p.nb2);
+    gemm_simt_kernel<<<grid, 256, 0, st>>>(p);
+    return check_launch("gemm_simt_kernel");
+  }
+  MQ_REQUIRE(impl == MQDET_GEMM_IMPL_TCGEN05, "gemm: unknown impl %d", impl);
+  MQ_REQUIRE((a->K % 8) == 0 && (a->lda % 8) == 0 && (a->ldb % 8) == 0, "gemm: K/lda/ldb must be multiples of 8");
+  MQ_REQUIRE((a->a_b1 % 8) == 0 && (a->a_b2 % 8) == 0 && (a->b_b1 % 8) == 0 && (a->b_b2 % 8) == 0,
+             "gemm: batch strides must be multiples of 8");
+  MQ_REQUIRE(((uintptr_t)a->A % 16) == 0 && ((uintptr_t)a->B % 16) == 0, "gemm: A/B must be 16-byte aligned");
+  // Tile-N heuristic: widest tile that still gives >= ~1 wave of CTAs on 148 SMs.
+  const long mt = cdiv(p.M, BM), z = (long)p.nb1 * p.nb2;
+  if (p.N > 128 && mt * cdiv(p.N, 256) * z >= 148) return launch_tc<256, 4>(p, st);
+  if (p.N > 64 && (mt * cdiv(p.N, 128) * z >= 148 || p.N > 2048)) return launch_tc<128, 3>(p, st);
+  if (p.N > 32) return launch_tc<64, 4>(p, st);
+  return launch_tc<32, 4>(p, st);
+}

@@ -1,0 +1,250 @@
+// mqdet_b200 — multi-label NMS entirely on the device (no D2H of the suppression mask, no host scan).
+//
+// Reference: maskrcnn_benchmark/csrc/cuda/ml_nms.cu (devIoU :15-26, ml_nms_kernel :28-76, host scan :129-140,
+// ascending original indices :145-149) and the top-k cut of rpn/inference.py:757-767.
+// Same arithmetic (fp32, +1 pixel widths, label-gated, strict '>' threshold) so kept indices are bit-identical.
+//
+//   1. argsort_desc_kernel  : single-CTA bitonic sort of (score desc, index asc) -> order   [n <= 16384]
+//   2. nms_mask_kernel      : 64x64 blocks of the upper-triangular suppression bit matrix (sorted order)
+//   3. nms_scan_kernel      : single CTA; per 64-box block, one thread resolves the diagonal word serially,
+//                             all threads OR the kept rows into the removed-set words of later blocks
+//   4. nms_compact_kernel   : flags in ORIGINAL index space -> ascending kept indices (+ optional top-k cut)
+#include "common.cuh"
+#include "../../include/mqdet_b200.h"
+
+namespace mqdet {
+
+constexpr int NMS_MAX_N = 16384;
+constexpr int NMS_MAX_BLOCKS = NMS_MAX_N / 64;
+
+__device__ __forceinline__ float dev_iou(const float* a, const float* b) {
+  if (a[5] != b[5]) return 0.0f;
+  float left = fmaxf(a[0], b[0]), right = fminf(a[2], b[2]);
+  float top = fmaxf(a[1], b[1]), bottom = fminf(a[3], b[3]);
+  float width = fmaxf(right - left + 1, 0.f), height = fmaxf(bottom - top + 1, 0.f);
+  float interS = width * height;
+  float Sa = (a[2] - a[0] + 1) * (a[3] - a[1] + 1);
+  float Sb = (b[2] - b[0] + 1) * (b[3] - b[1] + 1);
+  return interS / (Sa + Sb - interS);
+}
+
+// keys: score descending, ties by ascending original index (== a stable descending sort).
+__global__ void __launch_bounds__(1024) argsort_desc_kernel(const float* __restrict__ scores, int n, long long* __restrict__ order) {
+  extern __shared__ unsigned long long keys[];
+  int np2 = 1;
+  while (np2 < n) np2 <<= 1;
+  for (int i = threadIdx.x; i < np2; i += blockDim.x) {
+    unsigned long long k = ~0ull;  // sentinels sort last
+    if (i < n) {
+      unsigned int u = __float_as_uint(scores[i]);
+      u = (u & 0x80000000u) ? ~u : (u | 0x80000000u);  // ascending-sortable
+      u = ~u;                                          // -> descending
+      k = ((unsigned long long)u << 32) | (unsigned int)i;
+    }
+    keys[i] = k;
+  }
+  __syncthreads();
+  for (int k = 2; k <= np2; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = threadIdx.x; i < np2; i += blockDim.x) {
+        int ixj = i ^ j;
+        if (ixj > i) {
+          unsigned long long a = keys[i], b = keys[ixj];
+          bool up = ((i & k) == 0);
+          if ((a > b) == up) {
+            keys[i] = b;
+            keys[ixj] = a;
+          }
+        }
+      }
+      __syncthreads();
+    }
+  }
+  for (int i = threadIdx.x; i < n; i += blockDim.x) order[i] = (long long)(keys[i] & 0xffffffffu);
+}
+
+// gathers boxes into sorted [n,6] rows (x1,y1,x2,y2,score,label) — the layout ml_nms.cu works on.
+__global__ void nms_gather_kernel(const float* __restrict__ boxes, const float* __restrict__ scores,
+                                  const float* __restrict__ labels, const long long* __restrict__ order, int n,
+                                  float* __restrict__ sorted) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  long long o = order[i];
+  sorted[i * 6 + 0] = boxes[o * 4 + 0];
+  sorted[i * 6 + 1] = boxes[o * 4 + 1];
+  sorted[i * 6 + 2] = boxes[o * 4 + 2];
+  sorted[i * 6 + 3] = boxes[o * 4 + 3];
+  sorted[i * 6 + 4] = scores[o];
+  sorted[i * 6 + 5] = labels[o];
+}
+
+__global__ void __launch_bounds__(64) nms_mask_kernel(int n, float thresh, const float* __restrict__ sorted,
+                                                      unsigned long long* __restrict__ mask) {
+  const int row_start = blockIdx.y, col_start = blockIdx.x;
+  const int col_blocks = (n + 63) / 64;
+  if (col_start < row_start) {  // lower triangle is never read by the scan
+    return;
+  }
+  const int row_size = min(n - row_start * 64, 64);
+  const int col_size = min(n - col_start * 64, 64);
+  __shared__ float bb[64 * 6];
+  if ((int)threadIdx.x < col_size) {
+#pragma unroll
+    for (int k = 0; k < 6; ++k) bb[threadIdx.x * 6 + k] = sorted[(64 * col_start + threadIdx.x) * 6 + k];
+  }
+  __syncthreads();
+  if ((int)threadIdx.x < row_size) {
+    const int cur = 64 * row_start + threadIdx.x;
+    const float* cb = sorted + cur * 6;
+    unsigned long long t = 0;
+    int start = (row_start == col_start) ? threadIdx.x + 1 : 0;
+    for (int i = start; i < col_size; ++i)
+      if (dev_iou(cb, bb + i * 6) > thresh) t |= 1ULL << i;
+    mask[(long)cur * col_blocks + col_start] = t;
+  }
+}
+
+// Greedy scan in sorted order. flags[orig] = 1 for kept boxes; kth_score = score of the max_det-th kept box.
+__global__ void __launch_bounds__(256) nms_scan_kernel(int n, const unsigned long long* __restrict__ mask,
+                                                       const long long* __restrict__ order, const float* __restrict__ sorted,
+                                                       int max_det, unsigned char* __restrict__ flags,
+                                                       float* __restrict__ kth_score, int* __restrict__ n_kept_sorted) {
+  __shared__ unsigned long long remv[NMS_MAX_BLOCKS];
+  __shared__ unsigned long long diag[64];
+  __shared__ unsigned long long keepbits;
+  __shared__ int kept_so_far;
+  const int col_blocks = (n + 63) / 64;
+  for (int i = threadIdx.x; i < col_blocks; i += blockDim.x) remv[i] = 0;
+  if (threadIdx.x == 0) {
+    kept_so_far = 0;
+    *kth_score = -INFINITY;
+  }
+  __syncthreads();
+  for (int blk = 0; blk < col_blocks; ++blk) {
+    const int base = blk * 64;
+    const int size = min(n - base, 64);
+    if ((int)threadIdx.x < size) diag[threadIdx.x] = mask[(long)(base + threadIdx.x) * col_blocks + blk];
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      unsigned long long r = remv[blk], kb = 0;
+      for (int t = 0; t < size; ++t) {
+        if (!(r & (1ULL << t))) {
+          kb |= 1ULL << t;
+          r |= diag[t];
+          ++kept_so_far;
+          if (max_det > 0 && kept_so_far == max_det) *kth_score = sorted[(base + t) * 6 + 4];
+        }
+      }
+      keepbits = kb;
+    }
+    __syncthreads();
+    const unsigned long long kb = keepbits;
+    if ((int)threadIdx.x < size && (kb & (1ULL << threadIdx.x))) flags[order[base + threadIdx.x]] = 1;
+    // OR the kept rows into the removed words of later column blocks
+    for (int j = blk + 1 + threadIdx.x; j < col_blocks; j += blockDim.x) {
+      unsigned long long r = remv[j];
+      unsigned long long bits = kb;
+      while (bits) {
+        int t = __ffsll((long long)bits) - 1;
+        bits &= bits - 1;
+        r |= mask[(long)(base + t) * col_blocks + j];
+      }
+      remv[j] = r;
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *n_kept_sorted = kept_so_far;
+}
+
+// Ascending compaction of flagged original indices; if more than max_det were kept, apply the
+// "score >= kth largest kept score" cut of rpn/inference.py:759-767 (ties keep extras).
+__global__ void __launch_bounds__(1024) nms_compact_kernel(int n, const unsigned char* __restrict__ flags,
+                                                           const float* __restrict__ scores, int max_det,
+                                                           const float* __restrict__ kth_score,
+                                                           const int* __restrict__ n_kept_sorted,
+                                                           long long* __restrict__ keep_out, int* __restrict__ num_keep) {
+  __shared__ int warp_tot[32];
+  __shared__ int running;
+  if (threadIdx.x == 0) running = 0;
+  __syncthreads();
+  const bool cut = max_det > 0 && *n_kept_sorted > max_det;
+  const float thr = *kth_score;
+  for (int base = 0; base < n; base += blockDim.x) {
+    const int i = base + threadIdx.x;
+    int f = 0;
+    if (i < n && flags[i]) f = cut ? (scores[i] >= thr) : 1;
+    const unsigned ball = __ballot_sync(0xffffffffu, f);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int prefix = __popc(ball & ((1u << lane) - 1));
+    if (lane == 0) warp_tot[warp] = __popc(ball);
+    __syncthreads();
+    int woff = 0;
+    for (int w = 0; w < warp; ++w) woff += warp_tot[w];
+    const int start = running;
+    if (f) keep_out[start + woff + prefix] = i;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int tot = 0;
+      for (int w = 0; w < (int)(blockDim.x >> 5); ++w) tot += warp_tot[w];
+      running = start + tot;
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *num_keep = running;
+}
+
+}  // namespace mqdet
+
+using namespace mqdet;
+
+static inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+extern "C" int mqdet_argsort_desc(const float* scores, int64_t n, int64_t* order, void* stream) {
+  MQ_REQUIRE(scores && order, "argsort_desc: null pointer");
+  MQ_REQUIRE(n >= 0 && n <= NMS_MAX_N, "argsort_desc: n=%ld exceeds %d", (long)n, NMS_MAX_N);
+  if (n == 0) return MQDET_OK;
+  int np2 = 1;
+  while (np2 < n) np2 <<= 1;
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(argsort_desc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, NMS_MAX_N * 8);
+    attr = true;
+  }
+  argsort_desc_kernel<<<1, 1024, (size_t)np2 * 8, (cudaStream_t)stream>>>(scores, (int)n, (long long*)order);
+  return check_launch("argsort_desc_kernel");
+}
+
+extern "C" int64_t mqdet_ml_nms_workspace_bytes(int64_t n) {
+  if (n <= 0) return 256;
+  const size_t cb = (size_t)(n + 63) / 64;
+  return (int64_t)(align256((size_t)n * 6 * 4) + align256((size_t)n * cb * 8) + align256((size_t)n) + 256);
+}
+
+extern "C" int mqdet_ml_nms(const float* boxes, const float* scores, const float* labels, const int64_t* order, int64_t n,
+                            float thresh, int64_t max_det, int64_t* keep_out, int32_t* num_keep, void* workspace,
+                            void* stream) {
+  MQ_REQUIRE(num_keep, "ml_nms: null num_keep");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (n == 0) {  // reference returns an empty tensor (csrc/ml_nms.h:19-20)
+    cudaMemsetAsync(num_keep, 0, sizeof(int32_t), st);
+    return MQDET_OK;
+  }
+  MQ_REQUIRE(boxes && scores && labels && order && keep_out && workspace, "ml_nms: null pointer");
+  MQ_REQUIRE(n <= NMS_MAX_N, "ml_nms: n=%ld exceeds %d", (long)n, NMS_MAX_N);
+  const int cb = (int)((n + 63) / 64);
+  uint8_t* ws = (uint8_t*)workspace;
+  float* sorted = (float*)ws;
+  ws += align256((size_t)n * 6 * 4);
+  unsigned long long* mask = (unsigned long long*)ws;
+  ws += align256((size_t)n * cb * 8);
+  unsigned char* flags = ws;
+  ws += align256((size_t)n);
+  float* kth = (float*)ws;
+  int* nkept = (int*)(ws + 16);
+  cudaMemsetAsync(flags, 0, (size_t)n, st);
+  nms_gather_kernel<<<cdiv(n, 256), 256, 0, st>>>(boxes, scores, labels, (const long long*)order, (int)n, sorted);
+  nms_mask_kernel<<<dim3(cb, cb), 64, 0, st>>>((int)n, thresh, sorted, mask);
+  nms_scan_kernel<<<1, 256, 0, st>>>((int)n, mask, (const long long*)order, sorted, (int)max_det, flags, kth, nkept);
+  nms_compact_kernel<<<1, 1024, 0, st>>>((int)n, flags, scores, (int)max_det, kth, nkept, (long long*)keep_out, num_keep);
+  return check_launch("ml_nms");
+}

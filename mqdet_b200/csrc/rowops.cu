@@ -1,0 +1,186 @@
+// mqdet_b200 — row-wise HBM-bound kernels: LayerNorm, add+LayerNorm, masked softmax, casts.
+// One warp per row, fp32 statistics, coalesced strided-by-lane accesses.
+#include "common.cuh"
+#include "../../include/mqdet_b200.h"
+
+namespace mqdet {
+
+template <typename T>
+__device__ __forceinline__ float ld_as_float(const T* p);
+template <>
+__device__ __forceinline__ float ld_as_float<float>(const float* p) { return *p; }
+template <>
+__device__ __forceinline__ float ld_as_float<__half>(const __half* p) { return __half2float(*p); }
+
+// LayerNorm: nn.LayerNorm semantics (biased variance, eps inside the sqrt), modeling_bert_new.py:150-153.
+template <typename T>
+__global__ void __launch_bounds__(256) layernorm_kernel(const T* __restrict__ x, long ldx, const float* __restrict__ gamma,
+                                                        const float* __restrict__ beta, float eps, long rows, int D,
+                                                        __half* __restrict__ out16, float* __restrict__ out32, long ldo,
+                                                        long zero_row_period) {
+  const long row = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const bool zero_row = zero_row_period > 0 && (row % zero_row_period) == zero_row_period - 1;
+  const T* xr = x + row * ldx;
+  float mean = 0.f, rstd;
+  if (zero_row) {
+    rstd = rsqrtf(eps);
+  } else {
+    float s = 0.f;
+    for (int i = lane; i < D; i += 32) s += ld_as_float(xr + i);
+    mean = warp_sum(s) / D;
+    float v = 0.f;
+    for (int i = lane; i < D; i += 32) {
+      float d = ld_as_float(xr + i) - mean;
+      v += d * d;
+    }
+    rstd = rsqrtf(warp_sum(v) / D + eps);
+  }
+  for (int i = lane; i < D; i += 32) {
+    float xv = zero_row ? 0.f : ld_as_float(xr + i);
+    float y = (xv - mean) * rstd * gamma[i] + beta[i];
+    if (out16) out16[row * ldo + i] = __float2half_rn(y);
+    if (out32) out32[row * ldo + i] = y;
+  }
+}
+
+// y = LN(a + b) (BertSelfOutput / BertOutput, rpn/modeling_bert.py:175-188,258-270), optional clamp of the sum and result.
+__global__ void __launch_bounds__(256) add_layernorm_kernel(const float* __restrict__ a, const float* __restrict__ b,
+                                                            const float* __restrict__ gamma,
+                                                            const float* __restrict__ beta, float eps, long rows, int D,
+                                                            float* __restrict__ out32, __half* __restrict__ out16,
+                                                            float clampv) {
+  const long row = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const float* ar = a + row * D;
+  const float* br = b + row * D;
+  float s = 0.f;
+  for (int i = lane; i < D; i += 32) s += ar[i] + br[i];
+  const float mean = warp_sum(s) / D;
+  float v = 0.f;
+  for (int i = lane; i < D; i += 32) {
+    float d = ar[i] + br[i] - mean;
+    v += d * d;
+  }
+  const float rstd = rsqrtf(warp_sum(v) / D + eps);
+  for (int i = lane; i < D; i += 32) {
+    float y = (ar[i] + br[i] - mean) * rstd * gamma[i] + beta[i];
+    if (clampv > 0.f) y = fminf(fmaxf(y, -clampv), clampv);
+    if (out32) out32[row * D + i] = y;
+    if (out16) out16[row * D + i] = __float2half_rn(y);
+  }
+}
+
+// Masked row softmax, warp per row. x fp16 or fp32 -> y fp16. Columns [n, n_pad) are written as 0.
+template <typename T>
+__global__ void __launch_bounds__(256) softmax_rows_kernel(const T* __restrict__ x, long ldx, __half* __restrict__ y, long ldy,
+                                                           long rows, int n, int n_pad, float scale,
+                                                           const float* __restrict__ colmask, long rows_per_batch,
+                                                           float mask_value, float keep_add) {
+  const long row = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const T* xr = x + row * ldx;
+  __half* yr = y + row * ldy;
+  const float* cm = colmask ? colmask + (row / rows_per_batch) * n : nullptr;
+  float mx = -INFINITY;
+  for (int i = lane; i < n; i += 32) {
+    float v = ld_as_float(xr + i) * scale;
+    if (cm) v += (cm[i] == 0.f) ? mask_value : keep_add;
+    mx = fmaxf(mx, v);
+  }
+  mx = warp_max(mx);
+  float sum = 0.f;
+  for (int i = lane; i < n; i += 32) {
+    float v = ld_as_float(xr + i) * scale;
+    if (cm) v += (cm[i] == 0.f) ? mask_value : keep_add;
+    sum += expf(v - mx);
+  }
+  sum = warp_sum(sum);
+  const float inv = 1.f / sum;
+  for (int i = lane; i < n_pad; i += 32) {
+    float o = 0.f;
+    if (i < n) {
+      float v = ld_as_float(xr + i) * scale;
+      if (cm) v += (cm[i] == 0.f) ? mask_value : keep_add;
+      o = expf(v - mx) * inv;
+    }
+    yr[i] = __float2half_rn(o);
+  }
+}
+
+__global__ void cast_f32_f16_kernel(const float* __restrict__ x, __half* __restrict__ y, long n) {
+  long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long stride = (long)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) y[i] = __float2half_rn(x[i]);
+}
+__global__ void cast_f16_f32_kernel(const __half* __restrict__ x, float* __restrict__ y, long n) {
+  long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long stride = (long)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) y[i] = __half2float(x[i]);
+}
+
+}  // namespace mqdet
+
+using namespace mqdet;
+
+extern "C" int mqdet_layernorm(const void* x, int in_dtype, int64_t ldx, const float* gamma, const float* beta, float eps,
+                               int64_t rows, int64_t D, void* out16, void* out32, int64_t ldo, int64_t zero_row_period,
+                               void* stream) {
+  MQ_REQUIRE(x && gamma && beta && (out16 || out32), "layernorm: null pointer");
+  MQ_REQUIRE(rows > 0 && D > 0, "layernorm: empty");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int wpb = 8;
+  dim3 grid(cdiv(rows, wpb));
+  if (in_dtype == MQDET_F32)
+    layernorm_kernel<float><<<grid, wpb * 32, 0, st>>>((const float*)x, ldx, gamma, beta, eps, rows, (int)D,
+                                                      (__half*)out16, (float*)out32, ldo, zero_row_period);
+  else
+    layernorm_kernel<__half><<<grid, wpb * 32, 0, st>>>((const __half*)x, ldx, gamma, beta, eps, rows, (int)D,
+                                                       (__half*)out16, (float*)out32, ldo, zero_row_period);
+  return check_launch("layernorm_kernel");
+}
+
+extern "C" int mqdet_add_layernorm(const float* a, const float* b, const float* gamma, const float* beta, float eps,
+                                   int64_t rows, int64_t D, float* out32, void* out16, float clampv, void* stream) {
+  MQ_REQUIRE(a && b && gamma && beta && (out16 || out32), "add_layernorm: null pointer");
+  const int wpb = 8;
+  add_layernorm_kernel<<<cdiv(rows, wpb), wpb * 32, 0, (cudaStream_t)stream>>>(a, b, gamma, beta, eps, rows, (int)D, out32,
+                                                                             (__half*)out16, clampv);
+  return check_launch("add_layernorm_kernel");
+}
+
+extern "C" int mqdet_softmax_rows(const void* x, int in_dtype, int64_t ldx, void* y, int64_t ldy, int64_t rows, int64_t n,
+                                  int64_t n_pad, float scale, const float* colmask, int64_t rows_per_batch,
+                                  float mask_value, float keep_add, void* stream) {
+  MQ_REQUIRE(x && y && rows > 0 && n > 0 && n_pad >= n, "softmax_rows: bad args");
+  if (rows_per_batch <= 0) rows_per_batch = rows;
+  const int wpb = 8;
+  dim3 grid(cdiv(rows, wpb));
+  cudaStream_t st = (cudaStream_t)stream;
+  if (in_dtype == MQDET_F32)
+    softmax_rows_kernel<float><<<grid, wpb * 32, 0, st>>>((const float*)x, ldx, (__half*)y, ldy, rows, (int)n, (int)n_pad,
+                                                         scale, colmask, rows_per_batch, mask_value, keep_add);
+  else
+    softmax_rows_kernel<__half><<<grid, wpb * 32, 0, st>>>((const __half*)x, ldx, (__half*)y, ldy, rows, (int)n,
+                                                          (int)n_pad, scale, colmask, rows_per_batch, mask_value,
+                                                          keep_add);
+  return check_launch("softmax_rows_kernel");
+}
+
+extern "C" int mqdet_cast_f32_f16(const float* x, void* y, int64_t n, void* stream) {
+  MQ_REQUIRE(x && y && n > 0, "cast: bad args");
+  int blocks = (int)((n + 255) / 256);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  cast_f32_f16_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(x, (__half*)y, n);
+  return check_launch("cast_f32_f16_kernel");
+}
+extern "C" int mqdet_cast_f16_f32(const void* x, float* y, int64_t n, void* stream) {
+  MQ_REQUIRE(x && y && n > 0, "cast: bad args");
+  int blocks = (int)((n + 255) / 256);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  cast_f16_f32_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>((const __half*)x, y, n);
+  return check_launch("cast_f16_f32_kernel");
+}

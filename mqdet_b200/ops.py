@@ -1,0 +1,265 @@
+"""Tensor-level wrappers over the C ABI (device pointers + sizes + current CUDA stream).
+
+PyTorch is used for memory, streams and views only; every arithmetic op below is a kernel of
+libmqdet_b200.so.  All wrappers launch on ``torch.cuda.current_stream()`` and never synchronise.
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+from ._lib import (ACT_GELU, ACT_NONE, ACT_RELU, F16, F32, IMPL_SIMT, IMPL_TCGEN05, VEC_NONE, VEC_PER_COL,
+                   VEC_PER_ROW, VEC_SCALAR, GemmArgs, check, load)
+
+# tests flip this to IMPL_SIMT to cross-check the tensor-core kernel against the plain FMA kernel
+DEFAULT_GEMM_IMPL = IMPL_TCGEN05
+
+# number of kernels launched through this module since the last reset (bench.py's gpu_launches)
+launch_count = 0
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
+
+
+def _dt(t):
+    if t.dtype == torch.float16:
+        return F16
+    if t.dtype == torch.float32:
+        return F32
+    raise TypeError(f"unsupported dtype {t.dtype}")
+
+
+def _need_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise _lib.MqdetError("mqdet_b200 ops require CUDA tensors (no CPU fallback)")
+
+
+def _as4(t):
+    """View a [..., rows, cols] tensor as (nb2, nb1, rows, cols) without copying."""
+    if t.dim() < 2 or t.dim() > 4:
+        raise ValueError(f"expected 2-4 dims, got {tuple(t.shape)}")
+    while t.dim() < 4:
+        t = t.unsqueeze(0)
+    if t.stride(-1) != 1 and t.shape[-1] != 1:
+        raise ValueError("last dimension must be contiguous")
+    return t
+
+
+def gemm(a, b, out=None, *, out_dtype=torch.float16, alpha=1.0, bias=None, bias_mode=VEC_PER_COL,
+         scale_after_bias=False, act=ACT_NONE, clamp=0.0, gate=None, gate_mode=VEC_NONE, gate_tanh=False,
+         residual=None, impl=None):
+    """out[..., m, n] = epilogue(sum_k a[..., m, k] * b[..., n, k]); fp16 operands, fp32 accumulation.
+
+    ``a``: [(nb2, (nb1,)) M, K] fp16, ``b``: [(nb2, (nb1,)) N, K] fp16 (an nn.Linear weight as is); arbitrary
+    strides on all but the last dim; size-1 batch dims of ``b``/``a`` broadcast.  See mqdet_gemm_f16 in
+    include/mqdet_b200.h for the epilogue order.
+    """
+    global launch_count
+    _need_cuda(a, b, out, bias, gate, residual)
+    if a.dtype != torch.float16 or b.dtype != torch.float16:
+        raise TypeError("gemm operands must be fp16")
+    a4, b4 = _as4(a), _as4(b)
+    nb2 = max(a4.shape[0], b4.shape[0])
+    nb1 = max(a4.shape[1], b4.shape[1])
+    M, K = a4.shape[2], a4.shape[3]
+    N = b4.shape[2]
+    if b4.shape[3] != K:
+        raise ValueError(f"K mismatch: a {tuple(a.shape)} vs b {tuple(b.shape)}")
+    if out is None:
+        out = torch.empty(torch.broadcast_shapes(a.shape[:-2], b.shape[:-2]) + (M, N), dtype=out_dtype, device=a.device)
+    o4 = _as4(out)
+    if o4.shape[2] != M or o4.shape[3] != N:
+        raise ValueError(f"out shape {tuple(out.shape)} does not match M={M} N={N}")
+
+    def bstride(t4, dim, n):
+        return 0 if (t4.shape[dim] == 1 and n > 1) else (t4.stride(dim) if t4.shape[dim] > 1 else 0)
+
+    g = GemmArgs()
+    g.A, g.B = a4.data_ptr(), b4.data_ptr()
+    g.M, g.N, g.K = M, N, K
+    g.lda, g.ldb = a4.stride(2), b4.stride(2)
+    g.nb1, g.nb2 = nb1, nb2
+    g.a_b1, g.a_b2 = bstride(a4, 1, nb1), bstride(a4, 0, nb2)
+    g.b_b1, g.b_b2 = bstride(b4, 1, nb1), bstride(b4, 0, nb2)
+    g.C, g.c_dtype = o4.data_ptr(), _dt(out)
+    g.ldc, g.c_b1, g.c_b2 = o4.stride(2), bstride(o4, 1, nb1), bstride(o4, 0, nb2)
+    g.alpha, g.scale_after_bias = float(alpha), int(bool(scale_after_bias))
+    if bias is not None:
+        if bias.dtype != torch.float32:
+            raise TypeError("bias must be fp32")
+        g.bias, g.bias_mode = bias.data_ptr(), bias_mode
+        if bias.dim() == 3:  # [nb2, nb1, n]
+            g.bias_b1, g.bias_b2 = bstride(bias, 1, nb1), bstride(bias, 0, nb2)
+        elif bias.dim() == 2:  # [nb1, n] (the innermost batch dim, like 3-D operands)
+            g.bias_b1, g.bias_b2 = bstride(bias, 0, nb1), 0
+    g.act, g.clamp = act, float(clamp)
+    if gate is not None:
+        if gate.dtype != torch.float32:
+            raise TypeError("gate must be fp32")
+        g.gate, g.gate_mode, g.gate_tanh = gate.data_ptr(), gate_mode, int(bool(gate_tanh))
+    if residual is not None:
+        r4 = _as4(residual)
+        g.R, g.r_dtype = r4.data_ptr(), _dt(residual)
+        g.ldr, g.r_b1, g.r_b2 = r4.stride(2), bstride(r4, 1, nb1), bstride(r4, 0, nb2)
+    check(load().mqdet_gemm_f16(ctypes.byref(g), DEFAULT_GEMM_IMPL if impl is None else impl, _stream()), "gemm")
+    launch_count += 1
+    return out
+
+
+def layernorm(x, gamma, beta, eps=1e-5, *, out16=True, out32=False, zero_row_period=0):
+    """nn.LayerNorm over the last dim of a contiguous [..., D] fp16/fp32 tensor -> (fp16, fp32) outputs."""
+    global launch_count
+    _need_cuda(x, gamma, beta)
+    D = x.shape[-1]
+    x2 = x.reshape(-1, D)
+    rows = x2.shape[0]
+    o16 = torch.empty(x.shape, dtype=torch.float16, device=x.device) if out16 else None
+    o32 = torch.empty(x.shape, dtype=torch.float32, device=x.device) if out32 else None
+    check(load().mqdet_layernorm(_ptr(x2), _dt(x2), x2.stride(0), _ptr(gamma), _ptr(beta), float(eps), rows, D,
+                                 _ptr(o16), _ptr(o32), D, int(zero_row_period), _stream()), "layernorm")
+    launch_count += 1
+    if out16 and out32:
+        return o16, o32
+    return o16 if out16 else o32
+
+
+def add_layernorm(a, b, gamma, beta, eps, *, out16=True, out32=True, clamp=0.0):
+    """LN(a + b) over the last dim; a, b contiguous fp32."""
+    global launch_count
+    _need_cuda(a, b)
+    D = a.shape[-1]
+    rows = a.numel() // D
+    o16 = torch.empty(a.shape, dtype=torch.float16, device=a.device) if out16 else None
+    o32 = torch.empty(a.shape, dtype=torch.float32, device=a.device) if out32 else None
+    check(load().mqdet_add_layernorm(_ptr(a), _ptr(b), _ptr(gamma), _ptr(beta), float(eps), rows, D, _ptr(o32),
+                                     _ptr(o16), float(clamp), _stream()), "add_layernorm")
+    launch_count += 1
+    return o16, o32
+
+
+def softmax_rows(x, *, n=None, scale=1.0, colmask=None, rows_per_batch=0, mask_value=0.0, keep_add=0.0, out=None):
+    """Row softmax over the last dim of x [..., n_pad] (fp16/fp32, contiguous) -> fp16; cols >= n are zeroed."""
+    global launch_count
+    _need_cuda(x, colmask)
+    n_pad = x.shape[-1]
+    n = n_pad if n is None else n
+    rows = x.numel() // n_pad
+    if out is None:
+        out = torch.empty(x.shape, dtype=torch.float16, device=x.device)
+    check(load().mqdet_softmax_rows(_ptr(x), _dt(x), n_pad, _ptr(out), n_pad, rows, n, n_pad, float(scale),
+                                    _ptr(colmask), int(rows_per_batch), float(mask_value), float(keep_add),
+                                    _stream()), "softmax_rows")
+    launch_count += 1
+    return out
+
+
+def cast_f16(x):
+    global launch_count
+    _need_cuda(x)
+    if x.dtype == torch.float16:
+        return x
+    x = x.contiguous()
+    y = torch.empty(x.shape, dtype=torch.float16, device=x.device)
+    check(load().mqdet_cast_f32_f16(_ptr(x), _ptr(y), x.numel(), _stream()), "cast_f32_f16")
+    launch_count += 1
+    return y
+
+
+def cast_f32(x):
+    global launch_count
+    _need_cuda(x)
+    if x.dtype == torch.float32:
+        return x
+    x = x.contiguous()
+    y = torch.empty(x.shape, dtype=torch.float32, device=x.device)
+    check(load().mqdet_cast_f16_f32(_ptr(x), _ptr(y), x.numel(), _stream()), "cast_f16_f32")
+    launch_count += 1
+    return y
+
+
+def gcp_build_index(mask, S):
+    """mask [B, V, T] fp32 0/1 -> (idx int32 [B, T, S] padded with V, counts int32 [B, T])."""
+    global launch_count
+    _need_cuda(mask)
+    B, V, T = mask.shape
+    mask = mask.contiguous().float()
+    idx = torch.empty((B, T, S), dtype=torch.int32, device=mask.device)
+    counts = torch.empty((B, T), dtype=torch.int32, device=mask.device)
+    check(load().mqdet_gcp_build_index(_ptr(mask), B, V, T, S, _ptr(idx), _ptr(counts), _stream()), "gcp_build_index")
+    launch_count += 1
+    return idx, counts
+
+
+def gcp_sparse_attn(q, kv, idx, heads, dim_head):
+    """q [B, T, H*Dh] fp16 (scaled), kv [B, V+1, 2*H*Dh] fp16, idx [B, T, S] int32 -> [B, T, H*Dh] fp16."""
+    global launch_count
+    _need_cuda(q, kv, idx)
+    B, T, inner = q.shape
+    V = kv.shape[1] - 1
+    S = idx.shape[2]
+    out = torch.empty_like(q)
+    check(load().mqdet_gcp_sparse_attn(_ptr(q), _ptr(kv), _ptr(idx), _ptr(out), B, T, V, S, heads, dim_head, _stream()),
+          "gcp_sparse_attn")
+    launch_count += 1
+    return out
+
+
+def gcp_gate_residual_ln(h1, w2, s, x, gamma, beta, eps=1e-5, want_gate=False):
+    """g = tanh(h1 . w2); x1 = s*g + x; returns (x1 fp32, LN(x1) fp16[, g])."""
+    global launch_count
+    _need_cuda(h1, w2, s, x)
+    D = s.shape[-1]
+    rows = s.numel() // D
+    Dg = h1.shape[-1]
+    x1 = torch.empty_like(s)
+    ln = torch.empty(s.shape, dtype=torch.float16, device=s.device)
+    g = torch.empty(s.shape[:-1], dtype=torch.float32, device=s.device) if want_gate else None
+    check(load().mqdet_gcp_gate_residual_ln(_ptr(h1), _ptr(w2), Dg, _ptr(s), _ptr(x), _ptr(gamma), _ptr(beta), float(eps),
+                                            rows, D, _ptr(x1), _ptr(ln), _ptr(g), _stream()), "gcp_gate_residual_ln")
+    launch_count += 1
+    return (x1, ln, g) if want_gate else (x1, ln)
+
+
+def argsort_desc(scores):
+    global launch_count
+    _need_cuda(scores)
+    n = scores.numel()
+    order = torch.empty((n,), dtype=torch.int64, device=scores.device)
+    if n:
+        check(load().mqdet_argsort_desc(_ptr(scores), n, _ptr(order), _stream()), "argsort_desc")
+        launch_count += 1
+    return order
+
+
+def ml_nms_device(boxes, scores, labels, thresh, max_det=0):
+    """Device-resident multi-label NMS. Returns (keep int64 [n] (first num valid, ascending), num int32 [1])."""
+    global launch_count
+    _need_cuda(boxes, scores, labels)
+    n = boxes.shape[0]
+    keep = torch.empty((max(n, 1),), dtype=torch.int64, device=boxes.device)
+    num = torch.zeros((1,), dtype=torch.int32, device=boxes.device)
+    if n == 0:
+        return keep[:0], num
+    boxes = boxes.contiguous().float()
+    scores = scores.contiguous().float()
+    labels = labels.contiguous().float()
+    order = argsort_desc(scores)
+    ws = torch.empty((int(load().mqdet_ml_nms_workspace_bytes(n)),), dtype=torch.uint8, device=boxes.device)
+    check(load().mqdet_ml_nms(_ptr(boxes), _ptr(scores), _ptr(labels), _ptr(order), n, float(thresh), int(max_det),
+                              _ptr(keep), _ptr(num), _ptr(ws), _stream()), "ml_nms")
+    launch_count += 5
+    return keep, num
+
+
+def ml_nms(boxes, scores, labels, thresh):
+    """Drop-in for maskrcnn_benchmark._C.ml_nms (csrc/ml_nms.h:11-27): kept original indices, ascending."""
+    if boxes.numel() == 0:
+        return torch.empty((0,), dtype=torch.int64, device="cpu")  # reference returns an empty CPU tensor (:19-20)
+    keep, num = ml_nms_device(boxes, scores, labels, thresh)
+    return keep[: int(num.item())]

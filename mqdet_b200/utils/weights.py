@@ -1,0 +1,38 @@
+"""fp16 operand cache for module parameters.
+
+Parameters stay fp32 nn.Parameters under the reference's names (state_dict compatible); the tensor-core GEMMs read
+fp16 copies that are (re)built lazily whenever the parameter's storage or version counter changes.
+"""
+import torch
+
+from .. import ops
+
+_cache = {}
+
+
+def w16(param, rows=None):
+    """fp16, contiguous copy of ``param`` (optionally a row slice ``rows=(lo, hi)``), cached per parameter version."""
+    key = (id(param), rows)
+    ent = _cache.get(key)
+    ver = (param.data_ptr(), param._version, param.device)
+    if ent is not None and ent[0] == ver:
+        return ent[1]
+    src = param.detach()
+    if rows is not None:
+        src = src[rows[0]:rows[1]]
+    if src.dtype == torch.float16:
+        h = src.contiguous()
+    else:
+        h = ops.cast_f16(src.float().contiguous())
+    _cache[key] = (ver, h)
+    return h
+
+
+def f32(param):
+    """fp32 contiguous view of a parameter (LayerNorm affine, biases, gates)."""
+    t = param.detach()
+    return t if (t.dtype == torch.float32 and t.is_contiguous()) else t.float().contiguous()
+
+
+def clear():
+    _cache.clear()

@@ -1,0 +1,151 @@
+"""TEST INFRASTRUCTURE ONLY — generates tests/golden/*.pt by running the REFERENCE's own modules (unmodified, loaded
+from /root/reference by oracle/ref_loader.py) on seeded synthetic weights/inputs (oracle/synth.py).
+
+    python -m oracle.make_golden            # in the build container (needs /root/reference)
+
+Each fixture stores the case description (seed, sizes) and a strided SUBSAMPLE of the reference output (full tensors
+would be MBs); weights/inputs are regenerated from the seed by ``case_inputs`` below, which the tests import too.
+"""
+import os
+import sys
+import types
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+from oracle import synth  # noqa: E402
+
+GOLDEN_DIR = os.path.join(ROOT, "tests", "golden")
+
+
+def ref_cfg():
+    vq = types.SimpleNamespace(ENABLED=True, FIX_ATTN_GATE=-1.0, CONDITION_GATE=True, NONLINEAR_GATE=True, NO_CAT=True,
+                               ADD_ADAPT_LAYER=False, RETURN_ATTN_GATE_VALUE=False, VISION_SCALE=1.0,
+                               AUGMENT_IMAGE_WITH_QUERY=False, TEXT_DROPOUT=0.4, NEW_MASK_TOKEN=False, QUERY_FUSION=False,
+                               SHARE_KV=False, NUM_QUERY_PER_CLASS=5)
+    fuse = types.SimpleNamespace(STABLE_SOFTMAX_2D=False, CLAMP_MIN_FOR_UNDERFLOW=True, CLAMP_MAX_FOR_OVERFLOW=True,
+                                 SEPARATE_BIDIRECTIONAL=False, DO_LANG_PROJ_OUTSIDE_CHECKPOINT=False)
+    model = types.SimpleNamespace(DYHEAD=types.SimpleNamespace(FUSE_CONFIG=fuse, NUM_CONVS=6))
+    return types.SimpleNamespace(VISION_QUERY=vq, MODEL=model)
+
+
+LEVELS_SMALL = [(20, 28), (10, 14), (5, 7), (3, 4), (2, 2)]  # a 160x224 "image" through strides 8..128
+
+
+def sub(t, *steps):
+    """strided subsample along the trailing dims"""
+    idx = [slice(None)] * (t.dim() - len(steps)) + [slice(None, None, s) for s in steps]
+    return t[tuple(idx)].contiguous().clone()
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# case inputs (shared with the tests)
+# ----------------------------------------------------------------------------------------------------------------------
+def case_inputs(name):
+    if name == "gcp_block":
+        gen = synth.Gen(1234)
+        sd = synth.gcp_block_sd(gen)
+        _, _, pmap = synth.prompt(10, 2, 256, gen)
+        _, m = synth.vision_queries(pmap, 5, 256, 768, gen)
+        B = 2
+        mask = m.expand(B, -1, -1).clone()
+        mask[0, 3] = 0
+        mask[0, 7:10] = 0
+        mask[1, 20:25] = 0
+        vision = gen.randn(B, 50, 768)
+        x = gen.randn(B, 256, 768)
+        return dict(sd=sd, x=x, vision=vision, mask=mask)
+    if name == "preselect":
+        gen = synth.Gen(1235)
+        sd = synth.preselect_sd(gen)
+        return dict(sd=sd, vision=gen.randn(2, 50, 256, scale=0.5), image=gen.randn(2, 1117, 256))
+    if name == "bi_attention":
+        gen = synth.Gen(1236)
+        sd = synth.bi_attention_sd(gen)
+        B, T = 2, 256
+        feats = [gen.randn(B, 256, h, w) for (h, w) in LEVELS_SMALL]
+        l = gen.randn(B, T, 768)
+        mask = torch.ones(B, T, dtype=torch.long)
+        mask[0, 100:] = 0
+        mask[1, 33:] = 0
+        return dict(sd=sd, feats=feats, l=l, mask=mask)
+    if name == "bert_layer":
+        gen = synth.Gen(1237)
+        sd = synth.bert_layer_sd(gen, "")
+        B, T = 2, 256
+        h = gen.randn(B, T, 768)
+        am = torch.ones(B, T)
+        am[0, 200:] = 0
+        am[1, 33:] = 0
+        return dict(sd=sd, h=h, am=am)
+    raise KeyError(name)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# reference runs
+# ----------------------------------------------------------------------------------------------------------------------
+@torch.no_grad()
+def run_reference(name):
+    from oracle import ref_loader as rl
+    c = case_inputs(name)
+    cfg = ref_cfg()
+    if name == "gcp_block":
+        m = rl.modeling_bert_new()
+        blk = m.GatedCrossAttentionBlock(dim=768, cfg=cfg).eval()
+        blk.load_state_dict(c["sd"], strict=True)
+        y = blk(c["x"], c["vision"], c["mask"])
+        s = blk.attn(c["x"], c["vision"], c["mask"])
+        return dict(y=y, s=s)
+    if name == "preselect":
+        m = rl.modeling_bert_new()
+        mod = m.PreSelectModule(dim=256, out_dim=768, cfg=cfg).eval()
+        mod.load_state_dict(c["sd"], strict=True)
+        return dict(vision=mod(c["vision"], c["image"])["vision"])
+    if name == "bi_attention":
+        fh = rl.fuse_helper()
+        blk = fh.BiAttentionBlockForCheckpoint(v_dim=256, l_dim=768, embed_dim=2048, num_heads=8, hidden_dim=3072,
+                                               dropout=0.1, drop_path=0.0, init_values=1.0 / 6, cfg=cfg).eval()
+        blk.load_state_dict(c["sd"], strict=True)
+        out = blk(*c["feats"], c["l"], c["mask"], None)
+        v = torch.cat([o.flatten(2).transpose(1, 2) for o in out[:5]], dim=1)  # [B,N,256], P3->P7 row-major
+        return dict(v=v, l=out[5])
+    if name == "bert_layer":
+        rb = rl.rpn_modeling_bert()
+        from transformers import BertConfig
+        config = BertConfig()
+        att = rb.BertAttention(config, True, True).eval()
+        inter = rb.BertIntermediate(config).eval()
+        outp = rb.BertOutput(config).eval()
+        sd = c["sd"]
+        att.load_state_dict({k[len("attention."):]: v for k, v in sd.items() if k.startswith("attention.")}, strict=True)
+        inter.load_state_dict({k[len("intermediate."):]: v for k, v in sd.items() if k.startswith("intermediate.")}, strict=True)
+        outp.load_state_dict({k[len("output."):]: v for k, v in sd.items() if k.startswith("output.")}, strict=True)
+        ext = (1.0 - c["am"][:, None, None, :]) * -10000.0
+        # wiring of BertEncoderLayer.forward (maskrcnn_benchmark/modeling/rpn/vldyhead.py:264-301)
+        a = att(c["h"], ext, None, output_attentions=False, past_key_value=None)[0]
+        return dict(h=outp(inter(a), a))
+    raise KeyError(name)
+
+
+SUBSAMPLE = {"gcp_block": {"y": (4, 8), "s": (4, 8)}, "preselect": {"vision": (1, 8)},
+             "bi_attention": {"v": (3, 4), "l": (4, 8)}, "bert_layer": {"h": (4, 8)}}
+
+
+def main():
+    os.makedirs(GOLDEN_DIR, exist_ok=True)
+    for name, subs in SUBSAMPLE.items():
+        out = run_reference(name)
+        fx = {"case": name, "subsample": subs, "torch": str(torch.__version__)}
+        for k, steps in subs.items():
+            fx[k] = sub(out[k].float(), *steps)
+            fx[k + "_absmax"] = out[k].abs().max().item()
+        path = os.path.join(GOLDEN_DIR, f"{name}.pt")
+        torch.save(fx, path)
+        print(name, {k: tuple(fx[k].shape) for k in subs}, os.path.getsize(path), "bytes")
+
+
+if __name__ == "__main__":
+    main()

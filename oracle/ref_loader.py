@@ -1,0 +1,137 @@
+"""TEST INFRASTRUCTURE ONLY — loads the reference's own hot-path modules from /root/reference, unmodified.
+
+Used by oracle/make_golden.py (to generate tests/golden/*.pt) and by tests/test_oracle_pinning.py (to pin the
+restatement in oracle/restate.py).  /root/reference exists only in the build container, never on the GPU box,
+so nothing under ``-m gpu``, ``smoke()`` or ``bench.py`` may import this file.
+
+The reference package cannot be imported as a package here (yacs / timm / einops_exts / maskrcnn_benchmark._C are
+absent), so individual files are loaded with importlib after installing small shims:
+  * ``einops_exts.rearrange_many``                      (pure reshape helper)
+  * five doc-decorator names the file imports from ``transformers.models.bert.modeling_bert`` (gone in HF 5.x)
+  * a stub ``maskrcnn_benchmark`` package exposing ``utils.torch_dropout`` (the real file) and ``modeling.utils``
+  * ``timm.models.layers.DropPath`` (identity at eval), ``to_2tuple``, ``trunc_normal_``
+No reference source is copied into this repository.
+"""
+import importlib.util
+import os
+import sys
+import types
+
+REF = os.environ.get("MQDET_REFERENCE", "/root/reference")
+
+
+def available():
+    return os.path.isdir(os.path.join(REF, "maskrcnn_benchmark"))
+
+
+def _load_file(mod_name, rel_path):
+    path = os.path.join(REF, rel_path)
+    spec = importlib.util.spec_from_file_location(mod_name, path)
+    mod = importlib.util.module_from_spec(spec)
+    sys.modules[mod_name] = mod
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def _install_shims():
+    import torch
+    from einops import rearrange
+
+    if "einops_exts" not in sys.modules:
+        m = types.ModuleType("einops_exts")
+        m.rearrange_many = lambda tensors, pattern, **kw: tuple(rearrange(t, pattern, **kw) for t in tensors)
+        sys.modules["einops_exts"] = m
+
+    import transformers.models.bert.modeling_bert as hf_bert
+
+    def _passthrough(*a, **k):
+        def deco(fn):
+            return fn
+        return deco
+
+    for name, val in [("add_start_docstrings_to_model_forward", _passthrough), ("add_code_sample_docstrings", _passthrough),
+                      ("BERT_INPUTS_DOCSTRING", "{}"), ("_CHECKPOINT_FOR_DOC", ""), ("_CONFIG_FOR_DOC", "")]:
+        if not hasattr(hf_bert, name):
+            setattr(hf_bert, name, val)
+    for name in ("BaseModelOutputWithPastAndCrossAttentions", "BaseModelOutputWithPoolingAndCrossAttentions"):
+        if not hasattr(hf_bert, name):
+            import transformers.modeling_outputs as mo
+            setattr(hf_bert, name, getattr(mo, name))
+    if not hasattr(hf_bert, "logger"):
+        import logging
+        hf_bert.logger = logging.getLogger("hf_bert")
+
+    if "timm" not in sys.modules:
+        timm = types.ModuleType("timm")
+        models = types.ModuleType("timm.models")
+        layers = types.ModuleType("timm.models.layers")
+
+        class DropPath(torch.nn.Module):
+            def __init__(self, p=0.0):
+                super().__init__()
+                self.p = p
+
+            def forward(self, x):
+                return x
+
+        layers.DropPath = DropPath
+        layers.to_2tuple = lambda x: x if isinstance(x, tuple) else (x, x)
+        layers.trunc_normal_ = torch.nn.init.trunc_normal_
+        timm.models = models
+        models.layers = layers
+        sys.modules.update({"timm": timm, "timm.models": models, "timm.models.layers": layers})
+
+    if "maskrcnn_benchmark" not in sys.modules:
+        pkg = types.ModuleType("maskrcnn_benchmark")
+        pkg.__path__ = []
+        utils = types.ModuleType("maskrcnn_benchmark.utils")
+        utils.__path__ = []
+        modeling = types.ModuleType("maskrcnn_benchmark.modeling")
+        modeling.__path__ = []
+        sys.modules.update({"maskrcnn_benchmark": pkg, "maskrcnn_benchmark.utils": utils,
+                            "maskrcnn_benchmark.modeling": modeling})
+        pkg.utils, pkg.modeling = utils, modeling
+        utils.torch_dropout = _load_file("maskrcnn_benchmark.utils.torch_dropout",
+                                         "maskrcnn_benchmark/utils/torch_dropout.py")
+        modeling.utils = _load_file("maskrcnn_benchmark.modeling.utils", "maskrcnn_benchmark/modeling/utils.py")
+
+
+_cache = {}
+
+
+def modeling_bert_new():
+    """maskrcnn_benchmark/modeling/language_backbone/modeling_bert_new.py (GCP, PreSelect, QVBert*)."""
+    if "mbn" not in _cache:
+        _install_shims()
+        _cache["mbn"] = _load_file("ref_modeling_bert_new",
+                                   "maskrcnn_benchmark/modeling/language_backbone/modeling_bert_new.py")
+    return _cache["mbn"]
+
+
+def fuse_helper():
+    """maskrcnn_benchmark/utils/fuse_helper.py (BiMultiHeadAttention, BiAttentionBlockForCheckpoint)."""
+    if "fh" not in _cache:
+        _install_shims()
+        _cache["fh"] = _load_file("ref_fuse_helper", "maskrcnn_benchmark/utils/fuse_helper.py")
+    return _cache["fh"]
+
+
+def rpn_modeling_bert():
+    """maskrcnn_benchmark/modeling/rpn/modeling_bert.py (BertAttention/Intermediate/Output with clamps)."""
+    if "rmb" not in _cache:
+        _install_shims()
+        import transformers.modeling_utils as mu
+        import transformers.pytorch_utils as pu
+        for name in ("find_pruneable_heads_and_indices", "prune_linear_layer", "apply_chunking_to_forward"):
+            if not hasattr(mu, name):
+                setattr(mu, name, getattr(pu, name, lambda *a, **k: None))
+        _cache["rmb"] = _load_file("ref_rpn_modeling_bert", "maskrcnn_benchmark/modeling/rpn/modeling_bert.py")
+    return _cache["rmb"]
+
+
+def swint():
+    """maskrcnn_benchmark/modeling/backbone/swint.py (WindowAttention, SwinTransformerBlock, ...)."""
+    if "swint" not in _cache:
+        _install_shims()
+        _cache["swint"] = _load_file("ref_swint", "maskrcnn_benchmark/modeling/backbone/swint.py")
+    return _cache["swint"]

@@ -1,0 +1,164 @@
+"""TEST INFRASTRUCTURE ONLY — deterministic synthetic weights and inputs.
+
+No checkpoints, tokenizer vocabularies or datasets exist offline, so every test/bench input is generated from a
+seeded ``torch.Generator`` on the CPU.  Weight dicts use the reference's ``state_dict`` key names so they load into
+the unmodified reference modules (pinning) as well as into mqdet_b200's drop-in modules.
+Gates are initialised NON-zero (the reference initialises them to 0, which would make GCP parity vacuous:
+modeling_bert_new.py:274,289).
+"""
+import math
+
+import torch
+
+
+class Gen:
+    def __init__(self, seed):
+        self.g = torch.Generator().manual_seed(seed)
+
+    def linear(self, out_f, in_f, bias=False, sd=None, name=None, bias_scale=0.02):
+        bound = 1.0 / math.sqrt(in_f)
+        w = (torch.rand(out_f, in_f, generator=self.g) * 2 - 1) * bound
+        sd[name + ".weight"] = w
+        if bias:
+            sd[name + ".bias"] = torch.randn(out_f, generator=self.g) * bias_scale
+
+    def xavier(self, out_f, in_f, sd, name, bias_scale=0.02):
+        bound = math.sqrt(6.0 / (in_f + out_f))
+        sd[name + ".weight"] = (torch.rand(out_f, in_f, generator=self.g) * 2 - 1) * bound
+        sd[name + ".bias"] = torch.randn(out_f, generator=self.g) * bias_scale
+
+    def norm(self, dim, sd, name):
+        sd[name + ".weight"] = 1.0 + 0.1 * torch.randn(dim, generator=self.g)
+        sd[name + ".bias"] = 0.1 * torch.randn(dim, generator=self.g)
+
+    def randn(self, *shape, scale=1.0):
+        return torch.randn(*shape, generator=self.g) * scale
+
+
+def gcp_block_sd(gen, p="", dim=768, heads=8, dim_head=64, ff_mult=4, sd=None):
+    """GatedCrossAttentionBlock parameters (modeling_bert_new.py:256-296): 6 592 897 params at dim=768."""
+    sd = {} if sd is None else sd
+    inner = heads * dim_head
+    gen.norm(dim, sd, p + "attn.norm")
+    gen.norm(dim, sd, p + "attn.norm_kv")
+    gen.linear(inner, dim, sd=sd, name=p + "attn.to_q")
+    gen.linear(2 * inner, dim, sd=sd, name=p + "attn.to_kv")
+    gen.linear(dim, inner, sd=sd, name=p + "attn.to_out")
+    gen.norm(dim, sd, p + "attn_gate.norm")
+    gen.linear(dim // 2, dim, sd=sd, name=p + "attn_gate.linear1")
+    sd[p + "attn_gate.linear2.weight"] = gen.randn(1, dim // 2, scale=0.1)
+    gen.norm(dim, sd, p + "ff.norm")
+    gen.linear(dim * ff_mult, dim, sd=sd, name=p + "ff.linear1")
+    gen.linear(dim, dim * ff_mult, sd=sd, name=p + "ff.linear2")
+    sd[p + "ff_gate"] = torch.tensor([0.3])
+    return sd
+
+
+def preselect_sd(gen, p="", dim=256, out_dim=768, heads=8, dim_head=32, ff_mult=4, num_layers=2, sd=None):
+    """PreSelectModule parameters (modeling_bert_new.py:377-431)."""
+    sd = {} if sd is None else sd
+    inner = heads * dim_head
+    for i in range(num_layers):
+        od = out_dim if i == num_layers - 1 else dim
+        lp = f"{p}layers.{i}."
+        gen.norm(dim, sd, lp + "image_condition.norm")
+        gen.norm(dim, sd, lp + "image_condition.norm_kv")
+        gen.linear(inner, dim, sd=sd, name=lp + "image_condition.to_q")
+        gen.linear(2 * inner, dim, sd=sd, name=lp + "image_condition.to_kv")
+        gen.linear(od, inner, sd=sd, name=lp + "image_condition.to_out")
+        gen.norm(od, sd, lp + "ff.norm")
+        gen.linear(od * ff_mult, od, sd=sd, name=lp + "ff.linear1")
+        gen.linear(od, od * ff_mult, sd=sd, name=lp + "ff.linear2")
+        if od != dim:
+            gen.linear(od, dim, sd=sd, name=lp + "res_mapping")
+    return sd
+
+
+def bert_layer_sd(gen, p, dim=768, inter=3072, sd=None, std=0.02):
+    """One BERT layer, HF key names; normal(0, 0.02) like BertPreTrainedModel._init_weights, non-trivial LN/bias."""
+    sd = {} if sd is None else sd
+    for name, (o, i) in {"attention.self.query": (dim, dim), "attention.self.key": (dim, dim),
+                         "attention.self.value": (dim, dim), "attention.output.dense": (dim, dim),
+                         "intermediate.dense": (inter, dim), "output.dense": (dim, inter)}.items():
+        # 0.02 std gives near-uniform attention; use a livelier scale so softmax parity is meaningful
+        sd[p + name + ".weight"] = gen.randn(o, i, scale=std * 2.5)
+        sd[p + name + ".bias"] = gen.randn(o, scale=0.02)
+    gen.norm(dim, sd, p + "attention.output.LayerNorm")
+    gen.norm(dim, sd, p + "output.LayerNorm")
+    return sd
+
+
+def qvbert_sd(gen, vocab=30522, dim=768, layers=12, max_pos=512, start_qv=6):
+    """QVBertModel parameters (modeling_bert_new.py:642-660): BERT-base + 6 GCP blocks + PreSelect."""
+    sd = {}
+    sd["embeddings.word_embeddings.weight"] = gen.randn(vocab, dim, scale=0.05)
+    sd["embeddings.position_embeddings.weight"] = gen.randn(max_pos, dim, scale=0.05)
+    sd["embeddings.token_type_embeddings.weight"] = gen.randn(2, dim, scale=0.05)
+    gen.norm(dim, sd, "embeddings.LayerNorm")
+    for i in range(layers):
+        bert_layer_sd(gen, f"encoder.layer.{i}.", dim, 4 * dim, sd)
+    for i in range(layers - start_qv):
+        gcp_block_sd(gen, f"encoder.qv_layer.{i}.", dim, sd=sd)
+    preselect_sd(gen, "pre_select.", 256, dim, sd=sd)
+    return sd
+
+
+def bi_attention_sd(gen, p="", v_dim=256, l_dim=768, embed=2048, num_convs=6, sd=None):
+    """BiAttentionBlockForCheckpoint parameters (fuse_helper.py:345-375, xavier init :207-216, gamma=1/NUM_CONVS)."""
+    sd = {} if sd is None else sd
+    gen.norm(v_dim, sd, p + "layer_norm_v")
+    gen.norm(l_dim, sd, p + "layer_norm_l")
+    gen.xavier(embed, v_dim, sd, p + "attn.v_proj")
+    gen.xavier(embed, l_dim, sd, p + "attn.l_proj")
+    gen.xavier(embed, v_dim, sd, p + "attn.values_v_proj")
+    gen.xavier(embed, l_dim, sd, p + "attn.values_l_proj")
+    gen.xavier(v_dim, embed, sd, p + "attn.out_v_proj")
+    gen.xavier(l_dim, embed, sd, p + "attn.out_l_proj")
+    sd[p + "gamma_v"] = torch.full((v_dim,), 1.0 / num_convs) * (1 + 0.1 * gen.randn(v_dim))
+    sd[p + "gamma_l"] = torch.full((l_dim,), 1.0 / num_convs) * (1 + 0.1 * gen.randn(l_dim))
+    return sd
+
+
+def dot_head_sd(gen, p="", l_dim=768, channels=256, sd=None):
+    """dot_product_projection_text, bias_lang, bias0, log_scale (vldyhead.py:711-720)."""
+    sd = {} if sd is None else sd
+    gen.linear(channels, l_dim, bias=True, sd=sd, name=p + "dot_product_projection_text")
+    sd[p + "bias_lang"] = gen.randn(l_dim, scale=0.05)
+    sd[p + "bias0"] = torch.tensor([-math.log((1 - 0.01) / 0.01)])
+    sd[p + "log_scale"] = torch.tensor([0.0])
+    return sd
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# prompts / queries
+# ------------------------------------------------------------------------------------------------------------------
+def prompt(num_classes, tokens_per_class=2, T=256, gen=None, vocab_lo=1996, vocab_hi=29000):
+    """Synthetic tokenised caption "c1. c2. ..." (SURVEY.md §8d): [CLS]=101, class c -> tokens 1+3c..,
+    '.'=1012 separators, [SEP]=102, [PAD]=0.  Returns (input_ids [1,T], attention_mask [1,T], positive_map)."""
+    ids = torch.zeros(1, T, dtype=torch.long)
+    ids[0, 0] = 101
+    pos = 1
+    positive_map = {}
+    for c in range(num_classes):
+        toks = list(range(pos, pos + tokens_per_class))
+        positive_map[c + 1] = toks
+        ids[0, toks] = torch.randint(vocab_lo, vocab_hi, (tokens_per_class,), generator=gen.g)
+        pos += tokens_per_class
+        ids[0, pos] = 1012
+        pos += 1
+    assert pos < T
+    ids[0, pos] = 102
+    mask = torch.zeros(1, T, dtype=torch.long)
+    mask[0, : pos + 1] = 1
+    return ids, mask, positive_map
+
+
+def vision_queries(positive_map, K, T=256, dim=256, gen=None):
+    """What QuerySelector.forward returns for one image (query_selector.py:40-116): queries [1, V, dim] and the
+    binarised mask [1, V, T] with 1 on the token positions of the query's class."""
+    V = len(positive_map) * K
+    q = gen.randn(1, V, dim, scale=0.5)
+    m = torch.zeros(1, V, T)
+    for ci, (label, toks) in enumerate(sorted(positive_map.items())):
+        m[0, ci * K:(ci + 1) * K, toks] = 1.0
+    return q, m

@@ -1,0 +1,89 @@
+"""CPU: the oracle restatement (oracle/restate.py) reproduces the golden vectors that oracle/make_golden.py recorded
+from the REFERENCE's own modules (tests/golden/*.pt).  fp32 vs fp32, so the tolerance is summation-order noise."""
+import os
+
+import pytest
+import torch
+
+from util import ROOT
+
+from oracle import make_golden, restate
+
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+
+def _cmp(fx, key, full, tol=2e-5):
+    steps = fx["subsample"][key]
+    got = make_golden.sub(full.float(), *steps)
+    ref = fx[key]
+    err = (got - ref).abs().max().item()
+    bound = tol * fx[key + "_absmax"] + 1e-6
+    assert err <= bound, f"{fx['case']}.{key}: {err:.3e} > {bound:.3e}"
+
+
+def test_gcp_block_golden():
+    fx = torch.load(os.path.join(GOLD, "gcp_block.pt"))
+    c = make_golden.case_inputs("gcp_block")
+    _cmp(fx, "y", restate.gcp_block(c["x"], c["vision"], c["mask"], c["sd"]))
+    _cmp(fx, "s", restate.gcp_sparse_attention(c["x"], c["vision"], c["mask"], c["sd"], "attn."))
+
+
+def test_preselect_golden():
+    fx = torch.load(os.path.join(GOLD, "preselect.pt"))
+    c = make_golden.case_inputs("preselect")
+    _cmp(fx, "vision", restate.preselect(c["vision"], c["image"], c["sd"]))
+
+
+def test_bi_attention_golden():
+    fx = torch.load(os.path.join(GOLD, "bi_attention.pt"))
+    c = make_golden.case_inputs("bi_attention")
+    v = torch.cat([f.flatten(2).transpose(1, 2) for f in c["feats"]], dim=1)
+    v2, l2 = restate.bi_attention(v, c["l"], c["mask"], c["sd"])
+    _cmp(fx, "v", v2)
+    _cmp(fx, "l", l2)
+
+
+def test_bert_layer_golden():
+    fx = torch.load(os.path.join(GOLD, "bert_layer.pt"))
+    c = make_golden.case_inputs("bert_layer")
+    h = restate.bert_layer(c["h"], restate.extended_mask(c["am"]), c["sd"], "", clamp=50000.0)
+    _cmp(fx, "h", h)
+    # the +-5e4 clamps are inactive at these magnitudes: the un-clamped HF-style layer gives the same numbers
+    _cmp(fx, "h", restate.bert_layer(c["h"], restate.extended_mask(c["am"]), c["sd"], ""))
+
+
+def test_gcp_semantic_traps():
+    """Properties the reference code implies (SURVEY.md §7 'semantic traps')."""
+    c = make_golden.case_inputs("gcp_block")
+    sd, x, vision, mask = c["sd"], c["x"], c["vision"], c["mask"]
+    s = restate.gcp_sparse_attention(x, vision, mask, sd, "attn.")
+    no_cls = mask.sum(1) == 0
+    assert s[no_cls].abs().max().item() == 0.0  # all-padding rows: softmax*0 -> exactly zero
+    # K/V depend only on the unique query: permuting tokens permutes outputs
+    perm = torch.randperm(256, generator=torch.Generator().manual_seed(0))
+    s2 = restate.gcp_sparse_attention(x[:, perm], vision, mask[:, :, perm], sd, "attn.")
+    assert torch.allclose(s2, s[:, perm], atol=1e-6)
+    # identity at the reference's zero-initialised gates (modeling_bert_new.py:274,289)
+    sd0 = dict(sd)
+    sd0["attn_gate.linear2.weight"] = torch.zeros_like(sd["attn_gate.linear2.weight"])
+    sd0["ff_gate"] = torch.zeros(1)
+    assert torch.equal(restate.gcp_block(x, vision, mask, sd0), x)
+
+
+def test_ml_nms_oracle_properties():
+    g = torch.Generator().manual_seed(0)
+    n = 400
+    xy = torch.rand(n, 2, generator=g) * 300
+    wh = torch.rand(n, 2, generator=g) * 80 + 5
+    boxes = torch.cat([xy, xy + wh], 1)
+    scores = torch.rand(n, generator=g)
+    labels = torch.randint(1, 4, (n,), generator=g).float()
+    keep = restate.ml_nms(boxes, scores, labels, 0.6)
+    assert torch.equal(keep, torch.sort(keep)[0])  # ascending original indices (ml_nms.cu:145-149)
+    # idempotence: NMS of the kept set keeps everything
+    k2 = restate.ml_nms(boxes[keep], scores[keep], labels[keep], 0.6)
+    assert k2.numel() == keep.numel()
+    # label gating: with all-distinct labels nothing is suppressed
+    assert restate.ml_nms(boxes, scores, torch.arange(n).float(), 0.6).numel() == n
+    # class-agnostic case equals torchvision-style greedy NMS with the +1 convention when boxes are far apart
+    assert restate.ml_nms(boxes[:1], scores[:1], labels[:1], 0.6).tolist() == [0]
