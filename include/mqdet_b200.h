@@ -119,6 +119,11 @@ int mqdet_softmax_rows(const void* x, int in_dtype, int64_t ldx, void* y, int64_
                        int64_t n_pad, float scale, const float* colmask, int64_t rows_per_batch, float mask_value,
                        float keep_add, void* stream);
 
+/* Text side of the dot-product token head (vldyhead.py:810,818): e = x / max(||x||, eps) written as fp16 and/or
+ * fp32, dot[r] = e[r,:] . w + b0[0] (w, b0, dot optional). */
+int mqdet_l2norm_rowdot(const float* x, int64_t rows, int64_t D, float eps, const float* w, const float* b0, void* e16,
+                        float* e32, float* dot, void* stream);
+
 /* fp32 -> fp16 cast (n elements), and fp16 -> fp32. */
 int mqdet_cast_f32_f16(const float* x, void* y, int64_t n, void* stream);
 int mqdet_cast_f16_f32(const void* x, float* y, int64_t n, void* stream);
@@ -134,6 +139,46 @@ int mqdet_argsort_desc(const float* scores, int64_t n, int64_t* order, void* str
 int64_t mqdet_ml_nms_workspace_bytes(int64_t n);
 int mqdet_ml_nms(const float* boxes, const float* scores, const float* labels, const int64_t* order, int64_t n,
                  float thresh, int64_t max_det, int64_t* keep_out, int32_t* num_keep, void* workspace, void* stream);
+
+/* ---- DyHead vision path (vldyhead.py DyConv.forward :205-247) -------------------------------------------------
+ * All FPN levels of an image are rows of one fp16 tensor x[B][N][C] (N = sum_l H_l*W_l, level l at row offset
+ * off_l, row-major).  level_hw: HOST int32 [nlev][2] = (H_l, W_l). */
+#define MQDET_MAX_LEVELS 8
+
+/* DCNv2 sampling stage (deform_conv_kernel_cuda.cu:578-641) -> fp16 column matrix [B*rows][9*C], k = tap*C + c.
+ *   branch 1: level l -> l (stride 1; rows = N)            DyConv[1]
+ *   branch 2: level l-1 -> l (stride 2; rows = N - H0*W0)  DyConv[2]
+ *   branch 0: level l+1 at its own size, offsets/mask of level l re-read through the OUTPUT strides (the
+ *             reinterpretation quirk, deform_conv_kernel_cuda.cu:605-618; rows = N - H0*W0)   DyConv[0]
+ *   om: fp32 [B][N][om_ld] pixel-major offset-conv output (18 offsets (dh,dw per tap) + 9 mask logits, sigmoid
+ *       applied here); NULL -> plain 3x3 convolution sampling. */
+int mqdet_dcn_cols(const void* x, const float* om, int64_t om_ld, const int32_t* level_hw, int64_t nlev, int64_t B,
+                   int64_t C, int branch, void* cols, void* stream);
+
+/* Per-(image, segment) per-channel partial sums (sum, sum of squares, row-weighted sum) of fp16 y [B][rows][C].
+ * seg_off_dev: DEVICE int32 [nseg+1] row offsets; partial: mqdet_chan_stats_floats(B, nseg, C) floats. */
+int64_t mqdet_chan_stats_floats(int64_t B, int64_t nseg, int64_t C);
+int mqdet_chan_stats(const void* y, const int32_t* seg_off_dev, int64_t nseg, int64_t B, int64_t rows_per_img, int64_t C,
+                     const float* row_weights, float* partial, void* stream);
+
+/* GroupNorm(groups) affine + scale-attention scalar per (image, segment) from the partial sums (vldyhead.py:226-238):
+ * affine [B][nseg][2][C] (GN(y) = a*y + b), attn [B][nseg] = h_sigmoid(relu(attn_w . GAP(GN(y)) + attn_b)). */
+int mqdet_gn_attn(const float* partial, const int32_t* seg_off_dev, int64_t nseg, int64_t B, int64_t C, int64_t groups,
+                  int weighted, const float* gn_w, const float* gn_b, float eps, const float* attn_w, const float* attn_b,
+                  float* affine, float* attn, void* stream);
+
+/* mid = mean_k attn_k * GN_k(y_k), branch 0 bilinearly upsampled (align_corners=True) from the coarser grid. */
+int mqdet_dyconv_combine(const void* y1, const void* y2, const void* y0, const float* aff1, const float* aff2,
+                         const float* aff0, const float* at1, const float* at2, const float* at0, const int32_t* level_hw,
+                         int64_t nlev, int64_t B, int64_t C, void* mid, void* stream);
+
+/* DyReLU (layers/dyrelu.py:80-104): coefficients per (image, level) from the partial sums of `mid`, then
+ * out = max(mid*a1 + b1, mid*a2 + b2). */
+int mqdet_dyrelu_coef(const float* partial, const int32_t* seg_off_dev, int64_t nseg, int64_t B, int64_t C,
+                      int64_t squeeze, const float* w1, const float* b1, const float* w2, const float* b2, float* coef,
+                      void* stream);
+int mqdet_dyrelu_apply(const void* mid, const float* coef, const int32_t* level_hw, int64_t nlev, int64_t B, int64_t C,
+                       void* out, void* stream);
 
 #ifdef __cplusplus
 }

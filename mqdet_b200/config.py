@@ -1,0 +1,46 @@
+"""Minimal attribute-namespace configuration (yacs is not available offline).
+
+Only the keys the hot-path modules read, with the values of configs/pretrain/mq-glip-t.yaml and
+maskrcnn_benchmark/config/defaults.py; a real yacs ``cfg`` object works in its place (same attribute paths).
+"""
+from types import SimpleNamespace as NS
+
+
+def mq_glip_t_cfg(**over):
+    cfg = NS(
+        MODEL=NS(
+            DEVICE="cuda",
+            BACKBONE=NS(OUT_CHANNELS=256),
+            SWINT=NS(EMBED_DIM=96, DEPTHS=(2, 2, 6, 2), NUM_HEADS=(3, 6, 12, 24), WINDOW_SIZE=7, MLP_RATIO=4,
+                     OUT_CHANNELS=(96, 192, 384, 768)),
+            LANGUAGE_BACKBONE=NS(LANG_DIM=768, MAX_QUERY_LEN=256, N_LAYERS=1, MODEL_TYPE="bert-base-uncased", PAD_MAX=True),
+            GROUP_NORM=NS(NUM_GROUPS=16),
+            RPN=NS(ASPECT_RATIOS=(1.0,), SCALES_PER_OCTAVE=1, ANCHOR_SIZES=(64, 128, 256, 512, 1024),
+                   ANCHOR_STRIDE=(8, 16, 32, 64, 128), RETURN_FUSED_FEATURES=False),
+            ATSS=NS(INFERENCE_TH=0.05, PRE_NMS_TOP_N=1000, NMS_TH=0.6, DETECTIONS_PER_IMG=100, NUM_CLASSES=81),
+            DYHEAD=NS(NUM_CLASSES=81, CHANNELS=256, NUM_CONVS=6, USE_GN=True, USE_DYRELU=True, USE_DFCONV=True,
+                      USE_DYFUSE=True, PRIOR_PROB=0.01, LOG_SCALE=0.0, SCORE_AGG="MEAN",
+                      FUSE_CONFIG=NS(EARLY_FUSE_ON=True, TYPE="MHA-B", JOINT_EMB_SIZE=256,
+                                     USE_DOT_PRODUCT_TOKEN_LOSS=True, USE_FUSED_FEATURES_DOT_PRODUCT=True,
+                                     USE_TOKEN_LOSS=False, USE_CONTRASTIVE_ALIGN_LOSS=False, MLM_LOSS=False,
+                                     STABLE_SOFTMAX_2D=False, CLAMP_MIN_FOR_UNDERFLOW=True, CLAMP_MAX_FOR_OVERFLOW=True,
+                                     CLAMP_BERTATTN_MIN_FOR_UNDERFLOW=True, CLAMP_BERTATTN_MAX_FOR_OVERFLOW=True,
+                                     CLAMP_DOT_PRODUCT=True, SEPARATE_BIDIRECTIONAL=False,
+                                     DO_LANG_PROJ_OUTSIDE_CHECKPOINT=False)),
+        ),
+        VISION_QUERY=NS(ENABLED=True, FIX_ATTN_GATE=-1.0, CONDITION_GATE=True, NONLINEAR_GATE=True, NO_CAT=True,
+                        ADD_ADAPT_LAYER=False, RETURN_ATTN_GATE_VALUE=False, VISION_SCALE=1.0,
+                        AUGMENT_IMAGE_WITH_QUERY=False, TEXT_DROPOUT=0.4, NEW_MASK_TOKEN=False, QUERY_FUSION=False,
+                        SHARE_KV=False, NUM_QUERY_PER_CLASS=5, SELECT_FPN_LEVEL=True, QUERY_BANK_PATH="",
+                        LEARNABLE_BANK=False, ADD_VISION_LAYER=False, PURE_TEXT_RATE=0.0, RANDOM_KSHOT=False),
+        TEST=NS(MDETR_STYLE_AGGREGATE_CLASS_NUM=-1, USE_MULTISCALE=False),
+        INPUT=NS(PIXEL_MEAN=[103.530, 116.280, 123.675], PIXEL_STD=[57.375, 57.120, 58.395]),
+        DATALOADER=NS(SIZE_DIVISIBILITY=32),
+    )
+    for k, v in over.items():
+        node = cfg
+        parts = k.split(".")
+        for p in parts[:-1]:
+            node = getattr(node, p)
+        setattr(node, parts[-1], v)
+    return cfg

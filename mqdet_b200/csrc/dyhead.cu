@@ -1,0 +1,468 @@
+// mqdet_b200 — DyHead vision-path kernels (DyConv = DCNv2 x3 + GroupNorm + scale-attention + DyReLU), NHWC.
+//
+// Reference: maskrcnn_benchmark/modeling/rpn/vldyhead.py DyConv.forward :205-247, Conv3x3Norm :111-152;
+//            maskrcnn_benchmark/csrc/cuda/deform_conv_kernel_cuda.cu :473-505 (bilinear), :578-641 (im2col);
+//            maskrcnn_benchmark/layers/dyrelu.py :80-120.
+//
+// Layout: all FPN levels of an image live in one fp16 tensor x[B][N][C] (N = sum_l H_l*W_l, level l at row offset
+// off_l, row-major (h, w)); every kernel below walks ALL levels in one launch through a LevelTable.
+// The DCNv2 sampling stage writes an fp16 column matrix [rows][9*C] (k = tap*C + c) that feeds the tcgen05 GEMM.
+#include "common.cuh"
+#include "../../include/mqdet_b200.h"
+
+namespace mqdet {
+
+struct LevelTable {
+  int n;
+  int H[MQDET_MAX_LEVELS], W[MQDET_MAX_LEVELS], off[MQDET_MAX_LEVELS];
+};
+
+static int fill_levels(LevelTable* t, const int32_t* hw, int64_t nlev) {
+  if (nlev < 1 || nlev > MQDET_MAX_LEVELS) return -1;
+  t->n = (int)nlev;
+  int off = 0;
+  for (int l = 0; l < nlev; ++l) {
+    t->H[l] = hw[2 * l];
+    t->W[l] = hw[2 * l + 1];
+    t->off[l] = off;
+    off += t->H[l] * t->W[l];
+  }
+  return off;
+}
+
+__device__ __forceinline__ void ld8h(const __half* p, float (&f)[8]) {
+  const uint4 a = *reinterpret_cast<const uint4*>(p);
+  const __half2* h = reinterpret_cast<const __half2*>(&a);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 x = __half22float2(h[i]);
+    f[2 * i] = x.x;
+    f[2 * i + 1] = x.y;
+  }
+}
+__device__ __forceinline__ void st8h(__half* p, const float (&f)[8]) {
+  __half2 h[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) h[i] = __floats2half2_rn(f[2 * i], f[2 * i + 1]);
+  *reinterpret_cast<uint4*>(p) = *reinterpret_cast<uint4*>(h);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// DCNv2 / plain 3x3 sampling -> column matrix.   One warp per (output pixel, tap); lanes across C (8 ch / lane).
+// branch 1: input level l -> output level l, stride 1   (rows: all levels, N per image)
+// branch 2: input level l-1 -> output level l, stride 2 (rows: levels 1..L-1)
+// branch 0: input level l+1, output at level l+1's size, offsets/mask of level l re-read through the OUTPUT strides
+//           (deform_conv_kernel_cuda.cu:605-618; rows: "virtual" levels 1..L-1 sized like the inputs)
+// om: [B][N][OM_LD] fp32 pixel-major offset/mask logits (27 used: 18 offsets (dh,dw per tap), 9 mask logits);
+//     om == nullptr -> plain 3x3 convolution sampling (zero offsets, mask 1).
+// The reference indexes a per-(image, level) NCHW-flat buffer [27][H_l*W_l]; flat index f of the offset part maps to
+// (channel f / HW_l, pixel f % HW_l), and of the (separately materialised, sigmoid-ed) mask part to channel 18 + f / HW_l.
+// ---------------------------------------------------------------------------------------------------------------
+template <int C>
+__global__ void __launch_bounds__(256) dcn_cols_kernel(const __half* __restrict__ x, const float* __restrict__ om,
+                                                       int om_ld, LevelTable lt, int branch, int B, long rows_per_img,
+                                                       __half* __restrict__ cols) {
+  const long gw = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;  // global warp = (row, tap)
+  const int lane = threadIdx.x & 31;
+  const long total = (long)B * rows_per_img * 9;
+  if (gw >= total) return;
+  const int tap = (int)(gw % 9);
+  const long r = gw / 9;
+  const int b = (int)(r / rows_per_img);
+  int q = (int)(r % rows_per_img);  // row within this image's output rows
+  const int N = lt.off[lt.n - 1] + lt.H[lt.n - 1] * lt.W[lt.n - 1];
+  // locate output level
+  int lo;      // level whose offsets are used
+  int li;      // input level
+  int Ho, Wo;  // output grid
+  int stride;
+  if (branch == 1) {
+    int l = 0;
+    while (l + 1 < lt.n && q >= lt.off[l + 1]) ++l;
+    q -= lt.off[l];
+    lo = l; li = l; Ho = lt.H[l]; Wo = lt.W[l]; stride = 1;
+  } else {
+    int l = 1;
+    const int base = lt.off[1];
+    while (l + 1 < lt.n && q + base >= lt.off[l + 1]) ++l;
+    q -= lt.off[l] - base;
+    Ho = lt.H[l]; Wo = lt.W[l];
+    if (branch == 2) { lo = l; li = l - 1; stride = 2; }
+    else { lo = l - 1; li = l; stride = 1; }
+  }
+  const int ho = q / Wo, wo = q % Wo;
+  const int Hi = lt.H[li], Wi = lt.W[li];
+  const int ti = tap / 3, tj = tap % 3;
+  float off_h = 0.f, off_w = 0.f, m = 1.f;
+  if (om) {
+    const int HWl = lt.H[lo] * lt.W[lo];
+    const float* omb = om + ((long)b * N + lt.off[lo]) * om_ld;
+    const int HWo = Ho * Wo, pix = ho * Wo + wo;
+    const int fh = (2 * tap) * HWo + pix, fw = (2 * tap + 1) * HWo + pix, fm = tap * HWo + pix;
+    off_h = omb[(long)(fh % HWl) * om_ld + fh / HWl];
+    off_w = omb[(long)(fw % HWl) * om_ld + fw / HWl];
+    const float ml = omb[(long)(fm % HWl) * om_ld + 18 + fm / HWl];
+    m = 1.f / (1.f + expf(-ml));
+  }
+  const float h_im = (float)(ho * stride - 1 + ti) + off_h;
+  const float w_im = (float)(wo * stride - 1 + tj) + off_w;
+  float acc[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+  if (h_im > -1.f && w_im > -1.f && h_im < (float)Hi && w_im < (float)Wi) {
+    const int h_low = (int)floorf(h_im), w_low = (int)floorf(w_im);
+    const int h_high = h_low + 1, w_high = w_low + 1;
+    const float lh = h_im - h_low, lw = w_im - w_low, hh = 1.f - lh, hw = 1.f - lw;
+    const __half* xb = x + ((long)b * N + lt.off[li]) * C + lane * 8;
+    float v[8];
+    if (h_low >= 0 && w_low >= 0) {
+      ld8h(xb + (long)(h_low * Wi + w_low) * C, v);
+      const float w1 = hh * hw;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[i] += w1 * v[i];
+    }
+    if (h_low >= 0 && w_high <= Wi - 1) {
+      ld8h(xb + (long)(h_low * Wi + w_high) * C, v);
+      const float w2 = hh * lw;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[i] += w2 * v[i];
+    }
+    if (h_high <= Hi - 1 && w_low >= 0) {
+      ld8h(xb + (long)(h_high * Wi + w_low) * C, v);
+      const float w3 = lh * hw;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[i] += w3 * v[i];
+    }
+    if (h_high <= Hi - 1 && w_high <= Wi - 1) {
+      ld8h(xb + (long)(h_high * Wi + w_high) * C, v);
+      const float w4 = lh * lw;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[i] += w4 * v[i];
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] *= m;
+  }
+  st8h(cols + (r * 9 + tap) * C + lane * 8, acc);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Per-(image, segment) per-channel statistics of an fp16 [rows, C] matrix: sum, sum of squares, weighted sum.
+// Segments are contiguous row ranges (one per level); deterministic two-stage reduction (no atomics):
+//   stage 1: grid (chunks, segments*B) -> partial[b][seg][chunk][3][C]      stage 2: folded into the consumers.
+// rw: optional per-row weights (bilinear-upsample GAP weights for the DyConv[0] branch), else weighted sum == sum.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int STAT_CHUNKS = 32;
+
+template <int C>
+__global__ void __launch_bounds__(256) chan_stats_kernel(const __half* __restrict__ y, const int* __restrict__ seg_off,
+                                                         int nseg, long rows_per_img, const float* __restrict__ rw,
+                                                         float* __restrict__ partial) {
+  // block = 256 threads = 8 row-lanes x 32 channel-lanes (8 channels each)
+  const int chunk = blockIdx.x, sb = blockIdx.y;
+  const int b = sb / nseg, seg = sb % nseg;
+  const int r0 = seg_off[seg], r1 = seg_off[seg + 1];
+  const int cl = threadIdx.x & 31, rl = threadIdx.x >> 5;
+  float s[8], q[8], w[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s[i] = q[i] = w[i] = 0.f;
+  for (int r = r0 + chunk * 8 + rl; r < r1; r += STAT_CHUNKS * 8) {
+    float v[8];
+    ld8h(y + ((long)b * rows_per_img + r) * C + cl * 8, v);
+    const float wt = rw ? rw[r] : 1.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      s[i] += v[i];
+      q[i] += v[i] * v[i];
+      w[i] += wt * v[i];
+    }
+  }
+  __shared__ float sh[8][3][C];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    sh[rl][0][cl * 8 + i] = s[i];
+    sh[rl][1][cl * 8 + i] = q[i];
+    sh[rl][2][cl * 8 + i] = w[i];
+  }
+  __syncthreads();
+  float* out = partial + (((long)b * nseg + seg) * STAT_CHUNKS + chunk) * 3 * C;
+  for (int i = threadIdx.x; i < 3 * C; i += 256) {
+    const int k = i / C, c = i % C;
+    float t = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) t += sh[j][k][c];
+    out[i] = t;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// GroupNorm parameters + scale-attention scalar per (image, segment)   [vldyhead.py:226-238]
+//   partial stats -> per-group mu/rstd -> per-channel affine (ga, gb) with GN(y)[c] = ga[c]*y + gb[c]
+//   GAP(fea)[c] = ga[c]*mean_w(y)[c] + gb[c]  (mean_w = plain mean, or the bilinear-upsample-weighted mean for the
+//   DyConv[0] branch whose feature is upsampled AFTER the norm);  attn = h_sigmoid(relu(w_attn . GAP + b_attn))
+// One block (C threads = channels) per (b, seg).  out: affine[b][seg][2][C], attn[b][seg].
+// ---------------------------------------------------------------------------------------------------------------
+template <int C, int G>
+__global__ void __launch_bounds__(C) gn_attn_kernel(const float* __restrict__ partial, const int* __restrict__ seg_off,
+                                                    int nseg, int weighted, const float* __restrict__ gn_w,
+                                                    const float* __restrict__ gn_b, float eps,
+                                                    const float* __restrict__ attn_w, const float* __restrict__ attn_b,
+                                                    float* __restrict__ affine, float* __restrict__ attn) {
+  const int sb = blockIdx.x, seg = sb % nseg;
+  const int c = threadIdx.x;
+  const float* p = partial + (long)sb * STAT_CHUNKS * 3 * C;
+  float s = 0.f, q = 0.f, w = 0.f;
+  for (int k = 0; k < STAT_CHUNKS; ++k) {
+    s += p[(k * 3 + 0) * C + c];
+    q += p[(k * 3 + 1) * C + c];
+    w += p[(k * 3 + 2) * C + c];
+  }
+  const float rows = (float)(seg_off[seg + 1] - seg_off[seg]);
+  __shared__ float sh_s[C], sh_q[C], sh_d[C];
+  sh_s[c] = s;
+  sh_q[c] = q;
+  __syncthreads();
+  constexpr int CPG = C / G;
+  const int g = c / CPG;
+  float gs = 0.f, gq = 0.f;
+#pragma unroll
+  for (int i = 0; i < CPG; ++i) {
+    gs += sh_s[g * CPG + i];
+    gq += sh_q[g * CPG + i];
+  }
+  const float cnt = rows * CPG;
+  const float mu = gs / cnt;
+  const float var = fmaxf(gq / cnt - mu * mu, 0.f);
+  const float rstd = rsqrtf(var + eps);
+  const float ga = rstd * gn_w[c], gb = gn_b[c] - mu * rstd * gn_w[c];
+  affine[((long)sb * 2 + 0) * C + c] = ga;
+  affine[((long)sb * 2 + 1) * C + c] = gb;
+  const float ymean = weighted ? w : s / rows;
+  sh_d[c] = (ga * ymean + gb) * attn_w[c];
+  __syncthreads();
+  for (int o = C / 2; o > 0; o >>= 1) {
+    if (c < o) sh_d[c] += sh_d[c + o];
+    __syncthreads();
+  }
+  if (c == 0) {
+    const float a = fmaxf(sh_d[0] + attn_b[0], 0.f);   // Conv2d(256,1,1) + ReLU
+    attn[sb] = fminf(fmaxf(a + 3.f, 0.f), 6.f) / 6.f;  // h_sigmoid
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Scale-aware fusion (vldyhead.py:219-238): mid[p] = mean_k attn_k * GN_k(y_k)[p]; branch 0 is bilinearly upsampled
+// (align_corners=True, F.upsample_bilinear :224) from the next-coarser grid.  One warp per pixel, 8 channels per lane.
+// ---------------------------------------------------------------------------------------------------------------
+template <int C>
+__global__ void __launch_bounds__(256) dyconv_combine_kernel(const __half* __restrict__ y1, const __half* __restrict__ y2,
+                                                             const __half* __restrict__ y0, const float* __restrict__ aff1,
+                                                             const float* __restrict__ aff2, const float* __restrict__ aff0,
+                                                             const float* __restrict__ at1, const float* __restrict__ at2,
+                                                             const float* __restrict__ at0, LevelTable lt, int B,
+                                                             __half* __restrict__ mid) {
+  const long gw = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  const int L = lt.n;
+  const int N = lt.off[L - 1] + lt.H[L - 1] * lt.W[L - 1];
+  const int N1 = N - lt.H[0] * lt.W[0];
+  if (gw >= (long)B * N) return;
+  const int b = (int)(gw / N);
+  const int pn = (int)(gw % N);
+  int l = 0;
+  while (l + 1 < L && pn >= lt.off[l + 1]) ++l;
+  const int q = pn - lt.off[l];
+  const int H = lt.H[l], W = lt.W[l];
+  const int c0 = lane * 8;
+  float acc[8], v[8];
+  {  // branch 1 (same level)
+    const float a = at1[b * L + l];
+    const float* ga = aff1 + ((long)(b * L + l) * 2) * C + c0;
+    ld8h(y1 + ((long)b * N + pn) * C + c0, v);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = a * (ga[i] * v[i] + ga[C + i]);
+  }
+  int nk = 1;
+  if (l > 0) {  // branch 2: stride-2 conv of the finer level, already at this resolution; segment index l-1
+    const float a = at2[b * (L - 1) + l - 1];
+    const float* ga = aff2 + ((long)(b * (L - 1) + l - 1) * 2) * C + c0;
+    ld8h(y2 + ((long)b * N1 + (pn - lt.off[1])) * C + c0, v);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] += a * (ga[i] * v[i] + ga[C + i]);
+    ++nk;
+  }
+  if (l < L - 1) {  // branch 0: conv on the coarser level (segment index l), upsampled to (H, W)
+    const float a = at0[b * (L - 1) + l];
+    const float* ga = aff0 + ((long)(b * (L - 1) + l) * 2) * C + c0;
+    const int Hs = lt.H[l + 1], Ws = lt.W[l + 1];
+    const int h = q / W, w = q % W;
+    // area_pixel_compute_source_index, align_corners=True (fp32 scale like ATen)
+    const float sh = (H > 1) ? (float)(Hs - 1) / (float)(H - 1) : 0.f;
+    const float sw = (W > 1) ? (float)(Ws - 1) / (float)(W - 1) : 0.f;
+    const float fh = sh * h, fw = sw * w;
+    const int h0 = (int)fh, w0 = (int)fw;
+    const int h1 = h0 + ((h0 < Hs - 1) ? 1 : 0), w1 = w0 + ((w0 < Ws - 1) ? 1 : 0);
+    const float lh = fh - h0, lw = fw - w0;
+    const __half* yb = y0 + ((long)b * N1 + (lt.off[l + 1] - lt.off[1])) * C + c0;
+    float t[8], u[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) u[i] = 0.f;
+    ld8h(yb + (long)(h0 * Ws + w0) * C, t);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) u[i] += (1.f - lh) * (1.f - lw) * t[i];
+    ld8h(yb + (long)(h0 * Ws + w1) * C, t);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) u[i] += (1.f - lh) * lw * t[i];
+    ld8h(yb + (long)(h1 * Ws + w0) * C, t);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) u[i] += lh * (1.f - lw) * t[i];
+    ld8h(yb + (long)(h1 * Ws + w1) * C, t);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) u[i] += lh * lw * t[i];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] += a * (ga[i] * u[i] + ga[C + i]);
+    ++nk;
+  }
+  const float inv = 1.f / nk;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[i] *= inv;
+  st8h(mid + ((long)b * N + pn) * C + c0, acc);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// DyReLU coefficients (layers/dyrelu.py:80-104; K2, use_bias, reduction 4): per (image, level)
+//   y = h_sigmoid(W2 relu(W1 GAP(x) + b1) + b2)  [4C] -> a1=(y0-.5)*2+1, b1=y1-.5, a2=(y2-.5)*2, b2=y3-.5
+// One block of C threads per (b, level).  coef[b][l][4][C].
+// ---------------------------------------------------------------------------------------------------------------
+template <int C, int SQ>
+__global__ void __launch_bounds__(C) dyrelu_coef_kernel(const float* __restrict__ partial, const int* __restrict__ seg_off,
+                                                        int nseg, const float* __restrict__ w1,
+                                                        const float* __restrict__ b1, const float* __restrict__ w2,
+                                                        const float* __restrict__ b2, float* __restrict__ coef) {
+  const int sb = blockIdx.x, seg = sb % nseg;
+  const int c = threadIdx.x;
+  const float* p = partial + (long)sb * STAT_CHUNKS * 3 * C;
+  float s = 0.f;
+  for (int k = 0; k < STAT_CHUNKS; ++k) s += p[(k * 3 + 0) * C + c];
+  __shared__ float gap[C], hid[SQ];
+  gap[c] = s / (float)(seg_off[seg + 1] - seg_off[seg]);
+  __syncthreads();
+  if (c < SQ) {
+    float t = b1[c];
+    for (int i = 0; i < C; ++i) t = fmaf(w1[c * C + i], gap[i], t);
+    hid[c] = fmaxf(t, 0.f);
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int o = k * C + c;
+    float t = b2[o];
+    for (int i = 0; i < SQ; ++i) t = fmaf(w2[o * SQ + i], hid[i], t);
+    t = fminf(fmaxf(t + 3.f, 0.f), 6.f) / 6.f;  // h_sigmoid
+    float r;
+    if (k == 0) r = (t - 0.5f) * 2.f + 1.f;
+    else if (k == 1) r = t - 0.5f;
+    else if (k == 2) r = (t - 0.5f) * 2.f;
+    else r = t - 0.5f;
+    coef[((long)sb * 4 + k) * C + c] = r;
+  }
+}
+
+template <int C>
+__global__ void __launch_bounds__(256) dyrelu_apply_kernel(const __half* __restrict__ mid, const float* __restrict__ coef,
+                                                           LevelTable lt, int B, __half* __restrict__ out) {
+  const long gw = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  const int L = lt.n;
+  const int N = lt.off[L - 1] + lt.H[L - 1] * lt.W[L - 1];
+  if (gw >= (long)B * N) return;
+  const int b = (int)(gw / N), pn = (int)(gw % N);
+  int l = 0;
+  while (l + 1 < L && pn >= lt.off[l + 1]) ++l;
+  const float* cf = coef + ((long)(b * L + l) * 4) * C + lane * 8;
+  float v[8], o[8];
+  ld8h(mid + gw * C + lane * 8, v);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) o[i] = fmaxf(v[i] * cf[i] + cf[C + i], v[i] * cf[2 * C + i] + cf[3 * C + i]);
+  st8h(out + gw * C + lane * 8, o);
+}
+
+}  // namespace mqdet
+
+using namespace mqdet;
+
+extern "C" int mqdet_dcn_cols(const void* x, const float* om, int64_t om_ld, const int32_t* level_hw, int64_t nlev,
+                              int64_t B, int64_t C, int branch, void* cols, void* stream) {
+  MQ_REQUIRE(x && cols && level_hw, "dcn_cols: null pointer");
+  MQ_REQUIRE(C == 256, "dcn_cols: C must be 256 (got %ld)", (long)C);
+  MQ_REQUIRE(branch >= 0 && branch <= 2, "dcn_cols: branch must be 0, 1 or 2");
+  LevelTable lt;
+  const int N = fill_levels(&lt, level_hw, nlev);
+  MQ_REQUIRE(N > 0, "dcn_cols: bad level table");
+  MQ_REQUIRE(branch == 1 || nlev >= 2, "dcn_cols: branches 0/2 need at least two levels");
+  const long rows_per_img = branch == 1 ? N : N - lt.H[0] * lt.W[0];
+  const long warps = B * rows_per_img * 9;
+  const long blocks = (warps * 32 + 255) / 256;
+  dcn_cols_kernel<256><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((const __half*)x, om, (int)om_ld, lt, branch,
+                                                                          (int)B, rows_per_img, (__half*)cols);
+  return check_launch("dcn_cols_kernel");
+}
+
+extern "C" int64_t mqdet_chan_stats_floats(int64_t B, int64_t nseg, int64_t C) { return B * nseg * STAT_CHUNKS * 3 * C; }
+
+extern "C" int mqdet_chan_stats(const void* y, const int32_t* seg_off_dev, int64_t nseg, int64_t B, int64_t rows_per_img,
+                                int64_t C, const float* row_weights, float* partial, void* stream) {
+  MQ_REQUIRE(y && seg_off_dev && partial, "chan_stats: null pointer");
+  MQ_REQUIRE(C == 256, "chan_stats: C must be 256");
+  chan_stats_kernel<256><<<dim3(STAT_CHUNKS, (unsigned)(B * nseg)), 256, 0, (cudaStream_t)stream>>>(
+      (const __half*)y, seg_off_dev, (int)nseg, rows_per_img, row_weights, partial);
+  return check_launch("chan_stats_kernel");
+}
+
+extern "C" int mqdet_gn_attn(const float* partial, const int32_t* seg_off_dev, int64_t nseg, int64_t B, int64_t C,
+                             int64_t groups, int weighted, const float* gn_w, const float* gn_b, float eps,
+                             const float* attn_w, const float* attn_b, float* affine, float* attn, void* stream) {
+  MQ_REQUIRE(partial && seg_off_dev && gn_w && gn_b && attn_w && attn_b && affine && attn, "gn_attn: null pointer");
+  MQ_REQUIRE(C == 256 && groups == 16, "gn_attn: C=256, groups=16 only (MODEL.GROUP_NORM.NUM_GROUPS)");
+  gn_attn_kernel<256, 16><<<(unsigned)(B * nseg), 256, 0, (cudaStream_t)stream>>>(partial, seg_off_dev, (int)nseg, weighted,
+                                                                                  gn_w, gn_b, eps, attn_w, attn_b, affine,
+                                                                                  attn);
+  return check_launch("gn_attn_kernel");
+}
+
+extern "C" int mqdet_dyconv_combine(const void* y1, const void* y2, const void* y0, const float* aff1, const float* aff2,
+                                    const float* aff0, const float* at1, const float* at2, const float* at0,
+                                    const int32_t* level_hw, int64_t nlev, int64_t B, int64_t C, void* mid, void* stream) {
+  MQ_REQUIRE(y1 && aff1 && at1 && mid && level_hw, "dyconv_combine: null pointer");
+  MQ_REQUIRE(C == 256, "dyconv_combine: C must be 256");
+  LevelTable lt;
+  const int N = fill_levels(&lt, level_hw, nlev);
+  MQ_REQUIRE(N > 0, "dyconv_combine: bad level table");
+  MQ_REQUIRE(nlev == 1 || (y2 && y0 && aff2 && aff0 && at2 && at0), "dyconv_combine: missing cross-level inputs");
+  const long blocks = ((long)B * N * 32 + 255) / 256;
+  dyconv_combine_kernel<256><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
+      (const __half*)y1, (const __half*)y2, (const __half*)y0, aff1, aff2, aff0, at1, at2, at0, lt, (int)B, (__half*)mid);
+  return check_launch("dyconv_combine_kernel");
+}
+
+extern "C" int mqdet_dyrelu_coef(const float* partial, const int32_t* seg_off_dev, int64_t nseg, int64_t B, int64_t C,
+                                 int64_t squeeze, const float* w1, const float* b1, const float* w2, const float* b2,
+                                 float* coef, void* stream) {
+  MQ_REQUIRE(partial && seg_off_dev && w1 && b1 && w2 && b2 && coef, "dyrelu_coef: null pointer");
+  MQ_REQUIRE(C == 256 && squeeze == 64, "dyrelu_coef: C=256, squeeze=64 only");
+  dyrelu_coef_kernel<256, 64><<<(unsigned)(B * nseg), 256, 0, (cudaStream_t)stream>>>(partial, seg_off_dev, (int)nseg, w1, b1,
+                                                                                      w2, b2, coef);
+  return check_launch("dyrelu_coef_kernel");
+}
+
+extern "C" int mqdet_dyrelu_apply(const void* mid, const float* coef, const int32_t* level_hw, int64_t nlev, int64_t B,
+                                  int64_t C, void* out, void* stream) {
+  MQ_REQUIRE(mid && coef && out && level_hw, "dyrelu_apply: null pointer");
+  MQ_REQUIRE(C == 256, "dyrelu_apply: C must be 256");
+  LevelTable lt;
+  const int N = fill_levels(&lt, level_hw, nlev);
+  MQ_REQUIRE(N > 0, "dyrelu_apply: bad level table");
+  const long blocks = ((long)B * N * 32 + 255) / 256;
+  dyrelu_apply_kernel<256><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((const __half*)mid, coef, lt, (int)B,
+                                                                              (__half*)out);
+  return check_launch("dyrelu_apply_kernel");
+}

@@ -42,8 +42,9 @@ struct GemmP {
   int a_bcast1, a_bcast2, b_bcast1, b_bcast2;  // 1 -> TMA coordinate pinned to 0
 };
 
-// One output element's epilogue (shared by both kernels).
-__device__ __forceinline__ float epi_one(const GemmP& p, float acc, long row, long col, int z1, int z2,
+// One output element's epilogue, split so the tensor-core kernel can apply the residual in its coalesced phase:
+//   epi_pre : alpha / bias / activation / clamp / gate      epi_one = epi_pre + residual
+__device__ __forceinline__ float epi_pre(const GemmP& p, float acc, long row, long col, int z1, int z2,
                                          float gate_scalar) {
   float v = acc;
   float b = 0.f;
@@ -66,11 +67,17 @@ __device__ __forceinline__ float epi_one(const GemmP& p, float acc, long row, lo
     float g = p.gate[row];
     v *= p.gate_tanh ? tanhf(g) : g;
   }
-  if (p.R) {
-    long off = z1 * p.r_b1 + z2 * p.r_b2 + row * p.ldr + col;
-    v += (p.r_dtype == MQDET_F32) ? reinterpret_cast<const float*>(p.R)[off]
+  return v;
+}
+__device__ __forceinline__ float ld_residual(const GemmP& p, long row, long col, int z1, int z2) {
+  const long off = z1 * p.r_b1 + z2 * p.r_b2 + row * p.ldr + col;
+  return (p.r_dtype == MQDET_F32) ? reinterpret_cast<const float*>(p.R)[off]
                                   : __half2float(reinterpret_cast<const __half*>(p.R)[off]);
-  }
+}
+__device__ __forceinline__ float epi_one(const GemmP& p, float acc, long row, long col, int z1, int z2,
+                                         float gate_scalar) {
+  float v = epi_pre(p, acc, row, col, z1, z2, gate_scalar);
+  if (p.R) v += ld_residual(p, row, col, z1, z2);
   return v;
 }
 
@@ -169,61 +176,113 @@ __global__ void __launch_bounds__(256) gemm_tc_kernel(const __grid_constant__ CU
       tc_commit(tmem_full_bar);  // accumulator complete
     }
   } else if (warp >= 4) {
+    // ---- epilogue ------------------------------------------------------------------------------------------
+    // phase 1: TMEM -> registers (thread == output row) -> alpha/bias/act/clamp/gate -> fp32 staging tile in the
+    //          (now idle) operand ring, rows padded by 16 B so the float4 stores are bank-conflict free
+    // phase 2: staging -> (+ residual, read coalesced) -> 16-byte coalesced global stores, lanes along columns
     const int ew = warp - 4;  // == warp % 4 -> TMEM lane quarter this warp may access
     mbar_wait(tmem_full_bar, 0);
     tc_fence_after();
-    const long row = (long)m_tile * BM + ew * 32 + lane;
-    const bool row_ok = row < p.M;
+    constexpr int LDS = BN + 4;  // staging row stride in floats
+    float* stage = reinterpret_cast<float*>(smem);
+    const int r_local = ew * 32 + lane;
+    const long row = (long)m_tile * BM + r_local;
     float gate_scalar = 1.f;
     if (p.gate_mode == MQDET_VEC_SCALAR) {
       gate_scalar = p.gate[0];
       if (p.gate_tanh) gate_scalar = tanhf(gate_scalar);
     }
-    const bool vec_ok = ((p.ldc & 7) == 0) && ((p.c_b1 & 7) == 0) && ((p.c_b2 & 7) == 0) &&
-                        ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0);
 #pragma unroll 1
     for (int c0 = 0; c0 < BN; c0 += 32) {
       uint32_t r[32];
       tmem_ld_32x32(tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)c0, r);
       tmem_ld_wait();
       const long col0 = (long)n_tile * BN + c0;
-      if (row_ok && col0 < p.N) {
-        float v[32];
+      float4* dst = reinterpret_cast<float4*>(stage + r_local * LDS + c0);
+      const bool live = row < p.M && col0 < p.N;
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const long col = col0 + i;
-          v[i] = (col < p.N) ? epi_one(p, __uint_as_float(r[i]), row, col, z1, z2, gate_scalar) : 0.f;
-        }
-        if (vec_ok && col0 + 32 <= p.N) {
-          const long off = z1 * p.c_b1 + z2 * p.c_b2 + row * p.ldc + col0;
-          if (p.c_dtype == MQDET_F32) {
-            float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.C) + off);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) dst[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-          } else {
-            uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__half*>(p.C) + off);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              __half2 h0 = __floats2half2_rn(v[8 * i + 0], v[8 * i + 1]);
-              __half2 h1 = __floats2half2_rn(v[8 * i + 2], v[8 * i + 3]);
-              __half2 h2 = __floats2half2_rn(v[8 * i + 4], v[8 * i + 5]);
-              __half2 h3 = __floats2half2_rn(v[8 * i + 6], v[8 * i + 7]);
-              uint4 u;
-              u.x = *reinterpret_cast<uint32_t*>(&h0);
-              u.y = *reinterpret_cast<uint32_t*>(&h1);
-              u.z = *reinterpret_cast<uint32_t*>(&h2);
-              u.w = *reinterpret_cast<uint32_t*>(&h3);
-              dst[i] = u;
-            }
-          }
+      for (int i = 0; i < 8; ++i) {
+        float4 v;
+        if (live) {
+          const long c = col0 + 4 * i;
+          v.x = (c + 0 < p.N) ? epi_pre(p, __uint_as_float(r[4 * i + 0]), row, c + 0, z1, z2, gate_scalar) : 0.f;
+          v.y = (c + 1 < p.N) ? epi_pre(p, __uint_as_float(r[4 * i + 1]), row, c + 1, z1, z2, gate_scalar) : 0.f;
+          v.z = (c + 2 < p.N) ? epi_pre(p, __uint_as_float(r[4 * i + 2]), row, c + 2, z1, z2, gate_scalar) : 0.f;
+          v.w = (c + 3 < p.N) ? epi_pre(p, __uint_as_float(r[4 * i + 3]), row, c + 3, z1, z2, gate_scalar) : 0.f;
         } else {
-#pragma unroll 1
-          for (int i = 0; i < 32; ++i)
-            if (col0 + i < p.N) store_one(p, v[i], row, col0 + i, z1, z2);
+          v = make_float4(0.f, 0.f, 0.f, 0.f);
         }
+        dst[i] = v;
       }
     }
     tc_fence_before();
+    asm volatile("bar.sync 1, 128;" ::: "memory");  // the 4 epilogue warps only
+
+    constexpr int LPR = BN / 8;        // lanes per row (8 columns each)
+    constexpr int RPI = 32 / LPR * 4;  // rows per iteration over the 4 warps
+    const bool c_vec = ((p.ldc & 7) == 0) && ((p.c_b1 & 7) == 0) && ((p.c_b2 & 7) == 0) &&
+                       ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0);
+    const bool r_vec = p.R && ((p.ldr & 7) == 0) && ((p.r_b1 & 7) == 0) && ((p.r_b2 & 7) == 0) &&
+                       ((reinterpret_cast<uintptr_t>(p.R) & 15) == 0);
+    const int lc = (lane % LPR) * 8;
+    const long col = (long)n_tile * BN + lc;
+#pragma unroll 1
+    for (int r0 = 0; r0 < BM; r0 += RPI) {
+      const int rl = r0 + ew * (32 / LPR) + lane / LPR;
+      const long grow = (long)m_tile * BM + rl;
+      if (grow >= p.M || col >= p.N) continue;
+      const float4 s0 = *reinterpret_cast<const float4*>(stage + rl * LDS + lc);
+      const float4 s1 = *reinterpret_cast<const float4*>(stage + rl * LDS + lc + 4);
+      float v[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+      const bool full = col + 8 <= p.N;
+      if (p.R) {
+        if (full && r_vec) {
+          const long off = z1 * p.r_b1 + z2 * p.r_b2 + grow * p.ldr + col;
+          if (p.r_dtype == MQDET_F32) {
+            const float4 a = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.R) + off);
+            const float4 b = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.R) + off + 4);
+            v[0] += a.x; v[1] += a.y; v[2] += a.z; v[3] += a.w;
+            v[4] += b.x; v[5] += b.y; v[6] += b.z; v[7] += b.w;
+          } else {
+            const uint4 u = *reinterpret_cast<const uint4*>(reinterpret_cast<const __half*>(p.R) + off);
+            const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const float2 f = __half22float2(h[i]);
+              v[2 * i] += f.x;
+              v[2 * i + 1] += f.y;
+            }
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            if (col + i < p.N) v[i] += ld_residual(p, grow, col + i, z1, z2);
+        }
+      }
+      if (full && c_vec) {
+        const long off = z1 * p.c_b1 + z2 * p.c_b2 + grow * p.ldc + col;
+        if (p.c_dtype == MQDET_F32) {
+          float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.C) + off);
+          dst[0] = make_float4(v[0], v[1], v[2], v[3]);
+          dst[1] = make_float4(v[4], v[5], v[6], v[7]);
+        } else {
+          __half2 h0 = __floats2half2_rn(v[0], v[1]);
+          __half2 h1 = __floats2half2_rn(v[2], v[3]);
+          __half2 h2 = __floats2half2_rn(v[4], v[5]);
+          __half2 h3 = __floats2half2_rn(v[6], v[7]);
+          uint4 u;
+          u.x = *reinterpret_cast<uint32_t*>(&h0);
+          u.y = *reinterpret_cast<uint32_t*>(&h1);
+          u.z = *reinterpret_cast<uint32_t*>(&h2);
+          u.w = *reinterpret_cast<uint32_t*>(&h3);
+          *reinterpret_cast<uint4*>(reinterpret_cast<__half*>(p.C) + off) = u;
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          if (col + i < p.N) store_one(p, v[i], grow, col + i, z1, z2);
+      }
+    }
   }
   __syncthreads();
   if (warp == 2) {
@@ -388,10 +447,12 @@ extern "C" int mqdet_gemm_f16(const mqdet_gemm_args* a, int impl, void* stream) 
   MQ_REQUIRE((a->a_b1 % 8) == 0 && (a->a_b2 % 8) == 0 && (a->b_b1 % 8) == 0 && (a->b_b2 % 8) == 0,
              "gemm: batch strides must be multiples of 8");
   MQ_REQUIRE(((uintptr_t)a->A % 16) == 0 && ((uintptr_t)a->B % 16) == 0, "gemm: A/B must be 16-byte aligned");
-  // Tile-N heuristic: widest tile that still gives >= ~1 wave of CTAs on 148 SMs.
+  // Tile-N heuristic.  128x128 tiles with a 3-deep ring (97 KB) let two CTAs share an SM so one CTA's epilogue
+  // overlaps the other's main loop -- the right choice for the short-K, output-bound products that dominate this
+  // model (K = 256..768).  Long-K products are MMA/L2 bound: 128x256 tiles halve the operand re-reads.
   const long mt = cdiv(p.M, BM), z = (long)p.nb1 * p.nb2;
-  if (p.N > 128 && mt * cdiv(p.N, 256) * z >= 148) return launch_tc<256, 4>(p, st);
-  if (p.N > 64 && (mt * cdiv(p.N, 128) * z >= 148 || p.N > 2048)) return launch_tc<128, 3>(p, st);
+  if (p.N >= 256 && p.K >= 1024 && mt * cdiv(p.N, 256) * z >= 148) return launch_tc<256, 4>(p, st);
+  if (p.N > 64 && (mt * cdiv(p.N, 128) * z >= 120 || p.N > 1024)) return launch_tc<128, 3>(p, st);
   if (p.N > 32) return launch_tc<64, 4>(p, st);
   return launch_tc<32, 4>(p, st);
 }

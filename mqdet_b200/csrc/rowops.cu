@@ -122,9 +122,43 @@ __global__ void cast_f16_f32_kernel(const __half* __restrict__ x, float* __restr
   for (; i < n; i += stride) y[i] = __half2float(x[i]);
 }
 
+// e = x / max(||x||_2, eps) (F.normalize, vldyhead.py:810) and beta = e . w + b0 (:818).  One warp per row.
+__global__ void __launch_bounds__(256) l2norm_rowdot_kernel(const float* __restrict__ x, long rows, int D, float eps,
+                                                            const float* __restrict__ w, const float* __restrict__ b0,
+                                                            __half* __restrict__ e16, float* __restrict__ e32,
+                                                            float* __restrict__ dot) {
+  const long row = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const float* xr = x + row * D;
+  float s = 0.f;
+  for (int i = lane; i < D; i += 32) s += xr[i] * xr[i];
+  const float inv = 1.f / fmaxf(sqrtf(warp_sum(s)), eps);
+  float d = 0.f;
+  for (int i = lane; i < D; i += 32) {
+    const float e = xr[i] * inv;
+    if (e16) e16[row * D + i] = __float2half_rn(e);
+    if (e32) e32[row * D + i] = e;
+    if (w) d = fmaf(e, w[i], d);
+  }
+  if (dot) {
+    d = warp_sum(d);
+    if (lane == 0) dot[row] = d + (b0 ? b0[0] : 0.f);
+  }
+}
+
 }  // namespace mqdet
 
 using namespace mqdet;
+
+extern "C" int mqdet_l2norm_rowdot(const float* x, int64_t rows, int64_t D, float eps, const float* w, const float* b0,
+                                   void* e16, float* e32, float* dot, void* stream) {
+  MQ_REQUIRE(x && rows > 0 && D > 0 && (e16 || e32 || dot), "l2norm_rowdot: bad args");
+  const int wpb = 8;
+  l2norm_rowdot_kernel<<<cdiv(rows, wpb), wpb * 32, 0, (cudaStream_t)stream>>>(x, rows, (int)D, eps, w, b0, (__half*)e16, e32,
+                                                                             dot);
+  return check_launch("l2norm_rowdot_kernel");
+}
 
 extern "C" int mqdet_layernorm(const void* x, int in_dtype, int64_t ldx, const float* gamma, const float* beta, float eps,
                                int64_t rows, int64_t D, void* out16, void* out32, int64_t ldo, int64_t zero_row_period,

@@ -50,32 +50,30 @@ _pad_cache = {}
 
 def sparse_index(attention_mask):
     """[B,V,T] 0/1 mask -> int32 [B,T,S] ascending query indices padded with V (get_index_with_padding_batch :40-63).
-    S = the global max count; computing it needs one device->host read, done once per distinct mask tensor."""
-    key = (attention_mask.data_ptr(), attention_mask._version, tuple(attention_mask.shape))
+    S = the global max count; computing it needs one device->host read, done once per distinct mask tensor.
+    The cache holds the tensor itself (identity + version), never a bare data_ptr that the allocator could recycle."""
     ent = _idx_cache.get("e")
-    if ent is not None and ent[0] == key:
-        return ent[1]
-    B, V, T = attention_mask.shape
+    if ent is not None and ent[0] is attention_mask and ent[1] == attention_mask._version:
+        return ent[2]
     m = attention_mask if attention_mask.dtype == torch.float32 else attention_mask.float()
     _, counts = ops.gcp_build_index(m, 1)
     S = int(counts.max().item())
     if S > 16:
         raise MqdetError(f"GCP sparse attention supports at most 16 queries per token, mask has {S}")
     idx, _ = ops.gcp_build_index(m, max(S, 1))
-    _idx_cache["e"] = (key, idx)
+    _idx_cache["e"] = (attention_mask, attention_mask._version, idx)
     return idx
 
 
 def padded_vision(vision):
-    """cat(vision, zero row) -> fp32 [B, V+1, D] (modeling_bert_new.py:176-177); cached per vision tensor."""
-    key = (vision.data_ptr(), vision._version, tuple(vision.shape), vision.dtype)
+    """cat(vision, zero row) -> fp32 [B, V+1, D] (modeling_bert_new.py:176-177); cached per vision tensor object."""
     ent = _pad_cache.get("e")
-    if ent is not None and ent[0] == key:
-        return ent[1]
+    if ent is not None and ent[0] is vision and ent[1] == vision._version:
+        return ent[2]
     B, V, D = vision.shape
     buf = torch.zeros((B, V + 1, D), dtype=torch.float32, device=vision.device)
     buf[:, :V].copy_(vision)
-    _pad_cache["e"] = (key, buf)
+    _pad_cache["e"] = (vision, vision._version, buf)
     return buf
 
 

@@ -159,6 +159,22 @@ def softmax_rows(x, *, n=None, scale=1.0, colmask=None, rows_per_batch=0, mask_v
     return out
 
 
+def l2_normalize(x32, w=None, b0=None, eps=1e-12):
+    """e = F.normalize(x, p=2, dim=-1) of a contiguous fp32 tensor -> (e fp16, e fp32, dot) with
+    dot[r] = e[r, :] . w + b0 when ``w`` is given (the token bias of the dot-product head, vldyhead.py:818)."""
+    global launch_count
+    _need_cuda(x32, w, b0)
+    D = x32.shape[-1]
+    rows = x32.numel() // D
+    e16 = torch.empty(x32.shape, dtype=torch.float16, device=x32.device)
+    e32 = torch.empty_like(x32)
+    dot = torch.empty(x32.shape[:-1], dtype=torch.float32, device=x32.device) if w is not None else None
+    check(load().mqdet_l2norm_rowdot(_ptr(x32), rows, D, float(eps), _ptr(w), _ptr(b0), _ptr(e16), _ptr(e32), _ptr(dot),
+                                     _stream()), "l2norm_rowdot")
+    launch_count += 1
+    return e16, e32, dot
+
+
 def cast_f16(x):
     global launch_count
     _need_cuda(x)
@@ -263,3 +279,109 @@ def ml_nms(boxes, scores, labels, thresh):
         return torch.empty((0,), dtype=torch.int64, device="cpu")  # reference returns an empty CPU tensor (:19-20)
     keep, num = ml_nms_device(boxes, scores, labels, thresh)
     return keep[: int(num.item())]
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# DyHead vision path
+# ----------------------------------------------------------------------------------------------------------------------
+class Levels:
+    """FPN level table: sizes [(H, W)], row offsets into the concatenated [B, N, C] tensor, device segment tables."""
+
+    def __init__(self, sizes, device):
+        import numpy as np
+        self.sizes = [(int(h), int(w)) for h, w in sizes]
+        self.n = len(self.sizes)
+        hw = np.asarray(self.sizes, dtype=np.int32).reshape(-1, 2)
+        self.hw_host = np.ascontiguousarray(hw)
+        self.hw_ptr = self.hw_host.ctypes.data_as(ctypes.c_void_p)
+        off = [0]
+        for h, w in self.sizes:
+            off.append(off[-1] + h * w)
+        self.off = off
+        self.N = off[-1]
+        self.N1 = self.N - self.sizes[0][0] * self.sizes[0][1]
+        self.seg_all = torch.tensor(off, dtype=torch.int32, device=device)  # levels 0..L-1 over N rows
+        self.seg_tail = torch.tensor([o - off[1] for o in off[1:]], dtype=torch.int32, device=device)  # levels 1..L-1
+        # GAP weights of the align_corners bilinear upsample (level l+1 -> l), normalised to sum 1 per segment:
+        # GAP(up(z)) = sum_q w[q] z[q] with w separable (column sums of the 1-D interpolation matrices)
+        ws = []
+        for l in range(self.n - 1):
+            (H, W), (Hs, Ws) = self.sizes[l], self.sizes[l + 1]
+            ws.append((torch.outer(_upsample_colsum(Hs, H), _upsample_colsum(Ws, W)) / float(H * W)).reshape(-1))
+        self.up_w = torch.cat(ws).float().to(device) if ws else None
+
+
+def _upsample_colsum(n_in, n_out):
+    """column sums of the [n_out, n_in] align_corners=True linear-interpolation matrix (fp32 like ATen)."""
+    import numpy as np
+    w = np.zeros(n_in, dtype=np.float64)
+    scale = np.float32(n_in - 1) / np.float32(n_out - 1) if n_out > 1 else np.float32(0)
+    for i in range(n_out):
+        src = np.float32(scale * np.float32(i))
+        i0 = int(src)
+        i1 = i0 + (1 if i0 < n_in - 1 else 0)
+        lam = float(src - np.float32(i0))
+        w[i0] += 1.0 - lam
+        w[i1] += lam
+    return torch.from_numpy(w)
+
+
+def dcn_cols(x16, om, levels, branch):
+    """x16 [B,N,256] fp16, om [B,N,om_ld] fp32 or None -> fp16 column matrix [B*rows, 2304] for DyConv[branch]."""
+    global launch_count
+    _need_cuda(x16, om)
+    B, N, C = x16.shape
+    rows = levels.N if branch == 1 else levels.N1
+    cols = torch.empty((B * rows, 9 * C), dtype=torch.float16, device=x16.device)
+    check(load().mqdet_dcn_cols(_ptr(x16), _ptr(om), om.shape[-1] if om is not None else 0, levels.hw_ptr, levels.n, B, C,
+                                int(branch), _ptr(cols), _stream()), "dcn_cols")
+    launch_count += 1
+    return cols
+
+
+def chan_stats(y16, seg, B, rows_per_img, row_weights=None):
+    global launch_count
+    nseg = seg.numel() - 1
+    C = y16.shape[-1]
+    partial = torch.empty((int(load().mqdet_chan_stats_floats(B, nseg, C)),), dtype=torch.float32, device=y16.device)
+    check(load().mqdet_chan_stats(_ptr(y16), _ptr(seg), nseg, B, rows_per_img, C, _ptr(row_weights), _ptr(partial),
+                                  _stream()), "chan_stats")
+    launch_count += 1
+    return partial
+
+
+def gn_attn(partial, seg, B, C, groups, weighted, gn_w, gn_b, eps, attn_w, attn_b):
+    global launch_count
+    nseg = seg.numel() - 1
+    affine = torch.empty((B, nseg, 2, C), dtype=torch.float32, device=partial.device)
+    attn = torch.empty((B, nseg), dtype=torch.float32, device=partial.device)
+    check(load().mqdet_gn_attn(_ptr(partial), _ptr(seg), nseg, B, C, groups, int(weighted), _ptr(gn_w), _ptr(gn_b),
+                               float(eps), _ptr(attn_w), _ptr(attn_b), _ptr(affine), _ptr(attn), _stream()), "gn_attn")
+    launch_count += 1
+    return affine, attn
+
+
+def dyconv_combine(y1, y2, y0, aff1, aff2, aff0, at1, at2, at0, levels, B):
+    global launch_count
+    C = y1.shape[-1]
+    mid = torch.empty((B, levels.N, C), dtype=torch.float16, device=y1.device)
+    check(load().mqdet_dyconv_combine(_ptr(y1), _ptr(y2), _ptr(y0), _ptr(aff1), _ptr(aff2), _ptr(aff0), _ptr(at1),
+                                      _ptr(at2), _ptr(at0), levels.hw_ptr, levels.n, B, C, _ptr(mid), _stream()),
+          "dyconv_combine")
+    launch_count += 1
+    return mid
+
+
+def dyrelu(mid, levels, w1, b1, w2, b2):
+    """DyReLU over every level of mid [B,N,256] fp16 -> fp16."""
+    global launch_count
+    B, N, C = mid.shape
+    partial = chan_stats(mid, levels.seg_all, B, N)
+    coef = torch.empty((B, levels.n, 4, C), dtype=torch.float32, device=mid.device)
+    check(load().mqdet_dyrelu_coef(_ptr(partial), _ptr(levels.seg_all), levels.n, B, C, w1.shape[0], _ptr(w1), _ptr(b1),
+                                   _ptr(w2), _ptr(b2), _ptr(coef), _stream()), "dyrelu_coef")
+    out = torch.empty_like(mid)
+    check(load().mqdet_dyrelu_apply(_ptr(mid), _ptr(coef), levels.hw_ptr, levels.n, B, C, _ptr(out), _stream()),
+          "dyrelu_apply")
+    launch_count += 2
+    return out

@@ -1,0 +1,164 @@
+"""Bi-directional image<->text multi-head attention of the VL deep-fusion tower on sm_100a kernels.
+
+Drop-in for maskrcnn_benchmark/utils/fuse_helper.py: ``BiMultiHeadAttention`` (:171-303) and
+``BiAttentionBlockForCheckpoint`` (:344-426), same constructor arguments / parameter names / forward signatures,
+eval mode (dropout and DropPath are identities).
+
+Layout: the 5 FPN levels are kept concatenated as ONE fp16 tensor v [B, N, 256] (P3->P7, row-major (h, w)) — exactly the
+``permute_and_flatten`` + ``cat`` the reference builds at :398-404 — so the tower never converts back to NCHW between
+layers (``forward_flat``).  ``forward`` keeps the reference's NCHW-in / NCHW-out signature for drop-in use.
+
+Every product is a K-major x K-major tcgen05 GEMM; transposed operands are produced by swapping operand roles
+(V^T = W . x^T), never by a transpose kernel:
+    Q  = (LN(v) Wv^T + b) * d^-1/2      [B,N,E]      K  = LN(l) Wl^T + b          [B,T,E]
+    VvT= Wvv LN(v)^T + b (per row)      [B,E,N]      VlT= Wvl LN(l)^T + b         [B,E,T]
+    A  = clamp(Q_h K_h^T)  [B,H,N,T] -> softmax_T(A + mask)   -> out_v = P_v VlT_h^T
+    At = clamp(K_h Q_h^T)  [B,H,T,N] -> softmax_N(At - max)   -> out_l = P_l VvT_h^T
+    v' = LN(v) + gamma_v * (out_v Wov^T + b)       l' = LN(l) + gamma_l * (out_l Wol^T + b)
+"""
+import torch
+from torch import nn
+
+from .. import ops
+from .._lib import VEC_PER_COL, VEC_PER_ROW, MqdetError
+from .weights import f32, w16
+
+
+def _flatten_levels(feats):
+    """[B,C,h,w] x L -> [B, sum(hw), C] (permute_and_flatten + cat, fuse_helper.py:398-404). Data movement only."""
+    return torch.cat([f.flatten(2).transpose(1, 2) for f in feats], dim=1).contiguous()
+
+
+def _split_levels(v, sizes):
+    """[B,N,C] -> list of [B,C,h,w] (:406-412)."""
+    out, start = [], 0
+    B, _, C = v.shape
+    for (h, w) in sizes:
+        out.append(v[:, start:start + h * w].transpose(1, 2).reshape(B, C, h, w).contiguous())
+        start += h * w
+    return out
+
+
+class BiMultiHeadAttention(nn.Module):
+    def __init__(self, v_dim, l_dim, embed_dim, num_heads, dropout=0.1, cfg=None):
+        super().__init__()
+        self.embed_dim = embed_dim
+        self.num_heads = num_heads
+        self.head_dim = embed_dim // num_heads
+        self.v_dim, self.l_dim = v_dim, l_dim
+        assert self.head_dim * num_heads == embed_dim
+        self.scale = self.head_dim ** (-0.5)
+        self.dropout = dropout
+        self.v_proj = nn.Linear(v_dim, embed_dim)
+        self.l_proj = nn.Linear(l_dim, embed_dim)
+        self.values_v_proj = nn.Linear(v_dim, embed_dim)
+        self.values_l_proj = nn.Linear(l_dim, embed_dim)
+        self.out_v_proj = nn.Linear(embed_dim, v_dim)
+        self.out_l_proj = nn.Linear(embed_dim, l_dim)
+        fc = cfg.MODEL.DYHEAD.FUSE_CONFIG
+        self.stable_softmax_2d = fc.STABLE_SOFTMAX_2D
+        self.clamp_min_for_underflow = fc.CLAMP_MIN_FOR_UNDERFLOW
+        self.clamp_max_for_overflow = fc.CLAMP_MAX_FOR_OVERFLOW
+        if self.stable_softmax_2d:
+            raise NotImplementedError("STABLE_SOFTMAX_2D (GroundingDINO fuse_modules.py) is SURVEY.md §8f 'next'")
+        self._reset_parameters()
+
+    def _reset_parameters(self):
+        for m in (self.v_proj, self.l_proj, self.values_v_proj, self.values_l_proj, self.out_v_proj, self.out_l_proj):
+            nn.init.xavier_uniform_(m.weight)
+            m.bias.data.fill_(0)
+
+    @torch.no_grad()
+    def _attend(self, vn16, ln16, mask_l, v_epilogue=None, l_epilogue=None):
+        """vn16 [B,N,256] fp16, ln16 [B,T,768] fp16 (already layer-normed), mask_l [B,T] -> (dv, dl).
+        ``*_epilogue`` = dict(gate=gamma, residual=normed input) fuses the layer-scale + residual into the out-proj."""
+        B, N, Cv = vn16.shape
+        T = ln16.shape[1]
+        H, d, E = self.num_heads, self.head_dim, self.embed_dim
+        dev = vn16.device
+        Np = (N + 7) // 8 * 8
+        clamp = 50000.0 if (self.clamp_min_for_underflow or self.clamp_max_for_overflow) else 0.0
+        q = ops.gemm(vn16.view(B * N, Cv), w16(self.v_proj.weight), bias=f32(self.v_proj.bias), alpha=self.scale,
+                     scale_after_bias=True).view(B, N, H, d)
+        k = ops.gemm(ln16.view(B * T, -1), w16(self.l_proj.weight), bias=f32(self.l_proj.bias)).view(B, T, H, d)
+        vvT = torch.zeros((B, E, Np), dtype=torch.float16, device=dev) if Np != N else \
+            torch.empty((B, E, Np), dtype=torch.float16, device=dev)
+        ops.gemm(w16(self.values_v_proj.weight), vn16, out=vvT[:, :, :N], bias=f32(self.values_v_proj.bias),
+                 bias_mode=VEC_PER_ROW)
+        vlT = ops.gemm(w16(self.values_l_proj.weight), ln16, bias=f32(self.values_l_proj.bias), bias_mode=VEC_PER_ROW)
+
+        qh, kh = q.permute(0, 2, 1, 3), k.permute(0, 2, 1, 3)
+        # image -> text direction
+        A = torch.empty((B, H, N, T), dtype=torch.float16, device=dev)
+        ops.gemm(qh, kh, out=A, clamp=clamp)
+        cm = mask_l.float().contiguous() if mask_l is not None else None
+        Pv = ops.softmax_rows(A, colmask=cm, rows_per_batch=H * N, mask_value=-9e15, keep_add=1.0, out=A)
+        ov = torch.empty((B, N, H, d), dtype=torch.float16, device=dev)
+        ops.gemm(Pv, vlT.view(B, H, d, T), out=ov.permute(0, 2, 1, 3))
+        # text -> image direction (softmax over all N locations, no mask)
+        At = torch.empty((B, H, T, Np), dtype=torch.float16, device=dev)
+        ops.gemm(kh, qh, out=At[..., :N], clamp=clamp)
+        Pl = ops.softmax_rows(At, n=N, out=At)
+        ol = torch.empty((B, T, H, d), dtype=torch.float16, device=dev)
+        ops.gemm(Pl, vvT.view(B, H, d, Np), out=ol.permute(0, 2, 1, 3))
+
+        ve = v_epilogue or {}
+        le = l_epilogue or {}
+        dv = ops.gemm(ov.view(B * N, E), w16(self.out_v_proj.weight), bias=f32(self.out_v_proj.bias),
+                      gate=ve.get("gate"), gate_mode=VEC_PER_COL if ve else 0,
+                      residual=ve["residual"].view(B * N, Cv) if ve else None)
+        dl = ops.gemm(ol.view(B * T, E), w16(self.out_l_proj.weight), bias=f32(self.out_l_proj.bias),
+                      out_dtype=torch.float32, gate=le.get("gate"), gate_mode=VEC_PER_COL if le else 0,
+                      residual=le["residual"].view(B * T, -1) if le else None)
+        return dv.view(B, N, Cv), dl.view(B, T, -1)
+
+    @torch.no_grad()
+    def forward(self, v, l, attention_mask_l=None):
+        """Reference signature (:218): v [B,N,v_dim], l [B,T,l_dim] -> (attn_output_v, attn_output_l) in fp32."""
+        if not v.is_cuda:
+            raise MqdetError("BiMultiHeadAttention: CUDA tensors required (no CPU fallback)")
+        dv, dl = self._attend(ops.cast_f16(v.contiguous()), ops.cast_f16(l.contiguous()), attention_mask_l)
+        return ops.cast_f32(dv), dl
+
+
+class BiAttentionBlockForCheckpoint(nn.Module):
+    def __init__(self, v_dim, l_dim, embed_dim, num_heads, hidden_dim=None, dropout=0.1, drop_path=.0, init_values=1e-4,
+                 cfg=None):
+        super().__init__()
+        self.layer_norm_v = nn.LayerNorm(v_dim)
+        self.layer_norm_l = nn.LayerNorm(l_dim)
+        self.attn = BiMultiHeadAttention(v_dim=v_dim, l_dim=l_dim, embed_dim=embed_dim, num_heads=num_heads,
+                                         dropout=dropout, cfg=cfg)
+        self.drop_path = nn.Identity()  # eval
+        self.gamma_v = nn.Parameter(init_values * torch.ones((v_dim)), requires_grad=True)
+        self.gamma_l = nn.Parameter(init_values * torch.ones((l_dim)), requires_grad=True)
+        self.cfg = cfg
+        if cfg.MODEL.DYHEAD.FUSE_CONFIG.SEPARATE_BIDIRECTIONAL:
+            raise NotImplementedError("SEPARATE_BIDIRECTIONAL is False in every MQ-GLIP config")
+
+    @torch.no_grad()
+    def forward_flat(self, v16, l32, attention_mask_l):
+        """Tower fast path: v16 [B,N,256] fp16 (levels concatenated), l32 [B,T,768] fp32 -> (v' fp16, l' fp32)."""
+        nv, nl = self.layer_norm_v, self.layer_norm_l
+        vn16 = ops.layernorm(v16, f32(nv.weight), f32(nv.bias), nv.eps)
+        ln16, ln32 = ops.layernorm(l32, f32(nl.weight), f32(nl.bias), nl.eps, out16=True, out32=True)
+        # v' = LN(v) + gamma_v * dv ; l' = LN(l) + gamma_l * dl   (residual on the normalised inputs, :420-425)
+        return self.attn._attend(vn16, ln16, attention_mask_l,
+                                 v_epilogue=dict(gate=f32(self.gamma_v), residual=vn16),
+                                 l_epilogue=dict(gate=f32(self.gamma_l), residual=ln32))
+
+    def single_attention_call(self, v, l, attention_mask_l=None, dummy_tensor=None):
+        v2, l2 = self.forward_flat(ops.cast_f16(v.contiguous()), l.float().contiguous(), attention_mask_l)
+        return ops.cast_f32(v2), l2
+
+    @torch.no_grad()
+    def forward(self, q0, q1, q2, q3, q4, l, attention_mask_l=None, dummy_tensor=None):
+        """Reference signature (:377): five [B,256,h,w] maps + l -> 10-tuple (5 maps, new l, 4 x None)."""
+        feats = [q0, q1, q2, q3, q4]
+        if not q0.is_cuda:
+            raise MqdetError("BiAttentionBlockForCheckpoint: CUDA tensors required (no CPU fallback)")
+        sizes = [(f.shape[2], f.shape[3]) for f in feats]
+        v = _flatten_levels(feats)
+        new_v, new_l = self.single_attention_call(v, l, attention_mask_l)
+        lv = _split_levels(new_v, sizes)
+        return lv[0], lv[1], lv[2], lv[3], lv[4], new_l, None, None, None, None

@@ -3,6 +3,8 @@
 Parameters stay fp32 nn.Parameters under the reference's names (state_dict compatible); the tensor-core GEMMs read
 fp16 copies that are (re)built lazily whenever the parameter's storage or version counter changes.
 """
+import weakref
+
 import torch
 
 from .. import ops
@@ -15,7 +17,7 @@ def w16(param, rows=None):
     key = (id(param), rows)
     ent = _cache.get(key)
     ver = (param.data_ptr(), param._version, param.device)
-    if ent is not None and ent[0] == ver:
+    if ent is not None and ent[0] == ver and ent[2]() is param:
         return ent[1]
     src = param.detach()
     if rows is not None:
@@ -24,7 +26,9 @@ def w16(param, rows=None):
         h = src.contiguous()
     else:
         h = ops.cast_f16(src.float().contiguous())
-    _cache[key] = (ver, h)
+    # weak reference: a recycled id()/data_ptr of a dead parameter can never alias a live one, and the fp16 copy is
+    # dropped together with the parameter
+    _cache[key] = (ver, h, weakref.ref(param, lambda _r, k=key: _cache.pop(k, None)))
     return h
 
 

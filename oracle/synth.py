@@ -162,3 +162,41 @@ def vision_queries(positive_map, K, T=256, dim=256, gen=None):
     for ci, (label, toks) in enumerate(sorted(positive_map.items())):
         m[0, ci * K:(ci + 1) * K, toks] = 1.0
     return q, m
+
+
+def dyconv_sd(gen, p="", C=256, sd=None):
+    """DyConv parameters (vldyhead.py:155-204; DYReLU layers/dyrelu.py:38-78).  Livelier than the reference's
+    std-0.01 init so that offsets move by whole pixels, masks vary and the DyReLU/attention branches are exercised."""
+    sd = {} if sd is None else sd
+    for k in range(3):
+        sd[f"{p}DyConv.{k}.conv.weight"] = gen.randn(C, C, 3, 3, scale=0.03)
+        sd[f"{p}DyConv.{k}.conv.bias"] = gen.randn(C, scale=0.05)
+        gen.norm(C, sd, f"{p}DyConv.{k}.bn")
+    sd[p + "AttnConv.1.weight"] = gen.randn(1, C, 1, 1, scale=0.3)
+    sd[p + "AttnConv.1.bias"] = gen.randn(1, scale=0.5)
+    sd[p + "relu.fc.0.weight"] = gen.randn(C // 4, C, scale=0.2)
+    sd[p + "relu.fc.0.bias"] = gen.randn(C // 4, scale=0.1)
+    sd[p + "relu.fc.2.weight"] = gen.randn(4 * C, C // 4, scale=0.3)
+    sd[p + "relu.fc.2.bias"] = gen.randn(4 * C, scale=0.3)
+    sd[p + "offset.weight"] = gen.randn(27, C, 3, 3, scale=0.02)
+    sd[p + "offset.bias"] = gen.randn(27, scale=0.5)
+    return sd
+
+
+def vldyhead_sd(gen, num_convs=6, C=256, l_dim=768, num_classes=80):
+    """VLDyHead parameters (vldyhead.py:594-767) with the reference's key names."""
+    sd = {}
+    for i in range(num_convs):
+        bi_attention_sd(gen, f"dyhead_tower.{3 * i}.b_attn.", C, l_dim, 2048, num_convs, sd)
+        bert_layer_sd(gen, f"dyhead_tower.{3 * i + 1}.", l_dim, 4 * l_dim, sd)
+        dyconv_sd(gen, f"dyhead_tower.{3 * i + 2}.", C, sd)
+    sd["cls_logits.weight"] = gen.randn(num_classes, C, 1, 1, scale=0.01)
+    sd["cls_logits.bias"] = torch.full((num_classes,), -math.log(99.0))
+    sd["bbox_pred.weight"] = gen.randn(4, C, 1, 1, scale=0.05)
+    sd["bbox_pred.bias"] = gen.randn(4, scale=0.1)
+    sd["centerness.weight"] = gen.randn(1, C, 1, 1, scale=0.05)
+    sd["centerness.bias"] = gen.randn(1, scale=0.1)
+    dot_head_sd(gen, "", l_dim, C, sd)
+    for l in range(5):
+        sd[f"scales.{l}.scale"] = torch.tensor([1.0 + 0.1 * l])
+    return sd

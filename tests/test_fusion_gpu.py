@@ -1,0 +1,103 @@
+"""GPU parity of the VL deep-fusion tower: BiAttention fusion, DyConv (DCNv2 + GN + scale attention + DyReLU) and the
+full VLDyHead (6 x [fusion, BERT layer, DyConv] + dot-product token head) against the CPU oracle."""
+import os
+
+import pytest
+import torch
+
+from util import FP16_TOL, ROOT, assert_close, load_sd
+
+pytestmark = pytest.mark.gpu
+
+SIZES = [(20, 28), (10, 14), (5, 7), (3, 4), (2, 2)]
+
+
+def test_bi_attention_vs_oracle_and_golden(dev):
+    from mqdet_b200.config import mq_glip_t_cfg
+    from mqdet_b200.utils.fuse_helper import BiAttentionBlockForCheckpoint
+    from oracle import make_golden, restate
+    c = make_golden.case_inputs("bi_attention")
+    blk = BiAttentionBlockForCheckpoint(v_dim=256, l_dim=768, embed_dim=2048, num_heads=8, hidden_dim=3072, dropout=0.1,
+                                        drop_path=0.0, init_values=1.0 / 6, cfg=mq_glip_t_cfg())
+    blk = load_sd(blk, c["sd"]).to(dev).eval()
+    v = restate.flatten_levels(c["feats"])
+    v_ref, l_ref = restate.bi_attention(v, c["l"], c["mask"], c["sd"])
+    out = blk(*[f.to(dev) for f in c["feats"]], c["l"].to(dev), c["mask"].to(dev), None)
+    v_out = restate.flatten_levels([o.cpu() for o in out[:5]])
+    assert_close(v_out, v_ref, what="fusion: visual stream")
+    assert_close(out[5], l_ref, what="fusion: language stream")
+    assert out[6] is None and len(out) == 10
+    fx = torch.load(os.path.join(ROOT, "tests", "golden", "bi_attention.pt"))
+    for key, got in (("v", v_out), ("l", out[5].cpu())):
+        g = make_golden.sub(got.float(), *fx["subsample"][key])
+        err = (g - fx[key]).abs().max().item()
+        assert err <= FP16_TOL * fx[key + "_absmax"] + FP16_TOL, (key, err)
+
+
+def test_dcn_cols_plain_equals_unfold(dev):
+    """om == NULL: the sampling stage is a plain 3x3/pad-1 im2col with k = tap*C + c."""
+    from mqdet_b200 import ops
+    g = torch.Generator().manual_seed(2)
+    feats = [torch.randn(2, 256, h, w, generator=g) for h, w in SIZES]
+    lv = ops.Levels(SIZES, dev)
+    x16 = torch.cat([f.flatten(2).transpose(1, 2) for f in feats], 1).half().to(dev).contiguous()
+    cols = ops.dcn_cols(x16, None, lv, 1).float().cpu().view(2, lv.N, 9, 256)
+    for l, f in enumerate(feats):
+        h, w = SIZES[l]
+        u = torch.nn.functional.unfold(f.half().float(), 3, padding=1).view(2, 256, 9, h * w).permute(0, 3, 2, 1)
+        assert torch.equal(cols[:, lv.off[l]:lv.off[l + 1]], u)
+
+
+def test_dyconv(dev):
+    from mqdet_b200 import ops
+    from mqdet_b200.modeling.rpn.vldyhead import Conv3x3Norm, DyConv
+    from oracle import restate, synth
+    gen = synth.Gen(77)
+    sd = synth.dyconv_sd(gen)
+    feats = [gen.randn(2, 256, h, w) for h, w in SIZES]
+    ref = restate.flatten_levels(restate.dyconv(feats, sd))
+    conv_func = lambda i, o, s: Conv3x3Norm(i, o, s, deformable=True, bn_type=["gn", 16])  # noqa: E731
+    mod = load_sd(DyConv(256, 256, conv_func=conv_func, use_dyrelu=True, use_dyfuse=True, use_deform=True), sd)
+    mod = mod.to(dev).eval()
+    lv = ops.Levels(SIZES, dev)
+    x16 = restate.flatten_levels(feats).half().to(dev).contiguous()
+    out = mod.forward_flat(x16, lv)
+    assert_close(out, ref, 3e-3, "DyConv (fp16 activations)")
+    # reference-facing dict API
+    o2 = mod({"visual": [f.to(dev) for f in feats], "lang": None})["visual"]
+    assert [tuple(o.shape) for o in o2] == [tuple(f.shape) for f in feats]
+    assert_close(restate.flatten_levels([o.cpu() for o in o2]), ref, 3e-3, "DyConv dict API")
+
+
+def test_vldyhead_tower(dev):
+    from mqdet_b200 import ops
+    from mqdet_b200.config import mq_glip_t_cfg
+    from mqdet_b200.modeling.rpn.vldyhead import VLDyHead
+    from oracle import restate, synth
+    gen = synth.Gen(78)
+    nconv = 6
+    sd = synth.vldyhead_sd(gen, nconv)
+    B, T = 2, 256
+    feats = [gen.randn(B, 256, h, w) for h, w in SIZES]
+    hidden = gen.randn(B, T, 768)
+    masks = torch.ones(B, T, dtype=torch.long)
+    masks[0, 120:] = 0
+    masks[1, 31:] = 0
+    ref = restate.vl_dyhead(feats, hidden, masks, sd, nconv)
+    head = load_sd(VLDyHead(mq_glip_t_cfg()), sd).to(dev).eval()
+    lv = ops.Levels(SIZES, dev)
+    v16 = restate.flatten_levels(feats).half().to(dev).contiguous()
+    r = head.forward_flat(v16, lv, hidden.to(dev), masks.to(dev))
+    # 18 chained fp16 stages: the bound is the north-star 1e-3 scaled by sqrt(#stages) ~ 4e-3 relative
+    assert_close(r["hidden"], ref["hidden"], 4e-3, "tower: language stream")
+    assert_close(r["visual"], restate.flatten_levels(ref["visual"]), 6e-3, "tower: visual stream")
+    assert_close(r["dot_product_logits"], ref["dot_product_logits"], 4e-3, "tower: dot-product logits")
+    ref_reg = restate.flatten_levels(ref["bbox_reg"])
+    scale = torch.cat([torch.full((h * w,), float(sd[f"scales.{l}.scale"])) for l, (h, w) in enumerate(SIZES)])
+    assert_close(r["reg_ctr"][..., :4].cpu() * scale[None, :, None], ref_reg, 6e-3, "tower: bbox regression")
+    assert_close(r["reg_ctr"][..., 4].cpu(), restate.flatten_levels(ref["centerness"])[..., 0], 6e-3, "tower: centerness")
+    # reference-facing tuple API
+    out = head([f.to(dev) for f in feats], {"hidden": hidden.to(dev), "masks": masks.to(dev)})
+    assert len(out) == 10 and len(out[6]) == 5 and out[6][0].shape == (B, 20 * 28, T)
+    assert_close(torch.cat([o.cpu() for o in out[6]], 1), ref["dot_product_logits"], 4e-3, "tuple API logits")
+    assert_close(restate.flatten_levels([o.cpu() for o in out[1]]), ref_reg, 6e-3, "tuple API bbox_reg")

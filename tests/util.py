@@ -20,6 +20,21 @@ def rel_err(out, ref):
     return (out - ref).abs().max().item() / (ref.abs().max().item() + 1e-12)
 
 
+_records = []
+
+
+def _dump_records():
+    if _records and os.path.isdir(os.path.join(ROOT, "gpurun_out")):
+        import json
+        with open(os.path.join(ROOT, "gpurun_out", "parity_errors.json"), "w") as f:
+            json.dump(_records, f, indent=1)
+
+
+import atexit  # noqa: E402
+
+atexit.register(_dump_records)
+
+
 def assert_close(out, ref, tol=FP16_TOL, what=""):
     out = out.detach().float().cpu()
     ref = ref.detach().float().cpu()
@@ -27,6 +42,8 @@ def assert_close(out, ref, tol=FP16_TOL, what=""):
     assert torch.isfinite(out).all(), f"{what}: non-finite output"
     err = (out - ref).abs().max().item()
     bound = tol * ref.abs().max().item() + tol
+    _records.append(dict(what=what, max_abs_err=err, bound=bound, ref_absmax=ref.abs().max().item(),
+                         rel=err / (ref.abs().max().item() + 1e-12)))
     assert err <= bound, f"{what}: max|err| {err:.3e} > {bound:.3e} (max|ref| {ref.abs().max().item():.3e})"
     return err
 
