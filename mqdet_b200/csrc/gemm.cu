@@ -177,110 +177,133 @@ __global__ void __launch_bounds__(256) gemm_tc_kernel(const __grid_constant__ CU
     }
   } else if (warp >= 4) {
     // ---- epilogue ------------------------------------------------------------------------------------------
-    // phase 1: TMEM -> registers (thread == output row) -> alpha/bias/act/clamp/gate -> fp32 staging tile in the
-    //          (now idle) operand ring, rows padded by 16 B so the float4 stores are bank-conflict free
-    // phase 2: staging -> (+ residual, read coalesced) -> 16-byte coalesced global stores, lanes along columns
+    // phase 1: TMEM -> registers (thread == output row) -> RAW fp32 accumulators into a staging tile that re-uses the
+    //          (now idle) operand ring; rows padded by 16 B so the float4 stores are bank-conflict free.
+    // phase 2: lanes along columns (8 per lane, fixed for the whole tile): per-column bias/gate are loaded once,
+    //          then a rolled loop over rows applies alpha/bias/act/clamp/gate/residual and issues 16-byte coalesced
+    //          stores.  The whole epilogue is ~400 instructions: it is executed once per CTA, so code size (I-cache
+    //          misses), not ALU work, is what it is optimised for.
     const int ew = warp - 4;  // == warp % 4 -> TMEM lane quarter this warp may access
     mbar_wait(tmem_full_bar, 0);
     tc_fence_after();
     constexpr int LDS = BN + 4;  // staging row stride in floats
     float* stage = reinterpret_cast<float*>(smem);
-    const int r_local = ew * 32 + lane;
-    const long row = (long)m_tile * BM + r_local;
-    float gate_scalar = 1.f;
-    if (p.gate_mode == MQDET_VEC_SCALAR) {
-      gate_scalar = p.gate[0];
-      if (p.gate_tanh) gate_scalar = tanhf(gate_scalar);
-    }
+    {
+      float4* dst = reinterpret_cast<float4*>(stage + (ew * 32 + lane) * LDS);
 #pragma unroll 1
-    for (int c0 = 0; c0 < BN; c0 += 32) {
-      uint32_t r[32];
-      tmem_ld_32x32(tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)c0, r);
-      tmem_ld_wait();
-      const long col0 = (long)n_tile * BN + c0;
-      float4* dst = reinterpret_cast<float4*>(stage + r_local * LDS + c0);
-      const bool live = row < p.M && col0 < p.N;
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        uint32_t r[32];
+        tmem_ld_32x32(tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)c0, r);
+        tmem_ld_wait();
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        float4 v;
-        if (live) {
-          const long c = col0 + 4 * i;
-          v.x = (c + 0 < p.N) ? epi_pre(p, __uint_as_float(r[4 * i + 0]), row, c + 0, z1, z2, gate_scalar) : 0.f;
-          v.y = (c + 1 < p.N) ? epi_pre(p, __uint_as_float(r[4 * i + 1]), row, c + 1, z1, z2, gate_scalar) : 0.f;
-          v.z = (c + 2 < p.N) ? epi_pre(p, __uint_as_float(r[4 * i + 2]), row, c + 2, z1, z2, gate_scalar) : 0.f;
-          v.w = (c + 3 < p.N) ? epi_pre(p, __uint_as_float(r[4 * i + 3]), row, c + 3, z1, z2, gate_scalar) : 0.f;
-        } else {
-          v = make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-        dst[i] = v;
+        for (int i = 0; i < 8; ++i)
+          dst[c0 / 4 + i] = make_float4(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1]),
+                                        __uint_as_float(r[4 * i + 2]), __uint_as_float(r[4 * i + 3]));
       }
     }
     tc_fence_before();
     asm volatile("bar.sync 1, 128;" ::: "memory");  // the 4 epilogue warps only
 
-    constexpr int LPR = BN / 8;        // lanes per row (8 columns each)
-    constexpr int RPI = 32 / LPR * 4;  // rows per iteration over the 4 warps
-    const bool c_vec = ((p.ldc & 7) == 0) && ((p.c_b1 & 7) == 0) && ((p.c_b2 & 7) == 0) &&
-                       ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0);
-    const bool r_vec = p.R && ((p.ldr & 7) == 0) && ((p.r_b1 & 7) == 0) && ((p.r_b2 & 7) == 0) &&
-                       ((reinterpret_cast<uintptr_t>(p.R) & 15) == 0);
+    constexpr int LPR = BN / 8;  // lanes per row (8 columns each)
+    constexpr int RPW = 32 / LPR;  // rows per warp per iteration
     const int lc = (lane % LPR) * 8;
     const long col = (long)n_tile * BN + lc;
-#pragma unroll 1
-    for (int r0 = 0; r0 < BM; r0 += RPI) {
-      const int rl = r0 + ew * (32 / LPR) + lane / LPR;
-      const long grow = (long)m_tile * BM + rl;
-      if (grow >= p.M || col >= p.N) continue;
-      const float4 s0 = *reinterpret_cast<const float4*>(stage + rl * LDS + lc);
-      const float4 s1 = *reinterpret_cast<const float4*>(stage + rl * LDS + lc + 4);
-      float v[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+    if (col < p.N) {
       const bool full = col + 8 <= p.N;
-      if (p.R) {
-        if (full && r_vec) {
-          const long off = z1 * p.r_b1 + z2 * p.r_b2 + grow * p.ldr + col;
-          if (p.r_dtype == MQDET_F32) {
-            const float4 a = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.R) + off);
-            const float4 b = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.R) + off + 4);
-            v[0] += a.x; v[1] += a.y; v[2] += a.z; v[3] += a.w;
-            v[4] += b.x; v[5] += b.y; v[6] += b.z; v[7] += b.w;
-          } else {
-            const uint4 u = *reinterpret_cast<const uint4*>(reinterpret_cast<const __half*>(p.R) + off);
-            const __half2* h = reinterpret_cast<const __half2*>(&u);
+      const bool c_vec = full && ((p.ldc & 7) == 0) && ((p.c_b1 & 7) == 0) && ((p.c_b2 & 7) == 0) &&
+                         ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0);
+      const bool r_vec = full && p.R && ((p.ldr & 7) == 0) && ((p.r_b1 & 7) == 0) && ((p.r_b2 & 7) == 0) &&
+                         ((reinterpret_cast<uintptr_t>(p.R) & 15) == 0);
+      float bcol[8], gcol[8];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const float2 f = __half22float2(h[i]);
-              v[2 * i] += f.x;
-              v[2 * i + 1] += f.y;
-            }
-          }
-        } else {
-#pragma unroll
-          for (int i = 0; i < 8; ++i)
-            if (col + i < p.N) v[i] += ld_residual(p, grow, col + i, z1, z2);
-        }
+      for (int i = 0; i < 8; ++i) {
+        bcol[i] = 0.f;
+        gcol[i] = 1.f;
       }
-      if (full && c_vec) {
-        const long off = z1 * p.c_b1 + z2 * p.c_b2 + grow * p.ldc + col;
-        if (p.c_dtype == MQDET_F32) {
-          float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.C) + off);
-          dst[0] = make_float4(v[0], v[1], v[2], v[3]);
-          dst[1] = make_float4(v[4], v[5], v[6], v[7]);
-        } else {
-          __half2 h0 = __floats2half2_rn(v[0], v[1]);
-          __half2 h1 = __floats2half2_rn(v[2], v[3]);
-          __half2 h2 = __floats2half2_rn(v[4], v[5]);
-          __half2 h3 = __floats2half2_rn(v[6], v[7]);
-          uint4 u;
-          u.x = *reinterpret_cast<uint32_t*>(&h0);
-          u.y = *reinterpret_cast<uint32_t*>(&h1);
-          u.z = *reinterpret_cast<uint32_t*>(&h2);
-          u.w = *reinterpret_cast<uint32_t*>(&h3);
-          *reinterpret_cast<uint4*>(reinterpret_cast<__half*>(p.C) + off) = u;
-        }
-      } else {
+      if (p.bias_mode == MQDET_VEC_PER_COL) {
+        const float* bp = p.bias + z1 * p.bias_b1 + z2 * p.bias_b2 + col;
 #pragma unroll
         for (int i = 0; i < 8; ++i)
-          if (col + i < p.N) store_one(p, v[i], grow, col + i, z1, z2);
+          if (col + i < p.N) bcol[i] = bp[i];
+      }
+      if (p.gate_mode == MQDET_VEC_PER_COL) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          if (col + i < p.N) gcol[i] = p.gate_tanh ? tanhf(p.gate[col + i]) : p.gate[col + i];
+      } else if (p.gate_mode == MQDET_VEC_SCALAR) {
+        const float g = p.gate_tanh ? tanhf(p.gate[0]) : p.gate[0];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) gcol[i] = g;
+      }
+      const long c_base = z1 * p.c_b1 + z2 * p.c_b2 + col;
+      const long r_base = z1 * p.r_b1 + z2 * p.r_b2 + col;
+#pragma unroll 1
+      for (int rl = ew * RPW + lane / LPR; rl < BM; rl += 4 * RPW) {
+        const long grow = (long)m_tile * BM + rl;
+        if (grow >= p.M) break;
+        const float4 s0 = *reinterpret_cast<const float4*>(stage + rl * LDS + lc);
+        const float4 s1 = *reinterpret_cast<const float4*>(stage + rl * LDS + lc + 4);
+        float v[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+        float brow = 0.f, grow_g = 1.f;
+        if (p.bias_mode == MQDET_VEC_PER_ROW) brow = p.bias[z1 * p.bias_b1 + z2 * p.bias_b2 + grow];
+        if (p.gate_mode == MQDET_VEC_PER_ROW) grow_g = p.gate_tanh ? tanhf(p.gate[grow]) : p.gate[grow];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float b = bcol[i] + brow;
+          float t = p.scale_after_bias ? p.alpha * (v[i] + b) : fmaf(p.alpha, v[i], b);
+          if (p.act == MQDET_ACT_GELU)
+            t = gelu_erf(t);
+          else if (p.act == MQDET_ACT_RELU)
+            t = fmaxf(t, 0.f);
+          if (p.clamp > 0.f) t = fminf(fmaxf(t, -p.clamp), p.clamp);
+          v[i] = t * gcol[i] * grow_g;
+        }
+        if (p.R) {
+          if (r_vec) {
+            if (p.r_dtype == MQDET_F32) {
+              const float* rp = reinterpret_cast<const float*>(p.R) + r_base + grow * p.ldr;
+              const float4 a = *reinterpret_cast<const float4*>(rp);
+              const float4 b = *reinterpret_cast<const float4*>(rp + 4);
+              v[0] += a.x; v[1] += a.y; v[2] += a.z; v[3] += a.w;
+              v[4] += b.x; v[5] += b.y; v[6] += b.z; v[7] += b.w;
+            } else {
+              const uint4 u = *reinterpret_cast<const uint4*>(reinterpret_cast<const __half*>(p.R) + r_base + grow * p.ldr);
+              const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const float2 f = __half22float2(h[i]);
+                v[2 * i] += f.x;
+                v[2 * i + 1] += f.y;
+              }
+            }
+          } else {
+#pragma unroll 1
+            for (int i = 0; i < 8; ++i)
+              if (col + i < p.N) v[i] += ld_residual(p, grow, col + i, z1, z2);
+          }
+        }
+        if (c_vec) {
+          if (p.c_dtype == MQDET_F32) {
+            float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.C) + c_base + grow * p.ldc);
+            dst[0] = make_float4(v[0], v[1], v[2], v[3]);
+            dst[1] = make_float4(v[4], v[5], v[6], v[7]);
+          } else {
+            __half2 h0 = __floats2half2_rn(v[0], v[1]);
+            __half2 h1 = __floats2half2_rn(v[2], v[3]);
+            __half2 h2 = __floats2half2_rn(v[4], v[5]);
+            __half2 h3 = __floats2half2_rn(v[6], v[7]);
+            uint4 u;
+            u.x = *reinterpret_cast<uint32_t*>(&h0);
+            u.y = *reinterpret_cast<uint32_t*>(&h1);
+            u.z = *reinterpret_cast<uint32_t*>(&h2);
+            u.w = *reinterpret_cast<uint32_t*>(&h3);
+            *reinterpret_cast<uint4*>(reinterpret_cast<__half*>(p.C) + c_base + grow * p.ldc) = u;
+          }
+        } else {
+#pragma unroll 1
+          for (int i = 0; i < 8; ++i)
+            if (col + i < p.N) store_one(p, v[i], grow, col + i, z1, z2);
+        }
       }
     }
   }

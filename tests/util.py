@@ -35,7 +35,7 @@ import atexit  # noqa: E402
 atexit.register(_dump_records)
 
 
-def assert_close(out, ref, tol=FP16_TOL, what=""):
+def assert_close(out, ref, tol=FP16_TOL, what="", defer=None):
     out = out.detach().float().cpu()
     ref = ref.detach().float().cpu()
     assert out.shape == ref.shape, f"{what}: shape {tuple(out.shape)} vs {tuple(ref.shape)}"
@@ -43,7 +43,12 @@ def assert_close(out, ref, tol=FP16_TOL, what=""):
     err = (out - ref).abs().max().item()
     bound = tol * ref.abs().max().item() + tol
     _records.append(dict(what=what, max_abs_err=err, bound=bound, ref_absmax=ref.abs().max().item(),
-                         rel=err / (ref.abs().max().item() + 1e-12)))
+                         rel=err / (ref.abs().max().item() + 1e-12), mean_abs_err=(out - ref).abs().mean().item(),
+                         ref_absmean=ref.abs().mean().item()))
+    if defer is not None:
+        if err > bound:
+            defer.append(f"{what}: max|err| {err:.3e} > {bound:.3e}")
+        return err
     assert err <= bound, f"{what}: max|err| {err:.3e} > {bound:.3e} (max|ref| {ref.abs().max().item():.3e})"
     return err
 
