@@ -180,6 +180,59 @@ int mqdet_dyrelu_coef(const float* partial, const int32_t* seg_off_dev, int64_t 
 int mqdet_dyrelu_apply(const void* mid, const float* coef, const int32_t* level_hw, int64_t nlev, int64_t B, int64_t C,
                        void* out, void* stream);
 
+/* ---- ATSS post-processing (rpn/inference.py:620-769), device-resident, no host synchronisation ------------------
+ * logits [B,N,T] (fp16/fp32), reg_ctr [B,N,5] fp32 (4 box deltas before the per-level Scale, 1 centerness logit),
+ * tokmap_dev int32 [C][max_tok] token positions of class c+1 padded with -1 (the positive map), level tables on
+ * the HOST (level_hw int32 [nlev][2], strides / base_anchors [nlev][4] / reg_scales [nlev] floats).
+ * Per (image, level): sigmoid -> class mean -> score > pre_nms_thresh -> rank = score*sigmoid(ctr) -> exact top-k
+ * (ties by ascending (location, class)) -> BoxCoder.decode against the generated anchor -> clip -> sqrt(rank).
+ * Outputs (row stride out_stride >= nlev*topk per image): per-level blocks out_* at [l*topk, ...), level_counts
+ * [B][nlev]; dense concatenation cat_* (level 0 first) with totals[B].  out_key (optional) = level<<40|loc<<12|cls.
+ * cand_ws: mqdet_atss_workspace_bytes(...) bytes. */
+int64_t mqdet_atss_workspace_bytes(const int32_t* level_hw, int64_t nlev, int64_t C, int64_t B);
+int mqdet_atss_candidates(const void* logits, int logits_dtype, const float* reg_ctr, const int32_t* tokmap_dev, int64_t C,
+                          int64_t max_tok, int64_t T, const int32_t* level_hw, int64_t nlev, const float* strides,
+                          const float* base_anchors, const float* reg_scales, int64_t B, float pre_nms_thresh, int64_t topk,
+                          int64_t out_stride, float img_w, float img_h, void* cand_ws, int32_t* level_counts,
+                          float* out_boxes, float* out_scores, float* out_labels, int64_t* out_key, float* cat_boxes,
+                          float* cat_scores, float* cat_labels, int32_t* totals, void* stream);
+
+/* Batched multi-label NMS: rows of n_max (multiple of 256) candidates per image, counts on the device. */
+int64_t mqdet_ml_nms_batched_workspace_bytes(int64_t B, int64_t n_max);
+int mqdet_ml_nms_batched(const float* boxes, const float* scores, const float* labels, const int32_t* counts_dev, int64_t B,
+                         int64_t n_max, float thresh, int64_t max_det, int64_t* keep_out, int32_t* num_keep, void* workspace,
+                         void* stream);
+
+/* det[b][i][0:6] = (x1,y1,x2,y2,score,label) of kept candidate i (< num_keep[b]), zero-padded to max_out rows:
+ * the fixed-shape per-image result that is copied to the host / all-gathered over NCCL. */
+int mqdet_gather_detections(const float* boxes, const float* scores, const float* labels, const int64_t* keep,
+                            const int32_t* num_keep, int64_t B, int64_t n_max, int64_t max_out, float* det, void* stream);
+
+/* Anchors of one FPN level (anchor_generator.py:72-109): base_anchor (HOST float[4]) shifted by (x*stride, y*stride);
+ * visibility (optional uint8) = fully inside the image (STRADDLE_THRESH 0). */
+int mqdet_anchors(float* out, uint8_t* visibility, int64_t grid_h, int64_t grid_w, float stride, const float* base_anchor,
+                  float img_w, float img_h, void* stream);
+
+/* ---- Swin backbone / FPN glue kernels (modeling/backbone/swint.py, fpn.py) ---------------------------------------
+ * Token layout [B][H*W][C] row-major. */
+/* PatchEmbed input gather (swint.py:393-431): image fp32 NCHW [B,3,H,W] -> fp16 [B*ceil(H/4)*ceil(W/4), 48]. */
+int mqdet_patchify4(const float* img, int64_t B, int64_t H, int64_t W, void* out, void* stream);
+/* (S)W-MSA core (swint.py:111-142,186-242): qkv fp16 [B*H*W, 3C] -> out fp16 [B*H*W, C]; pads to a multiple of the
+ * window with qkv_bias rows, cyclic shift + -100 region mask by index math, bias_dense fp32 [heads][49][49]. */
+int mqdet_swin_window_attn(const void* qkv, const float* qkv_bias, const float* bias_dense, int64_t B, int64_t H, int64_t W,
+                           int64_t heads, int64_t window, int64_t shift, float scale, void* out, void* stream);
+/* PatchMerging gather + LayerNorm(4C) (swint.py:256-284): x fp32 [B,H*W,C] -> fp16 [B*ceil(H/2)*ceil(W/2), 4C]. */
+int mqdet_patch_merge_ln(const float* x, int64_t B, int64_t H, int64_t W, int64_t C, const float* gamma, const float* beta,
+                         float eps, void* out, void* stream);
+/* FPN top-down merge (fpn.py:88-95): out = lateral + nearest_upsample(top); fp16 [B,H*W,C] / [B,Hs*Ws,C]. */
+int mqdet_upsample_add(const void* lateral, const void* top, int64_t B, int64_t H, int64_t W, int64_t Hs, int64_t Ws,
+                       int64_t C, void* out, void* stream);
+/* Plain 3x3 / pad 1 / stride {1,2} im2col of fp16 NHWC [B][H*W][C] (batch stride in elements) -> [B*Ho*Wo][9C]. */
+int mqdet_im2col3x3(const void* x, int64_t x_batch_stride, int64_t B, int64_t H, int64_t W, int64_t C, int64_t stride,
+                    int relu_in, void* cols, void* stream);
+/* AvgPool2d(2) of every pyramid level + concat (generalized_vl_rcnn_new.py:291-293): fp16 [B,N,C] -> fp32 [B,I,C]. */
+int mqdet_avgpool2_levels(const void* x, const int32_t* level_hw, int64_t nlev, int64_t B, int64_t C, float* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

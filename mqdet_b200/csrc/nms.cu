@@ -29,8 +29,15 @@ __device__ __forceinline__ float dev_iou(const float* a, const float* b) {
 }
 
 // keys: score descending, ties by ascending original index (== a stable descending sort).
-__global__ void __launch_bounds__(1024) argsort_desc_kernel(const float* __restrict__ scores, int n, long long* __restrict__ order) {
+__global__ void __launch_bounds__(1024) argsort_desc_kernel(const float* __restrict__ scores, int n, long long* __restrict__ order,
+                                                            const int* __restrict__ n_arr, int n_max) {
   extern __shared__ unsigned long long keys[];
+  if (n_arr) {  // batched: one CTA per image, rows of n_max
+    n = min(n_arr[blockIdx.x], n_max);
+    scores += (long)blockIdx.x * n_max;
+    order += (long)blockIdx.x * n_max;
+    if (n == 0) return;
+  }
   int np2 = 1;
   while (np2 < n) np2 <<= 1;
   for (int i = threadIdx.x; i < np2; i += blockDim.x) {
@@ -66,8 +73,14 @@ __global__ void __launch_bounds__(1024) argsort_desc_kernel(const float* __restr
 // gathers boxes into sorted [n,6] rows (x1,y1,x2,y2,score,label) — the layout ml_nms.cu works on.
 __global__ void nms_gather_kernel(const float* __restrict__ boxes, const float* __restrict__ scores,
                                   const float* __restrict__ labels, const long long* __restrict__ order, int n,
-                                  float* __restrict__ sorted) {
+                                  float* __restrict__ sorted, const int* __restrict__ n_arr, int n_max) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n_arr) {
+    const int b = blockIdx.y;
+    n = min(n_arr[b], n_max);
+    boxes += (long)b * n_max * 4; scores += (long)b * n_max; labels += (long)b * n_max; order += (long)b * n_max;
+    sorted += (long)b * n_max * 6;
+  }
   if (i >= n) return;
   long long o = order[i];
   sorted[i * 6 + 0] = boxes[o * 4 + 0];
@@ -79,10 +92,17 @@ __global__ void nms_gather_kernel(const float* __restrict__ boxes, const float* 
 }
 
 __global__ void __launch_bounds__(64) nms_mask_kernel(int n, float thresh, const float* __restrict__ sorted,
-                                                      unsigned long long* __restrict__ mask) {
+                                                      unsigned long long* __restrict__ mask, const int* __restrict__ n_arr,
+                                                      int n_max) {
   const int row_start = blockIdx.y, col_start = blockIdx.x;
+  if (n_arr) {
+    const int b = blockIdx.z;
+    n = min(n_arr[b], n_max);
+    sorted += (long)b * n_max * 6;
+    mask += (long)b * n_max * ((n_max + 63) / 64);
+  }
   const int col_blocks = (n + 63) / 64;
-  if (col_start < row_start) {  // lower triangle is never read by the scan
+  if (col_start < row_start || row_start >= col_blocks || col_start >= col_blocks) {  // lower triangle is never read
     return;
   }
   const int row_size = min(n - row_start * 64, 64);
@@ -108,7 +128,15 @@ __global__ void __launch_bounds__(64) nms_mask_kernel(int n, float thresh, const
 __global__ void __launch_bounds__(256) nms_scan_kernel(int n, const unsigned long long* __restrict__ mask,
                                                        const long long* __restrict__ order, const float* __restrict__ sorted,
                                                        int max_det, unsigned char* __restrict__ flags,
-                                                       float* __restrict__ kth_score, int* __restrict__ n_kept_sorted) {
+                                                       float* __restrict__ kth_score, int* __restrict__ n_kept_sorted,
+                                                       const int* __restrict__ n_arr, int n_max) {
+  if (n_arr) {
+    const int b = blockIdx.x;
+    n = min(n_arr[b], n_max);
+    mask += (long)b * n_max * ((n_max + 63) / 64);
+    order += (long)b * n_max; sorted += (long)b * n_max * 6; flags += (long)b * n_max;
+    kth_score += b; n_kept_sorted += b;
+  }
   __shared__ unsigned long long remv[NMS_MAX_BLOCKS];
   __shared__ unsigned long long diag[64];
   __shared__ unsigned long long keepbits;
@@ -162,7 +190,14 @@ __global__ void __launch_bounds__(1024) nms_compact_kernel(int n, const unsigned
                                                            const float* __restrict__ scores, int max_det,
                                                            const float* __restrict__ kth_score,
                                                            const int* __restrict__ n_kept_sorted,
-                                                           long long* __restrict__ keep_out, int* __restrict__ num_keep) {
+                                                           long long* __restrict__ keep_out, int* __restrict__ num_keep,
+                                                           const int* __restrict__ n_arr, int n_max) {
+  if (n_arr) {
+    const int b = blockIdx.x;
+    n = min(n_arr[b], n_max);
+    flags += (long)b * n_max; scores += (long)b * n_max; keep_out += (long)b * n_max;
+    kth_score += b; n_kept_sorted += b; num_keep += b;
+  }
   __shared__ int warp_tot[32];
   __shared__ int running;
   if (threadIdx.x == 0) running = 0;
@@ -210,7 +245,7 @@ extern "C" int mqdet_argsort_desc(const float* scores, int64_t n, int64_t* order
     cudaFuncSetAttribute(argsort_desc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, NMS_MAX_N * 8);
     attr = true;
   }
-  argsort_desc_kernel<<<1, 1024, (size_t)np2 * 8, (cudaStream_t)stream>>>(scores, (int)n, (long long*)order);
+  argsort_desc_kernel<<<1, 1024, (size_t)np2 * 8, (cudaStream_t)stream>>>(scores, (int)n, (long long*)order, nullptr, 0);
   return check_launch("argsort_desc_kernel");
 }
 
@@ -242,9 +277,51 @@ extern "C" int mqdet_ml_nms(const float* boxes, const float* scores, const float
   float* kth = (float*)ws;
   int* nkept = (int*)(ws + 16);
   cudaMemsetAsync(flags, 0, (size_t)n, st);
-  nms_gather_kernel<<<cdiv(n, 256), 256, 0, st>>>(boxes, scores, labels, (const long long*)order, (int)n, sorted);
-  nms_mask_kernel<<<dim3(cb, cb), 64, 0, st>>>((int)n, thresh, sorted, mask);
-  nms_scan_kernel<<<1, 256, 0, st>>>((int)n, mask, (const long long*)order, sorted, (int)max_det, flags, kth, nkept);
-  nms_compact_kernel<<<1, 1024, 0, st>>>((int)n, flags, scores, (int)max_det, kth, nkept, (long long*)keep_out, num_keep);
+  nms_gather_kernel<<<cdiv(n, 256), 256, 0, st>>>(boxes, scores, labels, (const long long*)order, (int)n, sorted, nullptr, 0);
+  nms_mask_kernel<<<dim3(cb, cb), 64, 0, st>>>((int)n, thresh, sorted, mask, nullptr, 0);
+  nms_scan_kernel<<<1, 256, 0, st>>>((int)n, mask, (const long long*)order, sorted, (int)max_det, flags, kth, nkept, nullptr, 0);
+  nms_compact_kernel<<<1, 1024, 0, st>>>((int)n, flags, scores, (int)max_det, kth, nkept, (long long*)keep_out, num_keep, nullptr, 0);
   return check_launch("ml_nms");
+}
+
+// Batched variant: B images, rows of n_max candidates, per-image counts on the DEVICE (no host sync).
+extern "C" int64_t mqdet_ml_nms_batched_workspace_bytes(int64_t B, int64_t n_max) {
+  const size_t cb = (size_t)(n_max + 63) / 64;
+  return (int64_t)(B * (align256((size_t)n_max * 8) + align256((size_t)n_max * 6 * 4) + align256((size_t)n_max * cb * 8) +
+                        align256((size_t)n_max)) + align256((size_t)B * 8) + 256);
+}
+
+extern "C" int mqdet_ml_nms_batched(const float* boxes, const float* scores, const float* labels, const int32_t* counts_dev,
+                                    int64_t B, int64_t n_max, float thresh, int64_t max_det, int64_t* keep_out,
+                                    int32_t* num_keep, void* workspace, void* stream) {
+  MQ_REQUIRE(boxes && scores && labels && counts_dev && keep_out && num_keep && workspace, "ml_nms_batched: null pointer");
+  MQ_REQUIRE(B > 0 && n_max > 0 && n_max <= NMS_MAX_N, "ml_nms_batched: bad sizes B=%ld n_max=%ld", (long)B, (long)n_max);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int cb = (int)((n_max + 63) / 64);
+  uint8_t* ws = (uint8_t*)workspace;
+  long long* order = (long long*)ws;          ws += B * align256((size_t)n_max * 8);
+  float* sorted = (float*)ws;                 ws += B * align256((size_t)n_max * 6 * 4);
+  unsigned long long* mask = (unsigned long long*)ws;  ws += B * align256((size_t)n_max * cb * 8);
+  unsigned char* flags = ws;                  ws += B * align256((size_t)n_max);
+  float* kth = (float*)ws;
+  int* nkept = (int*)(ws + B * 4);
+  // the per-image strides inside the kernels are n_max elements (not the 256-aligned sizes): keep them consistent
+  MQ_REQUIRE(align256((size_t)n_max * 8) == (size_t)n_max * 8 && align256((size_t)n_max) == (size_t)n_max,
+             "ml_nms_batched: n_max must be a multiple of 256 (got %ld)", (long)n_max);
+  cudaMemsetAsync(flags, 0, (size_t)B * n_max, st);
+  int np2 = 1;
+  while (np2 < n_max) np2 <<= 1;
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(argsort_desc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, NMS_MAX_N * 8);
+    attr = true;
+  }
+  argsort_desc_kernel<<<(unsigned)B, 1024, (size_t)np2 * 8, st>>>(scores, 0, order, counts_dev, (int)n_max);
+  nms_gather_kernel<<<dim3(cdiv(n_max, 256), (unsigned)B), 256, 0, st>>>(boxes, scores, labels, order, 0, sorted, counts_dev,
+                                                                         (int)n_max);
+  nms_mask_kernel<<<dim3(cb, cb, (unsigned)B), 64, 0, st>>>(0, thresh, sorted, mask, counts_dev, (int)n_max);
+  nms_scan_kernel<<<(unsigned)B, 256, 0, st>>>(0, mask, order, sorted, (int)max_det, flags, kth, nkept, counts_dev, (int)n_max);
+  nms_compact_kernel<<<(unsigned)B, 1024, 0, st>>>(0, flags, scores, (int)max_det, kth, nkept, (long long*)keep_out, num_keep,
+                                                   counts_dev, (int)n_max);
+  return check_launch("ml_nms_batched");
 }

@@ -1,0 +1,310 @@
+// mqdet_b200 — Swin backbone / FPN data-movement and window-attention kernels (HBM-bound, coalesced NHWC rows).
+//
+// Reference: maskrcnn_benchmark/modeling/backbone/swint.py — PatchEmbed :393-431, window_partition/reverse :33-61,
+//            WindowAttention.forward :111-142, SwinTransformerBlock.forward :186-242 (pad, cyclic shift, mask),
+//            BasicLayer mask build :354-373, PatchMerging.forward :256-284;
+//            maskrcnn_benchmark/modeling/backbone/fpn.py FPN.forward :59-129, LastLevelP6P7 :137-154;
+//            generalized_vl_rcnn_new.py flatten_fpn_features :291-293 (AvgPool2d(2)).
+// Token layout everywhere: [B][H*W][C], row-major (h, w).  The dense projections (qkv, proj, MLP, reductions, 1x1/3x3
+// convolutions) run on the tcgen05 GEMM; these kernels only gather/scatter and do the 49x49 window attention.
+#include "common.cuh"
+#include "../../include/mqdet_b200.h"
+
+namespace mqdet {
+
+// image [B,3,H,W] fp32 NCHW -> patches [B*(H/4)*(W/4), 48] fp16, k = c*16 + i*4 + j (Conv2d(3,96,4,4) weight order);
+// zero padding on the right/bottom when H or W is not a multiple of 4 (swint.py:413-418).
+__global__ void patchify4_kernel(const float* __restrict__ img, int B, int H, int W, int Hp, int Wp, __half* __restrict__ out) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long total = (long)B * Hp * Wp * 48;
+  if (i >= total) return;
+  const int k = (int)(i % 48);
+  const long t = i / 48;
+  const int pw = (int)(t % Wp), ph = (int)((t / Wp) % Hp), b = (int)(t / ((long)Wp * Hp));
+  const int c = k / 16, ii = (k % 16) / 4, jj = k % 4;
+  const int y = ph * 4 + ii, x = pw * 4 + jj;
+  float v = 0.f;
+  if (y < H && x < W) v = img[(((long)b * 3 + c) * H + y) * W + x];
+  out[i] = __float2half_rn(v);
+}
+
+// Window attention for one (window, head): head_dim 32, window 7x7 (N = 49 tokens), fp32 math.
+// qkv [B*H*W, 3*C] fp16 (q | k | v, each C = heads*32 wide); bias_dense [heads][N][N] fp32 (relative position bias);
+// padded tokens (beyond H/W after padding to a multiple of the window) carry qkv = qkv_bias because the reference
+// pads the NORMALISED input with zeros before the qkv Linear (:200-205); cyclic shift + region mask (-100) are index math.
+template <int WS>
+__global__ void __launch_bounds__(64) swin_window_attn_kernel(const __half* __restrict__ qkv, const float* __restrict__ qkv_bias,
+                                                              const float* __restrict__ bias_dense, int B, int H, int W,
+                                                              int heads, int shift, float scale, __half* __restrict__ out) {
+  constexpr int N = WS * WS, D = 32;
+  const int C = heads * D;
+  const int Hp = (H + WS - 1) / WS * WS, Wp = (W + WS - 1) / WS * WS;
+  const int nWw = Wp / WS, nW = (Hp / WS) * nWw;
+  const int head = blockIdx.y;
+  const int b = blockIdx.x / nW, win = blockIdx.x % nW;
+  const int wi = win / nWw, wj = win % nWw;
+  __shared__ float ks[N][D + 1], vs[N][D + 1];
+  __shared__ int tok[N], region[N];
+  const int t = threadIdx.x;
+  if (t < N) {
+    const int r = t / WS, c = t % WS;
+    const int hs = wi * WS + r, wsft = wj * WS + c;            // coordinate in the shifted, padded frame
+    const int ho = (hs + shift) % Hp, wo = (wsft + shift) % Wp;  // coordinate in the un-shifted frame (roll by -shift)
+    tok[t] = (ho < H && wo < W) ? (ho * W + wo) : -1;
+    int idh = 0, idw = 0;
+    if (shift > 0) {
+      idh = (hs < Hp - WS) ? 0 : ((hs < Hp - shift) ? 1 : 2);
+      idw = (wsft < Wp - WS) ? 0 : ((wsft < Wp - shift) ? 1 : 2);
+    }
+    region[t] = idh * 3 + idw;
+  }
+  __syncthreads();
+  for (int i = t; i < N * D; i += 64) {
+    const int n = i / D, d = i % D;
+    const int tk = tok[n];
+    float kv, vv;
+    if (tk >= 0) {
+      const __half* row = qkv + ((long)b * H * W + tk) * 3 * C + head * D + d;
+      kv = __half2float(row[C]);
+      vv = __half2float(row[2 * C]);
+    } else {
+      kv = qkv_bias[C + head * D + d];
+      vv = qkv_bias[2 * C + head * D + d];
+    }
+    ks[n][d] = kv;
+    vs[n][d] = vv;
+  }
+  __syncthreads();
+  if (t >= N) return;
+  const int tk = tok[t];
+  if (tk < 0) return;  // outputs at padded positions are cropped away (:231-232)
+  float q[D];
+  {
+    const __half* row = qkv + ((long)b * H * W + tk) * 3 * C + head * D;
+#pragma unroll
+    for (int d = 0; d < D; ++d) q[d] = __half2float(row[d]) * scale;
+  }
+  float s[N];
+  float mx = -INFINITY;
+  const float* bd = bias_dense + ((long)head * N + t) * N;
+  const int rg = region[t];
+#pragma unroll 1
+  for (int j = 0; j < N; ++j) {
+    float a = 0.f;
+#pragma unroll
+    for (int d = 0; d < D; ++d) a = fmaf(q[d], ks[j][d], a);
+    a += bd[j];
+    if (shift > 0 && region[j] != rg) a += -100.0f;
+    s[j] = a;
+    mx = fmaxf(mx, a);
+  }
+  float den = 0.f;
+#pragma unroll 1
+  for (int j = 0; j < N; ++j) {
+    s[j] = expf(s[j] - mx);
+    den += s[j];
+  }
+  const float inv = 1.f / den;
+  float o[D];
+#pragma unroll
+  for (int d = 0; d < D; ++d) o[d] = 0.f;
+#pragma unroll 1
+  for (int j = 0; j < N; ++j) {
+    const float p = s[j] * inv;
+#pragma unroll
+    for (int d = 0; d < D; ++d) o[d] = fmaf(p, vs[j][d], o[d]);
+  }
+  __half* orow = out + ((long)b * H * W + tk) * C + head * D;
+#pragma unroll
+  for (int d = 0; d < D; d += 2) *reinterpret_cast<__half2*>(orow + d) = __floats2half2_rn(o[d], o[d + 1]);
+}
+
+// PatchMerging gather + LayerNorm(4C) (:256-284): out row (b, h2, w2) = LN(cat[x(2h2,2w2), x(2h2+1,2w2), x(2h2,2w2+1),
+// x(2h2+1,2w2+1)]) with zero rows outside (odd H/W padding).  x fp32 [B, H*W, C] -> fp16 [B*H2*W2, 4C]. Warp per row.
+__global__ void __launch_bounds__(256) patch_merge_ln_kernel(const float* __restrict__ x, int B, int H, int W, int C,
+                                                             const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                             float eps, __half* __restrict__ out) {
+  const int H2 = (H + 1) / 2, W2 = (W + 1) / 2;
+  const long row = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= (long)B * H2 * W2) return;
+  const int w2 = (int)(row % W2), h2 = (int)((row / W2) % H2), b = (int)(row / ((long)W2 * H2));
+  const int D4 = 4 * C;
+  auto src = [&](int i) -> float {
+    const int q = i / C, c = i % C;
+    const int hh = 2 * h2 + (q & 1), ww = 2 * w2 + (q >> 1);
+    return (hh < H && ww < W) ? x[((long)b * H * W + (long)hh * W + ww) * C + c] : 0.f;
+  };
+  float s = 0.f;
+  for (int i = lane; i < D4; i += 32) s += src(i);
+  const float mean = warp_sum(s) / D4;
+  float v = 0.f;
+  for (int i = lane; i < D4; i += 32) {
+    const float d = src(i) - mean;
+    v += d * d;
+  }
+  const float rstd = rsqrtf(warp_sum(v) / D4 + eps);
+  for (int i = lane; i < D4; i += 32) out[row * D4 + i] = __float2half_rn((src(i) - mean) * rstd * gamma[i] + beta[i]);
+}
+
+// FPN top-down merge (fpn.py:88-95): out = lateral + nearest_upsample(top).  fp16 rows of C=256, warp per pixel.
+__global__ void __launch_bounds__(256) upsample_add_kernel(const __half* __restrict__ lateral, const __half* __restrict__ top,
+                                                           int B, int H, int W, int Hs, int Ws, int C,
+                                                           __half* __restrict__ out) {
+  const long gw = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (gw >= (long)B * H * W) return;
+  const int w = (int)(gw % W), h = (int)((gw / W) % H), b = (int)(gw / ((long)W * H));
+  // F.interpolate(mode="nearest"): src = floor(dst * in / out) computed in fp32 like ATen
+  const int hs = min((int)floorf(h * ((float)Hs / (float)H)), Hs - 1);
+  const int ws = min((int)floorf(w * ((float)Ws / (float)W)), Ws - 1);
+  const __half* lp = lateral + gw * C;
+  const __half* tp = top + ((long)b * Hs * Ws + (long)hs * Ws + ws) * C;
+  for (int c = lane * 8; c < C; c += 256) {
+    const uint4 a = *reinterpret_cast<const uint4*>(lp + c);
+    const uint4 t4 = *reinterpret_cast<const uint4*>(tp + c);
+    const __half2* ah = reinterpret_cast<const __half2*>(&a);
+    const __half2* th = reinterpret_cast<const __half2*>(&t4);
+    __half2 o[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 x = __half22float2(ah[i]), y = __half22float2(th[i]);
+      o[i] = __floats2half2_rn(x.x + y.x, x.y + y.y);
+    }
+    *reinterpret_cast<uint4*>(out + gw * C + c) = *reinterpret_cast<uint4*>(o);
+  }
+}
+
+// Plain 3x3 / pad 1 / stride s im2col of an fp16 NHWC map [B][H*W][C] (arbitrary batch stride) -> cols [B*Ho*Wo][9*C],
+// k = tap*C + c; optional ReLU on the input (LastLevelP6P7: p7 = conv(relu(p6)), fpn.py:152).  Warp per (pixel, tap).
+__global__ void __launch_bounds__(256) im2col3x3_kernel(const __half* __restrict__ x, long x_batch_stride, int B, int H, int W,
+                                                        int C, int stride, int relu_in, __half* __restrict__ cols) {
+  const int Ho = (H + 2 - 3) / stride + 1, Wo = (W + 2 - 3) / stride + 1;
+  const long gw = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (gw >= (long)B * Ho * Wo * 9) return;
+  const int tap = (int)(gw % 9);
+  const long r = gw / 9;
+  const int wo = (int)(r % Wo), ho = (int)((r / Wo) % Ho), b = (int)(r / ((long)Wo * Ho));
+  const int hi = ho * stride - 1 + tap / 3, wi = wo * stride - 1 + tap % 3;
+  const bool ok = hi >= 0 && hi < H && wi >= 0 && wi < W;
+  const __half* src = x + (long)b * x_batch_stride + ((long)hi * W + wi) * C;
+  __half* dst = cols + (r * 9 + tap) * C;
+  for (int c = lane * 8; c < C; c += 256) {
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (ok) {
+      v = *reinterpret_cast<const uint4*>(src + c);
+      if (relu_in) {
+        __half2* h = reinterpret_cast<__half2*>(&v);
+        const __half2 z = __float2half2_rn(0.f);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) h[i] = __hmax2(h[i], z);
+      }
+    }
+    *reinterpret_cast<uint4*>(dst + c) = v;
+  }
+}
+
+// AvgPool2d(2) (floor) of every level of the concatenated pyramid -> concatenated pooled tokens, fp16 -> fp32.
+struct PoolLevels {
+  int n;
+  int H[MQDET_MAX_LEVELS], W[MQDET_MAX_LEVELS], off[MQDET_MAX_LEVELS], ooff[MQDET_MAX_LEVELS + 1];
+};
+__global__ void __launch_bounds__(256) avgpool2_levels_kernel(const __half* __restrict__ x, PoolLevels lv, int B, int N, int C,
+                                                              float* __restrict__ out) {
+  const long gw = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  const int I = lv.ooff[lv.n];
+  if (gw >= (long)B * I) return;
+  const int b = (int)(gw / I), q = (int)(gw % I);
+  int l = 0;
+  while (l + 1 < lv.n && q >= lv.ooff[l + 1]) ++l;
+  const int W2 = lv.W[l] / 2;
+  const int p = q - lv.ooff[l];
+  const int h2 = p / W2, w2 = p % W2;
+  const __half* base = x + ((long)b * N + lv.off[l]) * C;
+  for (int c = lane; c < C; c += 32) {
+    float s = 0.f;
+#pragma unroll
+    for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+      for (int dx = 0; dx < 2; ++dx) s += __half2float(base[((long)(2 * h2 + dy) * lv.W[l] + 2 * w2 + dx) * C + c]);
+    out[gw * C + c] = s * 0.25f;
+  }
+}
+
+}  // namespace mqdet
+
+using namespace mqdet;
+
+extern "C" int mqdet_patchify4(const float* img, int64_t B, int64_t H, int64_t W, void* out, void* stream) {
+  MQ_REQUIRE(img && out && B > 0 && H > 0 && W > 0, "patchify4: bad args");
+  const int Hp = (int)((H + 3) / 4), Wp = (int)((W + 3) / 4);
+  const long total = B * Hp * Wp * 48;
+  patchify4_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(img, (int)B, (int)H, (int)W, Hp, Wp,
+                                                                                     (__half*)out);
+  return check_launch("patchify4_kernel");
+}
+
+extern "C" int mqdet_swin_window_attn(const void* qkv, const float* qkv_bias, const float* bias_dense, int64_t B, int64_t H,
+                                      int64_t W, int64_t heads, int64_t window, int64_t shift, float scale, void* out,
+                                      void* stream) {
+  MQ_REQUIRE(qkv && qkv_bias && bias_dense && out, "swin_window_attn: null pointer");
+  MQ_REQUIRE(window == 7, "swin_window_attn: window 7 only (Swin-T/GLIP-T; Swin-L's 12x12 is SURVEY.md §8f)");
+  MQ_REQUIRE(shift >= 0 && shift < window, "swin_window_attn: bad shift");
+  const int Hp = (int)((H + window - 1) / window * window), Wp = (int)((W + window - 1) / window * window);
+  const int nW = (Hp / (int)window) * (Wp / (int)window);
+  dim3 grid((unsigned)(B * nW), (unsigned)heads);
+  swin_window_attn_kernel<7><<<grid, 64, 0, (cudaStream_t)stream>>>((const __half*)qkv, qkv_bias, bias_dense, (int)B, (int)H,
+                                                                    (int)W, (int)heads, (int)shift, scale, (__half*)out);
+  return check_launch("swin_window_attn_kernel");
+}
+
+extern "C" int mqdet_patch_merge_ln(const float* x, int64_t B, int64_t H, int64_t W, int64_t C, const float* gamma,
+                                    const float* beta, float eps, void* out, void* stream) {
+  MQ_REQUIRE(x && gamma && beta && out, "patch_merge_ln: null pointer");
+  const long rows = B * ((H + 1) / 2) * ((W + 1) / 2);
+  patch_merge_ln_kernel<<<cdiv(rows, 8), 256, 0, (cudaStream_t)stream>>>(x, (int)B, (int)H, (int)W, (int)C, gamma, beta, eps,
+                                                                        (__half*)out);
+  return check_launch("patch_merge_ln_kernel");
+}
+
+extern "C" int mqdet_upsample_add(const void* lateral, const void* top, int64_t B, int64_t H, int64_t W, int64_t Hs,
+                                  int64_t Ws, int64_t C, void* out, void* stream) {
+  MQ_REQUIRE(lateral && top && out && (C % 8) == 0, "upsample_add: bad args");
+  const long warps = B * H * W;
+  upsample_add_kernel<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      (const __half*)lateral, (const __half*)top, (int)B, (int)H, (int)W, (int)Hs, (int)Ws, (int)C, (__half*)out);
+  return check_launch("upsample_add_kernel");
+}
+
+extern "C" int mqdet_im2col3x3(const void* x, int64_t x_batch_stride, int64_t B, int64_t H, int64_t W, int64_t C,
+                               int64_t stride, int relu_in, void* cols, void* stream) {
+  MQ_REQUIRE(x && cols && (C % 8) == 0 && (stride == 1 || stride == 2), "im2col3x3: bad args");
+  const int Ho = (int)((H + 2 - 3) / stride + 1), Wo = (int)((W + 2 - 3) / stride + 1);
+  const long warps = B * Ho * Wo * 9;
+  im2col3x3_kernel<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      (const __half*)x, x_batch_stride, (int)B, (int)H, (int)W, (int)C, (int)stride, relu_in, (__half*)cols);
+  return check_launch("im2col3x3_kernel");
+}
+
+extern "C" int mqdet_avgpool2_levels(const void* x, const int32_t* level_hw, int64_t nlev, int64_t B, int64_t C, float* out,
+                                     void* stream) {
+  MQ_REQUIRE(x && level_hw && out && nlev >= 1 && nlev <= MQDET_MAX_LEVELS, "avgpool2_levels: bad args");
+  PoolLevels lv;
+  lv.n = (int)nlev;
+  int off = 0, ooff = 0;
+  for (int l = 0; l < nlev; ++l) {
+    lv.H[l] = level_hw[2 * l];
+    lv.W[l] = level_hw[2 * l + 1];
+    lv.off[l] = off;
+    lv.ooff[l] = ooff;
+    off += lv.H[l] * lv.W[l];
+    ooff += (lv.H[l] / 2) * (lv.W[l] / 2);
+  }
+  lv.ooff[nlev] = ooff;
+  const long warps = B * ooff;
+  avgpool2_levels_kernel<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, (cudaStream_t)stream>>>((const __half*)x, lv, (int)B,
+                                                                                                off, (int)C, out);
+  return check_launch("avgpool2_levels_kernel");
+}

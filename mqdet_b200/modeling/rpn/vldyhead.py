@@ -271,7 +271,7 @@ class VLDyHead(nn.Module):
         B = v16.shape[0]
         logits, bbox_reg, centerness, dots, fused = [], [], [], [], []
         vis32 = ops.cast_f32(r["visual"])
-        cw = w16(self.cls_logits.weight.view(self.cls_logits.weight.shape[0], -1))
+        cw = w16(self.cls_logits.weight, view=(self.cls_logits.weight.shape[0], -1))
         for l, (h, w) in enumerate(levels.sizes):
             s, e = levels.off[l], levels.off[l + 1]
             rc = r["reg_ctr"][:, s:e]

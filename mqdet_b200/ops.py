@@ -385,3 +385,155 @@ def dyrelu(mid, levels, w1, b1, w2, b2):
           "dyrelu_apply")
     launch_count += 2
     return out
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# ATSS post-processing
+# ----------------------------------------------------------------------------------------------------------------------
+def base_anchor(stride, size):
+    """generate_anchors for ONE square anchor (anchor_generator.py:355-425): window [0,0,s-1,s-1] scaled to `size`."""
+    import math
+    ctr = 0.5 * (stride - 1)
+    ws = float(round(math.sqrt(stride * stride)))
+    w = ws * (size / stride)
+    return [ctr - 0.5 * (w - 1), ctr - 0.5 * (w - 1), ctr + 0.5 * (w - 1), ctr + 0.5 * (w - 1)]
+
+
+def make_tokmap(positive_map, num_classes, device):
+    """{label(1-based): [token positions]} -> int32 [C, max_tok] padded with -1."""
+    max_tok = max([len(v) if not isinstance(v, int) else 1 for v in positive_map.values()] + [1])
+    tm = torch.full((num_classes, max_tok), -1, dtype=torch.int32)
+    for label, toks in positive_map.items():
+        toks = [toks] if isinstance(toks, int) else list(toks)
+        if 1 <= label <= num_classes:
+            tm[label - 1, : len(toks)] = torch.tensor(toks, dtype=torch.int32)
+    return tm.to(device)
+
+
+def atss_postprocess(logits, reg_ctr, tokmap, levels, strides, anchor_sizes, reg_scales, img_w, img_h, *, pre_nms_thresh=0.05,
+                     pre_nms_top_n=1000, nms_thresh=0.6, max_det=100, max_out=128, want_keys=False):
+    """logits [B,N,T], reg_ctr [B,N,5] -> dict(det [B,max_out,6], num [B], + the pre-NMS candidates). All on device."""
+    import numpy as np
+    global launch_count
+    _need_cuda(logits, reg_ctr, tokmap)
+    B, N, T = logits.shape
+    C, max_tok = tokmap.shape
+    dev = logits.device
+    L = levels.n
+    stride_h = np.asarray(strides, dtype=np.float32)
+    base_h = np.asarray([base_anchor(s, a) for s, a in zip(strides, anchor_sizes)], dtype=np.float32)
+    scale_h = np.asarray(reg_scales, dtype=np.float32)
+    S = (L * pre_nms_top_n + 255) // 256 * 256
+    ws = torch.empty((int(load().mqdet_atss_workspace_bytes(levels.hw_ptr, L, C, B)),), dtype=torch.uint8, device=dev)
+    lvl_counts = torch.empty((B, L), dtype=torch.int32, device=dev)
+    ob = torch.empty((B, S, 4), dtype=torch.float32, device=dev)
+    osc = torch.empty((B, S), dtype=torch.float32, device=dev)
+    ol = torch.empty((B, S), dtype=torch.float32, device=dev)
+    okey = torch.empty((B, S), dtype=torch.int64, device=dev) if want_keys else None
+    cb, csc, cl = torch.empty_like(ob), torch.empty_like(osc), torch.empty_like(ol)
+    totals = torch.empty((B,), dtype=torch.int32, device=dev)
+    check(load().mqdet_atss_candidates(_ptr(logits), _dt(logits), _ptr(reg_ctr), _ptr(tokmap), C, max_tok, T, levels.hw_ptr, L,
+                                       stride_h.ctypes.data_as(ctypes.c_void_p), base_h.ctypes.data_as(ctypes.c_void_p),
+                                       scale_h.ctypes.data_as(ctypes.c_void_p), B, float(pre_nms_thresh), int(pre_nms_top_n),
+                                       S, float(img_w), float(img_h), _ptr(ws), _ptr(lvl_counts), _ptr(ob), _ptr(osc),
+                                       _ptr(ol), _ptr(okey), _ptr(cb), _ptr(csc), _ptr(cl), _ptr(totals), _stream()),
+          "atss_candidates")
+    nws = torch.empty((int(load().mqdet_ml_nms_batched_workspace_bytes(B, S)),), dtype=torch.uint8, device=dev)
+    keep = torch.empty((B, S), dtype=torch.int64, device=dev)
+    num = torch.empty((B,), dtype=torch.int32, device=dev)
+    check(load().mqdet_ml_nms_batched(_ptr(cb), _ptr(csc), _ptr(cl), _ptr(totals), B, S, float(nms_thresh), int(max_det),
+                                      _ptr(keep), _ptr(num), _ptr(nws), _stream()), "ml_nms_batched")
+    det = torch.empty((B, max_out, 6), dtype=torch.float32, device=dev)
+    check(load().mqdet_gather_detections(_ptr(cb), _ptr(csc), _ptr(cl), _ptr(keep), _ptr(num), B, S, max_out, _ptr(det),
+                                         _stream()), "gather_detections")
+    launch_count += 10
+    return {"det": det, "num": num, "cand_boxes": cb, "cand_scores": csc, "cand_labels": cl, "cand_totals": totals,
+            "level_counts": lvl_counts, "level_keys": okey, "keep": keep}
+
+
+def anchors(grid_h, grid_w, stride, size, img_w, img_h, device):
+    """Anchors [H*W, 4] + visibility [H*W] of one level (anchor_generator.py:72-109)."""
+    import numpy as np
+    global launch_count
+    out = torch.empty((grid_h * grid_w, 4), dtype=torch.float32, device=device)
+    vis = torch.empty((grid_h * grid_w,), dtype=torch.uint8, device=device)
+    base = np.asarray(base_anchor(stride, size), dtype=np.float32)
+    check(load().mqdet_anchors(_ptr(out), _ptr(vis), grid_h, grid_w, float(stride), base.ctypes.data_as(ctypes.c_void_p),
+                               float(img_w), float(img_h), _stream()), "anchors")
+    launch_count += 1
+    return out, vis.bool()
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# Swin / FPN glue
+# ----------------------------------------------------------------------------------------------------------------------
+def patchify4(img):
+    """[B,3,H,W] fp32 -> (fp16 [B*Hp*Wp, 48], Hp, Wp)."""
+    global launch_count
+    _need_cuda(img)
+    B, _, H, W = img.shape
+    Hp, Wp = (H + 3) // 4, (W + 3) // 4
+    img = img.float().contiguous()
+    out = torch.empty((B * Hp * Wp, 48), dtype=torch.float16, device=img.device)
+    check(load().mqdet_patchify4(_ptr(img), B, H, W, _ptr(out), _stream()), "patchify4")
+    launch_count += 1
+    return out, Hp, Wp
+
+
+def swin_window_attn(qkv16, qkv_bias, bias_dense, B, H, W, heads, window, shift, scale):
+    global launch_count
+    _need_cuda(qkv16, qkv_bias, bias_dense)
+    C = qkv16.shape[-1] // 3
+    out = torch.empty((B * H * W, C), dtype=torch.float16, device=qkv16.device)
+    check(load().mqdet_swin_window_attn(_ptr(qkv16), _ptr(qkv_bias), _ptr(bias_dense), B, H, W, heads, window, shift,
+                                        float(scale), _ptr(out), _stream()), "swin_window_attn")
+    launch_count += 1
+    return out
+
+
+def patch_merge_ln(x32, B, H, W, gamma, beta, eps):
+    global launch_count
+    _need_cuda(x32)
+    C = x32.shape[-1]
+    H2, W2 = (H + 1) // 2, (W + 1) // 2
+    out = torch.empty((B * H2 * W2, 4 * C), dtype=torch.float16, device=x32.device)
+    check(load().mqdet_patch_merge_ln(_ptr(x32), B, H, W, C, _ptr(gamma), _ptr(beta), float(eps), _ptr(out), _stream()),
+          "patch_merge_ln")
+    launch_count += 1
+    return out, H2, W2
+
+
+def upsample_add(lateral16, top16, B, H, W, Hs, Ws):
+    global launch_count
+    _need_cuda(lateral16, top16)
+    C = lateral16.shape[-1]
+    out = torch.empty_like(lateral16)
+    check(load().mqdet_upsample_add(_ptr(lateral16), _ptr(top16), B, H, W, Hs, Ws, C, _ptr(out), _stream()), "upsample_add")
+    launch_count += 1
+    return out
+
+
+def im2col3x3(x16, B, H, W, stride=1, relu_in=False):
+    """x16: fp16 [B, H*W, C] (may be a batch-strided view with contiguous rows) -> cols [B*Ho*Wo, 9C], Ho, Wo."""
+    global launch_count
+    _need_cuda(x16)
+    C = x16.shape[-1]
+    assert x16.stride(-1) == 1 and x16.stride(-2) == C
+    Ho, Wo = (H + 2 - 3) // stride + 1, (W + 2 - 3) // stride + 1
+    cols = torch.empty((B * Ho * Wo, 9 * C), dtype=torch.float16, device=x16.device)
+    check(load().mqdet_im2col3x3(_ptr(x16), x16.stride(0) if x16.dim() == 3 else H * W * C, B, H, W, C, stride,
+                                 int(bool(relu_in)), _ptr(cols), _stream()), "im2col3x3")
+    launch_count += 1
+    return cols, Ho, Wo
+
+
+def avgpool2_levels(x16, levels):
+    """fp16 [B,N,C] pyramid -> fp32 [B, I, C] pooled tokens (AvgPool2d(2) per level, concatenated)."""
+    global launch_count
+    _need_cuda(x16)
+    B, N, C = x16.shape
+    I = sum((h // 2) * (w // 2) for h, w in levels.sizes)
+    out = torch.empty((B, I, C), dtype=torch.float32, device=x16.device)
+    check(load().mqdet_avgpool2_levels(_ptr(x16), levels.hw_ptr, levels.n, B, C, _ptr(out), _stream()), "avgpool2_levels")
+    launch_count += 1
+    return out

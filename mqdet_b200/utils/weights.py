@@ -12,8 +12,11 @@ from .. import ops
 _cache = {}
 
 
-def w16(param, rows=None):
-    """fp16, contiguous copy of ``param`` (optionally a row slice ``rows=(lo, hi)``), cached per parameter version."""
+def w16(param, rows=None, view=None):
+    """fp16, contiguous copy of ``param`` (optionally a row slice ``rows=(lo, hi)``, optionally reshaped to ``view``),
+    cached per parameter version.  Always pass the nn.Parameter itself (not a temporary view) so the cache can hit."""
+    if view is not None:
+        return w16(param, rows).view(*view)
     key = (id(param), rows)
     ent = _cache.get(key)
     ver = (param.data_ptr(), param._version, param.device)

@@ -81,6 +81,12 @@ def case_inputs(name):
         am[0, 200:] = 0
         am[1, 33:] = 0
         return dict(sd=sd, h=h, am=am)
+    if name == "swin_fpn":
+        gen = synth.Gen(1238)
+        sd = synth.swin_sd(gen)
+        fsd = synth.fpn_sd(gen)
+        img = gen.randn(2, 3, 150, 203, scale=1.0)  # not a multiple of 4/7/2: exercises every padding path
+        return dict(sd=sd, fsd=fsd, img=img)
     raise KeyError(name)
 
 
@@ -127,11 +133,32 @@ def run_reference(name):
         # wiring of BertEncoderLayer.forward (maskrcnn_benchmark/modeling/rpn/vldyhead.py:264-301)
         a = att(c["h"], ext, None, output_attentions=False, past_key_value=None)[0]
         return dict(h=outp(inter(a), a))
+    if name == "swin_fpn":
+        sw = rl.swint()
+        body = sw.SwinTransformer(embed_dim=96, depths=[2, 2, 6, 2], num_heads=[3, 6, 12, 24], window_size=7,
+                                  drop_path_rate=0.0, frozen_stages=-1, use_checkpoint=False)
+        body.eval()  # the reference's train() override returns None, so no chaining
+        sdb = dict(c["sd"])
+        for k, v in body.state_dict().items():
+            if k.endswith("relative_position_index"):
+                sdb[k] = v
+        body.load_state_dict(sdb, strict=True)
+        outs = body(c["img"])
+        fpn_mod = rl.fpn()
+        conv_block = lambda i, o, k, s=1: torch.nn.Conv2d(i, o, k, s, padding=(k - 1) // 2)  # noqa: E731
+        f = fpn_mod.FPN([0, 192, 384, 768], 256, conv_block, top_blocks=fpn_mod.LastLevelP6P7(256, 256)).eval()
+        f.load_state_dict(c["fsd"], strict=True)
+        pyr = f(outs)
+        res = {f"c{i + 2}": o for i, o in enumerate(outs)}
+        res.update({f"p{i + 3}": o for i, o in enumerate(pyr)})
+        return res
     raise KeyError(name)
 
 
 SUBSAMPLE = {"gcp_block": {"y": (4, 8), "s": (4, 8)}, "preselect": {"vision": (1, 8)},
-             "bi_attention": {"v": (3, 4), "l": (4, 8)}, "bert_layer": {"h": (4, 8)}}
+             "bi_attention": {"v": (3, 4), "l": (4, 8)}, "bert_layer": {"h": (4, 8)},
+             "swin_fpn": {"c3": (4, 2, 2), "c4": (4, 1, 1), "c5": (8, 1, 1), "p3": (4, 2, 2), "p4": (4, 1, 1), "p5": (4, 1, 1),
+                          "p6": (2, 1, 1), "p7": (1, 1, 1)}}
 
 
 def main():

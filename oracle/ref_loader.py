@@ -135,3 +135,11 @@ def swint():
         _install_shims()
         _cache["swint"] = _load_file("ref_swint", "maskrcnn_benchmark/modeling/backbone/swint.py")
     return _cache["swint"]
+
+
+def fpn():
+    """maskrcnn_benchmark/modeling/backbone/fpn.py (FPN, LastLevelP6P7)."""
+    if "fpn" not in _cache:
+        _install_shims()
+        _cache["fpn"] = _load_file("ref_fpn", "maskrcnn_benchmark/modeling/backbone/fpn.py")
+    return _cache["fpn"]

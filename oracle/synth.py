@@ -200,3 +200,46 @@ def vldyhead_sd(gen, num_convs=6, C=256, l_dim=768, num_classes=80):
     for l in range(5):
         sd[f"scales.{l}.scale"] = torch.tensor([1.0 + 0.1 * l])
     return sd
+
+
+def swin_sd(gen, depths=(2, 2, 6, 2), heads=(3, 6, 12, 24), embed=96, ws=7, p=""):
+    """SwinTransformer parameters with the reference's key names (swint.py), livelier than trunc_normal(0.02)."""
+    sd = {}
+    sd[p + "patch_embed.proj.weight"] = gen.randn(embed, 3, 4, 4, scale=0.15)
+    sd[p + "patch_embed.proj.bias"] = gen.randn(embed, scale=0.05)
+    gen.norm(embed, sd, p + "patch_embed.norm")
+    for i, depth in enumerate(depths):
+        C = embed * 2 ** i
+        for j in range(depth):
+            bp = f"{p}layers.{i}.blocks.{j}."
+            gen.norm(C, sd, bp + "norm1")
+            sd[bp + "attn.relative_position_bias_table"] = gen.randn((2 * ws - 1) ** 2, heads[i], scale=0.5)
+            sd[bp + "attn.qkv.weight"] = gen.randn(3 * C, C, scale=1.5 / math.sqrt(C))
+            sd[bp + "attn.qkv.bias"] = gen.randn(3 * C, scale=0.2)
+            sd[bp + "attn.proj.weight"] = gen.randn(C, C, scale=1.0 / math.sqrt(C))
+            sd[bp + "attn.proj.bias"] = gen.randn(C, scale=0.05)
+            gen.norm(C, sd, bp + "norm2")
+            sd[bp + "mlp.fc1.weight"] = gen.randn(4 * C, C, scale=1.0 / math.sqrt(C))
+            sd[bp + "mlp.fc1.bias"] = gen.randn(4 * C, scale=0.05)
+            sd[bp + "mlp.fc2.weight"] = gen.randn(C, 4 * C, scale=0.5 / math.sqrt(4 * C))
+            sd[bp + "mlp.fc2.bias"] = gen.randn(C, scale=0.05)
+        if i < len(depths) - 1:
+            gen.norm(4 * C, sd, f"{p}layers.{i}.downsample.norm")
+            sd[f"{p}layers.{i}.downsample.reduction.weight"] = gen.randn(2 * C, 4 * C, scale=1.0 / math.sqrt(4 * C))
+        if i > 0:  # norm0 is nn.Identity for *-RETINANET backbones (swint.py:547-548)
+            gen.norm(C, sd, f"{p}norm{i}")
+    return sd
+
+
+def fpn_sd(gen, in_channels=(192, 384, 768), C=256, p=""):
+    """FPN + LastLevelP6P7 parameters (fpn.py), kaiming-uniform-like scale with non-zero biases."""
+    sd = {}
+    for k, cin in zip((2, 3, 4), in_channels):
+        sd[f"{p}fpn_inner{k}.weight"] = gen.randn(C, cin, 1, 1, scale=1.0 / math.sqrt(cin))
+        sd[f"{p}fpn_inner{k}.bias"] = gen.randn(C, scale=0.05)
+        sd[f"{p}fpn_layer{k}.weight"] = gen.randn(C, C, 3, 3, scale=1.0 / math.sqrt(9 * C))
+        sd[f"{p}fpn_layer{k}.bias"] = gen.randn(C, scale=0.05)
+    for k in ("p6", "p7"):
+        sd[f"{p}top_blocks.{k}.weight"] = gen.randn(C, C, 3, 3, scale=1.0 / math.sqrt(9 * C))
+        sd[f"{p}top_blocks.{k}.bias"] = gen.randn(C, scale=0.05)
+    return sd

@@ -1,0 +1,83 @@
+"""GPU parity of the Swin-T backbone (window attention with padding / cyclic shift / region mask in-kernel) and the FPN
+against the CPU oracle and the vectors recorded from the reference's SwinTransformer / FPN modules."""
+import os
+
+import pytest
+import torch
+
+from util import FP16_TOL, ROOT, assert_close, load_sd
+
+pytestmark = pytest.mark.gpu
+
+
+def _load_swin(sd, dev):
+    from mqdet_b200.modeling.backbone.swint import SwinTransformer
+    m = SwinTransformer()
+    own = m.state_dict()
+    full = dict(sd)
+    for k in own:
+        if k.endswith("relative_position_index"):
+            full[k] = own[k]
+    return load_sd(m, full).to(dev).eval()
+
+
+def test_swin_block_shift_and_padding(dev):
+    """One shifted block on a 38x51 grid (pads to 42x56): exercises padded keys (= qkv bias), roll and the -100 mask."""
+    from mqdet_b200.modeling.backbone.swint import SwinTransformerBlock
+    from oracle import restate, synth
+    gen = synth.Gen(91)
+    sd = {k[len("layers.0.blocks.1."):]: v for k, v in synth.swin_sd(gen).items() if k.startswith("layers.0.blocks.1.")}
+    B, H, W, C = 2, 38, 51, 96
+    x = gen.randn(B, H * W, C)
+    for shift in (0, 3):
+        ref = restate.swin_block(x, H, W, sd, "", 3, 7, shift)
+        blk = SwinTransformerBlock(C, 3, 7, shift)
+        full = dict(sd)
+        full["attn.relative_position_index"] = blk.state_dict()["attn.relative_position_index"]
+        blk = load_sd(blk, full).to(dev).eval()
+        blk.H, blk.W = H, W
+        out = blk(x.to(dev), None)
+        assert_close(out, ref, what=f"Swin block shift={shift}")
+
+
+def test_swin_fpn_vs_oracle_and_golden(dev):
+    from mqdet_b200.modeling.backbone.fpn import FPN, LastLevelP6P7
+    from oracle import make_golden, restate
+    c = make_golden.case_inputs("swin_fpn")
+    body = _load_swin(c["sd"], dev)
+    fpn = load_sd(FPN([0, 192, 384, 768], 256, LastLevelP6P7(256, 256)), c["fsd"]).to(dev).eval()
+    ref_c = restate.swin_transformer(c["img"], c["sd"])
+    ref_p = restate.fpn(ref_c, c["fsd"])
+    outs = body(c["img"].to(dev))
+    assert len(outs) == 4
+    bad = []
+    for i, (o, r) in enumerate(zip(outs, ref_c)):
+        assert_close(o, r, 3e-3, f"Swin stage{i + 2}", defer=bad)  # 12 blocks with fp16 GEMM operands, fp32 residual
+    pyr = fpn(outs)
+    for i, (o, r) in enumerate(zip(pyr, ref_p)):
+        assert_close(o, r, 4e-3, f"FPN P{i + 3}", defer=bad)
+    # flat fast path == NCHW API
+    feats = body.forward_flat(c["img"].to(dev))
+    p16, levels = fpn.forward_flat([feats[i] for i in (1, 2, 3)])
+    assert levels.sizes == [tuple(r.shape[2:]) for r in ref_p]
+    assert_close(p16, restate.flatten_levels(ref_p), 4e-3, "FPN flat pyramid", defer=bad)
+    fx = torch.load(os.path.join(ROOT, "tests", "golden", "swin_fpn.pt"))
+    for key, got in [("c3", outs[1]), ("c5", outs[3]), ("p3", pyr[0]), ("p7", pyr[4])]:
+        g = make_golden.sub(got.float().cpu(), *fx["subsample"][key])
+        err = (g - fx[key]).abs().max().item()
+        if err > 4e-3 * fx[key + "_absmax"] + 4e-3:
+            bad.append(f"golden {key}: {err:.3e}")
+    assert not bad, bad
+
+
+def test_avgpool_levels(dev):
+    from mqdet_b200 import ops
+    g = torch.Generator().manual_seed(4)
+    sizes = [(19, 26), (10, 13), (5, 7), (3, 4), (2, 2)]
+    feats = [torch.randn(2, 256, h, w, generator=g) for h, w in sizes]
+    lv = ops.Levels(sizes, dev)
+    x16 = torch.cat([f.flatten(2).transpose(1, 2) for f in feats], 1).half().to(dev).contiguous()
+    out = ops.avgpool2_levels(x16, lv)
+    ref = torch.cat([torch.nn.functional.avg_pool2d(f.half().float(), 2).flatten(2).transpose(1, 2) for f in feats], 1)
+    assert out.shape == ref.shape
+    assert_close(out, ref, 1e-5, "AvgPool2d(2) + flatten + cat")

@@ -87,3 +87,15 @@ def test_ml_nms_oracle_properties():
     assert restate.ml_nms(boxes, scores, torch.arange(n).float(), 0.6).numel() == n
     # class-agnostic case equals torchvision-style greedy NMS with the +1 convention when boxes are far apart
     assert restate.ml_nms(boxes[:1], scores[:1], labels[:1], 0.6).tolist() == [0]
+
+
+def test_swin_fpn_golden():
+    """Restated Swin-T + FPN vs vectors recorded from the reference's SwinTransformer / FPN modules."""
+    fx = torch.load(os.path.join(GOLD, "swin_fpn.pt"))
+    c = make_golden.case_inputs("swin_fpn")
+    outs = restate.swin_transformer(c["img"], c["sd"])
+    pyr = restate.fpn(outs, c["fsd"])
+    for i, o in enumerate(outs[1:]):
+        _cmp(fx, f"c{i + 3}", o, 1e-4)
+    for i, o in enumerate(pyr):
+        _cmp(fx, f"p{i + 3}", o, 1e-4)

@@ -42,3 +42,13 @@ def test_bert_layer_vs_reference():
     c = make_golden.case_inputs("bert_layer")
     ref = make_golden.run_reference("bert_layer")
     _close(restate.bert_layer(c["h"], restate.extended_mask(c["am"]), c["sd"], "", clamp=50000.0), ref["h"])
+
+
+def test_swin_fpn_vs_reference():
+    c = make_golden.case_inputs("swin_fpn")
+    ref = make_golden.run_reference("swin_fpn")
+    outs = restate.swin_transformer(c["img"], c["sd"])
+    for i, o in enumerate(outs):
+        _close(o, ref[f"c{i + 2}"], 1e-5)
+    for i, o in enumerate(restate.fpn(outs, c["fsd"])):
+        _close(o, ref[f"p{i + 3}"], 1e-5)
