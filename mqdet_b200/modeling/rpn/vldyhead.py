@@ -285,3 +285,66 @@ class VLDyHead(nn.Module):
         language_dict_features["hidden"] = r["hidden"]
         fused_out = fused if getattr(self.cfg.MODEL.RPN, "RETURN_FUSED_FEATURES", False) else None
         return logits, bbox_reg, centerness, None, None, None, dots, None, None, fused_out
+
+
+class VLDyHeadModule(nn.Module):
+    """vldyhead.py:903-1077, inference branch: head -> anchors -> ATSS post-processing -> list[BoxList]."""
+
+    def __init__(self, cfg, **kwargs):
+        super().__init__()
+        self.cfg = cfg
+        self.head = VLDyHead(cfg)
+        self._scales = None
+
+    def _reg_scales(self):
+        ps = [s.scale for s in self.head.scales]
+        key = tuple((p.data_ptr(), p._version) for p in ps)
+        if self._scales is None or self._scales[0] != key:
+            self._scales = (key, [float(p.detach().item()) for p in ps])
+        return self._scales[1]
+
+    @torch.no_grad()
+    def forward_flat(self, pyr16, levels, image_sizes, lang_hidden, lang_masks, positive_map, max_out=128):
+        """pyr16 [B,N,256] fp16 -> device-resident detections: dict(det [B,max_out,6], num [B], ...)."""
+        cfg = self.cfg
+        r = self.head.forward_flat(pyr16, levels, lang_hidden, lang_masks)
+        tokmap = ops.make_tokmap(positive_map, cfg.MODEL.DYHEAD.NUM_CLASSES - 1, pyr16.device)
+        ih, iw = image_sizes[0]
+        if any(tuple(s) != (ih, iw) for s in image_sizes):
+            raise NotImplementedError("forward_flat batches images of one size; use forward() per size group")
+        out = ops.atss_postprocess(r["dot_product_logits"], r["reg_ctr"], tokmap, levels, cfg.MODEL.RPN.ANCHOR_STRIDE,
+                                   cfg.MODEL.RPN.ANCHOR_SIZES, self._reg_scales()[:levels.n], float(iw), float(ih),
+                                   pre_nms_thresh=cfg.MODEL.ATSS.INFERENCE_TH, pre_nms_top_n=cfg.MODEL.ATSS.PRE_NMS_TOP_N,
+                                   nms_thresh=cfg.MODEL.ATSS.NMS_TH, max_det=cfg.MODEL.ATSS.DETECTIONS_PER_IMG,
+                                   max_out=max_out)
+        out["head"] = r
+        return out
+
+    @staticmethod
+    def to_boxlists(det, num, image_sizes):
+        """One device->host copy of the fixed-shape result, then BoxList(mode xyxy, fields labels/scores) per image."""
+        from ...structures.bounding_box import BoxList
+        det_h = det.cpu()
+        num_h = num.cpu()
+        res = []
+        for b, (h, w) in enumerate(image_sizes):
+            k = min(int(num_h[b]), det_h.shape[1])
+            bl = BoxList(det_h[b, :k, :4].clone(), (w, h), mode="xyxy")
+            bl.add_field("labels", det_h[b, :k, 5].long())
+            bl.add_field("scores", det_h[b, :k, 4].clone())
+            res.append(bl)
+        return res
+
+    @torch.no_grad()
+    def forward(self, images, features, targets=None, language_dict_features=None, positive_map=None, captions=None,
+                swint_feature_c4=None):
+        """Reference signature: features = list of [B,256,h,w]; returns (list[BoxList], {}, fused_visual_features)."""
+        if self.training:
+            raise NotImplementedError("training (ATSS loss / backward) is SURVEY.md §8f")
+        sizes = images.image_sizes if hasattr(images, "image_sizes") else [tuple(images.shape[-2:])] * features[0].shape[0]
+        levels = ops.Levels([(f.shape[2], f.shape[3]) for f in features], features[0].device)
+        v16 = ops.cast_f16(_flatten_levels(features))
+        out = self.forward_flat(v16, levels, sizes, language_dict_features["hidden"], language_dict_features["masks"],
+                                positive_map)
+        language_dict_features["hidden"] = out["head"]["hidden"]
+        return self.to_boxlists(out["det"], out["num"], sizes), {}, None

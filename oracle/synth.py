@@ -91,7 +91,7 @@ def bert_layer_sd(gen, p, dim=768, inter=3072, sd=None, std=0.02):
 def qvbert_sd(gen, vocab=30522, dim=768, layers=12, max_pos=512, start_qv=6):
     """QVBertModel parameters (modeling_bert_new.py:642-660): BERT-base + 6 GCP blocks + PreSelect."""
     sd = {}
-    sd["embeddings.word_embeddings.weight"] = gen.randn(vocab, dim, scale=0.05)
+    sd["embeddings.word_embeddings.weight"] = gen.randn(vocab, dim, scale=0.5)
     sd["embeddings.position_embeddings.weight"] = gen.randn(max_pos, dim, scale=0.05)
     sd["embeddings.token_type_embeddings.weight"] = gen.randn(2, dim, scale=0.05)
     gen.norm(dim, sd, "embeddings.LayerNorm")
@@ -123,7 +123,8 @@ def dot_head_sd(gen, p="", l_dim=768, channels=256, sd=None):
     """dot_product_projection_text, bias_lang, bias0, log_scale (vldyhead.py:711-720)."""
     sd = {} if sd is None else sd
     gen.linear(channels, l_dim, bias=True, sd=sd, name=p + "dot_product_projection_text")
-    sd[p + "bias_lang"] = gen.randn(l_dim, scale=0.05)
+    sd[p + "dot_product_projection_text.weight"] *= 20.0  # logits spread over several units so scores/top-k/NMS are non-degenerate
+    sd[p + "bias_lang"] = gen.randn(l_dim, scale=0.3)
     sd[p + "bias0"] = torch.tensor([-math.log((1 - 0.01) / 0.01)])
     sd[p + "log_scale"] = torch.tensor([0.0])
     return sd
@@ -243,3 +244,33 @@ def fpn_sd(gen, in_channels=(192, 384, 768), C=256, p=""):
         sd[f"{p}top_blocks.{k}.weight"] = gen.randn(C, C, 3, 3, scale=1.0 / math.sqrt(9 * C))
         sd[f"{p}top_blocks.{k}.bias"] = gen.randn(C, scale=0.05)
     return sd
+
+
+def detector_sd(gen, num_convs=6, bias0=None):
+    """Full MQ-GLIP-T parameter set with the reference's key names (277 M parameters)."""
+    sd = {}
+    sd.update({"backbone.body." + k: v for k, v in swin_sd(gen).items()})
+    sd.update({"backbone.fpn." + k: v for k, v in fpn_sd(gen).items()})
+    sd.update({"language_backbone.body.model." + k: v for k, v in qvbert_sd(gen).items()})
+    head = vldyhead_sd(gen, num_convs)
+    if bias0 is not None:
+        head["bias0"] = torch.tensor([float(bias0)])
+    sd.update({"rpn.head." + k: v for k, v in head.items()})
+    return sd
+
+
+def query_bank(positive_map, K, gen, dim=256):
+    """{label: FloatTensor[K, 1, dim]} — the on-disk bank format of extract_vision_query (query_selector.py:24,37)."""
+    return {label: gen.randn(K, 1, dim, scale=0.5) for label in sorted(positive_map)}
+
+
+def images(gen, B, h, w, size_divisibility=32, mean=(103.530, 116.280, 123.675), std=(57.375, 57.120, 58.395)):
+    """Synthetic BGR-255 images normalised like the reference transform, zero-padded to a multiple of 32
+    (configs/pretrain/mq-glip-t.yaml:84-85,95)."""
+    raw = torch.rand(B, 3, h, w, generator=gen.g) * 255.0
+    x = (raw - torch.tensor(mean).view(1, 3, 1, 1)) / torch.tensor(std).view(1, 3, 1, 1)
+    H = -(-h // size_divisibility) * size_divisibility
+    W = -(-w // size_divisibility) * size_divisibility
+    out = torch.zeros(B, 3, H, W)
+    out[:, :, :h, :w] = x
+    return out

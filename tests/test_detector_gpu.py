@@ -1,0 +1,70 @@
+"""End-to-end GPU parity of GeneralizedVLRCNN_New.forward (Swin-T -> FPN -> QuerySelector/PreSelect/GCP-BERT -> VLDyHead ->
+ATSS post-processing -> BoxList) against the CPU oracle on a small synthetic image, 10-class prompt, K=5 queries."""
+import pytest
+import torch
+
+from util import assert_close, load_sd
+
+pytestmark = pytest.mark.gpu
+
+
+def _iou(a, b):
+    x1, y1 = torch.max(a[:, None, 0], b[None, :, 0]), torch.max(a[:, None, 1], b[None, :, 1])
+    x2, y2 = torch.min(a[:, None, 2], b[None, :, 2]), torch.min(a[:, None, 3], b[None, :, 3])
+    inter = (x2 - x1 + 1).clamp(min=0) * (y2 - y1 + 1).clamp(min=0)
+    aa = (a[:, 2] - a[:, 0] + 1) * (a[:, 3] - a[:, 1] + 1)
+    ab = (b[:, 2] - b[:, 0] + 1) * (b[:, 3] - b[:, 1] + 1)
+    return inter / (aa[:, None] + ab[None] - inter)
+
+
+def test_detector_forward(dev):
+    from mqdet_b200.config import mq_glip_t_cfg
+    from mqdet_b200.modeling.detector.generalized_vl_rcnn_new import GeneralizedVLRCNN_New
+    from mqdet_b200.structures.bounding_box import BoxList
+    from oracle import restate, synth
+    gen = synth.Gen(2024)
+    sd = synth.detector_sd(gen, bias0=-1.5)  # the reference's -log(99) prior would leave no candidate above 0.05
+    ids, am, pmap = synth.prompt(10, 2, 256, gen)
+    bank = synth.query_bank(pmap, 5, gen)
+    B, h, w = 2, 150, 203
+    img = synth.images(gen, B, h, w)  # padded to 160 x 224
+    ref = restate.detector(img, (h, w), ids, am, pmap, bank, sd)
+
+    model = GeneralizedVLRCNN_New(mq_glip_t_cfg())
+    own = model.state_dict()
+    full = dict(sd)
+    for k in own:
+        if k.endswith("relative_position_index"):
+            full[k] = own[k]
+    model = load_sd(model, full).to(dev).eval()
+    model.query_selector.set_query_bank(bank)
+    from mqdet_b200.structures.image_list import ImageList
+    il = ImageList(img.to(dev), [(h, w)] * B)
+    out = model.forward_device(il, {"input_ids": ids, "attention_mask": am}, pmap)
+    bad = []
+    assert_close(out["head"]["hidden"], ref["fused_hidden"], 5e-3, "e2e: fused language stream", defer=bad)
+    assert_close(out["head"]["dot_product_logits"], ref["logits"], 5e-3, "e2e: dot-product logits", defer=bad)
+    assert not bad, bad
+    res = model(il, captions={"input_ids": ids, "attention_mask": am}, positive_map=pmap)
+    assert len(res) == B and all(isinstance(r, BoxList) for r in res)
+    for b, r in enumerate(res):
+        rb, rs, rl = ref["detections"][b]
+        assert r.mode == "xyxy" and r.size == (w, h)
+        assert r.get_field("labels").dtype == torch.int64 and r.get_field("scores").dtype == torch.float32
+        assert len(r) >= min(100, rb.shape[0]) - 5
+        # fp16-operand noise moves scores by ~1e-3: match detections instead of demanding identical index lists
+        iou = _iou(rb, r.bbox)
+        same = rl[:, None] == r.get_field("labels")[None]
+        matched = ((iou > 0.9) & same & ((rs[:, None] - r.get_field("scores")[None]).abs() < 5e-3)).any(1)
+        assert matched.float().mean().item() >= 0.9, f"image {b}: only {matched.float().mean().item():.2f} matched"
+        assert (r.bbox[:, 0] >= 0).all() and (r.bbox[:, 2] <= w - 1).all() and (r.bbox[:, 3] <= h - 1).all()
+
+
+def test_detector_rejects_cpu_and_strings():
+    from mqdet_b200._lib import MqdetError
+    from mqdet_b200.config import mq_glip_t_cfg
+    from mqdet_b200.modeling.detector.generalized_vl_rcnn_new import GeneralizedVLRCNN_New
+    m = GeneralizedVLRCNN_New(mq_glip_t_cfg(**{"MODEL.DYHEAD.NUM_CONVS": 1})).eval()
+    with pytest.raises(MqdetError):
+        m(torch.zeros(1, 3, 64, 64), captions={"input_ids": torch.zeros(1, 256, dtype=torch.long),
+                                               "attention_mask": torch.ones(1, 256, dtype=torch.long)}, positive_map={1: [1]})
