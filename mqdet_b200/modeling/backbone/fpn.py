@@ -55,7 +55,7 @@ class FPN(nn.Module):
         h5, w5 = sizes[-1]
         h6, w6 = (h5 + 2 - 3) // 2 + 1, (w5 + 2 - 3) // 2 + 1
         h7, w7 = (h6 + 2 - 3) // 2 + 1, (w6 + 2 - 3) // 2 + 1
-        levels = ops.Levels(sizes + [(h6, w6), (h7, w7)], dev)
+        levels = ops.get_levels(sizes + [(h6, w6), (h7, w7)], dev)
         pyr = torch.empty((B, levels.N, C), dtype=torch.float16, device=dev)
 
         def conv1x1(name, t):

@@ -48,6 +48,7 @@ class GeneralizedVLRCNN_New(nn.Module):
         self.query_selector = QuerySelector(cfg) if cfg.VISION_QUERY.ENABLED else None
         self.tokenizer = None  # attach an HF tokenizer to accept string captions
         self.DEBUG = False
+        self._prompt = None
 
     def load_query_bank(self, path):
         self.query_selector.load_query_bank(path)
@@ -76,6 +77,25 @@ class GeneralizedVLRCNN_New(nn.Module):
         return tok.input_ids.to(device), tok.attention_mask.to(device)
 
     @torch.no_grad()
+    def _prompt_state(self, captions, positive_map, B, dev):
+        """Everything that depends only on the prompt (token ids, selected vision queries, their token mask) is built
+        once per (captions, positive_map) object pair and batch size — the reference rebuilds it in every forward
+        (Python loops over classes in QuerySelector.forward :57-100 and a tokenizer call :378-383)."""
+        st = self._prompt
+        if st is not None and st["captions"] is captions and st["positive_map"] is positive_map and st["B"] == B:
+            return st
+        ids, am = self._tokenize(captions, dev)
+        if ids.shape[0] == 1 and B > 1:
+            ids, am = ids.expand(B, -1).contiguous(), am.expand(B, -1).contiguous()
+        vision = vmask = None
+        if self.query_selector is not None and self.query_selector.query_bank is not None:
+            labels, all_map = self.get_labels_and_maps_from_positive_map(positive_map)
+            vision, vmask, _ = self.query_selector([labels] * B, [all_map] * B, None)
+            vision, vmask = vision.float().contiguous(), vmask.float().contiguous()
+        self._prompt = dict(captions=captions, positive_map=positive_map, B=B, ids=ids, am=am, vision=vision, vmask=vmask)
+        return self._prompt
+
+    @torch.no_grad()
     def forward_device(self, images, captions, positive_map, max_out=128):
         """Everything up to (and excluding) the device->host copy: returns the device-resident result dict."""
         if self.training:
@@ -85,20 +105,13 @@ class GeneralizedVLRCNN_New(nn.Module):
         if not x.is_cuda:
             raise MqdetError("GeneralizedVLRCNN_New: CUDA images required (no CPU fallback)")
         B = x.shape[0]
-        dev = x.device
         feats = self.backbone.body.forward_flat(x)
         pyr16, levels = self.backbone.fpn.forward_flat([feats[i] for i in (1, 2, 3)])
-        ids, am = self._tokenize(captions, dev)
-        if ids.shape[0] == 1 and B > 1:
-            ids, am = ids.expand(B, -1).contiguous(), am.expand(B, -1).contiguous()
-        vision = vmask = pooled = None
-        if self.query_selector is not None and self.query_selector.query_bank is not None:
-            labels, all_map = self.get_labels_and_maps_from_positive_map(positive_map)
-            vision, vmask, _ = self.query_selector([labels] * B, [all_map] * B, None)
-            pooled = ops.avgpool2_levels(pyr16, levels)  # flatten_fpn_features (:291-293)
-        lang = self.language_backbone.body({"input_ids": ids, "attention_mask": am,
-                                            "vision_inputs": {"vision": vision, "images": pooled,
-                                                              "vision_attention_mask": vmask,
+        st = self._prompt_state(captions, positive_map, B, x.device)
+        pooled = ops.avgpool2_levels(pyr16, levels) if st["vision"] is not None else None  # flatten_fpn_features (:291-293)
+        lang = self.language_backbone.body({"input_ids": st["ids"], "attention_mask": st["am"],
+                                            "vision_inputs": {"vision": st["vision"], "images": pooled,
+                                                              "vision_attention_mask": st["vmask"],
                                                               "batched_pos_category_map": None}})
         out = self.rpn.forward_flat(pyr16, levels, images.image_sizes, lang["hidden"], lang["masks"], positive_map, max_out)
         out["image_sizes"] = images.image_sizes

@@ -136,7 +136,7 @@ class DyConv(nn.Module):
         feats = inputs["visual"]
         if not feats[0].is_cuda:
             raise MqdetError("DyConv: CUDA tensors required (no CPU fallback)")
-        levels = ops.Levels([(f.shape[2], f.shape[3]) for f in feats], feats[0].device)
+        levels = ops.get_levels([(f.shape[2], f.shape[3]) for f in feats], feats[0].device)
         x16 = ops.cast_f16(_flatten_levels(feats))
         out = ops.cast_f32(self.forward_flat(x16, levels))
         return {"visual": _split_levels(out, levels.sizes), "lang": inputs["lang"]}
@@ -265,7 +265,7 @@ class VLDyHead(nn.Module):
         """Reference signature (:769): x = list of [B,256,h,w]; returns the reference's 10-tuple of per-level lists."""
         if not x[0].is_cuda:
             raise MqdetError("VLDyHead: CUDA tensors required (no CPU fallback)")
-        levels = ops.Levels([(f.shape[2], f.shape[3]) for f in x], x[0].device)
+        levels = ops.get_levels([(f.shape[2], f.shape[3]) for f in x], x[0].device)
         v16 = ops.cast_f16(_flatten_levels(x))
         r = self.forward_flat(v16, levels, language_dict_features["hidden"], language_dict_features["masks"])
         B = v16.shape[0]
@@ -295,6 +295,7 @@ class VLDyHeadModule(nn.Module):
         self.cfg = cfg
         self.head = VLDyHead(cfg)
         self._scales = None
+        self._tokmap = None
 
     def _reg_scales(self):
         ps = [s.scale for s in self.head.scales]
@@ -308,7 +309,9 @@ class VLDyHeadModule(nn.Module):
         """pyr16 [B,N,256] fp16 -> device-resident detections: dict(det [B,max_out,6], num [B], ...)."""
         cfg = self.cfg
         r = self.head.forward_flat(pyr16, levels, lang_hidden, lang_masks)
-        tokmap = ops.make_tokmap(positive_map, cfg.MODEL.DYHEAD.NUM_CLASSES - 1, pyr16.device)
+        if self._tokmap is None or self._tokmap[0] is not positive_map:
+            self._tokmap = (positive_map, ops.make_tokmap(positive_map, cfg.MODEL.DYHEAD.NUM_CLASSES - 1, pyr16.device))
+        tokmap = self._tokmap[1]
         ih, iw = image_sizes[0]
         if any(tuple(s) != (ih, iw) for s in image_sizes):
             raise NotImplementedError("forward_flat batches images of one size; use forward() per size group")
@@ -342,7 +345,7 @@ class VLDyHeadModule(nn.Module):
         if self.training:
             raise NotImplementedError("training (ATSS loss / backward) is SURVEY.md §8f")
         sizes = images.image_sizes if hasattr(images, "image_sizes") else [tuple(images.shape[-2:])] * features[0].shape[0]
-        levels = ops.Levels([(f.shape[2], f.shape[3]) for f in features], features[0].device)
+        levels = ops.get_levels([(f.shape[2], f.shape[3]) for f in features], features[0].device)
         v16 = ops.cast_f16(_flatten_levels(features))
         out = self.forward_flat(v16, levels, sizes, language_dict_features["hidden"], language_dict_features["masks"],
                                 positive_map)

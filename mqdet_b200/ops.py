@@ -17,6 +17,9 @@ DEFAULT_GEMM_IMPL = IMPL_TCGEN05
 # number of kernels launched through this module since the last reset (bench.py's gpu_launches)
 launch_count = 0
 
+# bench.py sets this to a list to time every GEMM launch with CUDA events on the launching stream (roofline.achieved)
+GEMM_PROFILE = None
+
 
 def _stream():
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
@@ -107,7 +110,13 @@ def gemm(a, b, out=None, *, out_dtype=torch.float16, alpha=1.0, bias=None, bias_
         r4 = _as4(residual)
         g.R, g.r_dtype = r4.data_ptr(), _dt(residual)
         g.ldr, g.r_b1, g.r_b2 = r4.stride(2), bstride(r4, 1, nb1), bstride(r4, 0, nb2)
+    if GEMM_PROFILE is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
     check(load().mqdet_gemm_f16(ctypes.byref(g), DEFAULT_GEMM_IMPL if impl is None else impl, _stream()), "gemm")
+    if GEMM_PROFILE is not None:
+        e1.record()
+        GEMM_PROFILE.append((e0, e1, 2.0 * M * N * K * nb1 * nb2, (M, N, K, nb1 * nb2)))
     launch_count += 1
     return out
 
@@ -309,6 +318,18 @@ class Levels:
             (H, W), (Hs, Ws) = self.sizes[l], self.sizes[l + 1]
             ws.append((torch.outer(_upsample_colsum(Hs, H), _upsample_colsum(Ws, W)) / float(H * W)).reshape(-1))
         self.up_w = torch.cat(ws).float().to(device) if ws else None
+
+
+_levels_cache = {}
+
+
+def get_levels(sizes, device):
+    """Cached Levels (building one uploads small tables to the device)."""
+    key = (tuple((int(h), int(w)) for h, w in sizes), str(device))
+    lv = _levels_cache.get(key)
+    if lv is None:
+        lv = _levels_cache[key] = Levels(sizes, device)
+    return lv
 
 
 def _upsample_colsum(n_in, n_out):

@@ -99,3 +99,19 @@ def test_swin_fpn_golden():
         _cmp(fx, f"c{i + 3}", o, 1e-4)
     for i, o in enumerate(pyr):
         _cmp(fx, f"p{i + 3}", o, 1e-4)
+
+
+def test_dcn_fast_path_equals_gather_formulation():
+    """oracle dcn_v2: the torchvision fast path (used when offsets are not re-interpreted) equals the explicit restatement
+    of deform_conv_kernel_cuda.cu:578-641, for stride 1 and 2."""
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(2, 16, 9, 11, generator=g)
+    w = torch.randn(8, 16, 3, 3, generator=g) * 0.1
+    b = torch.randn(8, generator=g)
+    for stride in (1, 2):
+        Ho, Wo = (9 - 1) // stride + 1, (11 - 1) // stride + 1
+        off = torch.randn(2, 18 * Ho * Wo, generator=g) * 2
+        m = torch.rand(2, 9 * Ho * Wo, generator=g)
+        a = restate.dcn_v2(x, off, m, w, b, stride, fast=True)
+        c = restate.dcn_v2(x, off, m, w, b, stride, fast=False)
+        assert (a - c).abs().max().item() <= 1e-5
