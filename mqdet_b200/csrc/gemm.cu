@@ -40,6 +40,7 @@ struct GemmP {
   int r_dtype;
   long ldr, r_b1, r_b2;
   int a_bcast1, a_bcast2, b_bcast1, b_bcast2;  // 1 -> TMA coordinate pinned to 0
+  int use_tma_store;                           // epilogue variant (host decides from alignment / residual)
 };
 
 // One output element's epilogue, split so the tensor-core kernel can apply the residual in its coalesced phase:
@@ -106,7 +107,7 @@ struct TcCfg {
 template <int BN, int STAGES>
 __global__ void __launch_bounds__(256) gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a,
                                                       const __grid_constant__ CUtensorMap tma_b,
-                                                      const GemmP p) {
+                                                      const __grid_constant__ CUtensorMap tma_c, const GemmP p) {
   using Cfg = TcCfg<BN, STAGES>;
   extern __shared__ uint8_t smem_raw[];
   // 128B-swizzled tiles need 1024-byte alignment.
@@ -128,6 +129,7 @@ __global__ void __launch_bounds__(256) gemm_tc_kernel(const __grid_constant__ CU
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tma_a);
     tma_prefetch_desc(&tma_b);
+    if (p.use_tma_store) tma_prefetch_desc(&tma_c);
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
@@ -176,133 +178,174 @@ __global__ void __launch_bounds__(256) gemm_tc_kernel(const __grid_constant__ CU
       tc_commit(tmem_full_bar);  // accumulator complete
     }
   } else if (warp >= 4) {
-    // ---- epilogue ------------------------------------------------------------------------------------------
-    // phase 1: TMEM -> registers (thread == output row) -> RAW fp32 accumulators into a staging tile that re-uses the
-    //          (now idle) operand ring; rows padded by 16 B so the float4 stores are bank-conflict free.
-    // phase 2: lanes along columns (8 per lane, fixed for the whole tile): per-column bias/gate are loaded once,
-    //          then a rolled loop over rows applies alpha/bias/act/clamp/gate/residual and issues 16-byte coalesced
-    //          stores.  The whole epilogue is ~400 instructions: it is executed once per CTA, so code size (I-cache
-    //          misses), not ALU work, is what it is optimised for.
+    // ---- epilogue (4 warps; thread == output row == TMEM lane) -------------------------------------------------
+    // The operand ring is idle once tmem_full fires, so it doubles as the staging tile.  16 accumulator columns at
+    // a time: tcgen05.ld -> alpha/bias/act/clamp/gate in registers -> staging.
+    //   TMA-store variant (no residual, aligned C): values are converted to the output type and written in the
+    //     128B-swizzled box layout (chunk ^ (row & 7): conflict-free), then ONE thread issues cp.async.bulk.tensor
+    //     stores; the TMA unit clips the M/N edges.  ~350 instructions per thread for a 128x128 tile.
+    //   fallback variant: fp32 staging rows padded by 16 B, then a coalesced row loop adds the residual and stores.
     const int ew = warp - 4;  // == warp % 4 -> TMEM lane quarter this warp may access
     mbar_wait(tmem_full_bar, 0);
     tc_fence_after();
-    constexpr int LDS = BN + 4;  // staging row stride in floats
-    float* stage = reinterpret_cast<float*>(smem);
-    {
-      float4* dst = reinterpret_cast<float4*>(stage + (ew * 32 + lane) * LDS);
+    const int r_local = ew * 32 + lane;
+    const long row = (long)m_tile * BM + r_local;
+    float gate_s = 1.f;
+    if (p.gate_mode == MQDET_VEC_SCALAR) gate_s = p.gate_tanh ? tanhf(p.gate[0]) : p.gate[0];
+    if (p.gate_mode == MQDET_VEC_PER_ROW && row < p.M) gate_s = p.gate_tanh ? tanhf(p.gate[row]) : p.gate[row];
+    float brow = 0.f;
+    if (p.bias_mode == MQDET_VEC_PER_ROW && row < p.M) brow = p.bias[z1 * p.bias_b1 + z2 * p.bias_b2 + row];
+    const float* bias_col = (p.bias_mode == MQDET_VEC_PER_COL) ? p.bias + z1 * p.bias_b1 + z2 * p.bias_b2 : nullptr;
+    const float* gate_col = (p.gate_mode == MQDET_VEC_PER_COL) ? p.gate : nullptr;
+    constexpr int LDS = BN + 4;  // fallback staging row stride (floats)
+    float* stage32 = reinterpret_cast<float*>(smem);
 #pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32) {
-        uint32_t r[32];
-        tmem_ld_32x32(tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)c0, r);
-        tmem_ld_wait();
+    for (int c0 = 0; c0 < BN; c0 += 16) {
+      uint32_t r[16];
+      tmem_ld_32x16(tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)c0, r);
+      tmem_ld_wait();
+      const long col0 = (long)n_tile * BN + c0;
+      float v[16];
+      const bool inb = col0 + 16 <= p.N;
 #pragma unroll
-        for (int i = 0; i < 8; ++i)
-          dst[c0 / 4 + i] = make_float4(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1]),
-                                        __uint_as_float(r[4 * i + 2]), __uint_as_float(r[4 * i + 3]));
+      for (int i = 0; i < 16; ++i) {
+        float b = brow;
+        if (bias_col && (inb || col0 + i < p.N)) b = bias_col[col0 + i];
+        const float a = __uint_as_float(r[i]);
+        v[i] = p.scale_after_bias ? p.alpha * (a + b) : fmaf(p.alpha, a, b);
       }
-    }
-    tc_fence_before();
-    asm volatile("bar.sync 1, 128;" ::: "memory");  // the 4 epilogue warps only
-
-    constexpr int LPR = BN / 8;  // lanes per row (8 columns each)
-    constexpr int RPW = 32 / LPR;  // rows per warp per iteration
-    const int lc = (lane % LPR) * 8;
-    const long col = (long)n_tile * BN + lc;
-    if (col < p.N) {
-      const bool full = col + 8 <= p.N;
-      const bool c_vec = full && ((p.ldc & 7) == 0) && ((p.c_b1 & 7) == 0) && ((p.c_b2 & 7) == 0) &&
-                         ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0);
-      const bool r_vec = full && p.R && ((p.ldr & 7) == 0) && ((p.r_b1 & 7) == 0) && ((p.r_b2 & 7) == 0) &&
-                         ((reinterpret_cast<uintptr_t>(p.R) & 15) == 0);
-      float bcol[8], gcol[8];
+      if (p.act == MQDET_ACT_GELU) {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        bcol[i] = 0.f;
-        gcol[i] = 1.f;
+        for (int i = 0; i < 16; ++i) v[i] = gelu_erf(v[i]);
+      } else if (p.act == MQDET_ACT_RELU) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.f);
       }
-      if (p.bias_mode == MQDET_VEC_PER_COL) {
-        const float* bp = p.bias + z1 * p.bias_b1 + z2 * p.bias_b2 + col;
+      if (p.clamp > 0.f) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i)
-          if (col + i < p.N) bcol[i] = bp[i];
+        for (int i = 0; i < 16; ++i) v[i] = fminf(fmaxf(v[i], -p.clamp), p.clamp);
       }
-      if (p.gate_mode == MQDET_VEC_PER_COL) {
+      if (gate_col) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i)
-          if (col + i < p.N) gcol[i] = p.gate_tanh ? tanhf(p.gate[col + i]) : p.gate[col + i];
-      } else if (p.gate_mode == MQDET_VEC_SCALAR) {
-        const float g = p.gate_tanh ? tanhf(p.gate[0]) : p.gate[0];
+        for (int i = 0; i < 16; ++i)
+          if (inb || col0 + i < p.N) v[i] *= p.gate_tanh ? tanhf(gate_col[col0 + i]) : gate_col[col0 + i];
+      } else if (p.gate_mode != MQDET_VEC_NONE) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) gcol[i] = g;
+        for (int i = 0; i < 16; ++i) v[i] *= gate_s;
       }
-      const long c_base = z1 * p.c_b1 + z2 * p.c_b2 + col;
-      const long r_base = z1 * p.r_b1 + z2 * p.r_b2 + col;
-#pragma unroll 1
-      for (int rl = ew * RPW + lane / LPR; rl < BM; rl += 4 * RPW) {
-        const long grow = (long)m_tile * BM + rl;
-        if (grow >= p.M) break;
-        const float4 s0 = *reinterpret_cast<const float4*>(stage + rl * LDS + lc);
-        const float4 s1 = *reinterpret_cast<const float4*>(stage + rl * LDS + lc + 4);
-        float v[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
-        float brow = 0.f, grow_g = 1.f;
-        if (p.bias_mode == MQDET_VEC_PER_ROW) brow = p.bias[z1 * p.bias_b1 + z2 * p.bias_b2 + grow];
-        if (p.gate_mode == MQDET_VEC_PER_ROW) grow_g = p.gate_tanh ? tanhf(p.gate[grow]) : p.gate[grow];
+      if (p.use_tma_store) {
+        if (p.c_dtype == MQDET_F16) {
+          // column block of 64 halfs (128 B rows); this thread's 16 columns = chunks j0, j0+1
+          uint8_t* blk = smem + (c0 >> 6) * (BM * 128) + r_local * 128;
+          const int j0 = (c0 & 63) >> 3;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const float b = bcol[i] + brow;
-          float t = p.scale_after_bias ? p.alpha * (v[i] + b) : fmaf(p.alpha, v[i], b);
-          if (p.act == MQDET_ACT_GELU)
-            t = gelu_erf(t);
-          else if (p.act == MQDET_ACT_RELU)
-            t = fmaxf(t, 0.f);
-          if (p.clamp > 0.f) t = fminf(fmaxf(t, -p.clamp), p.clamp);
-          v[i] = t * gcol[i] * grow_g;
-        }
-        if (p.R) {
-          if (r_vec) {
-            if (p.r_dtype == MQDET_F32) {
-              const float* rp = reinterpret_cast<const float*>(p.R) + r_base + grow * p.ldr;
-              const float4 a = *reinterpret_cast<const float4*>(rp);
-              const float4 b = *reinterpret_cast<const float4*>(rp + 4);
-              v[0] += a.x; v[1] += a.y; v[2] += a.z; v[3] += a.w;
-              v[4] += b.x; v[5] += b.y; v[6] += b.z; v[7] += b.w;
-            } else {
-              const uint4 u = *reinterpret_cast<const uint4*>(reinterpret_cast<const __half*>(p.R) + r_base + grow * p.ldr);
-              const __half2* h = reinterpret_cast<const __half2*>(&u);
-#pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                const float2 f = __half22float2(h[i]);
-                v[2 * i] += f.x;
-                v[2 * i + 1] += f.y;
-              }
-            }
-          } else {
-#pragma unroll 1
-            for (int i = 0; i < 8; ++i)
-              if (col + i < p.N) v[i] += ld_residual(p, grow, col + i, z1, z2);
-          }
-        }
-        if (c_vec) {
-          if (p.c_dtype == MQDET_F32) {
-            float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.C) + c_base + grow * p.ldc);
-            dst[0] = make_float4(v[0], v[1], v[2], v[3]);
-            dst[1] = make_float4(v[4], v[5], v[6], v[7]);
-          } else {
-            __half2 h0 = __floats2half2_rn(v[0], v[1]);
-            __half2 h1 = __floats2half2_rn(v[2], v[3]);
-            __half2 h2 = __floats2half2_rn(v[4], v[5]);
-            __half2 h3 = __floats2half2_rn(v[6], v[7]);
+          for (int h = 0; h < 2; ++h) {
+            __half2 h0 = __floats2half2_rn(v[8 * h + 0], v[8 * h + 1]);
+            __half2 h1 = __floats2half2_rn(v[8 * h + 2], v[8 * h + 3]);
+            __half2 h2 = __floats2half2_rn(v[8 * h + 4], v[8 * h + 5]);
+            __half2 h3 = __floats2half2_rn(v[8 * h + 6], v[8 * h + 7]);
             uint4 u;
             u.x = *reinterpret_cast<uint32_t*>(&h0);
             u.y = *reinterpret_cast<uint32_t*>(&h1);
             u.z = *reinterpret_cast<uint32_t*>(&h2);
             u.w = *reinterpret_cast<uint32_t*>(&h3);
-            *reinterpret_cast<uint4*>(reinterpret_cast<__half*>(p.C) + c_base + grow * p.ldc) = u;
+            *reinterpret_cast<uint4*>(blk + (((j0 + h) ^ (r_local & 7)) << 4)) = u;
           }
         } else {
+          // column block of 32 floats (128 B rows); 16 columns = chunks j0 .. j0+3
+          uint8_t* blk = smem + (c0 >> 5) * (BM * 128) + r_local * 128;
+          const int j0 = (c0 & 31) >> 2;
+#pragma unroll
+          for (int h = 0; h < 4; ++h)
+            *reinterpret_cast<float4*>(blk + (((j0 + h) ^ (r_local & 7)) << 4)) =
+                make_float4(v[4 * h], v[4 * h + 1], v[4 * h + 2], v[4 * h + 3]);
+        }
+      } else {
+        float4* dst = reinterpret_cast<float4*>(stage32 + r_local * LDS + c0);
+#pragma unroll
+        for (int h = 0; h < 4; ++h) dst[h] = make_float4(v[4 * h], v[4 * h + 1], v[4 * h + 2], v[4 * h + 3]);
+      }
+    }
+    tc_fence_before();
+    if (p.use_tma_store) {
+      fence_proxy_async();  // generic-proxy smem writes -> visible to the TMA (async proxy)
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (threadIdx.x == 128) {
+        const int cz1 = p.nb1 == 1 ? 0 : z1, cz2 = p.nb2 == 1 ? 0 : z2;
+        const int cpb = (p.c_dtype == MQDET_F16) ? 64 : 32;  // columns per 128-byte block
+        for (int cb = 0; cb * cpb < BN; ++cb) {
+          const long cc = (long)n_tile * BN + cb * cpb;
+          if (cc < p.N) tma_store_4d(&tma_c, smem + cb * (BM * 128), (int)cc, m_tile * BM, cz1, cz2);
+        }
+        tma_store_commit_and_wait_read();  // smem must stay intact until the TMA has read it
+      }
+    } else {
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      constexpr int LPR = BN / 8;    // lanes per row (8 columns each)
+      constexpr int RPW = 32 / LPR;  // rows per warp per iteration
+      const int lc = (lane % LPR) * 8;
+      const long col = (long)n_tile * BN + lc;
+      if (col < p.N) {
+        const bool full = col + 8 <= p.N;
+        const bool c_vec = full && ((p.ldc & 7) == 0) && ((p.c_b1 & 7) == 0) && ((p.c_b2 & 7) == 0) &&
+                           ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0);
+        const bool r_vec = full && p.R && ((p.ldr & 7) == 0) && ((p.r_b1 & 7) == 0) && ((p.r_b2 & 7) == 0) &&
+                           ((reinterpret_cast<uintptr_t>(p.R) & 15) == 0);
+        const long c_base = z1 * p.c_b1 + z2 * p.c_b2 + col;
+        const long r_base = z1 * p.r_b1 + z2 * p.r_b2 + col;
 #pragma unroll 1
-          for (int i = 0; i < 8; ++i)
-            if (col + i < p.N) store_one(p, v[i], grow, col + i, z1, z2);
+        for (int rl = ew * RPW + lane / LPR; rl < BM; rl += 4 * RPW) {
+          const long grow = (long)m_tile * BM + rl;
+          if (grow >= p.M) break;
+          const float4 s0 = *reinterpret_cast<const float4*>(stage32 + rl * LDS + lc);
+          const float4 s1 = *reinterpret_cast<const float4*>(stage32 + rl * LDS + lc + 4);
+          float v[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+          if (p.R) {
+            if (r_vec) {
+              if (p.r_dtype == MQDET_F32) {
+                const float* rp = reinterpret_cast<const float*>(p.R) + r_base + grow * p.ldr;
+                const float4 a = *reinterpret_cast<const float4*>(rp);
+                const float4 b = *reinterpret_cast<const float4*>(rp + 4);
+                v[0] += a.x; v[1] += a.y; v[2] += a.z; v[3] += a.w;
+                v[4] += b.x; v[5] += b.y; v[6] += b.z; v[7] += b.w;
+              } else {
+                const uint4 u = *reinterpret_cast<const uint4*>(reinterpret_cast<const __half*>(p.R) + r_base + grow * p.ldr);
+                const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  const float2 f = __half22float2(h[i]);
+                  v[2 * i] += f.x;
+                  v[2 * i + 1] += f.y;
+                }
+              }
+            } else {
+#pragma unroll 1
+              for (int i = 0; i < 8; ++i)
+                if (col + i < p.N) v[i] += ld_residual(p, grow, col + i, z1, z2);
+            }
+          }
+          if (c_vec) {
+            if (p.c_dtype == MQDET_F32) {
+              float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.C) + c_base + grow * p.ldc);
+              dst[0] = make_float4(v[0], v[1], v[2], v[3]);
+              dst[1] = make_float4(v[4], v[5], v[6], v[7]);
+            } else {
+              __half2 h0 = __floats2half2_rn(v[0], v[1]);
+              __half2 h1 = __floats2half2_rn(v[2], v[3]);
+              __half2 h2 = __floats2half2_rn(v[4], v[5]);
+              __half2 h3 = __floats2half2_rn(v[6], v[7]);
+              uint4 u;
+              u.x = *reinterpret_cast<uint32_t*>(&h0);
+              u.y = *reinterpret_cast<uint32_t*>(&h1);
+              u.z = *reinterpret_cast<uint32_t*>(&h2);
+              u.w = *reinterpret_cast<uint32_t*>(&h3);
+              *reinterpret_cast<uint4*>(reinterpret_cast<__half*>(p.C) + c_base + grow * p.ldc) = u;
+            }
+          } else {
+#pragma unroll 1
+            for (int i = 0; i < 8; ++i)
+              if (col + i < p.N) store_one(p, v[i], grow, col + i, z1, z2);
+          }
         }
       }
     }
@@ -409,6 +452,40 @@ static int make_operand_map(CUtensorMap* map, const void* ptr, long rows, long K
   return MQDET_OK;
 }
 
+// 4-D map over the OUTPUT viewed as [b2][b1][M][N]; box = [1][1][128 rows][128 bytes], 128B swizzle (TMA store).
+static int make_output_map(CUtensorMap* map, const GemmP& p) {
+  PFN_encodeTiled enc = get_encode_fn();
+  if (!enc) return MQDET_ERR_CUDA;
+  const int es = (p.c_dtype == MQDET_F16) ? 2 : 4;
+  cuuint64_t dims[4] = {(cuuint64_t)p.N, (cuuint64_t)p.M, (cuuint64_t)p.nb1, (cuuint64_t)p.nb2};
+  cuuint64_t strides[3] = {(cuuint64_t)p.ldc * es, (cuuint64_t)(p.nb1 > 1 ? p.c_b1 : p.ldc * p.M) * es,
+                           (cuuint64_t)(p.nb2 > 1 ? p.c_b2 : p.ldc * p.M) * es};
+  cuuint32_t box[4] = {(cuuint32_t)(128 / es), (cuuint32_t)BM, 1, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(map, p.c_dtype == MQDET_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, p.C,
+                   dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled(C) failed (%d): M=%ld N=%ld ldc=%ld", (int)r, p.M, p.N, p.ldc);
+    return MQDET_ERR_CUDA;
+  }
+  return MQDET_OK;
+}
+
+// TMA store needs 16-byte aligned rows/batches, and the epilogue variant without residual.
+static bool can_tma_store(const GemmP& p, int BN) {
+  const int es = (p.c_dtype == MQDET_F16) ? 2 : 4;
+  const long al = 16 / es;
+  if (p.R || BN < 128 / es) return false;
+  if (p.N % al) return false;  // the TMA unit bounds the innermost dimension at 16-byte granularity (measured): a ragged
+                               // N would spill into the row padding, so those shapes take the masked fallback
+  if ((reinterpret_cast<uintptr_t>(p.C) & 15) || (p.ldc % al) || (p.nb1 > 1 && (p.c_b1 % al)) || (p.nb2 > 1 && (p.c_b2 % al)))
+    return false;
+  if (p.nb1 > 1 && p.c_b1 == 0) return false;
+  if (p.nb2 > 1 && p.c_b2 == 0) return false;
+  return true;
+}
+
 template <int BN, int STAGES>
 static int launch_tc(const GemmP& p0, cudaStream_t st) {
   using Cfg = TcCfg<BN, STAGES>;
@@ -418,6 +495,12 @@ static int launch_tc(const GemmP& p0, cudaStream_t st) {
   if (rc) return rc;
   rc = make_operand_map(&mb, p.B, p.N, p.K, p.ldb, p.nb1, p.b_b1, p.nb2, p.b_b2, BN, &p.b_bcast1, &p.b_bcast2);
   if (rc) return rc;
+  CUtensorMap mc = ma;  // placeholder when unused
+  p.use_tma_store = can_tma_store(p, BN) ? 1 : 0;
+  if (p.use_tma_store) {
+    rc = make_output_map(&mc, p);
+    if (rc) return rc;
+  }
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -429,7 +512,7 @@ static int launch_tc(const GemmP& p0, cudaStream_t st) {
     attr_set = true;
   }
   dim3 grid(cdiv(p.N, BN), cdiv(p.M, BM), p.nb1 * p.nb2);
-  gemm_tc_kernel<BN, STAGES><<<grid, 256, Cfg::SMEM_BYTES, st>>>(ma, mb, p);
+  gemm_tc_kernel<BN, STAGES><<<grid, 256, Cfg::SMEM_BYTES, st>>>(ma, mb, mc, p);
   return check_launch("gemm_tc_kernel");
 }
 
