@@ -48,7 +48,7 @@ __device__ __forceinline__ void st8h(__half* p, const float (&f)[8]) {
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// DCNv2 / plain 3x3 sampling -> column matrix.   One warp per (output pixel, tap); lanes across C (8 ch / lane).
+// DCNv2 / plain 3x3 sampling -> column matrix.   One warp per output pixel (9 taps); lanes across C (8 ch / lane).
 // branch 1: input level l -> output level l, stride 1   (rows: all levels, N per image)
 // branch 2: input level l-1 -> output level l, stride 2 (rows: levels 1..L-1)
 // branch 0: input level l+1, output at level l+1's size, offsets/mask of level l re-read through the OUTPUT strides
@@ -62,20 +62,15 @@ template <int C>
 __global__ void __launch_bounds__(256) dcn_cols_kernel(const __half* __restrict__ x, const float* __restrict__ om,
                                                        int om_ld, LevelTable lt, int branch, int B, long rows_per_img,
                                                        __half* __restrict__ cols) {
-  const long gw = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;  // global warp = (row, tap)
+  // one warp per OUTPUT PIXEL, looping over the 9 taps: the level lookup / coordinate arithmetic is done once, the 27
+  // offset/mask values of the pixel are fetched by 27 lanes in one request and broadcast with shuffles.
+  const long r = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
-  const long total = (long)B * rows_per_img * 9;
-  if (gw >= total) return;
-  const int tap = (int)(gw % 9);
-  const long r = gw / 9;
+  if (r >= (long)B * rows_per_img) return;
   const int b = (int)(r / rows_per_img);
-  int q = (int)(r % rows_per_img);  // row within this image's output rows
+  int q = (int)(r % rows_per_img);
   const int N = lt.off[lt.n - 1] + lt.H[lt.n - 1] * lt.W[lt.n - 1];
-  // locate output level
-  int lo;      // level whose offsets are used
-  int li;      // input level
-  int Ho, Wo;  // output grid
-  int stride;
+  int lo, li, Ho, Wo, stride;
   if (branch == 1) {
     int l = 0;
     while (l + 1 < lt.n && q >= lt.off[l + 1]) ++l;
@@ -92,57 +87,71 @@ __global__ void __launch_bounds__(256) dcn_cols_kernel(const __half* __restrict_
   }
   const int ho = q / Wo, wo = q % Wo;
   const int Hi = lt.H[li], Wi = lt.W[li];
-  const int ti = tap / 3, tj = tap % 3;
-  float off_h = 0.f, off_w = 0.f, m = 1.f;
-  if (om) {
+  // lane c < 27 fetches channel c of this pixel's offset/mask record (flat NCHW index c*HWo + pix re-read through the
+  // strides of the level the buffer was produced at)
+  float omv = 0.f;
+  if (om && lane < 27) {
     const int HWl = lt.H[lo] * lt.W[lo];
-    const float* omb = om + ((long)b * N + lt.off[lo]) * om_ld;
     const int HWo = Ho * Wo, pix = ho * Wo + wo;
-    const int fh = (2 * tap) * HWo + pix, fw = (2 * tap + 1) * HWo + pix, fm = tap * HWo + pix;
-    off_h = omb[(long)(fh % HWl) * om_ld + fh / HWl];
-    off_w = omb[(long)(fw % HWl) * om_ld + fw / HWl];
-    const float ml = omb[(long)(fm % HWl) * om_ld + 18 + fm / HWl];
-    m = 1.f / (1.f + expf(-ml));
+    const float* omb = om + ((long)b * N + lt.off[lo]) * om_ld;
+    if (lane < 18) {
+      const int f = lane * HWo + pix;
+      omv = omb[(long)(f % HWl) * om_ld + f / HWl];
+    } else {
+      const int f = (lane - 18) * HWo + pix;
+      const float ml = omb[(long)(f % HWl) * om_ld + 18 + f / HWl];
+      omv = 1.f / (1.f + expf(-ml));
+    }
   }
-  const float h_im = (float)(ho * stride - 1 + ti) + off_h;
-  const float w_im = (float)(wo * stride - 1 + tj) + off_w;
-  float acc[8];
-#pragma unroll
-  for (int i = 0; i < 8; ++i) acc[i] = 0.f;
-  if (h_im > -1.f && w_im > -1.f && h_im < (float)Hi && w_im < (float)Wi) {
-    const int h_low = (int)floorf(h_im), w_low = (int)floorf(w_im);
-    const int h_high = h_low + 1, w_high = w_low + 1;
-    const float lh = h_im - h_low, lw = w_im - w_low, hh = 1.f - lh, hw = 1.f - lw;
-    const __half* xb = x + ((long)b * N + lt.off[li]) * C + lane * 8;
-    float v[8];
-    if (h_low >= 0 && w_low >= 0) {
-      ld8h(xb + (long)(h_low * Wi + w_low) * C, v);
-      const float w1 = hh * hw;
-#pragma unroll
-      for (int i = 0; i < 8; ++i) acc[i] += w1 * v[i];
+  const __half* xb = x + ((long)b * N + lt.off[li]) * C + lane * 8;
+  __half* dst = cols + r * 9 * C + lane * 8;
+#pragma unroll 1
+  for (int tap = 0; tap < 9; ++tap) {
+    float off_h = 0.f, off_w = 0.f, m = 1.f;
+    if (om) {
+      off_h = __shfl_sync(0xffffffffu, omv, 2 * tap);
+      off_w = __shfl_sync(0xffffffffu, omv, 2 * tap + 1);
+      m = __shfl_sync(0xffffffffu, omv, 18 + tap);
     }
-    if (h_low >= 0 && w_high <= Wi - 1) {
-      ld8h(xb + (long)(h_low * Wi + w_high) * C, v);
-      const float w2 = hh * lw;
+    const float h_im = (float)(ho * stride - 1 + tap / 3) + off_h;
+    const float w_im = (float)(wo * stride - 1 + tap % 3) + off_w;
+    float acc[8];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) acc[i] += w2 * v[i];
+    for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+    if (h_im > -1.f && w_im > -1.f && h_im < (float)Hi && w_im < (float)Wi) {
+      const int h_low = (int)floorf(h_im), w_low = (int)floorf(w_im);
+      const int h_high = h_low + 1, w_high = w_low + 1;
+      const float lh = h_im - h_low, lw = w_im - w_low, hh = 1.f - lh, hw = 1.f - lw;
+      float v[8];
+      if (h_low >= 0 && w_low >= 0) {
+        ld8h(xb + (long)(h_low * Wi + w_low) * C, v);
+        const float w1 = hh * hw;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i] += w1 * v[i];
+      }
+      if (h_low >= 0 && w_high <= Wi - 1) {
+        ld8h(xb + (long)(h_low * Wi + w_high) * C, v);
+        const float w2 = hh * lw;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i] += w2 * v[i];
+      }
+      if (h_high <= Hi - 1 && w_low >= 0) {
+        ld8h(xb + (long)(h_high * Wi + w_low) * C, v);
+        const float w3 = lh * hw;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i] += w3 * v[i];
+      }
+      if (h_high <= Hi - 1 && w_high <= Wi - 1) {
+        ld8h(xb + (long)(h_high * Wi + w_high) * C, v);
+        const float w4 = lh * lw;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i] += w4 * v[i];
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[i] *= m;
     }
-    if (h_high <= Hi - 1 && w_low >= 0) {
-      ld8h(xb + (long)(h_high * Wi + w_low) * C, v);
-      const float w3 = lh * hw;
-#pragma unroll
-      for (int i = 0; i < 8; ++i) acc[i] += w3 * v[i];
-    }
-    if (h_high <= Hi - 1 && w_high <= Wi - 1) {
-      ld8h(xb + (long)(h_high * Wi + w_high) * C, v);
-      const float w4 = lh * lw;
-#pragma unroll
-      for (int i = 0; i < 8; ++i) acc[i] += w4 * v[i];
-    }
-#pragma unroll
-    for (int i = 0; i < 8; ++i) acc[i] *= m;
+    st8h(dst + tap * C, acc);
   }
-  st8h(cols + (r * 9 + tap) * C + lane * 8, acc);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -400,7 +409,7 @@ extern "C" int mqdet_dcn_cols(const void* x, const float* om, int64_t om_ld, con
   MQ_REQUIRE(N > 0, "dcn_cols: bad level table");
   MQ_REQUIRE(branch == 1 || nlev >= 2, "dcn_cols: branches 0/2 need at least two levels");
   const long rows_per_img = branch == 1 ? N : N - lt.H[0] * lt.W[0];
-  const long warps = B * rows_per_img * 9;
+  const long warps = B * rows_per_img;
   const long blocks = (warps * 32 + 255) / 256;
   dcn_cols_kernel<256><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((const __half*)x, om, (int)om_ld, lt, branch,
                                                                           (int)B, rows_per_img, (__half*)cols);

@@ -111,6 +111,113 @@ __global__ void __launch_bounds__(256) softmax_rows_kernel(const T* __restrict__
   }
 }
 
+// Vectorised fp16 row softmax (rows 16-byte aligned, n % 8 == 0): one warp per row, 8 halfs per lane per step.
+//   ITERS > 0 : the whole row (n <= ITERS*256) lives in registers -> one read, one write      (A: n = 256 tokens)
+//   ITERS == 0: two passes, online max/sum then normalise                                     (At: n = 22400 locations)
+template <int ITERS>
+__global__ void __launch_bounds__(256) softmax_rows_f16v_kernel(const __half* __restrict__ x, long ldx, __half* __restrict__ y,
+                                                                long ldy, long rows, int n, int n_pad, float scale,
+                                                                const float* __restrict__ colmask, long rows_per_batch,
+                                                                float mask_value, float keep_add) {
+  const long row = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const __half* xr = x + row * ldx;
+  __half* yr = y + row * ldy;
+  const float* cm = colmask ? colmask + (row / rows_per_batch) * n : nullptr;
+  auto load8 = [&](int c, float (&v)[8]) {
+    const uint4 u = *reinterpret_cast<const uint4*>(xr + c);
+    const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 f = __half22float2(h[i]);
+      v[2 * i] = f.x * scale;
+      v[2 * i + 1] = f.y * scale;
+    }
+    if (cm) {
+      const float4 m0 = *reinterpret_cast<const float4*>(cm + c);
+      const float4 m1 = *reinterpret_cast<const float4*>(cm + c + 4);
+      const float mm[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] += (mm[i] == 0.f) ? mask_value : keep_add;
+    }
+  };
+  auto store8 = [&](int c, const float (&v)[8]) {
+    __half2 h[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) h[i] = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
+    *reinterpret_cast<uint4*>(yr + c) = *reinterpret_cast<uint4*>(h);
+  };
+  if (ITERS > 0) {
+    float v[ITERS > 0 ? ITERS : 1][8];
+    float mx = -INFINITY;
+#pragma unroll
+    for (int it = 0; it < ITERS; ++it) {
+      const int c = it * 256 + lane * 8;
+      if (c < n) {
+        load8(c, v[it]);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) mx = fmaxf(mx, v[it][i]);
+      }
+    }
+    mx = warp_max(mx);
+    float sum = 0.f;
+#pragma unroll
+    for (int it = 0; it < ITERS; ++it) {
+      const int c = it * 256 + lane * 8;
+      if (c < n) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          v[it][i] = expf(v[it][i] - mx);
+          sum += v[it][i];
+        }
+      }
+    }
+    const float inv = 1.f / warp_sum(sum);
+#pragma unroll
+    for (int it = 0; it < ITERS; ++it) {
+      const int c = it * 256 + lane * 8;
+      if (c < n) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[it][i] *= inv;
+        store8(c, v[it]);
+      } else if (c < n_pad) {
+        const float z[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        store8(c, z);
+      }
+    }
+  } else {
+    float mx = -INFINITY, sum = 0.f;  // online (max, sum) per lane, merged across the warp afterwards
+    for (int c = lane * 8; c < n; c += 256) {
+      float v[8];
+      load8(c, v);
+      float m2 = mx;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) m2 = fmaxf(m2, v[i]);
+      float s2 = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) s2 += expf(v[i] - m2);
+      sum = sum * expf(mx - m2) + s2;
+      mx = m2;
+    }
+    const float gmx = warp_max(mx);
+    const float gsum = warp_sum(sum * expf(mx - gmx));  // lanes with no element: mx = -inf -> contributes 0
+    const float inv = 1.f / gsum;
+    for (int c = lane * 8; c < n_pad; c += 256) {
+      float v[8];
+      if (c < n) {
+        load8(c, v);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = expf(v[i] - gmx) * inv;
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = 0.f;
+      }
+      store8(c, v);
+    }
+  }
+}
+
 __global__ void cast_f32_f16_kernel(const float* __restrict__ x, __half* __restrict__ y, long n) {
   long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
   const long stride = (long)gridDim.x * blockDim.x;
@@ -194,6 +301,22 @@ extern "C" int mqdet_softmax_rows(const void* x, int in_dtype, int64_t ldx, void
   const int wpb = 8;
   dim3 grid(cdiv(rows, wpb));
   cudaStream_t st = (cudaStream_t)stream;
+  const bool vec = in_dtype == MQDET_F16 && (n % 8) == 0 && (n_pad % 8) == 0 && (ldx % 8) == 0 && (ldy % 8) == 0 &&
+                   ((uintptr_t)x % 16) == 0 && ((uintptr_t)y % 16) == 0 && (!colmask || ((uintptr_t)colmask % 16) == 0);
+  if (vec) {
+    const __half* xh = (const __half*)x;
+    __half* yh = (__half*)y;
+    if (n_pad <= 256)
+      softmax_rows_f16v_kernel<1><<<grid, wpb * 32, 0, st>>>(xh, ldx, yh, ldy, rows, (int)n, (int)n_pad, scale, colmask,
+                                                            rows_per_batch, mask_value, keep_add);
+    else if (n_pad <= 1024)
+      softmax_rows_f16v_kernel<4><<<grid, wpb * 32, 0, st>>>(xh, ldx, yh, ldy, rows, (int)n, (int)n_pad, scale, colmask,
+                                                            rows_per_batch, mask_value, keep_add);
+    else
+      softmax_rows_f16v_kernel<0><<<grid, wpb * 32, 0, st>>>(xh, ldx, yh, ldy, rows, (int)n, (int)n_pad, scale, colmask,
+                                                            rows_per_batch, mask_value, keep_add);
+    return check_launch("softmax_rows_f16v_kernel");
+  }
   if (in_dtype == MQDET_F32)
     softmax_rows_kernel<float><<<grid, wpb * 32, 0, st>>>((const float*)x, ldx, (__half*)y, ldy, rows, (int)n, (int)n_pad,
                                                          scale, colmask, rows_per_batch, mask_value, keep_add);
