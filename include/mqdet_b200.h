@@ -39,8 +39,9 @@ extern "C" {
 #define MQDET_VEC_PER_COL 2 /* length N */
 #define MQDET_VEC_PER_ROW 3 /* length M */
 
-#define MQDET_GEMM_IMPL_TCGEN05 0 /* TMA + tcgen05.mma + TMEM (product path) */
+#define MQDET_GEMM_IMPL_TCGEN05 0 /* TMA + tcgen05.mma + TMEM, persistent tile loop, double-buffered TMEM (product path) */
 #define MQDET_GEMM_IMPL_SIMT 1    /* plain shared-memory tiled fp32-FMA kernel (validation only) */
+#define MQDET_GEMM_IMPL_TCGEN05_ONESHOT 2 /* tcgen05, one tile per CTA (non-persistent variant, A/B measurements) */
 
 const char* mqdet_last_error(void);
 int mqdet_version(void);
@@ -118,6 +119,13 @@ int mqdet_gcp_build_index(const float* mask, int64_t B, int64_t V, int64_t T, in
 int mqdet_softmax_rows(const void* x, int in_dtype, int64_t ldx, void* y, int64_t ldy, int64_t rows, int64_t n,
                        int64_t n_pad, float scale, const float* colmask, int64_t rows_per_batch, float mask_value,
                        float keep_add, void* stream);
+
+/* Column softmax with transposed output: P[z][t][0:Np] = softmax_n(A[z][n][t]) (zero beyond N), fp16 in/out.
+ * BiAttention text->image direction (fuse_helper.py:257-268) without a second QK^T product.  T <= 256, T % 8 == 0.
+ * workspace: mqdet_colsoftmax_workspace_floats(Z, N, T) floats. */
+int64_t mqdet_colsoftmax_workspace_floats(int64_t Z, int64_t N, int64_t T);
+int mqdet_colsoftmax_transposed(const void* A, int64_t Z, int64_t N, int64_t T, void* P, int64_t Np, float* workspace,
+                                void* stream);
 
 /* Text side of the dot-product token head (vldyhead.py:810,818): e = x / max(||x||, eps) written as fp16 and/or
  * fp32, dot[r] = e[r,:] . w + b0[0] (w, b0, dot optional). */

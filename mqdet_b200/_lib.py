@@ -13,7 +13,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libmqdet_b200.so")
 F16, F32 = 0, 1
 ACT_NONE, ACT_GELU, ACT_RELU = 0, 1, 2
 VEC_NONE, VEC_SCALAR, VEC_PER_COL, VEC_PER_ROW = 0, 1, 2, 3
-IMPL_TCGEN05, IMPL_SIMT = 0, 1
+IMPL_TCGEN05, IMPL_SIMT, IMPL_TCGEN05_ONESHOT = 0, 1, 2
 
 
 class GemmArgs(ctypes.Structure):
@@ -52,6 +52,8 @@ SIGNATURES = {
     "mqdet_gcp_build_index": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_int64, c_void_p, c_void_p, c_void_p]),
     "mqdet_softmax_rows": (c_int, [c_void_p, c_int, c_int64, c_void_p, c_int64, c_int64, c_int64, c_int64, c_float,
                                    c_void_p, c_int64, c_float, c_float, c_void_p]),
+    "mqdet_colsoftmax_workspace_floats": (c_int64, [c_int64, c_int64, c_int64]),
+    "mqdet_colsoftmax_transposed": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_int64, c_void_p, c_void_p]),
     "mqdet_l2norm_rowdot": (c_int, [c_void_p, c_int64, c_int64, c_float, c_void_p, c_void_p, c_void_p, c_void_p,
                                     c_void_p, c_void_p]),
     "mqdet_cast_f32_f16": (c_int, [c_void_p, c_void_p, c_int64, c_void_p]),

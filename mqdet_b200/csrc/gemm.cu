@@ -96,6 +96,225 @@ __device__ __forceinline__ void store_one(const GemmP& p, float v, long row, lon
 constexpr int BM = 128;
 constexpr int BK = 64;  // 64 fp16 = 128 B = one swizzle row
 
+// ---- epilogue of one 128 x BN tile (4 warps; thread == output row == TMEM lane) -------------------------------------
+// 16 accumulator columns at a time: tcgen05.ld -> alpha/bias/act/clamp/gate in registers -> staging tile `stg`.
+//   TMA-store variant (no residual, aligned C): values are converted to the output type and written in the
+//     128B-swizzled box layout (chunk ^ (row & 7): conflict-free), then ONE thread issues cp.async.bulk.tensor
+//     stores; the TMA unit clips the M/N edges.  ~350 instructions per thread for a 128x128 tile.
+//   fallback variant: fp32 staging rows padded by 16 B, then a coalesced row loop adds the residual and stores.
+// tmem_empty_bar != nullptr (persistent kernel): arrive on it as soon as the accumulator has been read, and end with a
+// barrier of the 4 epilogue warps so the staging tile can be rewritten for the next tile.
+template <int BN>
+__device__ __forceinline__ void epilogue_tile(const GemmP& p, const CUtensorMap* tma_c, uint32_t tmem_acc, uint8_t* stg,
+                                              int m_tile, int n_tile, int z1, int z2, int ew, int lane,
+                                              uint64_t* tmem_empty_bar, int pend = 0, int half = 0, int nhalf = 1) {
+  // nhalf == 2: eight epilogue warps, two per TMEM lane quarter, each taking one half of the tile's columns
+  // ---- epilogue (4 warps; thread == output row == TMEM lane) -------------------------------------------------
+  // The operand ring is idle once tmem_full fires, so it doubles as the staging tile.  16 accumulator columns at
+  // a time: tcgen05.ld -> alpha/bias/act/clamp/gate in registers -> staging.
+  //   TMA-store variant (no residual, aligned C): values are converted to the output type and written in the
+  //     128B-swizzled box layout (chunk ^ (row & 7): conflict-free), then ONE thread issues cp.async.bulk.tensor
+  //     stores; the TMA unit clips the M/N edges.  ~350 instructions per thread for a 128x128 tile.
+  //   fallback variant: fp32 staging rows padded by 16 B, then a coalesced row loop adds the residual and stores.
+  const int r_local = ew * 32 + lane;
+  const long row = (long)m_tile * BM + r_local;
+  float gate_s = 1.f;
+  if (p.gate_mode == MQDET_VEC_SCALAR) gate_s = p.gate_tanh ? tanhf(p.gate[0]) : p.gate[0];
+  if (p.gate_mode == MQDET_VEC_PER_ROW && row < p.M) gate_s = p.gate_tanh ? tanhf(p.gate[row]) : p.gate[row];
+  float brow = 0.f;
+  if (p.bias_mode == MQDET_VEC_PER_ROW && row < p.M) brow = p.bias[z1 * p.bias_b1 + z2 * p.bias_b2 + row];
+  const float* bias_col = (p.bias_mode == MQDET_VEC_PER_COL) ? p.bias + z1 * p.bias_b1 + z2 * p.bias_b2 : nullptr;
+  const float* gate_col = (p.gate_mode == MQDET_VEC_PER_COL) ? p.gate : nullptr;
+  // parameter block -> registers once (the compiler otherwise re-reads the constant bank inside the unrolled loops)
+  const float alpha = p.alpha, clampv = p.clamp;
+  const int act = p.act;
+  const bool sab = p.scale_after_bias != 0, gate_tanh = p.gate_tanh != 0;
+  const bool has_gate_s = (p.gate_mode == MQDET_VEC_SCALAR) || (p.gate_mode == MQDET_VEC_PER_ROW);
+  const float brow_eff = sab ? alpha * brow : brow;  // alpha*(acc + b) == fma(alpha, acc, alpha*b)
+  constexpr int LDS = BN + 4;  // fallback staging row stride (floats)
+  float* stage32 = reinterpret_cast<float*>(stg);
+  const int nthr_epi = 128 * nhalf;
+#pragma unroll 1
+  for (int c0 = half * (BN / nhalf); c0 < (half + 1) * (BN / nhalf); c0 += 16) {
+    uint32_t r[16];
+    tmem_ld_32x16(tmem_acc + ((uint32_t)(ew * 32) << 16) + (uint32_t)c0, r);
+    tmem_ld_wait();
+    const long col0 = (long)n_tile * BN + c0;
+    // Every mode test below is warp-uniform and hoisted around a whole straight-line 16-element loop: the epilogue
+    // is issue-bound (4 warps per tile), so per-element predicates/parameter reloads are what must be avoided.
+    float v[16];
+    const bool inb = col0 + 16 <= p.N;
+    if (bias_col) {
+      float b[16];
+      if (inb && ((reinterpret_cast<uintptr_t>(bias_col + col0) & 15) == 0)) {
+        const float4* b4 = reinterpret_cast<const float4*>(bias_col + col0);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float4 t = b4[q];
+          b[4 * q] = t.x; b[4 * q + 1] = t.y; b[4 * q + 2] = t.z; b[4 * q + 3] = t.w;
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) b[i] = (col0 + i < p.N) ? bias_col[col0 + i] : 0.f;
+      }
+      if (sab) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = alpha * (__uint_as_float(r[i]) + b[i]);
+      } else {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = fmaf(alpha, __uint_as_float(r[i]), b[i]);
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) v[i] = fmaf(alpha, __uint_as_float(r[i]), brow_eff);
+    }
+    if (act == MQDET_ACT_GELU) {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) v[i] = gelu_erf(v[i]);
+    } else if (act == MQDET_ACT_RELU) {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.f);
+    }
+    if (clampv > 0.f) {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) v[i] = fminf(fmaxf(v[i], -clampv), clampv);
+    }
+    if (gate_col) {
+      if (inb) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] *= gate_tanh ? tanhf(gate_col[col0 + i]) : gate_col[col0 + i];
+      } else {
+#pragma unroll
+        for (int i = 0; i < 16; ++i)
+          if (col0 + i < p.N) v[i] *= gate_tanh ? tanhf(gate_col[col0 + i]) : gate_col[col0 + i];
+      }
+    } else if (has_gate_s) {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) v[i] *= gate_s;
+    }
+    if (p.use_tma_store) {
+      if (p.c_dtype == MQDET_F16) {
+        // column block of 64 halfs (128 B rows); this thread's 16 columns = chunks j0, j0+1
+        uint8_t* blk = stg + (c0 >> 6) * (BM * 128) + r_local * 128;
+        const int j0 = (c0 & 63) >> 3;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          __half2 h0 = __floats2half2_rn(v[8 * h + 0], v[8 * h + 1]);
+          __half2 h1 = __floats2half2_rn(v[8 * h + 2], v[8 * h + 3]);
+          __half2 h2 = __floats2half2_rn(v[8 * h + 4], v[8 * h + 5]);
+          __half2 h3 = __floats2half2_rn(v[8 * h + 6], v[8 * h + 7]);
+          uint4 u;
+          u.x = *reinterpret_cast<uint32_t*>(&h0);
+          u.y = *reinterpret_cast<uint32_t*>(&h1);
+          u.z = *reinterpret_cast<uint32_t*>(&h2);
+          u.w = *reinterpret_cast<uint32_t*>(&h3);
+          *reinterpret_cast<uint4*>(blk + (((j0 + h) ^ (r_local & 7)) << 4)) = u;
+        }
+      } else {
+        // column block of 32 floats (128 B rows); 16 columns = chunks j0 .. j0+3
+        uint8_t* blk = stg + (c0 >> 5) * (BM * 128) + r_local * 128;
+        const int j0 = (c0 & 31) >> 2;
+#pragma unroll
+        for (int h = 0; h < 4; ++h)
+          *reinterpret_cast<float4*>(blk + (((j0 + h) ^ (r_local & 7)) << 4)) =
+              make_float4(v[4 * h], v[4 * h + 1], v[4 * h + 2], v[4 * h + 3]);
+      }
+    } else {
+      float4* dst = reinterpret_cast<float4*>(stage32 + r_local * LDS + c0);
+#pragma unroll
+      for (int h = 0; h < 4; ++h) dst[h] = make_float4(v[4 * h], v[4 * h + 1], v[4 * h + 2], v[4 * h + 3]);
+    }
+  }
+  tc_fence_before();
+  if (tmem_empty_bar) {  // persistent kernel: the accumulator buffer may be overwritten by the next tile's MMAs
+    __syncwarp();
+    if (lane == 0) mbar_arrive(tmem_empty_bar);
+  }
+  if (p.use_tma_store) {
+    fence_proxy_async();  // generic-proxy smem writes -> visible to the TMA (async proxy)
+    asm volatile("bar.sync 1, %0;" ::"r"(nthr_epi) : "memory");
+    if (ew == 0 && half == 0 && lane == 0) {
+      const int cz1 = p.nb1 == 1 ? 0 : z1, cz2 = p.nb2 == 1 ? 0 : z2;
+      const int cpb = (p.c_dtype == MQDET_F16) ? 64 : 32;  // columns per 128-byte block
+      for (int cb = 0; cb * cpb < BN; ++cb) {
+        const long cc = (long)n_tile * BN + cb * cpb;
+        if (cc < p.N) tma_store_4d(tma_c, stg + cb * (BM * 128), (int)cc, m_tile * BM, cz1, cz2);
+      }
+      tma_store_commit_and_wait_read();  // smem must stay intact until the TMA has read it
+    }
+  } else {
+    asm volatile("bar.sync 1, %0;" ::"r"(nthr_epi) : "memory");
+    constexpr int LPR = BN / 8;    // lanes per row (8 columns each)
+    constexpr int RPW = 32 / LPR;  // rows per warp per iteration
+    const int lc = (lane % LPR) * 8;
+    const long col = (long)n_tile * BN + lc;
+    if (col < p.N) {
+      const bool full = col + 8 <= p.N;
+      const bool c_vec = full && ((p.ldc & 7) == 0) && ((p.c_b1 & 7) == 0) && ((p.c_b2 & 7) == 0) &&
+                         ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0);
+      const bool r_vec = full && p.R && ((p.ldr & 7) == 0) && ((p.r_b1 & 7) == 0) && ((p.r_b2 & 7) == 0) &&
+                         ((reinterpret_cast<uintptr_t>(p.R) & 15) == 0);
+      const long c_base = z1 * p.c_b1 + z2 * p.c_b2 + col;
+      const long r_base = z1 * p.r_b1 + z2 * p.r_b2 + col;
+#pragma unroll 1
+      for (int rl = (ew + 4 * half) * RPW + lane / LPR; rl < BM; rl += 4 * nhalf * RPW) {
+        const long grow = (long)m_tile * BM + rl;
+        if (grow >= p.M) break;
+        const float4 s0 = *reinterpret_cast<const float4*>(stage32 + rl * LDS + lc);
+        const float4 s1 = *reinterpret_cast<const float4*>(stage32 + rl * LDS + lc + 4);
+        float v[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+        if (p.R) {
+          if (r_vec) {
+            if (p.r_dtype == MQDET_F32) {
+              const float* rp = reinterpret_cast<const float*>(p.R) + r_base + grow * p.ldr;
+              const float4 a = *reinterpret_cast<const float4*>(rp);
+              const float4 b = *reinterpret_cast<const float4*>(rp + 4);
+              v[0] += a.x; v[1] += a.y; v[2] += a.z; v[3] += a.w;
+              v[4] += b.x; v[5] += b.y; v[6] += b.z; v[7] += b.w;
+            } else {
+              const uint4 u = *reinterpret_cast<const uint4*>(reinterpret_cast<const __half*>(p.R) + r_base + grow * p.ldr);
+              const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const float2 f = __half22float2(h[i]);
+                v[2 * i] += f.x;
+                v[2 * i + 1] += f.y;
+              }
+            }
+          } else {
+#pragma unroll 1
+            for (int i = 0; i < 8; ++i)
+              if (col + i < p.N) v[i] += ld_residual(p, grow, col + i, z1, z2);
+          }
+        }
+        if (c_vec) {
+          if (p.c_dtype == MQDET_F32) {
+            float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.C) + c_base + grow * p.ldc);
+            dst[0] = make_float4(v[0], v[1], v[2], v[3]);
+            dst[1] = make_float4(v[4], v[5], v[6], v[7]);
+          } else {
+            __half2 h0 = __floats2half2_rn(v[0], v[1]);
+            __half2 h1 = __floats2half2_rn(v[2], v[3]);
+            __half2 h2 = __floats2half2_rn(v[4], v[5]);
+            __half2 h3 = __floats2half2_rn(v[6], v[7]);
+            uint4 u;
+            u.x = *reinterpret_cast<uint32_t*>(&h0);
+            u.y = *reinterpret_cast<uint32_t*>(&h1);
+            u.z = *reinterpret_cast<uint32_t*>(&h2);
+            u.w = *reinterpret_cast<uint32_t*>(&h3);
+            *reinterpret_cast<uint4*>(reinterpret_cast<__half*>(p.C) + c_base + grow * p.ldc) = u;
+          }
+        } else {
+#pragma unroll 1
+          for (int i = 0; i < 8; ++i)
+            if (col + i < p.N) store_one(p, v[i], grow, col + i, z1, z2);
+        }
+      }
+    }
+  }
+    if (tmem_empty_bar) asm volatile("bar.sync 1, %0;" ::"r"(nthr_epi) : "memory");
+}
+
 template <int BN, int STAGES>
 struct TcCfg {
   static constexpr int A_BYTES = BM * BK * 2;
@@ -178,182 +397,189 @@ __global__ void __launch_bounds__(256) gemm_tc_kernel(const __grid_constant__ CU
       tc_commit(tmem_full_bar);  // accumulator complete
     }
   } else if (warp >= 4) {
-    // ---- epilogue (4 warps; thread == output row == TMEM lane) -------------------------------------------------
-    // The operand ring is idle once tmem_full fires, so it doubles as the staging tile.  16 accumulator columns at
-    // a time: tcgen05.ld -> alpha/bias/act/clamp/gate in registers -> staging.
-    //   TMA-store variant (no residual, aligned C): values are converted to the output type and written in the
-    //     128B-swizzled box layout (chunk ^ (row & 7): conflict-free), then ONE thread issues cp.async.bulk.tensor
-    //     stores; the TMA unit clips the M/N edges.  ~350 instructions per thread for a 128x128 tile.
-    //   fallback variant: fp32 staging rows padded by 16 B, then a coalesced row loop adds the residual and stores.
-    const int ew = warp - 4;  // == warp % 4 -> TMEM lane quarter this warp may access
     mbar_wait(tmem_full_bar, 0);
     tc_fence_after();
-    const int r_local = ew * 32 + lane;
-    const long row = (long)m_tile * BM + r_local;
-    float gate_s = 1.f;
-    if (p.gate_mode == MQDET_VEC_SCALAR) gate_s = p.gate_tanh ? tanhf(p.gate[0]) : p.gate[0];
-    if (p.gate_mode == MQDET_VEC_PER_ROW && row < p.M) gate_s = p.gate_tanh ? tanhf(p.gate[row]) : p.gate[row];
-    float brow = 0.f;
-    if (p.bias_mode == MQDET_VEC_PER_ROW && row < p.M) brow = p.bias[z1 * p.bias_b1 + z2 * p.bias_b2 + row];
-    const float* bias_col = (p.bias_mode == MQDET_VEC_PER_COL) ? p.bias + z1 * p.bias_b1 + z2 * p.bias_b2 : nullptr;
-    const float* gate_col = (p.gate_mode == MQDET_VEC_PER_COL) ? p.gate : nullptr;
-    constexpr int LDS = BN + 4;  // fallback staging row stride (floats)
-    float* stage32 = reinterpret_cast<float*>(smem);
-#pragma unroll 1
-    for (int c0 = 0; c0 < BN; c0 += 16) {
-      uint32_t r[16];
-      tmem_ld_32x16(tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)c0, r);
-      tmem_ld_wait();
-      const long col0 = (long)n_tile * BN + c0;
-      float v[16];
-      const bool inb = col0 + 16 <= p.N;
-#pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        float b = brow;
-        if (bias_col && (inb || col0 + i < p.N)) b = bias_col[col0 + i];
-        const float a = __uint_as_float(r[i]);
-        v[i] = p.scale_after_bias ? p.alpha * (a + b) : fmaf(p.alpha, a, b);
-      }
-      if (p.act == MQDET_ACT_GELU) {
-#pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] = gelu_erf(v[i]);
-      } else if (p.act == MQDET_ACT_RELU) {
-#pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.f);
-      }
-      if (p.clamp > 0.f) {
-#pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] = fminf(fmaxf(v[i], -p.clamp), p.clamp);
-      }
-      if (gate_col) {
-#pragma unroll
-        for (int i = 0; i < 16; ++i)
-          if (inb || col0 + i < p.N) v[i] *= p.gate_tanh ? tanhf(gate_col[col0 + i]) : gate_col[col0 + i];
-      } else if (p.gate_mode != MQDET_VEC_NONE) {
-#pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] *= gate_s;
-      }
-      if (p.use_tma_store) {
-        if (p.c_dtype == MQDET_F16) {
-          // column block of 64 halfs (128 B rows); this thread's 16 columns = chunks j0, j0+1
-          uint8_t* blk = smem + (c0 >> 6) * (BM * 128) + r_local * 128;
-          const int j0 = (c0 & 63) >> 3;
-#pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            __half2 h0 = __floats2half2_rn(v[8 * h + 0], v[8 * h + 1]);
-            __half2 h1 = __floats2half2_rn(v[8 * h + 2], v[8 * h + 3]);
-            __half2 h2 = __floats2half2_rn(v[8 * h + 4], v[8 * h + 5]);
-            __half2 h3 = __floats2half2_rn(v[8 * h + 6], v[8 * h + 7]);
-            uint4 u;
-            u.x = *reinterpret_cast<uint32_t*>(&h0);
-            u.y = *reinterpret_cast<uint32_t*>(&h1);
-            u.z = *reinterpret_cast<uint32_t*>(&h2);
-            u.w = *reinterpret_cast<uint32_t*>(&h3);
-            *reinterpret_cast<uint4*>(blk + (((j0 + h) ^ (r_local & 7)) << 4)) = u;
-          }
-        } else {
-          // column block of 32 floats (128 B rows); 16 columns = chunks j0 .. j0+3
-          uint8_t* blk = smem + (c0 >> 5) * (BM * 128) + r_local * 128;
-          const int j0 = (c0 & 31) >> 2;
-#pragma unroll
-          for (int h = 0; h < 4; ++h)
-            *reinterpret_cast<float4*>(blk + (((j0 + h) ^ (r_local & 7)) << 4)) =
-                make_float4(v[4 * h], v[4 * h + 1], v[4 * h + 2], v[4 * h + 3]);
-        }
-      } else {
-        float4* dst = reinterpret_cast<float4*>(stage32 + r_local * LDS + c0);
-#pragma unroll
-        for (int h = 0; h < 4; ++h) dst[h] = make_float4(v[4 * h], v[4 * h + 1], v[4 * h + 2], v[4 * h + 3]);
-      }
-    }
-    tc_fence_before();
-    if (p.use_tma_store) {
-      fence_proxy_async();  // generic-proxy smem writes -> visible to the TMA (async proxy)
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      if (threadIdx.x == 128) {
-        const int cz1 = p.nb1 == 1 ? 0 : z1, cz2 = p.nb2 == 1 ? 0 : z2;
-        const int cpb = (p.c_dtype == MQDET_F16) ? 64 : 32;  // columns per 128-byte block
-        for (int cb = 0; cb * cpb < BN; ++cb) {
-          const long cc = (long)n_tile * BN + cb * cpb;
-          if (cc < p.N) tma_store_4d(&tma_c, smem + cb * (BM * 128), (int)cc, m_tile * BM, cz1, cz2);
-        }
-        tma_store_commit_and_wait_read();  // smem must stay intact until the TMA has read it
-      }
-    } else {
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      constexpr int LPR = BN / 8;    // lanes per row (8 columns each)
-      constexpr int RPW = 32 / LPR;  // rows per warp per iteration
-      const int lc = (lane % LPR) * 8;
-      const long col = (long)n_tile * BN + lc;
-      if (col < p.N) {
-        const bool full = col + 8 <= p.N;
-        const bool c_vec = full && ((p.ldc & 7) == 0) && ((p.c_b1 & 7) == 0) && ((p.c_b2 & 7) == 0) &&
-                           ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0);
-        const bool r_vec = full && p.R && ((p.ldr & 7) == 0) && ((p.r_b1 & 7) == 0) && ((p.r_b2 & 7) == 0) &&
-                           ((reinterpret_cast<uintptr_t>(p.R) & 15) == 0);
-        const long c_base = z1 * p.c_b1 + z2 * p.c_b2 + col;
-        const long r_base = z1 * p.r_b1 + z2 * p.r_b2 + col;
-#pragma unroll 1
-        for (int rl = ew * RPW + lane / LPR; rl < BM; rl += 4 * RPW) {
-          const long grow = (long)m_tile * BM + rl;
-          if (grow >= p.M) break;
-          const float4 s0 = *reinterpret_cast<const float4*>(stage32 + rl * LDS + lc);
-          const float4 s1 = *reinterpret_cast<const float4*>(stage32 + rl * LDS + lc + 4);
-          float v[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
-          if (p.R) {
-            if (r_vec) {
-              if (p.r_dtype == MQDET_F32) {
-                const float* rp = reinterpret_cast<const float*>(p.R) + r_base + grow * p.ldr;
-                const float4 a = *reinterpret_cast<const float4*>(rp);
-                const float4 b = *reinterpret_cast<const float4*>(rp + 4);
-                v[0] += a.x; v[1] += a.y; v[2] += a.z; v[3] += a.w;
-                v[4] += b.x; v[5] += b.y; v[6] += b.z; v[7] += b.w;
-              } else {
-                const uint4 u = *reinterpret_cast<const uint4*>(reinterpret_cast<const __half*>(p.R) + r_base + grow * p.ldr);
-                const __half2* h = reinterpret_cast<const __half2*>(&u);
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                  const float2 f = __half22float2(h[i]);
-                  v[2 * i] += f.x;
-                  v[2 * i + 1] += f.y;
-                }
-              }
-            } else {
-#pragma unroll 1
-              for (int i = 0; i < 8; ++i)
-                if (col + i < p.N) v[i] += ld_residual(p, grow, col + i, z1, z2);
-            }
-          }
-          if (c_vec) {
-            if (p.c_dtype == MQDET_F32) {
-              float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.C) + c_base + grow * p.ldc);
-              dst[0] = make_float4(v[0], v[1], v[2], v[3]);
-              dst[1] = make_float4(v[4], v[5], v[6], v[7]);
-            } else {
-              __half2 h0 = __floats2half2_rn(v[0], v[1]);
-              __half2 h1 = __floats2half2_rn(v[2], v[3]);
-              __half2 h2 = __floats2half2_rn(v[4], v[5]);
-              __half2 h3 = __floats2half2_rn(v[6], v[7]);
-              uint4 u;
-              u.x = *reinterpret_cast<uint32_t*>(&h0);
-              u.y = *reinterpret_cast<uint32_t*>(&h1);
-              u.z = *reinterpret_cast<uint32_t*>(&h2);
-              u.w = *reinterpret_cast<uint32_t*>(&h3);
-              *reinterpret_cast<uint4*>(reinterpret_cast<__half*>(p.C) + c_base + grow * p.ldc) = u;
-            }
-          } else {
-#pragma unroll 1
-            for (int i = 0; i < 8; ++i)
-              if (col + i < p.N) store_one(p, v[i], grow, col + i, z1, z2);
-          }
-        }
-      }
-    }
+    // the operand ring is idle once tmem_full fires, so it doubles as the staging tile
+    epilogue_tile<BN>(p, &tma_c, tmem_base, smem, m_tile, n_tile, z1, z2, warp - 4, lane, nullptr);
   }
   __syncthreads();
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc(tmem_base, BN);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Persistent variant: one CTA per SM walks tiles (n fastest, so neighbouring CTAs share the A panel through L2).
+//   * the TMA ring keeps streaming across tile boundaries (no pipeline drain/fill per tile),
+//   * TWO TMEM accumulators (2*BN columns): the MMA warp fills buffer i&1 while the epilogue warps drain the other,
+//   * the epilogue has its own staging tile, so TMEM->smem->TMA-store overlaps the next tile's loads and MMAs,
+//   * barrier init / TMEM allocation / descriptor prefetch are paid once per SM instead of once per tile.
+// ---------------------------------------------------------------------------------------------
+//   * BRES (K <= 256): the B tile (BN x K) stays resident in shared memory while the CTA walks a run of M tiles, so only A
+//     is streamed -> half the L2->SM traffic of the short-K products that are otherwise bound by it.
+constexpr int BRES_KB = 4;  // resident B covers K <= 4*64
+
+template <int BN, int STAGES, bool BRES>
+struct TcpCfg {
+  static constexpr int A_BYTES = BM * BK * 2;
+  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int STAGE_BYTES = BRES ? A_BYTES : A_BYTES + B_BYTES;
+  static constexpr int RING_BYTES = STAGES * STAGE_BYTES + (BRES ? BRES_KB * B_BYTES : 0);
+  // fp32 padded rows (fallback epilogue) >= swizzled tiles; the 256-wide tile is only dispatched with the fp16 TMA-store
+  // epilogue (64 KB) because its fallback tile would not fit next to the ring
+  static constexpr int STG_BYTES = BN == 256 ? BM * BN * 2 : ((BM * (BN + 4) * 4 + 1023) / 1024) * 1024;
+  static constexpr int SMEM_BYTES = RING_BYTES + STG_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+template <int BN, int STAGES, bool BRES>
+__global__ void __launch_bounds__(384, 1) gemm_tcp_kernel(const __grid_constant__ CUtensorMap tma_a,
+                                                          const __grid_constant__ CUtensorMap tma_b,
+                                                          const __grid_constant__ CUtensorMap tma_c, const GemmP p,
+                                                          int tiles_m, int tiles_n, int total_items, int mc) {
+  // Work items.  !BRES: item == tile (n fastest).  BRES: item == (z, chunk of `mc` consecutive M tiles, n tile), n fastest,
+  // so CTAs running side by side share the A panel through L2 while each keeps its own B tile resident.
+  using Cfg = TcpCfg<BN, STAGES, BRES>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + STAGES * Cfg::A_BYTES;  // ring stages (!BRES) or the resident B tile (BRES)
+  uint8_t* stg = smem + Cfg::RING_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::RING_BYTES + Cfg::STG_BYTES);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + STAGES;
+  uint64_t* tmem_full_bar = bars + 2 * STAGES;       // [2]
+  uint64_t* tmem_empty_bar = bars + 2 * STAGES + 2;  // [2]
+  uint64_t* b_full_bar = bars + 2 * STAGES + 4;
+  uint64_t* b_empty_bar = bars + 2 * STAGES + 5;
+  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 6);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int num_kb = (int)((p.K + BK - 1) / BK);
+  const int nchunks = BRES ? (tiles_m + mc - 1) / mc : 1;
+  // fp16 TMA-store tiles are 32 KB (BN=128): two of them fit the staging area -> stores of tile i overlap tile i+1
+  const bool stg2 = p.use_tma_store && p.c_dtype == MQDET_F16 && 2 * BM * BN * 2 <= Cfg::STG_BYTES;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tma_a);
+    tma_prefetch_desc(&tma_b);
+    if (p.use_tma_store) tma_prefetch_desc(&tma_c);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&tmem_full_bar[b], 1);
+      mbar_init(&tmem_empty_bar[b], 8);  // one arrival per epilogue warp (8 of them)
+    }
+    mbar_init(b_full_bar, 1);
+    mbar_init(b_empty_bar, 1);
+    fence_mbar_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_base_slot, 2 * BN);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_base_slot;
+
+  // item -> (z, first m tile, #m tiles, n tile)
+  auto decode = [&](int item, int& z, int& m0, int& mcount, int& n_tile) {
+    n_tile = item % tiles_n;
+    if (BRES) {
+      const int c = (item / tiles_n) % nchunks;
+      z = item / (tiles_n * nchunks);
+      m0 = c * mc;
+      mcount = min(mc, tiles_m - m0);
+    } else {
+      m0 = (item / tiles_n) % tiles_m;
+      z = item / (tiles_n * tiles_m);
+      mcount = 1;
+    }
+  };
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int it = 0, li = 0;  // ring position / local item counter
+      for (int item = blockIdx.x; item < total_items; item += gridDim.x, ++li) {
+        int z, m0, mcount, n_tile;
+        decode(item, z, m0, mcount, n_tile);
+        const int z1 = z % p.nb1, z2 = z / p.nb1;
+        const int az1 = p.a_bcast1 ? 0 : z1, az2 = p.a_bcast2 ? 0 : z2;
+        const int bz1 = p.b_bcast1 ? 0 : z1, bz2 = p.b_bcast2 ? 0 : z2;
+        if (BRES) {
+          mbar_wait(b_empty_bar, (li & 1) ^ 1);  // the previous item's MMAs no longer read the resident tile
+          mbar_expect_tx(b_full_bar, num_kb * Cfg::B_BYTES);
+          for (int kb = 0; kb < num_kb; ++kb)
+            tma_load_4d(smem_b + kb * Cfg::B_BYTES, &tma_b, b_full_bar, kb * BK, n_tile * BN, bz1, bz2);
+        }
+        for (int mt = 0; mt < mcount; ++mt) {
+          for (int kb = 0; kb < num_kb; ++kb, ++it) {
+            const int s = it % STAGES;
+            const uint32_t ph = (it / STAGES) & 1;
+            mbar_wait(&empty_bar[s], ph ^ 1);
+            mbar_expect_tx(&full_bar[s], Cfg::STAGE_BYTES);
+            tma_load_4d(smem_a + s * Cfg::A_BYTES, &tma_a, &full_bar[s], kb * BK, (m0 + mt) * BM, az1, az2);
+            if (!BRES) tma_load_4d(smem_b + s * Cfg::B_BYTES, &tma_b, &full_bar[s], kb * BK, n_tile * BN, bz1, bz2);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_f16(BM, BN, 0);
+      int it = 0, lt = 0, li = 0;
+      for (int item = blockIdx.x; item < total_items; item += gridDim.x, ++li) {
+        int z, m0, mcount, n_tile;
+        decode(item, z, m0, mcount, n_tile);
+        if (BRES) {
+          mbar_wait(b_full_bar, li & 1);
+          tc_fence_after();
+        }
+        for (int mt = 0; mt < mcount; ++mt, ++lt) {
+          const int buf = lt & 1;
+          mbar_wait(&tmem_empty_bar[buf], ((lt >> 1) & 1) ^ 1);  // epilogue has drained this accumulator
+          tc_fence_after();
+          const uint32_t acc = tmem_base + (uint32_t)(buf * BN);
+          for (int kb = 0; kb < num_kb; ++kb, ++it) {
+            const int s = it % STAGES;
+            const uint32_t ph = (it / STAGES) & 1;
+            mbar_wait(&full_bar[s], ph);
+            tc_fence_after();
+            const uint32_t a_addr = smem_u32(smem_a + s * Cfg::A_BYTES);
+            const uint32_t b_addr = smem_u32(smem_b + (BRES ? kb : s) * Cfg::B_BYTES);
+#pragma unroll
+            for (int k = 0; k < BK / 16; ++k) {
+              const uint64_t da = umma_desc_k_sw128(a_addr + k * 32);
+              const uint64_t db = umma_desc_k_sw128(b_addr + k * 32);
+              tc_mma_f16(acc, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+            }
+            tc_commit(&empty_bar[s]);
+          }
+          tc_commit(&tmem_full_bar[buf]);
+        }
+        if (BRES) tc_commit(b_empty_bar);  // fires when this item's last MMA has consumed the resident tile
+      }
+    }
+  } else if (warp >= 4) {
+    int lt = 0;
+    for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
+      int z, m0, mcount, n_tile;
+      decode(item, z, m0, mcount, n_tile);
+      for (int mt = 0; mt < mcount; ++mt, ++lt) {
+        const int buf = lt & 1;
+        mbar_wait(&tmem_full_bar[buf], (lt >> 1) & 1);
+        tc_fence_after();
+        epilogue_tile<BN>(p, &tma_c, tmem_base + (uint32_t)(buf * BN), stg + (stg2 ? (lt & 1) * (BM * BN * 2) : 0), m0 + mt, n_tile,
+                          z % p.nb1, z / p.nb1, (warp - 4) & 3, lane, &tmem_empty_bar[buf], stg2 ? 1 : 0, (warp - 4) >> 2, 2);
+      }
+    }
+    if (threadIdx.x == 128) tma_store_wait_read_all();
+  }
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 2 * BN);
   }
 }
 
@@ -516,6 +742,59 @@ static int launch_tc(const GemmP& p0, cudaStream_t st) {
   return check_launch("gemm_tc_kernel");
 }
 
+static int num_sms() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+template <int BN, int STAGES, bool BRES>
+static int launch_tcp(const GemmP& p0, cudaStream_t st) {
+  using Cfg = TcpCfg<BN, STAGES, BRES>;
+  GemmP p = p0;
+  CUtensorMap ma, mb;
+  int rc = make_operand_map(&ma, p.A, p.M, p.K, p.lda, p.nb1, p.a_b1, p.nb2, p.a_b2, BM, &p.a_bcast1, &p.a_bcast2);
+  if (rc) return rc;
+  rc = make_operand_map(&mb, p.B, p.N, p.K, p.ldb, p.nb1, p.b_b1, p.nb2, p.b_b2, BN, &p.b_bcast1, &p.b_bcast2);
+  if (rc) return rc;
+  CUtensorMap mc_map = ma;
+  p.use_tma_store = can_tma_store(p, BN) ? 1 : 0;
+  if (p.use_tma_store) {
+    rc = make_output_map(&mc_map, p);
+    if (rc) return rc;
+  }
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_tcp_kernel<BN, STAGES, BRES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         Cfg::SMEM_BYTES);
+    if (e != cudaSuccess) {
+      set_error("cudaFuncSetAttribute(smem=%d) failed: %s", Cfg::SMEM_BYTES, cudaGetErrorString(e));
+      return MQDET_ERR_CUDA;
+    }
+    attr_set = true;
+  }
+  const int tm = cdiv(p.M, BM), tn = cdiv(p.N, BN);
+  const long Z = (long)p.nb1 * p.nb2;
+  int mc = 1;
+  long total = (long)tm * tn * Z;
+  if (BRES) {
+    // runs of M tiles per resident B tile: long enough to amortise the B load, short enough for ~3 items per SM
+    const long want = 3L * num_sms();
+    mc = (int)(total / want);
+    if (mc < 1) mc = 1;
+    if (mc > tm) mc = tm;
+    total = (long)cdiv(tm, mc) * tn * Z;
+  }
+  const int grid = (int)(total < num_sms() ? total : num_sms());
+  gemm_tcp_kernel<BN, STAGES, BRES><<<grid, 384, Cfg::SMEM_BYTES, st>>>(ma, mb, mc_map, p, tm, tn, (int)total, mc);
+  return check_launch("gemm_tcp_kernel");
+}
+
 }  // namespace mqdet
 
 using namespace mqdet;
@@ -548,17 +827,31 @@ extern "C" int mqdet_gemm_f16(const mqdet_gemm_args* a, int impl, void* stream) 
     gemm_simt_kernel<<<grid, 256, 0, st>>>(p);
     return check_launch("gemm_simt_kernel");
   }
-  MQ_REQUIRE(impl == MQDET_GEMM_IMPL_TCGEN05, "gemm: unknown impl %d", impl);
+  MQ_REQUIRE(impl == MQDET_GEMM_IMPL_TCGEN05 || impl == MQDET_GEMM_IMPL_TCGEN05_ONESHOT, "gemm: unknown impl %d", impl);
   MQ_REQUIRE((a->K % 8) == 0 && (a->lda % 8) == 0 && (a->ldb % 8) == 0, "gemm: K/lda/ldb must be multiples of 8");
   MQ_REQUIRE((a->a_b1 % 8) == 0 && (a->a_b2 % 8) == 0 && (a->b_b1 % 8) == 0 && (a->b_b2 % 8) == 0,
              "gemm: batch strides must be multiples of 8");
   MQ_REQUIRE(((uintptr_t)a->A % 16) == 0 && ((uintptr_t)a->B % 16) == 0, "gemm: A/B must be 16-byte aligned");
-  // Tile-N heuristic.  128x128 tiles with a 3-deep ring (97 KB) let two CTAs share an SM so one CTA's epilogue
-  // overlaps the other's main loop -- the right choice for the short-K, output-bound products that dominate this
-  // model (K = 256..768).  Long-K products are MMA/L2 bound: 128x256 tiles halve the operand re-reads.
   const long mt = cdiv(p.M, BM), z = (long)p.nb1 * p.nb2;
-  if (p.N >= 256 && p.K >= 1024 && mt * cdiv(p.N, 256) * z >= 148) return launch_tc<256, 4>(p, st);
-  if (p.N > 64 && (mt * cdiv(p.N, 128) * z >= 120 || p.N > 1024)) return launch_tc<128, 3>(p, st);
-  if (p.N > 32) return launch_tc<64, 4>(p, st);
-  return launch_tc<32, 4>(p, st);
+  if (impl == MQDET_GEMM_IMPL_TCGEN05_ONESHOT) {
+    // one output tile per CTA, two CTAs per SM (the round-1a kernel, kept for A/B measurements)
+    if (p.N >= 256 && p.K >= 1024 && mt * cdiv(p.N, 256) * z >= 148) return launch_tc<256, 4>(p, st);
+    if (p.N > 64 && (mt * cdiv(p.N, 128) * z >= 120 || p.N > 1024)) return launch_tc<128, 3>(p, st);
+    if (p.N > 32) return launch_tc<64, 4>(p, st);
+    return launch_tc<32, 4>(p, st);
+  }
+  // Persistent kernel.  Short-K products (K <= 256) are L2->SM bandwidth bound at 128-wide tiles, so they keep the B tile
+  // resident (BRES) and stream only A; tile-N = the widest tile that still yields >= ~1 tile per SM.
+  // 128- vs 64-wide tiles: fewer waves x tile cost (MMA time per tile ~ BN) wins; ties go to the wider tile (fewer loads)
+  const long t128 = mt * cdiv(p.N, 128) * z, t64 = mt * cdiv(p.N, 64) * z;
+  const long w128 = (t128 + num_sms() - 1) / num_sms(), w64 = (t64 + num_sms() - 1) / num_sms();
+  const bool wide = p.N > 64 && (w128 * 128 <= w64 * 64);
+  if (p.K <= BRES_KB * BK && mt * cdiv(p.N, 128) * z >= 2L * num_sms()) {
+    if (wide) return launch_tcp<128, 4, true>(p, st);
+  }
+  if (p.K >= 512 && p.N >= 256 && p.c_dtype == MQDET_F16 && mt * cdiv(p.N, 256) * z >= num_sms() && can_tma_store(p, 256))
+    return launch_tcp<256, 3, false>(p, st);  // long-K: 128x256 tiles halve the A re-reads (MMA/L2 bound regime)
+  if (wide) return launch_tcp<128, 4, false>(p, st);
+  if (p.N > 32) return launch_tcp<64, 4, false>(p, st);
+  return launch_tcp<32, 4, false>(p, st);
 }

@@ -67,13 +67,22 @@ __global__ void __launch_bounds__(256) atss_candidates_kernel(const T* __restric
         ++n;
       }
     }
-    if (n == 0) continue;  // label absent from the positive map: score stays 0 (inference.py:773)
-    const float score = s / (float)n;
-    if (score > thresh) {
-      const float rank = score * cs;
-      const int slot = atomicAdd(&counts[b * lv.n + l], 1);
-      const unsigned int idx = (unsigned int)(loc * C + c);
-      cand[(long)b * cand_per_img + lv.cand_off[l] + slot] = ((unsigned long long)f2ord(rank) << 32) | (unsigned int)(~idx);
+    const float score = (n > 0) ? s / (float)n : 0.f;  // label absent from the positive map: score stays 0 (:773)
+    const bool hit = score > thresh;
+    // warp-aggregated append: one atomic per warp and class stripe instead of one per candidate
+    const unsigned ball = __ballot_sync(__activemask(), hit);
+    if (ball) {
+      const unsigned act = __activemask();
+      const int leader = __ffs(ball) - 1;
+      int base = 0;
+      if (lane == leader) base = atomicAdd(&counts[b * lv.n + l], __popc(ball));
+      base = __shfl_sync(act, base, leader);
+      if (hit) {
+        const float rank = score * cs;
+        const int slot = base + __popc(ball & ((1u << lane) - 1));
+        const unsigned int idx = (unsigned int)(loc * C + c);
+        cand[(long)b * cand_per_img + lv.cand_off[l] + slot] = ((unsigned long long)f2ord(rank) << 32) | (unsigned int)(~idx);
+      }
     }
   }
 }

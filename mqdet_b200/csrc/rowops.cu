@@ -218,6 +218,97 @@ __global__ void __launch_bounds__(256) softmax_rows_f16v_kernel(const __half* __
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Column softmax with transposed output: P[z][t][n] = softmax over n of A[z][n][t]   (BiAttention text->image side,
+// fuse_helper.py:257-268: softmax_N(A^T - rowmax(A^T))).  Replaces a second QK^T product + row softmax:
+//   1. colsoftmax_stats  : per (z, 256-row chunk) online (max, sum-exp) per column        -> partial[z][chunk][2][T]
+//   2. colsoftmax_finish : merges the chunks                                                -> stat[z][2][T] (max, 1/sum)
+//   3. colsoftmax_write  : 64-row tiles through shared memory, 16-byte coalesced transposed stores
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int CS_ROWS = 256;
+
+__global__ void __launch_bounds__(256) colsoftmax_stats_kernel(const __half* __restrict__ A, int N, int T,
+                                                               float* __restrict__ partial, int nchunks) {
+  const int chunk = blockIdx.x, z = blockIdx.y;
+  const int r0 = chunk * CS_ROWS, r1 = min(N, r0 + CS_ROWS);
+  const __half* a = A + (long)z * N * T;
+  for (int t = threadIdx.x; t < T; t += blockDim.x) {
+    float m = -INFINITY, s = 0.f;
+    for (int r = r0; r < r1; ++r) {
+      const float v = __half2float(a[(long)r * T + t]);
+      const float m2 = fmaxf(m, v);
+      s = s * expf(m - m2) + expf(v - m2);
+      m = m2;
+    }
+    float* o = partial + (((long)z * nchunks + chunk) * 2) * T;
+    o[t] = m;
+    o[T + t] = s;
+  }
+}
+
+__global__ void colsoftmax_finish_kernel(const float* __restrict__ partial, int T, int nchunks, float* __restrict__ stat) {
+  const int z = blockIdx.x;
+  for (int t = threadIdx.x; t < T; t += blockDim.x) {
+    float m = -INFINITY;
+    for (int c = 0; c < nchunks; ++c) m = fmaxf(m, partial[(((long)z * nchunks + c) * 2) * T + t]);
+    float s = 0.f;
+    for (int c = 0; c < nchunks; ++c) {
+      const float* o = partial + (((long)z * nchunks + c) * 2) * T;
+      s += o[T + t] * expf(o[t] - m);
+    }
+    stat[((long)z * 2) * T + t] = m;
+    stat[((long)z * 2 + 1) * T + t] = 1.f / s;
+  }
+}
+
+// tile: 64 rows (n) x T columns -> P[z][t][n0..n0+63];  T <= 256, T % 8 == 0.
+// Row-major staging (16-byte conflict-free stores), then lane == column t reads 16 consecutive rows (2-byte loads,
+// consecutive lanes -> consecutive half-words) and writes one full 32-byte sector of P[t][n0+r0 .. +15].
+__global__ void __launch_bounds__(256) colsoftmax_write_kernel(const __half* __restrict__ A, int N, int Np, int T,
+                                                               const float* __restrict__ stat, __half* __restrict__ P) {
+  __shared__ __align__(16) __half tile[64][256 + 8];
+  const int n0 = blockIdx.x * 64, z = blockIdx.y;
+  const __half* a = A + (long)z * N * T;
+  const float* mx = stat + ((long)z * 2) * T;
+  const float* inv = mx + T;
+  const int vec_per_row = T / 8;
+  for (int i = threadIdx.x; i < 64 * vec_per_row; i += 256) {
+    const int r = i / vec_per_row, c = (i % vec_per_row) * 8;
+    __half2 o[4];
+    if (n0 + r < N) {
+      const uint4 u = *reinterpret_cast<const uint4*>(a + (long)(n0 + r) * T + c);
+      const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float2 f = __half22float2(h[k]);
+        o[k] = __floats2half2_rn(expf(f.x - mx[c + 2 * k]) * inv[c + 2 * k], expf(f.y - mx[c + 2 * k + 1]) * inv[c + 2 * k + 1]);
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) o[k] = __float2half2_rn(0.f);  // rows beyond N: zero padding of the K dimension of P.Vv
+    }
+    *reinterpret_cast<uint4*>(&tile[r][c]) = *reinterpret_cast<uint4*>(o);
+  }
+  __syncthreads();
+  __half* p = P + (long)z * T * Np;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tgroups = (T + 31) / 32;
+  for (int it = warp; it < tgroups * 4; it += 8) {
+    const int t = (it / 4) * 32 + lane, r0 = (it % 4) * 16;
+    if (t >= T) continue;
+    __align__(16) __half v[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) v[k] = tile[r0 + k][t];
+    __half* dst = p + (long)t * Np + n0 + r0;
+    if (n0 + r0 + 16 <= Np) {
+      *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<uint4*>(&v[0]);
+      *reinterpret_cast<uint4*>(dst + 8) = *reinterpret_cast<uint4*>(&v[8]);
+    } else if (n0 + r0 + 8 <= Np) {
+      *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<uint4*>(&v[0]);
+    }
+  }
+}
+
 __global__ void cast_f32_f16_kernel(const float* __restrict__ x, __half* __restrict__ y, long n) {
   long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
   const long stride = (long)gridDim.x * blockDim.x;
@@ -340,4 +431,24 @@ extern "C" int mqdet_cast_f16_f32(const void* x, float* y, int64_t n, void* stre
   if (blocks > 148 * 16) blocks = 148 * 16;
   cast_f16_f32_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>((const __half*)x, y, n);
   return check_launch("cast_f16_f32_kernel");
+}
+
+extern "C" int64_t mqdet_colsoftmax_workspace_floats(int64_t Z, int64_t N, int64_t T) {
+  const int64_t nchunks = (N + CS_ROWS - 1) / CS_ROWS;
+  return Z * nchunks * 2 * T + Z * 2 * T;
+}
+
+extern "C" int mqdet_colsoftmax_transposed(const void* A, int64_t Z, int64_t N, int64_t T, void* P, int64_t Np, float* workspace,
+                                           void* stream) {
+  MQ_REQUIRE(A && P && workspace && Z > 0 && N > 0, "colsoftmax_transposed: bad args");
+  MQ_REQUIRE(T > 0 && T <= 256 && (T % 8) == 0 && (Np % 8) == 0 && Np >= N, "colsoftmax_transposed: need T<=256, T%%8==0, Np%%8==0");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int nchunks = (int)((N + CS_ROWS - 1) / CS_ROWS);
+  float* partial = workspace;
+  float* stat = workspace + Z * nchunks * 2 * T;
+  colsoftmax_stats_kernel<<<dim3(nchunks, (unsigned)Z), 256, 0, st>>>((const __half*)A, (int)N, (int)T, partial, nchunks);
+  colsoftmax_finish_kernel<<<(unsigned)Z, 256, 0, st>>>(partial, (int)T, nchunks, stat);
+  colsoftmax_write_kernel<<<dim3((unsigned)((Np + 63) / 64), (unsigned)Z), 256, 0, st>>>((const __half*)A, (int)N, (int)Np, (int)T,
+                                                                                       stat, (__half*)P);
+  return check_launch("colsoftmax_transposed");
 }

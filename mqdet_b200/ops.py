@@ -8,7 +8,7 @@ import ctypes
 import torch
 
 from . import _lib
-from ._lib import (ACT_GELU, ACT_NONE, ACT_RELU, F16, F32, IMPL_SIMT, IMPL_TCGEN05, VEC_NONE, VEC_PER_COL,
+from ._lib import (ACT_GELU, ACT_NONE, ACT_RELU, F16, F32, IMPL_SIMT, IMPL_TCGEN05, IMPL_TCGEN05_ONESHOT, VEC_NONE, VEC_PER_COL,
                    VEC_PER_ROW, VEC_SCALAR, GemmArgs, check, load)
 
 # tests flip this to IMPL_SIMT to cross-check the tensor-core kernel against the plain FMA kernel
@@ -182,6 +182,20 @@ def l2_normalize(x32, w=None, b0=None, eps=1e-12):
                                      _stream()), "l2norm_rowdot")
     launch_count += 1
     return e16, e32, dot
+
+
+def colsoftmax_transposed(A16, Np=None):
+    """A16 [..., N, T] fp16 -> P [..., T, Np] fp16 with P[t, n] = softmax over n of A[n, t] (zero for n >= N)."""
+    global launch_count
+    _need_cuda(A16)
+    N, T = A16.shape[-2], A16.shape[-1]
+    Z = A16.numel() // (N * T)
+    Np = (N + 7) // 8 * 8 if Np is None else Np
+    P = torch.empty(A16.shape[:-2] + (T, Np), dtype=torch.float16, device=A16.device)
+    ws = torch.empty((int(load().mqdet_colsoftmax_workspace_floats(Z, N, T)),), dtype=torch.float32, device=A16.device)
+    check(load().mqdet_colsoftmax_transposed(_ptr(A16), Z, N, T, _ptr(P), Np, _ptr(ws), _stream()), "colsoftmax_transposed")
+    launch_count += 3
+    return P
 
 
 def cast_f16(x):

@@ -12,8 +12,8 @@ Every product is a K-major x K-major tcgen05 GEMM; transposed operands are produ
 (V^T = W . x^T), never by a transpose kernel:
     Q  = (LN(v) Wv^T + b) * d^-1/2      [B,N,E]      K  = LN(l) Wl^T + b          [B,T,E]
     VvT= Wvv LN(v)^T + b (per row)      [B,E,N]      VlT= Wvl LN(l)^T + b         [B,E,T]
-    A  = clamp(Q_h K_h^T)  [B,H,N,T] -> softmax_T(A + mask)   -> out_v = P_v VlT_h^T
-    At = clamp(K_h Q_h^T)  [B,H,T,N] -> softmax_N(At - max)   -> out_l = P_l VvT_h^T
+    A  = clamp(Q_h K_h^T)  [B,H,N,T] -> softmax_T(A + mask)            -> out_v = P_v VlT_h^T
+                                     -> column softmax, transposed    -> out_l = P_l VvT_h^T
     v' = LN(v) + gamma_v * (out_v Wov^T + b)       l' = LN(l) + gamma_l * (out_l Wol^T + b)
 """
 import torch
@@ -88,18 +88,18 @@ class BiMultiHeadAttention(nn.Module):
         vlT = ops.gemm(w16(self.values_l_proj.weight), ln16, bias=f32(self.values_l_proj.bias), bias_mode=VEC_PER_ROW)
 
         qh, kh = q.permute(0, 2, 1, 3), k.permute(0, 2, 1, 3)
-        # image -> text direction
+        # scores A = clamp(Q_h K_h^T)  [B,H,N,T]  (ONE product serves both directions)
         A = torch.empty((B, H, N, T), dtype=torch.float16, device=dev)
         ops.gemm(qh, kh, out=A, clamp=clamp)
+        # text -> image direction first (A is normalised in place afterwards): softmax over all N locations, no mask,
+        # written transposed [B,H,T,Np] so that P_l . Vv is again a K-major x K-major product
+        Pl = ops.colsoftmax_transposed(A, Np)
+        ol = torch.empty((B, T, H, d), dtype=torch.float16, device=dev)
+        # image -> text direction: softmax over the T tokens with the padding mask
         cm = mask_l.float().contiguous() if mask_l is not None else None
         Pv = ops.softmax_rows(A, colmask=cm, rows_per_batch=H * N, mask_value=-9e15, keep_add=1.0, out=A)
         ov = torch.empty((B, N, H, d), dtype=torch.float16, device=dev)
         ops.gemm(Pv, vlT.view(B, H, d, T), out=ov.permute(0, 2, 1, 3))
-        # text -> image direction (softmax over all N locations, no mask)
-        At = torch.empty((B, H, T, Np), dtype=torch.float16, device=dev)
-        ops.gemm(kh, qh, out=At[..., :N], clamp=clamp)
-        Pl = ops.softmax_rows(At, n=N, out=At)
-        ol = torch.empty((B, T, H, d), dtype=torch.float16, device=dev)
         ops.gemm(Pl, vvT.view(B, H, d, Np), out=ol.permute(0, 2, 1, 3))
 
         ve = v_epilogue or {}

@@ -52,6 +52,26 @@ def test_plain(dev, M, N, K, out_dtype):
     _check(out, ref, out_dtype == torch.float16)
     simt = ops.gemm(a, b, out_dtype=out_dtype, impl=ops.IMPL_SIMT)
     _check(simt, ref, out_dtype == torch.float16)
+    oneshot = ops.gemm(a, b, out_dtype=out_dtype, impl=ops.IMPL_TCGEN05_ONESHOT)  # non-persistent tcgen05 variant
+    _check(oneshot, ref, out_dtype == torch.float16)
+
+
+def test_persistent_many_tiles_per_cta(dev):
+    """> 148 tiles so every CTA of the persistent kernel loops (ring wrap, both TMEM buffers, staging reuse), with a
+    ragged last M tile and batches."""
+    from mqdet_b200 import ops
+    g = torch.Generator(device="cpu").manual_seed(77)
+    # the last three shapes have K <= 256 and >= 2 tiles per SM: they take the B-resident (BRES) variant, including a
+    # ragged M-chunk tail and per-batch B tiles
+    for (Bz, M, N, K) in [(1, 128 * 40 + 37, 512, 256), (5, 1000, 384, 192), (1, 70000, 128, 64), (1, 128 * 100 + 5, 512, 256),
+                          (6, 128 * 30, 256, 192), (3, 22400, 256, 256)]:
+        a = (torch.randn(Bz, M, K, generator=g) * 0.5).half().to(dev)
+        b = (torch.randn(Bz, N, K, generator=g) * 0.5).half().to(dev)
+        bias = torch.randn(N, generator=g).to(dev)
+        res = torch.randn(Bz, M, N, generator=g).to(dev)
+        ref = torch.einsum("zmk,znk->zmn", a.float(), b.float())
+        _check(ops.gemm(a, b, bias=bias), ref + bias, True)                                   # TMA-store epilogue
+        _check(ops.gemm(a, b, bias=bias, residual=res, out_dtype=torch.float32), ref + bias + res, False)  # fallback epilogue
 
 
 def test_epilogues(dev):

@@ -58,7 +58,15 @@ for i, (M, N, K, what) in enumerate(SHAPES):
     e1.record()
     torch.cuda.synchronize()
     cms = e0.elapsed_time(e1) / 10
-    res[f"{M}x{N}x{K}"] = dict(what=what, ms=round(ms, 4), tflops=round(2 * M * N * K / ms / 1e9, 1), cublas_ms=round(cms, 4),
+    for _ in range(3):
+        ops.gemm(a, b, out=c, impl=ops.IMPL_TCGEN05_ONESHOT)
+    e0.record()
+    for _ in range(10):
+        ops.gemm(a, b, out=c, impl=ops.IMPL_TCGEN05_ONESHOT)
+    e1.record()
+    torch.cuda.synchronize()
+    oms = e0.elapsed_time(e1) / 10
+    res[f"{M}x{N}x{K}"] = dict(what=what, ms=round(ms, 4), oneshot_ms=round(oms, 4), tflops=round(2 * M * N * K / ms / 1e9, 1), cublas_ms=round(cms, 4),
                                cublas_tflops=round(2 * M * N * K / cms / 1e9, 1),
                                out_gbs=round(M * N * 2 / ms / 1e6, 1))
     print(f"{M}x{N}x{K}", res[f"{M}x{N}x{K}"], flush=True)
