@@ -845,7 +845,7 @@ extern "C" int mqdet_gemm_f16(const mqdet_gemm_args* a, int impl, void* stream) 
   // 128- vs 64-wide tiles: fewer waves x tile cost (MMA time per tile ~ BN) wins; ties go to the wider tile (fewer loads)
   const long t128 = mt * cdiv(p.N, 128) * z, t64 = mt * cdiv(p.N, 64) * z;
   const long w128 = (t128 + num_sms() - 1) / num_sms(), w64 = (t64 + num_sms() - 1) / num_sms();
-  const bool wide = p.N > 64 && (w128 * 128 <= w64 * 64);
+  const bool wide = p.N > 64 && (w128 * 128 * 10 <= w64 * 64 * 12);  // the narrow tile must win by > 20 %
   if (p.K <= BRES_KB * BK && mt * cdiv(p.N, 128) * z >= 2L * num_sms()) {
     if (wide) return launch_tcp<128, 4, true>(p, st);
   }

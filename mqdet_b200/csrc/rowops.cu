@@ -272,16 +272,35 @@ __global__ void __launch_bounds__(256) colsoftmax_write_kernel(const __half* __r
   const float* mx = stat + ((long)z * 2) * T;
   const float* inv = mx + T;
   const int vec_per_row = T / 8;
+  // 256 % vec_per_row == 0 (T in {8,..,256}, power-of-two multiples of 8 used here) -> a thread keeps its 8 columns for
+  // the whole tile: their (max, 1/sum) are loaded once
+  const bool fixed_cols = (256 % vec_per_row) == 0;
+  float mxr[8], ivr[8];
+  if (fixed_cols) {
+    const int c = (threadIdx.x % vec_per_row) * 8;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      mxr[k] = mx[c + k];
+      ivr[k] = inv[c + k];
+    }
+  }
   for (int i = threadIdx.x; i < 64 * vec_per_row; i += 256) {
     const int r = i / vec_per_row, c = (i % vec_per_row) * 8;
     __half2 o[4];
     if (n0 + r < N) {
       const uint4 u = *reinterpret_cast<const uint4*>(a + (long)(n0 + r) * T + c);
       const __half2* h = reinterpret_cast<const __half2*>(&u);
+      if (!fixed_cols) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          mxr[k] = mx[c + k];
+          ivr[k] = inv[c + k];
+        }
+      }
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         const float2 f = __half22float2(h[k]);
-        o[k] = __floats2half2_rn(expf(f.x - mx[c + 2 * k]) * inv[c + 2 * k], expf(f.y - mx[c + 2 * k + 1]) * inv[c + 2 * k + 1]);
+        o[k] = __floats2half2_rn(__expf(f.x - mxr[2 * k]) * ivr[2 * k], __expf(f.y - mxr[2 * k + 1]) * ivr[2 * k + 1]);
       }
     } else {
 #pragma unroll

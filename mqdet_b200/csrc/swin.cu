@@ -28,95 +28,186 @@ __global__ void patchify4_kernel(const float* __restrict__ img, int B, int H, in
   out[i] = __float2half_rn(v);
 }
 
-// Window attention for one (window, head): head_dim 32, window 7x7 (N = 49 tokens), fp32 math.
+// Window attention for one (window, head): head_dim 32, window 7x7 (N = 49 tokens).
 // qkv [B*H*W, 3*C] fp16 (q | k | v, each C = heads*32 wide); bias_dense [heads][N][N] fp32 (relative position bias);
 // padded tokens (beyond H/W after padding to a multiple of the window) carry qkv = qkv_bias because the reference
 // pads the NORMALISED input with zeros before the qkv Linear (:200-205); cyclic shift + region mask (-100) are index math.
+//
+// One WARP per (window, head), 49 tokens padded to 64 x 56: S = Q K^T and O = P V run on mma.sync.m16n8k16 (fp16 in,
+// fp32 accumulate; a 49x49x32 problem is far below the tcgen05 tile), softmax in the accumulator fragments (quad
+// shuffles), P re-used as the A fragment of the second product (no shared-memory round trip); V is staged transposed
+// in shared memory (B fragments need two consecutive KEYS per register).
+__device__ __forceinline__ void mma_16816(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+__device__ __forceinline__ uint32_t pack_h2(float x, float y) {
+  __half2 h = __floats2half2_rn(x, y);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
 template <int WS>
-__global__ void __launch_bounds__(64) swin_window_attn_kernel(const __half* __restrict__ qkv, const float* __restrict__ qkv_bias,
-                                                              const float* __restrict__ bias_dense, int B, int H, int W,
-                                                              int heads, int shift, float scale, __half* __restrict__ out) {
-  constexpr int N = WS * WS, D = 32;
+__global__ void __launch_bounds__(128) swin_window_attn_kernel(const __half* __restrict__ qkv, const float* __restrict__ qkv_bias,
+                                                               const float* __restrict__ bias_dense, int B, int H, int W,
+                                                               int heads, int shift, float scale, __half* __restrict__ out) {
+  constexpr int N = WS * WS, D = 32, NP = 64, VLD = 72;
+  static_assert(N <= 56, "key padding assumes <= 56 tokens per window");
   const int C = heads * D;
   const int Hp = (H + WS - 1) / WS * WS, Wp = (W + WS - 1) / WS * WS;
   const int nWw = Wp / WS, nW = (Hp / WS) * nWw;
-  const int head = blockIdx.y;
-  const int b = blockIdx.x / nW, win = blockIdx.x % nW;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long unit = (long)blockIdx.x * 4 + warp;  // (b, window, head), head fastest
+  if (unit >= (long)B * nW * heads) return;
+  const int head = (int)(unit % heads);
+  const int win = (int)((unit / heads) % nW);
+  const int b = (int)(unit / ((long)heads * nW));
   const int wi = win / nWw, wj = win % nWw;
-  __shared__ float ks[N][D + 1], vs[N][D + 1];
-  __shared__ int tok[N], region[N];
-  const int t = threadIdx.x;
-  if (t < N) {
-    const int r = t / WS, c = t % WS;
-    const int hs = wi * WS + r, wsft = wj * WS + c;            // coordinate in the shifted, padded frame
-    const int ho = (hs + shift) % Hp, wo = (wsft + shift) % Wp;  // coordinate in the un-shifted frame (roll by -shift)
-    tok[t] = (ho < H && wo < W) ? (ho * W + wo) : -1;
-    int idh = 0, idw = 0;
-    if (shift > 0) {
-      idh = (hs < Hp - WS) ? 0 : ((hs < Hp - shift) ? 1 : 2);
-      idw = (wsft < Wp - WS) ? 0 : ((wsft < Wp - shift) ? 1 : 2);
+  __shared__ __align__(16) __half vT[4][D][VLD];
+  __shared__ int s_tok[4][NP], s_reg[4][NP];
+  int* tok = s_tok[warp];
+  int* reg = s_reg[warp];
+  for (int t = lane; t < NP; t += 32) {
+    int tk = -2, rg = 0;  // -2: beyond the 49 window tokens
+    if (t < N) {
+      const int r = t / WS, c = t % WS;
+      const int hs = wi * WS + r, wsft = wj * WS + c;              // coordinate in the shifted, padded frame
+      const int ho = (hs + shift) % Hp, wo = (wsft + shift) % Wp;  // un-shifted frame (roll by -shift)
+      tk = (ho < H && wo < W) ? (ho * W + wo) : -1;                // -1: padding token (qkv = bias)
+      if (shift > 0) {
+        const int idh = (hs < Hp - WS) ? 0 : ((hs < Hp - shift) ? 1 : 2);
+        const int idw = (wsft < Wp - WS) ? 0 : ((wsft < Wp - shift) ? 1 : 2);
+        rg = idh * 3 + idw;
+      }
     }
-    region[t] = idh * 3 + idw;
+    tok[t] = tk;
+    reg[t] = rg;
   }
-  __syncthreads();
-  for (int i = t; i < N * D; i += 64) {
-    const int n = i / D, d = i % D;
-    const int tk = tok[n];
-    float kv, vv;
-    if (tk >= 0) {
-      const __half* row = qkv + ((long)b * H * W + tk) * 3 * C + head * D + d;
-      kv = __half2float(row[C]);
-      vv = __half2float(row[2 * C]);
-    } else {
-      kv = qkv_bias[C + head * D + d];
-      vv = qkv_bias[2 * C + head * D + d];
+  __syncwarp();
+  const __half* base = qkv + (long)b * H * W * 3 * C + head * D;
+  // V^T -> shared: vT[d][j] (zero for j >= N)
+  for (int i = lane; i < NP * (D / 2); i += 32) {
+    const int j = i / (D / 2), d2 = (i % (D / 2)) * 2;
+    __half2 v = __float2half2_rn(0.f);
+    if (j < N) {
+      const int tk = tok[j];
+      if (tk >= 0) v = *reinterpret_cast<const __half2*>(base + (long)tk * 3 * C + 2 * C + d2);
+      else v = __floats2half2_rn(qkv_bias[2 * C + head * D + d2], qkv_bias[2 * C + head * D + d2 + 1]);
     }
-    ks[n][d] = kv;
-    vs[n][d] = vv;
+    vT[warp][d2][j] = __low2half(v);
+    vT[warp][d2 + 1][j] = __high2half(v);
   }
-  __syncthreads();
-  if (t >= N) return;
-  const int tk = tok[t];
-  if (tk < 0) return;  // outputs at padded positions are cropped away (:231-232)
-  float q[D];
-  {
-    const __half* row = qkv + ((long)b * H * W + tk) * 3 * C + head * D;
+  __syncwarp();
+  const int g = lane >> 2, t4 = lane & 3;
+  // 4-byte fetch of two consecutive dims of token slot `slot` (q: which = 0, k: which = 1)
+  auto ld2 = [&](int slot, int which, int dim) -> uint32_t {
+    const int tk = (slot < NP) ? tok[slot] : -2;
+    if (tk >= 0) return *reinterpret_cast<const uint32_t*>(base + (long)tk * 3 * C + which * C + dim);
+    if (tk == -1) return pack_h2(qkv_bias[which * C + head * D + dim], qkv_bias[which * C + head * D + dim + 1]);
+    return 0u;
+  };
+  // K fragments: 7 key tiles x 2 k-steps x 2 registers, kept for all query tiles
+  uint32_t kf[7][2][2];
 #pragma unroll
-    for (int d = 0; d < D; ++d) q[d] = __half2float(row[d]) * scale;
-  }
-  float s[N];
-  float mx = -INFINITY;
-  const float* bd = bias_dense + ((long)head * N + t) * N;
-  const int rg = region[t];
+  for (int nj = 0; nj < 7; ++nj)
+#pragma unroll
+    for (int ki = 0; ki < 2; ++ki) {
+      kf[nj][ki][0] = ld2(8 * nj + g, 1, 16 * ki + 2 * t4);
+      kf[nj][ki][1] = ld2(8 * nj + g, 1, 16 * ki + 2 * t4 + 8);
+    }
+  const float* bd = bias_dense + (long)head * N * N;
 #pragma unroll 1
-  for (int j = 0; j < N; ++j) {
-    float a = 0.f;
+  for (int mi = 0; mi < 4; ++mi) {
+    const int r0 = 16 * mi + g, r1 = r0 + 8;  // the two query rows this lane holds
+    if (16 * mi >= N) break;
+    uint32_t qf[2][4];
 #pragma unroll
-    for (int d = 0; d < D; ++d) a = fmaf(q[d], ks[j][d], a);
-    a += bd[j];
-    if (shift > 0 && region[j] != rg) a += -100.0f;
-    s[j] = a;
-    mx = fmaxf(mx, a);
+    for (int ki = 0; ki < 2; ++ki) {
+      qf[ki][0] = ld2(r0, 0, 16 * ki + 2 * t4);
+      qf[ki][1] = ld2(r1, 0, 16 * ki + 2 * t4);
+      qf[ki][2] = ld2(r0, 0, 16 * ki + 2 * t4 + 8);
+      qf[ki][3] = ld2(r1, 0, 16 * ki + 2 * t4 + 8);
+    }
+    float sacc[7][4];
+#pragma unroll
+    for (int nj = 0; nj < 7; ++nj) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) sacc[nj][e] = 0.f;
+      mma_16816(sacc[nj], qf[0], kf[nj][0]);
+      mma_16816(sacc[nj], qf[1], kf[nj][1]);
+    }
+    // scale, relative position bias, shift mask, key padding; row max
+    const int rg0 = (r0 < N) ? reg[r0] : 0, rg1 = (r1 < N) ? reg[r1] : 0;
+    float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+    for (int nj = 0; nj < 7; ++nj)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int j = 8 * nj + 2 * t4 + (e & 1);
+        const int r = (e < 2) ? r0 : r1;
+        float v = -INFINITY;
+        if (j < N && r < N) {
+          v = sacc[nj][e] * scale + bd[r * N + j];
+          if (shift > 0 && reg[j] != ((e < 2) ? rg0 : rg1)) v += -100.0f;
+        }
+        sacc[nj][e] = v;
+        if (e < 2) mx0 = fmaxf(mx0, v); else mx1 = fmaxf(mx1, v);
+      }
+    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
+    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
+    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+    float sum0 = 0.f, sum1 = 0.f;
+#pragma unroll
+    for (int nj = 0; nj < 7; ++nj)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float m = (e < 2) ? mx0 : mx1;
+        const float pv = (sacc[nj][e] == -INFINITY) ? 0.f : expf(sacc[nj][e] - m);
+        sacc[nj][e] = pv;
+        if (e < 2) sum0 += pv; else sum1 += pv;
+      }
+    sum0 += __shfl_xor_sync(0xffffffffu, sum0, 1);
+    sum0 += __shfl_xor_sync(0xffffffffu, sum0, 2);
+    sum1 += __shfl_xor_sync(0xffffffffu, sum1, 1);
+    sum1 += __shfl_xor_sync(0xffffffffu, sum1, 2);
+    // O = P V : P fragments come straight from the S accumulators (key tiles 2kj, 2kj+1 -> k-step kj)
+    float oacc[4][4];
+#pragma unroll
+    for (int ni = 0; ni < 4; ++ni)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) oacc[ni][e] = 0.f;
+#pragma unroll
+    for (int kj = 0; kj < 4; ++kj) {
+      uint32_t pf[4];
+      pf[0] = pack_h2(sacc[2 * kj][0], sacc[2 * kj][1]);
+      pf[1] = pack_h2(sacc[2 * kj][2], sacc[2 * kj][3]);
+      if (2 * kj + 1 < 7) {
+        pf[2] = pack_h2(sacc[2 * kj + 1][0], sacc[2 * kj + 1][1]);
+        pf[3] = pack_h2(sacc[2 * kj + 1][2], sacc[2 * kj + 1][3]);
+      } else {
+        pf[2] = pf[3] = 0u;
+      }
+#pragma unroll
+      for (int ni = 0; ni < 4; ++ni) {
+        uint32_t vf[2];
+        vf[0] = *reinterpret_cast<const uint32_t*>(&vT[warp][8 * ni + g][16 * kj + 2 * t4]);
+        vf[1] = *reinterpret_cast<const uint32_t*>(&vT[warp][8 * ni + g][16 * kj + 2 * t4 + 8]);
+        mma_16816(oacc[ni], pf, vf);
+      }
+    }
+    const float inv0 = (sum0 > 0.f) ? 1.f / sum0 : 0.f, inv1 = (sum1 > 0.f) ? 1.f / sum1 : 0.f;
+    const int tk0 = (r0 < N) ? tok[r0] : -2, tk1 = (r1 < N) ? tok[r1] : -2;
+#pragma unroll
+    for (int ni = 0; ni < 4; ++ni) {
+      const int d = 8 * ni + 2 * t4;
+      if (tk0 >= 0)  // outputs at padded positions are cropped away (:231-232)
+        *reinterpret_cast<uint32_t*>(out + ((long)b * H * W + tk0) * C + head * D + d) = pack_h2(oacc[ni][0] * inv0, oacc[ni][1] * inv0);
+      if (tk1 >= 0)
+        *reinterpret_cast<uint32_t*>(out + ((long)b * H * W + tk1) * C + head * D + d) = pack_h2(oacc[ni][2] * inv1, oacc[ni][3] * inv1);
+    }
   }
-  float den = 0.f;
-#pragma unroll 1
-  for (int j = 0; j < N; ++j) {
-    s[j] = expf(s[j] - mx);
-    den += s[j];
-  }
-  const float inv = 1.f / den;
-  float o[D];
-#pragma unroll
-  for (int d = 0; d < D; ++d) o[d] = 0.f;
-#pragma unroll 1
-  for (int j = 0; j < N; ++j) {
-    const float p = s[j] * inv;
-#pragma unroll
-    for (int d = 0; d < D; ++d) o[d] = fmaf(p, vs[j][d], o[d]);
-  }
-  __half* orow = out + ((long)b * H * W + tk) * C + head * D;
-#pragma unroll
-  for (int d = 0; d < D; d += 2) *reinterpret_cast<__half2*>(orow + d) = __floats2half2_rn(o[d], o[d + 1]);
 }
 
 // PatchMerging gather + LayerNorm(4C) (:256-284): out row (b, h2, w2) = LN(cat[x(2h2,2w2), x(2h2+1,2w2), x(2h2,2w2+1),
@@ -254,8 +345,9 @@ extern "C" int mqdet_swin_window_attn(const void* qkv, const float* qkv_bias, co
   MQ_REQUIRE(shift >= 0 && shift < window, "swin_window_attn: bad shift");
   const int Hp = (int)((H + window - 1) / window * window), Wp = (int)((W + window - 1) / window * window);
   const int nW = (Hp / (int)window) * (Wp / (int)window);
-  dim3 grid((unsigned)(B * nW), (unsigned)heads);
-  swin_window_attn_kernel<7><<<grid, 64, 0, (cudaStream_t)stream>>>((const __half*)qkv, qkv_bias, bias_dense, (int)B, (int)H,
+  const long units = B * (long)nW * heads;
+  dim3 grid((unsigned)((units + 3) / 4));
+  swin_window_attn_kernel<7><<<grid, 128, 0, (cudaStream_t)stream>>>((const __half*)qkv, qkv_bias, bias_dense, (int)B, (int)H,
                                                                     (int)W, (int)heads, (int)shift, scale, (__half*)out);
   return check_launch("swin_window_attn_kernel");
 }
