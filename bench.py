@@ -160,13 +160,13 @@ def main():
     sizes = [(H_IMG, W_IMG)] * B
     img_host = img.pin_memory()
     img_dev = img.to(dev)
-    gathered = torch.empty((world * B, 128, 6), dtype=torch.float32, device=dev) if world > 1 else None
+    from mqdet_b200 import parallel
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)  # > 126 MB L2
 
     def step(x):
         out = model.forward_device(ImageList(x, sizes), caps, pmap)
-        if world > 1:  # the ONE collective of the data path: fixed-shape per-image detections over NVLink
-            dist.all_gather_into_tensor(gathered, out["det"])
+        # the ONE collective of the data path: fixed-shape per-image detections over NCCL / NVLink (identity at N = 1)
+        out["det_all"], out["num_all"] = parallel.all_gather_detections(out["det"], out["num"])
         return out
 
     def barrier():

@@ -58,6 +58,29 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
 __device__ __forceinline__ void fence_mbar_init() {
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 }
+// explicit shared-space 128-bit accesses on 32-bit addresses (pointers derived from the aligned dynamic-smem base are
+// otherwise compiled as generic LD.E/ST.E with 64-bit address arithmetic)
+__device__ __forceinline__ void sts128(uint32_t addr, uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
+}
+__device__ __forceinline__ float4 lds128f(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+// packed fp32x2 FMA (sm_100): (d0, d1) = (a0, a1) * (s, s) + (b0, b1) in ONE issue slot
+__device__ __forceinline__ void ffma2(float& d0, float& d1, float a0, float a1, float s, float b0, float b1) {
+  asm("{\n"
+      ".reg .b64 va, vs, vb, vd;\n"
+      "mov.b64 va, {%2, %3};\n"
+      "mov.b64 vs, {%4, %4};\n"
+      "mov.b64 vb, {%5, %6};\n"
+      "fma.rn.f32x2 vd, va, vs, vb;\n"
+      "mov.b64 {%0, %1}, vd;\n"
+      "}\n"
+      : "=f"(d0), "=f"(d1)
+      : "f"(a0), "f"(a1), "f"(s), "f"(b0), "f"(b1));
+}
 __device__ __forceinline__ void fence_proxy_async() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
@@ -109,6 +132,9 @@ __device__ __forceinline__ void tma_store_4d(const CUtensorMap* m, const void* s
 __device__ __forceinline__ void tma_store_commit_and_wait_read1() {  // leave the newest group in flight
   asm volatile("cp.async.bulk.commit_group;" ::: "memory");
   asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+}
+__device__ __forceinline__ void tma_store_commit() {
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
 }
 __device__ __forceinline__ void tma_store_wait_read_all() {
   asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
@@ -181,6 +207,15 @@ __device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&r)[16])
 }
 __device__ __forceinline__ void tmem_ld_wait() {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+// wait::ld that also "touches" the destination registers of an earlier tcgen05.ld, so that the compiler cannot schedule
+// their first use above the wait when the load was issued several statements earlier (software-pipelined epilogue)
+__device__ __forceinline__ void tmem_ld_wait_dep(uint32_t (&r)[16]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]),
+                 "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
+               :
+               : "memory");
 }
 
 // K-major, 128-byte-swizzled shared-memory matrix descriptor (8-row groups 1024 B apart).

@@ -40,7 +40,9 @@ struct GemmP {
   int r_dtype;
   long ldr, r_b1, r_b2;
   int a_bcast1, a_bcast2, b_bcast1, b_bcast2;  // 1 -> TMA coordinate pinned to 0
-  int use_tma_store;                           // epilogue variant (host decides from alignment / residual)
+  int use_tma_store;
+  // epilogue variant (host decides from alignment / residual)
+  int debug;                                   // MQDET_GEMM_DEBUG experiments: 1 = no epilogue, 2 = no TMA store, 4 = no A loads
 };
 
 // One output element's epilogue, split so the tensor-core kernel can apply the residual in its coalesced phase:
@@ -107,8 +109,11 @@ constexpr int BK = 64;  // 64 fp16 = 128 B = one swizzle row
 template <int BN>
 __device__ __forceinline__ void epilogue_tile(const GemmP& p, const CUtensorMap* tma_c, uint32_t tmem_acc, uint8_t* stg,
                                               int m_tile, int n_tile, int z1, int z2, int ew, int lane,
-                                              uint64_t* tmem_empty_bar, int pend = 0, int half = 0, int nhalf = 1) {
-  // nhalf == 2: eight epilogue warps, two per TMEM lane quarter, each taking one half of the tile's columns
+                                              uint64_t* tmem_empty_bar, int pend = 0, int half = 0, int nhalf = 1,
+                                              int cw0 = 0, int cw = BN, bool release = true) {
+  // nhalf == 2: eight epilogue warps, two per TMEM lane quarter, each taking one half of the window's columns
+  // [cw0, cw0 + cw): the column window of the tile handled by this call (TMA-store variant only; default = whole tile);
+  //   `stg` holds just that window, and the accumulator is released (`release`) by the call that reads its last window
   // ---- epilogue (4 warps; thread == output row == TMEM lane) -------------------------------------------------
   // The operand ring is idle once tmem_full fires, so it doubles as the staging tile.  16 accumulator columns at
   // a time: tcgen05.ld -> alpha/bias/act/clamp/gate in registers -> staging.
@@ -134,11 +139,24 @@ __device__ __forceinline__ void epilogue_tile(const GemmP& p, const CUtensorMap*
   constexpr int LDS = BN + 4;  // fallback staging row stride (floats)
   float* stage32 = reinterpret_cast<float*>(stg);
   const int nthr_epi = 128 * nhalf;
+  const bool issuer = (ew == 0 && half == 0 && lane == 0);
+  const uint32_t t_row = tmem_acc + ((uint32_t)(ew * 32) << 16);
+  const int c_begin = cw0 + half * (cw / nhalf), c_end = cw0 + (half + 1) * (cw / nhalf);
+  // Software pipeline over 16-column chunks: the tcgen05.ld of chunk i+1 is in flight while chunk i is converted.
+  uint32_t r[16];
+  tmem_ld_32x16(t_row + (uint32_t)c_begin, r);
+  if (p.use_tma_store && tmem_empty_bar && !pend) {
+    // persistent kernel, ONE staging tile: the previous tile's TMA store must have read it before it is rewritten
+    if (issuer) tma_store_wait_read_all();
+    asm volatile("bar.sync 1, %0;" ::"r"(nthr_epi) : "memory");
+  }
 #pragma unroll 1
-  for (int c0 = half * (BN / nhalf); c0 < (half + 1) * (BN / nhalf); c0 += 16) {
-    uint32_t r[16];
-    tmem_ld_32x16(tmem_acc + ((uint32_t)(ew * 32) << 16) + (uint32_t)c0, r);
-    tmem_ld_wait();
+  for (int c0 = c_begin; c0 < c_end; c0 += 16) {
+    tmem_ld_wait_dep(r);
+    float acc[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) acc[i] = __uint_as_float(r[i]);
+    if (c0 + 16 < c_end) tmem_ld_32x16(t_row + (uint32_t)(c0 + 16), r);
     const long col0 = (long)n_tile * BN + c0;
     // Every mode test below is warp-uniform and hoisted around a whole straight-line 16-element loop: the epilogue
     // is issue-bound (4 warps per tile), so per-element predicates/parameter reloads are what must be avoided.
@@ -159,14 +177,14 @@ __device__ __forceinline__ void epilogue_tile(const GemmP& p, const CUtensorMap*
       }
       if (sab) {
 #pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] = alpha * (__uint_as_float(r[i]) + b[i]);
+        for (int i = 0; i < 16; ++i) v[i] = alpha * (acc[i] + b[i]);
       } else {
 #pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] = fmaf(alpha, __uint_as_float(r[i]), b[i]);
+        for (int i = 0; i < 16; ++i) v[i] = fmaf(alpha, acc[i], b[i]);
       }
     } else {
 #pragma unroll
-      for (int i = 0; i < 16; ++i) v[i] = fmaf(alpha, __uint_as_float(r[i]), brow_eff);
+      for (int i = 0; i < 16; ++i) v[i] = fmaf(alpha, acc[i], brow_eff);
     }
     if (act == MQDET_ACT_GELU) {
 #pragma unroll
@@ -195,7 +213,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmP& p, const CUtensorMap*
     if (p.use_tma_store) {
       if (p.c_dtype == MQDET_F16) {
         // column block of 64 halfs (128 B rows); this thread's 16 columns = chunks j0, j0+1
-        uint8_t* blk = stg + (c0 >> 6) * (BM * 128) + r_local * 128;
+        uint8_t* blk = stg + ((c0 - cw0) >> 6) * (BM * 128) + r_local * 128;
         const int j0 = (c0 & 63) >> 3;
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
@@ -212,7 +230,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmP& p, const CUtensorMap*
         }
       } else {
         // column block of 32 floats (128 B rows); 16 columns = chunks j0 .. j0+3
-        uint8_t* blk = stg + (c0 >> 5) * (BM * 128) + r_local * 128;
+        uint8_t* blk = stg + ((c0 - cw0) >> 5) * (BM * 128) + r_local * 128;
         const int j0 = (c0 & 31) >> 2;
 #pragma unroll
         for (int h = 0; h < 4; ++h)
@@ -226,21 +244,26 @@ __device__ __forceinline__ void epilogue_tile(const GemmP& p, const CUtensorMap*
     }
   }
   tc_fence_before();
-  if (tmem_empty_bar) {  // persistent kernel: the accumulator buffer may be overwritten by the next tile's MMAs
+  if (tmem_empty_bar && release) {  // persistent kernel: the accumulator buffer may be overwritten by the next tile's MMAs
     __syncwarp();
     if (lane == 0) mbar_arrive(tmem_empty_bar);
   }
   if (p.use_tma_store) {
     fence_proxy_async();  // generic-proxy smem writes -> visible to the TMA (async proxy)
+    // two staging tiles (pend): the store issued one tile ago used the OTHER tile, which the next epilogue rewrites
+    // right after this barrier -> it must have been read by now (it had a whole tile time; this wait is ~free)
+    if (pend && issuer) tma_store_wait_read_all();
     asm volatile("bar.sync 1, %0;" ::"r"(nthr_epi) : "memory");
-    if (ew == 0 && half == 0 && lane == 0) {
+    if (issuer) {
       const int cz1 = p.nb1 == 1 ? 0 : z1, cz2 = p.nb2 == 1 ? 0 : z2;
       const int cpb = (p.c_dtype == MQDET_F16) ? 64 : 32;  // columns per 128-byte block
-      for (int cb = 0; cb * cpb < BN; ++cb) {
-        const long cc = (long)n_tile * BN + cb * cpb;
-        if (cc < p.N) tma_store_4d(tma_c, stg + cb * (BM * 128), (int)cc, m_tile * BM, cz1, cz2);
+      for (int cb = 0; cb * cpb < cw; ++cb) {
+        const long cc = (long)n_tile * BN + cw0 + cb * cpb;
+        if (cc < p.N && !(p.debug & 2)) tma_store_4d(tma_c, stg + cb * (BM * 128), (int)cc, m_tile * BM, cz1, cz2);
       }
-      tma_store_commit_and_wait_read();  // smem must stay intact until the TMA has read it
+      // one-shot kernel: the CTA exits next, shared memory must outlive the read.  Persistent kernel: the read is
+      // awaited where the staging tile is reused (above) and once more before the kernel ends.
+      if (tmem_empty_bar) tma_store_commit(); else tma_store_commit_and_wait_read();
     }
   } else {
     asm volatile("bar.sync 1, %0;" ::"r"(nthr_epi) : "memory");
@@ -312,7 +335,106 @@ __device__ __forceinline__ void epilogue_tile(const GemmP& p, const CUtensorMap*
       }
     }
   }
-    if (tmem_empty_bar) asm volatile("bar.sync 1, %0;" ::"r"(nthr_epi) : "memory");
+  if (tmem_empty_bar && !p.use_tma_store) asm volatile("bar.sync 1, %0;" ::"r"(nthr_epi) : "memory");
+}
+
+// ---- fast epilogue of the persistent kernel ---------------------------------------------------------------------------
+// The common case of the hot products: v = alpha * acc + bias (per column from shared memory | per row | none), optional
+// clamp, fp16/fp32 output through the swizzled staging tile + TMA store.  Kept apart from the generic epilogue so that its
+// loop is ~35 instructions per 16 columns (2 per element: packed FFMA2, F2FP pairs, 128-bit shared stores) and contiguous
+// in the instruction cache: with K <= 256 a 128x256 tile has only ~2000 tensor-pipe cycles to hide 32768 outputs.
+// Two register sets ping-pong so that the tcgen05.ld of the next 16 columns is in flight while this one is converted.
+template <int BN>
+__device__ __forceinline__ void epilogue_fast(const GemmP& p, const CUtensorMap* tma_c, uint32_t tmem_acc, uint8_t* stg,
+                                              const float* sbias, float brow_eff, int m_tile, int n_tile, int z1, int z2, int ew,
+                                              int lane, uint64_t* tmem_empty_bar, bool dbl, int half, int cw0, int cw,
+                                              bool release) {
+  const int r_local = ew * 32 + lane;
+  const bool issuer = (ew == 0 && half == 0 && lane == 0);
+  const uint32_t t_row = tmem_acc + ((uint32_t)(ew * 32) << 16);
+  const int c_begin = cw0 + half * (cw >> 1), c_end = c_begin + (cw >> 1);  // (cw / 2) % 32 == 0
+  const float alpha = p.alpha, clampv = p.clamp;
+  const bool f16 = p.c_dtype == MQDET_F16;
+  const int sw = r_local & 7;
+  const uint32_t stg_row = smem_u32(stg) + r_local * 128;
+  const uint32_t sb_addr = sbias ? smem_u32(sbias) : 0u;
+  uint32_t ra[16], rb[16];
+  tmem_ld_32x16(t_row + (uint32_t)c_begin, ra);
+  if (!dbl) {  // ONE staging tile: the previous tile's TMA store must have read it before it is rewritten
+    if (issuer) tma_store_wait_read_all();
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+  }
+  auto emit = [&](uint32_t (&r)[16], int c0) {
+    float v[16];
+    if (sbias) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float4 t = lds128f(sb_addr + (uint32_t)(c0 * 4 + q * 16));
+        ffma2(v[4 * q], v[4 * q + 1], __uint_as_float(r[4 * q]), __uint_as_float(r[4 * q + 1]), alpha, t.x, t.y);
+        ffma2(v[4 * q + 2], v[4 * q + 3], __uint_as_float(r[4 * q + 2]), __uint_as_float(r[4 * q + 3]), alpha, t.z, t.w);
+      }
+    } else {
+#pragma unroll
+      for (int q = 0; q < 8; ++q)
+        ffma2(v[2 * q], v[2 * q + 1], __uint_as_float(r[2 * q]), __uint_as_float(r[2 * q + 1]), alpha, brow_eff, brow_eff);
+    }
+    if (f16) {
+      __half2 h[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) h[q] = __floats2half2_rn(v[2 * q], v[2 * q + 1]);
+      if (clampv > 0.f) {  // clamp after rounding == rounding after clamp (rounding is monotonic)
+        const __half2 hi = __float2half2_rn(clampv), lo = __float2half2_rn(-clampv);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) h[q] = __hmax2(__hmin2(h[q], hi), lo);
+      }
+      // column block of 64 halfs (128 B rows); this thread's 16 columns = 16-byte chunks j0, j0+1
+      const uint32_t blk = stg_row + ((c0 - cw0) >> 6) * (BM * 128);
+      const int j0 = (c0 & 63) >> 3;
+      const uint32_t* hv = reinterpret_cast<const uint32_t*>(h);
+      sts128(blk + (((j0) ^ sw) << 4), hv[0], hv[1], hv[2], hv[3]);
+      sts128(blk + (((j0 + 1) ^ sw) << 4), hv[4], hv[5], hv[6], hv[7]);
+    } else {
+      if (clampv > 0.f) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = fminf(fmaxf(v[i], -clampv), clampv);
+      }
+      // column block of 32 floats (128 B rows); 16 columns = chunks j0 .. j0+3
+      const uint32_t blk = stg_row + ((c0 - cw0) >> 5) * (BM * 128);
+      const int j0 = (c0 & 31) >> 2;
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        sts128(blk + (((j0 + q) ^ sw) << 4), __float_as_uint(v[4 * q]), __float_as_uint(v[4 * q + 1]), __float_as_uint(v[4 * q + 2]),
+               __float_as_uint(v[4 * q + 3]));
+    }
+  };
+#pragma unroll 1
+  for (int c0 = c_begin; c0 < c_end; c0 += 32) {
+    tmem_ld_wait_dep(ra);
+    tmem_ld_32x16(t_row + (uint32_t)(c0 + 16), rb);
+    emit(ra, c0);
+    tmem_ld_wait_dep(rb);
+    if (c0 + 32 < c_end) tmem_ld_32x16(t_row + (uint32_t)(c0 + 32), ra);
+    emit(rb, c0 + 16);
+  }
+  tc_fence_before();
+  if (release) {  // the accumulator buffer may be overwritten by the next tile's MMAs
+    __syncwarp();
+    if (lane == 0) mbar_arrive(tmem_empty_bar);
+  }
+  fence_proxy_async();  // generic-proxy smem writes -> visible to the TMA (async proxy)
+  // two staging tiles: the store issued one call ago used the OTHER tile, which the next call rewrites right after this
+  // barrier -> it must have been read by now
+  if (dbl && issuer) tma_store_wait_read_all();
+  asm volatile("bar.sync 1, 256;" ::: "memory");
+  if (issuer) {
+    const int cz1 = p.nb1 == 1 ? 0 : z1, cz2 = p.nb2 == 1 ? 0 : z2;
+    const int cpb = f16 ? 64 : 32;  // columns per 128-byte block
+    for (int cb = 0; cb * cpb < cw; ++cb) {
+      const long cc = (long)n_tile * BN + cw0 + cb * cpb;
+      if (cc < p.N) tma_store_4d(tma_c, stg + cb * (BM * 128), (int)cc, m_tile * BM, cz1, cz2);
+    }
+    tma_store_commit();  // the read is awaited where the staging tile is reused and once more before the kernel ends
+  }
 }
 
 template <int BN, int STAGES>
@@ -428,8 +550,9 @@ struct TcpCfg {
   static constexpr int RING_BYTES = STAGES * STAGE_BYTES + (BRES ? BRES_KB * B_BYTES : 0);
   // fp32 padded rows (fallback epilogue) >= swizzled tiles; the 256-wide tile is only dispatched with the fp16 TMA-store
   // epilogue (64 KB) because its fallback tile would not fit next to the ring
-  static constexpr int STG_BYTES = BN == 256 ? BM * BN * 2 : ((BM * (BN + 4) * 4 + 1023) / 1024) * 1024;
-  static constexpr int SMEM_BYTES = RING_BYTES + STG_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  // the B-resident 256-wide tile leaves room for two 64-column windows only (128 KB B + 48 KB A ring + 32 KB)
+  static constexpr int STG_BYTES = BN == 256 ? (BRES ? 2 * BM * 64 * 2 : BM * BN * 2) : ((BM * (BN + 4) * 4 + 1023) / 1024) * 1024;
+  static constexpr int SMEM_BYTES = RING_BYTES + STG_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + BN * 4 /*bias*/;
 };
 
 template <int BN, int STAGES, bool BRES>
@@ -453,6 +576,7 @@ __global__ void __launch_bounds__(384, 1) gemm_tcp_kernel(const __grid_constant_
   uint64_t* b_full_bar = bars + 2 * STAGES + 4;
   uint64_t* b_empty_bar = bars + 2 * STAGES + 5;
   uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 6);
+  float* sbias = reinterpret_cast<float*>(bars + 32);  // [BN] per-column bias of the current tile (fast epilogue)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -518,6 +642,10 @@ __global__ void __launch_bounds__(384, 1) gemm_tcp_kernel(const __grid_constant_
             const int s = it % STAGES;
             const uint32_t ph = (it / STAGES) & 1;
             mbar_wait(&empty_bar[s], ph ^ 1);
+            if ((p.debug & 4) && it >= STAGES) {
+              mbar_arrive(&full_bar[s]);
+              continue;
+            }
             mbar_expect_tx(&full_bar[s], Cfg::STAGE_BYTES);
             tma_load_4d(smem_a + s * Cfg::A_BYTES, &tma_a, &full_bar[s], kb * BK, (m0 + mt) * BM, az1, az2);
             if (!BRES) tma_load_4d(smem_b + s * Cfg::B_BYTES, &tma_b, &full_bar[s], kb * BK, n_tile * BN, bz1, bz2);
@@ -563,15 +691,70 @@ __global__ void __launch_bounds__(384, 1) gemm_tcp_kernel(const __grid_constant_
     }
   } else if (warp >= 4) {
     int lt = 0;
+    const int ew = (warp - 4) & 3, half = (warp - 4) >> 2, tid_e = threadIdx.x - 128;
+    // the fast epilogue covers alpha/bias/clamp with a TMA-store output; everything else takes the generic one
+    const bool fast = BN >= 64 && p.use_tma_store && p.act == MQDET_ACT_NONE && p.gate_mode == MQDET_VEC_NONE;
+    const bool bcol = p.bias_mode == MQDET_VEC_PER_COL, brow = p.bias_mode == MQDET_VEC_PER_ROW;
+    const float bscale = p.scale_after_bias ? p.alpha : 1.f;  // alpha * (acc + b) == fma(alpha, acc, alpha * b)
     for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
       int z, m0, mcount, n_tile;
       decode(item, z, m0, mcount, n_tile);
+      const int z1 = z % p.nb1, z2 = z / p.nb1;
       for (int mt = 0; mt < mcount; ++mt, ++lt) {
         const int buf = lt & 1;
+        if (fast) {
+          // bias values are fetched BEFORE waiting for the accumulator, so their latency is never exposed
+          const bool refresh = bcol && (!BRES || mt == 0);
+          float bpre = 0.f, brow_eff = 0.f;
+          if (refresh) {
+            const long col = (long)n_tile * BN + tid_e;
+            if (tid_e < BN && col < p.N) bpre = bscale * p.bias[z1 * p.bias_b1 + z2 * p.bias_b2 + col];
+          }
+          if (brow) {
+            const long row = (long)(m0 + mt) * BM + ew * 32 + lane;
+            if (row < p.M) brow_eff = bscale * p.bias[z1 * p.bias_b1 + z2 * p.bias_b2 + row];
+          }
+          mbar_wait(&tmem_full_bar[buf], (lt >> 1) & 1);
+          tc_fence_after();
+          if (p.debug & 1) {
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty_bar[buf]);
+            continue;
+          }
+          if (refresh) {  // every epilogue warp left the previous tile's column loop at its closing barrier
+            if (tid_e < BN) sbias[tid_e] = bpre;
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+          }
+          const float* sb = bcol ? sbias : nullptr;
+          if constexpr (BN == 256 && BRES) {
+            // four 64-column windows through two alternating 16 KB staging tiles (fp16 TMA-store epilogue only)
+#pragma unroll 1
+            for (int w = 0; w < 4; ++w)
+              epilogue_fast<BN>(p, &tma_c, tmem_base + (uint32_t)(buf * BN), stg + (w & 1) * (BM * 128), sb, brow_eff, m0 + mt,
+                                n_tile, z1, z2, ew, lane, &tmem_empty_bar[buf], true, half, w * 64, 64, w == 3);
+          } else {
+            epilogue_fast<BN>(p, &tma_c, tmem_base + (uint32_t)(buf * BN), stg + (stg2 ? (lt & 1) * (BM * BN * 2) : 0), sb,
+                              brow_eff, m0 + mt, n_tile, z1, z2, ew, lane, &tmem_empty_bar[buf], stg2, half, 0, BN, true);
+          }
+          continue;
+        }
         mbar_wait(&tmem_full_bar[buf], (lt >> 1) & 1);
         tc_fence_after();
-        epilogue_tile<BN>(p, &tma_c, tmem_base + (uint32_t)(buf * BN), stg + (stg2 ? (lt & 1) * (BM * BN * 2) : 0), m0 + mt, n_tile,
-                          z % p.nb1, z / p.nb1, (warp - 4) & 3, lane, &tmem_empty_bar[buf], stg2 ? 1 : 0, (warp - 4) >> 2, 2);
+        if (p.debug & 1) {
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tmem_empty_bar[buf]);
+          continue;
+        }
+        if constexpr (BN == 256 && BRES) {
+          // (dispatched with the TMA-store epilogue only) four 64-column windows, two alternating 16 KB staging tiles
+#pragma unroll 1
+          for (int w = 0; w < 4; ++w)
+            epilogue_tile<BN>(p, &tma_c, tmem_base + (uint32_t)(buf * BN), stg + (w & 1) * (BM * 128), m0 + mt, n_tile, z1, z2, ew,
+                              lane, &tmem_empty_bar[buf], 1, half, 2, w * 64, 64, w == 3);
+        } else {
+          epilogue_tile<BN>(p, &tma_c, tmem_base + (uint32_t)(buf * BN), stg + (stg2 ? (lt & 1) * (BM * BN * 2) : 0), m0 + mt,
+                            n_tile, z1, z2, ew, lane, &tmem_empty_bar[buf], stg2 ? 1 : 0, half, 2);
+        }
       }
     }
     if (threadIdx.x == 128) tma_store_wait_read_all();
@@ -783,14 +966,29 @@ static int launch_tcp(const GemmP& p0, cudaStream_t st) {
   int mc = 1;
   long total = (long)tm * tn * Z;
   if (BRES) {
-    // runs of M tiles per resident B tile: long enough to amortise the B load, short enough for ~3 items per SM
-    const long want = 3L * num_sms();
-    mc = (int)(total / want);
-    if (mc < 1) mc = 1;
-    if (mc > tm) mc = tm;
+    // Runs of `mc` M tiles per resident B tile.  Items are dealt round-robin to the CTAs, so the kernel lasts
+    // rounds x (mc + B-tile reload, ~1.5 tile times exposed): pick the run length that minimises it (long runs amortise
+    // the reload, short ones balance the last round); ties go to the longer run.
+    const long sms = num_sms();
+    double best = 1e30;
+    for (int c = 1; c <= tm; ++c) {
+      const long items = (long)cdiv(tm, c) * tn * Z;
+      const long rounds = (items + sms - 1) / sms;
+      const double cost = (double)rounds * (c + 1.5);
+      if (cost <= best) {
+        best = cost;
+        mc = c;
+      }
+    }
     total = (long)cdiv(tm, mc) * tn * Z;
   }
   const int grid = (int)(total < num_sms() ? total : num_sms());
+  if (const char* dbg = getenv("MQDET_GEMM_DEBUG")) {
+    GemmP q = p;
+    q.debug = atoi(dbg);
+    gemm_tcp_kernel<BN, STAGES, BRES><<<grid, 384, Cfg::SMEM_BYTES, st>>>(ma, mb, mc_map, q, tm, tn, (int)total, mc);
+    return check_launch("gemm_tcp_kernel");
+  }
   gemm_tcp_kernel<BN, STAGES, BRES><<<grid, 384, Cfg::SMEM_BYTES, st>>>(ma, mb, mc_map, p, tm, tn, (int)total, mc);
   return check_launch("gemm_tcp_kernel");
 }
@@ -847,6 +1045,11 @@ extern "C" int mqdet_gemm_f16(const mqdet_gemm_args* a, int impl, void* stream) 
   const long w128 = (t128 + num_sms() - 1) / num_sms(), w64 = (t64 + num_sms() - 1) / num_sms();
   const bool wide = p.N > 64 && (w128 * 128 * 10 <= w64 * 64 * 12);  // the narrow tile must win by > 20 %
   if (p.K <= BRES_KB * BK && mt * cdiv(p.N, 128) * z >= 2L * num_sms()) {
+    // 128x128 MMAs (both operands from shared memory) run at about half the tensor rate of 128x256 (measured: 684 vs
+    // 1750 TFLOP/s with loads and epilogue disabled), so the 256-wide resident tile is used whenever the output can take
+    // the fp16 TMA-store epilogue
+    if (p.N >= 256 && p.c_dtype == MQDET_F16 && can_tma_store(p, 256) && mt * cdiv(p.N, 256) * z >= num_sms())
+      return launch_tcp<256, 3, true>(p, st);
     if (wide) return launch_tcp<128, 4, true>(p, st);
   }
   if (p.K >= 512 && p.N >= 256 && p.c_dtype == MQDET_F16 && mt * cdiv(p.N, 256) * z >= num_sms() && can_tma_store(p, 256))

@@ -50,6 +50,9 @@ for i, (M, N, K, what) in enumerate(SHAPES):
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / 10
+    if mode == "timeonly":
+        print(f"{M}x{N}x{K} ms={ms:.4f} tflops={2 * M * N * K / ms / 1e9:.1f}", flush=True)
+        continue
     for _ in range(3):
         torch.matmul(a, b.T, out=c)
     e0.record()
