@@ -136,6 +136,12 @@ int mqdet_l2norm_rowdot(const float* x, int64_t rows, int64_t D, float eps, cons
 int mqdet_cast_f32_f16(const float* x, void* y, int64_t n, void* stream);
 int mqdet_cast_f16_f32(const void* x, float* y, int64_t n, void* stream);
 
+/* GroundingDINO ContrastiveEmbed.forward tail (groundingdino_new/models/GroundingDINO/utils.py:261-266): logits [B,Q,Tmax]
+ * f32 whose first T columns hold x . y^T (mqdet_gemm_f16); columns of padding tokens (text_token_mask [B,T] bytes, 0 =
+ * padding) and columns T..Tmax-1 are set to -inf in place. */
+int mqdet_contrastive_mask(float* logits, const uint8_t* text_token_mask, int64_t B, int64_t Q, int64_t T, int64_t Tmax,
+                           void* stream);
+
 /* Stable descending argsort of n <= 16384 fp32 scores (ties: lower index first), single CTA bitonic sort. */
 int mqdet_argsort_desc(const float* scores, int64_t n, int64_t* order, void* stream);
 

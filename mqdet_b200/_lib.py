@@ -58,6 +58,7 @@ SIGNATURES = {
                                     c_void_p, c_void_p]),
     "mqdet_cast_f32_f16": (c_int, [c_void_p, c_void_p, c_int64, c_void_p]),
     "mqdet_cast_f16_f32": (c_int, [c_void_p, c_void_p, c_int64, c_void_p]),
+    "mqdet_contrastive_mask": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64, c_void_p]),
     "mqdet_argsort_desc": (c_int, [c_void_p, c_int64, c_void_p, c_void_p]),
     "mqdet_ml_nms_workspace_bytes": (c_int64, [c_int64]),
     "mqdet_dcn_cols": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int64, c_int, c_void_p,
@@ -101,11 +102,37 @@ class MqdetError(RuntimeError):
     """Raised when a C-ABI call returns a negative code (mirrors the reference's AT_ERROR -> RuntimeError)."""
 
 
+# tools/breakdown.py sets this to a list: every C-ABI call is then bracketed by CUDA events -> (symbol, e0, e1)
+CALL_PROFILE = None
+
+
+class _Profiled:
+    """Proxy over the CDLL that times each entry point on the current stream (diagnostics only)."""
+
+    def __init__(self, lib):
+        self._lib = lib
+
+    def __getattr__(self, name):
+        fn = getattr(self._lib, name)
+        if name not in SIGNATURES or SIGNATURES[name][0] is not c_int or not SIGNATURES[name][1]:
+            return fn
+
+        def timed(*a):
+            import torch
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            rc = fn(*a)
+            e1.record()
+            CALL_PROFILE.append((name, e0, e1))
+            return rc
+        return timed
+
+
 def load():
     """Load the shared library and bind every declared symbol (raises if the build is missing)."""
     global _lib
     if _lib is not None:
-        return _lib
+        return _Profiled(_lib) if CALL_PROFILE is not None else _lib
     if not os.path.exists(LIB_PATH):
         raise MqdetError(
             f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "

@@ -51,6 +51,21 @@ __device__ __forceinline__ float gelu_erf(float x) {
   return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
 }
 
+// erf-GELU in ~18 issue slots (no branches): erfc(|z|) = t * P4(t) * exp(-z^2), t = 1 / (1 + 0.3275911 |z|)
+// (Abramowitz-Stegun 7.1.26, |abs err| < 1.5e-7), and 1 + erf(z) = erfc(|z|) for z < 0 (no cancellation), 2 - erfc(z) else.
+__device__ __forceinline__ float gelu_fast(float x) {
+  const float z = x * 0.70710678118654752440f;
+  const float az = fabsf(z);
+  float t;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, az, 1.f)));
+  float q = fmaf(1.061405429f, t, -1.453152027f);
+  q = fmaf(q, t, 1.421413741f);
+  q = fmaf(q, t, -0.284496736f);
+  q = fmaf(q, t, 0.254829592f);
+  const float e = q * t * __expf(-az * az);
+  return 0.5f * x * (z < 0.f ? e : 2.f - e);
+}
+
 // ---- mbarrier ------------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
@@ -80,6 +95,19 @@ __device__ __forceinline__ void ffma2(float& d0, float& d1, float a0, float a1, 
       "}\n"
       : "=f"(d0), "=f"(d1)
       : "f"(a0), "f"(a1), "f"(s), "f"(b0), "f"(b1));
+}
+// (d0, d1) = (a0, a1) * (s0, s1) + (b0, b1)
+__device__ __forceinline__ void ffma2v(float& d0, float& d1, float a0, float a1, float s0, float s1, float b0, float b1) {
+  asm("{\n"
+      ".reg .b64 va, vs, vb, vd;\n"
+      "mov.b64 va, {%2, %3};\n"
+      "mov.b64 vs, {%4, %5};\n"
+      "mov.b64 vb, {%6, %7};\n"
+      "fma.rn.f32x2 vd, va, vs, vb;\n"
+      "mov.b64 {%0, %1}, vd;\n"
+      "}\n"
+      : "=f"(d0), "=f"(d1)
+      : "f"(a0), "f"(a1), "f"(s0), "f"(s1), "f"(b0), "f"(b1));
 }
 __device__ __forceinline__ void fence_proxy_async() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");

@@ -42,6 +42,7 @@ struct GemmP {
   int a_bcast1, a_bcast2, b_bcast1, b_bcast2;  // 1 -> TMA coordinate pinned to 0
   int use_tma_store;
   // epilogue variant (host decides from alignment / residual)
+  int fast_epi;                                // persistent kernel: the compact epilogue applies (fast_epilogue_ok)
   int debug;                                   // MQDET_GEMM_DEBUG experiments: 1 = no epilogue, 2 = no TMA store, 4 = no A loads
 };
 
@@ -339,53 +340,106 @@ __device__ __forceinline__ void epilogue_tile(const GemmP& p, const CUtensorMap*
 }
 
 // ---- fast epilogue of the persistent kernel ---------------------------------------------------------------------------
-// The common case of the hot products: v = alpha * acc + bias (per column from shared memory | per row | none), optional
-// clamp, fp16/fp32 output through the swizzled staging tile + TMA store.  Kept apart from the generic epilogue so that its
-// loop is ~35 instructions per 16 columns (2 per element: packed FFMA2, F2FP pairs, 128-bit shared stores) and contiguous
-// in the instruction cache: with K <= 256 a 128x256 tile has only ~2000 tensor-pipe cycles to hide 32768 outputs.
-// Two register sets ping-pong so that the tcgen05.ld of the next 16 columns is in flight while this one is converted.
+// v = act(acc * S + T) (+ residual), optional clamp, fp16/fp32 output through the swizzled
+// staging tile + TMA store, where the gate is folded into the scale:  S = alpha * g,  T = b * g (or alpha * b * g).
+// S/T are either uniform per thread (no per-column vector) or read from two shared-memory rows filled once per tile/item.
+// Kept apart from the generic epilogue so that its loop is ~2 instructions per element (packed FFMA2, F2FP pairs, 128-bit
+// shared accesses) and contiguous in the instruction cache: with K <= 256 a 128x256 tile has only ~2000 tensor-pipe
+// cycles to hide 32768 outputs.  Two register sets ping-pong so that the tcgen05.ld (and the residual loads) of the next
+// 16 columns are in flight while this one is converted.
+struct FastEpi {
+  const float* s_vec;  // shared: per-column scale (nullptr -> uniform s_u / t_u)
+  const float* t_vec;  // shared: per-column addend
+  float s_u, t_u;
+  const void* res;     // residual row of this thread (already offset to row / batch), nullptr -> none
+  int res_f16;
+};
+
 template <int BN>
 __device__ __forceinline__ void epilogue_fast(const GemmP& p, const CUtensorMap* tma_c, uint32_t tmem_acc, uint8_t* stg,
-                                              const float* sbias, float brow_eff, int m_tile, int n_tile, int z1, int z2, int ew,
-                                              int lane, uint64_t* tmem_empty_bar, bool dbl, int half, int cw0, int cw,
-                                              bool release) {
+                                              const FastEpi& fe, int m_tile, int n_tile, int z1, int z2, int ew, int lane,
+                                              uint64_t* tmem_empty_bar, bool dbl, int half, int cw0, int cw, bool release) {
   const int r_local = ew * 32 + lane;
   const bool issuer = (ew == 0 && half == 0 && lane == 0);
   const uint32_t t_row = tmem_acc + ((uint32_t)(ew * 32) << 16);
   const int c_begin = cw0 + half * (cw >> 1), c_end = c_begin + (cw >> 1);  // (cw / 2) % 32 == 0
-  const float alpha = p.alpha, clampv = p.clamp;
+  const float clampv = p.clamp;
+  const int act = p.act;
   const bool f16 = p.c_dtype == MQDET_F16;
   const int sw = r_local & 7;
   const uint32_t stg_row = smem_u32(stg) + r_local * 128;
-  const uint32_t sb_addr = sbias ? smem_u32(sbias) : 0u;
+  const bool vec = fe.s_vec != nullptr;
+  const uint32_t s_addr = vec ? smem_u32(fe.s_vec) : 0u, t_addr = vec ? smem_u32(fe.t_vec) : 0u;
+  const float s_u = fe.s_u, t_u = fe.t_u;
+  const bool has_res = fe.res != nullptr, res16 = fe.res_f16 != 0;
+  const long ncol0 = (long)n_tile * BN;
   uint32_t ra[16], rb[16];
+  uint4 qa[4], qb[4];
+  // residual of 16 columns: 2 (fp16) or 4 (fp32) 16-byte loads; N % (16 / elem) == 0 (TMA-store rule) so a vector is
+  // either fully inside the row or fully outside
+  auto load_res = [&](uint4 (&q)[4], int c0) {
+    const long col = ncol0 + c0;
+    if (res16) {
+      const uint4* src = reinterpret_cast<const uint4*>(reinterpret_cast<const __half*>(fe.res) + col);
+#pragma unroll
+      for (int k = 0; k < 2; ++k) q[k] = (col + 8 * k < p.N) ? __ldg(src + k) : make_uint4(0, 0, 0, 0);
+    } else {
+      const uint4* src = reinterpret_cast<const uint4*>(reinterpret_cast<const float*>(fe.res) + col);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) q[k] = (col + 4 * k < p.N) ? __ldg(src + k) : make_uint4(0, 0, 0, 0);
+    }
+  };
   tmem_ld_32x16(t_row + (uint32_t)c_begin, ra);
+  if (has_res) load_res(qa, c_begin);
   if (!dbl) {  // ONE staging tile: the previous tile's TMA store must have read it before it is rewritten
     if (issuer) tma_store_wait_read_all();
     asm volatile("bar.sync 1, 256;" ::: "memory");
   }
-  auto emit = [&](uint32_t (&r)[16], int c0) {
+  auto emit = [&](uint32_t (&r)[16], uint4 (&q)[4], int c0) {
     float v[16];
-    if (sbias) {
+    if (vec) {
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const float4 t = lds128f(sb_addr + (uint32_t)(c0 * 4 + q * 16));
-        ffma2(v[4 * q], v[4 * q + 1], __uint_as_float(r[4 * q]), __uint_as_float(r[4 * q + 1]), alpha, t.x, t.y);
-        ffma2(v[4 * q + 2], v[4 * q + 3], __uint_as_float(r[4 * q + 2]), __uint_as_float(r[4 * q + 3]), alpha, t.z, t.w);
+      for (int k = 0; k < 4; ++k) {
+        const float4 sv = lds128f(s_addr + (uint32_t)(c0 * 4 + k * 16));
+        const float4 tv = lds128f(t_addr + (uint32_t)(c0 * 4 + k * 16));
+        ffma2v(v[4 * k], v[4 * k + 1], __uint_as_float(r[4 * k]), __uint_as_float(r[4 * k + 1]), sv.x, sv.y, tv.x, tv.y);
+        ffma2v(v[4 * k + 2], v[4 * k + 3], __uint_as_float(r[4 * k + 2]), __uint_as_float(r[4 * k + 3]), sv.z, sv.w, tv.z, tv.w);
       }
     } else {
 #pragma unroll
-      for (int q = 0; q < 8; ++q)
-        ffma2(v[2 * q], v[2 * q + 1], __uint_as_float(r[2 * q]), __uint_as_float(r[2 * q + 1]), alpha, brow_eff, brow_eff);
+      for (int k = 0; k < 8; ++k)
+        ffma2(v[2 * k], v[2 * k + 1], __uint_as_float(r[2 * k]), __uint_as_float(r[2 * k + 1]), s_u, t_u, t_u);
+    }
+    if (act == MQDET_ACT_GELU) {
+#pragma unroll
+      for (int k = 0; k < 16; ++k) v[k] = gelu_fast(v[k]);
+    } else if (act == MQDET_ACT_RELU) {
+#pragma unroll
+      for (int k = 0; k < 16; ++k) v[k] = fmaxf(v[k], 0.f);
+    }
+    if (has_res) {
+      if (res16) {
+        const __half2* h2 = reinterpret_cast<const __half2*>(q);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const float2 f = __half22float2(h2[k]);
+          v[2 * k] += f.x;
+          v[2 * k + 1] += f.y;
+        }
+      } else {
+        const float* f = reinterpret_cast<const float*>(q);
+#pragma unroll
+        for (int k = 0; k < 16; ++k) v[k] += f[k];
+      }
     }
     if (f16) {
       __half2 h[8];
 #pragma unroll
-      for (int q = 0; q < 8; ++q) h[q] = __floats2half2_rn(v[2 * q], v[2 * q + 1]);
+      for (int k = 0; k < 8; ++k) h[k] = __floats2half2_rn(v[2 * k], v[2 * k + 1]);
       if (clampv > 0.f) {  // clamp after rounding == rounding after clamp (rounding is monotonic)
         const __half2 hi = __float2half2_rn(clampv), lo = __float2half2_rn(-clampv);
 #pragma unroll
-        for (int q = 0; q < 8; ++q) h[q] = __hmax2(__hmin2(h[q], hi), lo);
+        for (int k = 0; k < 8; ++k) h[k] = __hmax2(__hmin2(h[k], hi), lo);
       }
       // column block of 64 halfs (128 B rows); this thread's 16 columns = 16-byte chunks j0, j0+1
       const uint32_t blk = stg_row + ((c0 - cw0) >> 6) * (BM * 128);
@@ -402,19 +456,23 @@ __device__ __forceinline__ void epilogue_fast(const GemmP& p, const CUtensorMap*
       const uint32_t blk = stg_row + ((c0 - cw0) >> 5) * (BM * 128);
       const int j0 = (c0 & 31) >> 2;
 #pragma unroll
-      for (int q = 0; q < 4; ++q)
-        sts128(blk + (((j0 + q) ^ sw) << 4), __float_as_uint(v[4 * q]), __float_as_uint(v[4 * q + 1]), __float_as_uint(v[4 * q + 2]),
-               __float_as_uint(v[4 * q + 3]));
+      for (int k = 0; k < 4; ++k)
+        sts128(blk + (((j0 + k) ^ sw) << 4), __float_as_uint(v[4 * k]), __float_as_uint(v[4 * k + 1]), __float_as_uint(v[4 * k + 2]),
+               __float_as_uint(v[4 * k + 3]));
     }
   };
 #pragma unroll 1
   for (int c0 = c_begin; c0 < c_end; c0 += 32) {
     tmem_ld_wait_dep(ra);
     tmem_ld_32x16(t_row + (uint32_t)(c0 + 16), rb);
-    emit(ra, c0);
+    if (has_res) load_res(qb, c0 + 16);
+    emit(ra, qa, c0);
     tmem_ld_wait_dep(rb);
-    if (c0 + 32 < c_end) tmem_ld_32x16(t_row + (uint32_t)(c0 + 32), ra);
-    emit(rb, c0 + 16);
+    if (c0 + 32 < c_end) {
+      tmem_ld_32x16(t_row + (uint32_t)(c0 + 32), ra);
+      if (has_res) load_res(qa, c0 + 32);
+    }
+    emit(rb, qb, c0 + 16);
   }
   tc_fence_before();
   if (release) {  // the accumulator buffer may be overwritten by the next tile's MMAs
@@ -430,7 +488,7 @@ __device__ __forceinline__ void epilogue_fast(const GemmP& p, const CUtensorMap*
     const int cz1 = p.nb1 == 1 ? 0 : z1, cz2 = p.nb2 == 1 ? 0 : z2;
     const int cpb = f16 ? 64 : 32;  // columns per 128-byte block
     for (int cb = 0; cb * cpb < cw; ++cb) {
-      const long cc = (long)n_tile * BN + cw0 + cb * cpb;
+      const long cc = ncol0 + cw0 + cb * cpb;
       if (cc < p.N) tma_store_4d(tma_c, stg + cb * (BM * 128), (int)cc, m_tile * BM, cz1, cz2);
     }
     tma_store_commit();  // the read is awaited where the staging tile is reused and once more before the kernel ends
@@ -552,7 +610,7 @@ struct TcpCfg {
   // epilogue (64 KB) because its fallback tile would not fit next to the ring
   // the B-resident 256-wide tile leaves room for two 64-column windows only (128 KB B + 48 KB A ring + 32 KB)
   static constexpr int STG_BYTES = BN == 256 ? (BRES ? 2 * BM * 64 * 2 : BM * BN * 2) : ((BM * (BN + 4) * 4 + 1023) / 1024) * 1024;
-  static constexpr int SMEM_BYTES = RING_BYTES + STG_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + BN * 4 /*bias*/;
+  static constexpr int SMEM_BYTES = RING_BYTES + STG_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + 2 * BN * 4 /*epilogue scale / addend rows*/;
 };
 
 template <int BN, int STAGES, bool BRES>
@@ -576,7 +634,8 @@ __global__ void __launch_bounds__(384, 1) gemm_tcp_kernel(const __grid_constant_
   uint64_t* b_full_bar = bars + 2 * STAGES + 4;
   uint64_t* b_empty_bar = bars + 2 * STAGES + 5;
   uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 6);
-  float* sbias = reinterpret_cast<float*>(bars + 32);  // [BN] per-column bias of the current tile (fast epilogue)
+  float* s_vec = reinterpret_cast<float*>(bars + 32);  // [BN] per-column scale and [BN] addend of the current tile
+  float* t_vec = s_vec + BN;                            // (fast epilogue)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -692,10 +751,14 @@ __global__ void __launch_bounds__(384, 1) gemm_tcp_kernel(const __grid_constant_
   } else if (warp >= 4) {
     int lt = 0;
     const int ew = (warp - 4) & 3, half = (warp - 4) >> 2, tid_e = threadIdx.x - 128;
-    // the fast epilogue covers alpha/bias/clamp with a TMA-store output; everything else takes the generic one
-    const bool fast = BN >= 64 && p.use_tma_store && p.act == MQDET_ACT_NONE && p.gate_mode == MQDET_VEC_NONE;
+    // the fast epilogue covers everything without an activation when the output takes the TMA store (host: fast_epilogue_ok)
+    const bool fast = p.fast_epi != 0;
     const bool bcol = p.bias_mode == MQDET_VEC_PER_COL, brow = p.bias_mode == MQDET_VEC_PER_ROW;
+    const bool gcol = p.gate_mode == MQDET_VEC_PER_COL, grow = p.gate_mode == MQDET_VEC_PER_ROW;
+    const bool vec = bcol || gcol;
     const float bscale = p.scale_after_bias ? p.alpha : 1.f;  // alpha * (acc + b) == fma(alpha, acc, alpha * b)
+    float g_u = 1.f;
+    if (fast && p.gate_mode == MQDET_VEC_SCALAR) g_u = p.gate_tanh ? tanhf(p.gate[0]) : p.gate[0];
     for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
       int z, m0, mcount, n_tile;
       decode(item, z, m0, mcount, n_tile);
@@ -703,16 +766,36 @@ __global__ void __launch_bounds__(384, 1) gemm_tcp_kernel(const __grid_constant_
       for (int mt = 0; mt < mcount; ++mt, ++lt) {
         const int buf = lt & 1;
         if (fast) {
-          // bias values are fetched BEFORE waiting for the accumulator, so their latency is never exposed
-          const bool refresh = bcol && (!BRES || mt == 0);
-          float bpre = 0.f, brow_eff = 0.f;
-          if (refresh) {
+          // per-column / per-row parameters are fetched BEFORE waiting for the accumulator: their latency is never exposed
+          const bool refresh = vec && (!BRES || mt == 0);
+          float s_pre = p.alpha, t_pre = 0.f;
+          if (refresh && tid_e < BN) {
             const long col = (long)n_tile * BN + tid_e;
-            if (tid_e < BN && col < p.N) bpre = bscale * p.bias[z1 * p.bias_b1 + z2 * p.bias_b2 + col];
+            float g = g_u, bv = 0.f;
+            if (col < p.N) {
+              if (gcol) g = p.gate_tanh ? tanhf(p.gate[col]) : p.gate[col];
+              if (bcol) bv = p.bias[z1 * p.bias_b1 + z2 * p.bias_b2 + col];
+            }
+            s_pre = p.alpha * g;
+            t_pre = bscale * bv * g;
           }
-          if (brow) {
-            const long row = (long)(m0 + mt) * BM + ew * 32 + lane;
-            if (row < p.M) brow_eff = bscale * p.bias[z1 * p.bias_b1 + z2 * p.bias_b2 + row];
+          const long row = (long)(m0 + mt) * BM + ew * 32 + lane;
+          FastEpi fe;
+          fe.s_vec = vec ? s_vec : nullptr;
+          fe.t_vec = t_vec;
+          float g_r = g_u, b_r = 0.f;
+          if (row < p.M) {
+            if (grow) g_r = p.gate_tanh ? tanhf(p.gate[row]) : p.gate[row];
+            if (brow) b_r = p.bias[z1 * p.bias_b1 + z2 * p.bias_b2 + row];
+          }
+          fe.s_u = p.alpha * g_r;
+          fe.t_u = bscale * b_r * g_r;
+          fe.res = nullptr;
+          fe.res_f16 = p.r_dtype == MQDET_F16;
+          if (p.R && row < p.M) {
+            const long off = z1 * p.r_b1 + z2 * p.r_b2 + row * p.ldr;
+            fe.res = fe.res_f16 ? (const void*)(reinterpret_cast<const __half*>(p.R) + off)
+                                : (const void*)(reinterpret_cast<const float*>(p.R) + off);
           }
           mbar_wait(&tmem_full_bar[buf], (lt >> 1) & 1);
           tc_fence_after();
@@ -722,19 +805,21 @@ __global__ void __launch_bounds__(384, 1) gemm_tcp_kernel(const __grid_constant_
             continue;
           }
           if (refresh) {  // every epilogue warp left the previous tile's column loop at its closing barrier
-            if (tid_e < BN) sbias[tid_e] = bpre;
+            if (tid_e < BN) {
+              s_vec[tid_e] = s_pre;
+              t_vec[tid_e] = t_pre;
+            }
             asm volatile("bar.sync 1, 256;" ::: "memory");
           }
-          const float* sb = bcol ? sbias : nullptr;
           if constexpr (BN == 256 && BRES) {
             // four 64-column windows through two alternating 16 KB staging tiles (fp16 TMA-store epilogue only)
 #pragma unroll 1
             for (int w = 0; w < 4; ++w)
-              epilogue_fast<BN>(p, &tma_c, tmem_base + (uint32_t)(buf * BN), stg + (w & 1) * (BM * 128), sb, brow_eff, m0 + mt,
-                                n_tile, z1, z2, ew, lane, &tmem_empty_bar[buf], true, half, w * 64, 64, w == 3);
+              epilogue_fast<BN>(p, &tma_c, tmem_base + (uint32_t)(buf * BN), stg + (w & 1) * (BM * 128), fe, m0 + mt, n_tile, z1, z2,
+                                ew, lane, &tmem_empty_bar[buf], true, half, w * 64, 64, w == 3);
           } else {
-            epilogue_fast<BN>(p, &tma_c, tmem_base + (uint32_t)(buf * BN), stg + (stg2 ? (lt & 1) * (BM * BN * 2) : 0), sb,
-                              brow_eff, m0 + mt, n_tile, z1, z2, ew, lane, &tmem_empty_bar[buf], stg2, half, 0, BN, true);
+            epilogue_fast<BN>(p, &tma_c, tmem_base + (uint32_t)(buf * BN), stg + (stg2 ? (lt & 1) * (BM * BN * 2) : 0), fe, m0 + mt,
+                              n_tile, z1, z2, ew, lane, &tmem_empty_bar[buf], stg2, half, 0, BN, true);
           }
           continue;
         }
@@ -881,11 +966,31 @@ static int make_output_map(CUtensorMap* map, const GemmP& p) {
   return MQDET_OK;
 }
 
-// TMA store needs 16-byte aligned rows/batches, and the epilogue variant without residual.
-static bool can_tma_store(const GemmP& p, int BN) {
+// What the persistent kernel's fast epilogue covers (everything else takes the generic one, which has no TMA-store +
+// residual variant): no activation; the gate folds into the scale, so a clamp (applied BEFORE the gate) excludes gates,
+// and a per-row gate/bias excludes per-column vectors; residual rows must take 16-byte loads.
+static bool fast_epilogue_ok(const GemmP& p) {
+  // order of the full epilogue: bias -> activation -> clamp -> gate -> residual; the fast one computes acc * S + T with the
+  // gate folded in, then activation, residual, clamp: identical unless an activation or clamp meets a gate / residual
+  if (p.act != MQDET_ACT_NONE && p.gate_mode != MQDET_VEC_NONE) return false;
+  if (p.clamp > 0.f && (p.gate_mode != MQDET_VEC_NONE || p.R)) return false;
+  const bool colv = p.bias_mode == MQDET_VEC_PER_COL || p.gate_mode == MQDET_VEC_PER_COL;
+  const bool rowv = p.bias_mode == MQDET_VEC_PER_ROW || p.gate_mode == MQDET_VEC_PER_ROW;
+  if (colv && rowv) return false;
+  if (p.R) {
+    const long al = p.r_dtype == MQDET_F16 ? 8 : 4;
+    if ((reinterpret_cast<uintptr_t>(p.R) & 15) || (p.ldr % al) || (p.nb1 > 1 && (p.r_b1 % al)) || (p.nb2 > 1 && (p.r_b2 % al)))
+      return false;
+  }
+  return true;
+}
+
+// TMA store needs 16-byte aligned rows/batches; a residual only goes with it in the persistent kernel's fast epilogue.
+static bool can_tma_store(const GemmP& p, int BN, bool persistent = false) {
   const int es = (p.c_dtype == MQDET_F16) ? 2 : 4;
   const long al = 16 / es;
-  if (p.R || BN < 128 / es) return false;
+  if (BN < 128 / es) return false;
+  if (p.R && !(persistent && BN >= 64 && fast_epilogue_ok(p))) return false;
   if (p.N % al) return false;  // the TMA unit bounds the innermost dimension at 16-byte granularity (measured): a ragged
                                // N would spill into the row padding, so those shapes take the masked fallback
   if ((reinterpret_cast<uintptr_t>(p.C) & 15) || (p.ldc % al) || (p.nb1 > 1 && (p.c_b1 % al)) || (p.nb2 > 1 && (p.c_b2 % al)))
@@ -946,7 +1051,8 @@ static int launch_tcp(const GemmP& p0, cudaStream_t st) {
   rc = make_operand_map(&mb, p.B, p.N, p.K, p.ldb, p.nb1, p.b_b1, p.nb2, p.b_b2, BN, &p.b_bcast1, &p.b_bcast2);
   if (rc) return rc;
   CUtensorMap mc_map = ma;
-  p.use_tma_store = can_tma_store(p, BN) ? 1 : 0;
+  p.use_tma_store = can_tma_store(p, BN, true) ? 1 : 0;
+  p.fast_epi = (p.use_tma_store && BN >= 64 && fast_epilogue_ok(p)) ? 1 : 0;
   if (p.use_tma_store) {
     rc = make_output_map(&mc_map, p);
     if (rc) return rc;
@@ -1048,11 +1154,11 @@ extern "C" int mqdet_gemm_f16(const mqdet_gemm_args* a, int impl, void* stream) 
     // 128x128 MMAs (both operands from shared memory) run at about half the tensor rate of 128x256 (measured: 684 vs
     // 1750 TFLOP/s with loads and epilogue disabled), so the 256-wide resident tile is used whenever the output can take
     // the fp16 TMA-store epilogue
-    if (p.N >= 256 && p.c_dtype == MQDET_F16 && can_tma_store(p, 256) && mt * cdiv(p.N, 256) * z >= num_sms())
+    if (p.N >= 256 && p.c_dtype == MQDET_F16 && can_tma_store(p, 256, true) && mt * cdiv(p.N, 256) * z >= num_sms())
       return launch_tcp<256, 3, true>(p, st);
     if (wide) return launch_tcp<128, 4, true>(p, st);
   }
-  if (p.K >= 512 && p.N >= 256 && p.c_dtype == MQDET_F16 && mt * cdiv(p.N, 256) * z >= num_sms() && can_tma_store(p, 256))
+  if (p.K >= 512 && p.N >= 256 && p.c_dtype == MQDET_F16 && mt * cdiv(p.N, 256) * z >= num_sms() && can_tma_store(p, 256, true))
     return launch_tcp<256, 3, false>(p, st);  // long-K: 128x256 tiles halve the A re-reads (MMA/L2 bound regime)
   if (wide) return launch_tcp<128, 4, false>(p, st);
   if (p.N > 32) return launch_tcp<64, 4, false>(p, st);

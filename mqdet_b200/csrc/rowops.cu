@@ -328,6 +328,17 @@ __global__ void __launch_bounds__(256) colsoftmax_write_kernel(const __half* __r
   }
 }
 
+// ContrastiveEmbed tail (groundingdino_new/models/GroundingDINO/utils.py:261-266): columns of padding tokens and the
+// columns T .. Tmax-1 of the [B, Q, Tmax] logits become -inf; the first T columns were written by the x . y^T product.
+__global__ void contrastive_mask_kernel(float* __restrict__ logits, const uint8_t* __restrict__ text_token_mask, long rows,
+                                        int Q, int T, int Tmax) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * Tmax) return;
+  const int t = (int)(i % Tmax);
+  const long b = (i / Tmax) / Q;
+  if (t >= T || !text_token_mask[b * T + t]) logits[i] = -INFINITY;
+}
+
 __global__ void cast_f32_f16_kernel(const float* __restrict__ x, __half* __restrict__ y, long n) {
   long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
   const long stride = (long)gridDim.x * blockDim.x;
@@ -444,6 +455,15 @@ extern "C" int mqdet_cast_f32_f16(const float* x, void* y, int64_t n, void* stre
   cast_f32_f16_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(x, (__half*)y, n);
   return check_launch("cast_f32_f16_kernel");
 }
+extern "C" int mqdet_contrastive_mask(float* logits, const uint8_t* text_token_mask, int64_t B, int64_t Q, int64_t T,
+                                      int64_t Tmax, void* stream) {
+  MQ_REQUIRE(logits && text_token_mask && B > 0 && Q > 0 && T > 0 && Tmax >= T, "contrastive_mask: bad args");
+  const long n = B * Q * Tmax;
+  contrastive_mask_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(logits, text_token_mask, B * Q, (int)Q,
+                                                                                       (int)T, (int)Tmax);
+  return check_launch("contrastive_mask");
+}
+
 extern "C" int mqdet_cast_f16_f32(const void* x, float* y, int64_t n, void* stream) {
   MQ_REQUIRE(x && y && n > 0, "cast: bad args");
   int blocks = (int)((n + 255) / 256);

@@ -222,6 +222,21 @@ def cast_f32(x):
     return y
 
 
+def contrastive_embed(x16, y16, text_token_mask, max_text_len):
+    """x16 [B,Q,D] fp16, y16 [B,T,D] fp16, text_token_mask [B,T] bool -> logits [B,Q,max_text_len] fp32:
+    x . y^T, -inf on padding tokens and on columns T..max_text_len-1 (GroundingDINO utils.py:242-268)."""
+    global launch_count
+    _need_cuda(x16, y16, text_token_mask)
+    B, Q, _ = x16.shape
+    T = y16.shape[1]
+    out = torch.empty((B, Q, max_text_len), dtype=torch.float32, device=x16.device)
+    gemm(x16, y16, out=out[:, :, :T])
+    m8 = text_token_mask.to(torch.uint8).contiguous()
+    check(load().mqdet_contrastive_mask(_ptr(out), _ptr(m8), B, Q, T, max_text_len, _stream()), "contrastive_mask")
+    launch_count += 1
+    return out
+
+
 def gcp_build_index(mask, S):
     """mask [B, V, T] fp32 0/1 -> (idx int32 [B, T, S] padded with V, counts int32 [B, T])."""
     global launch_count

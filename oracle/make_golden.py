@@ -87,6 +87,13 @@ def case_inputs(name):
         fsd = synth.fpn_sd(gen)
         img = gen.randn(2, 3, 150, 203, scale=1.0)  # not a multiple of 4/7/2: exercises every padding path
         return dict(sd=sd, fsd=fsd, img=img)
+    if name == "contrastive_embed":
+        gen = synth.Gen(1239)
+        B, Q, T, D = 2, 900, 195, 256
+        mask = torch.ones(B, T, dtype=torch.bool)
+        mask[0, 150:] = False
+        mask[1, 17:] = False
+        return dict(x=gen.randn(B, Q, D), y=gen.randn(B, T, D), mask=mask)
     raise KeyError(name)
 
 
@@ -133,6 +140,9 @@ def run_reference(name):
         # wiring of BertEncoderLayer.forward (maskrcnn_benchmark/modeling/rpn/vldyhead.py:264-301)
         a = att(c["h"], ext, None, output_attentions=False, past_key_value=None)[0]
         return dict(h=outp(inter(a), a))
+    if name == "contrastive_embed":
+        mod = rl.gdino_utils().ContrastiveEmbed(max_text_len=256)
+        return dict(logits=mod(c["x"], {"encoded_text": c["y"], "text_token_mask": c["mask"]}))
     if name == "swin_fpn":
         sw = rl.swint()
         body = sw.SwinTransformer(embed_dim=96, depths=[2, 2, 6, 2], num_heads=[3, 6, 12, 24], window_size=7,
@@ -157,18 +167,22 @@ def run_reference(name):
 
 SUBSAMPLE = {"gcp_block": {"y": (4, 8), "s": (4, 8)}, "preselect": {"vision": (1, 8)},
              "bi_attention": {"v": (3, 4), "l": (4, 8)}, "bert_layer": {"h": (4, 8)},
+             "contrastive_embed": {"logits": (9, 1)},
              "swin_fpn": {"c3": (4, 2, 2), "c4": (4, 1, 1), "c5": (8, 1, 1), "p3": (4, 2, 2), "p4": (4, 1, 1), "p5": (4, 1, 1),
                           "p6": (2, 1, 1), "p7": (1, 1, 1)}}
 
 
 def main():
     os.makedirs(GOLDEN_DIR, exist_ok=True)
+    only = sys.argv[1:]
     for name, subs in SUBSAMPLE.items():
+        if only and name not in only:
+            continue
         out = run_reference(name)
         fx = {"case": name, "subsample": subs, "torch": str(torch.__version__)}
         for k, steps in subs.items():
             fx[k] = sub(out[k].float(), *steps)
-            fx[k + "_absmax"] = out[k].abs().max().item()
+            fx[k + "_absmax"] = out[k][torch.isfinite(out[k])].abs().max().item()
         path = os.path.join(GOLDEN_DIR, f"{name}.pt")
         torch.save(fx, path)
         print(name, {k: tuple(fx[k].shape) for k in subs}, os.path.getsize(path), "bytes")

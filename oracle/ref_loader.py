@@ -137,6 +137,13 @@ def swint():
     return _cache["swint"]
 
 
+def gdino_utils():
+    """groundingdino_new/models/GroundingDINO/utils.py (ContrastiveEmbed; the file only needs torch)."""
+    if "gdu" not in _cache:
+        _cache["gdu"] = _load_file("ref_gdino_utils", "groundingdino_new/models/GroundingDINO/utils.py")
+    return _cache["gdu"]
+
+
 def fpn():
     """maskrcnn_benchmark/modeling/backbone/fpn.py (FPN, LastLevelP6P7)."""
     if "fpn" not in _cache:

@@ -74,6 +74,51 @@ def test_persistent_many_tiles_per_cta(dev):
         _check(ops.gemm(a, b, bias=bias, residual=res, out_dtype=torch.float32), ref + bias + res, False)  # fallback epilogue
 
 
+def test_persistent_epilogue_modes(dev):
+    """Every epilogue combination the forward uses, at sizes that take the persistent kernels (>= 2 tiles per SM):
+    the compact fast epilogue (scale/addend folding, residual prefetch, clamp), the generic one (GELU) and the
+    128x256 B-resident / long-K tiles with their 64-column staging windows."""
+    from mqdet_b200 import ops
+    from mqdet_b200._lib import ACT_GELU, VEC_PER_COL, VEC_PER_ROW, VEC_SCALAR
+    g = torch.Generator(device="cpu").manual_seed(21)
+
+    def mk(*shape, s=0.3):
+        return (torch.randn(*shape, generator=g) * s)
+
+    # K <= 256 (B-resident tiles), N = 512: 256-wide tile when the output is fp16 + TMA-storable
+    M, N, K = 128 * 300 + 40, 512, 256
+    a, b = mk(M, K).half().to(dev), mk(N, K).half().to(dev)
+    bc, br, gc = mk(N, s=1).to(dev), mk(M, s=1).to(dev), mk(N, s=1).to(dev)
+    r16, r32 = mk(M, N, s=1).half().to(dev), mk(M, N, s=1).to(dev)
+    gs = torch.tensor([0.4], device=dev)
+    _check(ops.gemm(a, b, bias=bc, alpha=0.25, scale_after_bias=True), _ref(a, b, bias=bc, bias_mode="col", alpha=0.25, scale_after_bias=True), True)
+    _check(ops.gemm(a, b, bias=br, bias_mode=VEC_PER_ROW), _ref(a, b, bias=br, bias_mode="row"), True)
+    _check(ops.gemm(a, b, clamp=2.0), _ref(a, b, clamp=2.0), True)
+    _check(ops.gemm(a, b, bias=bc, act=ACT_GELU), _ref(a, b, bias=bc, bias_mode="col", act="gelu"), True)
+    _check(ops.gemm(a, b, bias=bc, gate=gc, gate_mode=VEC_PER_COL, residual=r16),
+           _ref(a, b, bias=bc, bias_mode="col", gate=gc, residual=r16), True)
+    _check(ops.gemm(a, b, bias=bc, residual=r32, out_dtype=torch.float32), _ref(a, b, bias=bc, bias_mode="col", residual=r32), False)
+    _check(ops.gemm(a, b, gate=gs, gate_mode=VEC_SCALAR, gate_tanh=True, residual=r32, out_dtype=torch.float32),
+           _ref(a, b, gate=gs, gate_tanh=True, residual=r32), False)
+    _check(ops.gemm(a, b, bias=bc, gate=br, gate_mode=VEC_PER_ROW, out_dtype=torch.float32),   # col bias + row gate: generic
+           _ref(a, b, bias=bc, bias_mode="col") * br[:, None], False)
+    # long K (ring-streamed 128x256 tile), gamma * (acc + b) + fp16 residual = the BiAttention out-projection
+    M, N, K = 128 * 200 + 8, 256, 1024
+    a, b = mk(M, K).half().to(dev), mk(N, K, s=0.1).half().to(dev)
+    bc, gc = mk(N, s=1).to(dev), mk(N, s=1).to(dev)
+    r16 = mk(M, N, s=1).half().to(dev)
+    _check(ops.gemm(a, b, bias=bc, gate=gc, gate_mode=VEC_PER_COL, residual=r16),
+           _ref(a, b, bias=bc, bias_mode="col", gate=gc, residual=r16), True)
+    _check(ops.gemm(a, b, bias=bc, act=ACT_GELU), _ref(a, b, bias=bc, bias_mode="col", act="gelu"), True)
+    # batched, per-batch bias rows, narrow tile (N = 64) fast epilogue
+    Bz, M, N, K = 3, 128 * 120, 64, 128
+    a, b = mk(Bz, M, K).half().to(dev), mk(Bz, N, K).half().to(dev)
+    r32 = mk(Bz, M, N, s=1).to(dev)
+    ref = torch.einsum("zmk,znk->zmn", a.float(), b.float())
+    _check(ops.gemm(a, b, residual=r32, out_dtype=torch.float32), ref + r32, False)
+    _check(ops.gemm(a, b, alpha=0.5), 0.5 * ref, True)
+
+
 def test_epilogues(dev):
     from mqdet_b200 import ops
     from mqdet_b200._lib import ACT_GELU, ACT_RELU, VEC_PER_COL, VEC_PER_ROW, VEC_SCALAR

@@ -115,3 +115,14 @@ def test_dcn_fast_path_equals_gather_formulation():
         a = restate.dcn_v2(x, off, m, w, b, stride, fast=True)
         c = restate.dcn_v2(x, off, m, w, b, stride, fast=False)
         assert (a - c).abs().max().item() <= 1e-5
+
+
+def test_contrastive_embed_golden():
+    """GroundingDINO ContrastiveEmbed: -inf pattern exact, finite logits to summation-order noise."""
+    fx = torch.load(os.path.join(GOLD, "contrastive_embed.pt"))
+    c = make_golden.case_inputs("contrastive_embed")
+    got = make_golden.sub(restate.contrastive_embed(c["x"], c["y"], c["mask"], 256), *fx["subsample"]["logits"])
+    ref = fx["logits"]
+    assert torch.equal(torch.isinf(got), torch.isinf(ref))
+    fin = torch.isfinite(ref)
+    assert (got[fin] - ref[fin]).abs().max().item() <= 2e-5 * fx["logits_absmax"]

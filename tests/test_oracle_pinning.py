@@ -52,3 +52,13 @@ def test_swin_fpn_vs_reference():
         _close(o, ref[f"c{i + 2}"], 1e-5)
     for i, o in enumerate(restate.fpn(outs, c["fsd"])):
         _close(o, ref[f"p{i + 3}"], 1e-5)
+
+
+def test_contrastive_embed_vs_reference():
+    c = make_golden.case_inputs("contrastive_embed")
+    ref = make_golden.run_reference("contrastive_embed")["logits"]
+    got = restate.contrastive_embed(c["x"], c["y"], c["mask"], 256)
+    assert got.shape == ref.shape == (2, 900, 256)
+    assert torch.equal(torch.isinf(got), torch.isinf(ref))          # padding tokens and columns T..255 are -inf
+    fin = torch.isfinite(ref)
+    assert torch.equal(got[fin], ref[fin])                           # same fp32 product

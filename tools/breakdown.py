@@ -85,38 +85,34 @@ total = t0.elapsed_time(t1)
 print(f"total {total:.2f} ms (B={B})")
 for k, v in agg.items():
     print(f"  {v:8.2f} ms  {100*v/total:5.1f}%  {k}")
-# GEMM shape histogram
-prof = ops.GEMM_PROFILE = []
+# per C-ABI entry point (all of the product's kernels go through these) + GEMM shapes
+from mqdet_b200 import _lib
+_lib.CALL_PROFILE = []
+ops.GEMM_PROFILE = []
+t0.record()
 model.forward_device(ImageList(x, sizes), caps, pmap)
+t1.record()
 torch.cuda.synchronize()
+calls, prof = _lib.CALL_PROFILE, ops.GEMM_PROFILE
+_lib.CALL_PROFILE = None
 ops.GEMM_PROFILE = None
-sh = collections.defaultdict(lambda: [0, 0.0, 0.0])
+by = {}
+for name, a, b in calls:
+    e = by.setdefault(name, [0, 0.0])
+    e[0] += 1
+    e[1] += a.elapsed_time(b)
+tot = sum(v[1] for v in by.values())
+print(f"C-ABI calls: {sum(v[0] for v in by.values())} launches, {tot:.2f} ms inside them, step (with event overhead) {t0.elapsed_time(t1):.2f} ms")
+for name, (c, ms) in sorted(by.items(), key=lambda kv: -kv[1][1]):
+    print(f"  {ms:8.2f} ms {100 * ms / tot:5.1f}%  x{c:4d}  {name}")
+sh = {}
 for a, b, fl, shape in prof:
-    e = sh[shape]
+    e = sh.setdefault(shape, [0, 0.0, 0.0])
     e[0] += 1
     e[1] += a.elapsed_time(b)
     e[2] += fl
-print("top GEMM shapes (M,N,K,batch): count, ms, TFLOP/s")
-for shape, (c, ms, fl) in sorted(sh.items(), key=lambda kv: -kv[1][1])[:14]:
-    print(f"  {shape}: x{c} {ms:7.2f} ms {fl/ms/1e9:7.1f}")
-json.dump({"total_ms": total, "stages": agg}, open(os.path.join(ROOT, "gpurun_out", "breakdown.json"), "w"), indent=1)
-
-# kernel-level totals via torch.profiler (CUPTI): shares only, not a benchmark
-try:
-    from torch.profiler import ProfilerActivity, profile
-    mb.BertLayer.forward = orig_bert
-    with profile(activities=[ProfilerActivity.CUDA]) as prof_:
-        model.forward_device(ImageList(x, sizes), caps, pmap)
-        torch.cuda.synchronize()
-    rows = []
-    for e in prof_.key_averages():
-        t = getattr(e, "device_time_total", None) or getattr(e, "cuda_time_total", 0)
-        if t:
-            rows.append((t / 1e3, e.count, e.key))
-    rows.sort(reverse=True)
-    tot = sum(r[0] for r in rows)
-    print(f"kernel total {tot:.2f} ms")
-    for t, c, k in rows[:30]:
-        print(f"  {t:8.2f} ms {100*t/tot:5.1f}%  x{c:4d}  {k[:100]}")
-except Exception as e:  # profiler unavailable
-    print("torch.profiler failed:", repr(e))
+print("GEMM shapes (M,N,K,batch): count, ms, TFLOP/s")
+for shape, (c, ms, fl) in sorted(sh.items(), key=lambda kv: -kv[1][1])[:24]:
+    print(f"  {shape}: x{c} {ms:7.2f} ms {fl / ms / 1e9:7.1f}")
+json.dump({"total_ms": total, "stages": agg, "calls": {k: v for k, v in by.items()},
+           "gemm": {str(k): v for k, v in sh.items()}}, open(os.path.join(ROOT, "gpurun_out", "breakdown.json"), "w"), indent=1)
