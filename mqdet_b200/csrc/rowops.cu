@@ -45,6 +45,94 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const T* __restrict__ x,
   }
 }
 
+// Register-cached variants: the row is read ONCE.
+//   layernorm_reg_kernel<T, K>: D == 32 * K, element i of lane l is x[l + 32 i] (every load/store covers contiguous bytes)
+//   layernorm_h256_kernel     : fp16 rows of 256 (the fused visual stream): one 16-byte vector per lane
+// Same arithmetic as layernorm_kernel (two-pass mean / biased variance in fp32).
+template <typename T, int K>
+__global__ void __launch_bounds__(256) layernorm_reg_kernel(const T* __restrict__ x, long ldx, const float* __restrict__ gamma,
+                                                            const float* __restrict__ beta, float eps, long rows,
+                                                            __half* __restrict__ out16, float* __restrict__ out32, long ldo,
+                                                            long zero_row_period) {
+  const long row = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  constexpr int D = 32 * K;
+  const bool zero_row = zero_row_period > 0 && (row % zero_row_period) == zero_row_period - 1;
+  const T* xr = x + row * ldx;
+  float v[K];
+#pragma unroll
+  for (int i = 0; i < K; ++i) v[i] = zero_row ? 0.f : ld_as_float(xr + lane + 32 * i);
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < K; ++i) s += v[i];
+  const float mean = zero_row ? 0.f : warp_sum(s) / D;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < K; ++i) {
+    const float d = v[i] - mean;
+    q += d * d;
+  }
+  const float rstd = zero_row ? rsqrtf(eps) : rsqrtf(warp_sum(q) / D + eps);
+#pragma unroll
+  for (int i = 0; i < K; ++i) {
+    const int c = lane + 32 * i;
+    const float y = (v[i] - mean) * rstd * gamma[c] + beta[c];
+    if (out16) out16[row * ldo + c] = __float2half_rn(y);
+    if (out32) out32[row * ldo + c] = y;
+  }
+}
+
+__global__ void __launch_bounds__(256) layernorm_h256_kernel(const __half* __restrict__ x, long ldx,
+                                                             const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                             float eps, long rows, __half* __restrict__ out16,
+                                                             float* __restrict__ out32, long ldo, long zero_row_period) {
+  const long row = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const bool zero_row = zero_row_period > 0 && (row % zero_row_period) == zero_row_period - 1;
+  float v[8];
+  {
+    const uint4 u = zero_row ? make_uint4(0, 0, 0, 0) : *reinterpret_cast<const uint4*>(x + row * ldx + lane * 8);
+    const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 f = __half22float2(h[i]);
+      v[2 * i] = f.x;
+      v[2 * i + 1] = f.y;
+    }
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s += v[i];
+  const float mean = zero_row ? 0.f : warp_sum(s) * (1.f / 256.f);
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float d = v[i] - mean;
+    q += d * d;
+  }
+  const float rstd = zero_row ? rsqrtf(eps) : rsqrtf(warp_sum(q) * (1.f / 256.f) + eps);
+  const float4 g0 = *reinterpret_cast<const float4*>(gamma + lane * 8), g1 = *reinterpret_cast<const float4*>(gamma + lane * 8 + 4);
+  const float4 b0 = *reinterpret_cast<const float4*>(beta + lane * 8), b1 = *reinterpret_cast<const float4*>(beta + lane * 8 + 4);
+  const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+  const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+  float y[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) y[i] = (v[i] - mean) * rstd * gg[i] + bb[i];
+  if (out16) {
+    __half2 o[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) o[i] = __floats2half2_rn(y[2 * i], y[2 * i + 1]);
+    *reinterpret_cast<uint4*>(out16 + row * ldo + lane * 8) = *reinterpret_cast<uint4*>(o);
+  }
+  if (out32) {
+    float4* d = reinterpret_cast<float4*>(out32 + row * ldo + lane * 8);
+    d[0] = make_float4(y[0], y[1], y[2], y[3]);
+    d[1] = make_float4(y[4], y[5], y[6], y[7]);
+  }
+}
+
 // y = LN(a + b) (BertSelfOutput / BertOutput, rpn/modeling_bert.py:175-188,258-270), optional clamp of the sum and result.
 __global__ void __launch_bounds__(256) add_layernorm_kernel(const float* __restrict__ a, const float* __restrict__ b,
                                                             const float* __restrict__ gamma,
@@ -108,6 +196,59 @@ __global__ void __launch_bounds__(256) softmax_rows_kernel(const T* __restrict__
       o = expf(v - mx) * inv;
     }
     yr[i] = __float2half_rn(o);
+  }
+}
+
+// Hot case of the fusion tower (A [B*H*N, 256 tokens], in place): one warp owns RW consecutive rows per step and issues all
+// RW 16-byte loads before touching any of them (4x the bytes in flight of the generic kernel), exp via FFMA + MUFU.EX2.
+template <int RW>
+__global__ void __launch_bounds__(256) softmax_rows256_kernel(const __half* __restrict__ x, long ldx, __half* __restrict__ y,
+                                                              long ldy, long rows, float scale, const float* __restrict__ colmask,
+                                                              long rows_per_batch, float mask_value, float keep_add) {
+  const int lane = threadIdx.x & 31;
+  const long r0 = ((long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * RW;
+  if (r0 >= rows) return;
+  constexpr float L2E = 1.4426950408889634f;
+  uint4 u[RW];
+#pragma unroll
+  for (int j = 0; j < RW; ++j)
+    u[j] = (r0 + j < rows) ? *reinterpret_cast<const uint4*>(x + (r0 + j) * ldx + lane * 8) : make_uint4(0, 0, 0, 0);
+#pragma unroll
+  for (int j = 0; j < RW; ++j) {
+    const long row = r0 + j;
+    if (row >= rows) break;
+    float v[8];
+    const __half2* h = reinterpret_cast<const __half2*>(&u[j]);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 f = __half22float2(h[i]);
+      v[2 * i] = f.x * scale;
+      v[2 * i + 1] = f.y * scale;
+    }
+    if (colmask) {
+      const float* cm = colmask + (row / rows_per_batch) * 256 + lane * 8;
+      const float4 m0 = *reinterpret_cast<const float4*>(cm);
+      const float4 m1 = *reinterpret_cast<const float4*>(cm + 4);
+      const float mm[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] += (mm[i] == 0.f) ? mask_value : keep_add;
+    }
+    float mx = v[0];
+#pragma unroll
+    for (int i = 1; i < 8; ++i) mx = fmaxf(mx, v[i]);
+    mx = warp_max(mx);
+    const float ms = -mx * L2E;
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      v[i] = exp2f(fmaf(v[i], L2E, ms));
+      sum += v[i];
+    }
+    const float inv = 1.f / warp_sum(sum);
+    __half2 o[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) o[i] = __floats2half2_rn(v[2 * i] * inv, v[2 * i + 1] * inv);
+    *reinterpret_cast<uint4*>(y + row * ldy + lane * 8) = *reinterpret_cast<uint4*>(o);
   }
 }
 
@@ -225,10 +366,11 @@ __global__ void __launch_bounds__(256) softmax_rows_f16v_kernel(const __half* __
 //   2. colsoftmax_finish : merges the chunks                                                -> stat[z][2][T] (max, 1/sum)
 //   3. colsoftmax_write  : 64-row tiles through shared memory, 16-byte coalesced transposed stores
 // ---------------------------------------------------------------------------------------------------------------
-constexpr int CS_ROWS = 256;
+constexpr int CS_ROWS = 512;
 
-__global__ void __launch_bounds__(256) colsoftmax_stats_kernel(const __half* __restrict__ A, int N, int T,
-                                                               float* __restrict__ partial, int nchunks) {
+// generic fallback (T not a power of two): thread == column, serial online softmax over the chunk's rows
+__global__ void __launch_bounds__(256) colsoftmax_stats_generic_kernel(const __half* __restrict__ A, int N, int T,
+                                                                       float* __restrict__ partial, int nchunks) {
   const int chunk = blockIdx.x, z = blockIdx.y;
   const int r0 = chunk * CS_ROWS, r1 = min(N, r0 + CS_ROWS);
   const __half* a = A + (long)z * N * T;
@@ -246,6 +388,84 @@ __global__ void __launch_bounds__(256) colsoftmax_stats_kernel(const __half* __r
   }
 }
 
+// T in {8, 16, .., 256} (power of two): a thread keeps 8 columns (one 16-byte vector) and walks the chunk 8 rows at a time:
+// 8 independent 16-byte loads in flight, block maximum first, then ONE exp per element (+ 8 rescales per 64 elements);
+// the 256 / (T/8) row groups of the CTA are merged through shared memory.
+__global__ void __launch_bounds__(256) colsoftmax_stats_kernel(const __half* __restrict__ A, int N, int T,
+                                                               float* __restrict__ partial, int nchunks) {
+  __shared__ float sm[2048], ss[2048];  // [row group][column]: groups * T == 2048 for every T
+  constexpr float L2E = 1.4426950408889634f;
+  const int chunk = blockIdx.x, z = blockIdx.y;
+  const int vpr = T >> 3;                 // vectors per row
+  const int groups = 256 / vpr;           // row groups of the CTA
+  const int g = threadIdx.x / vpr, c = (threadIdx.x % vpr) * 8;
+  const int r0 = chunk * CS_ROWS, r1 = min(N, r0 + CS_ROWS);
+  const __half* a = A + (long)z * N * T + c;
+  float m[8], sacc[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    m[i] = -INFINITY;
+    sacc[i] = 0.f;
+  }
+  for (int rb = r0 + g; rb < r1; rb += groups * 8) {
+    uint4 u[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int r = rb + j * groups;
+      // rows beyond the chunk: repeat the first row of the block (valid) and mask it out of the sum below
+      u[j] = *reinterpret_cast<const uint4*>(a + (long)(r < r1 ? r : rb) * T);
+    }
+    float bm[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) bm[i] = m[i];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const __half2* h = reinterpret_cast<const __half2*>(&u[j]);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float2 f = __half22float2(h[i]);
+        bm[2 * i] = fmaxf(bm[2 * i], f.x);
+        bm[2 * i + 1] = fmaxf(bm[2 * i + 1], f.y);
+      }
+    }
+    float nm[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      sacc[i] *= exp2f((m[i] - bm[i]) * L2E);  // m = -inf on the first block: exp2(-inf) = 0, sacc stays 0
+      m[i] = bm[i];
+      nm[i] = -bm[i] * L2E;
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      if (rb + j * groups < r1) {
+        const __half2* h = reinterpret_cast<const __half2*>(&u[j]);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float2 f = __half22float2(h[i]);
+          sacc[2 * i] += exp2f(fmaf(f.x, L2E, nm[2 * i]));
+          sacc[2 * i + 1] += exp2f(fmaf(f.y, L2E, nm[2 * i + 1]));
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    sm[g * T + c + i] = m[i];
+    ss[g * T + c + i] = sacc[i];
+  }
+  __syncthreads();
+  for (int t = threadIdx.x; t < T; t += blockDim.x) {
+    float mm = -INFINITY;
+    for (int k = 0; k < groups; ++k) mm = fmaxf(mm, sm[k * T + t]);
+    float s = 0.f;
+    for (int k = 0; k < groups; ++k)
+      if (sm[k * T + t] > -INFINITY) s += ss[k * T + t] * exp2f((sm[k * T + t] - mm) * L2E);
+    float* o = partial + (((long)z * nchunks + chunk) * 2) * T;
+    o[t] = mm;
+    o[T + t] = s;
+  }
+}
+
 __global__ void colsoftmax_finish_kernel(const float* __restrict__ partial, int T, int nchunks, float* __restrict__ stat) {
   const int z = blockIdx.x;
   for (int t = threadIdx.x; t < T; t += blockDim.x) {
@@ -254,7 +474,7 @@ __global__ void colsoftmax_finish_kernel(const float* __restrict__ partial, int 
     float s = 0.f;
     for (int c = 0; c < nchunks; ++c) {
       const float* o = partial + (((long)z * nchunks + c) * 2) * T;
-      s += o[T + t] * expf(o[t] - m);
+      if (o[t] > -INFINITY) s += o[T + t] * expf(o[t] - m);
     }
     stat[((long)z * 2) * T + t] = m;
     stat[((long)z * 2 + 1) * T + t] = 1.f / s;
@@ -280,7 +500,7 @@ __global__ void __launch_bounds__(256) colsoftmax_write_kernel(const __half* __r
     const int c = (threadIdx.x % vec_per_row) * 8;
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-      mxr[k] = mx[c + k];
+      mxr[k] = -mx[c + k] * 1.4426950408889634f;  // exp(v - m) = exp2(v * log2e - m * log2e)
       ivr[k] = inv[c + k];
     }
   }
@@ -293,14 +513,15 @@ __global__ void __launch_bounds__(256) colsoftmax_write_kernel(const __half* __r
       if (!fixed_cols) {
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
-          mxr[k] = mx[c + k];
+          mxr[k] = -mx[c + k] * 1.4426950408889634f;
           ivr[k] = inv[c + k];
         }
       }
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         const float2 f = __half22float2(h[k]);
-        o[k] = __floats2half2_rn(__expf(f.x - mxr[2 * k]) * ivr[2 * k], __expf(f.y - mxr[2 * k + 1]) * ivr[2 * k + 1]);
+        o[k] = __floats2half2_rn(exp2f(fmaf(f.x, 1.4426950408889634f, mxr[2 * k])) * ivr[2 * k],
+                                 exp2f(fmaf(f.y, 1.4426950408889634f, mxr[2 * k + 1])) * ivr[2 * k + 1]);
       }
     } else {
 #pragma unroll
@@ -396,6 +617,41 @@ extern "C" int mqdet_layernorm(const void* x, int in_dtype, int64_t ldx, const f
   cudaStream_t st = (cudaStream_t)stream;
   const int wpb = 8;
   dim3 grid(cdiv(rows, wpb));
+  const bool al16 = ((uintptr_t)x % 16) == 0 && (ldx % 8) == 0 && (ldo % 8) == 0 && (!out16 || ((uintptr_t)out16 % 16) == 0) &&
+                    (!out32 || ((uintptr_t)out32 % 16) == 0) && ((uintptr_t)gamma % 16) == 0 && ((uintptr_t)beta % 16) == 0;
+  if (in_dtype == MQDET_F16 && D == 256 && al16) {
+    layernorm_h256_kernel<<<grid, wpb * 32, 0, st>>>((const __half*)x, ldx, gamma, beta, eps, rows, (__half*)out16, (float*)out32,
+                                                    ldo, zero_row_period);
+    return check_launch("layernorm_h256_kernel");
+  }
+#define MQ_LN_REG(TT, KK)                                                                                                   \
+  layernorm_reg_kernel<TT, KK><<<grid, wpb * 32, 0, st>>>((const TT*)x, ldx, gamma, beta, eps, rows, (__half*)out16,        \
+                                                          (float*)out32, ldo, zero_row_period)
+  if ((D % 32) == 0 && D / 32 <= 24) {
+    const int k = (int)(D / 32);
+    bool done = true;
+    if (in_dtype == MQDET_F32) {
+      switch (k) {
+        case 3: MQ_LN_REG(float, 3); break;
+        case 6: MQ_LN_REG(float, 6); break;
+        case 8: MQ_LN_REG(float, 8); break;
+        case 12: MQ_LN_REG(float, 12); break;
+        case 24: MQ_LN_REG(float, 24); break;
+        default: done = false;
+      }
+    } else {
+      switch (k) {
+        case 3: MQ_LN_REG(__half, 3); break;
+        case 6: MQ_LN_REG(__half, 6); break;
+        case 8: MQ_LN_REG(__half, 8); break;
+        case 12: MQ_LN_REG(__half, 12); break;
+        case 24: MQ_LN_REG(__half, 24); break;
+        default: done = false;
+      }
+    }
+    if (done) return check_launch("layernorm_reg_kernel");
+  }
+#undef MQ_LN_REG
   if (in_dtype == MQDET_F32)
     layernorm_kernel<float><<<grid, wpb * 32, 0, st>>>((const float*)x, ldx, gamma, beta, eps, rows, (int)D,
                                                       (__half*)out16, (float*)out32, ldo, zero_row_period);
@@ -427,7 +683,11 @@ extern "C" int mqdet_softmax_rows(const void* x, int in_dtype, int64_t ldx, void
   if (vec) {
     const __half* xh = (const __half*)x;
     __half* yh = (__half*)y;
-    if (n_pad <= 256)
+    if (n == 256 && n_pad == 256) {
+      constexpr int RW = 4;
+      softmax_rows256_kernel<RW><<<(unsigned)cdiv(rows, (long)wpb * RW), wpb * 32, 0, st>>>(xh, ldx, yh, ldy, rows, scale, colmask,
+                                                                                           rows_per_batch, mask_value, keep_add);
+    } else if (n_pad <= 256)
       softmax_rows_f16v_kernel<1><<<grid, wpb * 32, 0, st>>>(xh, ldx, yh, ldy, rows, (int)n, (int)n_pad, scale, colmask,
                                                             rows_per_batch, mask_value, keep_add);
     else if (n_pad <= 1024)
@@ -485,7 +745,10 @@ extern "C" int mqdet_colsoftmax_transposed(const void* A, int64_t Z, int64_t N, 
   const int nchunks = (int)((N + CS_ROWS - 1) / CS_ROWS);
   float* partial = workspace;
   float* stat = workspace + Z * nchunks * 2 * T;
-  colsoftmax_stats_kernel<<<dim3(nchunks, (unsigned)Z), 256, 0, st>>>((const __half*)A, (int)N, (int)T, partial, nchunks);
+  if ((T & (T - 1)) == 0 && ((uintptr_t)A % 16) == 0)
+    colsoftmax_stats_kernel<<<dim3(nchunks, (unsigned)Z), 256, 0, st>>>((const __half*)A, (int)N, (int)T, partial, nchunks);
+  else
+    colsoftmax_stats_generic_kernel<<<dim3(nchunks, (unsigned)Z), 256, 0, st>>>((const __half*)A, (int)N, (int)T, partial, nchunks);
   colsoftmax_finish_kernel<<<(unsigned)Z, 256, 0, st>>>(partial, (int)T, nchunks, stat);
   colsoftmax_write_kernel<<<dim3((unsigned)((Np + 63) / 64), (unsigned)Z), 256, 0, st>>>((const __half*)A, (int)N, (int)Np, (int)T,
                                                                                        stat, (__half*)P);
