@@ -40,6 +40,11 @@ __device__ __forceinline__ void ld8h(const __half* p, float (&f)[8]) {
     f[2 * i + 1] = x.y;
   }
 }
+__device__ __forceinline__ void ld8f(const float* p, float (&f)[8]) {  // 32-byte aligned
+  const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+  f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w;
+  f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+}
 __device__ __forceinline__ void st8h(__half* p, const float (&f)[8]) {
   __half2 h[4];
 #pragma unroll
@@ -262,6 +267,7 @@ __global__ void __launch_bounds__(C) gn_attn_kernel(const float* __restrict__ pa
 // Scale-aware fusion (vldyhead.py:219-238): mid[p] = mean_k attn_k * GN_k(y_k)[p]; branch 0 is bilinearly upsampled
 // (align_corners=True, F.upsample_bilinear :224) from the next-coarser grid.  One warp per pixel, 8 channels per lane.
 // ---------------------------------------------------------------------------------------------------------------
+constexpr int DC_PPW = 4;
 template <int C>
 __global__ void __launch_bounds__(256) dyconv_combine_kernel(const __half* __restrict__ y1, const __half* __restrict__ y2,
                                                              const __half* __restrict__ y0, const float* __restrict__ aff1,
@@ -269,72 +275,105 @@ __global__ void __launch_bounds__(256) dyconv_combine_kernel(const __half* __res
                                                              const float* __restrict__ at1, const float* __restrict__ at2,
                                                              const float* __restrict__ at0, LevelTable lt, int B,
                                                              __half* __restrict__ mid) {
-  const long gw = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  // one warp per run of DC_PPW consecutive pixels; the (attention x GroupNorm affine) rows of the run's (image, level) are
+  // folded into one scale/offset pair per branch and kept in registers across the run
+  const long gw0 = (((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5) * DC_PPW;
   const int lane = threadIdx.x & 31;
   const int L = lt.n;
   const int N = lt.off[L - 1] + lt.H[L - 1] * lt.W[L - 1];
   const int N1 = N - lt.H[0] * lt.W[0];
-  if (gw >= (long)B * N) return;
-  const int b = (int)(gw / N);
-  const int pn = (int)(gw % N);
-  int l = 0;
-  while (l + 1 < L && pn >= lt.off[l + 1]) ++l;
-  const int q = pn - lt.off[l];
-  const int H = lt.H[l], W = lt.W[l];
+  const long total = (long)B * N;
+  if (gw0 >= total) return;
   const int c0 = lane * 8;
-  float acc[8], v[8];
-  {  // branch 1 (same level)
-    const float a = at1[b * L + l];
-    const float* ga = aff1 + ((long)(b * L + l) * 2) * C + c0;
+  int cur = -1;
+  float s1[8], s2[8], s0[8], off[8];  // acc = s1*y1 + s2*y2 + s0*up(y0) + off, already divided by the branch count
+  bool has2 = false, has0 = false;
+#pragma unroll 1
+  for (int j = 0; j < DC_PPW; ++j) {
+    const long gw = gw0 + j;
+    if (gw >= total) break;
+    const int b = (int)(gw / N);
+    const int pn = (int)(gw % N);
+    int l = 0;
+    while (l + 1 < L && pn >= lt.off[l + 1]) ++l;
+    if (b * L + l != cur) {
+      cur = b * L + l;
+      has2 = l > 0;
+      has0 = l < L - 1;
+      const float inv = 1.f / (float)(1 + (has2 ? 1 : 0) + (has0 ? 1 : 0));
+      float g[8], o[8];
+      {
+        const float a = at1[b * L + l] * inv;
+        const float* ga = aff1 + ((long)(b * L + l) * 2) * C + c0;
+        ld8f(ga, g);
+        ld8f(ga + C, o);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          s1[i] = a * g[i];
+          off[i] = a * o[i];
+        }
+      }
+      if (has2) {  // branch 2: stride-2 conv of the finer level, already at this resolution; segment index l-1
+        const float a = at2[b * (L - 1) + l - 1] * inv;
+        const float* ga = aff2 + ((long)(b * (L - 1) + l - 1) * 2) * C + c0;
+        ld8f(ga, g);
+        ld8f(ga + C, o);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          s2[i] = a * g[i];
+          off[i] += a * o[i];
+        }
+      }
+      if (has0) {  // branch 0: conv on the coarser level (segment index l), upsampled to (H, W)
+        const float a = at0[b * (L - 1) + l] * inv;
+        const float* ga = aff0 + ((long)(b * (L - 1) + l) * 2) * C + c0;
+        ld8f(ga, g);
+        ld8f(ga + C, o);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          s0[i] = a * g[i];
+          off[i] += a * o[i];  // bilinear weights sum to 1: the affine offset passes through the upsampling
+        }
+      }
+    }
+    const int q = pn - lt.off[l];
+    const int H = lt.H[l], W = lt.W[l];
+    float acc[8], v[8];
     ld8h(y1 + ((long)b * N + pn) * C + c0, v);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) acc[i] = a * (ga[i] * v[i] + ga[C + i]);
+    for (int i = 0; i < 8; ++i) acc[i] = fmaf(s1[i], v[i], off[i]);
+    if (has2) {
+      ld8h(y2 + ((long)b * N1 + (pn - lt.off[1])) * C + c0, v);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[i] = fmaf(s2[i], v[i], acc[i]);
+    }
+    if (has0) {
+      const int Hs = lt.H[l + 1], Ws = lt.W[l + 1];
+      const int h = q / W, w = q % W;
+      // area_pixel_compute_source_index, align_corners=True (fp32 scale like ATen)
+      const float sh = (H > 1) ? (float)(Hs - 1) / (float)(H - 1) : 0.f;
+      const float sw = (W > 1) ? (float)(Ws - 1) / (float)(W - 1) : 0.f;
+      const float fh = sh * h, fw = sw * w;
+      const int h0 = (int)fh, w0 = (int)fw;
+      const int h1 = h0 + ((h0 < Hs - 1) ? 1 : 0), w1 = w0 + ((w0 < Ws - 1) ? 1 : 0);
+      const float lh = fh - h0, lw = fw - w0;
+      const __half* yb = y0 + ((long)b * N1 + (lt.off[l + 1] - lt.off[1])) * C + c0;
+      float t00[8], t01[8], t10[8], t11[8];
+      ld8h(yb + (long)(h0 * Ws + w0) * C, t00);
+      ld8h(yb + (long)(h0 * Ws + w1) * C, t01);
+      ld8h(yb + (long)(h1 * Ws + w0) * C, t10);
+      ld8h(yb + (long)(h1 * Ws + w1) * C, t11);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        float u = (1.f - lh) * (1.f - lw) * t00[i];
+        u += (1.f - lh) * lw * t01[i];
+        u += lh * (1.f - lw) * t10[i];
+        u += lh * lw * t11[i];
+        acc[i] = fmaf(s0[i], u, acc[i]);
+      }
+    }
+    st8h(mid + ((long)b * N + pn) * C + c0, acc);
   }
-  int nk = 1;
-  if (l > 0) {  // branch 2: stride-2 conv of the finer level, already at this resolution; segment index l-1
-    const float a = at2[b * (L - 1) + l - 1];
-    const float* ga = aff2 + ((long)(b * (L - 1) + l - 1) * 2) * C + c0;
-    ld8h(y2 + ((long)b * N1 + (pn - lt.off[1])) * C + c0, v);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) acc[i] += a * (ga[i] * v[i] + ga[C + i]);
-    ++nk;
-  }
-  if (l < L - 1) {  // branch 0: conv on the coarser level (segment index l), upsampled to (H, W)
-    const float a = at0[b * (L - 1) + l];
-    const float* ga = aff0 + ((long)(b * (L - 1) + l) * 2) * C + c0;
-    const int Hs = lt.H[l + 1], Ws = lt.W[l + 1];
-    const int h = q / W, w = q % W;
-    // area_pixel_compute_source_index, align_corners=True (fp32 scale like ATen)
-    const float sh = (H > 1) ? (float)(Hs - 1) / (float)(H - 1) : 0.f;
-    const float sw = (W > 1) ? (float)(Ws - 1) / (float)(W - 1) : 0.f;
-    const float fh = sh * h, fw = sw * w;
-    const int h0 = (int)fh, w0 = (int)fw;
-    const int h1 = h0 + ((h0 < Hs - 1) ? 1 : 0), w1 = w0 + ((w0 < Ws - 1) ? 1 : 0);
-    const float lh = fh - h0, lw = fw - w0;
-    const __half* yb = y0 + ((long)b * N1 + (lt.off[l + 1] - lt.off[1])) * C + c0;
-    float t[8], u[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) u[i] = 0.f;
-    ld8h(yb + (long)(h0 * Ws + w0) * C, t);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) u[i] += (1.f - lh) * (1.f - lw) * t[i];
-    ld8h(yb + (long)(h0 * Ws + w1) * C, t);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) u[i] += (1.f - lh) * lw * t[i];
-    ld8h(yb + (long)(h1 * Ws + w0) * C, t);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) u[i] += lh * (1.f - lw) * t[i];
-    ld8h(yb + (long)(h1 * Ws + w1) * C, t);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) u[i] += lh * lw * t[i];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) acc[i] += a * (ga[i] * u[i] + ga[C + i]);
-    ++nk;
-  }
-  const float inv = 1.f / nk;
-#pragma unroll
-  for (int i = 0; i < 8; ++i) acc[i] *= inv;
-  st8h(mid + ((long)b * N + pn) * C + c0, acc);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -376,23 +415,52 @@ __global__ void __launch_bounds__(C) dyrelu_coef_kernel(const float* __restrict_
   }
 }
 
+// One warp per run of DR_PPW consecutive pixels (8 channels per lane): the four coefficient rows of the run's (image,
+// level) stay in registers and are reloaded only when the run crosses a level boundary; all pixel vectors of the run are
+// loaded before the first one is used.
+constexpr int DR_PPW = 8;
 template <int C>
 __global__ void __launch_bounds__(256) dyrelu_apply_kernel(const __half* __restrict__ mid, const float* __restrict__ coef,
                                                            LevelTable lt, int B, __half* __restrict__ out) {
-  const long gw = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long gw0 = (((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5) * DR_PPW;
   const int lane = threadIdx.x & 31;
   const int L = lt.n;
   const int N = lt.off[L - 1] + lt.H[L - 1] * lt.W[L - 1];
-  if (gw >= (long)B * N) return;
-  const int b = (int)(gw / N), pn = (int)(gw % N);
-  int l = 0;
-  while (l + 1 < L && pn >= lt.off[l + 1]) ++l;
-  const float* cf = coef + ((long)(b * L + l) * 4) * C + lane * 8;
-  float v[8], o[8];
-  ld8h(mid + gw * C + lane * 8, v);
+  const long total = (long)B * N;
+  if (gw0 >= total) return;
+  uint4 u[DR_PPW];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) o[i] = fmaxf(v[i] * cf[i] + cf[C + i], v[i] * cf[2 * C + i] + cf[3 * C + i]);
-  st8h(out + gw * C + lane * 8, o);
+  for (int j = 0; j < DR_PPW; ++j)
+    u[j] = (gw0 + j < total) ? *reinterpret_cast<const uint4*>(mid + (gw0 + j) * C + lane * 8) : make_uint4(0, 0, 0, 0);
+  int cur = -1;
+  float a1[8], b1[8], a2[8], b2[8];
+#pragma unroll
+  for (int j = 0; j < DR_PPW; ++j) {
+    const long gw = gw0 + j;
+    if (gw >= total) break;
+    const int b = (int)(gw / N), pn = (int)(gw % N);
+    int l = 0;
+    while (l + 1 < L && pn >= lt.off[l + 1]) ++l;
+    if (b * L + l != cur) {
+      cur = b * L + l;
+      const float* cf = coef + ((long)cur * 4) * C + lane * 8;
+      ld8f(cf, a1);
+      ld8f(cf + C, b1);
+      ld8f(cf + 2 * C, a2);
+      ld8f(cf + 3 * C, b2);
+    }
+    const __half2* h = reinterpret_cast<const __half2*>(&u[j]);
+    float v[8], o[8];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 f = __half22float2(h[i]);
+      v[2 * i] = f.x;
+      v[2 * i + 1] = f.y;
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) o[i] = fmaxf(v[i] * a1[i] + b1[i], v[i] * a2[i] + b2[i]);
+    st8h(out + gw * C + lane * 8, o);
+  }
 }
 
 }  // namespace mqdet
@@ -447,7 +515,7 @@ extern "C" int mqdet_dyconv_combine(const void* y1, const void* y2, const void* 
   const int N = fill_levels(&lt, level_hw, nlev);
   MQ_REQUIRE(N > 0, "dyconv_combine: bad level table");
   MQ_REQUIRE(nlev == 1 || (y2 && y0 && aff2 && aff0 && at2 && at0), "dyconv_combine: missing cross-level inputs");
-  const long blocks = ((long)B * N * 32 + 255) / 256;
+  const long blocks = (((long)B * N + DC_PPW - 1) / DC_PPW * 32 + 255) / 256;
   dyconv_combine_kernel<256><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
       (const __half*)y1, (const __half*)y2, (const __half*)y0, aff1, aff2, aff0, at1, at2, at0, lt, (int)B, (__half*)mid);
   return check_launch("dyconv_combine_kernel");
@@ -470,7 +538,7 @@ extern "C" int mqdet_dyrelu_apply(const void* mid, const float* coef, const int3
   LevelTable lt;
   const int N = fill_levels(&lt, level_hw, nlev);
   MQ_REQUIRE(N > 0, "dyrelu_apply: bad level table");
-  const long blocks = ((long)B * N * 32 + 255) / 256;
+  const long blocks = (((long)B * N + DR_PPW - 1) / DR_PPW * 32 + 255) / 256;
   dyrelu_apply_kernel<256><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((const __half*)mid, coef, lt, (int)B,
                                                                               (__half*)out);
   return check_launch("dyrelu_apply_kernel");
