@@ -18,6 +18,7 @@ random-init weights of the real architecture (no checkpoints offline).
 """
 import argparse
 import json
+import math
 import os
 import subprocess
 import sys
@@ -122,9 +123,11 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--batch", type=int, default=8, help="images per GPU per step (BASELINE config 2: 8)")
     ap.add_argument("--impl", default="mqdet", choices=["mqdet", "reference"])
-    ap.add_argument("--bias0", type=float, default=-1.5,
-                    help="dot-product head bias0 of the synthetic weights: sets the fraction of (location, class) pairs above "
-                         "the 0.05 pre-NMS threshold; the candidate / detection counts it yields are reported in config")
+    ap.add_argument("--bias0", type=float, default=-math.log((1 - 0.01) / 0.01),
+                    help="dot-product head bias0 of the synthetic weights; default = the reference's own initialisation "
+                         "-log((1-p)/p), PRIOR_PROB p = 0.01 (vldyhead.py:688-719, defaults.py:442).  It sets the fraction of "
+                         "(location, class) pairs above the 0.05 pre-NMS threshold; the candidate / detection counts it "
+                         "yields are reported in config.postprocess (-1.5 is a denser stress point: every level hits top-k)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-baseline-steps", type=int, default=1)
     args = ap.parse_args()

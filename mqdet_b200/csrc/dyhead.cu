@@ -128,27 +128,25 @@ __global__ void __launch_bounds__(256) dcn_cols_kernel(const __half* __restrict_
       const int h_high = h_low + 1, w_high = w_low + 1;
       const float lh = h_im - h_low, lw = w_im - w_low, hh = 1.f - lh, hw = 1.f - lw;
       float v[8];
-      if (h_low >= 0 && w_low >= 0) {
+      // corners of weight zero are not fetched (plain 3x3 sampling: integer coordinates -> one corner per tap)
+      const float w1 = hh * hw, w2 = hh * lw, w3 = lh * hw, w4 = lh * lw;
+      if (h_low >= 0 && w_low >= 0 && w1 != 0.f) {
         ld8h(xb + (long)(h_low * Wi + w_low) * C, v);
-        const float w1 = hh * hw;
 #pragma unroll
         for (int i = 0; i < 8; ++i) acc[i] += w1 * v[i];
       }
-      if (h_low >= 0 && w_high <= Wi - 1) {
+      if (h_low >= 0 && w_high <= Wi - 1 && w2 != 0.f) {
         ld8h(xb + (long)(h_low * Wi + w_high) * C, v);
-        const float w2 = hh * lw;
 #pragma unroll
         for (int i = 0; i < 8; ++i) acc[i] += w2 * v[i];
       }
-      if (h_high <= Hi - 1 && w_low >= 0) {
+      if (h_high <= Hi - 1 && w_low >= 0 && w3 != 0.f) {
         ld8h(xb + (long)(h_high * Wi + w_low) * C, v);
-        const float w3 = lh * hw;
 #pragma unroll
         for (int i = 0; i < 8; ++i) acc[i] += w3 * v[i];
       }
-      if (h_high <= Hi - 1 && w_high <= Wi - 1) {
+      if (h_high <= Hi - 1 && w_high <= Wi - 1 && w4 != 0.f) {
         ld8h(xb + (long)(h_high * Wi + w_high) * C, v);
-        const float w4 = lh * lw;
 #pragma unroll
         for (int i = 0; i < 8; ++i) acc[i] += w4 * v[i];
       }

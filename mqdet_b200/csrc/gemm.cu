@@ -355,7 +355,7 @@ struct FastEpi {
   int res_f16;
 };
 
-template <int BN>
+template <int BN, bool PLAIN>  // PLAIN: fp16 output, no activation, no residual (the hot products) -> compact straight code
 __device__ __forceinline__ void epilogue_fast(const GemmP& p, const CUtensorMap* tma_c, uint32_t tmem_acc, uint8_t* stg,
                                               const FastEpi& fe, int m_tile, int n_tile, int z1, int z2, int ew, int lane,
                                               uint64_t* tmem_empty_bar, bool dbl, int half, int cw0, int cw, bool release) {
@@ -364,14 +364,14 @@ __device__ __forceinline__ void epilogue_fast(const GemmP& p, const CUtensorMap*
   const uint32_t t_row = tmem_acc + ((uint32_t)(ew * 32) << 16);
   const int c_begin = cw0 + half * (cw >> 1), c_end = c_begin + (cw >> 1);  // (cw / 2) % 32 == 0
   const float clampv = p.clamp;
-  const int act = p.act;
-  const bool f16 = p.c_dtype == MQDET_F16;
+  const int act = PLAIN ? MQDET_ACT_NONE : p.act;
+  const bool f16 = PLAIN || p.c_dtype == MQDET_F16;
   const int sw = r_local & 7;
   const uint32_t stg_row = smem_u32(stg) + r_local * 128;
   const bool vec = fe.s_vec != nullptr;
   const uint32_t s_addr = vec ? smem_u32(fe.s_vec) : 0u, t_addr = vec ? smem_u32(fe.t_vec) : 0u;
   const float s_u = fe.s_u, t_u = fe.t_u;
-  const bool has_res = fe.res != nullptr, res16 = fe.res_f16 != 0;
+  const bool has_res = !PLAIN && fe.res != nullptr, res16 = fe.res_f16 != 0;
   const long ncol0 = (long)n_tile * BN;
   uint32_t ra[16], rb[16];
   uint4 qa[4], qb[4];
@@ -640,7 +640,6 @@ __global__ void __launch_bounds__(384, 1) gemm_tcp_kernel(const __grid_constant_
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int num_kb = (int)((p.K + BK - 1) / BK);
-  const int nchunks = BRES ? (tiles_m + mc - 1) / mc : 1;
   // fp16 TMA-store tiles are 32 KB (BN=128): two of them fit the staging area -> stores of tile i overlap tile i+1
   const bool stg2 = p.use_tma_store && p.c_dtype == MQDET_F16 && 2 * BM * BN * 2 <= Cfg::STG_BYTES;
 
@@ -666,27 +665,44 @@ __global__ void __launch_bounds__(384, 1) gemm_tcp_kernel(const __grid_constant_
   tc_fence_after();
   const uint32_t tmem_base = *tmem_base_slot;
 
-  // item -> (z, first m tile, #m tiles, n tile)
-  auto decode = [&](int item, int& z, int& m0, int& mcount, int& n_tile) {
-    n_tile = item % tiles_n;
+  // Work distribution.
+  //  !BRES: item == tile (n fastest), dealt round-robin.
+  //   BRES: the tiles are laid out as [z][M chunk of `mc` tiles][n tile][m inside the chunk] and every CTA takes ONE
+  //         contiguous span of ceil(total / grid) of them (perfect balance; spans cut inside a run simply reload the
+  //         resident B tile).  A segment = consecutive m tiles with the same (z, n) = one residency of a B tile; CTAs with
+  //         neighbouring spans work on the same rows of A at the same time and share them through L2.
+  const int share = BRES ? (total_items + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+  const int w_begin = BRES ? (int)blockIdx.x * share : (int)blockIdx.x;
+  const int w_end = BRES ? min(total_items, w_begin + share) : total_items;
+  auto next_item = [&](int& cur, int& z, int& m0, int& mcount, int& n_tile) -> bool {
+    if (cur >= w_end) return false;
     if (BRES) {
-      const int c = (item / tiles_n) % nchunks;
-      z = item / (tiles_n * nchunks);
-      m0 = c * mc;
-      mcount = min(mc, tiles_m - m0);
+      const int per_z = tiles_m * tiles_n;
+      z = cur / per_z;
+      const int u = cur - z * per_z;
+      const int c = u / (mc * tiles_n);
+      const int v = u - c * mc * tiles_n;
+      const int sc = min(mc, tiles_m - c * mc);
+      n_tile = v / sc;
+      const int mi = v - n_tile * sc;
+      m0 = c * mc + mi;
+      mcount = min(sc - mi, w_end - cur);
+      cur += mcount;
     } else {
-      m0 = (item / tiles_n) % tiles_m;
-      z = item / (tiles_n * tiles_m);
+      n_tile = cur % tiles_n;
+      m0 = (cur / tiles_n) % tiles_m;
+      z = cur / (tiles_n * tiles_m);
       mcount = 1;
+      cur += gridDim.x;
     }
+    return true;
   };
 
   if (warp == 0) {
     if (lane == 0) {
       int it = 0, li = 0;  // ring position / local item counter
-      for (int item = blockIdx.x; item < total_items; item += gridDim.x, ++li) {
-        int z, m0, mcount, n_tile;
-        decode(item, z, m0, mcount, n_tile);
+      int z, m0, mcount, n_tile;
+      for (int cur = w_begin; next_item(cur, z, m0, mcount, n_tile); ++li) {
         const int z1 = z % p.nb1, z2 = z / p.nb1;
         const int az1 = p.a_bcast1 ? 0 : z1, az2 = p.a_bcast2 ? 0 : z2;
         const int bz1 = p.b_bcast1 ? 0 : z1, bz2 = p.b_bcast2 ? 0 : z2;
@@ -716,9 +732,8 @@ __global__ void __launch_bounds__(384, 1) gemm_tcp_kernel(const __grid_constant_
     if (lane == 0) {
       constexpr uint32_t idesc = umma_idesc_f16(BM, BN, 0);
       int it = 0, lt = 0, li = 0;
-      for (int item = blockIdx.x; item < total_items; item += gridDim.x, ++li) {
-        int z, m0, mcount, n_tile;
-        decode(item, z, m0, mcount, n_tile);
+      int z, m0, mcount, n_tile;
+      for (int cur = w_begin; next_item(cur, z, m0, mcount, n_tile); ++li) {
         if (BRES) {
           mbar_wait(b_full_bar, li & 1);
           tc_fence_after();
@@ -753,15 +768,15 @@ __global__ void __launch_bounds__(384, 1) gemm_tcp_kernel(const __grid_constant_
     const int ew = (warp - 4) & 3, half = (warp - 4) >> 2, tid_e = threadIdx.x - 128;
     // the fast epilogue covers everything without an activation when the output takes the TMA store (host: fast_epilogue_ok)
     const bool fast = p.fast_epi != 0;
+    const bool plain = fast && p.c_dtype == MQDET_F16 && p.act == MQDET_ACT_NONE && p.R == nullptr;
     const bool bcol = p.bias_mode == MQDET_VEC_PER_COL, brow = p.bias_mode == MQDET_VEC_PER_ROW;
     const bool gcol = p.gate_mode == MQDET_VEC_PER_COL, grow = p.gate_mode == MQDET_VEC_PER_ROW;
     const bool vec = bcol || gcol;
     const float bscale = p.scale_after_bias ? p.alpha : 1.f;  // alpha * (acc + b) == fma(alpha, acc, alpha * b)
     float g_u = 1.f;
     if (fast && p.gate_mode == MQDET_VEC_SCALAR) g_u = p.gate_tanh ? tanhf(p.gate[0]) : p.gate[0];
-    for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
-      int z, m0, mcount, n_tile;
-      decode(item, z, m0, mcount, n_tile);
+    int z, m0, mcount, n_tile;
+    for (int cur = w_begin; next_item(cur, z, m0, mcount, n_tile);) {
       const int z1 = z % p.nb1, z2 = z / p.nb1;
       for (int mt = 0; mt < mcount; ++mt, ++lt) {
         const int buf = lt & 1;
@@ -814,12 +829,22 @@ __global__ void __launch_bounds__(384, 1) gemm_tcp_kernel(const __grid_constant_
           if constexpr (BN == 256 && BRES) {
             // four 64-column windows through two alternating 16 KB staging tiles (fp16 TMA-store epilogue only)
 #pragma unroll 1
-            for (int w = 0; w < 4; ++w)
-              epilogue_fast<BN>(p, &tma_c, tmem_base + (uint32_t)(buf * BN), stg + (w & 1) * (BM * 128), fe, m0 + mt, n_tile, z1, z2,
-                                ew, lane, &tmem_empty_bar[buf], true, half, w * 64, 64, w == 3);
+            for (int w = 0; w < 4; ++w) {
+              if (plain)
+                epilogue_fast<BN, true>(p, &tma_c, tmem_base + (uint32_t)(buf * BN), stg + (w & 1) * (BM * 128), fe, m0 + mt, n_tile,
+                                        z1, z2, ew, lane, &tmem_empty_bar[buf], true, half, w * 64, 64, w == 3);
+              else
+                epilogue_fast<BN, false>(p, &tma_c, tmem_base + (uint32_t)(buf * BN), stg + (w & 1) * (BM * 128), fe, m0 + mt, n_tile,
+                                         z1, z2, ew, lane, &tmem_empty_bar[buf], true, half, w * 64, 64, w == 3);
+            }
           } else {
-            epilogue_fast<BN>(p, &tma_c, tmem_base + (uint32_t)(buf * BN), stg + (stg2 ? (lt & 1) * (BM * BN * 2) : 0), fe, m0 + mt,
-                              n_tile, z1, z2, ew, lane, &tmem_empty_bar[buf], stg2, half, 0, BN, true);
+            uint8_t* const st_tile = stg + (stg2 ? (lt & 1) * (BM * BN * 2) : 0);
+            if (plain)
+              epilogue_fast<BN, true>(p, &tma_c, tmem_base + (uint32_t)(buf * BN), st_tile, fe, m0 + mt, n_tile, z1, z2, ew, lane,
+                                      &tmem_empty_bar[buf], stg2, half, 0, BN, true);
+            else
+              epilogue_fast<BN, false>(p, &tma_c, tmem_base + (uint32_t)(buf * BN), st_tile, fe, m0 + mt, n_tile, z1, z2, ew, lane,
+                                       &tmem_empty_bar[buf], stg2, half, 0, BN, true);
           }
           continue;
         }
@@ -1072,21 +1097,13 @@ static int launch_tcp(const GemmP& p0, cudaStream_t st) {
   int mc = 1;
   long total = (long)tm * tn * Z;
   if (BRES) {
-    // Runs of `mc` M tiles per resident B tile.  Items are dealt round-robin to the CTAs, so the kernel lasts
-    // rounds x (mc + B-tile reload, ~1.5 tile times exposed): pick the run length that minimises it (long runs amortise
-    // the reload, short ones balance the last round); ties go to the longer run.
+    // every CTA takes one contiguous span of the [z][chunk][n][m] tile order (see the kernel): chunk length = the span
+    // length, so that a span normally is ONE (chunk, n) cell and the CTAs of a chunk share its rows of A through L2;
+    // with a single n tile the chunk is the whole M range (spans cut it anywhere)
     const long sms = num_sms();
-    double best = 1e30;
-    for (int c = 1; c <= tm; ++c) {
-      const long items = (long)cdiv(tm, c) * tn * Z;
-      const long rounds = (items + sms - 1) / sms;
-      const double cost = (double)rounds * (c + 1.5);
-      if (cost <= best) {
-        best = cost;
-        mc = c;
-      }
-    }
-    total = (long)cdiv(tm, mc) * tn * Z;
+    const long g = total < sms ? total : sms;
+    const long share = (total + g - 1) / g;
+    mc = tn == 1 ? tm : (int)(share < 1 ? 1 : (share > tm ? tm : share));
   }
   const int grid = (int)(total < num_sms() ? total : num_sms());
   if (const char* dbg = getenv("MQDET_GEMM_DEBUG")) {
