@@ -169,6 +169,12 @@ int mqdet_ml_nms(const float* boxes, const float* scores, const float* labels, c
 int mqdet_dcn_cols(const void* x, const float* om, int64_t om_ld, const int32_t* level_hw, int64_t nlev, int64_t B,
                    int64_t C, int branch, void* cols, void* stream);
 
+/* Plain 3x3 / pad 1 / stride 1 convolution with O <= 32 output channels over all levels at once, no column matrix: the
+ * offset/mask conv of DyConv (`self.offset`, vldyhead.py:150-153,207-210).  x [B,N,256] f16 (levels concatenated),
+ * w [O][9*256] f16 with k = tap*256 + c (tap = ky*3 + kx), bias [O] f32 -> out [B*N, ld] f32 (columns 0..O-1 written). */
+int mqdet_conv3x3_small(const void* x, const void* w, const float* bias, const int32_t* level_hw, int64_t nlev, int64_t B,
+                        int64_t C, int64_t O, float* out, int64_t ld, void* stream);
+
 /* Per-(image, segment) per-channel partial sums (sum, sum of squares, row-weighted sum) of fp16 y [B][rows][C].
  * seg_off_dev: DEVICE int32 [nseg+1] row offsets; partial: mqdet_chan_stats_floats(B, nseg, C) floats. */
 int64_t mqdet_chan_stats_floats(int64_t B, int64_t nseg, int64_t C);

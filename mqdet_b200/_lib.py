@@ -63,6 +63,8 @@ SIGNATURES = {
     "mqdet_ml_nms_workspace_bytes": (c_int64, [c_int64]),
     "mqdet_dcn_cols": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int64, c_int, c_void_p,
                                c_void_p]),
+    "mqdet_conv3x3_small": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64, c_void_p,
+                                    c_int64, c_void_p]),
     "mqdet_chan_stats_floats": (c_int64, [c_int64, c_int64, c_int64]),
     "mqdet_chan_stats": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64, c_void_p, c_void_p, c_void_p]),
     "mqdet_gn_attn": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64, c_int, c_void_p, c_void_p, c_float,

@@ -461,6 +461,148 @@ __global__ void __launch_bounds__(256) dyrelu_apply_kernel(const __half* __restr
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Plain 3x3 / pad 1 / stride 1 convolution with <= 32 output channels over every pyramid level at once, WITHOUT a column
+// matrix: the 27-channel offset/mask conv of DyConv (vldyhead.py:150-153, 207-210).  An implicit GEMM on mma.sync
+// (M = 16 pixels per warp, N = 32, K = 9 x 256): the A fragments are 16-byte loads straight from the NHWC-rows
+// pyramid (neighbouring pixels hit L1), the weights [32][2304] live in shared memory (ldmatrix, rows padded by 16 B).
+// Channel permutation: within each 32-channel group thread t4 of a quad owns channels 8*t4 .. 8*t4+7 (one 16-byte
+// load) and feeds them to TWO k-steps as logical k = {2t4, 2t4+1, 2t4+8, 2t4+9} <- channels 8t4 + 4s + {0,1,2,3}; the
+// weights are stored in that logical order, so sum over k is unchanged.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int CS_O = 32, CS_K = 9 * 256, CS_LD = CS_K + 8;  // smem row stride in halfs (+16 B: conflict-free ldmatrix)
+constexpr int CS_WARPS = 12, CS_PIX = 16 * CS_WARPS;
+
+__device__ __forceinline__ void mma16816(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0,
+                                         uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void ldmatrix_x4(uint32_t (&r)[4], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(addr));
+}
+
+__global__ void __launch_bounds__(CS_WARPS * 32, 1) conv3x3_small_kernel(const __half* __restrict__ x,
+                                                                         const __half* __restrict__ w, int O,
+                                                                         const float* __restrict__ bias, LevelTable lt, int B,
+                                                                         float* __restrict__ out, int ld) {
+  extern __shared__ __align__(16) uint8_t cs_smem[];
+  __half* ws = reinterpret_cast<__half*>(cs_smem);
+  constexpr int C = 256;
+  // weights -> shared, logical k order: ws[n][tap*256 + kp*32 + s*16 + lk] = w[n][tap*256 + kp*32 + phys(s, lk)]
+  for (int i = threadIdx.x; i < CS_O * CS_K; i += blockDim.x) {
+    const int n = i / CS_K, k = i % CS_K;
+    const int lk = k & 15, s = (k >> 4) & 1, base = k & ~31;
+    const int t = (lk & 7) >> 1, e = lk & 1, hi = lk >> 3;
+    const int phys = base + 8 * t + 4 * s + 2 * hi + e;
+    ws[n * CS_LD + k] = (n < O) ? w[(long)n * CS_K + phys] : __float2half_rn(0.f);
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, t4 = lane & 3;
+  const int L = lt.n;
+  const int N = lt.off[L - 1] + lt.H[L - 1] * lt.W[L - 1];
+  const long total = (long)B * N;
+  // ldmatrix row address of this lane: matrix m = lane / 8 -> (n tile m / 2 [+2 for the second instruction], k half m % 2)
+  const uint32_t ws_addr = smem_u32(ws) + (uint32_t)((((lane >> 4) * 8 + (lane & 7)) * CS_LD + ((lane >> 3) & 1) * 8) * 2);
+  float bv[4][2];
+#pragma unroll
+  for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const int n = nt * 8 + 2 * t4 + e;
+      bv[nt][e] = (n < O) ? bias[n] : 0.f;
+    }
+  for (long tile = blockIdx.x; tile * CS_PIX < total; tile += gridDim.x) {
+    const long p0 = tile * CS_PIX + warp * 16;
+    if (p0 >= total) continue;
+    // the two pixels (fragment rows g and g + 8) of this lane
+    int ph[2], pw[2], pH[2], pW[2];
+    const __half* pbase[2];
+    bool pok[2];
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      const long gp = p0 + g + 8 * r;
+      pok[r] = gp < total;
+      const long gq = pok[r] ? gp : 0;
+      const int b = (int)(gq / N), pn = (int)(gq % N);
+      int l = 0;
+      while (l + 1 < L && pn >= lt.off[l + 1]) ++l;
+      const int q = pn - lt.off[l];
+      pH[r] = lt.H[l];
+      pW[r] = lt.W[l];
+      ph[r] = q / pW[r];
+      pw[r] = q % pW[r];
+      pbase[r] = x + ((long)b * N + lt.off[l]) * C + 8 * t4;
+    }
+    float acc[4][4];
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) acc[nt][e] = 0.f;
+    // chunk = half a tap = 4 channel groups of 32 = 8 k-steps; two register sets ping-pong (loads of chunk c+1 in flight
+    // while chunk c feeds the tensor cores)
+    auto load_chunk = [&](int ch, uint4 (&buf)[8]) {
+      const int tap = ch >> 1, half = ch & 1;
+      const int dy = tap / 3 - 1, dx = tap % 3 - 1;
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        const int hs = ph[r] + dy, wsrc = pw[r] + dx;
+        const bool ok = pok[r] && hs >= 0 && hs < pH[r] && wsrc >= 0 && wsrc < pW[r];
+        const __half* src = pbase[r] + ((long)hs * pW[r] + wsrc) * C + half * 128;
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          buf[r * 4 + j] = ok ? __ldg(reinterpret_cast<const uint4*>(src + j * 32)) : make_uint4(0, 0, 0, 0);
+      }
+    };
+    auto compute_chunk = [&](int ch, const uint4 (&buf)[8]) {
+      const int kbase = (ch >> 1) * 256 + (ch & 1) * 128;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const uint4 ug = buf[j], uh = buf[4 + j];
+#pragma unroll
+        for (int s2 = 0; s2 < 2; ++s2) {
+          const uint32_t kaddr = ws_addr + (uint32_t)((kbase + j * 32 + s2 * 16) * 2);
+          uint32_t b01[4], b23[4];
+          ldmatrix_x4(b01, kaddr);                                 // n tiles 0, 1
+          ldmatrix_x4(b23, kaddr + (uint32_t)(16 * CS_LD * 2));    // n tiles 2, 3
+          const uint32_t a0 = s2 ? ug.z : ug.x, a1 = s2 ? uh.z : uh.x, a2 = s2 ? ug.w : ug.y, a3 = s2 ? uh.w : uh.y;
+          mma16816(acc[0], a0, a1, a2, a3, b01[0], b01[1]);
+          mma16816(acc[1], a0, a1, a2, a3, b01[2], b01[3]);
+          mma16816(acc[2], a0, a1, a2, a3, b23[0], b23[1]);
+          mma16816(acc[3], a0, a1, a2, a3, b23[2], b23[3]);
+        }
+      }
+    };
+    uint4 bufA[8], bufB[8];
+    load_chunk(0, bufA);
+#pragma unroll 1
+    for (int ch = 0; ch < 18; ch += 2) {
+      load_chunk(ch + 1, bufB);
+      compute_chunk(ch, bufA);
+      if (ch + 2 < 18) load_chunk(ch + 2, bufA);
+      compute_chunk(ch + 1, bufB);
+    }
+    // C fragment: (row g, cols 2t4, 2t4+1), (row g+8, same cols) per n tile
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      const long gp = p0 + g + 8 * r;
+      if (gp >= total) continue;
+      float* o = out + gp * ld;
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int n = nt * 8 + 2 * t4 + e;
+          if (n < O) o[n] = acc[nt][2 * r + e] + bv[nt][e];
+        }
+    }
+  }
+}
+
 }  // namespace mqdet
 
 using namespace mqdet;
@@ -540,4 +682,29 @@ extern "C" int mqdet_dyrelu_apply(const void* mid, const float* coef, const int3
   dyrelu_apply_kernel<256><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((const __half*)mid, coef, lt, (int)B,
                                                                               (__half*)out);
   return check_launch("dyrelu_apply_kernel");
+}
+
+extern "C" int mqdet_conv3x3_small(const void* x, const void* w, const float* bias, const int32_t* level_hw, int64_t nlev,
+                                   int64_t B, int64_t C, int64_t O, float* out, int64_t ld, void* stream) {
+  MQ_REQUIRE(x && w && bias && out && level_hw, "conv3x3_small: null pointer");
+  MQ_REQUIRE(C == 256 && O >= 1 && O <= CS_O && ld >= O, "conv3x3_small: C must be 256, O <= 32, ld >= O");
+  MQ_REQUIRE(((uintptr_t)x % 16) == 0, "conv3x3_small: x must be 16-byte aligned");
+  LevelTable lt;
+  const int N = fill_levels(&lt, level_hw, nlev);
+  MQ_REQUIRE(N > 0, "conv3x3_small: bad level table");
+  constexpr int SMEM = CS_O * CS_LD * 2;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(conv3x3_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+    MQ_REQUIRE(e == cudaSuccess, "conv3x3_small: cudaFuncSetAttribute(%d) failed: %s", SMEM, cudaGetErrorString(e));
+    attr_set = true;
+  }
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const long tiles = ((long)B * N + CS_PIX - 1) / CS_PIX;
+  const int grid = (int)(tiles < sms ? tiles : sms);
+  conv3x3_small_kernel<<<grid, CS_WARPS * 32, SMEM, (cudaStream_t)stream>>>((const __half*)x, (const __half*)w, (int)O, bias, lt,
+                                                                           (int)B, out, (int)ld);
+  return check_launch("conv3x3_small_kernel");
 }

@@ -484,6 +484,7 @@ __global__ void colsoftmax_finish_kernel(const float* __restrict__ partial, int 
 // tile: 64 rows (n) x T columns -> P[z][t][n0..n0+63];  T <= 256, T % 8 == 0.
 // Row-major staging (16-byte conflict-free stores), then lane == column t reads 16 consecutive rows (2-byte loads,
 // consecutive lanes -> consecutive half-words) and writes one full 32-byte sector of P[t][n0+r0 .. +15].
+template <bool T256>
 __global__ void __launch_bounds__(256) colsoftmax_write_kernel(const __half* __restrict__ A, int N, int Np, int T,
                                                                const float* __restrict__ stat, __half* __restrict__ P) {
   __shared__ __align__(16) __half tile[64][256 + 8];
@@ -491,43 +492,60 @@ __global__ void __launch_bounds__(256) colsoftmax_write_kernel(const __half* __r
   const __half* a = A + (long)z * N * T;
   const float* mx = stat + ((long)z * 2) * T;
   const float* inv = mx + T;
-  const int vec_per_row = T / 8;
-  // 256 % vec_per_row == 0 (T in {8,..,256}, power-of-two multiples of 8 used here) -> a thread keeps its 8 columns for
-  // the whole tile: their (max, 1/sum) are loaded once
-  const bool fixed_cols = (256 % vec_per_row) == 0;
-  float mxr[8], ivr[8];
-  if (fixed_cols) {
-    const int c = (threadIdx.x % vec_per_row) * 8;
+  constexpr float L2E = 1.4426950408889634f;
+  if (T256) {
+    // T == 256: a thread keeps its 8 columns for all 8 of its rows; the 8 row loads are issued before any is used
+    const int c = (threadIdx.x & 31) * 8, rb = threadIdx.x >> 5;
+    float mxr[8], ivr[8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-      mxr[k] = -mx[c + k] * 1.4426950408889634f;  // exp(v - m) = exp2(v * log2e - m * log2e)
+      mxr[k] = -mx[c + k] * L2E;  // exp(v - m) = exp2(v * log2e - m * log2e)
       ivr[k] = inv[c + k];
     }
-  }
-  for (int i = threadIdx.x; i < 64 * vec_per_row; i += 256) {
-    const int r = i / vec_per_row, c = (i % vec_per_row) * 8;
-    __half2 o[4];
-    if (n0 + r < N) {
-      const uint4 u = *reinterpret_cast<const uint4*>(a + (long)(n0 + r) * T + c);
-      const __half2* h = reinterpret_cast<const __half2*>(&u);
-      if (!fixed_cols) {
+    uint4 u[8];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          mxr[k] = -mx[c + k] * 1.4426950408889634f;
-          ivr[k] = inv[c + k];
-        }
-      }
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const float2 f = __half22float2(h[k]);
-        o[k] = __floats2half2_rn(exp2f(fmaf(f.x, 1.4426950408889634f, mxr[2 * k])) * ivr[2 * k],
-                                 exp2f(fmaf(f.y, 1.4426950408889634f, mxr[2 * k + 1])) * ivr[2 * k + 1]);
-      }
-    } else {
-#pragma unroll
-      for (int k = 0; k < 4; ++k) o[k] = __float2half2_rn(0.f);  // rows beyond N: zero padding of the K dimension of P.Vv
+    for (int j = 0; j < 8; ++j) {
+      const int r = rb + 8 * j;
+      u[j] = (n0 + r < N) ? *reinterpret_cast<const uint4*>(a + (long)(n0 + r) * 256 + c) : make_uint4(0, 0, 0, 0);
     }
-    *reinterpret_cast<uint4*>(&tile[r][c]) = *reinterpret_cast<uint4*>(o);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int r = rb + 8 * j;
+      __half2 o[4];
+      if (n0 + r < N) {
+        const __half2* h = reinterpret_cast<const __half2*>(&u[j]);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float2 f = __half22float2(h[k]);
+          o[k] = __floats2half2_rn(exp2f(fmaf(f.x, L2E, mxr[2 * k])) * ivr[2 * k],
+                                   exp2f(fmaf(f.y, L2E, mxr[2 * k + 1])) * ivr[2 * k + 1]);
+        }
+      } else {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) o[k] = __float2half2_rn(0.f);  // rows beyond N: zero padding of the K dimension of P.Vv
+      }
+      *reinterpret_cast<uint4*>(&tile[r][c]) = *reinterpret_cast<uint4*>(o);
+    }
+  } else {
+    const int vec_per_row = T / 8;
+    for (int i = threadIdx.x; i < 64 * vec_per_row; i += 256) {
+      const int r = i / vec_per_row, c = (i % vec_per_row) * 8;
+      __half2 o[4];
+      if (n0 + r < N) {
+        const uint4 u = *reinterpret_cast<const uint4*>(a + (long)(n0 + r) * T + c);
+        const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float2 f = __half22float2(h[k]);
+          o[k] = __floats2half2_rn(exp2f((f.x - mx[c + 2 * k]) * L2E) * inv[c + 2 * k],
+                                   exp2f((f.y - mx[c + 2 * k + 1]) * L2E) * inv[c + 2 * k + 1]);
+        }
+      } else {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) o[k] = __float2half2_rn(0.f);
+      }
+      *reinterpret_cast<uint4*>(&tile[r][c]) = *reinterpret_cast<uint4*>(o);
+    }
   }
   __syncthreads();
   __half* p = P + (long)z * T * Np;
@@ -750,7 +768,11 @@ extern "C" int mqdet_colsoftmax_transposed(const void* A, int64_t Z, int64_t N, 
   else
     colsoftmax_stats_generic_kernel<<<dim3(nchunks, (unsigned)Z), 256, 0, st>>>((const __half*)A, (int)N, (int)T, partial, nchunks);
   colsoftmax_finish_kernel<<<(unsigned)Z, 256, 0, st>>>(partial, (int)T, nchunks, stat);
-  colsoftmax_write_kernel<<<dim3((unsigned)((Np + 63) / 64), (unsigned)Z), 256, 0, st>>>((const __half*)A, (int)N, (int)Np, (int)T,
+  if (T == 256 && ((uintptr_t)A % 16) == 0)
+    colsoftmax_write_kernel<true><<<dim3((unsigned)((Np + 63) / 64), (unsigned)Z), 256, 0, st>>>((const __half*)A, (int)N, (int)Np,
+                                                                                             (int)T, stat, (__half*)P);
+  else
+    colsoftmax_write_kernel<false><<<dim3((unsigned)((Np + 63) / 64), (unsigned)Z), 256, 0, st>>>((const __half*)A, (int)N, (int)Np, (int)T,
                                                                                        stat, (__half*)P);
   return check_launch("colsoftmax_transposed");
 }

@@ -104,11 +104,8 @@ class DyConv(nn.Module):
         """x16 [B, N, 256] fp16 -> next pyramid [B, N, 256] fp16 (vldyhead.py:205-247)."""
         B, N, C = x16.shape
         L = levels.n
-        # offset/mask conv (plain 3x3) for every level in one product; pixel-major [B*N, 32] fp32
-        cols = ops.dcn_cols(x16, None, levels, 1)
-        om = torch.empty((B * N, 32), dtype=torch.float32, device=x16.device)
-        ops.gemm(cols, _conv_w16(self.offset.weight), out=om[:, :27], bias=f32(self.offset.bias))
-        om3 = om.view(B, N, 32)
+        # offset/mask conv (plain 3x3, 27 channels) for every level in one implicit-GEMM launch; pixel-major [B*N, 32] fp32
+        om3 = ops.conv3x3_small(x16, _conv_w16(self.offset.weight), f32(self.offset.bias), levels).view(B, N, 32)
         aw = f32(self.AttnConv[1].weight).view(-1)
         ab = f32(self.AttnConv[1].bias)
 

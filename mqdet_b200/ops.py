@@ -389,6 +389,20 @@ def dcn_cols(x16, om, levels, branch):
     return cols
 
 
+def conv3x3_small(x16, w16_, bias, levels, ld=32):
+    """Plain 3x3 / pad 1 conv with <= 32 output channels over all levels, no column matrix (the DyConv offset/mask conv):
+    x16 [B,N,256] fp16, w16_ [O, 2304] fp16 (k = tap*256 + c), bias [O] fp32 -> [B*N, ld] fp32 (columns >= O untouched)."""
+    global launch_count
+    _need_cuda(x16, w16_, bias)
+    B, N, C = x16.shape
+    O = w16_.shape[0]
+    out = torch.empty((B * N, ld), dtype=torch.float32, device=x16.device)
+    check(load().mqdet_conv3x3_small(_ptr(x16), _ptr(w16_), _ptr(bias), levels.hw_ptr, levels.n, B, C, O, _ptr(out), ld,
+                                     _stream()), "conv3x3_small")
+    launch_count += 1
+    return out
+
+
 def chan_stats(y16, seg, B, rows_per_img, row_weights=None):
     global launch_count
     nseg = seg.numel() - 1

@@ -48,6 +48,28 @@ def test_dcn_cols_plain_equals_unfold(dev):
         assert torch.equal(cols[:, lv.off[l]:lv.off[l + 1]], u)
 
 
+def test_conv3x3_small_equals_conv2d(dev):
+    """The column-matrix-free 27-channel offset conv (implicit GEMM on mma.sync) == F.conv2d on the fp16-rounded operands;
+    level sizes chosen so that warps straddle level and image boundaries and the last pixel tile is ragged."""
+    from mqdet_b200 import ops
+    g = torch.Generator().manual_seed(4)
+    sizes = [(13, 17), (7, 9), (4, 5), (2, 3), (1, 1)]
+    B, O = 3, 27
+    feats = [torch.randn(B, 256, h, w, generator=g) for h, w in sizes]
+    wt = torch.randn(O, 256, 3, 3, generator=g) * 0.05
+    bias = torch.randn(O, generator=g)
+    lv = ops.Levels(sizes, dev)
+    x16 = torch.cat([f.flatten(2).transpose(1, 2) for f in feats], 1).half().to(dev).contiguous()
+    w16 = wt.permute(0, 2, 3, 1).reshape(O, -1).half().to(dev).contiguous()   # k = tap*C + c
+    out = ops.conv3x3_small(x16, w16, bias.to(dev), lv).view(B, lv.N, 32)[..., :O].cpu()
+    for l, f in enumerate(feats):
+        ref = torch.nn.functional.conv2d(f.half().float(), wt.half().float(), bias, padding=1)   # [B,O,h,w]
+        ref = ref.flatten(2).transpose(1, 2)
+        got = out[:, lv.off[l]:lv.off[l + 1]]
+        err = (got - ref).abs().max().item()
+        assert err <= 2e-4 * ref.abs().max().item() + 1e-5, (l, err)     # fp32 accumulation of fp16-exact products
+
+
 def test_dyconv(dev):
     from mqdet_b200 import ops
     from mqdet_b200.modeling.rpn.vldyhead import Conv3x3Norm, DyConv
