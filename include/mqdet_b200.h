@@ -127,6 +127,28 @@ int64_t mqdet_colsoftmax_workspace_floats(int64_t Z, int64_t N, int64_t T);
 int mqdet_colsoftmax_transposed(const void* A, int64_t Z, int64_t N, int64_t T, void* P, int64_t Np, float* workspace,
                                 void* stream);
 
+/* Column statistics only: workspace (mqdet_colsoftmax_workspace_floats(Z, N, T) floats) receives, at float offset
+ * Z * ceil(N/512) * 2 * T, stat[z][2][T] = (column max, 1 / column sum of exp) of A [Z][N][T] f16. */
+int mqdet_colsoftmax_stats(const void* A, int64_t Z, int64_t N, int64_t T, float* workspace, void* stream);
+
+/* T == 256: mqdet_colsoftmax_stats and the masked row softmax of the image -> text side in ONE pass over A, in place:
+ * statistics of the unmasked scores as above; then A[z][n][:] <- softmax_t(A[z][n][t] + (colmask[z / z_per_mask][t] == 0 ?
+ * mask_value : keep_add)) (fuse_helper.py:277-287).  colmask may be NULL (no mask). */
+int mqdet_colstats_rowsoftmax(void* A, int64_t Z, int64_t N, int64_t T, const float* colmask, int64_t z_per_mask,
+                              float mask_value, float keep_add, float* workspace, void* stream);
+
+/* Text -> image side of BiMultiHeadAttention (maskrcnn_benchmark/utils/fuse_helper.py:257-275,289-291) fused into one
+ * tcgen05 kernel per (image, head, 128 text tokens): out[z][t][:] = sum_n softmax_n(clamp(k_t . q_n))[n] * Vv[n][:], without
+ * materialising the transposed probabilities: S^T = K Q^T (tcgen05, 64 image tokens per step) -> exp(fp16-rounded score
+ * - column max) -> fp16 P tile in shared memory -> O += P Vv (tcgen05) -> O / column sum.  stat[z][2][T] as produced by
+ * mqdet_colsoftmax_stats from the SAME scores (q already carries the 1/sqrt(d) scale).  z = z2 * nb1 + z1.
+ *   k [z][T][d], q [z][N][d], vvT [z][d][Np] f16 (Np >= N, zero padded), out [z][T][d] f16; *_ld = row stride, *_b1 / *_b2 =
+ *   batch strides in elements (multiples of 8); d == 256, T <= 256. */
+int mqdet_biattn_text(const void* k, int64_t k_ld, int64_t k_b1, int64_t k_b2, const void* q, int64_t q_ld, int64_t q_b1,
+                      int64_t q_b2, const void* vvT, int64_t v_ld, int64_t v_b1, int64_t v_b2, const float* stat, float clamp,
+                      void* out, int64_t o_ld, int64_t o_b1, int64_t o_b2, int64_t nb1, int64_t nb2, int64_t T, int64_t N,
+                      int64_t Np, int64_t d, void* stream);
+
 /* Text side of the dot-product token head (vldyhead.py:810,818): e = x / max(||x||, eps) written as fp16 and/or
  * fp32, dot[r] = e[r,:] . w + b0[0] (w, b0, dot optional). */
 int mqdet_l2norm_rowdot(const float* x, int64_t rows, int64_t D, float eps, const float* w, const float* b0, void* e16,

@@ -54,6 +54,12 @@ SIGNATURES = {
                                    c_void_p, c_int64, c_float, c_float, c_void_p]),
     "mqdet_colsoftmax_workspace_floats": (c_int64, [c_int64, c_int64, c_int64]),
     "mqdet_colsoftmax_transposed": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_int64, c_void_p, c_void_p]),
+    "mqdet_colsoftmax_stats": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_void_p]),
+    "mqdet_colstats_rowsoftmax": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_int64, c_float, c_float, c_void_p,
+                                          c_void_p]),
+    "mqdet_biattn_text": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_int64, c_int64, c_int64, c_void_p, c_int64,
+                                  c_int64, c_int64, c_void_p, c_float, c_void_p, c_int64, c_int64, c_int64, c_int64, c_int64,
+                                  c_int64, c_int64, c_int64, c_int64, c_void_p]),
     "mqdet_l2norm_rowdot": (c_int, [c_void_p, c_int64, c_int64, c_float, c_void_p, c_void_p, c_void_p, c_void_p,
                                     c_void_p, c_void_p]),
     "mqdet_cast_f32_f16": (c_int, [c_void_p, c_void_p, c_int64, c_void_p]),

@@ -466,6 +466,117 @@ __global__ void __launch_bounds__(256) colsoftmax_stats_kernel(const __half* __r
   }
 }
 
+// Fusion-tower special (T == 256): ONE pass over A [Z][N][256] that (a) accumulates the per-column (max, sum-exp) partials
+// exactly like colsoftmax_stats_kernel and (b) replaces every row by its masked softmax over the 256 tokens (the
+// image -> text probabilities, fuse_helper.py:277-287) in place.  With 32 vectors per row a warp owns whole rows, so the
+// row reductions are warp shuffles; every element is read once by the thread that overwrites it.
+__global__ void __launch_bounds__(256) colstats_rowsoftmax256_kernel(__half* __restrict__ A, int N, float* __restrict__ partial,
+                                                                     int nchunks, const float* __restrict__ colmask,
+                                                                     int z_per_mask, float mask_value, float keep_add) {
+  constexpr int T = 256;
+  constexpr float L2E = 1.4426950408889634f;
+  __shared__ float sm[2048], ss[2048];
+  const int chunk = blockIdx.x, z = blockIdx.y;
+  const int g = threadIdx.x >> 5, lane = threadIdx.x & 31, c = lane * 8;
+  const int r0 = chunk * CS_ROWS, r1 = min(N, r0 + CS_ROWS);
+  __half* a = A + (long)z * N * T + c;
+  float madd[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) madd[i] = 0.f;
+  if (colmask) {
+    const float* cm = colmask + (long)(z / z_per_mask) * T + c;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) madd[i] = (cm[i] == 0.f) ? mask_value : keep_add;
+  }
+  float m[8], sacc[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    m[i] = -INFINITY;
+    sacc[i] = 0.f;
+  }
+  for (int rb = r0 + g; rb < r1; rb += 64) {
+    uint4 u[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int r = rb + j * 8;
+      u[j] = *reinterpret_cast<const uint4*>(a + (long)(r < r1 ? r : rb) * T);
+    }
+    // ---- column statistics (unmasked scores) ----
+    float bm[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) bm[i] = m[i];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const __half2* h = reinterpret_cast<const __half2*>(&u[j]);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float2 f = __half22float2(h[i]);
+        bm[2 * i] = fmaxf(bm[2 * i], f.x);
+        bm[2 * i + 1] = fmaxf(bm[2 * i + 1], f.y);
+      }
+    }
+    float nm[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      sacc[i] *= exp2f((m[i] - bm[i]) * L2E);
+      m[i] = bm[i];
+      nm[i] = -bm[i] * L2E;
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int r = rb + j * 8;
+      if (r >= r1) continue;  // warp-uniform
+      const __half2* h = reinterpret_cast<const __half2*>(&u[j]);
+      float v[8];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float2 f = __half22float2(h[i]);
+        v[2 * i] = f.x;
+        v[2 * i + 1] = f.y;
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) sacc[i] += exp2f(fmaf(v[i], L2E, nm[i]));
+      // ---- masked row softmax, in place ----
+      float mx = -INFINITY;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        v[i] += madd[i];
+        mx = fmaxf(mx, v[i]);
+      }
+      mx = warp_max(mx);
+      const float ms = -mx * L2E;
+      float sum = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        v[i] = exp2f(fmaf(v[i], L2E, ms));
+        sum += v[i];
+      }
+      const float inv = 1.f / warp_sum(sum);
+      __half2 o[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) o[i] = __floats2half2_rn(v[2 * i] * inv, v[2 * i + 1] * inv);
+      *reinterpret_cast<uint4*>(a + (long)r * T) = *reinterpret_cast<uint4*>(o);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    sm[g * T + c + i] = m[i];
+    ss[g * T + c + i] = sacc[i];
+  }
+  __syncthreads();
+  {
+    const int t = threadIdx.x;
+    float mm = -INFINITY;
+    for (int k = 0; k < 8; ++k) mm = fmaxf(mm, sm[k * T + t]);
+    float s = 0.f;
+    for (int k = 0; k < 8; ++k)
+      if (sm[k * T + t] > -INFINITY) s += ss[k * T + t] * exp2f((sm[k * T + t] - mm) * L2E);
+    float* o = partial + (((long)z * nchunks + chunk) * 2) * T;
+    o[t] = mm;
+    o[T + t] = s;
+  }
+}
+
 __global__ void colsoftmax_finish_kernel(const float* __restrict__ partial, int T, int nchunks, float* __restrict__ stat) {
   const int z = blockIdx.x;
   for (int t = threadIdx.x; t < T; t += blockDim.x) {
@@ -753,6 +864,36 @@ extern "C" int mqdet_cast_f16_f32(const void* x, float* y, int64_t n, void* stre
 extern "C" int64_t mqdet_colsoftmax_workspace_floats(int64_t Z, int64_t N, int64_t T) {
   const int64_t nchunks = (N + CS_ROWS - 1) / CS_ROWS;
   return Z * nchunks * 2 * T + Z * 2 * T;
+}
+
+extern "C" int mqdet_colsoftmax_stats(const void* A, int64_t Z, int64_t N, int64_t T, float* workspace, void* stream) {
+  MQ_REQUIRE(A && workspace && Z > 0 && N > 0, "colsoftmax_stats: bad args");
+  MQ_REQUIRE(T > 0 && T <= 256 && (T % 8) == 0, "colsoftmax_stats: need T<=256, T%%8==0");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int nchunks = (int)((N + CS_ROWS - 1) / CS_ROWS);
+  float* partial = workspace;
+  float* stat = workspace + Z * nchunks * 2 * T;
+  if ((T & (T - 1)) == 0 && ((uintptr_t)A % 16) == 0)
+    colsoftmax_stats_kernel<<<dim3(nchunks, (unsigned)Z), 256, 0, st>>>((const __half*)A, (int)N, (int)T, partial, nchunks);
+  else
+    colsoftmax_stats_generic_kernel<<<dim3(nchunks, (unsigned)Z), 256, 0, st>>>((const __half*)A, (int)N, (int)T, partial, nchunks);
+  colsoftmax_finish_kernel<<<(unsigned)Z, 256, 0, st>>>(partial, (int)T, nchunks, stat);
+  return check_launch("colsoftmax_stats");
+}
+
+extern "C" int mqdet_colstats_rowsoftmax(void* A, int64_t Z, int64_t N, int64_t T, const float* colmask, int64_t z_per_mask,
+                                         float mask_value, float keep_add, float* workspace, void* stream) {
+  MQ_REQUIRE(A && workspace && Z > 0 && N > 0, "colstats_rowsoftmax: bad args");
+  MQ_REQUIRE(T == 256, "colstats_rowsoftmax: T must be 256 (MODEL.LANGUAGE_BACKBONE.MAX_QUERY_LEN), got %ld", (long)T);
+  MQ_REQUIRE(((uintptr_t)A % 16) == 0 && (!colmask || z_per_mask >= 1), "colstats_rowsoftmax: A must be 16-byte aligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int nchunks = (int)((N + CS_ROWS - 1) / CS_ROWS);
+  float* partial = workspace;
+  float* stat = workspace + Z * nchunks * 2 * T;
+  colstats_rowsoftmax256_kernel<<<dim3(nchunks, (unsigned)Z), 256, 0, st>>>((__half*)A, (int)N, partial, nchunks, colmask,
+                                                                           (int)(colmask ? z_per_mask : 1), mask_value, keep_add);
+  colsoftmax_finish_kernel<<<(unsigned)Z, 256, 0, st>>>(partial, (int)T, nchunks, stat);
+  return check_launch("colstats_rowsoftmax");
 }
 
 extern "C" int mqdet_colsoftmax_transposed(const void* A, int64_t Z, int64_t N, int64_t T, void* P, int64_t Np, float* workspace,

@@ -56,6 +56,7 @@ class BiMultiHeadAttention(nn.Module):
         self.out_v_proj = nn.Linear(embed_dim, v_dim)
         self.out_l_proj = nn.Linear(embed_dim, l_dim)
         fc = cfg.MODEL.DYHEAD.FUSE_CONFIG
+        self.fused_text_side = True  # False: column-softmax + GEMM path (kept for A/B checks, tests/test_fusion_gpu.py)
         self.stable_softmax_2d = fc.STABLE_SOFTMAX_2D
         self.clamp_min_for_underflow = fc.CLAMP_MIN_FOR_UNDERFLOW
         self.clamp_max_for_overflow = fc.CLAMP_MAX_FOR_OVERFLOW
@@ -91,16 +92,30 @@ class BiMultiHeadAttention(nn.Module):
         # scores A = clamp(Q_h K_h^T)  [B,H,N,T]  (ONE product serves both directions)
         A = torch.empty((B, H, N, T), dtype=torch.float16, device=dev)
         ops.gemm(qh, kh, out=A, clamp=clamp)
-        # text -> image direction first (A is normalised in place afterwards): softmax over all N locations, no mask,
-        # written transposed [B,H,T,Np] so that P_l . Vv is again a K-major x K-major product
-        Pl = ops.colsoftmax_transposed(A, Np)
+        # text -> image direction first (A is normalised in place afterwards): softmax over all N locations, no mask.
         ol = torch.empty((B, T, H, d), dtype=torch.float16, device=dev)
-        # image -> text direction: softmax over the T tokens with the padding mask
+        fused = self.fused_text_side and d == 256
         cm = mask_l.float().contiguous() if mask_l is not None else None
-        Pv = ops.softmax_rows(A, colmask=cm, rows_per_batch=H * N, mask_value=-9e15, keep_add=1.0, out=A)
+        if fused and T == 256:
+            # ONE pass over A: column statistics of the scores + the masked row softmax (image -> text probabilities) in
+            # place; then ONE fused kernel for the text -> image side: S^T = K Q^T recomputed on the tensor cores, exp,
+            # P.Vv -- the transposed probabilities [B,H,T,N] are never written
+            stat = ops.colstats_rowsoftmax(A, cm, H, -9e15, 1.0)
+            Pv = A
+            ops.biattn_text(kh, qh, vvT.view(B, H, d, Np), stat, clamp, ol.permute(0, 2, 1, 3))
+        else:
+            if fused:
+                stat = ops.colsoftmax_stats(A)
+                ops.biattn_text(kh, qh, vvT.view(B, H, d, Np), stat, clamp, ol.permute(0, 2, 1, 3))
+            else:
+                # unfused: probabilities written transposed [B,H,T,Np] so that P_l . Vv is a K-major x K-major product
+                Pl = ops.colsoftmax_transposed(A, Np)
+            # image -> text direction: softmax over the T tokens with the padding mask
+            Pv = ops.softmax_rows(A, colmask=cm, rows_per_batch=H * N, mask_value=-9e15, keep_add=1.0, out=A)
         ov = torch.empty((B, N, H, d), dtype=torch.float16, device=dev)
         ops.gemm(Pv, vlT.view(B, H, d, T), out=ov.permute(0, 2, 1, 3))
-        ops.gemm(Pl, vvT.view(B, H, d, Np), out=ol.permute(0, 2, 1, 3))
+        if not fused:
+            ops.gemm(Pl, vvT.view(B, H, d, Np), out=ol.permute(0, 2, 1, 3))
 
         ve = v_epilogue or {}
         le = l_epilogue or {}

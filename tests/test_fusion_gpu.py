@@ -34,6 +34,32 @@ def test_bi_attention_vs_oracle_and_golden(dev):
         assert err <= FP16_TOL * fx[key + "_absmax"] + FP16_TOL, (key, err)
 
 
+def test_bi_attention_fused_equals_unfused(dev):
+    """The fused text->image kernel (tcgen05 S^T / exp / P.V with column statistics) and the one-pass statistics +
+    row-softmax kernel against the unfused path (transposed column softmax + GEMM, softmax_rows): same fp16 scores,
+    so the outputs agree far inside the oracle tolerance.  Ragged N (not a multiple of 64) and a T < 256 fallback."""
+    from mqdet_b200.config import mq_glip_t_cfg
+    from mqdet_b200.utils.fuse_helper import BiAttentionBlockForCheckpoint
+    from oracle import synth
+    gen = synth.Gen(31)
+    sd = synth.bi_attention_sd(gen)
+    blk = BiAttentionBlockForCheckpoint(v_dim=256, l_dim=768, embed_dim=2048, num_heads=8, hidden_dim=3072, dropout=0.1,
+                                        drop_path=0.0, init_values=1.0 / 6, cfg=mq_glip_t_cfg())
+    blk = load_sd(blk, sd).to(dev).eval()
+    for (B, N, T) in [(2, 1000, 256), (1, 333, 256), (2, 520, 64)]:
+        v16 = gen.randn(B, N, 256).half().to(dev)
+        l32 = gen.randn(B, T, 768).to(dev)
+        mask = torch.ones(B, T, dtype=torch.long)
+        mask[0, T // 3:] = 0
+        mask = mask.to(dev)
+        blk.attn.fused_text_side = True
+        v1, l1 = blk.forward_flat(v16, l32, mask)
+        blk.attn.fused_text_side = False
+        v0, l0 = blk.forward_flat(v16, l32, mask)
+        assert_close(v1, v0, 1e-3, f"fused vs unfused visual stream {B, N, T}")
+        assert_close(l1, l0, 1e-3, f"fused vs unfused language stream {B, N, T}")
+
+
 def test_dcn_cols_plain_equals_unfold(dev):
     """om == NULL: the sampling stage is a plain 3x3/pad-1 im2col with k = tap*C + c."""
     from mqdet_b200 import ops
