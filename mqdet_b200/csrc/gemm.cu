@@ -879,25 +879,27 @@ __global__ void __launch_bounds__(384, 1) gemm_tcp_kernel(const __grid_constant_
 // =====================================================================================================================
 // Fused text -> image side of the bi-directional attention (BiMultiHeadAttention, fuse_helper.py:257-275, 289-291):
 //     out[t, :] = sum_n softmax_n(clamp(k_t . q_n)) * Vv[n, :]        per (image, head), t = text token, n = image token
-// One CTA per (z, 128 text tokens).  The transposed probabilities [T, N] never reach HBM:
-//     S^T tile = K_tile (128 x 256, resident) . Q_i^T (64 image tokens)         tcgen05, accumulator in TMEM (2 buffers)
-//     P_i      = exp(fp16(clamp(S^T)) - colmax_t)  -> fp16, 128B-swizzled A-operand tile in shared memory   (4 warps)
-//     O       += P_i . Vv_i                                                       tcgen05, 128 x 256 accumulator in TMEM
-//     out      = O / colsum_t  -> fp16 -> TMA store
-// colmax / colsum come from mqdet_colsoftmax_stats over the SAME fp16 scores the image -> text side uses, so no online
-// rescaling is needed and both directions see identical scores.  Roles: warp 0 TMA producer, warp 1 MMA issuer (S of
-// tile i+1 is issued before P.V of tile i, so the tensor pipe works while the exponentials run), warp 2 TMEM allocator,
-// warps 4-19 exponentials + epilogue (thread == text token == TMEM lane, four warps per lane quarter).
+// One CTA per (z, 128 text tokens).  The transposed probabilities [T, N] never reach HBM.  Per step of 256 image tokens:
+//     S^T   = K_tile (128 x 256, resident) . Q_step^T      16 tcgen05 MMAs 128x256x16, Q streamed as four [256 x 64] k-blocks
+//     P_j   = exp(fp16(clamp(S^T[:, 64j..])) - colmax_t)   -> fp16, 128B-swizzled A-operand tile in shared memory (j = 0..3)
+//     O    += P_j . Vv_j                                    4 MMAs 128x256x16 per 64-token sub-block, O (128 x 256) in TMEM
+//     out   = O / colsum_t  -> fp16 -> TMA store
+// Every MMA is 256 wide: narrower ones (the first version used 64-token steps) pay ~the same ~130-160 cycles per
+// instruction for a fraction of the work.  colmax / colsum come from mqdet_colsoftmax_stats / mqdet_colstats_rowsoftmax over
+// the SAME fp16 scores the image -> text side uses, so no online rescaling is needed.
+// Roles: warp 0 = Q producer, warp 3 = V producer (separate rings: a Q k-block is free as soon as its MMAs retire),
+// warp 1 = MMA issuer, warp 2 = TMEM allocator, warps 4-19 = exponentials + epilogue (thread == text token == TMEM lane,
+// four warps per lane quarter, 16 of the 64 sub-block columns each).  TMEM: S^T 256 columns + O 256 columns.
 // =====================================================================================================================
-constexpr int BT_NT = 64;  // image tokens per step
-constexpr int BT_PF = 4;   // L2 prefetch distance in steps
+constexpr int BT_STEP = 256;  // image tokens per S^T accumulator
+constexpr int BT_SUB = 64;    // image tokens per P / V tile
+constexpr int BT_PF = 2;      // L2 prefetch distance in steps
 struct BtCfg {
-  static constexpr int KT_BYTES = 4 * BM * BK * 2;        // resident K tile: 4 k-blocks of [128 x 64]
-  static constexpr int Q_BYTES = 4 * BT_NT * BK * 2;      // 4 k-blocks of [64 x 64]
-  static constexpr int V_BYTES = 256 * BK * 2;            // Vv^T tile [256 d x 64 n]
-  static constexpr int SLOT_BYTES = Q_BYTES + V_BYTES;
-  static constexpr int P_BYTES = BM * BT_NT * 2;
-  static constexpr int SMEM_BYTES = KT_BYTES + 2 * SLOT_BYTES + 2 * P_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int KT_BYTES = 4 * BM * BK * 2;    // resident K tile: 4 k-blocks of [128 x 64]
+  static constexpr int Q_BYTES = BT_STEP * BK * 2;    // one k-block [256 n x 64 d]
+  static constexpr int V_BYTES = 256 * BT_SUB * 2;    // Vv^T tile [256 d x 64 n]
+  static constexpr int P_BYTES = BM * BT_SUB * 2;     // P tile [128 t x 64 n]
+  static constexpr int SMEM_BYTES = KT_BYTES + 2 * Q_BYTES + 2 * V_BYTES + 2 * P_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 };
 struct BtP {
   const float* stat;  // [Z][2][T]: column max, 1 / column sum
@@ -913,19 +915,20 @@ __global__ void __launch_bounds__(640, 1) biattn_text_kernel(const __grid_consta
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* kt = smem;
-  uint8_t* slots = smem + BtCfg::KT_BYTES;                       // slot s: [q 32 KB][v 32 KB]
-  uint8_t* ptile = slots + 2 * BtCfg::SLOT_BYTES;                // P tile s: 16 KB
-  uint64_t* bars = reinterpret_cast<uint64_t*>(ptile + 2 * BtCfg::P_BYTES);
+  uint8_t* qring = kt + BtCfg::KT_BYTES;           // 2 x 32 KB
+  uint8_t* vring = qring + 2 * BtCfg::Q_BYTES;     // 2 x 32 KB
+  uint8_t* pring = vring + 2 * BtCfg::V_BYTES;     // 2 x 16 KB
+  uint64_t* bars = reinterpret_cast<uint64_t*>(pring + 2 * BtCfg::P_BYTES);
   uint64_t* kt_full = bars;
-  uint64_t* q_full = bars + 1;    // [2] Q_i landed
-  uint64_t* q_empty = bars + 3;   // [2] S^T_i complete: the Q half of the slot may be overwritten (one step EARLIER than V)
-  uint64_t* v_full = bars + 5;    // [2] Vv_i landed
-  uint64_t* v_empty = bars + 7;   // [2] P.V of the tile complete: V half and P tile of the slot may be overwritten
-  uint64_t* s_full = bars + 9;    // [2] S^T accumulator complete
-  uint64_t* s_empty = bars + 11;  // [2] S^T accumulator read by the exp warps
-  uint64_t* p_full = bars + 13;   // [2] P tile written by the exp warps
-  uint64_t* o_full = bars + 15;
-  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(bars + 16);
+  uint64_t* q_full = bars + 1;    // [2] Q k-block landed
+  uint64_t* q_empty = bars + 3;   // [2] its four MMAs retired
+  uint64_t* v_full = bars + 5;    // [2] Vv sub-block landed
+  uint64_t* pv_done = bars + 7;   // [2] P_j . Vv_j retired: V slot and P slot may be overwritten
+  uint64_t* p_full = bars + 9;    // [2] P tile written by the 16 exp warps
+  uint64_t* s_full = bars + 11;   // S^T accumulator complete
+  uint64_t* s_empty = bars + 12;  // S^T accumulator copied to registers by the 16 exp warps
+  uint64_t* o_full = bars + 13;
+  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(bars + 14);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int mt = blockIdx.x, z = blockIdx.y;
@@ -942,92 +945,82 @@ __global__ void __launch_bounds__(640, 1) biattn_text_kernel(const __grid_consta
       mbar_init(&q_full[s], 1);
       mbar_init(&q_empty[s], 1);
       mbar_init(&v_full[s], 1);
-      mbar_init(&v_empty[s], 1);
-      mbar_init(&s_full[s], 1);
-      mbar_init(&s_empty[s], 16);  // one arrival per exp warp
-      mbar_init(&p_full[s], 16);
+      mbar_init(&pv_done[s], 1);
+      mbar_init(&p_full[s], 16);  // one arrival per exp warp
     }
+    mbar_init(s_full, 1);
+    mbar_init(s_empty, 16);
     mbar_init(o_full, 1);
     fence_mbar_init();
   }
-  if (warp == 2) tmem_alloc(tmem_base_slot, 512);  // S^T: 2 x 64 columns, O: 256 columns
+  if (warp == 2) tmem_alloc(tmem_base_slot, 512);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_base_slot;
-  const uint32_t tmem_o = tmem_base + 128;
+  const uint32_t tmem_s = *tmem_base_slot;
+  const uint32_t tmem_o = tmem_s + 256;
 
   if (warp == 0) {
     if (lane == 0) {
       mbar_expect_tx(kt_full, BtCfg::KT_BYTES);
       for (int kb = 0; kb < 4; ++kb)
         tma_load_4d(kt + kb * (BM * BK * 2), &tma_k, kt_full, kb * BK, mt * BM, p.k_bc1 ? 0 : z1, p.k_bc2 ? 0 : z2);
-      // Q stream (this thread); the V stream has its own producer (warp 3): a Q slot is free as soon as S^T of its tile
-      // is complete, one step before the V half, so its reload overlaps the exponentials and the P.V product
-      for (int i = 0; i < NS; ++i) {
-        const int s = i & 1;
-        if (i + BT_PF < NS)  // pull the tile needed BT_PF steps from now into L2: the ring itself is only two deep
-          for (int kb = 0; kb < 4; ++kb)
-            tma_prefetch_l2_4d(&tma_q, kb * BK, (i + BT_PF) * BT_NT, p.q_bc1 ? 0 : z1, p.q_bc2 ? 0 : z2);
-        if (i >= 2) mbar_wait(&q_empty[s], ((i >> 1) - 1) & 1);
-        uint8_t* sq = slots + s * BtCfg::SLOT_BYTES;
+      const int qz1 = p.q_bc1 ? 0 : z1, qz2 = p.q_bc2 ? 0 : z2;
+      for (int qc = 0; qc < 4 * NS; ++qc) {
+        const int i = qc >> 2, kb = qc & 3, s = qc & 1;
+        if (i + BT_PF < NS) tma_prefetch_l2_4d(&tma_q, kb * BK, (i + BT_PF) * BT_STEP, qz1, qz2);
+        if (qc >= 2) mbar_wait(&q_empty[s], ((qc >> 1) - 1) & 1);
         mbar_expect_tx(&q_full[s], BtCfg::Q_BYTES);
-        for (int kb = 0; kb < 4; ++kb)
-          tma_load_4d(sq + kb * (BT_NT * BK * 2), &tma_q, &q_full[s], kb * BK, i * BT_NT, p.q_bc1 ? 0 : z1, p.q_bc2 ? 0 : z2);
+        tma_load_4d(qring + s * BtCfg::Q_BYTES, &tma_q, &q_full[s], kb * BK, i * BT_STEP, qz1, qz2);
       }
     }
   } else if (warp == 3) {
     if (lane == 0) {
-      for (int i = 0; i < NS; ++i) {
-        const int s = i & 1;
-        if (i + BT_PF < NS) tma_prefetch_l2_4d(&tma_v, (i + BT_PF) * BT_NT, 0, p.v_bc1 ? 0 : z1, p.v_bc2 ? 0 : z2);
-        if (i >= 2) mbar_wait(&v_empty[s], ((i >> 1) - 1) & 1);
+      const int vz1 = p.v_bc1 ? 0 : z1, vz2 = p.v_bc2 ? 0 : z2;
+      for (int sc = 0; sc < 4 * NS; ++sc) {
+        const int s = sc & 1;
+        if (sc + 4 * BT_PF < 4 * NS) tma_prefetch_l2_4d(&tma_v, (sc + 4 * BT_PF) * BT_SUB, 0, vz1, vz2);
+        if (sc >= 2) mbar_wait(&pv_done[s], ((sc >> 1) - 1) & 1);
         mbar_expect_tx(&v_full[s], BtCfg::V_BYTES);
-        tma_load_4d(slots + s * BtCfg::SLOT_BYTES + BtCfg::Q_BYTES, &tma_v, &v_full[s], i * BT_NT, 0, p.v_bc1 ? 0 : z1,
-                    p.v_bc2 ? 0 : z2);
+        tma_load_4d(vring + s * BtCfg::V_BYTES, &tma_v, &v_full[s], sc * BT_SUB, 0, vz1, vz2);
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      constexpr uint32_t idesc_s = umma_idesc_f16(BM, BT_NT, 0);
-      constexpr uint32_t idesc_o = umma_idesc_f16(BM, 256, 0);
+      constexpr uint32_t idesc = umma_idesc_f16(BM, 256, 0);
       mbar_wait(kt_full, 0);
       tc_fence_after();
-      auto issue_s = [&](int j) {
-        const int s = j & 1;
-        mbar_wait(&q_full[s], (j >> 1) & 1);
-        if (j >= 2) mbar_wait(&s_empty[s], ((j >> 1) - 1) & 1);
+      const uint32_t kt_addr = smem_u32(kt);
+      for (int i = 0; i < NS; ++i) {
+        if (i >= 1) mbar_wait(s_empty, (i - 1) & 1);  // the exp warps hold step i-1's scores in registers
         tc_fence_after();
-        const uint32_t acc = tmem_base + (uint32_t)(s * BT_NT);
-        const uint32_t a0 = smem_u32(kt), b0 = smem_u32(slots + s * BtCfg::SLOT_BYTES);
-#pragma unroll
-        for (int kb = 0; kb < 4; ++kb)
+        for (int kb = 0; kb < 4; ++kb) {
+          const int qc = 4 * i + kb, s = qc & 1;
+          mbar_wait(&q_full[s], (qc >> 1) & 1);
+          tc_fence_after();
+          const uint32_t b0 = smem_u32(qring + s * BtCfg::Q_BYTES);
 #pragma unroll
           for (int k = 0; k < 4; ++k)
-            tc_mma_f16(acc, umma_desc_k_sw128(a0 + kb * (BM * BK * 2) + k * 32),
-                       umma_desc_k_sw128(b0 + kb * (BT_NT * BK * 2) + k * 32), idesc_s, (kb | k) != 0 ? 1u : 0u);
-        tc_commit(&s_full[s]);
-        tc_commit(&q_empty[s]);
-      };
-      issue_s(0);
-      for (int i = 0; i < NS; ++i) {
-        if (i + 1 < NS) issue_s(i + 1);
-        const int s = i & 1;
-        mbar_wait(&v_full[s], (i >> 1) & 1);
-        mbar_wait(&p_full[s], (i >> 1) & 1);
-        tc_fence_after();
-        const uint32_t a0 = smem_u32(ptile + s * BtCfg::P_BYTES);
-        const uint32_t b0 = smem_u32(slots + s * BtCfg::SLOT_BYTES + BtCfg::Q_BYTES);
+            tc_mma_f16(tmem_s, umma_desc_k_sw128(kt_addr + kb * (BM * BK * 2) + k * 32), umma_desc_k_sw128(b0 + k * 32), idesc,
+                       (kb | k) != 0 ? 1u : 0u);
+          tc_commit(&q_empty[s]);
+        }
+        tc_commit(s_full);
+        for (int j = 0; j < 4; ++j) {
+          const int sc = 4 * i + j, s = sc & 1;
+          mbar_wait(&v_full[s], (sc >> 1) & 1);
+          mbar_wait(&p_full[s], (sc >> 1) & 1);
+          tc_fence_after();
+          const uint32_t a0 = smem_u32(pring + s * BtCfg::P_BYTES), b0 = smem_u32(vring + s * BtCfg::V_BYTES);
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-          tc_mma_f16(tmem_o, umma_desc_k_sw128(a0 + k * 32), umma_desc_k_sw128(b0 + k * 32), idesc_o, (i | k) != 0 ? 1u : 0u);
-        tc_commit(&v_empty[s]);
+          for (int k = 0; k < 4; ++k)
+            tc_mma_f16(tmem_o, umma_desc_k_sw128(a0 + k * 32), umma_desc_k_sw128(b0 + k * 32), idesc, (sc | k) != 0 ? 1u : 0u);
+          tc_commit(&pv_done[s]);
+        }
       }
       tc_commit(o_full);
     }
   } else if (warp >= 4) {
-    // 16 exp warps: four per TMEM lane quarter, each owning 16 of the 64 score columns of a step (and 64 of the 256
-    // output columns in the epilogue) -> four warps per scheduler hide the tcgen05.ld / MUFU latencies
     const int ew = (warp - 4) & 3, part = (warp - 4) >> 2;
     const int row = ew * 32 + lane;
     const int t = mt * BM + row;
@@ -1042,43 +1035,47 @@ __global__ void __launch_bounds__(640, 1) biattn_text_kernel(const __grid_consta
     const uint32_t lane_addr = (uint32_t)(ew * 32) << 16;
     const int j0 = part * 2;  // 16-byte chunks of this thread's 16 columns inside the 128-byte P row
     for (int i = 0; i < NS; ++i) {
-      const int s = i & 1;
-      mbar_wait(&s_full[s], (i >> 1) & 1);
+      mbar_wait(s_full, i & 1);
       tc_fence_after();
-      uint32_t r[16];
-      tmem_ld_32x16(tmem_base + lane_addr + (uint32_t)(s * BT_NT + part * 16), r);
-      tmem_ld_wait();
-      if (i >= 2) mbar_wait(&v_empty[s], ((i >> 1) - 1) & 1);  // the P.V product that read this P tile has completed
-      const uint32_t prow = smem_u32(ptile + s * BtCfg::P_BYTES) + row * 128;
-      const int nrem = p.N - i * BT_NT - part * 16;  // valid columns of this thread's 16 (>= 16 except in the last step)
-      uint32_t h[8];
+      // this thread's 16 columns of each of the four 64-token sub-blocks
+      uint32_t r[4][16];
 #pragma unroll
-      for (int q2 = 0; q2 < 8; ++q2) {
-        const float a = fminf(fmaxf(__uint_as_float(r[2 * q2]), -clampv), clampv);
-        const float b = fminf(fmaxf(__uint_as_float(r[2 * q2 + 1]), -clampv), clampv);
-        // the score as the fp16 matrix A holds it (the statistics were taken from those values)
-        const float2 f = __half22float2(__floats2half2_rn(a, b));
-        float e0 = ex2_approx(fmaf(f.x, L2E, m_l2)), e1 = ex2_approx(fmaf(f.y, L2E, m_l2));
-        if (nrem < 16) {  // last step: image tokens beyond N (zero-filled q rows) must not contribute exp(-max)
-          if (2 * q2 >= nrem) e0 = 0.f;
-          if (2 * q2 + 1 >= nrem) e1 = 0.f;
-        }
-        h[q2] = pack_half2(e0, e1);
-      }
-      sts128(prow + (((j0) ^ sw) << 4), h[0], h[1], h[2], h[3]);
-      sts128(prow + (((j0 + 1) ^ sw) << 4), h[4], h[5], h[6], h[7]);
+      for (int j = 0; j < 4; ++j) tmem_ld_32x16(tmem_s + lane_addr + (uint32_t)(j * BT_SUB + part * 16), r[j]);
+      tmem_ld_wait();
       tc_fence_before();
-      fence_proxy_async();  // generic-proxy writes of P -> visible to the tensor core (async proxy)
       __syncwarp();
-      if (lane == 0) {
-        mbar_arrive(&s_empty[s]);
-        mbar_arrive(&p_full[s]);
+      if (lane == 0) mbar_arrive(s_empty);  // the accumulator may be overwritten by the next step's S^T
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int sc = 4 * i + j, s = sc & 1;
+        if (sc >= 2) mbar_wait(&pv_done[s], ((sc >> 1) - 1) & 1);  // the product that read this P slot has retired
+        const int nrem = p.N - sc * BT_SUB - part * 16;  // valid columns of this thread's 16 (< 16 only at the very end)
+        uint32_t h[8];
+#pragma unroll
+        for (int q2 = 0; q2 < 8; ++q2) {
+          const float a = fminf(fmaxf(__uint_as_float(r[j][2 * q2]), -clampv), clampv);
+          const float b = fminf(fmaxf(__uint_as_float(r[j][2 * q2 + 1]), -clampv), clampv);
+          // the score as the fp16 matrix A holds it (the statistics were taken from those values)
+          const float2 f = __half22float2(__floats2half2_rn(a, b));
+          float e0 = ex2_approx(fmaf(f.x, L2E, m_l2)), e1 = ex2_approx(fmaf(f.y, L2E, m_l2));
+          if (nrem < 16) {  // image tokens beyond N (zero-filled q rows) must not contribute exp(-max)
+            if (2 * q2 >= nrem) e0 = 0.f;
+            if (2 * q2 + 1 >= nrem) e1 = 0.f;
+          }
+          h[q2] = pack_half2(e0, e1);
+        }
+        const uint32_t prow = smem_u32(pring + s * BtCfg::P_BYTES) + row * 128;
+        sts128(prow + (((j0) ^ sw) << 4), h[0], h[1], h[2], h[3]);
+        sts128(prow + (((j0 + 1) ^ sw) << 4), h[4], h[5], h[6], h[7]);
+        fence_proxy_async();  // generic-proxy writes of P -> visible to the tensor core (async proxy)
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&p_full[s]);
       }
     }
-    // ---- epilogue: O / colsum -> fp16 -> swizzled staging (slot 0 is idle by now) -> TMA store ----
+    // ---- epilogue: O / colsum -> fp16 -> swizzled staging (the Q and V rings are idle by now) -> TMA store ----
     mbar_wait(o_full, 0);
     tc_fence_after();
-    const uint32_t blk = smem_u32(slots) + part * (BM * 128) + row * 128;  // this warp's 64-column block
+    const uint32_t blk = smem_u32(qring) + part * (BM * 128) + row * 128;  // this warp's 64-column block (4 x 16 KB)
     uint32_t ra[16], rb[16];
     tmem_ld_32x16(tmem_o + lane_addr + (uint32_t)(part * 64), ra);
 #pragma unroll
@@ -1101,14 +1098,14 @@ __global__ void __launch_bounds__(640, 1) biattn_text_kernel(const __grid_consta
     fence_proxy_async();
     asm volatile("bar.sync 1, 512;" ::: "memory");
     if (warp == 4 && lane == 0) {
-      for (int cb = 0; cb < 4; ++cb) tma_store_4d(&tma_o, slots + cb * (BM * 128), cb * 64, mt * BM, z1, z2);
+      for (int cb = 0; cb < 4; ++cb) tma_store_4d(&tma_o, qring + cb * (BM * 128), cb * 64, mt * BM, z1, z2);
       tma_store_commit_and_wait_read();
     }
   }
   __syncthreads();
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 512);
+    tmem_dealloc(tmem_s, 512);
   }
 }
 
@@ -1435,9 +1432,9 @@ extern "C" int mqdet_biattn_text(const void* k, int64_t k_ld, int64_t k_b1, int6
   memset(&p, 0, sizeof(p));
   int rc = make_operand_map(&mk, k, T, d, k_ld, (int)nb1, k_b1, (int)nb2, k_b2, BM, &p.k_bc1, &p.k_bc2);
   if (rc) return rc;
-  rc = make_operand_map(&mq, q, N, d, q_ld, (int)nb1, q_b1, (int)nb2, q_b2, BT_NT, &p.q_bc1, &p.q_bc2);
+  rc = make_operand_map(&mq, q, N, d, q_ld, (int)nb1, q_b1, (int)nb2, q_b2, BT_STEP, &p.q_bc1, &p.q_bc2);
   if (rc) return rc;
-  rc = make_operand_map(&mv, vvT, d, Np, v_ld, (int)nb1, v_b1, (int)nb2, v_b2, 256, &p.v_bc1, &p.v_bc2);
+  rc = make_operand_map(&mv, vvT, d, Np, v_ld, (int)nb1, v_b1, (int)nb2, v_b2, 256, &p.v_bc1, &p.v_bc2);  // box [64 n x 256 d]
   if (rc) return rc;
   GemmP o;
   memset(&o, 0, sizeof(o));
@@ -1451,7 +1448,7 @@ extern "C" int mqdet_biattn_text(const void* k, int64_t k_ld, int64_t k_b1, int6
   p.nb1 = (int)nb1;
   p.T = (int)T;
   p.N = (int)N;
-  p.n_steps = (int)((N + BT_NT - 1) / BT_NT);
+  p.n_steps = (int)((N + BT_STEP - 1) / BT_STEP);
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(biattn_text_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BtCfg::SMEM_BYTES);
