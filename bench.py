@@ -211,22 +211,43 @@ def main():
     value = world * B / (ms / 1e3)
 
     # ---- end to end through the public API with host buffers ----------------------------------------------------------
-    x_stage = torch.empty_like(img_dev)
+    # Every step's images start in pinned HOST memory and its detections end in pinned host memory, all inside the timed
+    # region.  The upload of step s+1 runs on a copy stream while step s computes (two device staging buffers), the way a
+    # prefetching data loader feeds the reference's `model(images.to(device))`; the forward itself is unchanged.
+    stage = [torch.empty_like(img_dev), torch.empty_like(img_dev)]
     det_host = torch.empty((B, 128, 6), dtype=torch.float32).pin_memory()
     num_host = torch.empty((B,), dtype=torch.int32).pin_memory()
-    for _ in range(2):
-        x_stage.copy_(img_host, non_blocking=True)
-        o = step(x_stage)
-        det_host.copy_(o["det"], non_blocking=True)
-        num_host.copy_(o["num"], non_blocking=True)
+    copy_stream = torch.cuda.Stream()
+    main = torch.cuda.current_stream()
+    up_done = [torch.cuda.Event(), torch.cuda.Event()]     # upload into stage[k] finished
+    fw_done = [torch.cuda.Event(), torch.cuda.Event()]     # the forward that read stage[k] finished
+
+    def upload(k):
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(fw_done[k])               # stage[k] is no longer being read
+            stage[k].copy_(img_host, non_blocking=True)
+            up_done[k].record(copy_stream)
+
+    def e2e_steps(n):
+        upload(0)
+        for s_ in range(n):
+            k = s_ & 1
+            if s_ + 1 < n:
+                upload(k ^ 1)
+            main.wait_event(up_done[k])
+            o_ = step(stage[k])
+            fw_done[k].record(main)
+            det_host.copy_(o_["det"], non_blocking=True)
+            num_host.copy_(o_["num"], non_blocking=True)
+        return o_
+
+    for ev_ in fw_done:
+        ev_.record(main)
+    e2e_steps(2)
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(args.steps):
-        x_stage.copy_(img_host, non_blocking=True)
-        o = step(x_stage)
-        det_host.copy_(o["det"], non_blocking=True)
-        num_host.copy_(o["num"], non_blocking=True)
+    o = e2e_steps(args.steps)
     e1.record()
     barrier()
     e2e_ms = e0.elapsed_time(e1) / args.steps
