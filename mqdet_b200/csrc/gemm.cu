@@ -362,7 +362,11 @@ __device__ __forceinline__ void epilogue_fast(const GemmP& p, const CUtensorMap*
   const int r_local = ew * 32 + lane;
   const bool issuer = (ew == 0 && half == 0 && lane == 0);
   const uint32_t t_row = tmem_acc + ((uint32_t)(ew * 32) << 16);
-  const int c_begin = cw0 + half * (cw >> 1), c_end = c_begin + (cw >> 1);  // (cw / 2) % 32 == 0
+  const int c_begin = cw0 + half * (cw >> 1);  // (cw / 2) % 32 == 0
+  // columns at or beyond N (partial last n tile) are clipped by the TMA store: do not convert them (32-column steps)
+  const long n_left = p.N - (long)n_tile * BN;
+  const int c_lim = (int)(n_left < (long)BN ? ((n_left + 31) & ~31L) : (long)BN);
+  const int c_end = min(c_begin + (cw >> 1), c_lim);
   const float clampv = p.clamp;
   const int act = PLAIN ? MQDET_ACT_NONE : p.act;
   const bool f16 = PLAIN || p.c_dtype == MQDET_F16;
@@ -389,8 +393,10 @@ __device__ __forceinline__ void epilogue_fast(const GemmP& p, const CUtensorMap*
       for (int k = 0; k < 4; ++k) q[k] = (col + 4 * k < p.N) ? __ldg(src + k) : make_uint4(0, 0, 0, 0);
     }
   };
-  tmem_ld_32x16(t_row + (uint32_t)c_begin, ra);
-  if (has_res) load_res(qa, c_begin);
+  if (c_begin < c_end) {
+    tmem_ld_32x16(t_row + (uint32_t)c_begin, ra);
+    if (has_res) load_res(qa, c_begin);
+  }
   if (!dbl) {  // ONE staging tile: the previous tile's TMA store must have read it before it is rewritten
     if (issuer) tma_store_wait_read_all();
     asm volatile("bar.sync 1, 256;" ::: "memory");
@@ -764,7 +770,7 @@ __global__ void __launch_bounds__(384, 1) gemm_tcp_kernel(const __grid_constant_
       }
     }
   } else if (warp >= 4) {
-    int lt = 0;
+    int lt = 0, wcount = 0;
     const int ew = (warp - 4) & 3, half = (warp - 4) >> 2, tid_e = threadIdx.x - 128;
     // the fast epilogue covers everything without an activation when the output takes the TMA store (host: fast_epilogue_ok)
     const bool fast = p.fast_epi != 0;
@@ -829,13 +835,16 @@ __global__ void __launch_bounds__(384, 1) gemm_tcp_kernel(const __grid_constant_
           if constexpr (BN == 256 && BRES) {
             // four 64-column windows through two alternating 16 KB staging tiles (fp16 TMA-store epilogue only)
 #pragma unroll 1
-            for (int w = 0; w < 4; ++w) {
+            const long nl = p.N - (long)n_tile * BN;
+            const int nwin = nl >= BN ? 4 : (int)((nl + 63) >> 6);  // windows entirely beyond N are skipped
+            for (int w = 0; w < nwin; ++w, ++wcount) {  // wcount: the two staging tiles strictly alternate across tiles
+              uint8_t* const st_win = stg + (wcount & 1) * (BM * 128);
               if (plain)
-                epilogue_fast<BN, true>(p, &tma_c, tmem_base + (uint32_t)(buf * BN), stg + (w & 1) * (BM * 128), fe, m0 + mt, n_tile,
-                                        z1, z2, ew, lane, &tmem_empty_bar[buf], true, half, w * 64, 64, w == 3);
+                epilogue_fast<BN, true>(p, &tma_c, tmem_base + (uint32_t)(buf * BN), st_win, fe, m0 + mt, n_tile, z1, z2, ew, lane,
+                                        &tmem_empty_bar[buf], true, half, w * 64, 64, w == nwin - 1);
               else
-                epilogue_fast<BN, false>(p, &tma_c, tmem_base + (uint32_t)(buf * BN), stg + (w & 1) * (BM * 128), fe, m0 + mt, n_tile,
-                                         z1, z2, ew, lane, &tmem_empty_bar[buf], true, half, w * 64, 64, w == 3);
+                epilogue_fast<BN, false>(p, &tma_c, tmem_base + (uint32_t)(buf * BN), st_win, fe, m0 + mt, n_tile, z1, z2, ew, lane,
+                                         &tmem_empty_bar[buf], true, half, w * 64, 64, w == nwin - 1);
             }
           } else {
             uint8_t* const st_tile = stg + (stg2 ? (lt & 1) * (BM * BN * 2) : 0);
