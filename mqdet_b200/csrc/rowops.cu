@@ -470,7 +470,7 @@ __global__ void __launch_bounds__(256) colsoftmax_stats_kernel(const __half* __r
 // exactly like colsoftmax_stats_kernel and (b) replaces every row by its masked softmax over the 256 tokens (the
 // image -> text probabilities, fuse_helper.py:277-287) in place.  With 32 vectors per row a warp owns whole rows, so the
 // row reductions are warp shuffles; every element is read once by the thread that overwrites it.
-__global__ void __launch_bounds__(256) colstats_rowsoftmax256_kernel(__half* __restrict__ A, int N, float* __restrict__ partial,
+__global__ void __launch_bounds__(256, 4) colstats_rowsoftmax256_kernel(__half* __restrict__ A, int N, float* __restrict__ partial,
                                                                      int nchunks, const float* __restrict__ colmask,
                                                                      int z_per_mask, float mask_value, float keep_add) {
   constexpr int T = 256;
@@ -480,13 +480,16 @@ __global__ void __launch_bounds__(256) colstats_rowsoftmax256_kernel(__half* __r
   const int g = threadIdx.x >> 5, lane = threadIdx.x & 31, c = lane * 8;
   const int r0 = chunk * CS_ROWS, r1 = min(N, r0 + CS_ROWS);
   __half* a = A + (long)z * N * T + c;
-  float madd[8];
-#pragma unroll
-  for (int i = 0; i < 8; ++i) madd[i] = 0.f;
+  // additive mask of this thread's 8 columns as bits (1 = token in use) -> 1 register instead of 8
+  unsigned keep_bits = 0xffu;
+  float add_keep = 0.f, add_mask = 0.f;
   if (colmask) {
     const float* cm = colmask + (long)(z / z_per_mask) * T + c;
+    keep_bits = 0u;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) madd[i] = (cm[i] == 0.f) ? mask_value : keep_add;
+    for (int i = 0; i < 8; ++i) keep_bits |= (cm[i] != 0.f ? 1u : 0u) << i;
+    add_keep = keep_add;
+    add_mask = mask_value;
   }
   float m[8], sacc[8];
 #pragma unroll
@@ -494,10 +497,11 @@ __global__ void __launch_bounds__(256) colstats_rowsoftmax256_kernel(__half* __r
     m[i] = -INFINITY;
     sacc[i] = 0.f;
   }
-  for (int rb = r0 + g; rb < r1; rb += 64) {
-    uint4 u[8];
+  constexpr int RB = 4;  // rows per thread per block: 4 x 16 B in flight, <= 64 registers -> 4 CTAs / SM
+  for (int rb = r0 + g; rb < r1; rb += 8 * RB) {
+    uint4 u[RB];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
+    for (int j = 0; j < RB; ++j) {
       const int r = rb + j * 8;
       u[j] = *reinterpret_cast<const uint4*>(a + (long)(r < r1 ? r : rb) * T);
     }
@@ -506,7 +510,7 @@ __global__ void __launch_bounds__(256) colstats_rowsoftmax256_kernel(__half* __r
 #pragma unroll
     for (int i = 0; i < 8; ++i) bm[i] = m[i];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
+    for (int j = 0; j < RB; ++j) {
       const __half2* h = reinterpret_cast<const __half2*>(&u[j]);
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
@@ -523,7 +527,7 @@ __global__ void __launch_bounds__(256) colstats_rowsoftmax256_kernel(__half* __r
       nm[i] = -bm[i] * L2E;
     }
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
+    for (int j = 0; j < RB; ++j) {
       const int r = rb + j * 8;
       if (r >= r1) continue;  // warp-uniform
       const __half2* h = reinterpret_cast<const __half2*>(&u[j]);
@@ -540,7 +544,7 @@ __global__ void __launch_bounds__(256) colstats_rowsoftmax256_kernel(__half* __r
       float mx = -INFINITY;
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
-        v[i] += madd[i];
+        v[i] += ((keep_bits >> i) & 1u) ? add_keep : add_mask;
         mx = fmaxf(mx, v[i]);
       }
       mx = warp_max(mx);
