@@ -148,35 +148,49 @@ __global__ void __launch_bounds__(256) nms_scan_kernel(int n, const unsigned lon
     *kth_score = -INFINITY;
   }
   __syncthreads();
+  __shared__ int kept_list[64];
+  __shared__ int kept_cnt;
   for (int blk = 0; blk < col_blocks; ++blk) {
     const int base = blk * 64;
     const int size = min(n - base, 64);
+    // Early exit (top-k cut only): once max_det boxes are kept, a later box can pass the `score >= kth kept score` cut of
+    // rpn/inference.py:759-767 only with a score equal to it; scores are sorted descending, so when the first score of a
+    // block is already below the threshold nothing after it can appear in the output (kept or not).
+    if (max_det > 0 && kept_so_far >= max_det && sorted[base * 6 + 4] < *kth_score) break;
     if ((int)threadIdx.x < size) diag[threadIdx.x] = mask[(long)(base + threadIdx.x) * col_blocks + blk];
     __syncthreads();
     if (threadIdx.x == 0) {
       unsigned long long r = remv[blk], kb = 0;
+      int cnt = 0;
       for (int t = 0; t < size; ++t) {
         if (!(r & (1ULL << t))) {
           kb |= 1ULL << t;
           r |= diag[t];
+          kept_list[cnt++] = t;
           ++kept_so_far;
           if (max_det > 0 && kept_so_far == max_det) *kth_score = sorted[(base + t) * 6 + 4];
         }
       }
       keepbits = kb;
+      kept_cnt = cnt;
     }
     __syncthreads();
     const unsigned long long kb = keepbits;
+    const int cnt = kept_cnt;
     if ((int)threadIdx.x < size && (kb & (1ULL << threadIdx.x))) flags[order[base + threadIdx.x]] = 1;
-    // OR the kept rows into the removed words of later column blocks
+    // OR the kept rows into the removed words of later column blocks: 8 independent loads in flight per thread
     for (int j = blk + 1 + threadIdx.x; j < col_blocks; j += blockDim.x) {
       unsigned long long r = remv[j];
-      unsigned long long bits = kb;
-      while (bits) {
-        int t = __ffsll((long long)bits) - 1;
-        bits &= bits - 1;
-        r |= mask[(long)(base + t) * col_blocks + j];
+      const unsigned long long* mrow = mask + (long)base * col_blocks + j;
+      int k = 0;
+      for (; k + 8 <= cnt; k += 8) {
+        unsigned long long w[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) w[u] = mrow[(long)kept_list[k + u] * col_blocks];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) r |= w[u];
       }
+      for (; k < cnt; ++k) r |= mrow[(long)kept_list[k] * col_blocks];
       remv[j] = r;
     }
     __syncthreads();
