@@ -252,6 +252,60 @@ __global__ void __launch_bounds__(256) softmax_rows256_kernel(const __half* __re
   }
 }
 
+// fp32 scores (the BERT self-attention products, [B*12*256, 256]): same single-read scheme with two float4 per lane.
+template <int RW>
+__global__ void __launch_bounds__(256) softmax_rows256_f32_kernel(const float* __restrict__ x, long ldx, __half* __restrict__ y,
+                                                                  long ldy, long rows, float scale,
+                                                                  const float* __restrict__ colmask, long rows_per_batch,
+                                                                  float mask_value, float keep_add) {
+  const int lane = threadIdx.x & 31;
+  const long r0 = ((long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * RW;
+  if (r0 >= rows) return;
+  constexpr float L2E = 1.4426950408889634f;
+  float4 u[RW][2];
+#pragma unroll
+  for (int j = 0; j < RW; ++j) {
+    if (r0 + j < rows) {
+      const float4* src = reinterpret_cast<const float4*>(x + (r0 + j) * ldx + lane * 8);
+      u[j][0] = src[0];
+      u[j][1] = src[1];
+    } else {
+      u[j][0] = u[j][1] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < RW; ++j) {
+    const long row = r0 + j;
+    if (row >= rows) break;
+    float v[8] = {u[j][0].x * scale, u[j][0].y * scale, u[j][0].z * scale, u[j][0].w * scale,
+                  u[j][1].x * scale, u[j][1].y * scale, u[j][1].z * scale, u[j][1].w * scale};
+    if (colmask) {
+      const float* cm = colmask + (row / rows_per_batch) * 256 + lane * 8;
+      const float4 m0 = *reinterpret_cast<const float4*>(cm);
+      const float4 m1 = *reinterpret_cast<const float4*>(cm + 4);
+      const float mm[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] += (mm[i] == 0.f) ? mask_value : keep_add;
+    }
+    float mx = v[0];
+#pragma unroll
+    for (int i = 1; i < 8; ++i) mx = fmaxf(mx, v[i]);
+    mx = warp_max(mx);
+    const float ms = -mx * L2E;
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      v[i] = exp2f(fmaf(v[i], L2E, ms));
+      sum += v[i];
+    }
+    const float inv = 1.f / warp_sum(sum);
+    __half2 o[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) o[i] = __floats2half2_rn(v[2 * i] * inv, v[2 * i + 1] * inv);
+    *reinterpret_cast<uint4*>(y + row * ldy + lane * 8) = *reinterpret_cast<uint4*>(o);
+  }
+}
+
 // Vectorised fp16 row softmax (rows 16-byte aligned, n % 8 == 0): one warp per row, 8 halfs per lane per step.
 //   ITERS > 0 : the whole row (n <= ITERS*256) lives in registers -> one read, one write      (A: n = 256 tokens)
 //   ITERS == 0: two passes, online max/sum then normalise                                     (At: n = 22400 locations)
@@ -830,6 +884,13 @@ extern "C" int mqdet_softmax_rows(const void* x, int in_dtype, int64_t ldx, void
       softmax_rows_f16v_kernel<0><<<grid, wpb * 32, 0, st>>>(xh, ldx, yh, ldy, rows, (int)n, (int)n_pad, scale, colmask,
                                                             rows_per_batch, mask_value, keep_add);
     return check_launch("softmax_rows_f16v_kernel");
+  }
+  if (in_dtype == MQDET_F32 && n == 256 && n_pad == 256 && (ldx % 4) == 0 && (ldy % 8) == 0 && ((uintptr_t)x % 16) == 0 &&
+      ((uintptr_t)y % 16) == 0 && (!colmask || ((uintptr_t)colmask % 16) == 0)) {
+    constexpr int RW = 2;
+    softmax_rows256_f32_kernel<RW><<<(unsigned)cdiv(rows, (long)wpb * RW), wpb * 32, 0, st>>>(
+        (const float*)x, ldx, (__half*)y, ldy, rows, scale, colmask, rows_per_batch, mask_value, keep_add);
+    return check_launch("softmax_rows256_f32_kernel");
   }
   if (in_dtype == MQDET_F32)
     softmax_rows_kernel<float><<<grid, wpb * 32, 0, st>>>((const float*)x, ldx, (__half*)y, ldy, rows, (int)n, (int)n_pad,
