@@ -1000,9 +1000,7 @@ __global__ void __launch_bounds__(640, 1) biattn_text_kernel(const __grid_consta
       mbar_wait(kt_full, 0);
       tc_fence_after();
       const uint32_t kt_addr = smem_u32(kt);
-      for (int i = 0; i < NS; ++i) {
-        if (i >= 1) mbar_wait(s_empty, (i - 1) & 1);  // the exp warps hold step i-1's scores in registers
-        tc_fence_after();
+      auto issue_s = [&](int i) {  // S^T of step i: 4 k-blocks x 4 MMAs
         for (int kb = 0; kb < 4; ++kb) {
           const int qc = 4 * i + kb, s = qc & 1;
           mbar_wait(&q_full[s], (qc >> 1) & 1);
@@ -1015,6 +1013,16 @@ __global__ void __launch_bounds__(640, 1) biattn_text_kernel(const __grid_consta
           tc_commit(&q_empty[s]);
         }
         tc_commit(s_full);
+      };
+      issue_s(0);
+      for (int i = 0; i < NS; ++i) {
+        // S^T of the NEXT step goes first: the exp warps hold step i's scores in registers (s_empty), so the tensor pipe
+        // computes S^T(i+1) while they turn S^T(i) into the four P tiles, and P(i).Vv follows back to back
+        if (i + 1 < NS) {
+          mbar_wait(s_empty, i & 1);
+          tc_fence_after();
+          issue_s(i + 1);
+        }
         for (int j = 0; j < 4; ++j) {
           const int sc = 4 * i + j, s = sc & 1;
           mbar_wait(&v_full[s], (sc >> 1) & 1);
