@@ -36,37 +36,37 @@ class QuerySelector(nn.Module):
         """In-memory bank {label: tensor[n, scales, C]} (tests / synthetic benchmarks; no file on disk)."""
         self.query_bank = {k: v.to(self.device) for k, v in bank.items()}
 
+    def _pick(self, label):
+        """Rows of the class's bank entry to use (the reference's sampler, same RNG calls in the same order)."""
+        cand = self.query_bank[label]
+        k = self.num_query_per_class
+        if self.cfg.VISION_QUERY.RANDOM_KSHOT and self.training:
+            k = np.random.choice(range(1, k + 1))
+        nq = min(len(cand), k)
+        if (random.random() < self.pure_text_rate) and self.training:
+            nq = 0
+        rows = np.random.choice(len(cand), nq, replace=False).tolist()
+        return cand, (rows if self.training else sorted(rows))
+
     def forward(self, batched_label_list, batched_location_map, batched_pos_labels=None):
+        """-> (queries [B, Q, C], masks [B, Q, T] in {0,1}, per-image has-query flags); (None,)*3 without a bank."""
         if self.query_bank is None:
             return None, None, None
-        batched_queries, batched_masks, batched_has = [], [], []
-        for k, (label_list, location_map) in enumerate(zip(batched_label_list, batched_location_map)):
-            q_img, m_img, has = [], [], []
-            for label, loc_map in zip(label_list, location_map):
-                cand = self.query_bank[label]
-                total = len(cand)
-                kq = np.random.choice(range(1, self.num_query_per_class + 1)) if (
-                    self.cfg.VISION_QUERY.RANDOM_KSHOT and self.training) else self.num_query_per_class
-                nq = min(total, kq)
-                if (random.random() < self.pure_text_rate) and self.training:
-                    nq = 0
-                idx = np.random.choice(total, nq, replace=False).tolist()
-                if not self.training:
-                    idx = sorted(idx)
-                if isinstance(cand, list):
-                    assert len(idx) == 0
+        per_q, per_m, per_has = [], [], []
+        for b, (labels, loc_maps) in enumerate(zip(batched_label_list, batched_location_map)):
+            feats, rows_of_mask, has = [], [], []
+            for label, loc_map in zip(labels, loc_maps):
+                cand, rows = self._pick(label)
+                if isinstance(cand, list):  # class without exemplars
+                    assert not rows
                 else:
-                    q = cand[idx]
-                    ns = q.shape[1]
-                    q_img.append(q.flatten(0, 1))
-                    m_img.append(loc_map.to(self.device)[None].expand(nq * ns, -1))
-                pos = True if batched_pos_labels is None else (label in batched_pos_labels[k])
-                if pos:
-                    has.append(1 if nq > 0 else 0)
-            batched_queries.append(torch.cat(q_img))
-            batched_masks.append(torch.cat(m_img))
-            batched_has.append(has)
-        queries = pad_sequence(batched_queries, batch_first=True)
-        masks = pad_sequence(batched_masks, batch_first=True)
-        masks[masks != 0] = 1
-        return queries, masks, batched_has
+                    q = cand[rows]  # [nq, scales, C]
+                    feats.append(q.reshape(-1, q.shape[-1]))
+                    rows_of_mask.append(loc_map.to(self.device)[None].expand(q.shape[0] * q.shape[1], -1))
+                if batched_pos_labels is None or label in batched_pos_labels[b]:
+                    has.append(int(len(rows) > 0))
+            per_q.append(torch.cat(feats))
+            per_m.append(torch.cat(rows_of_mask))
+            per_has.append(has)
+        masks = pad_sequence(per_m, batch_first=True)
+        return pad_sequence(per_q, batch_first=True), (masks != 0).to(masks.dtype), per_has

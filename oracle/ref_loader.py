@@ -144,6 +144,27 @@ def gdino_utils():
     return _cache["gdu"]
 
 
+def query_selector():
+    """maskrcnn_benchmark/modeling/query_selector/query_selector.py (pure torch / numpy)."""
+    if "qs" not in _cache:
+        _cache["qs"] = _load_file("ref_query_selector", "maskrcnn_benchmark/modeling/query_selector/query_selector.py")
+    return _cache["qs"]
+
+
+def bounding_box():
+    """maskrcnn_benchmark/structures/bounding_box.py (BoxList)."""
+    if "bb" not in _cache:
+        _cache["bb"] = _load_file("ref_bounding_box", "maskrcnn_benchmark/structures/bounding_box.py")
+    return _cache["bb"]
+
+
+def image_list():
+    """maskrcnn_benchmark/structures/image_list.py (ImageList, to_image_list)."""
+    if "il" not in _cache:
+        _cache["il"] = _load_file("ref_image_list", "maskrcnn_benchmark/structures/image_list.py")
+    return _cache["il"]
+
+
 def fpn():
     """maskrcnn_benchmark/modeling/backbone/fpn.py (FPN, LastLevelP6P7)."""
     if "fpn" not in _cache:
