@@ -7,12 +7,16 @@ be loaded into the unmodified reference module, tests/test_oracle_pinning.py).  
 product path (mqdet_b200/) never does.
 
 Pinning status (the reference ships no tests or golden vectors):
-  * GCP block, sparse attention, PreSelect, BiAttention fusion, in-repo BERT layer, Swin window attention:
-    pinned against the reference's own modules executed in the build container — fixtures tests/golden/*.pt,
-    generated by oracle/make_golden.py.
-  * HF BertLayer loop (QVBertEncoder.forward), DCNv2, ml_nms: the reference cannot execute these on CPU under the
-    container's library versions -> "parity unpinned": restated from the cited lines only
-    (ml_nms/DCNv2 are additionally compared with the reference's CUDA kernels when oracle/_ref is built).
+  * GCP block + sparse attention + index table, PreSelect, BiAttention fusion, in-repo BERT layer, Swin-T + FPN
+    (bit-identical), GroundingDINO ContrastiveEmbed: pinned against the reference's own modules executed in the build
+    container (tests/test_oracle_pinning.py) and through the fixtures tests/golden/*.pt recorded from them by
+    oracle/make_golden.py (tests/test_oracle_golden.py).
+  * ml_nms and DCNv2 (incl. the DyConv[0] offset re-interpretation): the reference has no CPU implementation; they are
+    pinned on the GPU against the reference's own CUDA kernels, compiled unmodified by oracle/build_ref.py into
+    oracle/_ref/ (tests/test_ref_kernels_gpu.py: bit-identical kept sets, DCNv2 within fp32 noise).
+  * "parity unpinned": only the HF-BertLayer loop ordering of QVBertEncoder.forward (HF 5.x in this container no longer
+    has the classes the reference subclasses) -- restated from modeling_bert_new.py:545-639; the single
+    BERT layer it iterates IS pinned.
 Paths are relative to the MQ-Det repository root.
 """
 import math
