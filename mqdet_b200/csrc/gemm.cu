@@ -1421,7 +1421,11 @@ extern "C" int mqdet_gemm_f16(const mqdet_gemm_args* a, int impl, void* stream) 
     // 128x128 MMAs (both operands from shared memory) run at about half the tensor rate of 128x256 (measured: 684 vs
     // 1750 TFLOP/s with loads and epilogue disabled), so the 256-wide resident tile is used whenever the output can take
     // the fp16 TMA-store epilogue
-    if (p.N >= 256 && p.c_dtype == MQDET_F16 && can_tma_store(p, 256, true) && mt * cdiv(p.N, 256) * z >= num_sms())
+    // ... unless the 256-wide tiling pads N by more than `waste` (e.g. N = 288 -> 512): those products are output / epilogue
+    // bound and take the 128-wide resident tile (MQDET_BRES256_MAXWASTE overrides the threshold for A/B runs)
+    static const float waste = getenv("MQDET_BRES256_MAXWASTE") ? (float)atof(getenv("MQDET_BRES256_MAXWASTE")) : 2.0f;
+    const bool fits256 = (float)(cdiv(p.N, 256) * 256) <= waste * (float)p.N;
+    if (p.N >= 256 && fits256 && p.c_dtype == MQDET_F16 && can_tma_store(p, 256, true) && mt * cdiv(p.N, 256) * z >= num_sms())
       return launch_tcp<256, 3, true>(p, st);
     if (wide) return launch_tcp<128, 4, true>(p, st);
   }
