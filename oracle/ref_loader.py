@@ -165,6 +165,54 @@ def image_list():
     return _cache["il"]
 
 
+def rpn_inference(ml_nms_fn):
+    """maskrcnn_benchmark/modeling/rpn/inference.py (ATSSPostProcessor, convert_grounding_to_od_logits) together with the
+    reference's own box_coder.py, bounding_box.py and boxlist_ops.py.  The only thing the file cannot get on CPU is the
+    compiled ``maskrcnn_benchmark.layers.ml_nms`` (a CUDA kernel): ``ml_nms_fn(boxes, scores, labels, thresh) -> kept
+    indices`` stands in for it (the kernel itself is pinned on the GPU, tests/test_ref_kernels_gpu.py)."""
+    _install_shims()
+    pkg = sys.modules["maskrcnn_benchmark"]
+    if "maskrcnn_benchmark.layers" not in sys.modules:
+        layers = types.ModuleType("maskrcnn_benchmark.layers")
+        sys.modules["maskrcnn_benchmark.layers"] = layers
+        pkg.layers = layers
+    layers = sys.modules["maskrcnn_benchmark.layers"]
+    layers.ml_nms = ml_nms_fn
+    layers.nms = lambda *a, **k: (_ for _ in ()).throw(NotImplementedError("single-class nms is not on the MQ-Det path"))
+    if "rpn_inf" not in _cache:
+        structures = types.ModuleType("maskrcnn_benchmark.structures")
+        structures.__path__ = []
+        sys.modules["maskrcnn_benchmark.structures"] = structures
+        pkg.structures = structures
+        structures.bounding_box = _load_file("maskrcnn_benchmark.structures.bounding_box",
+                                             "maskrcnn_benchmark/structures/bounding_box.py")
+        structures.boxlist_ops = _load_file("maskrcnn_benchmark.structures.boxlist_ops",
+                                            "maskrcnn_benchmark/structures/boxlist_ops.py")
+        modeling = sys.modules["maskrcnn_benchmark.modeling"]
+        modeling.box_coder = _load_file("maskrcnn_benchmark.modeling.box_coder", "maskrcnn_benchmark/modeling/box_coder.py")
+        rpn = types.ModuleType("maskrcnn_benchmark.modeling.rpn")
+        rpn.__path__ = []
+        sys.modules["maskrcnn_benchmark.modeling.rpn"] = rpn
+        modeling.rpn = rpn
+        _cache["rpn_inf"] = _load_file("maskrcnn_benchmark.modeling.rpn.inference", "maskrcnn_benchmark/modeling/rpn/inference.py")
+    inf = _cache["rpn_inf"]
+
+    def boxlist_ml_nms_gpu_branch(boxlist, nms_thresh, max_proposals=-1, score_field="scores", label_field="labels"):
+        # boxlist_ops.py:48-75 as executed for CUDA tensors (:69); on CPU tensors the reference takes a per-label debugging
+        # branch (:56-67) that is not what inference runs, so the wrapper is re-stated here around the substituted kernel
+        if nms_thresh <= 0:
+            return boxlist
+        mode = boxlist.mode
+        boxlist = boxlist.convert("xyxy")
+        keep = ml_nms_fn(boxlist.bbox, boxlist.get_field(score_field), boxlist.get_field(label_field).float(), nms_thresh)
+        if max_proposals > 0:
+            keep = keep[:max_proposals]
+        return boxlist[keep].convert(mode)
+
+    inf.boxlist_ml_nms = boxlist_ml_nms_gpu_branch
+    return inf
+
+
 def fpn():
     """maskrcnn_benchmark/modeling/backbone/fpn.py (FPN, LastLevelP6P7)."""
     if "fpn" not in _cache:

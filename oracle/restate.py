@@ -8,7 +8,8 @@ product path (mqdet_b200/) never does.
 
 Pinning status (the reference ships no tests or golden vectors):
   * GCP block + sparse attention + index table, PreSelect, BiAttention fusion, in-repo BERT layer, Swin-T + FPN
-    (bit-identical), GroundingDINO ContrastiveEmbed: pinned against the reference's own modules executed in the build
+    (bit-identical), ATSS post-processing (ATSSPostProcessor.forward with only the compiled ml_nms substituted),
+    GroundingDINO ContrastiveEmbed: pinned against the reference's own modules executed in the build
     container (tests/test_oracle_pinning.py) and through the fixtures tests/golden/*.pt recorded from them by
     oracle/make_golden.py (tests/test_oracle_golden.py).
   * ml_nms and DCNv2 (incl. the DyConv[0] offset re-interpretation): the reference has no CPU implementation; they are

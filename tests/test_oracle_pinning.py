@@ -1,9 +1,11 @@
 """CPU, build container only: pins oracle/restate.py against the reference's own modules executed from
 /root/reference (full tensors, not the committed subsamples).  Skipped where the reference is absent (GPU box)."""
+import sys
+
 import pytest
 import torch
 
-from oracle import make_golden, ref_loader, restate
+from oracle import make_golden, ref_loader, restate, synth
 
 pytestmark = pytest.mark.skipif(not ref_loader.available(), reason="/root/reference not present")
 
@@ -62,3 +64,45 @@ def test_contrastive_embed_vs_reference():
     assert torch.equal(torch.isinf(got), torch.isinf(ref))          # padding tokens and columns T..255 are -inf
     fin = torch.isfinite(ref)
     assert torch.equal(got[fin], ref[fin])                           # same fp32 product
+
+
+def test_atss_postprocess_vs_reference():
+    """ATSSPostProcessor.forward (rpn/inference.py:592-769) — sigmoid, MEAN token->class aggregation, 0.05 threshold,
+    per-level top-1000, BoxCoder.decode, clip, sqrt score, ml_nms over all levels, kthvalue cut at 100 — run from the
+    reference's own file on CPU, with only the compiled ml_nms kernel substituted (by the oracle's restatement of it, which
+    is pinned against the real kernel on the GPU).  The oracle's post-processing must produce the same detections."""
+    gen = synth.Gen(41)
+    sizes, strides = [(20, 28), (10, 14), (5, 7), (3, 4), (2, 2)], [8, 16, 32, 64, 128]
+    B, T, C = 2, 256, 80
+    img_w, img_h = 28 * 8, 20 * 8
+    _, _, pmap = synth.prompt(C, 2, T, gen)
+    inf = ref_loader.rpn_inference(lambda b, s, l, t: restate.ml_nms(b, s, l, t))
+    BoxList = sys.modules["maskrcnn_benchmark.structures.bounding_box"].BoxList
+    coder = sys.modules["maskrcnn_benchmark.modeling.box_coder"].BoxCoder(weights=(10.0, 10.0, 5.0, 5.0))
+    post = inf.ATSSPostProcessor(pre_nms_thresh=0.05, pre_nms_top_n=1000, nms_thresh=0.6, fpn_post_nms_top_n=100, min_size=0,
+                                 num_classes=C + 1, box_coder=coder, score_agg="MEAN")
+    regs = [gen.randn(B, 4, h, w) for h, w in sizes]
+    ctrs = [gen.randn(B, 1, h, w) for h, w in sizes]
+    dots = [gen.randn(B, h * w, T, scale=1.5) - 2.0 for h, w in sizes]          # ~6 % of (location, class) pairs pass 0.05
+    cls = [torch.zeros(B, C, h, w) for h, w in sizes]
+    anc = [restate.anchors_level(h, w, s, 8.0 * s) for (h, w), s in zip(sizes, strides)]
+    anchors = [[BoxList(a.clone(), (img_w, img_h), mode="xyxy") for a in anc] for _ in range(B)]
+    with torch.no_grad():
+        ref = post(regs, ctrs, anchors, cls, None, dots, pmap)
+    assert any(len(r) == 100 for r in ref) or all(len(r) > 0 for r in ref)
+    for b in range(B):
+        parts = [restate.atss_level_candidates(dots[l][b], regs[l][b].permute(1, 2, 0).reshape(-1, 4), ctrs[l][b].reshape(-1),
+                                               anc[l], pmap, C, img_w, img_h) for l in range(len(sizes))]
+        assert parts[0]["boxes"].shape[0] == 1000                                   # level 0 exercises the top-k
+        boxes = torch.cat([p["boxes"] for p in parts])
+        scores = torch.cat([p["scores"] for p in parts])
+        labels = torch.cat([p["labels"] for p in parts])
+        keep = restate.select_over_all_levels(boxes, scores, labels, 0.6, 100)
+        got = torch.cat([boxes[keep], scores[keep, None], labels[keep, None].float()], 1)
+        want = torch.cat([ref[b].bbox, ref[b].get_field("scores")[:, None], ref[b].get_field("labels")[:, None].float()], 1)
+        assert got.shape == want.shape, (got.shape, want.shape)
+
+        def canon(x):  # detection order is implementation-defined (topk(sorted=False)): compare as sets
+            key = x[:, 4].double() * 1e6 + x[:, 5].double() * 1e-3 + x[:, 0].double() * 1e-9
+            return x[torch.argsort(key)]
+        assert torch.allclose(canon(got), canon(want), rtol=1e-6, atol=1e-5)
