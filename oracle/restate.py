@@ -15,9 +15,11 @@ Pinning status (the reference ships no tests or golden vectors):
   * ml_nms and DCNv2 (incl. the DyConv[0] offset re-interpretation): the reference has no CPU implementation; they are
     pinned on the GPU against the reference's own CUDA kernels, compiled unmodified by oracle/build_ref.py into
     oracle/_ref/ (tests/test_ref_kernels_gpu.py: bit-identical kept sets, DCNv2 within fp32 noise).
-  * "parity unpinned": only the HF-BertLayer loop ordering of QVBertEncoder.forward (HF 5.x in this container no longer
-    has the classes the reference subclasses) -- restated from modeling_bert_new.py:545-639; the single
-    BERT layer it iterates IS pinned.
+  * QVBertEncoder.forward / QVBertModel.forward (GCP-before-layer-i ordering, masks, PreSelect before the encoder): run
+    from the reference's own classes with the twelve transformers-5 BertLayers (changed positional signature) swapped for
+    adapters around the reference's in-repo copy of the same layer (rpn/modeling_bert.py).
+  * "parity unpinned": nothing on the SURVEY §8 path; the only substituted pieces are the compiled kernels (pinned on the
+    GPU) and the HF-4 BertLayer class (replaced by the reference's in-repo copy of it).
 Paths are relative to the MQ-Det repository root.
 """
 import math

@@ -106,3 +106,102 @@ def test_atss_postprocess_vs_reference():
             key = x[:, 4].double() * 1e6 + x[:, 5].double() * 1e-3 + x[:, 0].double() * 1e-9
             return x[torch.argsort(key)]
         assert torch.allclose(canon(got), canon(want), rtol=1e-6, atol=1e-5)
+
+
+def test_qvbert_encoder_loop_vs_reference():
+    """QVBertEncoder.forward (modeling_bert_new.py:545-639) — WHICH layers get a GCP block, in which order, with which
+    masks — executed from the reference's own class.  transformers 5.x changed ``BertLayer.forward``'s positional
+    signature, so the twelve HF layers the encoder builds are replaced by adapters around the reference's in-repo BERT
+    copy (rpn/modeling_bert.py: the same post-LN layer, itself pinned by test_bert_layer_vs_reference); the GCP blocks,
+    the loop and the mask plumbing are the reference's."""
+    import torch.nn as nn
+    from transformers import BertConfig
+    m, rb = ref_loader.modeling_bert_new(), ref_loader.rpn_modeling_bert()
+    gen = synth.Gen(51)
+    sd = synth.qvbert_sd(gen)
+    config = BertConfig()
+    enc = m.QVBertEncoder(config, dim=768, cfg=make_golden.ref_cfg()).eval()
+    enc.gradient_checkpointing = False  # attribute of the transformers-4 BertEncoder base class the reference targets
+
+    class Layer(nn.Module):  # positional interface of the BertLayer the reference was written against
+        def __init__(self):
+            super().__init__()
+            self.attention = rb.BertAttention(config, False, False)
+            self.intermediate = rb.BertIntermediate(config)
+            self.output = rb.BertOutput(config)
+
+        def forward(self, h, attention_mask=None, head_mask=None, enc_h=None, enc_mask=None, past=None, output_attentions=False):
+            a = self.attention(h, attention_mask, None, output_attentions=False, past_key_value=None)[0]
+            return (self.output(self.intermediate(a), a),)
+
+    enc.layer = nn.ModuleList([Layer() for _ in range(config.num_hidden_layers)]).eval()
+    own = enc.state_dict()
+    enc.load_state_dict({k: sd["encoder." + k] for k in own}, strict=True)
+    B, T = 2, 256
+    _, _, pmap = synth.prompt(10, 2, T, gen)
+    _, vmask = synth.vision_queries(pmap, 5, T, 768, gen)
+    vmask = vmask.expand(B, -1, -1).clone()
+    vmask[1, 10:20] = 0
+    vq = gen.randn(B, vmask.shape[1], 768)
+    h = gen.randn(B, T, 768)
+    am = torch.ones(B, T)
+    am[0, 180:] = 0
+    ext = restate.extended_mask(am)
+    with torch.no_grad():
+        ref = enc(h, attention_mask=ext, vision=vq, vision_attention_mask=vmask).last_hidden_state
+        ref_text_only = enc(h, attention_mask=ext).last_hidden_state
+    got, got_text_only = h, h
+    for i in range(config.num_hidden_layers):
+        if i >= 6:
+            got = restate.gcp_block(got, vq, vmask, sd, f"encoder.qv_layer.{i - 6}.")
+        got = restate.bert_layer(got, ext, sd, f"encoder.layer.{i}.", 12)
+        got_text_only = restate.bert_layer(got_text_only, ext, sd, f"encoder.layer.{i}.", 12)
+    _close(got, ref)
+    _close(got_text_only, ref_text_only)
+    assert (ref - ref_text_only).abs().max().item() > 1e-3      # the vision queries do change the text stream
+
+
+def test_qvbert_model_vs_reference():
+    """QVBertModel.forward end to end (modeling_bert_new.py:690-848): embeddings, extended mask, PreSelect BEFORE the encoder,
+    the GCP/BERT loop — the reference's own class, with the twelve transformers-5 BertLayers swapped for adapters around
+    the reference's in-repo BERT layer (see test_qvbert_encoder_loop_vs_reference)."""
+    import torch.nn as nn
+    from transformers import BertConfig
+    m, rb = ref_loader.modeling_bert_new(), ref_loader.rpn_modeling_bert()
+    config = BertConfig()
+    gen = synth.Gen(52)
+    sd = synth.qvbert_sd(gen)
+    mod = m.QVBertModel(config, dim_t=768, dim_v=256, cfg=make_golden.ref_cfg(), add_pooling_layer=False).eval()
+    mod.encoder.gradient_checkpointing = False
+
+    class Layer(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.attention = rb.BertAttention(config, False, False)
+            self.intermediate = rb.BertIntermediate(config)
+            self.output = rb.BertOutput(config)
+
+        def forward(self, h, attention_mask=None, head_mask=None, enc_h=None, enc_mask=None, past=None, output_attentions=False):
+            a = self.attention(h, attention_mask, None, output_attentions=False, past_key_value=None)[0]
+            return (self.output(self.intermediate(a), a),)
+
+    mod.encoder.layer = nn.ModuleList([Layer() for _ in range(config.num_hidden_layers)]).eval()
+    mod.load_state_dict(sd, strict=True)
+    if not hasattr(mod.embeddings, "position_embedding_type"):  # transformers-4 BertEmbeddings attribute (BertConfig default)
+        mod.embeddings.position_embedding_type = "absolute"
+    if not hasattr(mod, "get_head_mask"):  # removed from PreTrainedModel in transformers 5
+        mod.get_head_mask = lambda head_mask, n, *a, **k: [None] * n
+    B, T = 2, 256
+    ids, am, pmap = synth.prompt(10, 2, T, gen)
+    ids, am = ids.expand(B, -1).contiguous(), am.expand(B, -1).clone()
+    am[1, 25:] = 0                                    # second caption truncated: padding inside the text stream
+    vis, vmask = synth.vision_queries(pmap, 5, T, 256, gen)
+    vis = vis.expand(B, -1, -1).contiguous()
+    vmask = vmask.expand(B, -1, -1).clone()
+    vmask[1, 5:10] = 0                                # one class of image 1 without exemplars
+    images = gen.randn(B, 300, 256)
+    with torch.no_grad():
+        ref = mod(input_ids=ids, attention_mask=am, vision=vis, images=images, vision_attention_mask=vmask)
+    got = restate.qvbert_model(ids, am, vis, images, vmask, sd)
+    _close(got["hidden"], ref.last_hidden_state)
+    assert len(ref["vision_query_gates"]["ffn_gates"]) == 6
