@@ -213,6 +213,90 @@ def rpn_inference(ml_nms_fn):
     return inf
 
 
+def vldyhead(dcn_fn):
+    """maskrcnn_benchmark/modeling/rpn/vldyhead.py (DyConv, BertEncoderLayer, VLFuse, VLDyHead) with the reference's own
+    dyrelu.py / se.py / misc.py / fuse_helper.py / rpn/modeling_bert.py / modeling_bert_new.py.  Not loadable pieces are
+    stubbed: the loss / anchor factories (never called by VLDyHead.forward), fbnet, clip_model, and the compiled
+    ``ModulatedDeformConv`` — a module with the same parameters whose forward calls
+    ``dcn_fn(x, offset, mask, weight, bias, stride)`` (the CUDA kernel itself is pinned on the GPU,
+    tests/test_ref_kernels_gpu.py)."""
+    import torch
+    from torch import nn
+    if "vldyhead" in _cache:
+        _cache["vldyhead"]._dcn_fn[0] = dcn_fn
+        return _cache["vldyhead"]
+    rpn_inference(lambda *a: (_ for _ in ()).throw(NotImplementedError))
+    fh = fuse_helper()
+    mbn = modeling_bert_new()
+    rmb = rpn_modeling_bert()
+    pkg = sys.modules["maskrcnn_benchmark"]
+    modeling = sys.modules["maskrcnn_benchmark.modeling"]
+    utils = sys.modules["maskrcnn_benchmark.utils"]
+    sys.modules["maskrcnn_benchmark.utils.fuse_helper"] = fh
+    utils.fuse_helper = fh
+    import transformers.modeling_utils as mu
+    import transformers.pytorch_utils as pu
+    if not hasattr(mu, "apply_chunking_to_forward"):
+        mu.apply_chunking_to_forward = pu.apply_chunking_to_forward
+    dcn_holder = [dcn_fn]
+
+    class ModulatedDeformConv(nn.Module):  # parameters / signature of layers/deform_conv.py:335-384, kernel substituted
+        def __init__(self, in_channels, out_channels, kernel_size, stride=1, padding=0, dilation=1, groups=1,
+                     deformable_groups=1, bias=True):
+            super().__init__()
+            assert kernel_size == 3 and padding == 1 and dilation == 1 and groups == 1 and deformable_groups == 1
+            self.stride = stride
+            self.weight = nn.Parameter(torch.zeros(out_channels, in_channels, 3, 3))
+            self.bias = nn.Parameter(torch.zeros(out_channels)) if bias else None
+
+        def forward(self, input, offset, mask):
+            return dcn_holder[0](input, offset, mask, self.weight, self.bias, self.stride)
+
+    layers = sys.modules["maskrcnn_benchmark.layers"]
+    layers.__path__ = []
+    dy = _load_file("maskrcnn_benchmark.layers.dyrelu", "maskrcnn_benchmark/layers/dyrelu.py")
+    se = _load_file("maskrcnn_benchmark.layers.se", "maskrcnn_benchmark/layers/se.py")
+    misc = _load_file("maskrcnn_benchmark.layers.misc", "maskrcnn_benchmark/layers/misc.py")
+    layers.DYReLU, layers.SELayer, layers.Scale = dy.DYReLU, se.SELayer, misc.Scale
+    layers.ModulatedDeformConv = ModulatedDeformConv
+    layers.NaiveSyncBatchNorm2d = layers.FrozenBatchNorm2d = nn.BatchNorm2d  # bn types the MQ configs never select
+
+    def stub(name, **attrs):
+        mod = types.ModuleType(name)
+        mod.__dict__.update(attrs)
+        sys.modules[name] = mod
+        return mod
+
+    unused = lambda *a, **k: None  # noqa: E731
+    stub("maskrcnn_benchmark.modeling.rpn.loss", make_atss_loss_evaluator=unused)
+    stub("maskrcnn_benchmark.modeling.rpn.anchor_generator", make_anchor_generator_complex=unused)
+    stub("maskrcnn_benchmark.modeling.backbone", __path__=[])
+    import math as _math
+    stub("maskrcnn_benchmark.modeling.backbone.fbnet", math=_math)  # vldyhead.py gets `math` through this star import
+    stub("maskrcnn_benchmark.engine", __path__=[])
+    stub("maskrcnn_benchmark.engine.inference", create_positive_map_label_to_token_from_positive_map=unused)
+    stub("maskrcnn_benchmark.modeling.language_backbone", __path__=[])
+    stub("maskrcnn_benchmark.modeling.language_backbone.clip_model", QuickGELU=nn.GELU, LayerNorm=nn.LayerNorm,
+         DropPath=sys.modules["timm.models.layers"].DropPath)
+    sys.modules["maskrcnn_benchmark.modeling.language_backbone.modeling_bert_new"] = mbn
+    sys.modules["maskrcnn_benchmark.modeling.rpn.modeling_bert"] = rmb
+    mod = _load_file("maskrcnn_benchmark.modeling.rpn.vldyhead", "maskrcnn_benchmark/modeling/rpn/vldyhead.py")
+    mod._dcn_fn = dcn_holder
+    _cache["vldyhead"] = mod
+    return mod
+
+
+def anchor_generator():
+    """maskrcnn_benchmark/modeling/rpn/anchor_generator.py (AnchorGenerator, make_anchor_generator_complex) on the
+    reference's own BoxList / ImageList."""
+    if "ag" not in _cache:
+        rpn_inference(lambda *a: None)  # installs the structures package (bounding_box, boxlist_ops)
+        st = sys.modules["maskrcnn_benchmark.structures"]
+        st.image_list = _load_file("maskrcnn_benchmark.structures.image_list", "maskrcnn_benchmark/structures/image_list.py")
+        _cache["ag"] = _load_file("ref_anchor_generator", "maskrcnn_benchmark/modeling/rpn/anchor_generator.py")
+    return _cache["ag"]
+
+
 def fpn():
     """maskrcnn_benchmark/modeling/backbone/fpn.py (FPN, LastLevelP6P7)."""
     if "fpn" not in _cache:

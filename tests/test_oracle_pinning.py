@@ -205,3 +205,115 @@ def test_qvbert_model_vs_reference():
     got = restate.qvbert_model(ids, am, vis, images, vmask, sd)
     _close(got["hidden"], ref.last_hidden_state)
     assert len(ref["vision_query_gates"]["ffn_gates"]) == 6
+
+
+def _dcn_stub(x, offset, mask, weight, bias, stride):
+    """Stands in for the compiled modulated_deform_conv (pinned against the real kernel on the GPU): the flat per-image
+    offset / (sigmoid-ed) mask buffers go to the oracle's restatement of the kernel, which indexes them with the OUTPUT
+    strides exactly like deform_conv_kernel_cuda.cu:605-618 (so the DyConv[0] re-interpretation happens here too)."""
+    B = x.shape[0]
+    return restate.dcn_v2(x, offset.reshape(B, -1), mask.reshape(B, -1), weight, bias, stride)
+
+
+def test_dyconv_vs_reference():
+    """DyConv.forward (vldyhead.py:205-247) from the reference's own class: offset conv, mask sigmoid, which level feeds
+    which deformable conv with which (re-interpreted) offsets, upsampling, GroupNorm, scale attention, DyReLU."""
+    vd = ref_loader.vldyhead(_dcn_stub)
+    gen = synth.Gen(61)
+    sd = synth.dyconv_sd(gen)
+    conv_func = lambda i, o, s: vd.Conv3x3Norm(i, o, s, deformable=True, bn_type=["gn", 16])  # noqa: E731
+    mod = vd.DyConv(256, 256, conv_func=conv_func, use_dyrelu=True, use_dyfuse=True, use_deform=True).eval()
+    mod.load_state_dict(sd, strict=True)
+    feats = [gen.randn(2, 256, h, w) for h, w in make_golden.LEVELS_SMALL]
+    with torch.no_grad():
+        ref = mod({"visual": feats, "lang": None})["visual"]
+    got = restate.dyconv(feats, sd)
+    for g, r in zip(got, ref):
+        _close(g, r, 1e-4)
+
+
+def _ref_head_cfg():
+    """mq-glip-t configuration of the head (configs/pretrain/mq-glip-t.yaml + config/defaults.py), incl. the keys only the
+    reference's constructor reads."""
+    import types
+    from mqdet_b200.config import mq_glip_t_cfg
+    cfg = mq_glip_t_cfg()
+    cfg.MODEL.DEVICE = "cpu"
+    for k, v in dict(USE_SYNCBN=False, USE_NSYNCBN=False, USE_CHECKPOINT=False, CONV_FUNC="", TOPK=9).items():
+        setattr(cfg.MODEL.DYHEAD, k, v)
+    for k, v in dict(USE_SHALLOW_CONTRASTIVE_LOSS=False, USE_BACKBONE_SHALLOW_CONTRASTIVE_LOSS=False, JOINT_EMB_DROPOUT=0.1,
+                     ADD_LINEAR_LAYER=False, USE_LAYER_SCALE=True, USE_CLASSIFICATION_LOSS=False, TOKEN_LOSS_WEIGHT=1.0,
+                     SHALLOW_CONTRASTIVE_LOSS_WEIGHT=1.0, MLM_LOSS_COEF=1.0, JOINT_OUT_SIZE=256, JOINT_MLP_LAYERS=2,
+                     DOT_PRODUCT_TOKEN_LOSS_WEIGHT=1.0, CONTRASTIVE_HIDDEN_DIM=64, CONTRASTIVE_ALIGN_LOSS_WEIGHT=1.0).items():
+        setattr(cfg.MODEL.DYHEAD.FUSE_CONFIG, k, v)
+    cfg.MODEL.RPN_ONLY = True
+    cfg.MODEL.CLIP = types.SimpleNamespace(WIDTH=512, VOCAB_SIZE=49408)
+    return cfg
+
+
+def test_vldyhead_vs_reference():
+    """The whole VL deep-fusion head from the reference's own VLDyHead.forward (vldyhead.py:769-900): 6 x [VLFuse (MHA-B
+    BiAttention) -> BertEncoderLayer -> DyConv], dot-product token head with its clamp, bbox (+ Scale) and centerness heads.
+    Substituted: the compiled DCNv2 kernel (oracle restatement, pinned on the GPU) and BertConfig.from_pretrained (no hub
+    access offline; bert-base-uncased == BertConfig()) and the transformers-4 `get_extended_attention_mask` helper."""
+    import contextlib
+    import io
+    from transformers import BertConfig
+    vd = ref_loader.vldyhead(_dcn_stub)
+
+    class _Cfg(BertConfig):
+        @classmethod
+        def from_pretrained(cls, name, **k):
+            assert name == "bert-base-uncased"
+            return BertConfig()
+
+    vd.BertConfig = _Cfg
+    # transformers-4 signature (mask, input_shape, device) and additive value of the PreTrainedModel helper the layer calls
+    # (:273); transformers 5 takes a dtype in third position.  -10000 vs finfo.min is immaterial: exp() underflows to 0
+    vd.BertEncoderLayer.get_extended_attention_mask = \
+        lambda self, mask, shape, device=None: (1.0 - mask[:, None, None, :].float()) * -10000.0
+    with contextlib.redirect_stdout(io.StringIO()):  # the constructor prints "EARLY FUSION ON" per layer
+        head = vd.VLDyHead(_ref_head_cfg()).eval()
+    gen = synth.Gen(62)
+    sd = synth.vldyhead_sd(gen)
+    head.load_state_dict(sd, strict=True)
+    B, T = 2, 256
+    feats = [gen.randn(B, 256, h, w) for h, w in make_golden.LEVELS_SMALL]
+    hidden = gen.randn(B, T, 768)
+    masks = torch.ones(B, T, dtype=torch.long)
+    masks[0, 120:] = 0
+    masks[1, 40:] = 0
+    lang = {"hidden": hidden.clone(), "masks": masks, "embedded": hidden.clone()}
+    with torch.no_grad():
+        out = head([f.clone() for f in feats], lang, embedding=lang["embedded"])
+    ref_logits, ref_bbox, ref_ctr, ref_dots = out[0], out[1], out[2], out[6]
+    got = restate.vl_dyhead(feats, hidden, masks, sd)
+    off = 0
+    for l, (h, w) in enumerate(make_golden.LEVELS_SMALL):
+        _close(got["dot_product_logits"][:, off:off + h * w], ref_dots[l], 2e-4)
+        _close(got["bbox_reg"][l], ref_bbox[l], 2e-4)
+        _close(got["centerness"][l], ref_ctr[l], 2e-4)
+        off += h * w
+    assert len(ref_logits) == 5 and out[3] is None and out[7] is None
+
+
+def test_anchors_vs_reference():
+    """make_anchor_generator_complex + AnchorGenerator.forward (anchor_generator.py:72-181) with the mq-glip-t RPN block
+    (sizes 64..1024, strides 8..128, one aspect ratio, one scale per octave): anchors and the visibility field of every
+    level, from the reference's own module, against the oracle's closed form and the visibility rule of mqdet_anchors."""
+    import types
+    ag = ref_loader.anchor_generator()
+    cfg = types.SimpleNamespace(MODEL=types.SimpleNamespace(RPN=types.SimpleNamespace(
+        ANCHOR_SIZES=(64, 128, 256, 512, 1024), ASPECT_RATIOS=(1.0,), ANCHOR_STRIDE=(8, 16, 32, 64, 128), STRADDLE_THRESH=0,
+        OCTAVE=2.0, SCALES_PER_OCTAVE=1, USE_FPN=True)))
+    gen = ag.make_anchor_generator_complex(cfg)
+    H, W = 160, 213                                             # true image size (the batch tensor is padded to 160 x 224)
+    sizes = make_golden.LEVELS_SMALL
+    il = sys.modules["maskrcnn_benchmark.structures.image_list"].ImageList(torch.zeros(1, 3, 160, 224), [(H, W)])
+    ref = gen(il, [torch.zeros(1, 256, h, w) for h, w in sizes])[0]
+    for (h, w), stride, size, bl in zip(sizes, (8, 16, 32, 64, 128), (64, 128, 256, 512, 1024), ref):
+        got = restate.anchors_level(h, w, stride, float(size))
+        assert torch.equal(got, bl.bbox)
+        assert bl.size == (W, H)
+        vis = (got[:, 0] >= 0) & (got[:, 1] >= 0) & (got[:, 2] < W) & (got[:, 3] < H)    # straddle_thresh = 0 (:96-110)
+        assert torch.equal(vis, bl.get_field("visibility").bool())
