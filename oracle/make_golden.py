@@ -32,6 +32,39 @@ def ref_cfg():
     return types.SimpleNamespace(VISION_QUERY=vq, MODEL=model)
 
 
+def ref_head_cfg():
+    """mq-glip-t configuration of the VL head (configs/pretrain/mq-glip-t.yaml + config/defaults.py) as an attribute
+    namespace, including the keys only the reference's constructors read."""
+    NS = types.SimpleNamespace
+    fuse = NS(EARLY_FUSE_ON=True, TYPE="MHA-B", JOINT_EMB_SIZE=256, JOINT_EMB_DROPOUT=0.1, JOINT_OUT_SIZE=256,
+              JOINT_MLP_LAYERS=2, USE_DOT_PRODUCT_TOKEN_LOSS=True, USE_FUSED_FEATURES_DOT_PRODUCT=True, USE_TOKEN_LOSS=False,
+              USE_CONTRASTIVE_ALIGN_LOSS=False, USE_SHALLOW_CONTRASTIVE_LOSS=False, USE_BACKBONE_SHALLOW_CONTRASTIVE_LOSS=False,
+              USE_CLASSIFICATION_LOSS=False, MLM_LOSS=False, MLM_LOSS_COEF=1.0, TOKEN_LOSS_WEIGHT=1.0,
+              DOT_PRODUCT_TOKEN_LOSS_WEIGHT=1.0, SHALLOW_CONTRASTIVE_LOSS_WEIGHT=1.0, CONTRASTIVE_ALIGN_LOSS_WEIGHT=1.0,
+              CONTRASTIVE_HIDDEN_DIM=64, ADD_LINEAR_LAYER=False, USE_LAYER_SCALE=True, STABLE_SOFTMAX_2D=False,
+              CLAMP_MIN_FOR_UNDERFLOW=True, CLAMP_MAX_FOR_OVERFLOW=True, CLAMP_BERTATTN_MIN_FOR_UNDERFLOW=True,
+              CLAMP_BERTATTN_MAX_FOR_OVERFLOW=True, CLAMP_DOT_PRODUCT=True, SEPARATE_BIDIRECTIONAL=False,
+              DO_LANG_PROJ_OUTSIDE_CHECKPOINT=False)
+    dyhead = NS(NUM_CLASSES=81, CHANNELS=256, NUM_CONVS=6, USE_GN=True, USE_SYNCBN=False, USE_NSYNCBN=False, USE_DYRELU=True,
+                USE_DFCONV=True, USE_DYFUSE=True, USE_CHECKPOINT=False, CONV_FUNC="", TOPK=9, PRIOR_PROB=0.01, LOG_SCALE=0.0,
+                SCORE_AGG="MEAN", FUSE_CONFIG=fuse)
+    model = NS(DEVICE="cpu", RPN_ONLY=True, BACKBONE=NS(OUT_CHANNELS=256), GROUP_NORM=NS(NUM_GROUPS=16), DYHEAD=dyhead,
+               LANGUAGE_BACKBONE=NS(LANG_DIM=768, MAX_QUERY_LEN=256, N_LAYERS=1, MODEL_TYPE="bert-base-uncased"),
+               RPN=NS(ASPECT_RATIOS=(1.0,), SCALES_PER_OCTAVE=1, RETURN_FUSED_FEATURES=False),
+               CLIP=NS(WIDTH=512, VOCAB_SIZE=49408))
+    return NS(MODEL=model, VISION_QUERY=ref_cfg().VISION_QUERY)
+
+
+def dcn_stub(x, offset, mask, weight, bias, stride):
+    """Stands in for the compiled modulated_deform_conv (pinned against the real kernel on the GPU,
+    tests/test_ref_kernels_gpu.py): the flat per-image offset / (sigmoid-ed) mask buffers go to the oracle's restatement of
+    the kernel, which indexes them with the OUTPUT strides exactly like deform_conv_kernel_cuda.cu:605-618 (so the DyConv[0]
+    offset re-interpretation happens here too)."""
+    from oracle import restate
+    B = x.shape[0]
+    return restate.dcn_v2(x, offset.reshape(B, -1), mask.reshape(B, -1), weight, bias, stride)
+
+
 LEVELS_SMALL = [(20, 28), (10, 14), (5, 7), (3, 4), (2, 2)]  # a 160x224 "image" through strides 8..128
 
 
@@ -87,6 +120,20 @@ def case_inputs(name):
         fsd = synth.fpn_sd(gen)
         img = gen.randn(2, 3, 150, 203, scale=1.0)  # not a multiple of 4/7/2: exercises every padding path
         return dict(sd=sd, fsd=fsd, img=img)
+    if name == "dyconv":
+        gen = synth.Gen(77)
+        sd = synth.dyconv_sd(gen)
+        return dict(sd=sd, feats=[gen.randn(2, 256, h, w) for h, w in LEVELS_SMALL])
+    if name == "vldyhead":
+        gen = synth.Gen(78)
+        sd = synth.vldyhead_sd(gen, 6)
+        B, T = 2, 256
+        feats = [gen.randn(B, 256, h, w) for h, w in LEVELS_SMALL]
+        hidden = gen.randn(B, T, 768)
+        masks = torch.ones(B, T, dtype=torch.long)
+        masks[0, 120:] = 0
+        masks[1, 31:] = 0
+        return dict(sd=sd, feats=feats, hidden=hidden, masks=masks)
     if name == "contrastive_embed":
         gen = synth.Gen(1239)
         B, Q, T, D = 2, 900, 195, 256
@@ -140,6 +187,25 @@ def run_reference(name):
         # wiring of BertEncoderLayer.forward (maskrcnn_benchmark/modeling/rpn/vldyhead.py:264-301)
         a = att(c["h"], ext, None, output_attentions=False, past_key_value=None)[0]
         return dict(h=outp(inter(a), a))
+    if name == "dyconv":
+        vd = rl.vldyhead(dcn_stub)
+        conv_func = lambda i, o, s: vd.Conv3x3Norm(i, o, s, deformable=True, bn_type=["gn", 16])  # noqa: E731
+        mod = vd.DyConv(256, 256, conv_func=conv_func, use_dyrelu=True, use_dyfuse=True, use_deform=True).eval()
+        mod.load_state_dict(c["sd"], strict=True)
+        out = mod({"visual": [f.clone() for f in c["feats"]], "lang": None})["visual"]
+        return dict(v=torch.cat([o.flatten(2).transpose(1, 2) for o in out], dim=1))
+    if name == "vldyhead":
+        import contextlib
+        import io
+        vd = rl.vldyhead(dcn_stub)
+        with contextlib.redirect_stdout(io.StringIO()):  # the constructor prints "EARLY FUSION ON" per layer
+            head = vd.VLDyHead(ref_head_cfg()).eval()
+        head.load_state_dict(c["sd"], strict=True)
+        lang = {"hidden": c["hidden"].clone(), "masks": c["masks"], "embedded": c["hidden"].clone()}
+        out = head([f.clone() for f in c["feats"]], lang, embedding=lang["embedded"])
+        flat = lambda xs: torch.cat([x.flatten(2).transpose(1, 2) for x in xs], dim=1)  # noqa: E731
+        return dict(logits=torch.cat(out[6], dim=1), hidden=lang["hidden"], bbox=flat(out[1]), ctr=flat(out[2]),
+                    per_level=(out[6], out[1], out[2]))
     if name == "contrastive_embed":
         mod = rl.gdino_utils().ContrastiveEmbed(max_text_len=256)
         return dict(logits=mod(c["x"], {"encoded_text": c["y"], "text_token_mask": c["mask"]}))
@@ -168,6 +234,8 @@ def run_reference(name):
 SUBSAMPLE = {"gcp_block": {"y": (4, 8), "s": (4, 8)}, "preselect": {"vision": (1, 8)},
              "bi_attention": {"v": (3, 4), "l": (4, 8)}, "bert_layer": {"h": (4, 8)},
              "contrastive_embed": {"logits": (9, 1)},
+             "dyconv": {"v": (3, 4)},
+             "vldyhead": {"logits": (3, 4), "hidden": (4, 8), "bbox": (3, 1), "ctr": (3, 1)},
              "swin_fpn": {"c3": (4, 2, 2), "c4": (4, 1, 1), "c5": (8, 1, 1), "p3": (4, 2, 2), "p4": (4, 1, 1), "p5": (4, 1, 1),
                           "p6": (2, 1, 1), "p7": (1, 1, 1)}}
 

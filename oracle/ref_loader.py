@@ -281,6 +281,21 @@ def vldyhead(dcn_fn):
     sys.modules["maskrcnn_benchmark.modeling.language_backbone.modeling_bert_new"] = mbn
     sys.modules["maskrcnn_benchmark.modeling.rpn.modeling_bert"] = rmb
     mod = _load_file("maskrcnn_benchmark.modeling.rpn.vldyhead", "maskrcnn_benchmark/modeling/rpn/vldyhead.py")
+    # environment adaptations (no arithmetic of the head is touched):
+    from transformers import BertConfig
+
+    class _OfflineBertConfig(BertConfig):  # VLDyHead.__init__ :600 asks the hub; bert-base-uncased == BertConfig()
+        @classmethod
+        def from_pretrained(cls, name, **k):
+            assert name == "bert-base-uncased"
+            return BertConfig()
+
+    mod.BertConfig = _OfflineBertConfig
+    # transformers-4 signature (mask, input_shape, device) and additive value of the PreTrainedModel helper that
+    # BertEncoderLayer.forward calls (:273); transformers 5 takes a dtype in third position.  -10000 vs finfo.min is
+    # immaterial: exp() underflows to exactly 0 either way.
+    mod.BertEncoderLayer.get_extended_attention_mask = \
+        lambda self, mask, shape, device=None: (1.0 - mask[:, None, None, :].float()) * -10000.0
     mod._dcn_fn = dcn_holder
     _cache["vldyhead"] = mod
     return mod

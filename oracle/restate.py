@@ -6,20 +6,17 @@ be loaded into the unmodified reference module, tests/test_oracle_pinning.py).  
 ``__graft_entry__.smoke()`` and ``bench.py``'s cpu_baseline / ``--impl reference`` leg may import this module; the
 product path (mqdet_b200/) never does.
 
-Pinning status (the reference ships no tests or golden vectors):
-  * GCP block + sparse attention + index table, PreSelect, BiAttention fusion, in-repo BERT layer, Swin-T + FPN
-    (bit-identical), ATSS post-processing (ATSSPostProcessor.forward with only the compiled ml_nms substituted),
-    GroundingDINO ContrastiveEmbed: pinned against the reference's own modules executed in the build
-    container (tests/test_oracle_pinning.py) and through the fixtures tests/golden/*.pt recorded from them by
-    oracle/make_golden.py (tests/test_oracle_golden.py).
-  * ml_nms and DCNv2 (incl. the DyConv[0] offset re-interpretation): the reference has no CPU implementation; they are
-    pinned on the GPU against the reference's own CUDA kernels, compiled unmodified by oracle/build_ref.py into
-    oracle/_ref/ (tests/test_ref_kernels_gpu.py: bit-identical kept sets, DCNv2 within fp32 noise).
-  * QVBertEncoder.forward / QVBertModel.forward (GCP-before-layer-i ordering, masks, PreSelect before the encoder): run
-    from the reference's own classes with the twelve transformers-5 BertLayers (changed positional signature) swapped for
-    adapters around the reference's in-repo copy of the same layer (rpn/modeling_bert.py).
-  * "parity unpinned": nothing on the SURVEY §8 path; the only substituted pieces are the compiled kernels (pinned on the
-    GPU) and the HF-4 BertLayer class (replaced by the reference's in-repo copy of it).
+Pinning status (the reference ships no tests or golden vectors) — every stage is checked against the
+reference's OWN code executed in the build container (tests/test_oracle_pinning.py, tests/test_host_cpu.py; loaders in
+oracle/ref_loader.py) and through fixtures recorded from it (tests/golden/*.pt by oracle/make_golden.py):
+  QuerySelector, PreSelect, GCP block + sparse attention + index table, QVBertEncoder / QVBertModel.forward, BiAttention,
+  BertEncoderLayer wiring, DyConv.forward, the whole VLDyHead.forward, ATSSPostProcessor.forward (+ BoxCoder, kthvalue cut),
+  AnchorGenerator, Swin-T + FPN (bit-identical), GroundingDINO ContrastiveEmbed, BoxList / to_image_list.
+Substitutions needed to run them on CPU here: the compiled ml_nms / DCNv2 kernels (-> this file's restatements, which are
+pinned on the GPU against the reference's CUDA sources built by oracle/build_ref.py, tests/test_ref_kernels_gpu.py) and
+transformers-4 API differences (BertLayer positional signature -> the reference's in-repo copy of the layer,
+get_extended_attention_mask, BertConfig.from_pretrained offline).  "parity unpinned": only the detector-level glue
+(flatten_fpn_features, label / location-map construction), restated from generalized_vl_rcnn_new.py:291-330.
 Paths are relative to the MQ-Det repository root.
 """
 import math

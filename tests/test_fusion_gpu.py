@@ -111,6 +111,11 @@ def test_dyconv(dev):
     x16 = restate.flatten_levels(feats).half().to(dev).contiguous()
     out = mod.forward_flat(x16, lv)
     assert_close(out, ref, 3e-3, "DyConv (fp16 activations)")
+    # the same inputs through the REFERENCE's own DyConv.forward (fixture recorded by oracle/make_golden.py)
+    from oracle import make_golden
+    fx = torch.load(os.path.join(ROOT, "tests", "golden", "dyconv.pt"))
+    g = make_golden.sub(out.float().cpu(), *fx["subsample"]["v"])
+    assert (g - fx["v"]).abs().max().item() <= 3e-3 * fx["v_absmax"] + 3e-3
     # reference-facing dict API
     o2 = mod({"visual": [f.to(dev) for f in feats], "lang": None})["visual"]
     assert [tuple(o.shape) for o in o2] == [tuple(f.shape) for f in feats]
@@ -159,4 +164,12 @@ def test_vldyhead_tower(dev):
     assert len(out) == 10 and len(out[6]) == 5 and out[6][0].shape == (B, 20 * 28, T)
     assert_close(torch.cat([o.cpu() for o in out[6]], 1), ref["dot_product_logits"], 1.5e-2, "tuple API logits", defer=bad)
     assert_close(restate.flatten_levels([o.cpu() for o in out[1]]), ref_reg, 2e-2, "tuple API bbox_reg", defer=bad)
+    # the same inputs through the REFERENCE's own VLDyHead.forward (fixture recorded by oracle/make_golden.py), same bounds
+    from oracle import make_golden
+    fx = torch.load(os.path.join(ROOT, "tests", "golden", "vldyhead.pt"))
+    for key, got_t, tol in (("logits", r["dot_product_logits"], 1.5e-2), ("hidden", r["hidden"], 4e-3)):
+        g = make_golden.sub(got_t.float().cpu(), *fx["subsample"][key])
+        err = (g - fx[key]).abs().max().item()
+        if err > tol * fx[key + "_absmax"] + tol:
+            bad.append(f"golden {key}: {err:.3e}")
     assert not bad, bad

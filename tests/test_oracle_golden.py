@@ -126,3 +126,20 @@ def test_contrastive_embed_golden():
     assert torch.equal(torch.isinf(got), torch.isinf(ref))
     fin = torch.isfinite(ref)
     assert (got[fin] - ref[fin]).abs().max().item() <= 2e-5 * fx["logits_absmax"]
+
+
+def test_dyconv_golden():
+    fx = torch.load(os.path.join(GOLD, "dyconv.pt"))
+    c = make_golden.case_inputs("dyconv")
+    _cmp(fx, "v", restate.flatten_levels(restate.dyconv(c["feats"], c["sd"])), 1e-4)
+
+
+def test_vldyhead_golden():
+    """Fixture recorded from the reference's own VLDyHead.forward (DCN kernel substituted): logits, language stream, boxes."""
+    fx = torch.load(os.path.join(GOLD, "vldyhead.pt"))
+    c = make_golden.case_inputs("vldyhead")
+    got = restate.vl_dyhead(c["feats"], c["hidden"], c["masks"], c["sd"])
+    _cmp(fx, "logits", got["dot_product_logits"], 2e-4)
+    _cmp(fx, "hidden", got["hidden"], 2e-4)
+    _cmp(fx, "bbox", restate.flatten_levels(got["bbox_reg"]), 2e-4)
+    _cmp(fx, "ctr", restate.flatten_levels(got["centerness"]), 2e-4)

@@ -207,94 +207,33 @@ def test_qvbert_model_vs_reference():
     assert len(ref["vision_query_gates"]["ffn_gates"]) == 6
 
 
-def _dcn_stub(x, offset, mask, weight, bias, stride):
-    """Stands in for the compiled modulated_deform_conv (pinned against the real kernel on the GPU): the flat per-image
-    offset / (sigmoid-ed) mask buffers go to the oracle's restatement of the kernel, which indexes them with the OUTPUT
-    strides exactly like deform_conv_kernel_cuda.cu:605-618 (so the DyConv[0] re-interpretation happens here too)."""
-    B = x.shape[0]
-    return restate.dcn_v2(x, offset.reshape(B, -1), mask.reshape(B, -1), weight, bias, stride)
+_dcn_stub = make_golden.dcn_stub
 
 
 def test_dyconv_vs_reference():
     """DyConv.forward (vldyhead.py:205-247) from the reference's own class: offset conv, mask sigmoid, which level feeds
     which deformable conv with which (re-interpreted) offsets, upsampling, GroupNorm, scale attention, DyReLU."""
-    vd = ref_loader.vldyhead(_dcn_stub)
-    gen = synth.Gen(61)
-    sd = synth.dyconv_sd(gen)
-    conv_func = lambda i, o, s: vd.Conv3x3Norm(i, o, s, deformable=True, bn_type=["gn", 16])  # noqa: E731
-    mod = vd.DyConv(256, 256, conv_func=conv_func, use_dyrelu=True, use_dyfuse=True, use_deform=True).eval()
-    mod.load_state_dict(sd, strict=True)
-    feats = [gen.randn(2, 256, h, w) for h, w in make_golden.LEVELS_SMALL]
-    with torch.no_grad():
-        ref = mod({"visual": feats, "lang": None})["visual"]
-    got = restate.dyconv(feats, sd)
-    for g, r in zip(got, ref):
-        _close(g, r, 1e-4)
-
-
-def _ref_head_cfg():
-    """mq-glip-t configuration of the head (configs/pretrain/mq-glip-t.yaml + config/defaults.py), incl. the keys only the
-    reference's constructor reads."""
-    import types
-    from mqdet_b200.config import mq_glip_t_cfg
-    cfg = mq_glip_t_cfg()
-    cfg.MODEL.DEVICE = "cpu"
-    for k, v in dict(USE_SYNCBN=False, USE_NSYNCBN=False, USE_CHECKPOINT=False, CONV_FUNC="", TOPK=9).items():
-        setattr(cfg.MODEL.DYHEAD, k, v)
-    for k, v in dict(USE_SHALLOW_CONTRASTIVE_LOSS=False, USE_BACKBONE_SHALLOW_CONTRASTIVE_LOSS=False, JOINT_EMB_DROPOUT=0.1,
-                     ADD_LINEAR_LAYER=False, USE_LAYER_SCALE=True, USE_CLASSIFICATION_LOSS=False, TOKEN_LOSS_WEIGHT=1.0,
-                     SHALLOW_CONTRASTIVE_LOSS_WEIGHT=1.0, MLM_LOSS_COEF=1.0, JOINT_OUT_SIZE=256, JOINT_MLP_LAYERS=2,
-                     DOT_PRODUCT_TOKEN_LOSS_WEIGHT=1.0, CONTRASTIVE_HIDDEN_DIM=64, CONTRASTIVE_ALIGN_LOSS_WEIGHT=1.0).items():
-        setattr(cfg.MODEL.DYHEAD.FUSE_CONFIG, k, v)
-    cfg.MODEL.RPN_ONLY = True
-    cfg.MODEL.CLIP = types.SimpleNamespace(WIDTH=512, VOCAB_SIZE=49408)
-    return cfg
+    c = make_golden.case_inputs("dyconv")
+    ref = make_golden.run_reference("dyconv")["v"]
+    _close(restate.flatten_levels(restate.dyconv(c["feats"], c["sd"])), ref, 1e-4)
 
 
 def test_vldyhead_vs_reference():
     """The whole VL deep-fusion head from the reference's own VLDyHead.forward (vldyhead.py:769-900): 6 x [VLFuse (MHA-B
     BiAttention) -> BertEncoderLayer -> DyConv], dot-product token head with its clamp, bbox (+ Scale) and centerness heads.
-    Substituted: the compiled DCNv2 kernel (oracle restatement, pinned on the GPU) and BertConfig.from_pretrained (no hub
-    access offline; bert-base-uncased == BertConfig()) and the transformers-4 `get_extended_attention_mask` helper."""
-    import contextlib
-    import io
-    from transformers import BertConfig
-    vd = ref_loader.vldyhead(_dcn_stub)
-
-    class _Cfg(BertConfig):
-        @classmethod
-        def from_pretrained(cls, name, **k):
-            assert name == "bert-base-uncased"
-            return BertConfig()
-
-    vd.BertConfig = _Cfg
-    # transformers-4 signature (mask, input_shape, device) and additive value of the PreTrainedModel helper the layer calls
-    # (:273); transformers 5 takes a dtype in third position.  -10000 vs finfo.min is immaterial: exp() underflows to 0
-    vd.BertEncoderLayer.get_extended_attention_mask = \
-        lambda self, mask, shape, device=None: (1.0 - mask[:, None, None, :].float()) * -10000.0
-    with contextlib.redirect_stdout(io.StringIO()):  # the constructor prints "EARLY FUSION ON" per layer
-        head = vd.VLDyHead(_ref_head_cfg()).eval()
-    gen = synth.Gen(62)
-    sd = synth.vldyhead_sd(gen)
-    head.load_state_dict(sd, strict=True)
-    B, T = 2, 256
-    feats = [gen.randn(B, 256, h, w) for h, w in make_golden.LEVELS_SMALL]
-    hidden = gen.randn(B, T, 768)
-    masks = torch.ones(B, T, dtype=torch.long)
-    masks[0, 120:] = 0
-    masks[1, 40:] = 0
-    lang = {"hidden": hidden.clone(), "masks": masks, "embedded": hidden.clone()}
-    with torch.no_grad():
-        out = head([f.clone() for f in feats], lang, embedding=lang["embedded"])
-    ref_logits, ref_bbox, ref_ctr, ref_dots = out[0], out[1], out[2], out[6]
-    got = restate.vl_dyhead(feats, hidden, masks, sd)
+    Substituted (oracle/ref_loader.py::vldyhead): the compiled DCNv2 kernel (oracle restatement, pinned on the GPU),
+    BertConfig.from_pretrained (no hub offline) and the transformers-4 `get_extended_attention_mask` helper."""
+    c = make_golden.case_inputs("vldyhead")
+    ref = make_golden.run_reference("vldyhead")
+    ref_dots, ref_bbox, ref_ctr = ref["per_level"]
+    got = restate.vl_dyhead(c["feats"], c["hidden"], c["masks"], c["sd"])
     off = 0
     for l, (h, w) in enumerate(make_golden.LEVELS_SMALL):
         _close(got["dot_product_logits"][:, off:off + h * w], ref_dots[l], 2e-4)
         _close(got["bbox_reg"][l], ref_bbox[l], 2e-4)
         _close(got["centerness"][l], ref_ctr[l], 2e-4)
         off += h * w
-    assert len(ref_logits) == 5 and out[3] is None and out[7] is None
+    _close(got["hidden"], ref["hidden"], 2e-4)
 
 
 def test_anchors_vs_reference():
