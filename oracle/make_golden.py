@@ -55,6 +55,37 @@ def ref_head_cfg():
     return NS(MODEL=model, VISION_QUERY=ref_cfg().VISION_QUERY)
 
 
+def ref_detector_cfg():
+    """ref_head_cfg() + the keys the detector, the anchor generator and the post-processor read (mq-glip-t.yaml)."""
+    NS = types.SimpleNamespace
+    cfg = ref_head_cfg()
+    m = cfg.MODEL
+    m.SWINT = NS(VERSION="v1")
+    m.LANGUAGE_BACKBONE.PAD_MAX = True
+    m.LANGUAGE_BACKBONE.MASK_SPECIAL = False
+    m.LANGUAGE_BACKBONE.USE_CHECKPOINT = False
+    m.RPN = NS(ASPECT_RATIOS=(1.0,), SCALES_PER_OCTAVE=1, RETURN_FUSED_FEATURES=False, ANCHOR_SIZES=(64, 128, 256, 512, 1024),
+               ANCHOR_STRIDE=(8, 16, 32, 64, 128), STRADDLE_THRESH=0, OCTAVE=2.0, USE_FPN=True)
+    m.ATSS = NS(INFERENCE_TH=0.05, INFERENCE_TH_TRAIN=0.0, PRE_NMS_TOP_N=1000, PRE_NMS_TOP_N_TRAIN=3000, NMS_TH=0.6,
+                DETECTIONS_PER_IMG=100, POST_NMS_TOP_N_TRAIN=1000, NUM_CLASSES=81)
+    m.ROI_MASK_HEAD = NS(PREDICTOR="MaskRCNNC4Predictor")
+    cfg.TEST = NS(USE_MULTISCALE=False, MDETR_STYLE_AGGREGATE_CLASS_NUM=-1)
+    cfg.GLIPKNOW = NS(PARALLEL_LANGUAGE_INPUT=False)
+    cfg.DATASETS = NS(ONE_HOT=False)
+    vq = cfg.VISION_QUERY
+    for k, v in dict(QUERY_BANK_PATH="", LEARNABLE_BANK=False, ADD_VISION_LAYER=False, PURE_TEXT_RATE=0.0, RANDOM_KSHOT=False,
+                     MASK_DURING_INFERENCE=False, GATE_REGULARIZATION=False, GATE_REGULARIZATION_SCALE=1.0).items():
+        setattr(vq, k, v)
+    return cfg
+
+
+def canonical_detections(d):
+    """[n, 6] (x1, y1, x2, y2, score, label) sorted by (score, label, x1): the reference's detection order depends on
+    topk(sorted=False), so detections are compared as sets."""
+    key = d[:, 4].double() * 1e6 + d[:, 5].double() * 1e-3 + d[:, 0].double() * 1e-9
+    return d[torch.argsort(key)]
+
+
 def dcn_stub(x, offset, mask, weight, bias, stride):
     """Stands in for the compiled modulated_deform_conv (pinned against the real kernel on the GPU,
     tests/test_ref_kernels_gpu.py): the flat per-image offset / (sigmoid-ed) mask buffers go to the oracle's restatement of
@@ -134,6 +165,12 @@ def case_inputs(name):
         masks[0, 120:] = 0
         masks[1, 31:] = 0
         return dict(sd=sd, feats=feats, hidden=hidden, masks=masks)
+    if name == "detector":
+        gen = synth.Gen(71)
+        sd = synth.detector_sd(gen, bias0=-1.0)  # enough (location, class) pairs above 0.05 to hit the top-k and the NMS
+        ids, am, pmap = synth.prompt(12, 2, 256, gen)
+        bank = synth.query_bank(pmap, 5, gen)
+        return dict(sd=sd, ids=ids, am=am, pmap=pmap, bank=bank, img=synth.images(gen, 1, 160, 224), size=(160, 224))
     if name == "contrastive_embed":
         gen = synth.Gen(1239)
         B, Q, T, D = 2, 900, 195, 256
@@ -206,6 +243,21 @@ def run_reference(name):
         flat = lambda xs: torch.cat([x.flatten(2).transpose(1, 2) for x in xs], dim=1)  # noqa: E731
         return dict(logits=torch.cat(out[6], dim=1), hidden=lang["hidden"], bbox=flat(out[1]), ctr=flat(out[2]),
                     per_level=(out[6], out[1], out[2]))
+    if name == "detector":
+        import numpy as np
+        from oracle import restate
+        det = rl.detector(ref_detector_cfg(), dcn_stub, lambda b, s, l, t: restate.ml_nms(b, s, l, t), (c["ids"], c["am"]))
+        full = dict(c["sd"])
+        for k, v in det.state_dict().items():  # index / anchor buffers are not parameters
+            if k not in full:
+                assert k.endswith("relative_position_index") or "cell_anchors" in k, k
+                full[k] = v
+        det.load_state_dict(full, strict=True)
+        det.query_selector.query_bank = {k: v.clone() for k, v in c["bank"].items()}
+        np.random.seed(0)
+        bl = det(c["img"], captions=["a synthetic caption"], positive_map=c["pmap"])[0]
+        d = torch.cat([bl.bbox, bl.get_field("scores")[:, None], bl.get_field("labels")[:, None].float()], 1)
+        return dict(det=canonical_detections(d), boxlist=bl)
     if name == "contrastive_embed":
         mod = rl.gdino_utils().ContrastiveEmbed(max_text_len=256)
         return dict(logits=mod(c["x"], {"encoded_text": c["y"], "text_token_mask": c["mask"]}))
@@ -235,6 +287,7 @@ SUBSAMPLE = {"gcp_block": {"y": (4, 8), "s": (4, 8)}, "preselect": {"vision": (1
              "bi_attention": {"v": (3, 4), "l": (4, 8)}, "bert_layer": {"h": (4, 8)},
              "contrastive_embed": {"logits": (9, 1)},
              "dyconv": {"v": (3, 4)},
+             "detector": {"det": (1, 1)},
              "vldyhead": {"logits": (3, 4), "hidden": (4, 8), "bbox": (3, 1), "ctr": (3, 1)},
              "swin_fpn": {"c3": (4, 2, 2), "c4": (4, 1, 1), "c5": (8, 1, 1), "p3": (4, 2, 2), "p4": (4, 1, 1), "p5": (4, 1, 1),
                           "p6": (2, 1, 1), "p7": (1, 1, 1)}}

@@ -225,7 +225,8 @@ def vldyhead(dcn_fn):
     if "vldyhead" in _cache:
         _cache["vldyhead"]._dcn_fn[0] = dcn_fn
         return _cache["vldyhead"]
-    rpn_inference(lambda *a: (_ for _ in ()).throw(NotImplementedError))
+    if "rpn_inf" not in _cache:
+        rpn_inference(lambda *a: (_ for _ in ()).throw(NotImplementedError))
     fh = fuse_helper()
     mbn = modeling_bert_new()
     rmb = rpn_modeling_bert()
@@ -305,11 +306,119 @@ def anchor_generator():
     """maskrcnn_benchmark/modeling/rpn/anchor_generator.py (AnchorGenerator, make_anchor_generator_complex) on the
     reference's own BoxList / ImageList."""
     if "ag" not in _cache:
-        rpn_inference(lambda *a: None)  # installs the structures package (bounding_box, boxlist_ops)
+        if "rpn_inf" not in _cache:
+            rpn_inference(lambda *a: None)  # installs the structures package (bounding_box, boxlist_ops)
         st = sys.modules["maskrcnn_benchmark.structures"]
         st.image_list = _load_file("maskrcnn_benchmark.structures.image_list", "maskrcnn_benchmark/structures/image_list.py")
         _cache["ag"] = _load_file("ref_anchor_generator", "maskrcnn_benchmark/modeling/rpn/anchor_generator.py")
     return _cache["ag"]
+
+
+def detector(cfg, dcn_fn, ml_nms_fn, tokenized):
+    """An instance of the reference's ``GeneralizedVLRCNN_New`` (modeling/detector/generalized_vl_rcnn_new.py) assembled from
+    the reference's own parts on CPU: Swin-T + FPN, QuerySelector, ``BertEncoder`` -> ``QVBertModel``, ``VLDyHeadModule``
+    (VLDyHead + AnchorGenerator + ATSSPostProcessor).  ``__init__`` is bypassed (it needs yacs registries, the HF hub and
+    the compiled ``_C``); the attributes it would create are set here with the same classes and the mq-glip-t configuration.
+    Substitutions: the two compiled kernels (``dcn_fn``, ``ml_nms_fn``), the transformers-4 shims of ``vldyhead`` /
+    ``QVBertModel`` (see there), and the tokenizer (no vocabulary offline): ``tokenized`` = (input_ids, attention_mask)
+    is what ``batch_encode_plus`` returns for any caption."""
+    import torch
+    from collections import OrderedDict
+    from torch import nn
+    from transformers import BertConfig
+    vd = vldyhead(dcn_fn)
+    ag = anchor_generator()
+    rpn_inference(ml_nms_fn)  # last: (re)binds the NMS substitute
+    vd.make_anchor_generator_complex = ag.make_anchor_generator_complex
+    mbn, rmb = modeling_bert_new(), rpn_modeling_bert()
+    sw, fp, qs = swint(), fpn(), query_selector()
+    modeling = sys.modules["maskrcnn_benchmark.modeling"]
+
+    def stub(name, **attrs):
+        mod = sys.modules.get(name) or types.ModuleType(name)
+        mod.__dict__.update(attrs)
+        sys.modules[name] = mod
+        return mod
+
+    unused = lambda *a, **k: None  # noqa: E731
+    if "det" not in _cache:
+        stub("maskrcnn_benchmark.modeling.poolers", CustomPooler=object, Pooler=object)
+        stub("maskrcnn_benchmark.modeling.backbone", build_backbone=unused)
+        stub("maskrcnn_benchmark.modeling.rpn", build_rpn=unused)
+        stub("maskrcnn_benchmark.modeling.roi_heads", build_roi_heads=unused)
+        stub("maskrcnn_benchmark.modeling.query_selector", build_query_selector=unused)
+        stub("maskrcnn_benchmark.modeling.language_backbone", build_language_backbone=unused)
+        stub("maskrcnn_benchmark.modeling.detector", __path__=[])
+        _cache["bmn"] = _load_file("maskrcnn_benchmark.modeling.language_backbone.bert_model_new",
+                                   "maskrcnn_benchmark/modeling/language_backbone/bert_model_new.py")
+        _cache["det"] = _load_file("maskrcnn_benchmark.modeling.detector.generalized_vl_rcnn_new",
+                                   "maskrcnn_benchmark/modeling/detector/generalized_vl_rcnn_new.py")
+    det_mod, bmn = _cache["det"], _cache["bmn"]
+    config = BertConfig()
+
+    # ---- language backbone: BertEncoder wrapper around QVBertModel (12 layer adapters, see tests) ----
+    qv = mbn.QVBertModel(config, dim_t=768, dim_v=256, cfg=cfg, add_pooling_layer=False)
+    qv.encoder.gradient_checkpointing = False
+
+    class Layer(nn.Module):  # positional interface of the transformers-4 BertLayer, built from the reference's in-repo copy
+        def __init__(self):
+            super().__init__()
+            self.attention = rmb.BertAttention(config, False, False)
+            self.intermediate = rmb.BertIntermediate(config)
+            self.output = rmb.BertOutput(config)
+
+        def forward(self, h, attention_mask=None, head_mask=None, enc_h=None, enc_mask=None, past=None, output_attentions=False):
+            a = self.attention(h, attention_mask, None, output_attentions=False, past_key_value=None)[0]
+            return (self.output(self.intermediate(a), a),)
+
+    qv.encoder.layer = nn.ModuleList([Layer() for _ in range(config.num_hidden_layers)])
+    if not hasattr(qv.embeddings, "position_embedding_type"):
+        qv.embeddings.position_embedding_type = "absolute"
+    if not hasattr(qv, "get_head_mask"):
+        qv.get_head_mask = lambda head_mask, n, *a, **k: [None] * n
+    body = bmn.BertEncoder.__new__(bmn.BertEncoder)
+    nn.Module.__init__(body)
+    body.cfg, body.bert_name, body.model, body.language_dim, body.num_layers = cfg, "bert-base-uncased", qv, 768, 1
+    lang = nn.Sequential(OrderedDict([("body", body)]))
+
+    # ---- visual backbone: Swin-T -> FPN (+P6, P7), as backbone/__init__.py:37-80 assembles it ----
+    body_v = sw.SwinTransformer(embed_dim=96, depths=[2, 2, 6, 2], num_heads=[3, 6, 12, 24], window_size=7, drop_path_rate=0.0,
+                                frozen_stages=-1, use_checkpoint=False)
+    conv_block = lambda i, o, k, s=1: nn.Conv2d(i, o, k, s, padding=(k - 1) // 2)  # noqa: E731
+    fpn_v = fp.FPN([0, 192, 384, 768], 256, conv_block, top_blocks=fp.LastLevelP6P7(256, 256))
+    backbone = nn.Sequential(OrderedDict([("body", body_v), ("fpn", fpn_v)]))
+
+    # ---- head module ----
+    import contextlib
+    import io
+    with contextlib.redirect_stdout(io.StringIO()):
+        rpn = vd.VLDyHeadModule(cfg)
+
+    class Tok:  # what batch_encode_plus(...) returns, for any caption
+        input_ids, attention_mask = tokenized
+        special_tokens_mask = 1 - tokenized[1]
+
+        def to(self, device):
+            return self
+
+    class Tokenizer:
+        mask_token_id, pad_token_id = 103, 0
+
+        def batch_encode_plus(self, captions, **kw):
+            return Tok()
+
+    det = det_mod.GeneralizedVLRCNN_New.__new__(det_mod.GeneralizedVLRCNN_New)
+    nn.Module.__init__(det)
+    det.cfg, det.backbone, det.language_backbone, det.rpn, det.roi_heads = cfg, backbone, lang, rpn, None
+    det.query_selector = qs.QuerySelector(cfg)
+    det.tokenizer = Tokenizer()
+    det.pool = nn.AvgPool2d(2)
+    det.use_mlm_loss, det.mlm_loss_for_only_positives, det.force_boxes = False, False, False
+    for flag in ("freeze_backbone", "freeze_fpn", "freeze_rpn", "linear_prob", "freeze_cls_logits", "add_linear_layer",
+                 "freeze_language_backbone"):  # read by the train()/eval() override (:188-229); all off at inference
+        setattr(det, flag, False)
+    det.eval()  # the reference's train() override returns None: no chaining
+    return det
 
 
 def fpn():

@@ -11,12 +11,14 @@ reference's OWN code executed in the build container (tests/test_oracle_pinning.
 oracle/ref_loader.py) and through fixtures recorded from it (tests/golden/*.pt by oracle/make_golden.py):
   QuerySelector, PreSelect, GCP block + sparse attention + index table, QVBertEncoder / QVBertModel.forward, BiAttention,
   BertEncoderLayer wiring, DyConv.forward, the whole VLDyHead.forward, ATSSPostProcessor.forward (+ BoxCoder, kthvalue cut),
-  AnchorGenerator, Swin-T + FPN (bit-identical), GroundingDINO ContrastiveEmbed, BoxList / to_image_list.
+  AnchorGenerator, Swin-T + FPN (bit-identical), GroundingDINO ContrastiveEmbed, BoxList / to_image_list, and the whole
+  GeneralizedVLRCNN_New.forward.
 Substitutions needed to run them on CPU here: the compiled ml_nms / DCNv2 kernels (-> this file's restatements, which are
 pinned on the GPU against the reference's CUDA sources built by oracle/build_ref.py, tests/test_ref_kernels_gpu.py) and
 transformers-4 API differences (BertLayer positional signature -> the reference's in-repo copy of the layer,
-get_extended_attention_mask, BertConfig.from_pretrained offline).  "parity unpinned": only the detector-level glue
-(flatten_fpn_features, label / location-map construction), restated from generalized_vl_rcnn_new.py:291-330.
+get_extended_attention_mask, BertConfig.from_pretrained offline, tokenizer).  The composition itself (`detector` below) is
+pinned against one whole eval forward of the reference's GeneralizedVLRCNN_New assembled from its own parts
+(test_detector_vs_reference; fixture tests/golden/detector.pt).  "parity unpinned": nothing on the SURVEY §8 path.
 Paths are relative to the MQ-Det repository root.
 """
 import math

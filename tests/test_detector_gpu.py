@@ -61,6 +61,34 @@ def test_detector_forward(dev):
         assert (r.bbox[:, 0] >= 0).all() and (r.bbox[:, 2] <= w - 1).all() and (r.bbox[:, 3] <= h - 1).all()
 
 
+def test_detector_vs_reference_golden(dev):
+    """The CUDA detector against detections recorded from the REFERENCE's own GeneralizedVLRCNN_New.forward executed on CPU
+    (tests/golden/detector.pt, oracle/make_golden.py): whole model, 12-class prompt, K = 5, one 160 x 224 image."""
+    import os
+    from util import ROOT
+    from mqdet_b200.config import mq_glip_t_cfg
+    from mqdet_b200.modeling.detector.generalized_vl_rcnn_new import GeneralizedVLRCNN_New
+    from mqdet_b200.structures.image_list import ImageList
+    from oracle import make_golden
+    c = make_golden.case_inputs("detector")
+    want = torch.load(os.path.join(ROOT, "tests", "golden", "detector.pt"))["det"]
+    model = GeneralizedVLRCNN_New(mq_glip_t_cfg())
+    full = dict(c["sd"])
+    for k, v in model.state_dict().items():
+        if k.endswith("relative_position_index"):
+            full[k] = v
+    model = load_sd(model, full).to(dev).eval()
+    model.query_selector.set_query_bank(c["bank"])
+    res = model(ImageList(c["img"].to(dev), [c["size"]]), captions={"input_ids": c["ids"], "attention_mask": c["am"]},
+                positive_map=c["pmap"])
+    r = res[0].to("cpu")
+    assert len(r) >= want.shape[0] - 5
+    iou = _iou(want[:, :4], r.bbox)
+    same = want[:, 5, None] == r.get_field("labels")[None].float()
+    matched = ((iou > 0.9) & same & ((want[:, 4, None] - r.get_field("scores")[None]).abs() < 2e-2)).any(1)
+    assert matched.float().mean().item() >= 0.85, f"only {matched.float().mean().item():.2f} of the reference detections matched"
+
+
 def test_detector_rejects_cpu_and_strings():
     from mqdet_b200._lib import MqdetError
     from mqdet_b200.config import mq_glip_t_cfg

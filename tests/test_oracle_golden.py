@@ -143,3 +143,16 @@ def test_vldyhead_golden():
     _cmp(fx, "hidden", got["hidden"], 2e-4)
     _cmp(fx, "bbox", restate.flatten_levels(got["bbox_reg"]), 2e-4)
     _cmp(fx, "ctr", restate.flatten_levels(got["centerness"]), 2e-4)
+
+
+def test_detector_golden():
+    """Detections recorded from the reference's own GeneralizedVLRCNN_New.forward (whole model, CPU)."""
+    fx = torch.load(os.path.join(GOLD, "detector.pt"))
+    c = make_golden.case_inputs("detector")
+    got = restate.detector(c["img"], c["size"], c["ids"], c["am"], c["pmap"], c["bank"], c["sd"], K=5, num_classes=80)
+    boxes, scores, labels = got["detections"][0]
+    have = make_golden.canonical_detections(torch.cat([boxes, scores[:, None], labels[:, None].float()], 1))
+    want = fx["det"]
+    assert have.shape == want.shape
+    assert torch.equal(want[:, 5], have[:, 5])
+    assert torch.allclose(want[:, 4], have[:, 4], rtol=2e-4, atol=2e-5) and torch.allclose(want[:, :4], have[:, :4], rtol=0, atol=5e-2)

@@ -2,6 +2,8 @@
 /root/reference (full tensors, not the committed subsamples).  Skipped where the reference is absent (GPU box)."""
 import sys
 
+import numpy as np
+
 import pytest
 import torch
 
@@ -256,3 +258,20 @@ def test_anchors_vs_reference():
         assert bl.size == (W, H)
         vis = (got[:, 0] >= 0) & (got[:, 1] >= 0) & (got[:, 2] < W) & (got[:, 3] < H)    # straddle_thresh = 0 (:96-110)
         assert torch.equal(vis, bl.get_field("visibility").bool())
+
+
+def test_detector_vs_reference():
+    """SURVEY.md §8 a17 (and a2): one whole eval forward of the reference's own ``GeneralizedVLRCNN_New.forward``
+    (generalized_vl_rcnn_new.py:307-519) on CPU — Swin-T + FPN, label / location maps, QuerySelector,
+    flatten_fpn_features, BertEncoder -> QVBertModel (PreSelect + GCP), VLDyHeadModule (tower, dot-product head, anchors,
+    ATSS post-processing) -> BoxList — against ``restate.detector``.  Substitutions as documented in
+    oracle/ref_loader.py::detector (two compiled kernels, transformers-4 shims, tokenizer)."""
+    c = make_golden.case_inputs("detector")
+    want = make_golden.run_reference("detector")["det"]
+    got = restate.detector(c["img"], c["size"], c["ids"], c["am"], c["pmap"], c["bank"], c["sd"], K=5, num_classes=80)
+    boxes, scores, labels = got["detections"][0]
+    have = make_golden.canonical_detections(torch.cat([boxes, scores[:, None], labels[:, None].float()], 1))
+    assert have.shape == want.shape and want.shape[0] > 10, (have.shape, want.shape)
+    assert torch.equal(want[:, 5], have[:, 5])                                       # same labels
+    assert torch.allclose(want[:, 4], have[:, 4], rtol=2e-4, atol=2e-5)              # scores
+    assert torch.allclose(want[:, :4], have[:, :4], rtol=0, atol=5e-2)               # boxes (pixels; image is 224 x 160)
