@@ -55,3 +55,37 @@ def test_no_cpu_fallback():
     from mqdet_b200._lib import MqdetError
     with pytest.raises(MqdetError):
         ops.layernorm(torch.zeros(2, 8), torch.ones(8), torch.zeros(8))
+
+
+def test_argument_validation_errors_without_gpu():
+    """Every entry point validates its arguments BEFORE touching CUDA: a bad call returns a negative code and a message in
+    mqdet_last_error() (mirrors the reference's AT_ERROR / TORCH_CHECK behaviour), also on a machine without a GPU."""
+    import ctypes
+    from mqdet_b200 import _lib
+    lib = _lib.load()
+    nul = ctypes.c_void_p(0)
+    one = ctypes.c_void_p(16)  # never dereferenced: the checks fail first
+
+    def expect(rc, needle):
+        assert rc < 0
+        msg = lib.mqdet_last_error().decode()
+        assert needle in msg, msg
+
+    g = _lib.GemmArgs()
+    expect(lib.mqdet_gemm_f16(ctypes.byref(g), 0, nul), "null pointer")
+    g.A = g.B = g.C = 16
+    g.M, g.N, g.K = 4, 4, 0
+    expect(lib.mqdet_gemm_f16(ctypes.byref(g), 0, nul), "empty problem")
+    g.K, g.lda, g.ldb, g.ldc, g.nb1, g.nb2 = 12, 12, 12, 4, 1, 1   # K % 8 != 0
+    expect(lib.mqdet_gemm_f16(ctypes.byref(g), 0, nul), "multiples of 8")
+    g.K = g.lda = g.ldb = 16
+    expect(lib.mqdet_gemm_f16(ctypes.byref(g), 7, nul), "unknown impl")
+    expect(lib.mqdet_layernorm(nul, 0, 8, nul, nul, 1e-5, 1, 8, nul, nul, 8, 0, nul), "null pointer")
+    expect(lib.mqdet_colsoftmax_transposed(one, 1, 10, 12, one, 16, one, nul), "T%8")          # T % 8 != 0
+    expect(lib.mqdet_colstats_rowsoftmax(one, 1, 10, 128, nul, 1, 0.0, 0.0, one, nul), "T must be 256")
+    expect(lib.mqdet_swin_window_attn(one, one, one, 1, 14, 14, 3, 12, 0, 1.0, one, nul), "window 7 only")
+    expect(lib.mqdet_dcn_cols(one, nul, 0, one, 5, 1, 128, 1, one, nul), "C must be 256")
+    expect(lib.mqdet_conv3x3_small(one, one, one, one, 5, 1, 256, 40, one, 64, nul), "O <= 32")
+    expect(lib.mqdet_biattn_text(one, 8, 8, 8, one, 8, 8, 8, one, 8, 8, 8, one, 0.0, one, 8, 8, 8, 1, 1, 256, 100, 104, 128,
+                                 nul), "head dim must be 256")
+    expect(lib.mqdet_contrastive_mask(one, one, 1, 1, 300, 256, nul), "bad args")                # Tmax < T
