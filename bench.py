@@ -190,8 +190,9 @@ def main():
     for _ in range(args.warmup):
         step(img_dev)
     barrier()
-    clocks = ClockSampler(local)
-    clocks.start()
+    clocks = ClockSampler(local)  # rank 0 samples its own GPU (one nvidia-smi poller per node is enough)
+    if rank == 0:
+        clocks.start()
     ops.launch_count = 0
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     barrier()
@@ -202,7 +203,7 @@ def main():
         ev[i][1].record()
     barrier()
     launches = ops.launch_count - 0
-    clk = clocks.stop()
+    clk = clocks.stop() if rank == 0 else None
     ms = sum(a.elapsed_time(b) for a, b in ev) / args.steps
     t = torch.tensor([ms], device=dev)
     if world > 1:
