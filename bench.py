@@ -81,7 +81,7 @@ class ClockSampler:
 
 def build_inputs(B, seed):
     import torch
-    from oracle import synth  # synthetic weights/inputs generator (test infrastructure; not the measured path)
+    from tools import synth  # synthetic weights/inputs generator (not the measured path)
     gen = synth.Gen(seed)
     ids, am, pmap = synth.prompt(NCLS, 2, 256, gen)
     bank = synth.query_bank(pmap, KQ, gen)
@@ -92,7 +92,8 @@ def build_inputs(B, seed):
 def run_reference(args):
     """CPU arm: the oracle restatement of the reference forward on the host cores, one image per step."""
     import torch
-    from oracle import restate, synth
+    from oracle import restate
+    from tools import synth
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -146,7 +147,7 @@ def main():
     from mqdet_b200.config import mq_glip_t_cfg
     from mqdet_b200.modeling.detector.generalized_vl_rcnn_new import GeneralizedVLRCNN_New
     from mqdet_b200.structures.image_list import ImageList
-    from oracle import synth
+    from tools import synth
 
     _lib.load()
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -178,7 +179,7 @@ def main():
     def step(x):
         out = model.forward_device(ImageList(x, sizes), caps, pmap)
         # the ONE collective of the data path: fixed-shape per-image detections over NCCL / NVLink (identity at N = 1)
-        out["det_all"], out["num_all"] = parallel.all_gather_detections(out["det"], out["num"])
+        out["det_all"] = parallel.all_gather_packed(out["det_packed"])  # [world*B, max_out+1, 6]: detections + count row
         return out
 
     def barrier():
@@ -216,8 +217,7 @@ def main():
     # region.  The upload of step s+1 runs on a copy stream while step s computes (two device staging buffers), the way a
     # prefetching data loader feeds the reference's `model(images.to(device))`; the forward itself is unchanged.
     stage = [torch.empty_like(img_dev), torch.empty_like(img_dev)]
-    det_host = torch.empty((B, 128, 6), dtype=torch.float32).pin_memory()
-    num_host = torch.empty((B,), dtype=torch.int32).pin_memory()
+    det_host = torch.empty((B, model.max_out() + 1, 6), dtype=torch.float32).pin_memory()  # detections + count row
     copy_stream = torch.cuda.Stream()
     main = torch.cuda.current_stream()
     up_done = [torch.cuda.Event(), torch.cuda.Event()]     # upload into stage[k] finished
@@ -238,8 +238,7 @@ def main():
             main.wait_event(up_done[k])
             o_ = step(stage[k])
             fw_done[k].record(main)
-            det_host.copy_(o_["det"], non_blocking=True)
-            num_host.copy_(o_["num"], non_blocking=True)
+            det_host.copy_(o_["det_packed"], non_blocking=True)
         return o_
 
     for ev_ in fw_done:
@@ -279,7 +278,7 @@ def main():
             "config": {"workload": f"MQ-GLIP-T full forward (Swin-T+FPN, BERT+GCP+PreSelect, 6x fusion/DyConv, dot-product "
                                    f"head, ATSS+ml_nms), batch {B}/GPU, 800x1333 (padded 800x1344), 80-class prompt T=256, "
                                    f"K=5 queries/class (BASELINE config 2), random-init weights",
-                       "global_batch": world * B, "parallelism": f"image-sharded dp{world}, 1 NCCL all-gather of [B,128,6]",
+                       "global_batch": world * B, "parallelism": f"image-sharded dp{world}, 1 NCCL all-gather of [B,{model.max_out() + 1},6] (detections + count row)",
                        "l2": "256 MiB buffer written between timed steps", "postprocess": pp},
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": pk["tflops"], "unit": "TFLOP/s",
                          "frac": achieved / pk["tflops"], "traffic": None, "peak_source": pk["src"],
@@ -287,7 +286,7 @@ def main():
                          "kernel_ms_per_step": g_ms, "kernel_share_of_step": g_ms / ms,
                          "algorithmic_tflop_per_step": g_flops / 1e12},
             "e2e": {"value": world * B / (e2e_ms / 1e3), "unit": "images/s", "ms_per_step": e2e_ms,
-                    "h2d_bytes_per_step": img_host.numel() * 4, "d2h_bytes_per_step": det_host.numel() * 4 + num_host.numel() * 4},
+                    "h2d_bytes_per_step": img_host.numel() * 4, "d2h_bytes_per_step": det_host.numel() * 4},
             "gpu_launches": launches, "clocks": clk,
         }
         if not args.no_cpu_baseline and world == 1:

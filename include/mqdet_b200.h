@@ -246,9 +246,12 @@ int mqdet_ml_nms_batched(const float* boxes, const float* scores, const float* l
                          void* stream);
 
 /* det[b][i][0:6] = (x1,y1,x2,y2,score,label) of kept candidate i (< num_keep[b]), zero-padded to max_out rows:
- * the fixed-shape per-image result that is copied to the host / all-gathered over NCCL. */
+ * the fixed-shape per-image result that is copied to the host / all-gathered over NCCL.  det holds det_rows >= max_out
+ * rows per image (0 -> max_out); with det_rows > max_out, row max_out carries (float)num_keep[b] in column 0 so that the
+ * detections and their count travel in ONE buffer (one D2H copy, one all-gather). */
 int mqdet_gather_detections(const float* boxes, const float* scores, const float* labels, const int64_t* keep,
-                            const int32_t* num_keep, int64_t B, int64_t n_max, int64_t max_out, float* det, void* stream);
+                            const int32_t* num_keep, int64_t B, int64_t n_max, int64_t max_out, int64_t det_rows, float* det,
+                            void* stream);
 
 /* Anchors of one FPN level (anchor_generator.py:72-109): base_anchor (HOST float[4]) shifted by (x*stride, y*stride);
  * visibility (optional uint8) = fully inside the image (STRADDLE_THRESH 0). */

@@ -244,11 +244,17 @@ __global__ void anchors_kernel(float* __restrict__ out, unsigned char* __restric
 // det[b][i] = (x1, y1, x2, y2, score, label) of the i-th kept candidate (ascending candidate index), i < num_keep[b]
 __global__ void gather_detections_kernel(const float* __restrict__ boxes, const float* __restrict__ scores,
                                          const float* __restrict__ labels, const long long* __restrict__ keep,
-                                         const int* __restrict__ num_keep, int n_max, int max_out, float* __restrict__ det) {
+                                         const int* __restrict__ num_keep, int n_max, int max_out, int det_rows,
+                                         float* __restrict__ det) {
   const int b = blockIdx.y, i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= max_out) return;
-  float* d = det + ((long)b * max_out + i) * 6;
-  if (i < num_keep[b]) {
+  if (i >= det_rows) return;
+  float* d = det + ((long)b * det_rows + i) * 6;
+  if (i == max_out) {  // packed result: the count rides in the row after the detections (one buffer -> one D2H / one all-gather)
+    d[0] = (float)num_keep[b];
+    d[1] = d[2] = d[3] = d[4] = d[5] = 0.f;
+  } else if (i > max_out) {
+    d[0] = d[1] = d[2] = d[3] = d[4] = d[5] = 0.f;
+  } else if (i < num_keep[b]) {
     const long long k = keep[(long)b * n_max + i];
     const float* bx = boxes + ((long)b * n_max + k) * 4;
     d[0] = bx[0]; d[1] = bx[1]; d[2] = bx[2]; d[3] = bx[3];
@@ -264,11 +270,13 @@ __global__ void gather_detections_kernel(const float* __restrict__ boxes, const 
 using namespace mqdet;
 
 extern "C" int mqdet_gather_detections(const float* boxes, const float* scores, const float* labels, const int64_t* keep,
-                                       const int32_t* num_keep, int64_t B, int64_t n_max, int64_t max_out, float* det,
-                                       void* stream) {
+                                       const int32_t* num_keep, int64_t B, int64_t n_max, int64_t max_out, int64_t det_rows,
+                                       float* det, void* stream) {
   MQ_REQUIRE(boxes && scores && labels && keep && num_keep && det && B > 0 && max_out > 0, "gather_detections: bad args");
-  gather_detections_kernel<<<dim3((unsigned)((max_out + 127) / 128), (unsigned)B), 128, 0, (cudaStream_t)stream>>>(
-      boxes, scores, labels, (const long long*)keep, num_keep, (int)n_max, (int)max_out, det);
+  if (det_rows <= 0) det_rows = max_out;
+  MQ_REQUIRE(det_rows >= max_out, "gather_detections: det_rows %ld < max_out %ld", (long)det_rows, (long)max_out);
+  gather_detections_kernel<<<dim3((unsigned)((det_rows + 127) / 128), (unsigned)B), 128, 0, (cudaStream_t)stream>>>(
+      boxes, scores, labels, (const long long*)keep, num_keep, (int)n_max, (int)max_out, (int)det_rows, det);
   return check_launch("gather_detections_kernel");
 }
 

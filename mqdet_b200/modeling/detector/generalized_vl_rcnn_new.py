@@ -52,6 +52,34 @@ class GeneralizedVLRCNN_New(nn.Module):
 
     def load_query_bank(self, path):
         self.query_selector.load_query_bank(path)
+        self.invalidate_prompt_cache()
+
+    def invalidate_prompt_cache(self):
+        """Drop everything cached per prompt (token ids, selected queries, masks, the head's token map)."""
+        self._prompt = None
+        self.rpn._tokmap = None
+
+    @staticmethod
+    def _prompt_key(captions, positive_map, B, bank_version):
+        """Content key of a prompt: token ids / caption strings, the positive map's entries, batch size and the query
+        bank version — an in-place edit of ``positive_map`` or a swapped bank is a different prompt."""
+        if isinstance(captions, dict):
+            ids = captions["input_ids"]
+            am = captions["attention_mask"]
+            if ids.is_cuda:  # no device->host sync on the hot path: storage identity + version counters
+                ck = (tuple(ids.shape), ids.data_ptr(), ids._version, am.data_ptr(), am._version)
+            else:
+                ck = (tuple(ids.shape), ids.detach().numpy().tobytes(), am.detach().numpy().tobytes())
+        else:
+            ck = tuple(captions) if isinstance(captions, (list, tuple)) else captions
+        pk = tuple((int(k), tuple(int(t) for t in (v if not isinstance(v, int) else [v]))) for k, v in sorted(positive_map.items()))
+        return (ck, pk, int(B), int(bank_version))
+
+    def max_out(self):
+        """Rows of the fixed-shape per-image result: DETECTIONS_PER_IMG plus head-room for the reference's `>= kth score`
+        ties (rpn/inference.py:757-767), rounded up to a multiple of 32 (100 -> 128, LVIS 300 -> 352)."""
+        d = int(self.cfg.MODEL.ATSS.DETECTIONS_PER_IMG)
+        return (d + 28 + 31) // 32 * 32
 
     @torch.no_grad()
     def get_labels_and_maps_from_positive_map(self, positive_map, dtype=torch.float):
@@ -82,8 +110,14 @@ class GeneralizedVLRCNN_New(nn.Module):
         once per (captions, positive_map) object pair and batch size — the reference rebuilds it in every forward
         (Python loops over classes in QuerySelector.forward :57-100 and a tokenizer call :378-383)."""
         st = self._prompt
-        if st is not None and st["captions"] is captions and st["positive_map"] is positive_map and st["B"] == B:
+        bank_version = self.query_selector.bank_version if self.query_selector is not None else 0
+        same_objects = st is not None and st["captions"] is captions and st["positive_map"] is positive_map
+        key = self._prompt_key(captions, positive_map, B, bank_version)
+        if st is not None and st["key"] == key:
+            if not same_objects:
+                st["captions"], st["positive_map"] = captions, positive_map
             return st
+        self.rpn._tokmap = None
         ids, am = self._tokenize(captions, dev)
         if ids.shape[0] == 1 and B > 1:
             ids, am = ids.expand(B, -1).contiguous(), am.expand(B, -1).contiguous()
@@ -92,12 +126,15 @@ class GeneralizedVLRCNN_New(nn.Module):
             labels, all_map = self.get_labels_and_maps_from_positive_map(positive_map)
             vision, vmask, _ = self.query_selector([labels] * B, [all_map] * B, None)
             vision, vmask = vision.float().contiguous(), vmask.float().contiguous()
-        self._prompt = dict(captions=captions, positive_map=positive_map, B=B, ids=ids, am=am, vision=vision, vmask=vmask)
+        self._prompt = dict(key=key, captions=captions, positive_map=positive_map, B=B, ids=ids, am=am, vision=vision,
+                            vmask=vmask)
         return self._prompt
 
     @torch.no_grad()
-    def forward_device(self, images, captions, positive_map, max_out=128):
-        """Everything up to (and excluding) the device->host copy: returns the device-resident result dict."""
+    def forward_device(self, images, captions, positive_map, max_out=None):
+        """Everything up to (and excluding) the device->host copy: returns the device-resident result dict.
+        ``max_out`` (rows of the fixed-shape detections) defaults to ``self.max_out()`` (from DETECTIONS_PER_IMG)."""
+        max_out = self.max_out() if max_out is None else int(max_out)
         if self.training:
             raise NotImplementedError("training is SURVEY.md §8f")
         images = to_image_list(images, self.cfg.DATALOADER.SIZE_DIVISIBILITY)
@@ -115,6 +152,7 @@ class GeneralizedVLRCNN_New(nn.Module):
                                                               "batched_pos_category_map": None}})
         out = self.rpn.forward_flat(pyr16, levels, images.image_sizes, lang["hidden"], lang["masks"], positive_map, max_out)
         out["image_sizes"] = images.image_sizes
+        out["pyramid16"], out["lang_hidden"] = pyr16, lang["hidden"]  # inputs of the fusion tower (parity tests read them)
         out["vision_query_gates"] = lang["vision_query_gates"]
         return out
 

@@ -317,10 +317,11 @@ class BertLayer(nn.Module):
         ctx = torch.empty((B, T, H, d), dtype=torch.float16, device=h32.device)
         ops.gemm(p, vT, out=ctx.permute(0, 2, 1, 3))
         ao = self.attention.output
-        a = ops.gemm(ctx.view(B * T, D), w16(ao.dense.weight), bias=f32(ao.dense.bias), out_dtype=torch.float32,
-                     clamp=self.clamp)
+        # BertSelfOutput has no clamp_values (rpn/modeling_bert.py:186-190); only the attention scores, BertIntermediate
+        # (before and after the GELU: same result as one clamp after it) and BertOutput are clamped (:140-143, 250-271)
+        a = ops.gemm(ctx.view(B * T, D), w16(ao.dense.weight), bias=f32(ao.dense.bias), out_dtype=torch.float32)
         a16, a32 = ops.add_layernorm(a, h32.view(B * T, D), f32(ao.LayerNorm.weight), f32(ao.LayerNorm.bias),
-                                     ao.LayerNorm.eps, clamp=self.clamp)
+                                     ao.LayerNorm.eps)
         it = ops.gemm(a16, w16(self.intermediate.dense.weight), bias=f32(self.intermediate.dense.bias), act=ACT_GELU,
                       clamp=self.clamp)
         o = ops.gemm(it, w16(self.output.dense.weight), bias=f32(self.output.dense.bias), out_dtype=torch.float32,

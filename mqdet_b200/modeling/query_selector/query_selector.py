@@ -28,13 +28,16 @@ class QuerySelector(nn.Module):
         self.pure_text_rate = cfg.VISION_QUERY.PURE_TEXT_RATE
         self.num_query_per_class = cfg.VISION_QUERY.NUM_QUERY_PER_CLASS
         self.cfg = cfg
+        self.bank_version = 0  # bumped whenever the bank changes: per-prompt caches of the detector key on it
 
     def load_query_bank(self, bank_path):
         self.query_bank = torch.load(bank_path, map_location=self.device)
+        self.bank_version += 1
 
     def set_query_bank(self, bank):
         """In-memory bank {label: tensor[n, scales, C]} (tests / synthetic benchmarks; no file on disk)."""
         self.query_bank = {k: v.to(self.device) for k, v in bank.items()}
+        self.bank_version += 1
 
     def _pick(self, label):
         """Rows of the class's bank entry to use (the reference's sampler, same RNG calls in the same order)."""

@@ -197,6 +197,15 @@ class VLDyHead(nn.Module):
         fc = cfg.MODEL.DYHEAD.FUSE_CONFIG
         if num_anchors != 1 or not fc.USE_DOT_PRODUCT_TOKEN_LOSS or not fc.USE_FUSED_FEATURES_DOT_PRODUCT:
             raise NotImplementedError("only the MQ-GLIP head (1 anchor, fused-feature dot-product token head)")
+        # flags the reference reads on this path whose non-shipped value would change the arithmetic: refuse, never ignore
+        if not getattr(fc, "CLAMP_DOT_PRODUCT", True):
+            raise NotImplementedError("FUSE_CONFIG.CLAMP_DOT_PRODUCT=False (vldyhead.py:884-886): the +-5e4 clamp is fused")
+        if getattr(cfg.VISION_QUERY, "QUERY_FUSION", False):
+            raise NotImplementedError("VISION_QUERY.QUERY_FUSION (SupportFuse, vldyhead.py:576-591) is off in every MQ config")
+        if getattr(getattr(cfg, "DATASETS", None), "ONE_HOT", False):
+            raise NotImplementedError("DATASETS.ONE_HOT is off in every MQ config")
+        if getattr(cfg.MODEL.LANGUAGE_BACKBONE, "MASK_SPECIAL", False):
+            raise NotImplementedError("LANGUAGE_BACKBONE.MASK_SPECIAL is off in every MQ config")
         bn_type = ["gn", cfg.MODEL.GROUP_NORM.NUM_GROUPS]
         conv_func = lambda i, o, s: Conv3x3Norm(i, o, s, deformable=cfg.MODEL.DYHEAD.USE_DFCONV, bn_type=bn_type)  # noqa: E731
         tower = []
@@ -302,12 +311,15 @@ class VLDyHeadModule(nn.Module):
         return self._scales[1]
 
     @torch.no_grad()
-    def forward_flat(self, pyr16, levels, image_sizes, lang_hidden, lang_masks, positive_map, max_out=128):
+    def forward_flat(self, pyr16, levels, image_sizes, lang_hidden, lang_masks, positive_map, max_out=None):
         """pyr16 [B,N,256] fp16 -> device-resident detections: dict(det [B,max_out,6], num [B], ...)."""
         cfg = self.cfg
+        if max_out is None:
+            max_out = (int(cfg.MODEL.ATSS.DETECTIONS_PER_IMG) + 28 + 31) // 32 * 32
         r = self.head.forward_flat(pyr16, levels, lang_hidden, lang_masks)
-        if self._tokmap is None or self._tokmap[0] is not positive_map:
-            self._tokmap = (positive_map, ops.make_tokmap(positive_map, cfg.MODEL.DYHEAD.NUM_CLASSES - 1, pyr16.device))
+        pkey = tuple((int(k), tuple(v) if not isinstance(v, int) else (v,)) for k, v in sorted(positive_map.items()))
+        if self._tokmap is None or self._tokmap[0] != pkey:
+            self._tokmap = (pkey, ops.make_tokmap(positive_map, cfg.MODEL.DYHEAD.NUM_CLASSES - 1, pyr16.device))
         tokmap = self._tokmap[1]
         ih, iw = image_sizes[0]
         if any(tuple(s) != (ih, iw) for s in image_sizes):
@@ -328,7 +340,10 @@ class VLDyHeadModule(nn.Module):
         num_h = num.cpu()
         res = []
         for b, (h, w) in enumerate(image_sizes):
-            k = min(int(num_h[b]), det_h.shape[1])
+            k = int(num_h[b])
+            if k > det_h.shape[1]:  # never clip silently: kept rows are in candidate (level-major) order, not score order
+                raise MqdetError(f"image {b}: {k} detections kept (score ties at the DETECTIONS_PER_IMG cut) exceed the "
+                                 f"{det_h.shape[1]}-row result buffer; pass a larger max_out")
             bl = BoxList(det_h[b, :k, :4].clone(), (w, h), mode="xyxy")
             bl.add_field("labels", det_h[b, :k, 5].long())
             bl.add_field("scores", det_h[b, :k, 4].clone())

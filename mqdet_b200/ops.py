@@ -553,12 +553,13 @@ def atss_postprocess(logits, reg_ctr, tokmap, levels, strides, anchor_sizes, reg
     num = torch.empty((B,), dtype=torch.int32, device=dev)
     check(load().mqdet_ml_nms_batched(_ptr(cb), _ptr(csc), _ptr(cl), _ptr(totals), B, S, float(nms_thresh), int(max_det),
                                       _ptr(keep), _ptr(num), _ptr(nws), _stream()), "ml_nms_batched")
-    det = torch.empty((B, max_out, 6), dtype=torch.float32, device=dev)
-    check(load().mqdet_gather_detections(_ptr(cb), _ptr(csc), _ptr(cl), _ptr(keep), _ptr(num), B, S, max_out, _ptr(det),
-                                         _stream()), "gather_detections")
+    # packed fixed-shape result [B, max_out + 1, 6]: rows 0..max_out-1 = detections, row max_out = (count, 0, ...)
+    packed = torch.empty((B, max_out + 1, 6), dtype=torch.float32, device=dev)
+    check(load().mqdet_gather_detections(_ptr(cb), _ptr(csc), _ptr(cl), _ptr(keep), _ptr(num), B, S, max_out, max_out + 1,
+                                         _ptr(packed), _stream()), "gather_detections")
     launch_count += 10
-    return {"det": det, "num": num, "cand_boxes": cb, "cand_scores": csc, "cand_labels": cl, "cand_totals": totals,
-            "level_counts": lvl_counts, "level_keys": okey, "keep": keep}
+    return {"det": packed[:, :max_out], "num": num, "det_packed": packed, "cand_boxes": cb, "cand_scores": csc,
+            "cand_labels": cl, "cand_totals": totals, "level_counts": lvl_counts, "level_keys": okey, "keep": keep}
 
 
 def anchors(grid_h, grid_w, stride, size, img_w, img_h, device):

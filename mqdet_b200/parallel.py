@@ -1,10 +1,11 @@
 """Multi-GPU data path: images are sharded over ranks (one process per GPU, weights replicated); the ONLY collective is a
-fixed-shape all-gather of the per-image detections over NCCL/NVLink (gloo in the CPU tests).
+fixed-shape all-gather of the per-image detections over NCCL/NVLink (gloo in the CPU tests) — ONE collective per step.
 
 It replaces the reference's pickled, variable-length ``all_gather`` of whole-dataset prediction dicts
 (maskrcnn_benchmark/utils/comm.py:61-102, engine/inference.py:293-312): after the top-k cut every image has at most
-``max_out`` rows of (x1, y1, x2, y2, score, label), so the exchange is ``[B_local, max_out, 6]`` fp32 + ``[B_local]``
-counts per rank (24.6 KB at B_local = 8) — latency-bound, never bandwidth-bound.
+``max_out`` rows of (x1, y1, x2, y2, score, label); the count of valid rows rides in an extra row of the same buffer
+(``mqdet_gather_detections`` with ``det_rows = max_out + 1``), so the exchange is ONE ``[B_local, max_out + 1, 6]`` fp32
+buffer per rank (24.8 KB at B_local = 8, max_out = 128) — latency-bound, never bandwidth-bound.
 """
 import torch
 import torch.distributed as dist
@@ -20,12 +21,34 @@ def all_gather_detections(det, num, group=None):
     num_all [world*B_local]) in RANK-MAJOR order; identity when no process group is initialised."""
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
         return det, num
+    det_all, num_all = unpack(all_gather_packed(pack(det, num), group))
+    return det_all, num_all.to(num.dtype)
+
+
+def pack(det, num):
+    """det [B, max_out, 6] + num [B] -> packed [B, max_out + 1, 6] (row max_out = (count, 0, ...)); host/test helper — the
+    device path gets the packed buffer straight from ``mqdet_gather_detections``."""
+    packed = torch.zeros((det.shape[0], det.shape[1] + 1, 6), dtype=det.dtype, device=det.device)
+    packed[:, :-1] = det
+    packed[:, -1, 0] = num.to(det.dtype)
+    return packed
+
+
+def unpack(packed):
+    """packed [B, max_out + 1, 6] -> (det view [B, max_out, 6], num int32 [B])."""
+    return packed[:, :-1], packed[:, -1, 0].round().to(torch.int32)
+
+
+def all_gather_packed(packed, group=None, out=None):
+    """ONE collective: packed [B_local, max_out + 1, 6] -> [world * B_local, max_out + 1, 6] in RANK-MAJOR order; identity
+    when no process group is initialised.  ``out`` = preallocated destination (CUDA-graph friendly)."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return packed
     world = dist.get_world_size(group)
-    det_all = torch.empty((world * det.shape[0],) + tuple(det.shape[1:]), dtype=det.dtype, device=det.device)
-    num_all = torch.empty((world * num.shape[0],), dtype=num.dtype, device=num.device)
-    dist.all_gather_into_tensor(det_all, det.contiguous(), group=group)
-    dist.all_gather_into_tensor(num_all, num.contiguous(), group=group)
-    return det_all, num_all
+    if out is None:
+        out = torch.empty((world * packed.shape[0],) + tuple(packed.shape[1:]), dtype=packed.dtype, device=packed.device)
+    dist.all_gather_into_tensor(out, packed.contiguous(), group=group)
+    return out
 
 
 def unshard(det_all, num_all, num_images, world):

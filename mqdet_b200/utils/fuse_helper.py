@@ -57,6 +57,11 @@ class BiMultiHeadAttention(nn.Module):
         self.out_l_proj = nn.Linear(embed_dim, l_dim)
         fc = cfg.MODEL.DYHEAD.FUSE_CONFIG
         self.fused_text_side = True  # False: column-softmax + GEMM path (kept for A/B checks, tests/test_fusion_gpu.py)
+        # "fused" (default): the product path; "f16": the score matrix A = q.k^T stored in fp16 (round-1 path, kept for
+        # A/B runs); "f32": diagnostic variant that keeps the
+        # scores in fp32 until both softmaxes have been taken, like the reference (fuse_helper.py:240-291) — twice the
+        # traffic, used by tests/test_parity_experiment_gpu.py to attribute the tower's end-to-end error
+        self.score_precision = "fused"
         self.stable_softmax_2d = fc.STABLE_SOFTMAX_2D
         self.clamp_min_for_underflow = fc.CLAMP_MIN_FOR_UNDERFLOW
         self.clamp_max_for_overflow = fc.CLAMP_MAX_FOR_OVERFLOW
@@ -89,6 +94,9 @@ class BiMultiHeadAttention(nn.Module):
         vlT = ops.gemm(w16(self.values_l_proj.weight), ln16, bias=f32(self.values_l_proj.bias), bias_mode=VEC_PER_ROW)
 
         qh, kh = q.permute(0, 2, 1, 3), k.permute(0, 2, 1, 3)
+        if self.score_precision == "f32":
+            return self._finish(*self._attend_f32_scores(qh, kh, vvT, vlT, mask_l, clamp, B, N, T, Np), v_epilogue, l_epilogue,
+                                B, N, T, Cv)
         # scores A = clamp(Q_h K_h^T)  [B,H,N,T]  (ONE product serves both directions)
         A = torch.empty((B, H, N, T), dtype=torch.float16, device=dev)
         ops.gemm(qh, kh, out=A, clamp=clamp)
@@ -116,7 +124,29 @@ class BiMultiHeadAttention(nn.Module):
         ops.gemm(Pv, vlT.view(B, H, d, T), out=ov.permute(0, 2, 1, 3))
         if not fused:
             ops.gemm(Pl, vvT.view(B, H, d, Np), out=ol.permute(0, 2, 1, 3))
+        return self._finish(ov, ol, v_epilogue, l_epilogue, B, N, T, Cv)
 
+    def _attend_f32_scores(self, qh, kh, vvT, vlT, mask_l, clamp, B, N, T, Np):
+        """Diagnostic: both score matrices in fp32 (A and its transpose as two products), softmaxes on the fp32 values."""
+        H, d = self.num_heads, self.head_dim
+        dev = qh.device
+        cm = mask_l.float().contiguous() if mask_l is not None else None
+        A32 = torch.empty((B, H, N, T), dtype=torch.float32, device=dev)
+        ops.gemm(qh, kh, out=A32, clamp=clamp)
+        Pv = ops.softmax_rows(A32, colmask=cm, rows_per_batch=H * N, mask_value=-9e15, keep_add=1.0)
+        del A32
+        AT32 = torch.empty((B, H, T, Np), dtype=torch.float32, device=dev)
+        ops.gemm(kh, qh, out=AT32[..., :N], clamp=clamp)
+        Pl = ops.softmax_rows(AT32, n=N)
+        del AT32
+        ov = torch.empty((B, N, H, d), dtype=torch.float16, device=dev)
+        ops.gemm(Pv, vlT.view(B, H, d, T), out=ov.permute(0, 2, 1, 3))
+        ol = torch.empty((B, T, H, d), dtype=torch.float16, device=dev)
+        ops.gemm(Pl, vvT.view(B, H, d, Np), out=ol.permute(0, 2, 1, 3))
+        return ov, ol
+
+    def _finish(self, ov, ol, v_epilogue, l_epilogue, B, N, T, Cv):
+        E = self.embed_dim
         ve = v_epilogue or {}
         le = l_epilogue or {}
         dv = ops.gemm(ov.view(B * N, E), w16(self.out_v_proj.weight), bias=f32(self.out_v_proj.bias),

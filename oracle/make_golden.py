@@ -6,6 +6,7 @@ from /root/reference by oracle/ref_loader.py) on seeded synthetic weights/inputs
 Each fixture stores the case description (seed, sizes) and a strided SUBSAMPLE of the reference output (full tensors
 would be MBs); weights/inputs are regenerated from the seed by ``case_inputs`` below, which the tests import too.
 """
+import math
 import os
 import sys
 import types
@@ -171,6 +172,14 @@ def case_inputs(name):
         ids, am, pmap = synth.prompt(12, 2, 256, gen)
         bank = synth.query_bank(pmap, 5, gen)
         return dict(sd=sd, ids=ids, am=am, pmap=pmap, bank=bank, img=synth.images(gen, 1, 160, 224), size=(160, 224))
+    if name == "detector_bench":
+        # BASELINE.json config 2 per image: ONE 800x1333 image (padded 800x1344), 80-class prompt, K = 5 queries per class,
+        # head bias at the reference's PRIOR_PROB initialisation (what bench.py runs, at B = 8 copies of such images)
+        gen = synth.Gen(72)
+        sd = synth.detector_sd(gen, bias0=-math.log(99.0))
+        ids, am, pmap = synth.prompt(80, 2, 256, gen)
+        bank = synth.query_bank(pmap, 5, gen)
+        return dict(sd=sd, ids=ids, am=am, pmap=pmap, bank=bank, img=synth.images(gen, 1, 800, 1333), size=(800, 1333))
     if name == "contrastive_embed":
         gen = synth.Gen(1239)
         B, Q, T, D = 2, 900, 195, 256
@@ -243,7 +252,7 @@ def run_reference(name):
         flat = lambda xs: torch.cat([x.flatten(2).transpose(1, 2) for x in xs], dim=1)  # noqa: E731
         return dict(logits=torch.cat(out[6], dim=1), hidden=lang["hidden"], bbox=flat(out[1]), ctr=flat(out[2]),
                     per_level=(out[6], out[1], out[2]))
-    if name == "detector":
+    if name in ("detector", "detector_bench"):
         import numpy as np
         from oracle import restate
         det = rl.detector(ref_detector_cfg(), dcn_stub, lambda b, s, l, t: restate.ml_nms(b, s, l, t), (c["ids"], c["am"]))
@@ -255,9 +264,19 @@ def run_reference(name):
         det.load_state_dict(full, strict=True)
         det.query_selector.query_bank = {k: v.clone() for k, v in c["bank"].items()}
         np.random.seed(0)
-        bl = det(c["img"], captions=["a synthetic caption"], positive_map=c["pmap"])[0]
+        cap = {}
+        # intermediates of the reference forward: language stream entering the head, head outputs (logits / fused hidden)
+        h1 = det.language_backbone.register_forward_hook(lambda m, i, o: cap.__setitem__("lang_hidden", o["hidden"].clone()))
+        h2 = det.rpn.head.register_forward_hook(lambda m, i, o: cap.__setitem__("head", o))
+        h3 = det.rpn.head.register_forward_pre_hook(lambda m, i: cap.__setitem__("pyr", [f.clone() for f in i[0]]))
+        il = sys.modules["maskrcnn_benchmark.structures.image_list"].ImageList(c["img"], [c["size"]])
+        bl = det(il, captions=["a synthetic caption"], positive_map=c["pmap"])[0]
+        for h in (h1, h2, h3):
+            h.remove()
         d = torch.cat([bl.bbox, bl.get_field("scores")[:, None], bl.get_field("labels")[:, None].float()], 1)
-        return dict(det=canonical_detections(d), boxlist=bl)
+        flat = lambda xs: torch.cat([x.flatten(2).transpose(1, 2) for x in xs], dim=1)  # noqa: E731
+        return dict(det=canonical_detections(d), boxlist=bl, lang_hidden=cap["lang_hidden"], logits=torch.cat(cap["head"][6], 1),
+                    pyramid=flat(cap["pyr"]), bbox=flat(cap["head"][1]), ctr=flat(cap["head"][2]))
     if name == "contrastive_embed":
         mod = rl.gdino_utils().ContrastiveEmbed(max_text_len=256)
         return dict(logits=mod(c["x"], {"encoded_text": c["y"], "text_token_mask": c["mask"]}))
@@ -288,6 +307,8 @@ SUBSAMPLE = {"gcp_block": {"y": (4, 8), "s": (4, 8)}, "preselect": {"vision": (1
              "contrastive_embed": {"logits": (9, 1)},
              "dyconv": {"v": (3, 4)},
              "detector": {"det": (1, 1)},
+             "detector_bench": {"det": (1, 1), "lang_hidden": (2, 8), "logits": (32, 2), "pyramid": (32, 4), "bbox": (16, 1),
+                                "ctr": (16, 1)},
              "vldyhead": {"logits": (3, 4), "hidden": (4, 8), "bbox": (3, 1), "ctr": (3, 1)},
              "swin_fpn": {"c3": (4, 2, 2), "c4": (4, 1, 1), "c5": (8, 1, 1), "p3": (4, 2, 2), "p4": (4, 1, 1), "p5": (4, 1, 1),
                           "p6": (2, 1, 1), "p7": (1, 1, 1)}}

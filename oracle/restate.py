@@ -145,8 +145,9 @@ def bert_layer(h, ext_mask, sd, p, heads=12, eps=1e-12, clamp=0.0):
     if ext_mask is not None:
         scores = scores + ext_mask
     ctx = (scores.softmax(-1) @ v).transpose(1, 2).reshape(B, T, D)
-    a = cl(_lin(ctx, sd, p + "attention.output.dense"))
-    a = cl(_ln(a + h, sd, p + "attention.output.LayerNorm", eps))
+    # BertSelfOutput carries no clamp (rpn/modeling_bert.py:177-190); scores, BertIntermediate and BertOutput do
+    a = _lin(ctx, sd, p + "attention.output.dense")
+    a = _ln(a + h, sd, p + "attention.output.LayerNorm", eps)
     i = cl(F.gelu(cl(_lin(a, sd, p + "intermediate.dense"))))
     o = cl(_lin(i, sd, p + "output.dense"))
     return cl(_ln(o + a, sd, p + "output.LayerNorm", eps))
