@@ -149,6 +149,32 @@ int mqdet_biattn_text(const void* k, int64_t k_ld, int64_t k_b1, int64_t k_b2, c
                       void* out, int64_t o_ld, int64_t o_b1, int64_t o_b2, int64_t nb1, int64_t nb2, int64_t T, int64_t N,
                       int64_t Np, int64_t d, void* stream);
 
+/* Same kernel, VN variant: the value operand is the layer-normed image-token tensor itself, vn [z][N][256] f16 (read MN-major
+ * from the same [token x channel] tile), so that out[z][t][:] = sum_n softmax_n(clamp(k_t . q_n))[n] * vn[n][:] — the value
+ * projection W_vv is applied AFTER the token reduction by the caller (sum_n p[n] = 1 moves the bias out as well), and the
+ * [B, E, N] value tensor is never built.  colmax [z][T] f32 = column maxima of the clamped fp32 scores (mqdet_biattn_image);
+ * the column sums are accumulated in-kernel from the fp32 scores (no fp16 re-quantisation). */
+int mqdet_biattn_text_vn(const void* k, int64_t k_ld, int64_t k_b1, int64_t k_b2, const void* q, int64_t q_ld, int64_t q_b1,
+                         int64_t q_b2, const void* vn, int64_t vn_ld, int64_t vn_b1, int64_t vn_b2, const float* colmax,
+                         float clamp, void* out, int64_t o_ld, int64_t o_b1, int64_t o_b2, int64_t nb1, int64_t nb2, int64_t T,
+                         int64_t N, void* stream);
+
+/* Image -> text side of BiMultiHeadAttention fused with the out-projection, layer scale and residual
+ * (maskrcnn_benchmark/utils/fuse_helper.py:240-256,277-302,420-425) in ONE persistent tcgen05 kernel: per 128 image tokens and
+ * head, S = q k^T stays in TMEM (fp32) -> clamp -> masked softmax over the T tokens in registers -> P V_l -> out-projection
+ * accumulated over the heads in a second TMEM accumulator -> out = res + gamma * (acc + bias).  Neither the score matrix nor
+ * the per-head context reach HBM.  mask [B][T] f32 (0 = padding token: probability exactly 0, like the reference's -9e15) or
+ * NULL; gamma / res may be NULL (1 / none).
+ *   q [B][N][H*256] (already scaled), k [B][T][H*256], vlT [B][H*256][T] (values_l^T), w [256][H*256] f16; *_ld row strides,
+ *   *_b image strides (elements, multiples of 8); out [B][N][256] f16.  8 <= T <= 256, T % 8 == 0, head dim 256.
+ * colmax [B*H][T] f32 receives max_n clamp(S[n][t]) — the softmax shift of the text -> image side (mqdet_biattn_text_vn).
+ * workspace: mqdet_biattn_image_workspace_floats(B, H, N, T) floats. */
+int64_t mqdet_biattn_image_workspace_floats(int64_t B, int64_t H, int64_t N, int64_t T);
+int mqdet_biattn_image(const void* q, int64_t q_ld, int64_t q_b, const void* k, int64_t k_ld, int64_t k_b, const void* vlT,
+                       int64_t vl_ld, int64_t vl_b, const void* w, int64_t w_ld, const float* bias, const float* gamma,
+                       const void* res, int64_t res_ld, int64_t res_b, const float* mask, float clamp, void* out, int64_t o_ld,
+                       int64_t o_b, float* colmax, float* workspace, int64_t B, int64_t H, int64_t N, int64_t T, void* stream);
+
 /* Text side of the dot-product token head (vldyhead.py:810,818): e = x / max(||x||, eps) written as fp16 and/or
  * fp32, dot[r] = e[r,:] . w + b0[0] (w, b0, dot optional). */
 int mqdet_l2norm_rowdot(const float* x, int64_t rows, int64_t D, float eps, const float* w, const float* b0, void* e16,

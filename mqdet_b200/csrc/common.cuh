@@ -29,6 +29,13 @@ int check_launch(const char* what);
 
 static inline int cdiv(long a, long b) { return (int)((a + b - 1) / b); }
 
+// host helpers of the tcgen05 kernels (capi.cu): cached TMA tensor maps, per-device SM count / shared-memory opt-in
+int make_operand_map(CUtensorMap* map, const void* ptr, long rows, long K, long ld, int nb1, long s1, int nb2, long s2,
+                     int box_rows, int* bcast1, int* bcast2);
+int make_store_map(CUtensorMap* map, void* C, int c_dtype, long M, long N, long ldc, int nb1, long c_b1, int nb2, long c_b2);
+int num_sms();
+int ensure_dyn_smem(const void* func, int bytes);
+
 // ---------------------------------------------------------------------------------------------
 // device helpers
 // ---------------------------------------------------------------------------------------------
@@ -274,6 +281,28 @@ __device__ __forceinline__ uint64_t umma_desc_k_sw128(uint32_t smem_addr) {
   d |= (uint64_t)1 << 46;
   d |= (uint64_t)2 << 61;
   return d;
+}
+
+// MN-major (the M / N index is the contiguous one), 128-byte-swizzled descriptor: the swizzle atom is 64 MN elements (128 B)
+// x 8 K rows; `lbo` = byte distance between atoms along MN (next 64 elements), `sbo` = between atoms along K (next 8 rows).
+// Used with the matching major bit of the instruction descriptor (UMMA_A_MN_MAJOR / UMMA_B_MN_MAJOR).
+__device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t smem_addr, uint32_t lbo, uint32_t sbo) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+constexpr uint32_t UMMA_A_MN_MAJOR = 1u << 15;
+constexpr uint32_t UMMA_B_MN_MAJOR = 1u << 16;
+
+// warp-wide max of an fp32 value in one instruction (sm_100a CREDUX.MAX.F32); every lane receives the result
+__device__ __forceinline__ float warp_redux_max(float v) {
+  float r;
+  asm volatile("redux.sync.max.f32 %0, %1, 0xffffffff;" : "=f"(r) : "f"(v));
+  return r;
 }
 
 // kind::f16 instruction descriptor: fp16 A/B (format 0) or bf16 (1), fp32 accumulate, K-major A/B.

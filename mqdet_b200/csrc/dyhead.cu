@@ -693,15 +693,8 @@ extern "C" int mqdet_conv3x3_small(const void* x, const void* w, const float* bi
   const int N = fill_levels(&lt, level_hw, nlev);
   MQ_REQUIRE(N > 0, "conv3x3_small: bad level table");
   constexpr int SMEM = CS_O * CS_LD * 2;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv3x3_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
-    MQ_REQUIRE(e == cudaSuccess, "conv3x3_small: cudaFuncSetAttribute(%d) failed: %s", SMEM, cudaGetErrorString(e));
-    attr_set = true;
-  }
-  int dev = 0, sms = 148;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  if (int rc = ensure_dyn_smem(reinterpret_cast<const void*>(&conv3x3_small_kernel), SMEM)) return rc;
+  const int sms = num_sms();
   const long tiles = ((long)B * N + CS_PIX - 1) / CS_PIX;
   const int grid = (int)(tiles < sms ? tiles : sms);
   conv3x3_small_kernel<<<grid, CS_WARPS * 32, SMEM, (cudaStream_t)stream>>>((const __half*)x, (const __half*)w, (int)O, bias, lt,

@@ -885,247 +885,6 @@ __global__ void __launch_bounds__(384, 1) gemm_tcp_kernel(const __grid_constant_
   }
 }
 
-// =====================================================================================================================
-// Fused text -> image side of the bi-directional attention (BiMultiHeadAttention, fuse_helper.py:257-275, 289-291):
-//     out[t, :] = sum_n softmax_n(clamp(k_t . q_n)) * Vv[n, :]        per (image, head), t = text token, n = image token
-// One CTA per (z, 128 text tokens).  The transposed probabilities [T, N] never reach HBM.  Per step of 256 image tokens:
-//     S^T   = K_tile (128 x 256, resident) . Q_step^T      16 tcgen05 MMAs 128x256x16, Q streamed as four [256 x 64] k-blocks
-//     P_j   = exp(fp16(clamp(S^T[:, 64j..])) - colmax_t)   -> fp16, 128B-swizzled A-operand tile in shared memory (j = 0..3)
-//     O    += P_j . Vv_j                                    4 MMAs 128x256x16 per 64-token sub-block, O (128 x 256) in TMEM
-//     out   = O / colsum_t  -> fp16 -> TMA store
-// Every MMA is 256 wide: narrower ones (the first version used 64-token steps) pay ~the same ~130-160 cycles per
-// instruction for a fraction of the work.  colmax / colsum come from mqdet_colsoftmax_stats / mqdet_colstats_rowsoftmax over
-// the SAME fp16 scores the image -> text side uses, so no online rescaling is needed.
-// Roles: warp 0 = Q producer, warp 3 = V producer (separate rings: a Q k-block is free as soon as its MMAs retire),
-// warp 1 = MMA issuer, warp 2 = TMEM allocator, warps 4-19 = exponentials + epilogue (thread == text token == TMEM lane,
-// four warps per lane quarter, 16 of the 64 sub-block columns each).  TMEM: S^T 256 columns + O 256 columns.
-// =====================================================================================================================
-constexpr int BT_STEP = 256;  // image tokens per S^T accumulator
-constexpr int BT_SUB = 64;    // image tokens per P / V tile
-constexpr int BT_PF = 2;      // L2 prefetch distance in steps
-struct BtCfg {
-  static constexpr int KT_BYTES = 4 * BM * BK * 2;    // resident K tile: 4 k-blocks of [128 x 64]
-  static constexpr int Q_BYTES = BT_STEP * BK * 2;    // one k-block [256 n x 64 d]
-  static constexpr int V_BYTES = 256 * BT_SUB * 2;    // Vv^T tile [256 d x 64 n]
-  static constexpr int P_BYTES = BM * BT_SUB * 2;     // P tile [128 t x 64 n]
-  static constexpr int SMEM_BYTES = KT_BYTES + 2 * Q_BYTES + 2 * V_BYTES + 2 * P_BYTES + 1024 /*align*/ + 256 /*barriers*/;
-};
-struct BtP {
-  const float* stat;  // [Z][2][T]: column max, 1 / column sum
-  float clamp;
-  int nb1, T, N, n_steps;
-  int k_bc1, k_bc2, q_bc1, q_bc2, v_bc1, v_bc2;  // 1 -> batch coordinate pinned to 0
-};
-
-__global__ void __launch_bounds__(640, 1) biattn_text_kernel(const __grid_constant__ CUtensorMap tma_k,
-                                                             const __grid_constant__ CUtensorMap tma_q,
-                                                             const __grid_constant__ CUtensorMap tma_v,
-                                                             const __grid_constant__ CUtensorMap tma_o, const BtP p) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* kt = smem;
-  uint8_t* qring = kt + BtCfg::KT_BYTES;           // 2 x 32 KB
-  uint8_t* vring = qring + 2 * BtCfg::Q_BYTES;     // 2 x 32 KB
-  uint8_t* pring = vring + 2 * BtCfg::V_BYTES;     // 2 x 16 KB
-  uint64_t* bars = reinterpret_cast<uint64_t*>(pring + 2 * BtCfg::P_BYTES);
-  uint64_t* kt_full = bars;
-  uint64_t* q_full = bars + 1;    // [2] Q k-block landed
-  uint64_t* q_empty = bars + 3;   // [2] its four MMAs retired
-  uint64_t* v_full = bars + 5;    // [2] Vv sub-block landed
-  uint64_t* pv_done = bars + 7;   // [2] P_j . Vv_j retired: V slot and P slot may be overwritten
-  uint64_t* p_full = bars + 9;    // [2] P tile written by the 16 exp warps
-  uint64_t* s_full = bars + 11;   // S^T accumulator complete
-  uint64_t* s_empty = bars + 12;  // S^T accumulator copied to registers by the 16 exp warps
-  uint64_t* o_full = bars + 13;
-  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(bars + 14);
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int mt = blockIdx.x, z = blockIdx.y;
-  const int z1 = z % p.nb1, z2 = z / p.nb1;
-  const int NS = p.n_steps;
-
-  if (threadIdx.x == 0) {
-    tma_prefetch_desc(&tma_k);
-    tma_prefetch_desc(&tma_q);
-    tma_prefetch_desc(&tma_v);
-    tma_prefetch_desc(&tma_o);
-    mbar_init(kt_full, 1);
-    for (int s = 0; s < 2; ++s) {
-      mbar_init(&q_full[s], 1);
-      mbar_init(&q_empty[s], 1);
-      mbar_init(&v_full[s], 1);
-      mbar_init(&pv_done[s], 1);
-      mbar_init(&p_full[s], 16);  // one arrival per exp warp
-    }
-    mbar_init(s_full, 1);
-    mbar_init(s_empty, 16);
-    mbar_init(o_full, 1);
-    fence_mbar_init();
-  }
-  if (warp == 2) tmem_alloc(tmem_base_slot, 512);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_s = *tmem_base_slot;
-  const uint32_t tmem_o = tmem_s + 256;
-
-  if (warp == 0) {
-    if (lane == 0) {
-      mbar_expect_tx(kt_full, BtCfg::KT_BYTES);
-      for (int kb = 0; kb < 4; ++kb)
-        tma_load_4d(kt + kb * (BM * BK * 2), &tma_k, kt_full, kb * BK, mt * BM, p.k_bc1 ? 0 : z1, p.k_bc2 ? 0 : z2);
-      const int qz1 = p.q_bc1 ? 0 : z1, qz2 = p.q_bc2 ? 0 : z2;
-      for (int qc = 0; qc < 4 * NS; ++qc) {
-        const int i = qc >> 2, kb = qc & 3, s = qc & 1;
-        if (i + BT_PF < NS) tma_prefetch_l2_4d(&tma_q, kb * BK, (i + BT_PF) * BT_STEP, qz1, qz2);
-        if (qc >= 2) mbar_wait(&q_empty[s], ((qc >> 1) - 1) & 1);
-        mbar_expect_tx(&q_full[s], BtCfg::Q_BYTES);
-        tma_load_4d(qring + s * BtCfg::Q_BYTES, &tma_q, &q_full[s], kb * BK, i * BT_STEP, qz1, qz2);
-      }
-    }
-  } else if (warp == 3) {
-    if (lane == 0) {
-      const int vz1 = p.v_bc1 ? 0 : z1, vz2 = p.v_bc2 ? 0 : z2;
-      for (int sc = 0; sc < 4 * NS; ++sc) {
-        const int s = sc & 1;
-        if (sc + 4 * BT_PF < 4 * NS) tma_prefetch_l2_4d(&tma_v, (sc + 4 * BT_PF) * BT_SUB, 0, vz1, vz2);
-        if (sc >= 2) mbar_wait(&pv_done[s], ((sc >> 1) - 1) & 1);
-        mbar_expect_tx(&v_full[s], BtCfg::V_BYTES);
-        tma_load_4d(vring + s * BtCfg::V_BYTES, &tma_v, &v_full[s], sc * BT_SUB, 0, vz1, vz2);
-      }
-    }
-  } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_f16(BM, 256, 0);
-      mbar_wait(kt_full, 0);
-      tc_fence_after();
-      const uint32_t kt_addr = smem_u32(kt);
-      auto issue_s = [&](int i) {  // S^T of step i: 4 k-blocks x 4 MMAs
-        for (int kb = 0; kb < 4; ++kb) {
-          const int qc = 4 * i + kb, s = qc & 1;
-          mbar_wait(&q_full[s], (qc >> 1) & 1);
-          tc_fence_after();
-          const uint32_t b0 = smem_u32(qring + s * BtCfg::Q_BYTES);
-#pragma unroll
-          for (int k = 0; k < 4; ++k)
-            tc_mma_f16(tmem_s, umma_desc_k_sw128(kt_addr + kb * (BM * BK * 2) + k * 32), umma_desc_k_sw128(b0 + k * 32), idesc,
-                       (kb | k) != 0 ? 1u : 0u);
-          tc_commit(&q_empty[s]);
-        }
-        tc_commit(s_full);
-      };
-      issue_s(0);
-      for (int i = 0; i < NS; ++i) {
-        // S^T of the NEXT step goes first: the exp warps hold step i's scores in registers (s_empty), so the tensor pipe
-        // computes S^T(i+1) while they turn S^T(i) into the four P tiles, and P(i).Vv follows back to back
-        if (i + 1 < NS) {
-          mbar_wait(s_empty, i & 1);
-          tc_fence_after();
-          issue_s(i + 1);
-        }
-        for (int j = 0; j < 4; ++j) {
-          const int sc = 4 * i + j, s = sc & 1;
-          mbar_wait(&v_full[s], (sc >> 1) & 1);
-          mbar_wait(&p_full[s], (sc >> 1) & 1);
-          tc_fence_after();
-          const uint32_t a0 = smem_u32(pring + s * BtCfg::P_BYTES), b0 = smem_u32(vring + s * BtCfg::V_BYTES);
-#pragma unroll
-          for (int k = 0; k < 4; ++k)
-            tc_mma_f16(tmem_o, umma_desc_k_sw128(a0 + k * 32), umma_desc_k_sw128(b0 + k * 32), idesc, (sc | k) != 0 ? 1u : 0u);
-          tc_commit(&pv_done[s]);
-        }
-      }
-      tc_commit(o_full);
-    }
-  } else if (warp >= 4) {
-    const int ew = (warp - 4) & 3, part = (warp - 4) >> 2;
-    const int row = ew * 32 + lane;
-    const int t = mt * BM + row;
-    constexpr float L2E = 1.4426950408889634f;
-    float m_l2 = 0.f, inv = 0.f;
-    if (t < p.T) {
-      m_l2 = -p.stat[((long)z * 2) * p.T + t] * L2E;
-      inv = p.stat[((long)z * 2 + 1) * p.T + t];
-    }
-    const float clampv = p.clamp > 0.f ? p.clamp : 3.0e38f;
-    const int sw = row & 7;
-    const uint32_t lane_addr = (uint32_t)(ew * 32) << 16;
-    const int j0 = part * 2;  // 16-byte chunks of this thread's 16 columns inside the 128-byte P row
-    for (int i = 0; i < NS; ++i) {
-      mbar_wait(s_full, i & 1);
-      tc_fence_after();
-      // this thread's 16 columns of each of the four 64-token sub-blocks
-      uint32_t r[4][16];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) tmem_ld_32x16(tmem_s + lane_addr + (uint32_t)(j * BT_SUB + part * 16), r[j]);
-      tmem_ld_wait();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(s_empty);  // the accumulator may be overwritten by the next step's S^T
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int sc = 4 * i + j, s = sc & 1;
-        if (sc >= 2) mbar_wait(&pv_done[s], ((sc >> 1) - 1) & 1);  // the product that read this P slot has retired
-        const int nrem = p.N - sc * BT_SUB - part * 16;  // valid columns of this thread's 16 (< 16 only at the very end)
-        uint32_t h[8];
-#pragma unroll
-        for (int q2 = 0; q2 < 8; ++q2) {
-          const float a = fminf(fmaxf(__uint_as_float(r[j][2 * q2]), -clampv), clampv);
-          const float b = fminf(fmaxf(__uint_as_float(r[j][2 * q2 + 1]), -clampv), clampv);
-          // the score as the fp16 matrix A holds it (the statistics were taken from those values)
-          const float2 f = __half22float2(__floats2half2_rn(a, b));
-          float e0 = ex2_approx(fmaf(f.x, L2E, m_l2)), e1 = ex2_approx(fmaf(f.y, L2E, m_l2));
-          if (nrem < 16) {  // image tokens beyond N (zero-filled q rows) must not contribute exp(-max)
-            if (2 * q2 >= nrem) e0 = 0.f;
-            if (2 * q2 + 1 >= nrem) e1 = 0.f;
-          }
-          h[q2] = pack_half2(e0, e1);
-        }
-        const uint32_t prow = smem_u32(pring + s * BtCfg::P_BYTES) + row * 128;
-        sts128(prow + (((j0) ^ sw) << 4), h[0], h[1], h[2], h[3]);
-        sts128(prow + (((j0 + 1) ^ sw) << 4), h[4], h[5], h[6], h[7]);
-        fence_proxy_async();  // generic-proxy writes of P -> visible to the tensor core (async proxy)
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&p_full[s]);
-      }
-    }
-    // ---- epilogue: O / colsum -> fp16 -> swizzled staging (the Q and V rings are idle by now) -> TMA store ----
-    mbar_wait(o_full, 0);
-    tc_fence_after();
-    const uint32_t blk = smem_u32(qring) + part * (BM * 128) + row * 128;  // this warp's 64-column block (4 x 16 KB)
-    uint32_t ra[16], rb[16];
-    tmem_ld_32x16(tmem_o + lane_addr + (uint32_t)(part * 64), ra);
-#pragma unroll
-    for (int c0 = 0; c0 < 64; c0 += 32) {
-      tmem_ld_wait_dep(ra);
-      tmem_ld_32x16(tmem_o + lane_addr + (uint32_t)(part * 64 + c0 + 16), rb);
-      uint32_t h[8];
-#pragma unroll
-      for (int q2 = 0; q2 < 8; ++q2) h[q2] = pack_half2(__uint_as_float(ra[2 * q2]) * inv, __uint_as_float(ra[2 * q2 + 1]) * inv);
-      sts128(blk + ((((c0 >> 3)) ^ sw) << 4), h[0], h[1], h[2], h[3]);
-      sts128(blk + ((((c0 >> 3) + 1) ^ sw) << 4), h[4], h[5], h[6], h[7]);
-      tmem_ld_wait_dep(rb);
-      if (c0 + 32 < 64) tmem_ld_32x16(tmem_o + lane_addr + (uint32_t)(part * 64 + c0 + 32), ra);
-#pragma unroll
-      for (int q2 = 0; q2 < 8; ++q2) h[q2] = pack_half2(__uint_as_float(rb[2 * q2]) * inv, __uint_as_float(rb[2 * q2 + 1]) * inv);
-      sts128(blk + ((((c0 >> 3) + 2) ^ sw) << 4), h[0], h[1], h[2], h[3]);
-      sts128(blk + ((((c0 >> 3) + 3) ^ sw) << 4), h[4], h[5], h[6], h[7]);
-    }
-    tc_fence_before();
-    fence_proxy_async();
-    asm volatile("bar.sync 1, 512;" ::: "memory");
-    if (warp == 4 && lane == 0) {
-      for (int cb = 0; cb < 4; ++cb) tma_store_4d(&tma_o, qring + cb * (BM * 128), cb * 64, mt * BM, z1, z2);
-      tma_store_commit_and_wait_read();
-    }
-  }
-  __syncthreads();
-  if (warp == 2) {
-    tc_fence_after();
-    tmem_dealloc(tmem_s, 512);
-  }
-}
-
 // ---------------------------------------------------------------------------------------------
 // SIMT validation kernel: 64x64 tile, 16x16 threads, 4x4 micro-tile.
 // ---------------------------------------------------------------------------------------------
@@ -1175,70 +934,9 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const GemmP p) {
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
-typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static PFN_encodeTiled get_encode_fn() {
-  static PFN_encodeTiled fn = nullptr;
-  if (!fn) {
-    void* ptr = nullptr;
-    cudaDriverEntryPointQueryResult qres;
-    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres);
-    if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !ptr) {
-      set_error("cudaGetDriverEntryPoint(cuTensorMapEncodeTiled) failed: %s", cudaGetErrorString(e));
-      return nullptr;
-    }
-    fn = reinterpret_cast<PFN_encodeTiled>(ptr);
-  }
-  return fn;
-}
-
-// 4-D map over an fp16 operand viewed as [b2][b1][rows][K]; box = [1][1][box_rows][64].
-static int make_operand_map(CUtensorMap* map, const void* ptr, long rows, long K, long ld, int nb1, long s1, int nb2,
-                            long s2, int box_rows, int* bcast1, int* bcast2) {
-  PFN_encodeTiled enc = get_encode_fn();
-  if (!enc) return MQDET_ERR_CUDA;
-  *bcast1 = (s1 == 0 || nb1 == 1);
-  *bcast2 = (s2 == 0 || nb2 == 1);
-  cuuint64_t dims[4] = {(cuuint64_t)K, (cuuint64_t)rows, (cuuint64_t)(*bcast1 ? 1 : nb1),
-                        (cuuint64_t)(*bcast2 ? 1 : nb2)};
-  // strides (bytes) of dims 1..3; unused batch dims get a harmless non-zero stride
-  cuuint64_t strides[3] = {(cuuint64_t)ld * 2, (cuuint64_t)((*bcast1 ? ld * rows : s1) * 2),
-                           (cuuint64_t)((*bcast2 ? ld * rows : s2) * 2)};
-  if (strides[1] == 0) strides[1] = 16;
-  if (strides[2] == 0) strides[2] = 16;
-  cuuint32_t box[4] = {(cuuint32_t)BK, (cuuint32_t)box_rows, 1, 1};
-  cuuint32_t estr[4] = {1, 1, 1, 1};
-  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) {
-    set_error("cuTensorMapEncodeTiled failed (%d): rows=%ld K=%ld ld=%ld nb1=%d s1=%ld nb2=%d s2=%ld ptr=%p", (int)r,
-              rows, K, ld, nb1, s1, nb2, s2, ptr);
-    return MQDET_ERR_CUDA;
-  }
-  return MQDET_OK;
-}
-
-// 4-D map over the OUTPUT viewed as [b2][b1][M][N]; box = [1][1][128 rows][128 bytes], 128B swizzle (TMA store).
+// make_operand_map / make_output_map / num_sms / ensure_dyn_smem: capi.cu (shared with biattn.cu; tensor maps are cached)
 static int make_output_map(CUtensorMap* map, const GemmP& p) {
-  PFN_encodeTiled enc = get_encode_fn();
-  if (!enc) return MQDET_ERR_CUDA;
-  const int es = (p.c_dtype == MQDET_F16) ? 2 : 4;
-  cuuint64_t dims[4] = {(cuuint64_t)p.N, (cuuint64_t)p.M, (cuuint64_t)p.nb1, (cuuint64_t)p.nb2};
-  cuuint64_t strides[3] = {(cuuint64_t)p.ldc * es, (cuuint64_t)(p.nb1 > 1 ? p.c_b1 : p.ldc * p.M) * es,
-                           (cuuint64_t)(p.nb2 > 1 ? p.c_b2 : p.ldc * p.M) * es};
-  cuuint32_t box[4] = {(cuuint32_t)(128 / es), (cuuint32_t)BM, 1, 1};
-  cuuint32_t estr[4] = {1, 1, 1, 1};
-  CUresult r = enc(map, p.c_dtype == MQDET_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, p.C,
-                   dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                   CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) {
-    set_error("cuTensorMapEncodeTiled(C) failed (%d): M=%ld N=%ld ldc=%ld", (int)r, p.M, p.N, p.ldc);
-    return MQDET_ERR_CUDA;
-  }
-  return MQDET_OK;
+  return make_store_map(map, p.C, p.c_dtype, p.M, p.N, p.ldc, p.nb1, p.c_b1, p.nb2, p.c_b2);
 }
 
 // What the persistent kernel's fast epilogue covers (everything else takes the generic one, which has no TMA-store +
@@ -1290,30 +988,11 @@ static int launch_tc(const GemmP& p0, cudaStream_t st) {
     rc = make_output_map(&mc, p);
     if (rc) return rc;
   }
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         Cfg::SMEM_BYTES);
-    if (e != cudaSuccess) {
-      set_error("cudaFuncSetAttribute(smem=%d) failed: %s", Cfg::SMEM_BYTES, cudaGetErrorString(e));
-      return MQDET_ERR_CUDA;
-    }
-    attr_set = true;
-  }
+  rc = ensure_dyn_smem(reinterpret_cast<const void*>(&gemm_tc_kernel<BN, STAGES>), Cfg::SMEM_BYTES);
+  if (rc) return rc;
   dim3 grid(cdiv(p.N, BN), cdiv(p.M, BM), p.nb1 * p.nb2);
   gemm_tc_kernel<BN, STAGES><<<grid, 256, Cfg::SMEM_BYTES, st>>>(ma, mb, mc, p);
   return check_launch("gemm_tc_kernel");
-}
-
-static int num_sms() {
-  static int n = 0;
-  if (!n) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    if (n <= 0) n = 148;
-  }
-  return n;
 }
 
 template <int BN, int STAGES, bool BRES>
@@ -1332,16 +1011,8 @@ static int launch_tcp(const GemmP& p0, cudaStream_t st) {
     rc = make_output_map(&mc_map, p);
     if (rc) return rc;
   }
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tcp_kernel<BN, STAGES, BRES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         Cfg::SMEM_BYTES);
-    if (e != cudaSuccess) {
-      set_error("cudaFuncSetAttribute(smem=%d) failed: %s", Cfg::SMEM_BYTES, cudaGetErrorString(e));
-      return MQDET_ERR_CUDA;
-    }
-    attr_set = true;
-  }
+  rc = ensure_dyn_smem(reinterpret_cast<const void*>(&gemm_tcp_kernel<BN, STAGES, BRES>), Cfg::SMEM_BYTES);
+  if (rc) return rc;
   const int tm = cdiv(p.M, BM), tn = cdiv(p.N, BN);
   const long Z = (long)p.nb1 * p.nb2;
   int mc = 1;
@@ -1436,50 +1107,3 @@ extern "C" int mqdet_gemm_f16(const mqdet_gemm_args* a, int impl, void* stream) 
   return launch_tcp<32, 4, false>(p, st);
 }
 
-extern "C" int mqdet_biattn_text(const void* k, int64_t k_ld, int64_t k_b1, int64_t k_b2, const void* q, int64_t q_ld,
-                                 int64_t q_b1, int64_t q_b2, const void* vvT, int64_t v_ld, int64_t v_b1, int64_t v_b2,
-                                 const float* stat, float clamp, void* out, int64_t o_ld, int64_t o_b1, int64_t o_b2,
-                                 int64_t nb1, int64_t nb2, int64_t T, int64_t N, int64_t Np, int64_t d, void* stream) {
-  MQ_REQUIRE(k && q && vvT && stat && out, "biattn_text: null pointer");
-  MQ_REQUIRE(d == 256, "biattn_text: head dim must be 256 (embed 2048 / 8 heads, fuse_helper.py:186-189), got %ld", (long)d);
-  MQ_REQUIRE(T >= 1 && T <= 256 && N >= 1 && Np >= N && (Np % 8) == 0, "biattn_text: need 1 <= T <= 256, Np >= N, Np %% 8 == 0");
-  MQ_REQUIRE(nb1 >= 1 && nb2 >= 1 && nb1 * nb2 <= 65535, "biattn_text: bad batch");
-  const int64_t lds[] = {k_ld, k_b1, k_b2, q_ld, q_b1, q_b2, v_ld, v_b1, v_b2, o_ld, o_b1, o_b2};
-  for (int64_t v : lds) MQ_REQUIRE((v % 8) == 0, "biattn_text: strides must be multiples of 8 elements");
-  MQ_REQUIRE(((uintptr_t)k % 16) == 0 && ((uintptr_t)q % 16) == 0 && ((uintptr_t)vvT % 16) == 0 && ((uintptr_t)out % 16) == 0,
-             "biattn_text: operands must be 16-byte aligned");
-  CUtensorMap mk, mq, mv, mo;
-  BtP p;
-  memset(&p, 0, sizeof(p));
-  int rc = make_operand_map(&mk, k, T, d, k_ld, (int)nb1, k_b1, (int)nb2, k_b2, BM, &p.k_bc1, &p.k_bc2);
-  if (rc) return rc;
-  rc = make_operand_map(&mq, q, N, d, q_ld, (int)nb1, q_b1, (int)nb2, q_b2, BT_STEP, &p.q_bc1, &p.q_bc2);
-  if (rc) return rc;
-  rc = make_operand_map(&mv, vvT, d, Np, v_ld, (int)nb1, v_b1, (int)nb2, v_b2, 256, &p.v_bc1, &p.v_bc2);  // box [64 n x 256 d]
-  if (rc) return rc;
-  GemmP o;
-  memset(&o, 0, sizeof(o));
-  o.C = out; o.c_dtype = MQDET_F16; o.M = T; o.N = d; o.nb1 = (int)nb1; o.nb2 = (int)nb2;
-  o.ldc = o_ld; o.c_b1 = o_b1; o.c_b2 = o_b2;
-  MQ_REQUIRE((nb1 == 1 || o_b1 != 0) && (nb2 == 1 || o_b2 != 0), "biattn_text: output batch strides must be non-zero");
-  rc = make_output_map(&mo, o);
-  if (rc) return rc;
-  p.stat = stat;
-  p.clamp = clamp;
-  p.nb1 = (int)nb1;
-  p.T = (int)T;
-  p.N = (int)N;
-  p.n_steps = (int)((N + BT_STEP - 1) / BT_STEP);
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(biattn_text_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BtCfg::SMEM_BYTES);
-    if (e != cudaSuccess) {
-      set_error("cudaFuncSetAttribute(smem=%d) failed: %s", BtCfg::SMEM_BYTES, cudaGetErrorString(e));
-      return MQDET_ERR_CUDA;
-    }
-    attr_set = true;
-  }
-  dim3 grid((unsigned)((T + BM - 1) / BM), (unsigned)(nb1 * nb2));
-  biattn_text_kernel<<<grid, 640, BtCfg::SMEM_BYTES, (cudaStream_t)stream>>>(mk, mq, mv, mo, p);
-  return check_launch("biattn_text_kernel");
-}

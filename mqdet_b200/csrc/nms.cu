@@ -254,11 +254,7 @@ extern "C" int mqdet_argsort_desc(const float* scores, int64_t n, int64_t* order
   if (n == 0) return MQDET_OK;
   int np2 = 1;
   while (np2 < n) np2 <<= 1;
-  static bool attr = false;
-  if (!attr) {
-    cudaFuncSetAttribute(argsort_desc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, NMS_MAX_N * 8);
-    attr = true;
-  }
+  if (int rc = ensure_dyn_smem(reinterpret_cast<const void*>(&argsort_desc_kernel), NMS_MAX_N * 8)) return rc;
   argsort_desc_kernel<<<1, 1024, (size_t)np2 * 8, (cudaStream_t)stream>>>(scores, (int)n, (long long*)order, nullptr, 0);
   return check_launch("argsort_desc_kernel");
 }
@@ -325,11 +321,7 @@ extern "C" int mqdet_ml_nms_batched(const float* boxes, const float* scores, con
   cudaMemsetAsync(flags, 0, (size_t)B * n_max, st);
   int np2 = 1;
   while (np2 < n_max) np2 <<= 1;
-  static bool attr = false;
-  if (!attr) {
-    cudaFuncSetAttribute(argsort_desc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, NMS_MAX_N * 8);
-    attr = true;
-  }
+  if (int rc = ensure_dyn_smem(reinterpret_cast<const void*>(&argsort_desc_kernel), NMS_MAX_N * 8)) return rc;
   argsort_desc_kernel<<<(unsigned)B, 1024, (size_t)np2 * 8, st>>>(scores, 0, order, counts_dev, (int)n_max);
   nms_gather_kernel<<<dim3(cdiv(n_max, 256), (unsigned)B), 256, 0, st>>>(boxes, scores, labels, order, 0, sorted, counts_dev,
                                                                          (int)n_max);

@@ -244,6 +244,48 @@ def biattn_text(kh, qh, vvT4, stat, clamp, out):
     return out
 
 
+def biattn_image(q, k, vlT, w_out16, bias, gamma, residual, mask, clamp, heads):
+    """Fused image -> text side + out-projection + layer scale + residual (mqdet_biattn_image).
+    q [B,N,E] fp16 (scaled), k [B,T,E], vlT [B,E,T], w_out16 [256,E] fp16; bias/gamma [256] fp32 or None; residual [B,N,256]
+    fp16 or None; mask [B,T] fp32 or None -> (out [B,N,256] fp16, colmax [B*H,T] fp32)."""
+    global launch_count
+    _need_cuda(q, k, vlT, w_out16, bias, gamma, residual, mask)
+    B, N, E = q.shape
+    T = k.shape[1]
+    for t in (q, k, vlT, w_out16):
+        if t.dtype != torch.float16 or t.stride(-1) != 1:
+            raise _lib.MqdetError("biattn_image: fp16 operands with a contiguous last dimension required")
+    out = torch.empty((B, N, 256), dtype=torch.float16, device=q.device)
+    colmax = torch.empty((B * heads, T), dtype=torch.float32, device=q.device)
+    ws = torch.empty((int(load().mqdet_biattn_image_workspace_floats(B, heads, N, T)),), dtype=torch.float32, device=q.device)
+    check(load().mqdet_biattn_image(_ptr(q), q.stride(1), q.stride(0), _ptr(k), k.stride(1), k.stride(0), _ptr(vlT), vlT.stride(1),
+                                    vlT.stride(0), _ptr(w_out16), w_out16.stride(0), _ptr(bias), _ptr(gamma), _ptr(residual),
+                                    residual.stride(1) if residual is not None else 0,
+                                    residual.stride(0) if residual is not None else 0, _ptr(mask), float(clamp), _ptr(out),
+                                    out.stride(1), out.stride(0), _ptr(colmax), _ptr(ws), B, heads, N, T, _stream()),
+          "biattn_image")
+    launch_count += 2
+    return out, colmax
+
+
+def biattn_text_vn(kh, qh, vn16, colmax, clamp, out):
+    """Fused text -> image attention on the image tokens themselves: kh [B,H,T,d], qh [B,H,N,d] (strided views), vn16 [B,N,256]
+    fp16, colmax [B*H,T] fp32 (from biattn_image), out [B,H,T,256] fp16 view <- softmax_n(scores)^T . vn."""
+    global launch_count
+    _need_cuda(kh, qh, vn16, colmax, out)
+    B, H, T, d = kh.shape
+    N = qh.shape[2]
+    for t in (kh, qh, vn16, out):
+        if t.stride(-1) != 1 or t.dtype != torch.float16:
+            raise _lib.MqdetError("biattn_text_vn: fp16 operands with a contiguous last dimension required")
+    check(load().mqdet_biattn_text_vn(_ptr(kh), kh.stride(2), kh.stride(1), kh.stride(0), _ptr(qh), qh.stride(2), qh.stride(1),
+                                      qh.stride(0), _ptr(vn16), vn16.stride(1), 0, vn16.stride(0), _ptr(colmax), float(clamp),
+                                      _ptr(out), out.stride(2), out.stride(1), out.stride(0), H, B, T, N, _stream()),
+          "biattn_text_vn")
+    launch_count += 1
+    return out
+
+
 def cast_f16(x):
     global launch_count
     _need_cuda(x)

@@ -87,6 +87,8 @@ class BiMultiHeadAttention(nn.Module):
         q = ops.gemm(vn16.view(B * N, Cv), w16(self.v_proj.weight), bias=f32(self.v_proj.bias), alpha=self.scale,
                      scale_after_bias=True).view(B, N, H, d)
         k = ops.gemm(ln16.view(B * T, -1), w16(self.l_proj.weight), bias=f32(self.l_proj.bias)).view(B, T, H, d)
+        if self.score_precision == "fused" and d == 256 and Cv == 256 and T % 8 == 0 and T <= 256:
+            return self._attend_fused(vn16, ln16, q, k, mask_l, clamp, v_epilogue, l_epilogue)
         vvT = torch.zeros((B, E, Np), dtype=torch.float16, device=dev) if Np != N else \
             torch.empty((B, E, Np), dtype=torch.float16, device=dev)
         ops.gemm(w16(self.values_v_proj.weight), vn16, out=vvT[:, :, :N], bias=f32(self.values_v_proj.bias),
@@ -125,6 +127,34 @@ class BiMultiHeadAttention(nn.Module):
         if not fused:
             ops.gemm(Pl, vvT.view(B, H, d, Np), out=ol.permute(0, 2, 1, 3))
         return self._finish(ov, ol, v_epilogue, l_epilogue, B, N, T, Cv)
+
+    def _attend_fused(self, vn16, ln16, q, k, mask_l, clamp, v_epilogue, l_epilogue):
+        """Product path: the score matrix never reaches HBM and stays fp32 until both softmaxes have been taken.
+          image side: ONE kernel = S (TMEM) -> masked row softmax -> P.V_l -> out-projection over the heads -> layer scale +
+                      residual; it also emits the column maxima of the scores;
+          text side : ONE kernel = S^T recomputed -> exp(. - column max) -> P^T . vn (the image tokens themselves; the value
+                      projection follows as a small per-head GEMM because sum_n p[n] = 1) with in-kernel column sums."""
+        B, N, Cv = vn16.shape
+        T = ln16.shape[1]
+        H, d, E = self.num_heads, self.head_dim, self.embed_dim
+        dev = vn16.device
+        ve = v_epilogue or {}
+        le = l_epilogue or {}
+        vlT = ops.gemm(w16(self.values_l_proj.weight), ln16, bias=f32(self.values_l_proj.bias), bias_mode=VEC_PER_ROW)
+        cm = mask_l.float().contiguous() if mask_l is not None else None
+        dv, colmax = ops.biattn_image(q.view(B, N, E), k.view(B, T, E), vlT, w16(self.out_v_proj.weight),
+                                      f32(self.out_v_proj.bias), ve.get("gate"), ve.get("residual"), cm, clamp, H)
+        qh, kh = q.permute(0, 2, 1, 3), k.permute(0, 2, 1, 3)
+        u = torch.empty((B, H, T, Cv), dtype=torch.float16, device=dev)
+        ops.biattn_text_vn(kh, qh, vn16, colmax, clamp, u)
+        # out_l[b, t, h, :] = u[b, h, t, :] . Wvv_h^T + b_h   (value projection after the token reduction)
+        ol = torch.empty((B, T, H, d), dtype=torch.float16, device=dev)
+        ops.gemm(u, w16(self.values_v_proj.weight).view(1, H, d, Cv), out=ol.permute(0, 2, 1, 3),
+                 bias=f32(self.values_v_proj.bias).view(H, d))
+        dl = ops.gemm(ol.view(B * T, E), w16(self.out_l_proj.weight), bias=f32(self.out_l_proj.bias),
+                      out_dtype=torch.float32, gate=le.get("gate"), gate_mode=VEC_PER_COL if le else 0,
+                      residual=le["residual"].view(B * T, -1) if le else None)
+        return dv, dl.view(B, T, -1)
 
     def _attend_f32_scores(self, qh, kh, vvT, vlT, mask_l, clamp, B, N, T, Np):
         """Diagnostic: both score matrices in fp32 (A and its transpose as two products), softmaxes on the fp32 values."""

@@ -35,9 +35,10 @@ def test_bi_attention_vs_oracle_and_golden(dev):
 
 
 def test_bi_attention_fused_equals_unfused(dev):
-    """The fused text->image kernel (tcgen05 S^T / exp / P.V with column statistics) and the one-pass statistics +
-    row-softmax kernel against the unfused path (transposed column softmax + GEMM, softmax_rows): same fp16 scores,
-    so the outputs agree far inside the oracle tolerance.  Ragged N (not a multiple of 64) and a T < 256 fallback."""
+    """The product path (image-side kernel: scores in TMEM -> softmax -> P.V_l -> out-projection -> layer scale + residual;
+    text-side kernel on the image tokens with in-kernel column sums) against the two unfused variants kept for A/B runs:
+    "f32" (fp32 score matrices in HBM, softmax_rows, plain GEMMs) and "f16" (round-1 path: fp16 score matrix, fused text
+    side with external statistics / transposed column softmax).  Ragged N (not a multiple of 64 / 128), T < 256, masks."""
     from mqdet_b200.config import mq_glip_t_cfg
     from mqdet_b200.utils.fuse_helper import BiAttentionBlockForCheckpoint
     from oracle import synth
@@ -46,18 +47,40 @@ def test_bi_attention_fused_equals_unfused(dev):
     blk = BiAttentionBlockForCheckpoint(v_dim=256, l_dim=768, embed_dim=2048, num_heads=8, hidden_dim=3072, dropout=0.1,
                                         drop_path=0.0, init_values=1.0 / 6, cfg=mq_glip_t_cfg())
     blk = load_sd(blk, sd).to(dev).eval()
-    for (B, N, T) in [(2, 1000, 256), (1, 333, 256), (2, 520, 64)]:
+    for (B, N, T) in [(2, 1000, 256), (1, 333, 256), (2, 520, 64), (3, 128, 256), (1, 2600, 200)]:
         v16 = gen.randn(B, N, 256).half().to(dev)
         l32 = gen.randn(B, T, 768).to(dev)
         mask = torch.ones(B, T, dtype=torch.long)
         mask[0, T // 3:] = 0
         mask = mask.to(dev)
-        blk.attn.fused_text_side = True
+        blk.attn.score_precision = "fused"
         v1, l1 = blk.forward_flat(v16, l32, mask)
-        blk.attn.fused_text_side = False
+        blk.attn.score_precision = "f32"
         v0, l0 = blk.forward_flat(v16, l32, mask)
-        assert_close(v1, v0, 1e-3, f"fused vs unfused visual stream {B, N, T}")
-        assert_close(l1, l0, 1e-3, f"fused vs unfused language stream {B, N, T}")
+        assert_close(v1, v0, 1e-3, f"fused vs f32-score visual stream {B, N, T}")
+        assert_close(l1, l0, 1e-3, f"fused vs f32-score language stream {B, N, T}")
+        if T == 256:
+            blk.attn.score_precision = "f16"
+            for fts in (True, False):
+                blk.attn.fused_text_side = fts
+                v2, l2 = blk.forward_flat(v16, l32, mask)
+                assert_close(v2, v0, 1e-3, f"f16-score (fused_text_side={fts}) vs f32-score visual stream {B, N, T}")
+                assert_close(l2, l0, 1e-3, f"f16-score (fused_text_side={fts}) vs f32-score language stream {B, N, T}")
+        blk.attn.score_precision = "fused"
+    # no mask at all, and an image whose tokens are ALL masked (uniform probabilities, like the reference's fp32 -9e15 sum)
+    v16 = gen.randn(2, 300, 256).half().to(dev)
+    l32 = gen.randn(2, 256, 768).to(dev)
+    va, la = blk.forward_flat(v16, l32, None)
+    blk.attn.score_precision = "f32"
+    vb, lb = blk.forward_flat(v16, l32, None)
+    assert_close(va, vb, 1e-3, "fused vs f32, no mask")
+    mask = torch.ones(2, 256, dtype=torch.long, device=dev)
+    mask[1] = 0
+    vd, ld = blk.forward_flat(v16, l32, mask)
+    blk.attn.score_precision = "fused"
+    vc, lc = blk.forward_flat(v16, l32, mask)
+    assert_close(vc, vd, 1e-3, "fused vs f32, fully masked image")
+    assert_close(lc, ld, 1e-3, "fused vs f32, fully masked image (language)")
 
 
 def test_dcn_cols_plain_equals_unfold(dev):
