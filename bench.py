@@ -79,6 +79,90 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
+def traffic_note():
+    """(dram bytes per launch of the dominant kernel from the committed ncu --set full capture, its source) or (None, why)."""
+    p = os.path.join(ROOT, "profiles", "r02_traffic.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d.get("dram_bytes_per_launch"), d.get("source")
+    return None, "no ncu --set full capture summarised in profiles/r02_traffic.json"
+
+
+# Algorithmic work per IMAGE and stage (SURVEY.md §8d, 80-class prompt, fp16 storage): (GFLOP, activation MB per image that
+# must cross HBM at least once, weight MB read once per step)
+STAGE_WORK = {
+    "swin": (96.0, 2 * 12.9 * 12, 55.0), "fpn": (28.0, 2 * 11.5, 7.0),
+    "preselect": (12.2, 2.86 + 0.8, 12.2), "gcp x6": (21.6, 6 * (0.79 + 0.61), 79.1),
+    "bert layers x18": (45.9 + 6 * 3.83, 18 * 0.79, 18 * 14.2),
+    "fusion x6 (biattention)": (860.1, 6 * (22.9 + 0.79), 6 * 12.6), "dyconv x6": (254.5, 6 * 3 * 23.0, 6 * 3.6),
+    "dot-product head": (2.94, 11.47 + 0.13 + 11.47, 0.4), "post-processing (atss + ml_nms)": (0.025, 11.5 + 0.36 + 3.2, 0.0),
+}
+
+
+def stage_profile(model, eager_step, B, pk):
+    """CUDA-event time of every stage of ONE eager forward + its algorithmic FLOPs / bytes (STAGE_WORK) -> per stage
+    {ms, tensor_frac, hbm_frac}: the north-star asks for both fractions on the GCP + fusion path."""
+    import torch
+    from mqdet_b200 import ops
+    import mqdet_b200.modeling.language_backbone.modeling_bert_new as mb
+    events, undo = [], []
+
+    def wrap(obj, name, label):
+        fn = getattr(obj, name)
+
+        def w(*a, **k):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            r = fn(*a, **k)
+            e1.record()
+            events.append((label, e0, e1))
+            return r
+        setattr(obj, name, w)
+        undo.append((obj, name, fn))
+
+    lm = model.language_backbone.body.model
+    wrap(model.backbone.body, "forward_flat", "swin")
+    wrap(model.backbone.fpn, "forward_flat", "fpn")
+    wrap(lm.pre_select, "forward", "preselect")
+    for blk in lm.encoder.qv_layer:
+        wrap(blk, "forward", "gcp x6")
+    wrap(mb.BertLayer, "forward", "bert layers x18")
+    tower = model.rpn.head.dyhead_tower
+    for i in range(0, len(tower), 3):
+        wrap(tower[i].b_attn, "forward_flat", "fusion x6 (biattention)")
+        wrap(tower[i + 2], "forward_flat", "dyconv x6")
+    wrap(ops, "atss_postprocess", "post-processing (atss + ml_nms)")
+    wrap(ops, "l2_normalize", "_head_start")
+    try:
+        for _ in range(2):
+            events.clear()
+            t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            t0.record()
+            eager_step()
+            t1.record()
+            torch.cuda.synchronize()
+    finally:
+        for obj, name, fn in reversed(undo):
+            setattr(obj, name, fn)
+    agg = {}
+    for label, a, b in events:
+        agg[label] = agg.get(label, 0.0) + a.elapsed_time(b)
+    # dot-product head = from l2_normalize to the start of the post-processing
+    hs = [a for lb, a, _ in events if lb == "_head_start"]
+    ps = [a for lb, a, _ in events if lb.startswith("post-processing")]
+    agg.pop("_head_start", None)
+    if hs and ps:
+        agg["dot-product head"] = hs[0].elapsed_time(ps[0])
+    out = {"eager_step_ms": t0.elapsed_time(t1)}
+    for label, ms_ in agg.items():
+        gf, act_mb, w_mb = STAGE_WORK[label]
+        flops, byts = gf * 1e9 * B, (act_mb * B + w_mb) * 1e6
+        out[label] = {"ms": round(ms_, 3), "algorithmic_gflop": round(flops / 1e9, 1), "algorithmic_mb": round(byts / 1e6, 1),
+                      "tensor_frac": round(flops / (ms_ / 1e3) / 1e12 / pk["tflops"], 4),
+                      "hbm_frac": round(byts / (ms_ / 1e3) / 1e9 / pk["hbm_gbs"], 4)}
+    return out
+
+
 def build_inputs(B, seed):
     import torch
     from tools import synth  # synthetic weights/inputs generator (not the measured path)
@@ -136,6 +220,7 @@ def main():
                          "(location, class) pairs above the 0.05 pre-NMS threshold; the candidate / detection counts it "
                          "yields are reported in config.postprocess (-1.5 is a denser stress point: every level hits top-k)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="launch the kernels eagerly instead of replaying the captured CUDA graph")
     ap.add_argument("--cpu-baseline-steps", type=int, default=1)
     args = ap.parse_args()
     if args.impl == "reference":
@@ -173,38 +258,51 @@ def main():
     sizes = [(H_IMG, W_IMG)] * B
     img_host = img.pin_memory()
     img_dev = img.to(dev)
-    from mqdet_b200 import parallel
+    from mqdet_b200.engine.inference import InferenceEngine
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)  # > 126 MB L2
-
-    def step(x):
-        out = model.forward_device(ImageList(x, sizes), caps, pmap)
-        # the ONE collective of the data path: fixed-shape per-image detections over NCCL / NVLink (identity at N = 1)
-        out["det_all"] = parallel.all_gather_packed(out["det_packed"])  # [world*B, max_out+1, 6]: detections + count row
-        return out
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
+    # one eager forward: counts the kernels of a step (the graph replays exactly these) and fills every cache
+    ops.launch_count = 0
+    model.forward_device(ImageList(img_dev, sizes), caps, pmap)
+    torch.cuda.synchronize()
+    launches_per_step = ops.launch_count
+    # The public inference API: the forward + the ONE collective captured as a CUDA graph, replayed per batch
+    # (mqdet_b200/engine/inference.py; --no-graph runs the same calls eagerly)
+    graph_note = "cuda-graph replay"
+    try:
+        engine = InferenceEngine(model, caps, pmap, tuple(img.shape), sizes, use_graph=not args.no_graph, warmup=max(1, args.warmup // 2))
+    except Exception as e:  # noqa: BLE001 - e.g. a collective that cannot be captured on this stack: fall back to eager launches
+        if args.no_graph:
+            raise
+        graph_note = f"eager (graph capture failed: {type(e).__name__}: {str(e)[:120]})"
+        torch.cuda.synchronize()
+        engine = InferenceEngine(model, caps, pmap, tuple(img.shape), sizes, use_graph=False, warmup=1)
+    if args.no_graph:
+        graph_note = "eager launches (--no-graph)"
+    engine.stage[0].copy_(img_dev)
+    engine.stage[1].copy_(img_dev)
+
     # ---- device-resident throughput ---------------------------------------------------------------------------------
     for _ in range(args.warmup):
-        step(img_dev)
+        engine.device_step()
     barrier()
     clocks = ClockSampler(local)  # rank 0 samples its own GPU (one nvidia-smi poller per node is enough)
     if rank == 0:
         clocks.start()
-    ops.launch_count = 0
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     barrier()
     for i in range(args.steps):
         flush.zero_()  # L2 flush between timed iterations (outside the per-step events)
         ev[i][0].record()
-        step(img_dev)
+        engine.device_step()
         ev[i][1].record()
     barrier()
-    launches = ops.launch_count - 0
-    clk = clocks.stop() if rank == 0 else None
+    launches = launches_per_step * args.steps
     ms = sum(a.elapsed_time(b) for a, b in ev) / args.steps
     t = torch.tensor([ms], device=dev)
     if world > 1:
@@ -213,62 +311,46 @@ def main():
     value = world * B / (ms / 1e3)
 
     # ---- end to end through the public API with host buffers ----------------------------------------------------------
-    # Every step's images start in pinned HOST memory and its detections end in pinned host memory, all inside the timed
-    # region.  The upload of step s+1 runs on a copy stream while step s computes (two device staging buffers), the way a
-    # prefetching data loader feeds the reference's `model(images.to(device))`; the forward itself is unchanged.
-    stage = [torch.empty_like(img_dev), torch.empty_like(img_dev)]
-    det_host = torch.empty((B, model.max_out() + 1, 6), dtype=torch.float32).pin_memory()  # detections + count row
-    copy_stream = torch.cuda.Stream()
-    main = torch.cuda.current_stream()
-    up_done = [torch.cuda.Event(), torch.cuda.Event()]     # upload into stage[k] finished
-    fw_done = [torch.cuda.Event(), torch.cuda.Event()]     # the forward that read stage[k] finished
-
-    def upload(k):
-        with torch.cuda.stream(copy_stream):
-            copy_stream.wait_event(fw_done[k])               # stage[k] is no longer being read
-            stage[k].copy_(img_host, non_blocking=True)
-            up_done[k].record(copy_stream)
-
-    def e2e_steps(n):
-        upload(0)
-        for s_ in range(n):
-            k = s_ & 1
-            if s_ + 1 < n:
-                upload(k ^ 1)
-            main.wait_event(up_done[k])
-            o_ = step(stage[k])
-            fw_done[k].record(main)
-            det_host.copy_(o_["det_packed"], non_blocking=True)
-        return o_
-
-    for ev_ in fw_done:
-        ev_.record(main)
-    e2e_steps(2)
+    # `for boxlists in engine.run(batches)`: every batch starts in pinned HOST memory and ends as list[BoxList] built from the
+    # pinned host copy of the packed result — H2D (103 MB), forward, all-gather, D2H and BoxList construction all inside the
+    # timed region.  The engine uploads batch s+1 on a copy stream while batch s computes (a prefetching data loader).
+    for _ in engine.run([img_host] * 2):
+        pass
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    n_boxes = 0
+    t_wall = time.time()
     e0.record()
-    o = e2e_steps(args.steps)
+    for boxlists in engine.run([img_host] * args.steps):
+        n_boxes += sum(len(bl) for bl in boxlists)
     e1.record()
     barrier()
-    e2e_ms = e0.elapsed_time(e1) / args.steps
+    e2e_wall_ms = 1e3 * (time.time() - t_wall) / args.steps
+    e2e_ms = max(e0.elapsed_time(e1) / args.steps, 0.0)
     t = torch.tensor([e2e_ms], device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_ms = float(t.item())
+    clk = clocks.stop() if rank == 0 else None
     # operating point of the post-processing (what the synthetic weights make it do), from the last step's device counters
+    o = engine.outs[0]["raw"] if engine.use_graph else model.forward_device(ImageList(img_dev, sizes), caps, pmap)
     pp = {"bias0": args.bias0, "pre_nms_thresh": 0.05,
           "pre_nms_boxes_per_image_after_topk": float(o["cand_totals"].float().mean().item()),
           "detections_per_image": float(o["num"].float().mean().item())}
 
-    # ---- roofline of the dominant kernel (the tcgen05 GEMM): every launch timed with CUDA events on its stream --------
+    # ---- roofline of the dominant kernel family (the tcgen05 GEMM): every launch timed with CUDA events on its stream ----
+    def eager_step():
+        return model.forward_device(ImageList(img_dev, sizes), caps, pmap)
+
     prof = ops.GEMM_PROFILE = []
-    step(img_dev)
+    eager_step()
     torch.cuda.synchronize()
     ops.GEMM_PROFILE = None
     g_ms = sum(a.elapsed_time(b) for a, b, _, _ in prof)
     g_flops = sum(f for _, _, f, _ in prof)
     pk = peaks()
     achieved = g_flops / (g_ms / 1e3) / 1e12 if g_ms > 0 else 0.0
+    stages = stage_profile(model, eager_step, B, pk) if rank == 0 else None
 
     if rank == 0:
         res = {
@@ -279,14 +361,18 @@ def main():
                                    f"head, ATSS+ml_nms), batch {B}/GPU, 800x1333 (padded 800x1344), 80-class prompt T=256, "
                                    f"K=5 queries/class (BASELINE config 2), random-init weights",
                        "global_batch": world * B, "parallelism": f"image-sharded dp{world}, 1 NCCL all-gather of [B,{model.max_out() + 1},6] (detections + count row)",
-                       "l2": "256 MiB buffer written between timed steps", "postprocess": pp},
+                       "launch": graph_note, "l2": "256 MiB buffer written between timed steps", "postprocess": pp,
+                       "tokenisation": "pre-tokenised ids (no bert-base-uncased vocabulary offline); prompt state cached per prompt"},
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": pk["tflops"], "unit": "TFLOP/s",
-                         "frac": achieved / pk["tflops"], "traffic": None, "peak_source": pk["src"],
+                         "frac": achieved / pk["tflops"], "traffic": traffic_note()[0], "peak_source": pk["src"],
                          "kernel": "gemm_tcp_kernel (persistent tcgen05 GEMM, all shapes of one step)", "launches": len(prof),
                          "kernel_ms_per_step": g_ms, "kernel_share_of_step": g_ms / ms,
-                         "algorithmic_tflop_per_step": g_flops / 1e12},
-            "e2e": {"value": world * B / (e2e_ms / 1e3), "unit": "images/s", "ms_per_step": e2e_ms,
-                    "h2d_bytes_per_step": img_host.numel() * 4, "d2h_bytes_per_step": det_host.numel() * 4},
+                         "algorithmic_tflop_per_step": g_flops / 1e12, "traffic_source": traffic_note()[1],
+                         "stages": stages},
+            "e2e": {"value": world * B / (e2e_ms / 1e3), "unit": "images/s", "ms_per_step": e2e_ms, "wall_ms_per_step": e2e_wall_ms,
+                    "h2d_bytes_per_step": img_host.numel() * 4, "d2h_bytes_per_step": engine.host[0].numel() * 4,
+                    "api": "mqdet_b200.engine.inference.InferenceEngine.run(host batches) -> list[BoxList] per batch",
+                    "boxes_returned": n_boxes},
             "gpu_launches": launches, "clocks": clk,
         }
         if not args.no_cpu_baseline and world == 1:

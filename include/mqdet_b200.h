@@ -250,7 +250,10 @@ int mqdet_dyrelu_apply(const void* mid, const float* coef, const int32_t* level_
 
 /* ---- ATSS post-processing (rpn/inference.py:620-769), device-resident, no host synchronisation ------------------
  * logits [B,N,T] (fp16/fp32), reg_ctr [B,N,5] fp32 (4 box deltas before the per-level Scale, 1 centerness logit),
- * tokmap_dev int32 [C][max_tok] token positions of class c+1 padded with -1 (the positive map), level tables on
+ * tokmap_dev int32 [C][max_tok] token positions of score column c padded with -1 (the positive map) — one table for the
+ * batch (tokmap_img_stride 0) or one per image (stride in int32 elements: prompt chunks batched as images); class_labels
+ * int32 [C] (labels_img_stride 0) / per image, or NULL: the label of column c is class_labels[c], default c + 1
+ * (convert_grounding_to_od_logits / _v2, rpn/inference.py:772-824); level tables on
  * the HOST (level_hw int32 [nlev][2], strides / base_anchors [nlev][4] / reg_scales [nlev] floats).
  * Per (image, level): sigmoid -> class mean -> score > pre_nms_thresh -> rank = score*sigmoid(ctr) -> exact top-k
  * (ties by ascending (location, class)) -> BoxCoder.decode against the generated anchor -> clip -> sqrt(rank).
@@ -258,7 +261,8 @@ int mqdet_dyrelu_apply(const void* mid, const float* coef, const int32_t* level_
  * [B][nlev]; dense concatenation cat_* (level 0 first) with totals[B].  out_key (optional) = level<<40|loc<<12|cls.
  * cand_ws: mqdet_atss_workspace_bytes(...) bytes. */
 int64_t mqdet_atss_workspace_bytes(const int32_t* level_hw, int64_t nlev, int64_t C, int64_t B);
-int mqdet_atss_candidates(const void* logits, int logits_dtype, const float* reg_ctr, const int32_t* tokmap_dev, int64_t C,
+int mqdet_atss_candidates(const void* logits, int logits_dtype, const float* reg_ctr, const int32_t* tokmap_dev,
+                          int64_t tokmap_img_stride, const int32_t* class_labels, int64_t labels_img_stride, int64_t C,
                           int64_t max_tok, int64_t T, const int32_t* level_hw, int64_t nlev, const float* strides,
                           const float* base_anchors, const float* reg_scales, int64_t B, float pre_nms_thresh, int64_t topk,
                           int64_t out_stride, float img_w, float img_h, void* cand_ws, int32_t* level_counts,

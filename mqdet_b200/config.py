@@ -44,3 +44,16 @@ def mq_glip_t_cfg(**over):
             node = getattr(node, p)
         setattr(node, parts[-1], v)
     return cfg
+
+
+def mq_glip_l_cfg(**over):
+    """configs/pretrain/mq-glip-l.yaml: Swin-L backbone (embed 192, depths 2/2/18/2, heads 6/12/24/48, window 12), 8 fusion
+    layers; with the LVIS evaluation keys of configs/vision_query_5shot/lvis_minival.yaml (300 detections per prompt chunk,
+    chunks of 40 classes, 3000 score columns in the reference's convert_grounding_to_od_logits_v2)."""
+    base = {"MODEL.SWINT.EMBED_DIM": 192, "MODEL.SWINT.DEPTHS": (2, 2, 18, 2), "MODEL.SWINT.NUM_HEADS": (6, 12, 24, 48),
+            "MODEL.SWINT.WINDOW_SIZE": 12, "MODEL.SWINT.OUT_CHANNELS": (192, 384, 768, 1536), "MODEL.DYHEAD.NUM_CONVS": 8,
+            "MODEL.ATSS.DETECTIONS_PER_IMG": 300, "TEST.MDETR_STYLE_AGGREGATE_CLASS_NUM": 3000}
+    base.update(over)
+    cfg = mq_glip_t_cfg(**base)
+    cfg.TEST.CHUNKED_EVALUATION = 40
+    return cfg

@@ -42,9 +42,9 @@ struct BtCfg {
   static constexpr int Q_BYTES = BT_STEP * BK * 2;    // one k-block [256 n x 64 d]
   static constexpr int V_BYTES = 256 * BT_SUB * 2;    // Vv^T tile [256 d x 64 n]  /  VN: image-token tile [64 n x 256 c]
   static constexpr int P_BYTES = BM * BT_SUB * 2;     // P tile [128 t x 64 n]
-  static constexpr int SMEM_BYTES = KT_BYTES + 2 * Q_BYTES + 2 * V_BYTES + 2 * P_BYTES + 1024 /*align*/ + 256 /*barriers*/ +
-                                    4 * BM * 4 /*VN: partial column sums*/;
+  static constexpr int SMEM_BYTES = KT_BYTES + 2 * Q_BYTES + 2 * V_BYTES + 2 * P_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 };
+static_assert(BtCfg::SMEM_BYTES <= 232448, "biattn_text: dynamic shared memory above the 227 KB per-CTA limit");
 struct BtP {
   const float* stat;  // [Z][2][T]: column max, 1 / column sum   (VN: [Z][T] column max only)
   float clamp;
@@ -75,7 +75,8 @@ __global__ void __launch_bounds__(640, 1) biattn_text_kernel(const __grid_consta
   uint64_t* s_empty = bars + 12;  // S^T accumulator copied to registers by the 16 exp warps
   uint64_t* o_full = bars + 13;
   uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(bars + 14);
-  float* lsum_sm = reinterpret_cast<float*>(bars + 32);  // [4 parts][128 rows] (VN)
+  // VN: [4 parts][128 rows] partial column sums, exchanged after the last S^T product has retired -> the K tile is free
+  float* lsum_sm = reinterpret_cast<float*>(kt);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int mt = blockIdx.x, z = blockIdx.y;
@@ -318,6 +319,7 @@ struct BiCfg {
   static constexpr int EXTRA_BYTES = (4 * BM * 2 + 4 * 256 + 256 + 512) * 4;  // rx, cmx, keep, s_vec|t_vec
   static constexpr int SMEM_BYTES = PX_BYTES + BI_STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + EXTRA_BYTES;
 };
+static_assert(BiCfg::SMEM_BYTES <= 232448, "biattn_image: dynamic shared memory above the 227 KB per-CTA limit");
 struct BiP {
   const float* mask;   // [B][T] 1 keep / 0 padding, or nullptr
   const float* bias;   // [256] out-projection bias

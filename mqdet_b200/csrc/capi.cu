@@ -171,6 +171,7 @@ int ensure_dyn_smem(const void* func, int bytes) {
   cudaError_t e = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
   if (e != cudaSuccess) {
     set_error("cudaFuncSetAttribute(smem=%d) failed: %s", bytes, cudaGetErrorString(e));
+    (void)cudaGetLastError();  // the failure is reported here; do not leave it for the caller's next CUDA call
     return MQDET_ERR_CUDA;
   }
   std::lock_guard<std::mutex> g(mu);

@@ -36,8 +36,8 @@ __device__ __forceinline__ float ord2f(unsigned int u) {
 
 template <typename T>
 __global__ void __launch_bounds__(256) atss_candidates_kernel(const T* __restrict__ logits, const float* __restrict__ reg_ctr,
-                                                              const int* __restrict__ tokmap, int C, int max_tok, int Tn,
-                                                              PPLevels lv, int B, float thresh,
+                                                              const int* __restrict__ tokmap, long tokmap_img_stride, int C,
+                                                              int max_tok, int Tn, PPLevels lv, int B, float thresh,
                                                               unsigned long long* __restrict__ cand, int* __restrict__ counts,
                                                               long cand_per_img) {
   __shared__ float sig[8][PP_MAX_T];
@@ -57,7 +57,7 @@ __global__ void __launch_bounds__(256) atss_candidates_kernel(const T* __restric
   const float cs = 1.f / (1.f + expf(-reg_ctr[gw * 5 + 4]));
   const int loc = pn - lv.off[l];
   for (int c = lane; c < C; c += 32) {
-    const int* tm = tokmap + c * max_tok;
+    const int* tm = tokmap + (long)b * tokmap_img_stride + c * max_tok;
     float s = 0.f;
     int n = 0;
     for (int j = 0; j < max_tok; ++j) {
@@ -91,6 +91,7 @@ __global__ void __launch_bounds__(256) atss_candidates_kernel(const T* __restric
 __global__ void __launch_bounds__(1024) atss_select_decode_kernel(const unsigned long long* __restrict__ cand,
                                                                   const int* counts,
                                                                   const float* __restrict__ reg_ctr, PPLevels lv, int C,
+                                                                  const int* __restrict__ class_labels, long labels_img_stride,
                                                                   int topk, float img_w, float img_h, long cand_per_img,
                                                                   int out_per_img, float* __restrict__ out_boxes,
                                                                   float* __restrict__ out_scores,
@@ -198,7 +199,9 @@ __global__ void __launch_bounds__(1024) atss_select_decode_kernel(const unsigned
     float* ob = out_boxes + (obase + tid) * 4;
     ob[0] = x1; ob[1] = y1; ob[2] = x2; ob[3] = y2;
     out_scores[obase + tid] = sqrtf(rank);
-    out_labels[obase + tid] = (float)(cls + 1);
+    // label of score column `cls`: cls + 1 (convert_grounding_to_od_logits :772-790) unless a label table is given (prompt
+    // chunks of a many-category vocabulary: the columns of a chunk are its classes in ascending label order)
+    out_labels[obase + tid] = class_labels ? (float)class_labels[(long)b * labels_img_stride + cls] : (float)(cls + 1);
     if (out_key) out_key[obase + tid] = ((long long)l << 40) | ((long long)loc << 12) | (long long)cls;
   }
   if (tid == 0) out_counts[b * lv.n + l] = k;
@@ -302,6 +305,7 @@ static int fill_pp_levels(PPLevels* lv, const int32_t* level_hw, int64_t nlev, c
 }
 
 extern "C" int mqdet_atss_candidates(const void* logits, int logits_dtype, const float* reg_ctr, const int32_t* tokmap_dev,
+                                     int64_t tokmap_img_stride, const int32_t* class_labels, int64_t labels_img_stride,
                                      int64_t C, int64_t max_tok, int64_t T, const int32_t* level_hw, int64_t nlev,
                                      const float* strides, const float* base_anchors, const float* reg_scales, int64_t B,
                                      float pre_nms_thresh, int64_t topk, int64_t out_stride, float img_w, float img_h,
@@ -326,17 +330,18 @@ extern "C" int mqdet_atss_candidates(const void* logits, int logits_dtype, const
   const long warps = B * (long)N;
   if (logits_dtype == MQDET_F32)
     atss_candidates_kernel<float><<<(unsigned)((warps + 7) / 8), 256, 0, st>>>(
-        (const float*)logits, reg_ctr, tokmap_dev, (int)C, (int)max_tok, (int)T, lv, (int)B, pre_nms_thresh,
+        (const float*)logits, reg_ctr, tokmap_dev, (long)tokmap_img_stride, (int)C, (int)max_tok, (int)T, lv, (int)B, pre_nms_thresh,
         (unsigned long long*)cand_ws, level_counts, cand_per_img);
   else
     atss_candidates_kernel<__half><<<(unsigned)((warps + 7) / 8), 256, 0, st>>>(
-        (const __half*)logits, reg_ctr, tokmap_dev, (int)C, (int)max_tok, (int)T, lv, (int)B, pre_nms_thresh,
+        (const __half*)logits, reg_ctr, tokmap_dev, (long)tokmap_img_stride, (int)C, (int)max_tok, (int)T, lv, (int)B, pre_nms_thresh,
         (unsigned long long*)cand_ws, level_counts, cand_per_img);
   int rc = check_launch("atss_candidates_kernel");
   if (rc) return rc;
   // level_counts is rewritten in place with min(count, topk) by the select kernel (it reads the raw count first)
   atss_select_decode_kernel<<<(unsigned)(B * nlev), 1024, 0, st>>>((const unsigned long long*)cand_ws, level_counts, reg_ctr,
-                                                                  lv, (int)C, (int)topk, img_w, img_h, cand_per_img,
+                                                                  lv, (int)C, class_labels, (long)labels_img_stride, (int)topk,
+                                                                  img_w, img_h, cand_per_img,
                                                                   out_per_img, out_boxes, out_scores, out_labels,
                                                                   (long long*)out_key, level_counts);
   rc = check_launch("atss_select_decode_kernel");

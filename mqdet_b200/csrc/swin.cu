@@ -28,15 +28,16 @@ __global__ void patchify4_kernel(const float* __restrict__ img, int B, int H, in
   out[i] = __float2half_rn(v);
 }
 
-// Window attention for one (window, head): head_dim 32, window 7x7 (N = 49 tokens).
+// Window attention for one (window, head): head_dim 32, window WS x WS (N = 49 tokens for Swin-T, 144 for Swin-L).
 // qkv [B*H*W, 3*C] fp16 (q | k | v, each C = heads*32 wide); bias_dense [heads][N][N] fp32 (relative position bias);
 // padded tokens (beyond H/W after padding to a multiple of the window) carry qkv = qkv_bias because the reference
 // pads the NORMALISED input with zeros before the qkv Linear (:200-205); cyclic shift + region mask (-100) are index math.
 //
-// One WARP per (window, head), 49 tokens padded to 64 x 56: S = Q K^T and O = P V run on mma.sync.m16n8k16 (fp16 in,
-// fp32 accumulate; a 49x49x32 problem is far below the tcgen05 tile), softmax in the accumulator fragments (quad
-// shuffles), P re-used as the A fragment of the second product (no shared-memory round trip); V is staged transposed
-// in shared memory (B fragments need two consecutive KEYS per register).
+// One CTA (4 warps) per (window, head).  The window's q / k / v head slices (64 B per token each) are staged in shared
+// memory with 16-byte loads (v transposed: the B fragments of P.V need two consecutive KEYS per register); warp w then
+// takes the 16-query tiles w, w+4, ...: S = Q K^T and O = P V on mma.sync.m16n8k16 (fp16 in, fp32 accumulate — a
+// 49x49x32 / 144x144x32 problem per head is far below a tcgen05 tile), softmax in the accumulator fragments (quad
+// shuffles), P re-used as the A fragment of the second product (no shared-memory round trip).
 __device__ __forceinline__ void mma_16816(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
   asm volatile(
       "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
@@ -49,27 +50,38 @@ __device__ __forceinline__ uint32_t pack_h2(float x, float y) {
 }
 
 template <int WS>
+struct SwinCfg {
+  static constexpr int N = WS * WS;
+  static constexpr int NP = (N + 15) / 16 * 16;   // tokens padded to whole 16-row query tiles / 16-key steps
+  static constexpr int NT = NP / 8;               // key tiles of 8
+  static constexpr int QLD = 40;                  // halfs per staged q / k row (32 + 8: conflict-free 4-byte fragment loads)
+  static constexpr int VLD = NP + 8;              // halfs per staged v^T row
+  static constexpr int SMEM = (2 * NP * QLD + 32 * VLD) * 2 + 2 * NP * 4;
+};
+
+template <int WS>
 __global__ void __launch_bounds__(128) swin_window_attn_kernel(const __half* __restrict__ qkv, const float* __restrict__ qkv_bias,
                                                                const float* __restrict__ bias_dense, int B, int H, int W,
                                                                int heads, int shift, float scale, __half* __restrict__ out) {
-  constexpr int N = WS * WS, D = 32, NP = 64, VLD = 72;
-  static_assert(N <= 56, "key padding assumes <= 56 tokens per window");
+  using Cfg = SwinCfg<WS>;
+  constexpr int N = Cfg::N, D = 32, NP = Cfg::NP, NT = Cfg::NT, QLD = Cfg::QLD, VLD = Cfg::VLD;
   const int C = heads * D;
   const int Hp = (H + WS - 1) / WS * WS, Wp = (W + WS - 1) / WS * WS;
   const int nWw = Wp / WS, nW = (Hp / WS) * nWw;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const long unit = (long)blockIdx.x * 4 + warp;  // (b, window, head), head fastest
-  if (unit >= (long)B * nW * heads) return;
+  const long unit = blockIdx.x;  // (b, window, head), head fastest: the heads of a window read the same token rows
   const int head = (int)(unit % heads);
   const int win = (int)((unit / heads) % nW);
   const int b = (int)(unit / ((long)heads * nW));
   const int wi = win / nWw, wj = win % nWw;
-  __shared__ __align__(16) __half vT[4][D][VLD];
-  __shared__ int s_tok[4][NP], s_reg[4][NP];
-  int* tok = s_tok[warp];
-  int* reg = s_reg[warp];
-  for (int t = lane; t < NP; t += 32) {
-    int tk = -2, rg = 0;  // -2: beyond the 49 window tokens
+  extern __shared__ __align__(16) uint8_t swin_smem[];
+  __half* qs = reinterpret_cast<__half*>(swin_smem);   // [NP][QLD]
+  __half* ks = qs + NP * QLD;                           // [NP][QLD]
+  __half* vT = ks + NP * QLD;                           // [32][VLD]
+  int* tok = reinterpret_cast<int*>(vT + 32 * VLD);     // [NP]
+  int* reg = tok + NP;                                  // [NP]
+  for (int t = threadIdx.x; t < NP; t += 128) {
+    int tk = -2, rg = 0;  // -2: beyond the window's tokens
     if (t < N) {
       const int r = t / WS, c = t % WS;
       const int hs = wi * WS + r, wsft = wj * WS + c;              // coordinate in the shifted, padded frame
@@ -84,64 +96,61 @@ __global__ void __launch_bounds__(128) swin_window_attn_kernel(const __half* __r
     tok[t] = tk;
     reg[t] = rg;
   }
-  __syncwarp();
+  __syncthreads();
   const __half* base = qkv + (long)b * H * W * 3 * C + head * D;
-  // V^T -> shared: vT[d][j] (zero for j >= N)
-  for (int i = lane; i < NP * (D / 2); i += 32) {
-    const int j = i / (D / 2), d2 = (i % (D / 2)) * 2;
-    __half2 v = __float2half2_rn(0.f);
-    if (j < N) {
-      const int tk = tok[j];
-      if (tk >= 0) v = *reinterpret_cast<const __half2*>(base + (long)tk * 3 * C + 2 * C + d2);
-      else v = __floats2half2_rn(qkv_bias[2 * C + head * D + d2], qkv_bias[2 * C + head * D + d2 + 1]);
+  // stage q | k | v of the window: 12 x 16-byte pieces per token (which = piece / 4, 8 dims each)
+  for (int i = threadIdx.x; i < NP * 12; i += 128) {
+    const int t = i / 12, piece = i - t * 12, which = piece >> 2, d0 = (piece & 3) * 8;
+    const int tk = tok[t];
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (tk >= 0) {
+      v = __ldg(reinterpret_cast<const uint4*>(base + (long)tk * 3 * C + which * C + d0));
+    } else if (tk == -1) {
+      const float* bp = qkv_bias + which * C + head * D + d0;
+      v.x = pack_h2(bp[0], bp[1]); v.y = pack_h2(bp[2], bp[3]); v.z = pack_h2(bp[4], bp[5]); v.w = pack_h2(bp[6], bp[7]);
     }
-    vT[warp][d2][j] = __low2half(v);
-    vT[warp][d2 + 1][j] = __high2half(v);
+    if (which == 0) {
+      *reinterpret_cast<uint4*>(qs + t * QLD + d0) = v;
+    } else if (which == 1) {
+      *reinterpret_cast<uint4*>(ks + t * QLD + d0) = v;
+    } else {
+      const __half* hv = reinterpret_cast<const __half*>(&v);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) vT[(d0 + e) * VLD + t] = hv[e];
+    }
   }
-  __syncwarp();
+  __syncthreads();
   const int g = lane >> 2, t4 = lane & 3;
-  // 4-byte fetch of two consecutive dims of token slot `slot` (q: which = 0, k: which = 1)
-  auto ld2 = [&](int slot, int which, int dim) -> uint32_t {
-    const int tk = (slot < NP) ? tok[slot] : -2;
-    if (tk >= 0) return *reinterpret_cast<const uint32_t*>(base + (long)tk * 3 * C + which * C + dim);
-    if (tk == -1) return pack_h2(qkv_bias[which * C + head * D + dim], qkv_bias[which * C + head * D + dim + 1]);
-    return 0u;
-  };
-  // K fragments: 7 key tiles x 2 k-steps x 2 registers, kept for all query tiles
-  uint32_t kf[7][2][2];
-#pragma unroll
-  for (int nj = 0; nj < 7; ++nj)
-#pragma unroll
-    for (int ki = 0; ki < 2; ++ki) {
-      kf[nj][ki][0] = ld2(8 * nj + g, 1, 16 * ki + 2 * t4);
-      kf[nj][ki][1] = ld2(8 * nj + g, 1, 16 * ki + 2 * t4 + 8);
-    }
   const float* bd = bias_dense + (long)head * N * N;
 #pragma unroll 1
-  for (int mi = 0; mi < 4; ++mi) {
+  for (int mi = warp; mi * 16 < N; mi += 4) {
     const int r0 = 16 * mi + g, r1 = r0 + 8;  // the two query rows this lane holds
-    if (16 * mi >= N) break;
     uint32_t qf[2][4];
 #pragma unroll
     for (int ki = 0; ki < 2; ++ki) {
-      qf[ki][0] = ld2(r0, 0, 16 * ki + 2 * t4);
-      qf[ki][1] = ld2(r1, 0, 16 * ki + 2 * t4);
-      qf[ki][2] = ld2(r0, 0, 16 * ki + 2 * t4 + 8);
-      qf[ki][3] = ld2(r1, 0, 16 * ki + 2 * t4 + 8);
+      qf[ki][0] = *reinterpret_cast<const uint32_t*>(qs + r0 * QLD + 16 * ki + 2 * t4);
+      qf[ki][1] = *reinterpret_cast<const uint32_t*>(qs + r1 * QLD + 16 * ki + 2 * t4);
+      qf[ki][2] = *reinterpret_cast<const uint32_t*>(qs + r0 * QLD + 16 * ki + 2 * t4 + 8);
+      qf[ki][3] = *reinterpret_cast<const uint32_t*>(qs + r1 * QLD + 16 * ki + 2 * t4 + 8);
     }
-    float sacc[7][4];
+    float sacc[NT][4];
 #pragma unroll
-    for (int nj = 0; nj < 7; ++nj) {
+    for (int nj = 0; nj < NT; ++nj) {
 #pragma unroll
       for (int e = 0; e < 4; ++e) sacc[nj][e] = 0.f;
-      mma_16816(sacc[nj], qf[0], kf[nj][0]);
-      mma_16816(sacc[nj], qf[1], kf[nj][1]);
+      uint32_t kf0[2], kf1[2];
+      kf0[0] = *reinterpret_cast<const uint32_t*>(ks + (8 * nj + g) * QLD + 2 * t4);
+      kf0[1] = *reinterpret_cast<const uint32_t*>(ks + (8 * nj + g) * QLD + 2 * t4 + 8);
+      kf1[0] = *reinterpret_cast<const uint32_t*>(ks + (8 * nj + g) * QLD + 16 + 2 * t4);
+      kf1[1] = *reinterpret_cast<const uint32_t*>(ks + (8 * nj + g) * QLD + 16 + 2 * t4 + 8);
+      mma_16816(sacc[nj], qf[0], kf0);
+      mma_16816(sacc[nj], qf[1], kf1);
     }
     // scale, relative position bias, shift mask, key padding; row max
     const int rg0 = (r0 < N) ? reg[r0] : 0, rg1 = (r1 < N) ? reg[r1] : 0;
     float mx0 = -INFINITY, mx1 = -INFINITY;
 #pragma unroll
-    for (int nj = 0; nj < 7; ++nj)
+    for (int nj = 0; nj < NT; ++nj)
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         const int j = 8 * nj + 2 * t4 + (e & 1);
@@ -160,7 +169,7 @@ __global__ void __launch_bounds__(128) swin_window_attn_kernel(const __half* __r
     mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
     float sum0 = 0.f, sum1 = 0.f;
 #pragma unroll
-    for (int nj = 0; nj < 7; ++nj)
+    for (int nj = 0; nj < NT; ++nj)
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         const float m = (e < 2) ? mx0 : mx1;
@@ -179,21 +188,17 @@ __global__ void __launch_bounds__(128) swin_window_attn_kernel(const __half* __r
 #pragma unroll
       for (int e = 0; e < 4; ++e) oacc[ni][e] = 0.f;
 #pragma unroll
-    for (int kj = 0; kj < 4; ++kj) {
+    for (int kj = 0; kj < NT / 2; ++kj) {
       uint32_t pf[4];
       pf[0] = pack_h2(sacc[2 * kj][0], sacc[2 * kj][1]);
       pf[1] = pack_h2(sacc[2 * kj][2], sacc[2 * kj][3]);
-      if (2 * kj + 1 < 7) {
-        pf[2] = pack_h2(sacc[2 * kj + 1][0], sacc[2 * kj + 1][1]);
-        pf[3] = pack_h2(sacc[2 * kj + 1][2], sacc[2 * kj + 1][3]);
-      } else {
-        pf[2] = pf[3] = 0u;
-      }
+      pf[2] = pack_h2(sacc[2 * kj + 1][0], sacc[2 * kj + 1][1]);
+      pf[3] = pack_h2(sacc[2 * kj + 1][2], sacc[2 * kj + 1][3]);
 #pragma unroll
       for (int ni = 0; ni < 4; ++ni) {
         uint32_t vf[2];
-        vf[0] = *reinterpret_cast<const uint32_t*>(&vT[warp][8 * ni + g][16 * kj + 2 * t4]);
-        vf[1] = *reinterpret_cast<const uint32_t*>(&vT[warp][8 * ni + g][16 * kj + 2 * t4 + 8]);
+        vf[0] = *reinterpret_cast<const uint32_t*>(vT + (8 * ni + g) * VLD + 16 * kj + 2 * t4);
+        vf[1] = *reinterpret_cast<const uint32_t*>(vT + (8 * ni + g) * VLD + 16 * kj + 2 * t4 + 8);
         mma_16816(oacc[ni], pf, vf);
       }
     }
@@ -341,14 +346,21 @@ extern "C" int mqdet_swin_window_attn(const void* qkv, const float* qkv_bias, co
                                       int64_t W, int64_t heads, int64_t window, int64_t shift, float scale, void* out,
                                       void* stream) {
   MQ_REQUIRE(qkv && qkv_bias && bias_dense && out, "swin_window_attn: null pointer");
-  MQ_REQUIRE(window == 7, "swin_window_attn: window 7 only (Swin-T/GLIP-T; Swin-L's 12x12 is SURVEY.md §8f)");
+  MQ_REQUIRE(window == 7 || window == 12, "swin_window_attn: window 7 (Swin-T) or 12 (Swin-L), got %ld", (long)window);
   MQ_REQUIRE(shift >= 0 && shift < window, "swin_window_attn: bad shift");
+  MQ_REQUIRE(((uintptr_t)qkv % 16) == 0 && (heads * 32 * 3) % 8 == 0, "swin_window_attn: qkv must be 16-byte aligned");
   const int Hp = (int)((H + window - 1) / window * window), Wp = (int)((W + window - 1) / window * window);
   const int nW = (Hp / (int)window) * (Wp / (int)window);
   const long units = B * (long)nW * heads;
-  dim3 grid((unsigned)((units + 3) / 4));
-  swin_window_attn_kernel<7><<<grid, 128, 0, (cudaStream_t)stream>>>((const __half*)qkv, qkv_bias, bias_dense, (int)B, (int)H,
-                                                                    (int)W, (int)heads, (int)shift, scale, (__half*)out);
+  MQ_REQUIRE(units < 2147483647L, "swin_window_attn: too many (window, head) units");
+  dim3 grid((unsigned)units);
+  if (window == 7) {
+    swin_window_attn_kernel<7><<<grid, 128, SwinCfg<7>::SMEM, (cudaStream_t)stream>>>(
+        (const __half*)qkv, qkv_bias, bias_dense, (int)B, (int)H, (int)W, (int)heads, (int)shift, scale, (__half*)out);
+  } else {
+    swin_window_attn_kernel<12><<<grid, 128, SwinCfg<12>::SMEM, (cudaStream_t)stream>>>(
+        (const __half*)qkv, qkv_bias, bias_dense, (int)B, (int)H, (int)W, (int)heads, (int)shift, scale, (__half*)out);
+  }
   return check_launch("swin_window_attn_kernel");
 }
 

@@ -117,8 +117,8 @@ class SwinTransformer(nn.Module):
     def __init__(self, embed_dim=96, depths=(2, 2, 6, 2), num_heads=(3, 6, 12, 24), window_size=7, mlp_ratio=4.,
                  out_features=("stage2", "stage3", "stage4", "stage5")):
         super().__init__()
-        if window_size != 7 or any((embed_dim * 2 ** i) // h != 32 for i, h in enumerate(num_heads)):
-            raise NotImplementedError("window 7 / head_dim 32 (Swin-T, MQ-GLIP-T) only; Swin-L is SURVEY.md §8f")
+        if window_size not in (7, 12) or any((embed_dim * 2 ** i) // h != 32 for i, h in enumerate(num_heads)):
+            raise NotImplementedError("window 7 (Swin-T, MQ-GLIP-T) or 12 (Swin-L, MQ-GLIP-L) with head_dim 32 only")
         self.num_layers = len(depths)
         self.embed_dim = embed_dim
         self.out_features = out_features

@@ -156,6 +156,115 @@ class GeneralizedVLRCNN_New(nn.Module):
         out["vision_query_gates"] = lang["vision_query_gates"]
         return out
 
+    # ---- many-category prompts: chunked evaluation (LVIS) --------------------------------------------------------------
+    @torch.no_grad()
+    def _chunk_state(self, captions, positive_map, dev):
+        """Per-chunk prompt state (token ids, selected vision queries + token mask, class columns in ascending label order),
+        cached by content like ``_prompt_state``."""
+        bank_version = self.query_selector.bank_version if self.query_selector is not None else 0
+        key = self._prompt_key(captions, positive_map, 1, bank_version)
+        cache = self.__dict__.setdefault("_chunk_cache", {})
+        st = cache.get(key)
+        if st is not None:
+            return st
+        ids, am = self._tokenize(captions, dev)
+        vision = vmask = None
+        if self.query_selector is not None and self.query_selector.query_bank is not None:
+            labels, all_map = self.get_labels_and_maps_from_positive_map(positive_map)
+            vision, vmask, _ = self.query_selector([labels], [all_map], None)
+            vision, vmask = vision[0].float().contiguous(), vmask[0].float().contiguous()
+        cols = sorted(int(k) for k in positive_map)
+        toks = [([positive_map[c]] if isinstance(positive_map[c], int) else list(positive_map[c])) for c in cols]
+        if len(cache) > 4096:
+            cache.clear()
+        st = cache[key] = dict(ids=ids[:1], am=am[:1], vision=vision, vmask=vmask, cols=cols, toks=toks)
+        return st
+
+    @torch.no_grad()
+    def forward_chunked_device(self, images, chunk_captions, chunk_positive_maps, chunks_per_pass=8, chunk_ids=None):
+        """Chunked evaluation of a many-category vocabulary (LVIS: 1203 classes as 31 prompts of 40 classes,
+        maskrcnn_benchmark/engine/inference.py:165-283,605-625).  The reference runs the WHOLE model once per chunk and
+        concatenates the per-chunk detections; here Swin + FPN run ONCE per image and the chunks travel as extra batch
+        elements (element e = chunk * B + image) through the language backbone, the fusion tower and the post-processing,
+        ``chunks_per_pass`` chunks at a time.  Score columns of a chunk are its classes in ascending label order and carry
+        their own label table (convert_grounding_to_od_logits_v2 semantics, rpn/inference.py:793-824).
+        ``chunk_ids``: the subset of chunks THIS rank evaluates (text-column sharding over ranks), default all.
+        Returns {"det_packed": [n_chunks_local, B, max_out + 1, 6] device tensor, "chunks": [chunk index ...], ...}."""
+        if self.training:
+            raise NotImplementedError("training is SURVEY.md §8f")
+        images = to_image_list(images, self.cfg.DATALOADER.SIZE_DIVISIBILITY)
+        x = images.tensors
+        if not x.is_cuda:
+            raise MqdetError("GeneralizedVLRCNN_New: CUDA images required (no CPU fallback)")
+        dev = x.device
+        B = x.shape[0]
+        T = self.cfg.MODEL.LANGUAGE_BACKBONE.MAX_QUERY_LEN
+        chunk_ids = list(range(len(chunk_captions))) if chunk_ids is None else list(chunk_ids)
+        feats = self.backbone.body.forward_flat(x)
+        pyr16, levels = self.backbone.fpn.forward_flat([feats[i] for i in (1, 2, 3)])   # ONCE per image, shared by all chunks
+        max_out = self.max_out()
+        packed = torch.empty((len(chunk_ids), B, max_out + 1, 6), dtype=torch.float32, device=dev)
+        pooled = None
+        for p0 in range(0, len(chunk_ids), chunks_per_pass):
+            group = chunk_ids[p0:p0 + chunks_per_pass]
+            G = len(group)
+            sts = [self._chunk_state(chunk_captions[c], chunk_positive_maps[c], dev) for c in group]
+            ids = torch.cat([st["ids"] for st in sts]).repeat_interleave(B, dim=0).contiguous()
+            am = torch.cat([st["am"] for st in sts]).repeat_interleave(B, dim=0).contiguous()
+            vision = vmask = None
+            if sts[0]["vision"] is not None:
+                Vmax = max(st["vision"].shape[0] for st in sts)
+                vision = torch.zeros((G, Vmax, sts[0]["vision"].shape[1]), dtype=torch.float32, device=dev)
+                vmask = torch.zeros((G, Vmax, T), dtype=torch.float32, device=dev)
+                for g, st in enumerate(sts):   # zero rows = pad_sequence padding of QuerySelector.forward (:112-116)
+                    vision[g, :st["vision"].shape[0]] = st["vision"]
+                    vmask[g, :st["vmask"].shape[0]] = st["vmask"]
+                vision = vision.repeat_interleave(B, dim=0).contiguous()
+                vmask = vmask.repeat_interleave(B, dim=0).contiguous()
+                if pooled is None:
+                    pooled = ops.avgpool2_levels(pyr16, levels)
+            Cmax = max(len(st["cols"]) for st in sts)
+            mt = max(max((len(t) for t in st["toks"]), default=1) for st in sts)
+            tok_h = torch.full((G, Cmax, mt), -1, dtype=torch.int32)
+            lab_h = torch.zeros((G, Cmax), dtype=torch.int32)
+            for g, st in enumerate(sts):
+                for j, (c, tk) in enumerate(zip(st["cols"], st["toks"])):
+                    tok_h[g, j, :len(tk)] = torch.tensor(tk, dtype=torch.int32)
+                    lab_h[g, j] = c
+            tokmap = tok_h.to(dev).repeat_interleave(B, dim=0).contiguous()
+            labels = lab_h.to(dev).repeat_interleave(B, dim=0).contiguous()
+            lang = self.language_backbone.body({"input_ids": ids, "attention_mask": am,
+                                                "vision_inputs": {"vision": vision,
+                                                                  "images": pooled.repeat(G, 1, 1) if vision is not None else None,
+                                                                  "vision_attention_mask": vmask,
+                                                                  "batched_pos_category_map": None}})
+            out = self.rpn.forward_flat(pyr16.repeat(G, 1, 1), levels, list(images.image_sizes) * G, lang["hidden"], lang["masks"],
+                                        None, max_out, tokmap=tokmap, class_labels=labels)
+            packed[p0:p0 + G] = out["det_packed"].view(G, B, max_out + 1, 6)
+        return {"det_packed": packed, "chunks": chunk_ids, "image_sizes": images.image_sizes, "pyramid16": pyr16}
+
+    def forward_chunked(self, images, chunk_captions, chunk_positive_maps, chunks_per_pass=8):
+        """-> list[BoxList]: per image, the per-chunk detections concatenated (``BoxList.concate_box_list``,
+        structures/bounding_box.py:273-285; engine/inference.py:704-706), chunk order preserved."""
+        from ...structures.bounding_box import BoxList
+        out = self.forward_chunked_device(images, chunk_captions, chunk_positive_maps, chunks_per_pass)
+        pk = out["det_packed"].cpu()
+        max_out = pk.shape[2] - 1
+        res = []
+        for b, (h, w) in enumerate(out["image_sizes"]):
+            parts = []
+            for g in range(pk.shape[0]):
+                n = int(round(float(pk[g, b, max_out, 0])))
+                if n > max_out:
+                    raise MqdetError(f"image {b}, chunk {g}: {n} detections exceed the {max_out}-row result buffer")
+                parts.append(pk[g, b, :n])
+            d = torch.cat(parts) if parts else torch.zeros((0, 6))
+            bl = BoxList(d[:, :4].clone(), (w, h), mode="xyxy")
+            bl.add_field("labels", d[:, 5].long())
+            bl.add_field("scores", d[:, 4].clone())
+            res.append(bl)
+        return res
+
     def forward(self, images, targets=None, captions=None, positive_map=None, greenlight_map=None,
                 return_backbone_features=False):
         """Reference signature (:307-314), eval: returns list[BoxList] (fields ``labels``, ``scores``; mode xyxy)."""

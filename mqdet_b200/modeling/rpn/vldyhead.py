@@ -311,16 +311,20 @@ class VLDyHeadModule(nn.Module):
         return self._scales[1]
 
     @torch.no_grad()
-    def forward_flat(self, pyr16, levels, image_sizes, lang_hidden, lang_masks, positive_map, max_out=None):
-        """pyr16 [B,N,256] fp16 -> device-resident detections: dict(det [B,max_out,6], num [B], ...)."""
+    def forward_flat(self, pyr16, levels, image_sizes, lang_hidden, lang_masks, positive_map, max_out=None, tokmap=None,
+                     class_labels=None):
+        """pyr16 [B,N,256] fp16 -> device-resident detections: dict(det [B,max_out,6], num [B], ...).
+        ``tokmap`` int32 [B,C,max_tok] (+ ``class_labels`` int32 [B,C]): explicit per-element positive maps (batched prompt
+        chunks) instead of the one ``positive_map`` dict shared by the batch."""
         cfg = self.cfg
         if max_out is None:
             max_out = (int(cfg.MODEL.ATSS.DETECTIONS_PER_IMG) + 28 + 31) // 32 * 32
         r = self.head.forward_flat(pyr16, levels, lang_hidden, lang_masks)
-        pkey = tuple((int(k), tuple(v) if not isinstance(v, int) else (v,)) for k, v in sorted(positive_map.items()))
-        if self._tokmap is None or self._tokmap[0] != pkey:
-            self._tokmap = (pkey, ops.make_tokmap(positive_map, cfg.MODEL.DYHEAD.NUM_CLASSES - 1, pyr16.device))
-        tokmap = self._tokmap[1]
+        if tokmap is None:
+            pkey = tuple((int(k), tuple(v) if not isinstance(v, int) else (v,)) for k, v in sorted(positive_map.items()))
+            if self._tokmap is None or self._tokmap[0] != pkey:
+                self._tokmap = (pkey, ops.make_tokmap(positive_map, cfg.MODEL.DYHEAD.NUM_CLASSES - 1, pyr16.device))
+            tokmap = self._tokmap[1]
         ih, iw = image_sizes[0]
         if any(tuple(s) != (ih, iw) for s in image_sizes):
             raise NotImplementedError("forward_flat batches images of one size; use forward() per size group")
@@ -328,7 +332,7 @@ class VLDyHeadModule(nn.Module):
                                    cfg.MODEL.RPN.ANCHOR_SIZES, self._reg_scales()[:levels.n], float(iw), float(ih),
                                    pre_nms_thresh=cfg.MODEL.ATSS.INFERENCE_TH, pre_nms_top_n=cfg.MODEL.ATSS.PRE_NMS_TOP_N,
                                    nms_thresh=cfg.MODEL.ATSS.NMS_TH, max_det=cfg.MODEL.ATSS.DETECTIONS_PER_IMG,
-                                   max_out=max_out)
+                                   max_out=max_out, class_labels=class_labels)
         out["head"] = r
         return out
 

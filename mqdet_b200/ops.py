@@ -563,13 +563,23 @@ def make_tokmap(positive_map, num_classes, device):
 
 
 def atss_postprocess(logits, reg_ctr, tokmap, levels, strides, anchor_sizes, reg_scales, img_w, img_h, *, pre_nms_thresh=0.05,
-                     pre_nms_top_n=1000, nms_thresh=0.6, max_det=100, max_out=128, want_keys=False):
-    """logits [B,N,T], reg_ctr [B,N,5] -> dict(det [B,max_out,6], num [B], + the pre-NMS candidates). All on device."""
+                     pre_nms_top_n=1000, nms_thresh=0.6, max_det=100, max_out=128, want_keys=False, class_labels=None):
+    """logits [B,N,T], reg_ctr [B,N,5] -> dict(det [B,max_out,6], num [B], + the pre-NMS candidates). All on device.
+    tokmap int32 [C, max_tok] (shared) or [B, C, max_tok] (one positive map per image: batched prompt chunks);
+    class_labels int32 [C] / [B, C] or None (label of score column c = c + 1)."""
     import numpy as np
     global launch_count
     _need_cuda(logits, reg_ctr, tokmap)
     B, N, T = logits.shape
-    C, max_tok = tokmap.shape
+    C, max_tok = tokmap.shape[-2:]
+    tm_stride = C * max_tok if tokmap.dim() == 3 else 0
+    if tokmap.dim() == 3 and tokmap.shape[0] != B:
+        raise ValueError("per-image tokmap must have one table per batch element")
+    lab_stride = 0
+    if class_labels is not None:
+        if class_labels.dtype != torch.int32 or class_labels.shape[-1] != C:
+            raise ValueError("class_labels must be int32 [C] or [B, C]")
+        lab_stride = C if class_labels.dim() == 2 else 0
     dev = logits.device
     L = levels.n
     stride_h = np.asarray(strides, dtype=np.float32)
@@ -584,7 +594,8 @@ def atss_postprocess(logits, reg_ctr, tokmap, levels, strides, anchor_sizes, reg
     okey = torch.empty((B, S), dtype=torch.int64, device=dev) if want_keys else None
     cb, csc, cl = torch.empty_like(ob), torch.empty_like(osc), torch.empty_like(ol)
     totals = torch.empty((B,), dtype=torch.int32, device=dev)
-    check(load().mqdet_atss_candidates(_ptr(logits), _dt(logits), _ptr(reg_ctr), _ptr(tokmap), C, max_tok, T, levels.hw_ptr, L,
+    check(load().mqdet_atss_candidates(_ptr(logits), _dt(logits), _ptr(reg_ctr), _ptr(tokmap), tm_stride, _ptr(class_labels),
+                                       lab_stride, C, max_tok, T, levels.hw_ptr, L,
                                        stride_h.ctypes.data_as(ctypes.c_void_p), base_h.ctypes.data_as(ctypes.c_void_p),
                                        scale_h.ctypes.data_as(ctypes.c_void_p), B, float(pre_nms_thresh), int(pre_nms_top_n),
                                        S, float(img_w), float(img_h), _ptr(ws), _ptr(lvl_counts), _ptr(ob), _ptr(osc),

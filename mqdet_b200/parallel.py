@@ -60,3 +60,28 @@ def unshard(det_all, num_all, num_images, world):
     order.sort()
     idx = torch.tensor([j for _, j in order], dtype=torch.long, device=det_all.device)
     return det_all.index_select(0, idx), num_all.index_select(0, idx)
+
+
+# ---- many-category prompts: the chunks of the vocabulary (text-token columns) shard over ranks --------------------------
+def shard_chunks(num_chunks, rank, world):
+    """prompt chunk c -> rank c % world (second partition axis: the reference evaluates the 31 LVIS chunks
+    one after the other on every rank, engine/inference.py:605-625)."""
+    return list(range(rank, num_chunks, world))
+
+
+def all_gather_chunks(packed_local, num_chunks, group=None):
+    """packed_local [n_local, B, max_out + 1, 6] = the packed detections of this rank's chunks (``shard_chunks`` order) ->
+    [num_chunks, B, max_out + 1, 6] in chunk order on every rank, with ONE fixed-shape all-gather (ranks with one chunk
+    fewer send a zero block: count 0)."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return packed_local
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    per = -(-num_chunks // world)
+    buf = packed_local
+    if packed_local.shape[0] < per:
+        buf = torch.zeros((per,) + tuple(packed_local.shape[1:]), dtype=packed_local.dtype, device=packed_local.device)
+        buf[: packed_local.shape[0]] = packed_local
+    out = torch.empty((world * per,) + tuple(buf.shape[1:]), dtype=buf.dtype, device=buf.device)
+    dist.all_gather_into_tensor(out, buf.contiguous(), group=group)
+    idx = torch.tensor([(c % world) * per + c // world for c in range(num_chunks)], dtype=torch.long, device=out.device)
+    return out.index_select(0, idx)

@@ -40,6 +40,51 @@ def test_swin_block_shift_and_padding(dev):
         assert_close(out, ref, what=f"Swin block shift={shift}")
 
 
+@pytest.mark.parametrize("H,W", [(40, 53), (24, 24), (7, 30)])
+def test_swin_l_block_window12(dev, H, W):
+    """Swin-L geometry (MQ-GLIP-L, configs/pretrain/mq-glip-l.yaml:11-17): window 12 (144-token windows), 6 heads x 32 at
+    embed 192; plain and shifted (6) blocks on grids that need padding, incl. one smaller than the window."""
+    from mqdet_b200.modeling.backbone.swint import SwinTransformerBlock
+    from oracle import restate, synth
+    gen = synth.Gen(92)
+    C, heads, ws = 192, 6, 12
+    full_sd = synth.swin_sd(gen, depths=(2,), heads=(heads,), embed=C, ws=ws)
+    sd = {k[len("layers.0.blocks.1."):]: v for k, v in full_sd.items() if k.startswith("layers.0.blocks.1.")}
+    B = 2
+    x = gen.randn(B, H * W, C)
+    for shift in (0, 6):
+        ref = restate.swin_block(x, H, W, sd, "", heads, ws, shift)
+        blk = SwinTransformerBlock(C, heads, ws, shift)
+        full = dict(sd)
+        full["attn.relative_position_index"] = blk.state_dict()["attn.relative_position_index"]
+        blk = load_sd(blk, full).to(dev).eval()
+        blk.H, blk.W = H, W
+        out = blk(x.to(dev), None)
+        assert_close(out, ref, what=f"Swin-L block {H}x{W} shift={shift}")
+
+
+def test_swin_l_backbone(dev):
+    """Whole Swin-L body (depths 2,2,18,2; heads 6,12,24,48; window 12) against the oracle on a small image."""
+    from mqdet_b200.modeling.backbone.swint import SwinTransformer
+    from oracle import restate, synth
+    gen = synth.Gen(93)
+    depths, heads, embed, ws = (2, 2, 18, 2), (6, 12, 24, 48), 192, 12
+    sd = synth.swin_sd(gen, depths=depths, heads=heads, embed=embed, ws=ws)
+    img = gen.randn(1, 3, 150, 203)
+    ref = restate.swin_transformer(img, sd, depths=depths, heads=heads, embed=embed, ws=ws)
+    m = SwinTransformer(embed_dim=embed, depths=depths, num_heads=heads, window_size=ws)
+    full = dict(sd)
+    for k, v in m.state_dict().items():
+        if k.endswith("relative_position_index"):
+            full[k] = v
+    m = load_sd(m, full).to(dev).eval()
+    outs = m(img.to(dev))
+    bad = []
+    for i, (o, r) in enumerate(zip(outs, ref)):
+        assert_close(o, r, 5e-3, f"Swin-L stage{i + 2}", defer=bad)  # 24 blocks with fp16 GEMM operands, fp32 residual
+    assert not bad, bad
+
+
 def test_swin_fpn_vs_oracle_and_golden(dev):
     from mqdet_b200.modeling.backbone.fpn import FPN, LastLevelP6P7
     from oracle import make_golden, restate

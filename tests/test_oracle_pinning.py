@@ -58,6 +58,32 @@ def test_swin_fpn_vs_reference():
         _close(o, ref[f"p{i + 3}"], 1e-5)
 
 
+def test_swin_l_vs_reference():
+    """Swin-L geometry of MQ-GLIP-L (window 12, embed 192, heads 6/12/24/48; depths shortened to 2,2,2,2 to keep the CPU
+    run short): the oracle's swin_transformer with ws=12 against the reference's own SwinTransformer."""
+    import torch
+    from oracle import ref_loader as rl
+    from oracle import synth
+    gen = synth.Gen(1240)
+    depths, heads, embed, ws = (2, 2, 2, 2), (6, 12, 24, 48), 192, 12
+    sd = synth.swin_sd(gen, depths=depths, heads=heads, embed=embed, ws=ws)
+    img = gen.randn(1, 3, 150, 203)
+    sw = rl.swint()
+    body = sw.SwinTransformer(embed_dim=embed, depths=list(depths), num_heads=list(heads), window_size=ws, drop_path_rate=0.0,
+                              frozen_stages=-1, use_checkpoint=False)
+    body.eval()
+    full = dict(sd)
+    for k, v in body.state_dict().items():
+        if k.endswith("relative_position_index"):
+            full[k] = v
+    body.load_state_dict(full, strict=True)
+    with torch.no_grad():
+        ref = body(img)
+        outs = restate.swin_transformer(img, sd, depths=depths, heads=heads, embed=embed, ws=ws)
+    for o, r in zip(outs, ref):
+        _close(o, r, 1e-5)
+
+
 def test_contrastive_embed_vs_reference():
     c = make_golden.case_inputs("contrastive_embed")
     ref = make_golden.run_reference("contrastive_embed")["logits"]

@@ -35,6 +35,41 @@ def test_sharded_all_gather_world2():
     assert dict(ret) == {0: True, 1: True}
 
 
+def _chunk_worker(rank, world, port, num_chunks, ret):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    sys.path.insert(0, ROOT)
+    from mqdet_b200 import parallel
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    calls = []
+    orig = dist.all_gather_into_tensor
+    dist.all_gather_into_tensor = lambda *a, **k: (calls.append(1), orig(*a, **k))[1]
+    mine = parallel.shard_chunks(num_chunks, rank, world)
+    B, max_out = 2, 8
+    local = torch.stack([parallel.pack(torch.full((B, max_out, 6), float(c)), torch.full((B,), c + 1, dtype=torch.int32))
+                         for c in mine])
+    allc = parallel.all_gather_chunks(local, num_chunks)
+    ok = allc.shape == (num_chunks, B, max_out + 1, 6) and len(calls) == 1
+    for c in range(num_chunks):
+        det, num = parallel.unpack(allc[c])
+        ok = ok and float(det[0, 0, 0]) == c and int(num[0]) == c + 1
+    # the image-sharded path also issues exactly ONE collective
+    calls.clear()
+    parallel.all_gather_packed(parallel.pack(torch.zeros(B, max_out, 6), torch.ones(B, dtype=torch.int32)))
+    ret[rank] = bool(ok and len(calls) == 1)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_chunk_sharding_world2_one_collective():
+    """text-column (prompt-chunk) sharding: 5 chunks over 2 ranks (3 + 2), ONE all-gather, chunk order restored."""
+    world = 2
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    port = 31500 + (os.getpid() % 2000)
+    mp.spawn(_chunk_worker, args=(world, port, 5, ret), nprocs=world, join=True)
+    assert dict(ret) == {0: True, 1: True}
+
+
 def test_single_process_is_identity():
     sys.path.insert(0, ROOT)
     from mqdet_b200 import parallel
@@ -42,3 +77,5 @@ def test_single_process_is_identity():
     a, b = parallel.all_gather_detections(det, num)
     assert a is det and b is num
     assert parallel.shard_indices(10, 1, 4) == [1, 5, 9]
+    d2, n2 = parallel.unpack(parallel.pack(det, num))
+    assert torch.equal(d2, det) and torch.equal(n2, num)

@@ -154,6 +154,32 @@ def prompt(num_classes, tokens_per_class=2, T=256, gen=None, vocab_lo=1996, voca
     return ids, mask, positive_map
 
 
+def chunked_prompts(num_classes, chunk, T=256, gen=None, vocab_lo=1996, vocab_hi=29000):
+    """LVIS-style chunked vocabulary (engine/inference.py:165-283: TEST.CHUNKED_EVALUATION classes per prompt): classes
+    1..num_classes in chunks of ``chunk``; class c has 2 + (c % 2) tokens, so token positions differ between chunks.
+    Returns [(input_ids [1,T], attention_mask [1,T], positive_map {global label: [token positions]}), ...]."""
+    out = []
+    for c0 in range(0, num_classes, chunk):
+        ids = torch.zeros(1, T, dtype=torch.long)
+        ids[0, 0] = 101
+        pos = 1
+        pm = {}
+        for c in range(c0 + 1, min(c0 + chunk, num_classes) + 1):
+            n = 2 + (c % 2)
+            toks = list(range(pos, pos + n))
+            pm[c] = toks
+            ids[0, toks] = torch.randint(vocab_lo, vocab_hi, (n,), generator=gen.g)
+            pos += n
+            ids[0, pos] = 1012
+            pos += 1
+        assert pos < T
+        ids[0, pos] = 102
+        mask = torch.zeros(1, T, dtype=torch.long)
+        mask[0, : pos + 1] = 1
+        out.append((ids, mask, pm))
+    return out
+
+
 def vision_queries(positive_map, K, T=256, dim=256, gen=None):
     """What QuerySelector.forward returns for one image (query_selector.py:40-116): queries [1, V, dim] and the
     binarised mask [1, V, T] with 1 on the token positions of the query's class."""
@@ -246,11 +272,14 @@ def fpn_sd(gen, in_channels=(192, 384, 768), C=256, p=""):
     return sd
 
 
-def detector_sd(gen, num_convs=6, bias0=None):
-    """Full MQ-GLIP-T parameter set with the reference's key names (277 M parameters)."""
+def detector_sd(gen, num_convs=6, bias0=None, swin=None):
+    """Full MQ-GLIP-T parameter set with the reference's key names (277 M parameters).  ``swin`` = dict(depths, heads, embed,
+    ws) selects another backbone (MQ-GLIP-L: depths (2,2,18,2), heads (6,12,24,48), embed 192, ws 12; with num_convs=8)."""
     sd = {}
-    sd.update({"backbone.body." + k: v for k, v in swin_sd(gen).items()})
-    sd.update({"backbone.fpn." + k: v for k, v in fpn_sd(gen).items()})
+    swin = swin or {}
+    embed = swin.get("embed", 96)
+    sd.update({"backbone.body." + k: v for k, v in swin_sd(gen, **swin).items()})
+    sd.update({"backbone.fpn." + k: v for k, v in fpn_sd(gen, in_channels=(2 * embed, 4 * embed, 8 * embed)).items()})
     sd.update({"language_backbone.body.model." + k: v for k, v in qvbert_sd(gen).items()})
     head = vldyhead_sd(gen, num_convs)
     if bias0 is not None:
