@@ -308,6 +308,16 @@ int mqdet_im2col3x3(const void* x, int64_t x_batch_stride, int64_t B, int64_t H,
 /* AvgPool2d(2) of every pyramid level + concat (generalized_vl_rcnn_new.py:291-293): fp16 [B,N,C] -> fp32 [B,I,C]. */
 int mqdet_avgpool2_levels(const void* x, const int32_t* level_hw, int64_t nlev, int64_t B, int64_t C, float* out, void* stream);
 
+/* ---- vision-query extraction (GeneralizedVLRCNN_New.extract_query, generalized_vl_rcnn_new.py:232-288) ----------------
+ * Pooler (modeling/poolers.py:46-129): FPN level of every box by LevelMapper (:11-43) + ROIAlignV2 of that level
+ * (torchvision roi_align, aligned = True, sampling_ratio 0 = adaptive) over the fp16 pyramid x [B][N][C] (levels concatenated).
+ * rois [R][5] = (image index, x1, y1, x2, y2) fp32 in image pixels; scales HOST float [nlev] (POOLER_SCALES).
+ * mean_only != 0: out [R][C] = mean over the pooled x pooled bins (query_feats.mean(dim=[-2,-1]), :263);
+ * otherwise out [R][C][pooled][pooled] fp32.  level_out int32 [R] optional. */
+int mqdet_roi_align_levels(const void* x, const int32_t* level_hw, int64_t nlev, const float* scales, int64_t B, int64_t C,
+                           const float* rois, int64_t R, int64_t pooled, int64_t sampling_ratio, int mean_only, float* out,
+                           int32_t* level_out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -17,6 +17,8 @@ def mq_glip_t_cfg(**over):
             GROUP_NORM=NS(NUM_GROUPS=16),
             RPN=NS(ASPECT_RATIOS=(1.0,), SCALES_PER_OCTAVE=1, ANCHOR_SIZES=(64, 128, 256, 512, 1024),
                    ANCHOR_STRIDE=(8, 16, 32, 64, 128), RETURN_FUSED_FEATURES=False),
+            ROI_BOX_HEAD=NS(POOLER_RESOLUTION=7, POOLER_SCALES=(0.125, 0.0625, 0.03125, 0.015625, 0.0078125),
+                            POOLER_SAMPLING_RATIO=0),
             ATSS=NS(INFERENCE_TH=0.05, PRE_NMS_TOP_N=1000, NMS_TH=0.6, DETECTIONS_PER_IMG=100, NUM_CLASSES=81),
             DYHEAD=NS(NUM_CLASSES=81, CHANNELS=256, NUM_CONVS=6, USE_GN=True, USE_DYRELU=True, USE_DFCONV=True,
                       USE_DYFUSE=True, PRIOR_PROB=0.01, LOG_SCALE=0.0, SCORE_AGG="MEAN",
@@ -32,7 +34,8 @@ def mq_glip_t_cfg(**over):
                         ADD_ADAPT_LAYER=False, RETURN_ATTN_GATE_VALUE=False, VISION_SCALE=1.0,
                         AUGMENT_IMAGE_WITH_QUERY=False, TEXT_DROPOUT=0.4, NEW_MASK_TOKEN=False, QUERY_FUSION=False,
                         SHARE_KV=False, NUM_QUERY_PER_CLASS=5, SELECT_FPN_LEVEL=True, QUERY_BANK_PATH="",
-                        LEARNABLE_BANK=False, ADD_VISION_LAYER=False, PURE_TEXT_RATE=0.0, RANDOM_KSHOT=False),
+                        LEARNABLE_BANK=False, ADD_VISION_LAYER=False, PURE_TEXT_RATE=0.0, RANDOM_KSHOT=False,
+                        EXPAND_RATIO=1.5, MAX_QUERY_NUMBER=5000, SIMILARITY_THRESHOLD=0.85),
         TEST=NS(MDETR_STYLE_AGGREGATE_CLASS_NUM=-1, USE_MULTISCALE=False),
         INPUT=NS(PIXEL_MEAN=[103.530, 116.280, 123.675], PIXEL_STD=[57.375, 57.120, 58.395]),
         DATALOADER=NS(SIZE_DIVISIBILITY=32),

@@ -23,6 +23,7 @@ from ...structures.image_list import to_image_list
 from ..backbone.fpn import FPN, LastLevelP6P7
 from ..backbone.swint import SwinTransformer
 from ..language_backbone.bert_model_new import BertEncoder
+from ..poolers import Pooler
 from ..query_selector.query_selector import QuerySelector
 from ..rpn.vldyhead import VLDyHeadModule
 
@@ -46,6 +47,14 @@ class GeneralizedVLRCNN_New(nn.Module):
         self.rpn = VLDyHeadModule(cfg)
         self.roi_heads = None  # RPN_ONLY: True (configs/pretrain/mq-glip-t.yaml:6)
         self.query_selector = QuerySelector(cfg) if cfg.VISION_QUERY.ENABLED else None
+        # box pooler for extracting the vision-query bank (:108-122; SELECT_FPN_LEVEL True in every MQ config)
+        rb = getattr(cfg.MODEL, "ROI_BOX_HEAD", None)
+        self.pooler = None
+        if rb is not None:
+            if not cfg.VISION_QUERY.SELECT_FPN_LEVEL:
+                raise NotImplementedError("VISION_QUERY.SELECT_FPN_LEVEL=False (CustomPooler) is off in every MQ config")
+            self.pooler = Pooler(output_size=(rb.POOLER_RESOLUTION, rb.POOLER_RESOLUTION), scales=rb.POOLER_SCALES,
+                                 sampling_ratio=rb.POOLER_SAMPLING_RATIO, use_v2=True)
         self.tokenizer = None  # attach an HF tokenizer to accept string captions
         self.DEBUG = False
         self._prompt = None
@@ -53,6 +62,65 @@ class GeneralizedVLRCNN_New(nn.Module):
     def load_query_bank(self, path):
         self.query_selector.load_query_bank(path)
         self.invalidate_prompt_cache()
+
+    def save_query_bank(self, query_images, path):
+        """The on-disk bank format of tools/extract_vision_query.py: torch.save of {label: FloatTensor[n, n_scales, C]}."""
+        torch.save({int(k): v.detach().cpu() for k, v in query_images.items()}, path)
+
+    @staticmethod
+    def expand_bbox(box_list, expand_ratio=1.5):
+        """generalized_vl_rcnn_new.py:32-49: boxes grown by ``expand_ratio`` about their centre, clipped to the image, empty
+        ones removed (host-side box bookkeeping on a handful of ground-truth boxes)."""
+        from ...structures.bounding_box import BoxList
+        out = []
+        for boxes in box_list:
+            assert boxes.mode == "xyxy"
+            bb = boxes.bbox.float()
+            bw, bh = bb[:, 2] - bb[:, 0], bb[:, 3] - bb[:, 1]
+            dw, dh = (bw * expand_ratio - bw) / 2, (bh * expand_ratio - bh) / 2
+            nb = BoxList(bb + torch.stack([-dw, -dh, dw, dh], dim=1), boxes.size, mode="xyxy")
+            nb.add_field("labels", boxes.get_field("labels"))
+            out.append(nb.clip_to_image(remove_empty=True))
+        return out
+
+    @torch.no_grad()
+    def extract_query(self, images=None, targets=None, query_images=None, visual_features=None, exclude_similar=False,
+                      device=None, max_query_number=None):
+        """Vision-query bank extraction (:232-288): expand every ground-truth box x EXPAND_RATIO, pool it from its FPN level
+        (aligned ROIAlign POOLER_RESOLUTION^2, mean over the bins -> one 256-vector per box) and append it to
+        ``query_images[label]`` ([n, 1, C]) up to MAX_QUERY_NUMBER per label, optionally skipping near-duplicates."""
+        from collections import defaultdict
+        import torch.nn.functional as F
+        if self.pooler is None:
+            raise MqdetError("extract_query needs cfg.MODEL.ROI_BOX_HEAD (POOLER_RESOLUTION / POOLER_SCALES / POOLER_SAMPLING_RATIO)")
+        query_images = defaultdict(list) if query_images is None else query_images
+        targets = self.expand_bbox([t for t in targets if t is not None], self.cfg.VISION_QUERY.EXPAND_RATIO)
+        if visual_features is None:
+            images = to_image_list(images)
+            x = images.tensors
+            if not x.is_cuda:
+                raise MqdetError("GeneralizedVLRCNN_New.extract_query: CUDA images required (no CPU fallback)")
+            feats = self.backbone.body.forward_flat(x)
+            pyr16, levels = self.backbone.fpn.forward_flat([feats[i] for i in (1, 2, 3)])
+        else:
+            levels = ops.get_levels([(f.shape[2], f.shape[3]) for f in visual_features], visual_features[0].device)
+            pyr16 = ops.cast_f16(torch.cat([f.flatten(2).transpose(1, 2) for f in visual_features], dim=1).contiguous())
+        feats, _ = self.pooler.forward_flat(pyr16, levels, targets, mean_only=True)     # [num_boxes, C]
+        query_feats = feats[:, None, :].cpu()                                            # [num_boxes, 1 scale, C]
+        labels = torch.cat([t.get_field("labels") for t in targets]) if targets else torch.zeros(0, dtype=torch.long)
+        assert len(labels) == len(query_feats)
+        max_query_number = self.cfg.VISION_QUERY.MAX_QUERY_NUMBER if max_query_number is None else max_query_number
+        for label, feat in zip(labels.tolist(), query_feats):
+            n = len(query_images[label])
+            if n >= max_query_number:
+                continue
+            if exclude_similar and n > 0:
+                bank = F.normalize(query_images[label], p=2, dim=-1)                    # [n, 1, C]
+                new = F.normalize(feat, p=2, dim=-1)                                     # [1, C]
+                if ((bank * new[None]).sum(-1) > self.cfg.VISION_QUERY.SIMILARITY_THRESHOLD).sum() > 0:
+                    continue
+            query_images[label] = feat[None] if n == 0 else torch.cat([query_images[label], feat[None]])
+        return query_images
 
     def invalidate_prompt_cache(self):
         """Drop everything cached per prompt (token ids, selected queries, masks, the head's token map)."""

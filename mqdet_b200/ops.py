@@ -701,3 +701,22 @@ def avgpool2_levels(x16, levels):
     check(load().mqdet_avgpool2_levels(_ptr(x16), levels.hw_ptr, levels.n, B, C, _ptr(out), _stream()), "avgpool2_levels")
     launch_count += 1
     return out
+
+
+def roi_align_levels(pyr16, levels, scales, rois, pooled=7, sampling_ratio=0, mean_only=True):
+    """Pooler (LevelMapper + aligned ROIAlign per level) over the fp16 pyramid [B,N,C]: rois [R,5] fp32 (image index, x1, y1, x2,
+    y2) -> ([R,C] fp32 mean over the pooled bins | [R,C,pooled,pooled] fp32, level int32 [R])."""
+    import numpy as np
+    global launch_count
+    _need_cuda(pyr16, rois)
+    B, N, C = pyr16.shape
+    R = rois.shape[0]
+    rois = rois.float().contiguous()
+    out = torch.empty((R, C) if mean_only else (R, C, pooled, pooled), dtype=torch.float32, device=pyr16.device)
+    lvl = torch.empty((R,), dtype=torch.int32, device=pyr16.device)
+    sc = np.asarray(scales, dtype=np.float32)
+    check(load().mqdet_roi_align_levels(_ptr(pyr16), levels.hw_ptr, levels.n, sc.ctypes.data_as(ctypes.c_void_p), B, C, _ptr(rois), R,
+                                        int(pooled), int(sampling_ratio), int(bool(mean_only)), _ptr(out), _ptr(lvl), _stream()),
+          "roi_align_levels")
+    launch_count += 1
+    return out, lvl

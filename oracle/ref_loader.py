@@ -421,6 +421,27 @@ def detector(cfg, dcn_fn, ml_nms_fn, tokenized):
     return det
 
 
+def poolers():
+    """maskrcnn_benchmark/modeling/poolers.py (LevelMapper, Pooler) with the reference's own layers/roi_align.py; the compiled
+    ``_C`` is only reached by the non-V2 ``ROIAlign`` (never built by the detector: use_v2=True), so an empty stand-in does."""
+    _install_shims()
+    if "poolers" not in _cache:
+        pkg = sys.modules["maskrcnn_benchmark"]
+        if not hasattr(pkg, "_C"):
+            pkg._C = types.ModuleType("maskrcnn_benchmark._C")
+            sys.modules["maskrcnn_benchmark._C"] = pkg._C
+        ra = _load_file("maskrcnn_benchmark.layers.roi_align", "maskrcnn_benchmark/layers/roi_align.py")
+        layers = sys.modules.get("maskrcnn_benchmark.layers")
+        if layers is None:
+            layers = types.ModuleType("maskrcnn_benchmark.layers")
+            layers.__path__ = []
+            sys.modules["maskrcnn_benchmark.layers"] = layers
+            pkg.layers = layers
+        layers.ROIAlign, layers.ROIAlignV2 = ra.ROIAlign, ra.ROIAlignV2
+        _cache["poolers"] = _load_file("maskrcnn_benchmark.modeling.poolers", "maskrcnn_benchmark/modeling/poolers.py")
+    return _cache["poolers"]
+
+
 def fpn():
     """maskrcnn_benchmark/modeling/backbone/fpn.py (FPN, LastLevelP6P7)."""
     if "fpn" not in _cache:

@@ -586,6 +586,39 @@ def fpn(stage_outs, sd, p=""):
 
 
 # ------------------------------------------------------------------------------------------------------------------
+# Vision-query extraction — generalized_vl_rcnn_new.py:232-288, modeling/poolers.py:11-129, layers/roi_align.py:71-81
+# ------------------------------------------------------------------------------------------------------------------
+def expand_boxes(bbox, image_size, ratio=1.5):
+    """expand_bbox (:32-49): grow about the centre, clip to [0, w-1] x [0, h-1], drop empty boxes.  Returns (boxes, keep)."""
+    w, h = image_size
+    bw, bh = bbox[:, 2] - bbox[:, 0], bbox[:, 3] - bbox[:, 1]
+    dw, dh = (bw * ratio - bw) / 2, (bh * ratio - bh) / 2
+    nb = bbox + torch.stack([-dw, -dh, dw, dh], dim=1)
+    nb[:, 0].clamp_(min=0, max=w - 1); nb[:, 1].clamp_(min=0, max=h - 1)
+    nb[:, 2].clamp_(min=0, max=w - 1); nb[:, 3].clamp_(min=0, max=h - 1)
+    keep = (nb[:, 3] > nb[:, 1]) & (nb[:, 2] > nb[:, 0])
+    return nb[keep], keep
+
+
+def pool_query_features(pyr, boxes_per_image, scales=(0.125, 0.0625, 0.03125, 0.015625, 0.0078125), resolution=7,
+                        sampling_ratio=0):
+    """Pooler.forward with use_v2=True (poolers.py:99-129) + mean over the bins (:263): pyr = list of [B,C,h,w] fp32 maps,
+    boxes_per_image = list of [K_i, 4] xyxy boxes (already expanded) -> ([sum K, C] features, [sum K] level indices)."""
+    import math
+    from torchvision.ops import roi_align
+    rois = torch.cat([torch.cat([torch.full((b.shape[0], 1), float(i)), b.float()], dim=1) for i, b in enumerate(boxes_per_image)])
+    k_min, k_max = -math.log2(scales[0]), -math.log2(scales[-1])
+    area = (rois[:, 3] - rois[:, 1] + 1) * (rois[:, 4] - rois[:, 2] + 1)          # BoxList.area(), TO_REMOVE = 1
+    lvls = torch.floor(4 + torch.log2(torch.sqrt(area) / 224 + 1e-6)).clamp(min=k_min, max=k_max).to(torch.int64) - int(k_min)
+    out = torch.zeros((rois.shape[0], pyr[0].shape[1], resolution, resolution))
+    for l, (f, sc) in enumerate(zip(pyr, scales)):
+        idx = torch.nonzero(lvls == l).squeeze(1)
+        if idx.numel():
+            out[idx] = roi_align(f, rois[idx], (resolution, resolution), sc, sampling_ratio, aligned=True)
+    return out.mean(dim=[-2, -1]), lvls
+
+
+# ------------------------------------------------------------------------------------------------------------------
 # Whole forward — maskrcnn_benchmark/modeling/detector/generalized_vl_rcnn_new.py:307-519 (eval), rpn/vldyhead.py:933-989
 # ------------------------------------------------------------------------------------------------------------------
 def _sub(sd, prefix):

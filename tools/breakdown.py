@@ -14,12 +14,12 @@ from mqdet_b200 import ops
 from mqdet_b200.config import mq_glip_t_cfg
 from mqdet_b200.modeling.detector.generalized_vl_rcnn_new import GeneralizedVLRCNN_New
 from mqdet_b200.structures.image_list import ImageList
-from oracle import synth
+from tools import synth
 
 dev = torch.device("cuda:0")
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 8
 gen, ids, am, pmap, bank, img = bench.build_inputs(B, 1235)
-sd = synth.detector_sd(synth.Gen(99), bias0=-1.5)
+sd = synth.detector_sd(synth.Gen(99), bias0=-4.59511985013459)
 model = GeneralizedVLRCNN_New(mq_glip_t_cfg())
 for k, v in model.state_dict().items():
     if k.endswith("relative_position_index"):

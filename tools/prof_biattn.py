@@ -11,7 +11,7 @@ import torch
 
 from mqdet_b200.config import mq_glip_t_cfg
 from mqdet_b200.utils.fuse_helper import BiAttentionBlockForCheckpoint
-from oracle import synth
+from tools import synth
 
 dev = torch.device("cuda:0")
 gen = synth.Gen(5)
