@@ -318,6 +318,16 @@ int mqdet_roi_align_levels(const void* x, const int32_t* level_hw, int64_t nlev,
                            const float* rois, int64_t R, int64_t pooled, int64_t sampling_ratio, int mean_only, float* out,
                            int32_t* level_out, void* stream);
 
+/* ---- GroundingDINO: multi-scale deformable attention forward (groundingdino_new/models/GroundingDINO/ms_deform_attn.py:93-133,
+ * 285-331; supersedes groundingdino_new._C.ms_deform_attn_forward, csrc_groundingdino/vision.cpp:53-56) ---------------------------
+ * value [B][Nv][heads*32] f16 (projected, masked rows zero; levels concatenated in level_hw order); proj [B*Q][proj_ld] f32 =
+ * the raw Linear outputs: sampling offsets at column ((h*L + l)*P + p)*2 + {x, y}, attention logits at aw_col0 + (h*L + l)*P + p;
+ * ref [B][Q][L][ref_dim] f32 normalised reference points (ref_dim 2) or boxes (4).  Per (image, query, head): softmax over the
+ * L*P logits, sampling locations, bilinear samples (zero padding, align_corners=False), weighted sum -> out [B*Q][heads*32]. */
+int mqdet_ms_deform_attn(const void* value, const float* proj, int64_t proj_ld, int64_t aw_col0, const float* ref, int64_t ref_dim,
+                         const int32_t* level_hw, int64_t nlev, int64_t B, int64_t Q, int64_t heads, int64_t head_dim,
+                         int64_t points, void* out, int out_dtype, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -720,3 +720,22 @@ def roi_align_levels(pyr16, levels, scales, rois, pooled=7, sampling_ratio=0, me
           "roi_align_levels")
     launch_count += 1
     return out, lvl
+
+
+def ms_deform_attn(value16, proj32, aw_col0, ref, levels, heads, points, out_dtype=torch.float16):
+    """Fused multi-scale deformable attention core: value16 [B,Nv,heads*32] fp16, proj32 [B*Q, >= heads*L*P*3] fp32 (sampling
+    offsets | attention logits from column aw_col0), ref [B,Q,L,2|4] fp32 -> [B,Q,heads*32]."""
+    global launch_count
+    _need_cuda(value16, proj32, ref)
+    B, Nv, E = value16.shape
+    Q = ref.shape[1]
+    if value16.dtype != torch.float16 or proj32.dtype != torch.float32 or not value16.is_contiguous() or proj32.stride(-1) != 1:
+        raise _lib.MqdetError("ms_deform_attn: value fp16 contiguous, proj fp32 with contiguous rows required")
+    if Nv != levels.N or ref.shape[2] != levels.n:
+        raise _lib.MqdetError("ms_deform_attn: value rows / reference points do not match the level table")
+    out = torch.empty((B, Q, E), dtype=out_dtype, device=value16.device)
+    check(load().mqdet_ms_deform_attn(_ptr(value16), _ptr(proj32), proj32.stride(0), int(aw_col0), _ptr(ref), ref.shape[-1],
+                                      levels.hw_ptr, levels.n, B, Q, heads, E // heads, points, _ptr(out), _dt(out), _stream()),
+          "ms_deform_attn")
+    launch_count += 1
+    return out

@@ -144,6 +144,17 @@ def gdino_utils():
     return _cache["gdu"]
 
 
+def gdino_ms_deform_attn():
+    """groundingdino_new/models/GroundingDINO/ms_deform_attn.py (its CPU path needs torch only; the failed ``_C`` import is
+    caught by the file itself)."""
+    if "msda" not in _cache:
+        import warnings
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            _cache["msda"] = _load_file("ref_gdino_msda", "groundingdino_new/models/GroundingDINO/ms_deform_attn.py")
+    return _cache["msda"]
+
+
 def query_selector():
     """maskrcnn_benchmark/modeling/query_selector/query_selector.py (pure torch / numpy)."""
     if "qs" not in _cache:

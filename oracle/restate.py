@@ -586,6 +586,43 @@ def fpn(stage_outs, sd, p=""):
 
 
 # ------------------------------------------------------------------------------------------------------------------
+# GroundingDINO multi-scale deformable attention — groundingdino_new/models/GroundingDINO/ms_deform_attn.py:93-133,236-352
+# ------------------------------------------------------------------------------------------------------------------
+def ms_deform_attn(query, value, reference_points, spatial_shapes, sd, p="", heads=8, points=4, key_padding_mask=None,
+                   query_pos=None):
+    """MultiScaleDeformableAttention.forward with batch_first=True: query [B,Q,E], value [B,Nv,E], reference_points
+    [B,Q,L,2|4] -> [B,Q,E]; the sampling core is the reference's own CPU path (grid_sample, :93-133)."""
+    if query_pos is not None:
+        query = query + query_pos
+    B, Q, E = query.shape
+    Nv = value.shape[1]
+    L = len(spatial_shapes)
+    d = E // heads
+    v = _lin(value, sd, p + "value_proj")
+    if key_padding_mask is not None:
+        v = v.masked_fill(key_padding_mask[..., None], 0.0)
+    v = v.view(B, Nv, heads, d)
+    off = _lin(query, sd, p + "sampling_offsets").view(B, Q, heads, L, points, 2)
+    aw = _lin(query, sd, p + "attention_weights").view(B, Q, heads, L * points).softmax(-1).view(B, Q, heads, L, points)
+    ss = torch.tensor(spatial_shapes, dtype=torch.float32)
+    if reference_points.shape[-1] == 2:
+        norm = torch.stack([ss[:, 1], ss[:, 0]], -1)
+        loc = reference_points[:, :, None, :, None, :] + off / norm[None, None, None, :, None, :]
+    else:
+        loc = reference_points[:, :, None, :, None, :2] + off / points * reference_points[:, :, None, :, None, 2:] * 0.5
+    vals = v.split([h * w for h, w in spatial_shapes], dim=1)
+    grids = 2 * loc - 1
+    sampled = []
+    for l, (h, w) in enumerate(spatial_shapes):
+        vl = vals[l].flatten(2).transpose(1, 2).reshape(B * heads, d, h, w)
+        g = grids[:, :, :, l].transpose(1, 2).flatten(0, 1)
+        sampled.append(F.grid_sample(vl, g, mode="bilinear", padding_mode="zeros", align_corners=False))
+    aw = aw.transpose(1, 2).reshape(B * heads, 1, Q, L * points)
+    out = (torch.stack(sampled, dim=-2).flatten(-2) * aw).sum(-1).view(B, heads * d, Q).transpose(1, 2)
+    return _lin(out, sd, p + "output_proj")
+
+
+# ------------------------------------------------------------------------------------------------------------------
 # Vision-query extraction — generalized_vl_rcnn_new.py:232-288, modeling/poolers.py:11-129, layers/roi_align.py:71-81
 # ------------------------------------------------------------------------------------------------------------------
 def expand_boxes(bbox, image_size, ratio=1.5):

@@ -354,3 +354,32 @@ def test_extract_query_vs_reference():
         got = feats[lab == label][:, None, :]
         assert want.shape == got.shape, (label, want.shape, got.shape)
         _close(got, want, 1e-5)
+
+
+@pytest.mark.parametrize("ref_dim", [2, 4])
+def test_ms_deform_attn_vs_reference(ref_dim):
+    """GroundingDINO MultiScaleDeformableAttention (ms_deform_attn.py:136-352, CPU path = multi_scale_deformable_attn_pytorch):
+    the oracle restatement against the reference's own module, 2-d reference points and 4-d reference boxes, padding mask."""
+    import torch
+    from oracle import ref_loader as rl
+    from oracle import synth
+    gen = synth.Gen(1300 + ref_dim)
+    sd = synth.msda_sd(gen)
+    shapes = [(20, 28), (10, 14), (5, 7), (3, 4)]
+    B, Q, E = 2, 37, 256
+    nv = sum(h * w for h, w in shapes)
+    query, value = gen.randn(B, Q, E), gen.randn(B, nv, E)
+    ref_pts = torch.rand(B, Q, 4, ref_dim, generator=gen.g)
+    if ref_dim == 4:
+        ref_pts[..., 2:] = ref_pts[..., 2:] * 0.3 + 0.05
+    mask = torch.zeros(B, nv, dtype=torch.bool)
+    mask[1, -40:] = True
+    mod = rl.gdino_ms_deform_attn().MultiScaleDeformableAttention(embed_dim=E, num_heads=8, num_levels=4, num_points=4, batch_first=True)
+    mod.load_state_dict(sd, strict=True)
+    mod.eval()
+    ss = torch.tensor(shapes)
+    lsi = torch.cat([ss.new_zeros(1), (ss[:, 0] * ss[:, 1]).cumsum(0)[:-1]])
+    with torch.no_grad():
+        want = mod(query, value=value, key_padding_mask=mask, reference_points=ref_pts, spatial_shapes=ss, level_start_index=lsi)
+        got = restate.ms_deform_attn(query, value, ref_pts, shapes, sd, key_padding_mask=mask)
+    _close(got, want, 1e-5)

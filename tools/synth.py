@@ -229,6 +229,20 @@ def vldyhead_sd(gen, num_convs=6, C=256, l_dim=768, num_classes=80):
     return sd
 
 
+def msda_sd(gen, p="", embed=256, heads=8, levels=4, points=4, sd=None):
+    """MultiScaleDeformableAttention parameters (ms_deform_attn.py:186-220), livelier than the reference's zero-initialised
+    offset / weight projections so that sampling locations and attention weights depend on the query."""
+    sd = {} if sd is None else sd
+    n = heads * levels * points
+    sd[p + "sampling_offsets.weight"] = gen.randn(n * 2, embed, scale=0.05)
+    sd[p + "sampling_offsets.bias"] = gen.randn(n * 2, scale=1.5)
+    sd[p + "attention_weights.weight"] = gen.randn(n, embed, scale=0.08)
+    sd[p + "attention_weights.bias"] = gen.randn(n, scale=0.3)
+    gen.xavier(embed, embed, sd, p + "value_proj")
+    gen.xavier(embed, embed, sd, p + "output_proj")
+    return sd
+
+
 def swin_sd(gen, depths=(2, 2, 6, 2), heads=(3, 6, 12, 24), embed=96, ws=7, p=""):
     """SwinTransformer parameters with the reference's key names (swint.py), livelier than trunc_normal(0.02)."""
     sd = {}
