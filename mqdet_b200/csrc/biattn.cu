@@ -354,8 +354,8 @@ __global__ void __launch_bounds__(640, 1) biattn_image_kernel(const __grid_const
   float* rx = reinterpret_cast<float*>(bars + 32);  // [4 parts][128 rows] partial row maxima
   float* rsum = rx + 4 * BM;                         // [4 parts][128 rows] partial row sums
   float* cmx = rsum + 4 * BM;                        // [4 lane quarters][256 tokens] column maxima
-  float* keep = cmx + 4 * 256;                       // [256] 1 = token takes part in the row softmax
-  float* s_vec = keep + 256;                         // [256] gamma
+  float* kl = cmx + 4 * 256;                         // [256] additive token mask of the row softmax: 0 keep / -inf masked
+  float* s_vec = kl + 256;                           // [256] gamma
   float* t_vec = s_vec + 256;                        // [256] gamma * bias
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -486,9 +486,10 @@ __global__ void __launch_bounds__(640, 1) biattn_image_kernel(const __grid_const
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++tcnt) {
       const int b = tile / p.tiles_per_img, ti = tile - b * p.tiles_per_img, m0 = ti * BM;
       const bool valid_row = m0 + row < p.N;
+      const bool full_tile = m0 + BM <= p.N;
       if (b != cur_b) {  // token mask of this image (warp-uniform branch: every thread walks the same items)
         asm volatile("bar.sync 1, 512;" ::: "memory");  // nobody still reads the previous image's flags
-        if (tid_e < 256) keep[tid_e] = (tid_e < p.T && (!p.mask || p.mask[(long)b * p.T + tid_e] != 0.f)) ? 1.f : 0.f;
+        if (tid_e < 256) kl[tid_e] = (tid_e < p.T && (!p.mask || p.mask[(long)b * p.T + tid_e] != 0.f)) ? 0.f : NEG_INF;
         asm volatile("bar.sync 1, 512;" ::: "memory");
         cur_b = b;
       }
@@ -498,7 +499,9 @@ __global__ void __launch_bounds__(640, 1) biattn_image_kernel(const __grid_const
         tc_fence_after();
         const uint32_t t_s = tmem_s + lane_addr + (uint32_t)(part * 64);
         // ---- pass 1 over this thread's 64 tokens: column maxima (for the text side) and the partial row maximum ----
-        float cm0 = NEG_INF, cm1 = NEG_INF, mpart = NEG_INF;
+        // The +-5e4 clamp of the scores (fuse_helper.py:245-252) is applied to the REDUCED values (clamp is monotonic:
+        // max(clamp(s)) == clamp(max(s))), not per element; `kl` carries the token mask as an additive 0 / -inf.
+        float mpart = NEG_INF;
         {
           uint32_t ra[16], rb[16];
           tmem_ld_32x16(t_s, ra);
@@ -507,39 +510,47 @@ __global__ void __launch_bounds__(640, 1) biattn_image_kernel(const __grid_const
             uint32_t (&r)[16] = (j & 1) ? rb : ra;
             tmem_ld_wait_dep(r);
             if (j + 1 < 4) tmem_ld_32x16(t_s + (uint32_t)((j + 1) * 16), (j & 1) ? ra : rb);
+            float cm[16];
+            if (full_tile) {  // warp-uniform: every row of the tile is a real image token
+#pragma unroll
+              for (int i = 0; i < 16; ++i) cm[i] = warp_redux_max(__uint_as_float(r[i]));
+            } else {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) cm[i] = warp_redux_max(valid_row ? __uint_as_float(r[i]) : NEG_INF);
+            }
+            if (lane == 0) {  // the reduction result is warp-uniform: one lane stores the 16 column maxima of this warp's 32 rows
+              float* dst = cmx + ew * 256 + part * 64 + j * 16;
+#pragma unroll
+              for (int i4 = 0; i4 < 4; ++i4)
+                *reinterpret_cast<float4*>(dst + i4 * 4) = make_float4(cm[i4 * 4], cm[i4 * 4 + 1], cm[i4 * 4 + 2], cm[i4 * 4 + 3]);
+            }
 #pragma unroll
             for (int i4 = 0; i4 < 4; ++i4) {
-              const float4 kf = *reinterpret_cast<const float4*>(keep + part * 64 + j * 16 + i4 * 4);
-              const float kk[4] = {kf.x, kf.y, kf.z, kf.w};
-#pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                const int c = j * 16 + i4 * 4 + i;
-                const float sc = fminf(fmaxf(__uint_as_float(r[i4 * 4 + i]), -clampv), clampv);
-                // column maximum over this warp's 32 image tokens (rows beyond N excluded); lane c & 31 keeps column c
-                const float red = warp_redux_max(valid_row ? sc : NEG_INF);
-                if ((c & 31) == lane) {
-                  if (c < 32) cm0 = red; else cm1 = red;
-                }
-                // masked tokens leave the row softmax (the reference adds -9e15: their exp is exactly 0 in fp32)
-                if (kk[i] != 0.f) mpart = fmaxf(mpart, sc);
-              }
+              const float4 kf = *reinterpret_cast<const float4*>(kl + part * 64 + j * 16 + i4 * 4);
+              mpart = fmaxf(mpart, __uint_as_float(r[i4 * 4 + 0]) + kf.x);
+              mpart = fmaxf(mpart, __uint_as_float(r[i4 * 4 + 1]) + kf.y);
+              mpart = fmaxf(mpart, __uint_as_float(r[i4 * 4 + 2]) + kf.z);
+              mpart = fmaxf(mpart, __uint_as_float(r[i4 * 4 + 3]) + kf.w);
             }
           }
         }
-        cmx[ew * 256 + part * 64 + lane] = cm0;
-        cmx[ew * 256 + part * 64 + 32 + lane] = cm1;
         rx[part * BM + row] = mpart;
         // the previous item's output staging (PX) must have been read by the TMA store before E overwrites it
         if (issuer && h == 0 && tcnt > 0) tma_store_wait_read_all();
         asm volatile("bar.sync 1, 512;" ::: "memory");
-        if (tid_e < p.T) {  // column-max partial of this (image, head, tile)
-          const float c4 = fmaxf(fmaxf(cmx[tid_e], cmx[256 + tid_e]), fmaxf(cmx[512 + tid_e], cmx[768 + tid_e]));
+        if (tid_e < p.T) {  // column-max partial of this (image, head, tile), clamped like the scores
+          float c4 = fmaxf(fmaxf(cmx[tid_e], cmx[256 + tid_e]), fmaxf(cmx[512 + tid_e], cmx[768 + tid_e]));
+          c4 = fminf(fmaxf(c4, -clampv), clampv);
           p.colmax_part[(((long)b * H + h) * p.tiles_per_img + ti) * p.T + tid_e] = c4;
         }
-        const float m = fmaxf(fmaxf(rx[row], rx[BM + row]), fmaxf(rx[2 * BM + row], rx[3 * BM + row]));
+        const float m_raw = fmaxf(fmaxf(rx[row], rx[BM + row]), fmaxf(rx[2 * BM + row], rx[3 * BM + row]));
         // every token masked: the reference's fp32 sum A + (-9e15) swallows A and the softmax is uniform over the T tokens
-        const bool uniform = (m == NEG_INF);
+        const bool uniform = (m_raw == NEG_INF);
+        const float m = fminf(fmaxf(m_raw, -clampv), clampv);  // max over the kept tokens of the CLAMPED scores
         const float ml2 = uniform ? 0.f : m * L2E;
+        // per-element clamping can only change exp(clamp(s) - m) when the row maximum itself exceeds the clamp (s > 5e4), or
+        // when m is so low that exp(-5e4 - m) does not underflow; otherwise exp(s - m) is bit-identical without it
+        const bool need_clamp = (m_raw > clampv) || (m_raw < -clampv + 256.f);
         if (hc > 0) mbar_wait(op_done, (hc - 1) & 1);  // the previous head's out-projection no longer reads PX
         // ---- pass 2: E = exp(S - rowmax) -> fp16 A-operand tile, partial row sum (normalisation deferred to the O conversion) ----
         float lpart = 0.f;
@@ -552,19 +563,33 @@ __global__ void __launch_bounds__(640, 1) biattn_image_kernel(const __grid_const
             tmem_ld_wait_dep(r);
             if (j + 1 < 4) tmem_ld_32x16(t_s + (uint32_t)((j + 1) * 16), (j & 1) ? ra : rb);
             float e[16];
+            if (!need_clamp && !uniform) {  // the common path: 4 issue slots per score (FFMA, FADD, MUFU.EX2, FADD)
 #pragma unroll
-            for (int i4 = 0; i4 < 4; ++i4) {
-              const float4 kf = *reinterpret_cast<const float4*>(keep + part * 64 + j * 16 + i4 * 4);
-              const float kk[4] = {kf.x, kf.y, kf.z, kf.w};
+              for (int i4 = 0; i4 < 4; ++i4) {
+                const float4 kf = *reinterpret_cast<const float4*>(kl + part * 64 + j * 16 + i4 * 4);
+                const float kk[4] = {kf.x, kf.y, kf.z, kf.w};
 #pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                const int c = j * 16 + i4 * 4 + i;
-                const float sc = fminf(fmaxf(__uint_as_float(r[i4 * 4 + i]), -clampv), clampv);
-                float ev = ex2_approx(fmaf(sc, L2E, -ml2));
-                if (kk[i] == 0.f) ev = 0.f;
-                if (uniform) ev = (part * 64 + c < p.T) ? 1.f : 0.f;
-                e[i4 * 4 + i] = ev;
-                lpart += ev;
+                for (int i = 0; i < 4; ++i) {
+                  // masked tokens: kl = -inf -> exp2(-inf) = 0, exactly what the reference's -9e15 does in fp32
+                  const float ev = ex2_approx(fmaf(__uint_as_float(r[i4 * 4 + i]), L2E, kk[i]) - ml2);
+                  e[i4 * 4 + i] = ev;
+                  lpart += ev;
+                }
+              }
+            } else {
+#pragma unroll
+              for (int i4 = 0; i4 < 4; ++i4) {
+                const float4 kf = *reinterpret_cast<const float4*>(kl + part * 64 + j * 16 + i4 * 4);
+                const float kk[4] = {kf.x, kf.y, kf.z, kf.w};
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  const int c = j * 16 + i4 * 4 + i;
+                  const float sc = fminf(fmaxf(__uint_as_float(r[i4 * 4 + i]), -clampv), clampv);
+                  float ev = ex2_approx(fmaf(sc, L2E, kk[i]) - ml2);
+                  if (uniform) ev = (part * 64 + c < p.T) ? 1.f : 0.f;
+                  e[i4 * 4 + i] = ev;
+                  lpart += ev;
+                }
               }
             }
             sts128(px_row + (((2 * j) ^ sw) << 4), pack_half2(e[0], e[1]), pack_half2(e[2], e[3]), pack_half2(e[4], e[5]),
