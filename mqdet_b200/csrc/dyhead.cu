@@ -110,7 +110,9 @@ __global__ void __launch_bounds__(256) dcn_cols_kernel(const __half* __restrict_
   }
   const __half* xb = x + ((long)b * N + lt.off[li]) * C + lane * 8;
   __half* dst = cols + r * 9 * C + lane * 8;
-#pragma unroll 1
+  // All four corner rows of a tap are fetched unconditionally (indices clamped into the map, invalid corners get weight 0)
+  // and three taps are in flight at a time: 12 independent 16-byte loads per lane instead of one load -> use -> next load.
+#pragma unroll 3
   for (int tap = 0; tap < 9; ++tap) {
     float off_h = 0.f, off_w = 0.f, m = 1.f;
     if (om) {
@@ -120,38 +122,30 @@ __global__ void __launch_bounds__(256) dcn_cols_kernel(const __half* __restrict_
     }
     const float h_im = (float)(ho * stride - 1 + tap / 3) + off_h;
     const float w_im = (float)(wo * stride - 1 + tap % 3) + off_w;
+    const bool inside = h_im > -1.f && w_im > -1.f && h_im < (float)Hi && w_im < (float)Wi;
+    const int h_low = (int)floorf(h_im), w_low = (int)floorf(w_im);
+    const int h_high = h_low + 1, w_high = w_low + 1;
+    const float lh = h_im - h_low, lw = w_im - w_low, hh = 1.f - lh, hw = 1.f - lw;
+    const bool hl_ok = inside && h_low >= 0, hh_ok = inside && h_high <= Hi - 1;
+    const bool wl_ok = w_low >= 0, wh_ok = w_high <= Wi - 1;
+    const float w1 = (hl_ok && wl_ok) ? hh * hw : 0.f, w2 = (hl_ok && wh_ok) ? hh * lw : 0.f;
+    const float w3 = (hh_ok && wl_ok) ? lh * hw : 0.f, w4 = (hh_ok && wh_ok) ? lh * lw : 0.f;
+    const int hl = min(max(h_low, 0), Hi - 1), hh_i = min(max(h_high, 0), Hi - 1);
+    const int wl = min(max(w_low, 0), Wi - 1), wh_i = min(max(w_high, 0), Wi - 1);
+    float v1[8], v2[8], v3[8], v4[8];
+    ld8h(xb + (long)(hl * Wi + wl) * C, v1);
+    ld8h(xb + (long)(hl * Wi + wh_i) * C, v2);
+    ld8h(xb + (long)(hh_i * Wi + wl) * C, v3);
+    ld8h(xb + (long)(hh_i * Wi + wh_i) * C, v4);
     float acc[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) acc[i] = 0.f;
-    if (h_im > -1.f && w_im > -1.f && h_im < (float)Hi && w_im < (float)Wi) {
-      const int h_low = (int)floorf(h_im), w_low = (int)floorf(w_im);
-      const int h_high = h_low + 1, w_high = w_low + 1;
-      const float lh = h_im - h_low, lw = w_im - w_low, hh = 1.f - lh, hw = 1.f - lw;
-      float v[8];
-      // corners of weight zero are not fetched (plain 3x3 sampling: integer coordinates -> one corner per tap)
-      const float w1 = hh * hw, w2 = hh * lw, w3 = lh * hw, w4 = lh * lw;
-      if (h_low >= 0 && w_low >= 0 && w1 != 0.f) {
-        ld8h(xb + (long)(h_low * Wi + w_low) * C, v);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) acc[i] += w1 * v[i];
-      }
-      if (h_low >= 0 && w_high <= Wi - 1 && w2 != 0.f) {
-        ld8h(xb + (long)(h_low * Wi + w_high) * C, v);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) acc[i] += w2 * v[i];
-      }
-      if (h_high <= Hi - 1 && w_low >= 0 && w3 != 0.f) {
-        ld8h(xb + (long)(h_high * Wi + w_low) * C, v);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) acc[i] += w3 * v[i];
-      }
-      if (h_high <= Hi - 1 && w_high <= Wi - 1 && w4 != 0.f) {
-        ld8h(xb + (long)(h_high * Wi + w_high) * C, v);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) acc[i] += w4 * v[i];
-      }
-#pragma unroll
-      for (int i = 0; i < 8; ++i) acc[i] *= m;
+    for (int i = 0; i < 8; ++i) {
+      // same accumulation order as before (corner 1..4, then the mask): identical results; a zero weight contributes 0
+      float a = w1 * v1[i];
+      a += w2 * v2[i];
+      a += w3 * v3[i];
+      a += w4 * v4[i];
+      acc[i] = a * m;
     }
     st8h(dst + tap * C, acc);
   }
