@@ -81,6 +81,15 @@ typedef struct mqdet_gemm_args {
 
 int mqdet_gemm_f16(const mqdet_gemm_args* args, int impl, void* stream);
 
+/* Dense multi-head cross-attention with head dim 32 in ONE flash-style kernel (PreSelect: MaskedCrossAttention.forward with
+ * spase_forward=False, no mask, modeling_bert_new.py:186-248,398-409): out[b,t,h,:] = softmax_i(q[b,t,h,:] . k[b,i,h,:]) v[b,i,h,:].
+ *   q [B][Tq][q_ld] f16 (already scaled; head h at column h*32), kv [B][I][kv_ld] f16 (K of head h at column h*32, V at
+ *   v_col0 + h*32: the to_kv Linear output as is), out [B][Tq][o_ld] f16; *_b = image strides in elements.  The fp32 score
+ *   tensor [B, heads, Tq, I] is never materialised (online softmax over 64-token chunks, fp32 statistics, fp16 P). */
+int mqdet_dense_cross_attn(const void* q, int64_t q_ld, int64_t q_b, const void* kv, int64_t kv_ld, int64_t kv_b, int64_t v_col0,
+                           void* out, int64_t o_ld, int64_t o_b, int64_t B, int64_t Tq, int64_t I, int64_t heads,
+                           int64_t head_dim, void* stream);
+
 /* Row-wise LayerNorm over the last dim D (biased variance, eps inside sqrt).
  * x: [rows, D] in_dtype with row stride ldx; out16 (fp16) and/or out32 (fp32) may be NULL.
  * If zero_row_period > 0, rows r with (r % zero_row_period) == zero_row_period-1 are treated as an

@@ -99,6 +99,7 @@ class MaskedCrossAttention(nn.Module):
         self.to_q = nn.Linear(input_dim, inner_dim, bias=False)
         self.to_kv = nn.Linear(input_dim, inner_dim * 2, bias=False)
         self.to_out = nn.Linear(inner_dim, output_dim, bias=False)
+        self.flash = True  # dense path: fused attention kernel (False: the unfused GEMM / softmax_rows path, kept for A/B tests)
 
     # -- sparse (GCP) ------------------------------------------------------------------------------------------
     def _sparse(self, x32, vision, attention_mask, out_residual=None):
@@ -124,6 +125,15 @@ class MaskedCrossAttention(nn.Module):
         Ipad = (I + 7) // 8 * 8
         xn = _ln16(x32, self.norm)
         cn = _ln16(ctx, self.norm_kv) if self.norm_kv is not None else ops.cast_f16(ctx)
+        if d == 32 and self.flash:
+            # ONE projection for K | V (the to_kv Linear as is) and ONE flash-style attention kernel: the fp32 score tensor
+            # [B, H, Tq, I] (571 MB at B = 8, 80 classes) is never written
+            q = ops.gemm(xn.view(B * Tq, D), w16(self.to_q.weight), alpha=self.scale).view(B, Tq, inner)
+            kv = ops.gemm(cn.view(B * I, D), w16(self.to_kv.weight)).view(B, I, 2 * inner)
+            o = ops.dense_cross_attn(q, kv, H, d)
+            out = ops.gemm(o.view(B * Tq, inner), w16(self.to_out.weight), out_dtype=torch.float32,
+                           residual=residual.reshape(B * Tq, -1) if residual is not None else None)
+            return out.view(B, Tq, -1)
         q = ops.gemm(xn.view(B * Tq, D), w16(self.to_q.weight), alpha=self.scale).view(B, Tq, H, d)
         k = ops.gemm(cn.view(B * I, D), w16(self.to_kv.weight, rows=(0, inner))).view(B, I, H, d)
         # V^T[b] = W_v . cn[b]^T  -> [B, inner, Ipad] so that P.V is again a K-major x K-major product

@@ -325,6 +325,22 @@ def contrastive_embed(x16, y16, text_token_mask, max_text_len):
     return out
 
 
+def dense_cross_attn(q, kv, heads, dim_head):
+    """Flash-style dense cross-attention (PreSelect): q [B,Tq,H*32] fp16 (scaled), kv [B,I,2*H*32] fp16 (K | V halves) ->
+    [B,Tq,H*32] fp16 = softmax_i(q.k^T) v per head, without materialising the scores."""
+    global launch_count
+    _need_cuda(q, kv)
+    B, Tq, inner = q.shape
+    I = kv.shape[1]
+    if q.dtype != torch.float16 or kv.dtype != torch.float16 or q.stride(-1) != 1 or kv.stride(-1) != 1:
+        raise _lib.MqdetError("dense_cross_attn: fp16 operands with a contiguous last dimension required")
+    out = torch.empty((B, Tq, inner), dtype=torch.float16, device=q.device)
+    check(load().mqdet_dense_cross_attn(_ptr(q), q.stride(1), q.stride(0), _ptr(kv), kv.stride(1), kv.stride(0), inner, _ptr(out),
+                                        out.stride(1), out.stride(0), B, Tq, I, heads, dim_head, _stream()), "dense_cross_attn")
+    launch_count += 1
+    return out
+
+
 def gcp_build_index(mask, S):
     """mask [B, V, T] fp32 0/1 -> (idx int32 [B, T, S] padded with V, counts int32 [B, T])."""
     global launch_count
