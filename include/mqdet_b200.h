@@ -170,19 +170,21 @@ int mqdet_biattn_text_vn(const void* k, int64_t k_ld, int64_t k_b1, int64_t k_b2
 
 /* Image -> text side of BiMultiHeadAttention fused with the out-projection, layer scale and residual
  * (maskrcnn_benchmark/utils/fuse_helper.py:240-256,277-302,420-425) in ONE persistent tcgen05 kernel: per 128 image tokens and
- * head, S = q k^T stays in TMEM (fp32) -> clamp -> masked softmax over the T tokens in registers -> P V_l -> out-projection
- * accumulated over the heads in a second TMEM accumulator -> out = res + gamma * (acc + bias).  Neither the score matrix nor
- * the per-head context reach HBM.  mask [B][T] f32 (0 = padding token: probability exactly 0, like the reference's -9e15) or
- * NULL; gamma / res may be NULL (1 / none).
- *   q [B][N][H*256] (already scaled), k [B][T][H*256], vlT [B][H*256][T] (values_l^T), w [256][H*256] f16; *_ld row strides,
- *   *_b image strides (elements, multiples of 8); out [B][N][256] f16.  8 <= T <= 256, T % 8 == 0, head dim 256.
+ * head, S = q k^T stays in TMEM (fp32) -> clamp -> masked softmax over the T tokens in registers -> P (fp16, shared memory) ->
+ * acc += P mT_h^T in a second TMEM accumulator summed over the heads -> out = res + gamma * (acc + bias).  Neither the score
+ * matrix nor a per-head context reaches HBM.  mask [B][T] f32 (0 = padding token: probability exactly 0, like the reference's
+ * -9e15; an all-masked image gets the uniform distribution the reference's fp32 sum produces) or NULL; gamma / res may be NULL.
+ *   q [B][N][H*256] (already scaled), k [B][T][H*256] f16; *_ld row strides, *_b image strides (elements, multiples of 8);
+ *   mT [B][H][256][T] f16 with mT[b][h][o][t] = sum_d W_out[o][h*256+d] * V_l[b][t][h*256+d]: the value and output projections
+ *   of head h folded into one operand ((P V_l,h) W_h^T == P (V_l,h W_h^T); m_ld row stride, m_bh head stride, m_b image stride);
+ *   out [B][N][256] f16.  8 <= T <= 256, T % 8 == 0, head dim 256.
  * colmax [B*H][T] f32 receives max_n clamp(S[n][t]) — the softmax shift of the text -> image side (mqdet_biattn_text_vn).
  * workspace: mqdet_biattn_image_workspace_floats(B, H, N, T) floats. */
 int64_t mqdet_biattn_image_workspace_floats(int64_t B, int64_t H, int64_t N, int64_t T);
-int mqdet_biattn_image(const void* q, int64_t q_ld, int64_t q_b, const void* k, int64_t k_ld, int64_t k_b, const void* vlT,
-                       int64_t vl_ld, int64_t vl_b, const void* w, int64_t w_ld, const float* bias, const float* gamma,
-                       const void* res, int64_t res_ld, int64_t res_b, const float* mask, float clamp, void* out, int64_t o_ld,
-                       int64_t o_b, float* colmax, float* workspace, int64_t B, int64_t H, int64_t N, int64_t T, void* stream);
+int mqdet_biattn_image(const void* q, int64_t q_ld, int64_t q_b, const void* k, int64_t k_ld, int64_t k_b, const void* mT,
+                       int64_t m_ld, int64_t m_bh, int64_t m_b, const float* bias, const float* gamma, const void* res,
+                       int64_t res_ld, int64_t res_b, const float* mask, float clamp, void* out, int64_t o_ld, int64_t o_b,
+                       float* colmax, float* workspace, int64_t B, int64_t H, int64_t N, int64_t T, void* stream);
 
 /* Text side of the dot-product token head (vldyhead.py:810,818): e = x / max(||x||, eps) written as fp16 and/or
  * fp32, dot[r] = e[r,:] . w + b0[0] (w, b0, dot optional). */

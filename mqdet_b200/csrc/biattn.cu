@@ -293,22 +293,26 @@ __global__ void __launch_bounds__(640, 1) biattn_text_kernel(const __grid_consta
 
 // =====================================================================================================================
 // Image -> text side, fused with the out-projection, layer scale and residual.
-//   q  [B][N][H*256] fp16 (already scaled by d^-1/2)      k  [B][T][H*256] fp16      vlT [B][H*256][T] fp16 (values_l^T)
-//   w  [256][H*256] fp16 (out_v_proj.weight)               out[B][N][256] fp16
+//   q  [B][N][H*256] fp16 (already scaled by d^-1/2)      k  [B][T][H*256] fp16
+//   mT [B][H][256 o][T] fp16 = (W_h V_l,h^T): the value AND output projections of head h folded into one [T x 256] operand per
+//                              (image, head) by a tiny GEMM — (P V_l,h) W_h^T == P (V_l,h W_h^T), so the per-head context O never
+//                              exists and a head costs two tensor-core products instead of three
+//   out[B][N][256] fp16
 // Persistent: one CTA per SM walks (image, 128-token tile) items; per item the eight heads run back to back:
 //   S (128 x 256 t)   = Q_h . K_h^T          16 MMAs 128x256x16, Q_h and K_h streamed as [.. x 64] k-blocks through a 3-stage ring
-//   E                 = exp(clamp(S) - rowmax) over the unmasked tokens (thread == image token == TMEM lane, 4 warps per lane
-//                       quarter, 64 tokens each, two passes over the TMEM columns; the partial row maxima are exchanged through
-//                       shared memory), fp16 -> shared memory (A operand); the 1 / rowsum goes into the O conversion
-//   O (128 x 256 d)   = E . V_l,h            into the same TMEM columns as S
-//   D (128 x 256 o)  += fp16(O / rowsum) . W_h^T      second TMEM accumulator, summed over the heads
-// The issuer runs S of head h+1 ahead of D of head h, so the tensor pipe works on D(h) while the warps exponentiate S(h+1).
+//   P                 = softmax_t(clamp(S) + mask): thread == image token == TMEM lane, 4 warps per lane quarter, 64 tokens each;
+//                       pass 1 over the TMEM columns = column maxima (for the text side) + partial row maxima, pass 2 = exp into
+//                       registers + partial row sums; both statistics are exchanged through shared memory; P = e / rowsum -> fp16
+//                       -> shared memory (A operand)
+//   D (128 x 256 o)  += P . mT_h^T           second TMEM accumulator, summed over the heads
 //   out               = res + gamma * (D + bias)
-// TMEM: columns 0..255 scratch (S, then O), 256..511 D.  Shared memory: one 64 KB tile PX (P, then fp16 O, finally the output
-// staging), 3 x 48 KB ring stages ([128 x 64] A slot + [256 x 64] B slot), exchange arrays.
+// The scratch columns are free as soon as pass 2 has read them, so the issuer runs S of head h+1 while the warps normalise and
+// store P of head h, and D of head h while they exponentiate S of head h+1.
+// TMEM: columns 0..255 S, 256..511 D.  Shared memory: one 64 KB tile PX (P, finally the output staging), 3 x 48 KB ring stages
+// ([128 x 64] A slot + [256 x 64] B slot), exchange arrays.
 // Column maxima of the clamped scores over the tile's valid rows go to colmax_part[b][h][tile][t] (reduced by
 // colmax_reduce_kernel); the text side needs them as the softmax shift.
-// Roles: warp 0 = TMA producer, warp 1 = MMA issuer, warp 2 = TMEM allocator, warps 4-19 = softmax / conversion / epilogue.
+// Roles: warp 0 = TMA producer, warp 1 = MMA issuer, warp 2 = TMEM allocator, warps 4-19 = softmax / epilogue.
 // =====================================================================================================================
 constexpr int BI_STAGES = 3;
 struct BiCfg {
@@ -316,7 +320,7 @@ struct BiCfg {
   static constexpr int A_BYTES = BM * BK * 2;                // 16 KB
   static constexpr int B_BYTES = 256 * BK * 2;               // 32 KB
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;      // 48 KB
-  static constexpr int EXTRA_BYTES = (4 * BM * 2 + 4 * 256 + 256 + 512) * 4;  // rx, cmx, keep, s_vec|t_vec
+  static constexpr int EXTRA_BYTES = (4 * BM * 2 + 4 * 256 + 256 + 512) * 4;  // rx | rsum, cmx, kl, s_vec | t_vec
   static constexpr int SMEM_BYTES = PX_BYTES + BI_STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + EXTRA_BYTES;
 };
 static_assert(BiCfg::SMEM_BYTES <= 232448, "biattn_image: dynamic shared memory above the 227 KB per-CTA limit");
@@ -331,10 +335,15 @@ struct BiP {
   int B, H, T, N, tiles_per_img, total_tiles;
 };
 
+__device__ __forceinline__ float lds32f(uint32_t addr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
+  return v;
+}
+
 __global__ void __launch_bounds__(640, 1) biattn_image_kernel(const __grid_constant__ CUtensorMap tma_q,
                                                               const __grid_constant__ CUtensorMap tma_k,
-                                                              const __grid_constant__ CUtensorMap tma_vl,
-                                                              const __grid_constant__ CUtensorMap tma_w,
+                                                              const __grid_constant__ CUtensorMap tma_m,
                                                               const __grid_constant__ CUtensorMap tma_o, const BiP p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -344,12 +353,10 @@ __global__ void __launch_bounds__(640, 1) biattn_image_kernel(const __grid_const
   uint64_t* full_bar = bars;                     // [3] ring stage landed
   uint64_t* empty_bar = bars + BI_STAGES;        // [3] its MMAs retired
   uint64_t* s_full = bars + 6;                   // S complete
-  uint64_t* p_ready = bars + 7;                  // P written (16 warps); also: S has been read
-  uint64_t* ov_full = bars + 8;                  // O complete
-  uint64_t* scratch_free = bars + 9;             // O has been read (16 warps)
-  uint64_t* ov16_ready = bars + 10;              // fp16 O written (16 warps)
-  uint64_t* op_done = bars + 11;                 // the head's out-projection MMAs retired: PX may be rewritten; last head: D complete
-  uint64_t* dv_free = bars + 12;                 // D has been read (16 warps)
+  uint64_t* scratch_free = bars + 7;             // S has been read (16 warps): the scratch columns may take the next head's S
+  uint64_t* p_ready = bars + 8;                  // P written (16 warps)
+  uint64_t* op_done = bars + 9;                  // the head's P . mT MMAs retired: PX may be rewritten; last head: D complete
+  uint64_t* dv_free = bars + 10;                 // D has been read (16 warps)
   uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(bars + 13);
   float* rx = reinterpret_cast<float*>(bars + 32);  // [4 parts][128 rows] partial row maxima
   float* rsum = rx + 4 * BM;                         // [4 parts][128 rows] partial row sums
@@ -364,18 +371,15 @@ __global__ void __launch_bounds__(640, 1) biattn_image_kernel(const __grid_const
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tma_q);
     tma_prefetch_desc(&tma_k);
-    tma_prefetch_desc(&tma_vl);
-    tma_prefetch_desc(&tma_w);
+    tma_prefetch_desc(&tma_m);
     tma_prefetch_desc(&tma_o);
     for (int s = 0; s < BI_STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
     mbar_init(s_full, 1);
-    mbar_init(p_ready, 16);
-    mbar_init(ov_full, 1);
     mbar_init(scratch_free, 16);
-    mbar_init(ov16_ready, 16);
+    mbar_init(p_ready, 16);
     mbar_init(op_done, 1);
     mbar_init(dv_free, 16);
     fence_mbar_init();
@@ -392,7 +396,7 @@ __global__ void __launch_bounds__(640, 1) biattn_image_kernel(const __grid_const
       int it = 0;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
         const int b = tile / p.tiles_per_img, m0 = (tile - b * p.tiles_per_img) * BM;
-        // consumption order of the MMA issuer: S(0); then per head  O(h), S(h+1), D(h)
+        // consumption order of the MMA issuer: S(0); then per head  S(h+1), D(h)
         auto load = [&](int ph, int h) {
           for (int kb = 0; kb < 4; ++kb, ++it) {
             const int s = it % BI_STAGES;
@@ -402,20 +406,16 @@ __global__ void __launch_bounds__(640, 1) biattn_image_kernel(const __grid_const
               mbar_expect_tx(&full_bar[s], BiCfg::STAGE_BYTES);
               tma_load_4d(st, &tma_q, &full_bar[s], h * 256 + kb * BK, m0, b, 0);
               tma_load_4d(st + BiCfg::A_BYTES, &tma_k, &full_bar[s], h * 256 + kb * BK, 0, b, 0);
-            } else if (ph == 1) {  // O: B = V_l,h^T [256 d x 64 t]
+            } else {  // D: B = mT_h [256 o x 64 t]
               mbar_expect_tx(&full_bar[s], BiCfg::B_BYTES);
-              tma_load_4d(st + BiCfg::A_BYTES, &tma_vl, &full_bar[s], kb * BK, h * 256, b, 0);
-            } else {  // D: B = W[:, h*256 + kb*64 ..] [256 o x 64 d]
-              mbar_expect_tx(&full_bar[s], BiCfg::B_BYTES);
-              tma_load_4d(st + BiCfg::A_BYTES, &tma_w, &full_bar[s], h * 256 + kb * BK, 0, 0, 0);
+              tma_load_4d(st + BiCfg::A_BYTES, &tma_m, &full_bar[s], kb * BK, 0, h, b);
             }
           }
         };
         load(0, 0);
         for (int h = 0; h < H; ++h) {
-          load(1, h);
           if (h + 1 < H) load(0, h + 1);
-          load(2, h);
+          load(1, h);
         }
       }
     }
@@ -424,46 +424,43 @@ __global__ void __launch_bounds__(640, 1) biattn_image_kernel(const __grid_const
       constexpr uint32_t idesc = umma_idesc_f16(BM, 256, 0);
       int it = 0, hc = 0, tcnt = 0;
       const uint32_t px_addr = smem_u32(px);
-      auto issue = [&](int ph, int h, int hcur) {
-        // ph 0: S = Q_h K_h^T -> scratch;  1: O = P V_l,h -> scratch;  2: D += fp16(O) W_h^T
+      auto issue = [&](int ph, int h) {
+        // ph 0: S = Q_h K_h^T -> scratch columns;  1: D += P mT_h^T
         for (int kb = 0; kb < 4; ++kb, ++it) {
           const int s = it % BI_STAGES;
           mbar_wait(&full_bar[s], (it / BI_STAGES) & 1);
           tc_fence_after();
           const uint32_t st = smem_u32(ring + s * BiCfg::STAGE_BYTES);
           const uint32_t a0 = ph == 0 ? st : px_addr + kb * BiCfg::A_BYTES, b0 = st + BiCfg::A_BYTES;
-          const uint32_t acc = ph == 2 ? tmem_d : tmem_s;
+          const uint32_t acc = ph == 0 ? tmem_s : tmem_d;
 #pragma unroll
           for (int k = 0; k < 4; ++k)
             tc_mma_f16(acc, umma_desc_k_sw128(a0 + k * 32), umma_desc_k_sw128(b0 + k * 32), idesc,
-                       ((ph == 2 ? h : 0) | kb | k) != 0 ? 1u : 0u);
+                       ((ph == 1 ? h : 0) | kb | k) != 0 ? 1u : 0u);
           tc_commit(&empty_bar[s]);
         }
-        tc_commit(ph == 0 ? s_full : (ph == 1 ? ov_full : op_done));
+        tc_commit(ph == 0 ? s_full : op_done);
       };
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++tcnt) {
-        // S of the item's first head (the previous item's last O must have been read out of the scratch columns)
+        // S of the item's first head (the previous item's last S must have been read out of the scratch columns)
         if (hc > 0) {
           mbar_wait(scratch_free, (hc - 1) & 1);
           tc_fence_after();
         }
-        issue(0, 0, hc);
+        issue(0, 0);
         for (int h = 0; h < H; ++h, ++hc) {
-          mbar_wait(p_ready, hc & 1);  // P in PX; S has been read
-          tc_fence_after();
-          issue(1, h, hc);
-          if (h + 1 < H) {  // the next head's S goes ahead of this head's out-projection: it only needs the scratch columns
+          if (h + 1 < H) {  // the next head's S only needs the scratch columns: it runs while P of this head is written
             mbar_wait(scratch_free, hc & 1);
             tc_fence_after();
-            issue(0, h + 1, hc + 1);
+            issue(0, h + 1);
           }
-          mbar_wait(ov16_ready, hc & 1);
+          mbar_wait(p_ready, hc & 1);
           tc_fence_after();
           if (h == 0 && tcnt > 0) {  // the previous item's D must have been read by the epilogue
             mbar_wait(dv_free, (tcnt - 1) & 1);
             tc_fence_after();
           }
-          issue(2, h, hc);
+          issue(1, h);
         }
       }
     }
@@ -473,6 +470,7 @@ __global__ void __launch_bounds__(640, 1) biattn_image_kernel(const __grid_const
     const int sw = row & 7;
     const uint32_t lane_addr = (uint32_t)(ew * 32) << 16;
     const uint32_t px_row = smem_u32(px) + part * BiCfg::A_BYTES + row * 128;  // this thread's 128-byte row of k-block `part`
+    const uint32_t kl_addr = smem_u32(kl) + part * 64 * 4, rx_addr = smem_u32(rx) + row * 4, rsum_addr = smem_u32(rsum) + row * 4;
     constexpr float L2E = 1.4426950408889634f;
     const float NEG_INF = __int_as_float(0xff800000);
     const float clampv = p.clamp > 0.f ? p.clamp : 3.0e38f;
@@ -494,7 +492,7 @@ __global__ void __launch_bounds__(640, 1) biattn_image_kernel(const __grid_const
         cur_b = b;
       }
       for (int h = 0; h < H; ++h, ++hc) {
-        // ================= S -> E = exp(S - rowmax) (unnormalised, fp16) =================
+        // ================= S -> P = softmax_t(clamp(S) + mask) =================
         mbar_wait(s_full, hc & 1);
         tc_fence_after();
         const uint32_t t_s = tmem_s + lane_addr + (uint32_t)(part * 64);
@@ -519,14 +517,15 @@ __global__ void __launch_bounds__(640, 1) biattn_image_kernel(const __grid_const
               for (int i = 0; i < 16; ++i) cm[i] = warp_redux_max(valid_row ? __uint_as_float(r[i]) : NEG_INF);
             }
             if (lane == 0) {  // the reduction result is warp-uniform: one lane stores the 16 column maxima of this warp's 32 rows
-              float* dst = cmx + ew * 256 + part * 64 + j * 16;
+              const uint32_t dst = smem_u32(cmx) + (uint32_t)((ew * 256 + part * 64 + j * 16) * 4);
 #pragma unroll
               for (int i4 = 0; i4 < 4; ++i4)
-                *reinterpret_cast<float4*>(dst + i4 * 4) = make_float4(cm[i4 * 4], cm[i4 * 4 + 1], cm[i4 * 4 + 2], cm[i4 * 4 + 3]);
+                sts128(dst + i4 * 16, __float_as_uint(cm[i4 * 4]), __float_as_uint(cm[i4 * 4 + 1]), __float_as_uint(cm[i4 * 4 + 2]),
+                       __float_as_uint(cm[i4 * 4 + 3]));
             }
 #pragma unroll
             for (int i4 = 0; i4 < 4; ++i4) {
-              const float4 kf = *reinterpret_cast<const float4*>(kl + part * 64 + j * 16 + i4 * 4);
+              const float4 kf = lds128f(kl_addr + (uint32_t)((j * 16 + i4 * 4) * 4));
               mpart = fmaxf(mpart, __uint_as_float(r[i4 * 4 + 0]) + kf.x);
               mpart = fmaxf(mpart, __uint_as_float(r[i4 * 4 + 1]) + kf.y);
               mpart = fmaxf(mpart, __uint_as_float(r[i4 * 4 + 2]) + kf.z);
@@ -535,7 +534,7 @@ __global__ void __launch_bounds__(640, 1) biattn_image_kernel(const __grid_const
           }
         }
         rx[part * BM + row] = mpart;
-        // the previous item's output staging (PX) must have been read by the TMA store before E overwrites it
+        // the previous item's output staging (PX) must have been read by the TMA store before P overwrites it
         if (issuer && h == 0 && tcnt > 0) tma_store_wait_read_all();
         asm volatile("bar.sync 1, 512;" ::: "memory");
         if (tid_e < p.T) {  // column-max partial of this (image, head, tile), clamped like the scores
@@ -543,7 +542,7 @@ __global__ void __launch_bounds__(640, 1) biattn_image_kernel(const __grid_const
           c4 = fminf(fmaxf(c4, -clampv), clampv);
           p.colmax_part[(((long)b * H + h) * p.tiles_per_img + ti) * p.T + tid_e] = c4;
         }
-        const float m_raw = fmaxf(fmaxf(rx[row], rx[BM + row]), fmaxf(rx[2 * BM + row], rx[3 * BM + row]));
+        const float m_raw = fmaxf(fmaxf(lds32f(rx_addr), lds32f(rx_addr + BM * 4)), fmaxf(lds32f(rx_addr + 2 * BM * 4), lds32f(rx_addr + 3 * BM * 4)));
         // every token masked: the reference's fp32 sum A + (-9e15) swallows A and the softmax is uniform over the T tokens
         const bool uniform = (m_raw == NEG_INF);
         const float m = fminf(fmaxf(m_raw, -clampv), clampv);  // max over the kept tokens of the CLAMPED scores
@@ -551,8 +550,8 @@ __global__ void __launch_bounds__(640, 1) biattn_image_kernel(const __grid_const
         // per-element clamping can only change exp(clamp(s) - m) when the row maximum itself exceeds the clamp (s > 5e4), or
         // when m is so low that exp(-5e4 - m) does not underflow; otherwise exp(s - m) is bit-identical without it
         const bool need_clamp = (m_raw > clampv) || (m_raw < -clampv + 256.f);
-        if (hc > 0) mbar_wait(op_done, (hc - 1) & 1);  // the previous head's out-projection no longer reads PX
-        // ---- pass 2: E = exp(S - rowmax) -> fp16 A-operand tile, partial row sum (normalisation deferred to the O conversion) ----
+        // ---- pass 2: e = exp(S - rowmax) kept in registers, partial row sum ----
+        float e[64];
         float lpart = 0.f;
         {
           uint32_t ra[16], rb[16];
@@ -562,24 +561,28 @@ __global__ void __launch_bounds__(640, 1) biattn_image_kernel(const __grid_const
             uint32_t (&r)[16] = (j & 1) ? rb : ra;
             tmem_ld_wait_dep(r);
             if (j + 1 < 4) tmem_ld_32x16(t_s + (uint32_t)((j + 1) * 16), (j & 1) ? ra : rb);
-            float e[16];
+            if (j == 3) {  // S has left the scratch columns: they may take the next head's S
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(scratch_free);
+            }
             if (!need_clamp && !uniform) {  // the common path: 4 issue slots per score (FFMA, FADD, MUFU.EX2, FADD)
 #pragma unroll
               for (int i4 = 0; i4 < 4; ++i4) {
-                const float4 kf = *reinterpret_cast<const float4*>(kl + part * 64 + j * 16 + i4 * 4);
+                const float4 kf = lds128f(kl_addr + (uint32_t)((j * 16 + i4 * 4) * 4));
                 const float kk[4] = {kf.x, kf.y, kf.z, kf.w};
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                   // masked tokens: kl = -inf -> exp2(-inf) = 0, exactly what the reference's -9e15 does in fp32
                   const float ev = ex2_approx(fmaf(__uint_as_float(r[i4 * 4 + i]), L2E, kk[i]) - ml2);
-                  e[i4 * 4 + i] = ev;
+                  e[j * 16 + i4 * 4 + i] = ev;
                   lpart += ev;
                 }
               }
             } else {
 #pragma unroll
               for (int i4 = 0; i4 < 4; ++i4) {
-                const float4 kf = *reinterpret_cast<const float4*>(kl + part * 64 + j * 16 + i4 * 4);
+                const float4 kf = lds128f(kl_addr + (uint32_t)((j * 16 + i4 * 4) * 4));
                 const float kk[4] = {kf.x, kf.y, kf.z, kf.w};
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
@@ -587,59 +590,33 @@ __global__ void __launch_bounds__(640, 1) biattn_image_kernel(const __grid_const
                   const float sc = fminf(fmaxf(__uint_as_float(r[i4 * 4 + i]), -clampv), clampv);
                   float ev = ex2_approx(fmaf(sc, L2E, kk[i]) - ml2);
                   if (uniform) ev = (part * 64 + c < p.T) ? 1.f : 0.f;
-                  e[i4 * 4 + i] = ev;
+                  e[c] = ev;
                   lpart += ev;
                 }
               }
             }
-            sts128(px_row + (((2 * j) ^ sw) << 4), pack_half2(e[0], e[1]), pack_half2(e[2], e[3]), pack_half2(e[4], e[5]),
-                   pack_half2(e[6], e[7]));
-            sts128(px_row + (((2 * j + 1) ^ sw) << 4), pack_half2(e[8], e[9]), pack_half2(e[10], e[11]), pack_half2(e[12], e[13]),
-                   pack_half2(e[14], e[15]));
           }
         }
         rsum[part * BM + row] = lpart;
-        fence_proxy_async();  // generic-proxy writes of E -> visible to the tensor core (async proxy)
-        tc_fence_before();
+        asm volatile("bar.sync 1, 512;" ::: "memory");
+        const float inv = 1.f / (lds32f(rsum_addr) + lds32f(rsum_addr + BM * 4) + lds32f(rsum_addr + 2 * BM * 4) + lds32f(rsum_addr + 3 * BM * 4));
+        if (hc > 0) mbar_wait(op_done, (hc - 1) & 1);  // the previous head's product no longer reads PX
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          sts128(px_row + ((j ^ sw) << 4), pack_half2(e[8 * j] * inv, e[8 * j + 1] * inv), pack_half2(e[8 * j + 2] * inv, e[8 * j + 3] * inv),
+                 pack_half2(e[8 * j + 4] * inv, e[8 * j + 5] * inv), pack_half2(e[8 * j + 6] * inv, e[8 * j + 7] * inv));
+        fence_proxy_async();  // generic-proxy writes of P -> visible to the tensor core (async proxy)
         __syncwarp();
         if (lane == 0) mbar_arrive(p_ready);
-        // ================= O = (E V) / rowsum -> fp16 =================
-        mbar_wait(ov_full, hc & 1);
-        tc_fence_after();
-        {
-          // every warp's partial sums were written before its p_ready arrival, which the O MMAs waited for
-          const float inv = 1.f / (rsum[row] + rsum[BM + row] + rsum[2 * BM + row] + rsum[3 * BM + row]);
-          uint32_t ra[16], rb[16];
-          tmem_ld_32x16(t_s, ra);
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            uint32_t (&r)[16] = (j & 1) ? rb : ra;
-            tmem_ld_wait_dep(r);
-            if (j + 1 < 4) tmem_ld_32x16(t_s + (uint32_t)((j + 1) * 16), (j & 1) ? ra : rb);
-            if (j == 3) {  // O has left the scratch columns: they may take the next head's S
-              tc_fence_before();
-              __syncwarp();
-              if (lane == 0) mbar_arrive(scratch_free);
-            }
-            uint32_t hh[8];
-#pragma unroll
-            for (int q2 = 0; q2 < 8; ++q2)
-              hh[q2] = pack_half2(__uint_as_float(r[2 * q2]) * inv, __uint_as_float(r[2 * q2 + 1]) * inv);
-            sts128(px_row + (((2 * j) ^ sw) << 4), hh[0], hh[1], hh[2], hh[3]);
-            sts128(px_row + (((2 * j + 1) ^ sw) << 4), hh[4], hh[5], hh[6], hh[7]);
-          }
-        }
-        fence_proxy_async();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(ov16_ready);
       }
       // ================= item epilogue: out = res + gamma * (D + bias) =================
-      mbar_wait(op_done, (hc - 1) & 1);  // the last head's out-projection: D complete, PX free
+      mbar_wait(op_done, (hc - 1) & 1);  // the last head's product: D complete, PX free
       tc_fence_after();
       {
         const bool has_res = p.res != nullptr && valid_row;
         const uint4* src = reinterpret_cast<const uint4*>(p.res + (long)b * p.res_b + (long)(m0 + row) * p.res_ld + part * 64);
         const uint32_t t_d = tmem_d + lane_addr + (uint32_t)(part * 64);
+        const uint32_t sv_addr = smem_u32(s_vec) + part * 64 * 4, tv_addr = smem_u32(t_vec) + part * 64 * 4;
         uint32_t ra[16], rb[16];
         tmem_ld_32x16(t_d, ra);
 #pragma unroll
@@ -652,7 +629,7 @@ __global__ void __launch_bounds__(640, 1) biattn_image_kernel(const __grid_const
           }
           tmem_ld_wait_dep(r);
           if (j + 1 < 4) tmem_ld_32x16(t_d + (uint32_t)((j + 1) * 16), (j & 1) ? ra : rb);
-          if (j == 3) {  // D has been read: the next item's out-projection may overwrite it
+          if (j == 3) {  // D has been read: the next item's products may overwrite it
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(dv_free);
@@ -660,8 +637,8 @@ __global__ void __launch_bounds__(640, 1) biattn_image_kernel(const __grid_const
           float o[16];
 #pragma unroll
           for (int i4 = 0; i4 < 4; ++i4) {
-            const float4 sv = *reinterpret_cast<const float4*>(s_vec + part * 64 + j * 16 + i4 * 4);
-            const float4 tv = *reinterpret_cast<const float4*>(t_vec + part * 64 + j * 16 + i4 * 4);
+            const float4 sv = lds128f(sv_addr + (uint32_t)((j * 16 + i4 * 4) * 4));
+            const float4 tv = lds128f(tv_addr + (uint32_t)((j * 16 + i4 * 4) * 4));
             o[i4 * 4 + 0] = fmaf(__uint_as_float(r[i4 * 4 + 0]), sv.x, tv.x);
             o[i4 * 4 + 1] = fmaf(__uint_as_float(r[i4 * 4 + 1]), sv.y, tv.y);
             o[i4 * 4 + 2] = fmaf(__uint_as_float(r[i4 * 4 + 2]), sv.z, tv.z);
@@ -786,28 +763,27 @@ extern "C" int64_t mqdet_biattn_image_workspace_floats(int64_t B, int64_t H, int
 }
 
 extern "C" int mqdet_biattn_image(const void* q, int64_t q_ld, int64_t q_b, const void* k, int64_t k_ld, int64_t k_b,
-                                  const void* vlT, int64_t vl_ld, int64_t vl_b, const void* w, int64_t w_ld, const float* bias,
+                                  const void* mT, int64_t m_ld, int64_t m_bh, int64_t m_b, const float* bias,
                                   const float* gamma, const void* res, int64_t res_ld, int64_t res_b, const float* mask,
                                   float clamp, void* out, int64_t o_ld, int64_t o_b, float* colmax, float* workspace, int64_t B,
                                   int64_t H, int64_t N, int64_t T, void* stream) {
-  MQ_REQUIRE(q && k && vlT && w && out && colmax && workspace, "biattn_image: null pointer");
+  MQ_REQUIRE(q && k && mT && out && colmax && workspace, "biattn_image: null pointer");
   MQ_REQUIRE(B >= 1 && H >= 1 && H <= 64 && N >= 1 && T >= 8 && T <= 256 && (T % 8) == 0,
              "biattn_image: need B, H, N >= 1, 8 <= T <= 256, T %% 8 == 0 (got B=%ld H=%ld N=%ld T=%ld)", (long)B, (long)H, (long)N, (long)T);
-  const int64_t lds[] = {q_ld, q_b, k_ld, k_b, vl_ld, vl_b, w_ld, o_ld, o_b, res ? res_ld : 0, res ? res_b : 0};
+  const int64_t lds[] = {q_ld, q_b, k_ld, k_b, m_ld, m_bh, m_b, o_ld, o_b, res ? res_ld : 0, res ? res_b : 0};
   for (int64_t x : lds) MQ_REQUIRE((x % 8) == 0, "biattn_image: strides must be multiples of 8 elements");
-  MQ_REQUIRE(((uintptr_t)q % 16) == 0 && ((uintptr_t)k % 16) == 0 && ((uintptr_t)vlT % 16) == 0 && ((uintptr_t)w % 16) == 0 &&
+  MQ_REQUIRE(((uintptr_t)q % 16) == 0 && ((uintptr_t)k % 16) == 0 && ((uintptr_t)mT % 16) == 0 &&
                  ((uintptr_t)out % 16) == 0 && ((uintptr_t)res % 16) == 0,
              "biattn_image: operands must be 16-byte aligned");
   const long E = H * 256;
-  CUtensorMap mq, mk, mvl, mw, mo;
+  CUtensorMap mq, mk, mm, mo;
   int bc1, bc2;
   int rc = make_operand_map(&mq, q, N, E, q_ld, (int)B, q_b, 1, 0, BM, &bc1, &bc2);
   if (rc) return rc;
   rc = make_operand_map(&mk, k, T, E, k_ld, (int)B, k_b, 1, 0, 256, &bc1, &bc2);
   if (rc) return rc;
-  rc = make_operand_map(&mvl, vlT, E, T, vl_ld, (int)B, vl_b, 1, 0, 256, &bc1, &bc2);
-  if (rc) return rc;
-  rc = make_operand_map(&mw, w, 256, E, w_ld, 1, 0, 1, 0, 256, &bc1, &bc2);
+  MQ_REQUIRE((H == 1 || m_bh != 0) && (B == 1 || m_b != 0), "biattn_image: mT head / image strides must be non-zero");
+  rc = make_operand_map(&mm, mT, 256, T, m_ld, (int)H, m_bh, (int)B, m_b, 256, &bc1, &bc2);  // [B][H][256 o][T]
   if (rc) return rc;
   MQ_REQUIRE(B == 1 || o_b != 0, "biattn_image: output batch stride must be non-zero");
   rc = make_store_map(&mo, out, MQDET_F16, N, 256, o_ld, (int)B, o_b, 1, 0);
@@ -828,7 +804,7 @@ extern "C" int mqdet_biattn_image(const void* q, int64_t q_ld, int64_t q_b, cons
   rc = ensure_dyn_smem(reinterpret_cast<const void*>(&biattn_image_kernel), BiCfg::SMEM_BYTES);
   if (rc) return rc;
   const int grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
-  biattn_image_kernel<<<grid, 640, BiCfg::SMEM_BYTES, (cudaStream_t)stream>>>(mq, mk, mvl, mw, mo, p);
+  biattn_image_kernel<<<grid, 640, BiCfg::SMEM_BYTES, (cudaStream_t)stream>>>(mq, mk, mm, mo, p);
   rc = check_launch("biattn_image_kernel");
   if (rc) return rc;
   colmax_reduce_kernel<<<(unsigned)(B * H), 256, 0, (cudaStream_t)stream>>>(workspace, p.tiles_per_img, (int)T, colmax);

@@ -244,22 +244,24 @@ def biattn_text(kh, qh, vvT4, stat, clamp, out):
     return out
 
 
-def biattn_image(q, k, vlT, w_out16, bias, gamma, residual, mask, clamp, heads):
+def biattn_image(q, k, mT, bias, gamma, residual, mask, clamp, heads):
     """Fused image -> text side + out-projection + layer scale + residual (mqdet_biattn_image).
-    q [B,N,E] fp16 (scaled), k [B,T,E], vlT [B,E,T], w_out16 [256,E] fp16; bias/gamma [256] fp32 or None; residual [B,N,256]
-    fp16 or None; mask [B,T] fp32 or None -> (out [B,N,256] fp16, colmax [B*H,T] fp32)."""
+    q [B,N,E] fp16 (scaled), k [B,T,E], mT [B,H,256,T] fp16 (= W_out,h . V_l,h^T per head); bias/gamma [256] fp32 or None;
+    residual [B,N,256] fp16 or None; mask [B,T] fp32 or None -> (out [B,N,256] fp16, colmax [B*H,T] fp32)."""
     global launch_count
-    _need_cuda(q, k, vlT, w_out16, bias, gamma, residual, mask)
+    _need_cuda(q, k, mT, bias, gamma, residual, mask)
     B, N, E = q.shape
     T = k.shape[1]
-    for t in (q, k, vlT, w_out16):
+    for t in (q, k, mT):
         if t.dtype != torch.float16 or t.stride(-1) != 1:
             raise _lib.MqdetError("biattn_image: fp16 operands with a contiguous last dimension required")
+    if tuple(mT.shape) != (B, heads, 256, T):
+        raise _lib.MqdetError(f"biattn_image: mT must be [B, H, 256, T], got {tuple(mT.shape)}")
     out = torch.empty((B, N, 256), dtype=torch.float16, device=q.device)
     colmax = torch.empty((B * heads, T), dtype=torch.float32, device=q.device)
     ws = torch.empty((int(load().mqdet_biattn_image_workspace_floats(B, heads, N, T)),), dtype=torch.float32, device=q.device)
-    check(load().mqdet_biattn_image(_ptr(q), q.stride(1), q.stride(0), _ptr(k), k.stride(1), k.stride(0), _ptr(vlT), vlT.stride(1),
-                                    vlT.stride(0), _ptr(w_out16), w_out16.stride(0), _ptr(bias), _ptr(gamma), _ptr(residual),
+    check(load().mqdet_biattn_image(_ptr(q), q.stride(1), q.stride(0), _ptr(k), k.stride(1), k.stride(0), _ptr(mT), mT.stride(2),
+                                    mT.stride(1), mT.stride(0), _ptr(bias), _ptr(gamma), _ptr(residual),
                                     residual.stride(1) if residual is not None else 0,
                                     residual.stride(0) if residual is not None else 0, _ptr(mask), float(clamp), _ptr(out),
                                     out.stride(1), out.stride(0), _ptr(colmax), _ptr(ws), B, heads, N, T, _stream()),

@@ -130,8 +130,8 @@ class BiMultiHeadAttention(nn.Module):
 
     def _attend_fused(self, vn16, ln16, q, k, mask_l, clamp, v_epilogue, l_epilogue):
         """Product path: the score matrix never reaches HBM and stays fp32 until both softmaxes have been taken.
-          image side: ONE kernel = S (TMEM) -> masked row softmax -> P.V_l -> out-projection over the heads -> layer scale +
-                      residual; it also emits the column maxima of the scores;
+          image side: ONE kernel = S (TMEM) -> masked row softmax -> P.(V_l W_out^T) accumulated over the heads -> layer scale
+                      + residual; it also emits the column maxima of the scores;
           text side : ONE kernel = S^T recomputed -> exp(. - column max) -> P^T . vn (the image tokens themselves; the value
                       projection follows as a small per-head GEMM because sum_n p[n] = 1) with in-kernel column sums."""
         B, N, Cv = vn16.shape
@@ -140,10 +140,14 @@ class BiMultiHeadAttention(nn.Module):
         dev = vn16.device
         ve = v_epilogue or {}
         le = l_epilogue or {}
-        vlT = ops.gemm(w16(self.values_l_proj.weight), ln16, bias=f32(self.values_l_proj.bias), bias_mode=VEC_PER_ROW)
+        # value and output projection of the image side folded per (image, head): mT[b,h,o,t] = sum_d Wout[o,h*d+dd] Vl[b,t,h*d+dd]
+        # ((P Vl_h) Wout_h^T == P (Vl_h Wout_h^T): the per-head context never exists, a head costs two products instead of three)
+        vl = ops.gemm(ln16.view(B * T, -1), w16(self.values_l_proj.weight), bias=f32(self.values_l_proj.bias)).view(B, T, H, d)
+        mT = torch.empty((B, H, Cv, T), dtype=torch.float16, device=dev)
+        ops.gemm(w16(self.out_v_proj.weight).view(1, Cv, H, d).permute(0, 2, 1, 3), vl.permute(0, 2, 1, 3), out=mT)
         cm = mask_l.float().contiguous() if mask_l is not None else None
-        dv, colmax = ops.biattn_image(q.view(B, N, E), k.view(B, T, E), vlT, w16(self.out_v_proj.weight),
-                                      f32(self.out_v_proj.bias), ve.get("gate"), ve.get("residual"), cm, clamp, H)
+        dv, colmax = ops.biattn_image(q.view(B, N, E), k.view(B, T, E), mT, f32(self.out_v_proj.bias), ve.get("gate"),
+                                      ve.get("residual"), cm, clamp, H)
         qh, kh = q.permute(0, 2, 1, 3), k.permute(0, 2, 1, 3)
         u = torch.empty((B, H, T, Cv), dtype=torch.float16, device=dev)
         ops.biattn_text_vn(kh, qh, vn16, colmax, clamp, u)

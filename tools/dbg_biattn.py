@@ -31,16 +31,18 @@ def main():
         mask = torch.ones(B, T)
         mask[0, T // 2:] = 0
         mask = mask.to(dev)
-        out, colmax = ops.biattn_image(q, k, vlT, w, bias, gamma, res, mask, 50000.0, H)
+        vl_h = vlT.float().view(B, H, 256, T)                                 # [B,H,d,T]
+        mT = torch.einsum("ohd,bhdt->bhot", w.float().view(256, H, 256), vl_h).half().contiguous()
+        out, colmax = ops.biattn_image(q, k, mT, bias, gamma, res, mask, 50000.0, H)
         torch.cuda.synchronize()
         qf, kf = q.float().view(B, N, H, 256).permute(0, 2, 1, 3), k.float().view(B, T, H, 256).permute(0, 2, 1, 3)
         S = (qf @ kf.transpose(-1, -2)).clamp(-5e4, 5e4)                     # [B,H,N,T]
         cm_ref = S.max(dim=2)[0].reshape(B * H, T)
         P = torch.softmax(S + torch.where(mask[:, None, None, :] == 0, -9e15, 1.0), dim=-1)
         vl = vlT.float().view(B, H, 256, T).transpose(-1, -2)                 # [B,H,T,256]
-        O = (P.half().float() @ vl)                                           # probabilities travel as fp16
-        O = O.permute(0, 2, 1, 3).reshape(B, N, E).half().float()
-        ref = res.float() + gamma * (O @ w.float().t() + bias)
+        # probabilities travel as fp16; the value and output projections are folded into mT (fp16)
+        D = torch.einsum("bhnt,bhot->bno", P.half().float(), mT.float())
+        ref = res.float() + gamma * (D + bias)
         print(f"B={B} N={N} T={T} H={H}: image out rel {rel(out, ref):.3e}  colmax abs {float((colmax - cm_ref).abs().max()):.3e}")
         u = torch.empty((B, H, T, 256), dtype=torch.float16, device=dev)
         ops.biattn_text_vn(k.view(B, T, H, 256).permute(0, 2, 1, 3), q.view(B, N, H, 256).permute(0, 2, 1, 3), vn, colmax, 50000.0, u)
