@@ -159,32 +159,38 @@ int mqdet_biattn_text(const void* k, int64_t k_ld, int64_t k_b1, int64_t k_b2, c
                       int64_t Np, int64_t d, void* stream);
 
 /* Same kernel, VN variant: the value operand is the layer-normed image-token tensor itself, vn [z][N][256] f16 (read MN-major
- * from the same [token x channel] tile), so that out[z][t][:] = sum_n softmax_n(clamp(k_t . q_n))[n] * vn[n][:] — the value
- * projection W_vv is applied AFTER the token reduction by the caller (sum_n p[n] = 1 moves the bias out as well), and the
+ * from the same [token x channel] tile), so that out[z][t][:] = sum_n softmax_n(clamp(k_t . q_n + rowbias_t))[n] * vn[n][:] — the
+ * value projection W_vv is applied AFTER the token reduction by the caller (sum_n p[n] = 1 moves the bias out as well), and the
  * [B, E, N] value tensor is never built.  colmax [z][T] f32 = column maxima of the clamped fp32 scores (mqdet_biattn_image);
- * the column sums are accumulated in-kernel from the fp32 scores (no fp16 re-quantisation). */
+ * the column sums are accumulated in-kernel from the fp32 scores (no fp16 re-quantisation).  rowbias [z][T * rb_ld] f32 or NULL:
+ * an additive score term per text token.  With k := gT (the query projection folded into the keys, see mqdet_biattn_image),
+ * q := vn (head stride 0) and rowbias := gbias, the kernel streams only the image tokens: q [B,N,E] is never built. */
 int mqdet_biattn_text_vn(const void* k, int64_t k_ld, int64_t k_b1, int64_t k_b2, const void* q, int64_t q_ld, int64_t q_b1,
                          int64_t q_b2, const void* vn, int64_t vn_ld, int64_t vn_b1, int64_t vn_b2, const float* colmax,
-                         float clamp, void* out, int64_t o_ld, int64_t o_b1, int64_t o_b2, int64_t nb1, int64_t nb2, int64_t T,
-                         int64_t N, void* stream);
+                         const float* rowbias, int64_t rb_ld, float clamp, void* out, int64_t o_ld, int64_t o_b1, int64_t o_b2,
+                         int64_t nb1, int64_t nb2, int64_t T, int64_t N, void* stream);
 
-/* Image -> text side of BiMultiHeadAttention fused with the out-projection, layer scale and residual
+/* Image -> text side of BiMultiHeadAttention fused with the query, value and output projections, layer scale and residual
  * (maskrcnn_benchmark/utils/fuse_helper.py:240-256,277-302,420-425) in ONE persistent tcgen05 kernel: per 128 image tokens and
- * head, S = q k^T stays in TMEM (fp32) -> clamp -> masked softmax over the T tokens in registers -> P (fp16, shared memory) ->
- * acc += P mT_h^T in a second TMEM accumulator summed over the heads -> out = res + gamma * (acc + bias).  Neither the score
- * matrix nor a per-head context reaches HBM.  mask [B][T] f32 (0 = padding token: probability exactly 0, like the reference's
- * -9e15; an all-masked image gets the uniform distribution the reference's fp32 sum produces) or NULL; gamma / res may be NULL.
- *   q [B][N][H*256] (already scaled), k [B][T][H*256] f16; *_ld row strides, *_b image strides (elements, multiples of 8);
- *   mT [B][H][256][T] f16 with mT[b][h][o][t] = sum_d W_out[o][h*256+d] * V_l[b][t][h*256+d]: the value and output projections
- *   of head h folded into one operand ((P V_l,h) W_h^T == P (V_l,h W_h^T); m_ld row stride, m_bh head stride, m_b image stride);
- *   out [B][N][256] f16.  8 <= T <= 256, T % 8 == 0, head dim 256.
+ * head, S = vn gT_h^T + gbias_h stays in TMEM (fp32) -> clamp -> masked softmax over the T tokens in registers -> P (fp16,
+ * shared memory) -> acc += P mT_h^T in a second TMEM accumulator summed over the heads -> out = res + gamma * (acc + bias).
+ * Neither q, the score matrix nor a per-head context reaches HBM.  mask [B][T] f32 (0 = padding token: probability exactly 0,
+ * like the reference's -9e15; an all-masked image gets the uniform distribution the reference's fp32 sum produces) or NULL;
+ * gamma / bias [256] f32 (16-byte aligned) and res may be NULL.
+ *   vn [B][N][256] f16 = the layer-normed image tokens; *_ld row strides, *_b image strides, *_bh head strides (elements, x8);
+ *   gT [B][H][T][256] f16 with gT[b][h][t][c] = d^-1/2 sum_dd Wq[h*256+dd][c] K[b][t][h*256+dd]: the query projection of head h
+ *   folded into the key operand (S = (vn Wq_h^T + bq_h) d^-1/2 K_h^T = vn gT_h^T + gbias_h); gbias [B*H][T * gb_ld] f32 =
+ *   d^-1/2 bq_h . K_h[t] (NULL: none);
+ *   mT [B][H][256][T] f16 with mT[b][h][o][t] = sum_dd W_out[o][h*256+dd] V_l[b][t][h*256+dd]: the value and output projections
+ *   folded ((P V_l,h) W_h^T == P (V_l,h W_h^T));  out [B][N][256] f16.  8 <= T <= 256, T % 8 == 0, head dim 256, H <= 8.
  * colmax [B*H][T] f32 receives max_n clamp(S[n][t]) — the softmax shift of the text -> image side (mqdet_biattn_text_vn).
  * workspace: mqdet_biattn_image_workspace_floats(B, H, N, T) floats. */
 int64_t mqdet_biattn_image_workspace_floats(int64_t B, int64_t H, int64_t N, int64_t T);
-int mqdet_biattn_image(const void* q, int64_t q_ld, int64_t q_b, const void* k, int64_t k_ld, int64_t k_b, const void* mT,
-                       int64_t m_ld, int64_t m_bh, int64_t m_b, const float* bias, const float* gamma, const void* res,
-                       int64_t res_ld, int64_t res_b, const float* mask, float clamp, void* out, int64_t o_ld, int64_t o_b,
-                       float* colmax, float* workspace, int64_t B, int64_t H, int64_t N, int64_t T, void* stream);
+int mqdet_biattn_image(const void* vn, int64_t vn_ld, int64_t vn_b, const void* gT, int64_t g_ld, int64_t g_bh, int64_t g_b,
+                       const float* gbias, int64_t gb_ld, const void* mT, int64_t m_ld, int64_t m_bh, int64_t m_b,
+                       const float* bias, const float* gamma, const void* res, int64_t res_ld, int64_t res_b, const float* mask,
+                       float clamp, void* out, int64_t o_ld, int64_t o_b, float* colmax, float* workspace, int64_t B, int64_t H,
+                       int64_t N, int64_t T, void* stream);
 
 /* Text side of the dot-product token head (vldyhead.py:810,818): e = x / max(||x||, eps) written as fp16 and/or
  * fp32, dot[r] = e[r,:] . w + b0[0] (w, b0, dot optional). */

@@ -61,12 +61,12 @@ SIGNATURES = {
                                   c_int64, c_int64, c_void_p, c_float, c_void_p, c_int64, c_int64, c_int64, c_int64, c_int64,
                                   c_int64, c_int64, c_int64, c_int64, c_void_p]),
     "mqdet_biattn_text_vn": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_int64, c_int64, c_int64, c_void_p, c_int64,
-                                     c_int64, c_int64, c_void_p, c_float, c_void_p, c_int64, c_int64, c_int64, c_int64, c_int64,
-                                     c_int64, c_int64, c_void_p]),
+                                     c_int64, c_int64, c_void_p, c_void_p, c_int64, c_float, c_void_p, c_int64, c_int64, c_int64,
+                                     c_int64, c_int64, c_int64, c_int64, c_void_p]),
     "mqdet_biattn_image_workspace_floats": (c_int64, [c_int64, c_int64, c_int64, c_int64]),
-    "mqdet_biattn_image": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_int64, c_int64, c_void_p, c_int64, c_int64, c_int64,
-                                   c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_float, c_void_p, c_int64, c_int64,
-                                   c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64, c_void_p]),
+    "mqdet_biattn_image": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_int64, c_int64, c_int64, c_void_p, c_int64, c_void_p,
+                                   c_int64, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_float,
+                                   c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64, c_void_p]),
     "mqdet_l2norm_rowdot": (c_int, [c_void_p, c_int64, c_int64, c_float, c_void_p, c_void_p, c_void_p, c_void_p,
                                     c_void_p, c_void_p]),
     "mqdet_cast_f32_f16": (c_int, [c_void_p, c_void_p, c_int64, c_void_p]),

@@ -51,6 +51,8 @@ struct BtP {
   int nb1, T, N, n_steps;
   int k_bc1, k_bc2, q_bc1, q_bc2, v_bc1, v_bc2;  // 1 -> batch coordinate pinned to 0
   uint32_t vn_lbo, vn_sbo;                        // VN: MN-major descriptor strides of the image-token tile
+  const float* rowbias;                           // VN: optional [Z][T * rb_ld] additive score bias per text token (folded q bias)
+  int rb_ld;
 };
 
 template <bool VN>
@@ -195,10 +197,11 @@ __global__ void __launch_bounds__(640, 1) biattn_text_kernel(const __grid_consta
     const int row = ew * 32 + lane;
     const int t = mt * BM + row;
     constexpr float L2E = 1.4426950408889634f;
-    float m_l2 = 0.f, inv = 0.f, lsum = 0.f;
+    float m_l2 = 0.f, inv = 0.f, lsum = 0.f, gb = 0.f;
     if (t < p.T) {
       if (VN) {
         m_l2 = -p.stat[(long)z * p.T + t] * L2E;
+        if (p.rowbias) gb = p.rowbias[((long)z * p.T + t) * p.rb_ld];
       } else {
         m_l2 = -p.stat[((long)z * 2) * p.T + t] * L2E;
         inv = p.stat[((long)z * 2 + 1) * p.T + t];
@@ -227,8 +230,8 @@ __global__ void __launch_bounds__(640, 1) biattn_text_kernel(const __grid_consta
         uint32_t h[8];
 #pragma unroll
         for (int q2 = 0; q2 < 8; ++q2) {
-          const float a = fminf(fmaxf(__uint_as_float(r[j][2 * q2]), -clampv), clampv);
-          const float b = fminf(fmaxf(__uint_as_float(r[j][2 * q2 + 1]), -clampv), clampv);
+          const float a = fminf(fmaxf(__uint_as_float(r[j][2 * q2]) + gb, -clampv), clampv);
+          const float b = fminf(fmaxf(__uint_as_float(r[j][2 * q2 + 1]) + gb, -clampv), clampv);
           // !VN: the score as the fp16 matrix A holds it (the statistics were taken from those values);
           //  VN: the fp32 score itself (the column maxima come from the fp32 scores of the image-side kernel)
           const float2 f = VN ? make_float2(a, b) : __half22float2(__floats2half2_rn(a, b));
@@ -293,13 +296,16 @@ __global__ void __launch_bounds__(640, 1) biattn_text_kernel(const __grid_consta
 
 // =====================================================================================================================
 // Image -> text side, fused with the out-projection, layer scale and residual.
-//   q  [B][N][H*256] fp16 (already scaled by d^-1/2)      k  [B][T][H*256] fp16
+//   vn [B][N][256] fp16 = the layer-normed image tokens
+//   gT [B][H][T][256 c] fp16 = K_h (d^-1/2 Wv_h): the query projection of head h folded into the key operand —
+//                              S = (vn Wv_h^T + bv) d^-1/2 K_h^T == vn gT_h^T + gbias_h[t] — so q is never built and ONE image-token
+//                              tile serves all heads;  gbias [B*H][T] fp32 = d^-1/2 bv_h . K_h[t]
 //   mT [B][H][256 o][T] fp16 = (W_h V_l,h^T): the value AND output projections of head h folded into one [T x 256] operand per
 //                              (image, head) by a tiny GEMM — (P V_l,h) W_h^T == P (V_l,h W_h^T), so the per-head context O never
 //                              exists and a head costs two tensor-core products instead of three
 //   out[B][N][256] fp16
 // Persistent: one CTA per SM walks (image, 128-token tile) items; per item the eight heads run back to back:
-//   S (128 x 256 t)   = Q_h . K_h^T          16 MMAs 128x256x16, Q_h and K_h streamed as [.. x 64] k-blocks through a 3-stage ring
+//   S (128 x 256 t)   = vn . gT_h^T (+ gbias_h)   16 MMAs 128x256x16, the operands streamed as [.. x 64] k-blocks through a 3-stage ring
 //   P                 = softmax_t(clamp(S) + mask): thread == image token == TMEM lane, 4 warps per lane quarter, 64 tokens each;
 //                       pass 1 over the TMEM columns = column maxima (for the text side) + partial row maxima, pass 2 = exp into
 //                       registers + partial row sums; both statistics are exchanged through shared memory; P = e / rowsum -> fp16
@@ -320,7 +326,8 @@ struct BiCfg {
   static constexpr int A_BYTES = BM * BK * 2;                // 16 KB
   static constexpr int B_BYTES = 256 * BK * 2;               // 32 KB
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;      // 48 KB
-  static constexpr int EXTRA_BYTES = (4 * BM * 2 + 4 * 256 + 256 + 512) * 4;  // rx | rsum, cmx, kl, s_vec | t_vec
+  static constexpr int MAX_HEADS = 8;
+  static constexpr int EXTRA_BYTES = (4 * BM * 2 + 4 * 256 + MAX_HEADS * 256) * 4;  // rx | rsum, cmx, gk
   static constexpr int SMEM_BYTES = PX_BYTES + BI_STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + EXTRA_BYTES;
 };
 static_assert(BiCfg::SMEM_BYTES <= 232448, "biattn_image: dynamic shared memory above the 227 KB per-CTA limit");
@@ -331,6 +338,8 @@ struct BiP {
   const __half* res;   // residual [B][N][256] (row stride res_ld, batch stride res_b) or nullptr
   long res_ld, res_b;
   float* colmax_part;  // [B][H][tiles_per_img][T]
+  const float* gbias;  // [B*H][T * gb_ld] additive score bias per (head, token): the folded query-projection bias, or nullptr
+  int gb_ld;
   float clamp;
   int B, H, T, N, tiles_per_img, total_tiles;
 };
@@ -361,9 +370,8 @@ __global__ void __launch_bounds__(640, 1) biattn_image_kernel(const __grid_const
   float* rx = reinterpret_cast<float*>(bars + 32);  // [4 parts][128 rows] partial row maxima
   float* rsum = rx + 4 * BM;                         // [4 parts][128 rows] partial row sums
   float* cmx = rsum + 4 * BM;                        // [4 lane quarters][256 tokens] column maxima
-  float* kl = cmx + 4 * 256;                         // [256] additive token mask of the row softmax: 0 keep / -inf masked
-  float* s_vec = kl + 256;                           // [256] gamma
-  float* t_vec = s_vec + 256;                        // [256] gamma * bias
+  float* gk = cmx + 4 * 256;                         // [H][256] additive row-softmax term per (head, token): folded query bias
+                                                     // + token mask (0 keep / -inf masked)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int H = p.H;
@@ -402,10 +410,10 @@ __global__ void __launch_bounds__(640, 1) biattn_image_kernel(const __grid_const
             const int s = it % BI_STAGES;
             mbar_wait(&empty_bar[s], ((it / BI_STAGES) & 1) ^ 1);
             uint8_t* st = ring + s * BiCfg::STAGE_BYTES;
-            if (ph == 0) {  // S: A = Q_h k-block, B = K_h k-block
+            if (ph == 0) {  // S: A = image-token k-block (the same for every head: L2 hit), B = gT_h k-block
               mbar_expect_tx(&full_bar[s], BiCfg::STAGE_BYTES);
-              tma_load_4d(st, &tma_q, &full_bar[s], h * 256 + kb * BK, m0, b, 0);
-              tma_load_4d(st + BiCfg::A_BYTES, &tma_k, &full_bar[s], h * 256 + kb * BK, 0, b, 0);
+              tma_load_4d(st, &tma_q, &full_bar[s], kb * BK, m0, b, 0);
+              tma_load_4d(st + BiCfg::A_BYTES, &tma_k, &full_bar[s], kb * BK, 0, h, b);
             } else {  // D: B = mT_h [256 o x 64 t]
               mbar_expect_tx(&full_bar[s], BiCfg::B_BYTES);
               tma_load_4d(st + BiCfg::A_BYTES, &tma_m, &full_bar[s], kb * BK, 0, h, b);
@@ -470,16 +478,11 @@ __global__ void __launch_bounds__(640, 1) biattn_image_kernel(const __grid_const
     const int sw = row & 7;
     const uint32_t lane_addr = (uint32_t)(ew * 32) << 16;
     const uint32_t px_row = smem_u32(px) + part * BiCfg::A_BYTES + row * 128;  // this thread's 128-byte row of k-block `part`
-    const uint32_t kl_addr = smem_u32(kl) + part * 64 * 4, rx_addr = smem_u32(rx) + row * 4, rsum_addr = smem_u32(rsum) + row * 4;
+    const uint32_t gk_addr0 = smem_u32(gk) + part * 64 * 4, rx_addr = smem_u32(rx) + row * 4, rsum_addr = smem_u32(rsum) + row * 4;
     constexpr float L2E = 1.4426950408889634f;
     const float NEG_INF = __int_as_float(0xff800000);
     const float clampv = p.clamp > 0.f ? p.clamp : 3.0e38f;
     const bool issuer = (tid_e == 0);
-    if (tid_e < 256) {
-      const float g = p.gamma ? p.gamma[tid_e] : 1.f;
-      s_vec[tid_e] = g;
-      t_vec[tid_e] = g * (p.bias ? p.bias[tid_e] : 0.f);
-    }
     int hc = 0, tcnt = 0, cur_b = -1;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++tcnt) {
       const int b = tile / p.tiles_per_img, ti = tile - b * p.tiles_per_img, m0 = ti * BM;
@@ -487,7 +490,11 @@ __global__ void __launch_bounds__(640, 1) biattn_image_kernel(const __grid_const
       const bool full_tile = m0 + BM <= p.N;
       if (b != cur_b) {  // token mask of this image (warp-uniform branch: every thread walks the same items)
         asm volatile("bar.sync 1, 512;" ::: "memory");  // nobody still reads the previous image's flags
-        if (tid_e < 256) kl[tid_e] = (tid_e < p.T && (!p.mask || p.mask[(long)b * p.T + tid_e] != 0.f)) ? 0.f : NEG_INF;
+        if (tid_e < 256) {
+          const bool kept = tid_e < p.T && (!p.mask || p.mask[(long)b * p.T + tid_e] != 0.f);
+          for (int hh = 0; hh < H; ++hh)
+            gk[hh * 256 + tid_e] = !kept ? NEG_INF : (p.gbias ? p.gbias[(((long)b * H + hh) * p.T + tid_e) * p.gb_ld] : 0.f);
+        }
         asm volatile("bar.sync 1, 512;" ::: "memory");
         cur_b = b;
       }
@@ -496,6 +503,7 @@ __global__ void __launch_bounds__(640, 1) biattn_image_kernel(const __grid_const
         mbar_wait(s_full, hc & 1);
         tc_fence_after();
         const uint32_t t_s = tmem_s + lane_addr + (uint32_t)(part * 64);
+        const uint32_t kl_addr = gk_addr0 + (uint32_t)(h * 256 * 4);  // this head's additive term (query bias + token mask)
         // ---- pass 1 over this thread's 64 tokens: column maxima (for the text side) and the partial row maximum ----
         // The +-5e4 clamp of the scores (fuse_helper.py:245-252) is applied to the REDUCED values (clamp is monotonic:
         // max(clamp(s)) == clamp(max(s))), not per element; `kl` carries the token mask as an additive 0 / -inf.
@@ -539,6 +547,7 @@ __global__ void __launch_bounds__(640, 1) biattn_image_kernel(const __grid_const
         asm volatile("bar.sync 1, 512;" ::: "memory");
         if (tid_e < p.T) {  // column-max partial of this (image, head, tile), clamped like the scores
           float c4 = fmaxf(fmaxf(cmx[tid_e], cmx[256 + tid_e]), fmaxf(cmx[512 + tid_e], cmx[768 + tid_e]));
+          if (p.gbias) c4 += p.gbias[(((long)b * H + h) * p.T + tid_e) * p.gb_ld];  // the text side sees the full score, no mask
           c4 = fminf(fmaxf(c4, -clampv), clampv);
           p.colmax_part[(((long)b * H + h) * p.tiles_per_img + ti) * p.T + tid_e] = c4;
         }
@@ -566,15 +575,16 @@ __global__ void __launch_bounds__(640, 1) biattn_image_kernel(const __grid_const
               __syncwarp();
               if (lane == 0) mbar_arrive(scratch_free);
             }
-            if (!need_clamp && !uniform) {  // the common path: 4 issue slots per score (FFMA, FADD, MUFU.EX2, FADD)
+            if (!need_clamp && !uniform) {  // the common path: 4 issue slots per score (FADD, FFMA, MUFU.EX2, FADD)
 #pragma unroll
               for (int i4 = 0; i4 < 4; ++i4) {
                 const float4 kf = lds128f(kl_addr + (uint32_t)((j * 16 + i4 * 4) * 4));
                 const float kk[4] = {kf.x, kf.y, kf.z, kf.w};
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
-                  // masked tokens: kl = -inf -> exp2(-inf) = 0, exactly what the reference's -9e15 does in fp32
-                  const float ev = ex2_approx(fmaf(__uint_as_float(r[i4 * 4 + i]), L2E, kk[i]) - ml2);
+                  // kk = folded query bias of this (head, token), or -inf on a masked token: exp2(-inf) = 0, exactly what the
+                  // reference's -9e15 does in fp32
+                  const float ev = ex2_approx(fmaf(__uint_as_float(r[i4 * 4 + i]) + kk[i], L2E, -ml2));
                   e[j * 16 + i4 * 4 + i] = ev;
                   lpart += ev;
                 }
@@ -587,8 +597,8 @@ __global__ void __launch_bounds__(640, 1) biattn_image_kernel(const __grid_const
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                   const int c = j * 16 + i4 * 4 + i;
-                  const float sc = fminf(fmaxf(__uint_as_float(r[i4 * 4 + i]), -clampv), clampv);
-                  float ev = ex2_approx(fmaf(sc, L2E, kk[i]) - ml2);
+                  const float sc = fminf(fmaxf(__uint_as_float(r[i4 * 4 + i]) + kk[i], -clampv), clampv);
+                  float ev = (kk[i] == NEG_INF) ? 0.f : ex2_approx(fmaf(sc, L2E, -ml2));
                   if (uniform) ev = (part * 64 + c < p.T) ? 1.f : 0.f;
                   e[c] = ev;
                   lpart += ev;
@@ -616,7 +626,8 @@ __global__ void __launch_bounds__(640, 1) biattn_image_kernel(const __grid_const
         const bool has_res = p.res != nullptr && valid_row;
         const uint4* src = reinterpret_cast<const uint4*>(p.res + (long)b * p.res_b + (long)(m0 + row) * p.res_ld + part * 64);
         const uint32_t t_d = tmem_d + lane_addr + (uint32_t)(part * 64);
-        const uint32_t sv_addr = smem_u32(s_vec) + part * 64 * 4, tv_addr = smem_u32(t_vec) + part * 64 * 4;
+        const float4* gam4 = reinterpret_cast<const float4*>(p.gamma) + part * 16;
+        const float4* bia4 = reinterpret_cast<const float4*>(p.bias) + part * 16;
         uint32_t ra[16], rb[16];
         tmem_ld_32x16(t_d, ra);
 #pragma unroll
@@ -637,12 +648,12 @@ __global__ void __launch_bounds__(640, 1) biattn_image_kernel(const __grid_const
           float o[16];
 #pragma unroll
           for (int i4 = 0; i4 < 4; ++i4) {
-            const float4 sv = lds128f(sv_addr + (uint32_t)((j * 16 + i4 * 4) * 4));
-            const float4 tv = lds128f(tv_addr + (uint32_t)((j * 16 + i4 * 4) * 4));
-            o[i4 * 4 + 0] = fmaf(__uint_as_float(r[i4 * 4 + 0]), sv.x, tv.x);
-            o[i4 * 4 + 1] = fmaf(__uint_as_float(r[i4 * 4 + 1]), sv.y, tv.y);
-            o[i4 * 4 + 2] = fmaf(__uint_as_float(r[i4 * 4 + 2]), sv.z, tv.z);
-            o[i4 * 4 + 3] = fmaf(__uint_as_float(r[i4 * 4 + 3]), sv.w, tv.w);
+            const float4 sv = p.gamma ? __ldg(gam4 + j * 4 + i4) : make_float4(1.f, 1.f, 1.f, 1.f);
+            const float4 bv = p.bias ? __ldg(bia4 + j * 4 + i4) : make_float4(0.f, 0.f, 0.f, 0.f);
+            o[i4 * 4 + 0] = (__uint_as_float(r[i4 * 4 + 0]) + bv.x) * sv.x;  // gamma * (D + bias)
+            o[i4 * 4 + 1] = (__uint_as_float(r[i4 * 4 + 1]) + bv.y) * sv.y;
+            o[i4 * 4 + 2] = (__uint_as_float(r[i4 * 4 + 2]) + bv.z) * sv.z;
+            o[i4 * 4 + 3] = (__uint_as_float(r[i4 * 4 + 3]) + bv.w) * sv.w;
           }
           const __half2* h0 = reinterpret_cast<const __half2*>(&rq0);
           const __half2* h1 = reinterpret_cast<const __half2*>(&rq1);
@@ -691,7 +702,7 @@ __global__ void colmax_reduce_kernel(const float* __restrict__ part, int tiles, 
 
 using namespace mqdet;
 
-static int text_launch(bool vn, const void* k, int64_t k_ld, int64_t k_b1, int64_t k_b2, const void* q, int64_t q_ld, int64_t q_b1,
+static int text_launch(bool vn, const float* rowbias, int64_t rb_ld, const void* k, int64_t k_ld, int64_t k_b1, int64_t k_b2, const void* q, int64_t q_ld, int64_t q_b1,
                        int64_t q_b2, const void* v, int64_t v_ld, int64_t v_b1, int64_t v_b2, const float* stat, float clamp,
                        void* out, int64_t o_ld, int64_t o_b1, int64_t o_b2, int64_t nb1, int64_t nb2, int64_t T, int64_t N,
                        int64_t Np, int64_t d, void* stream) {
@@ -724,6 +735,8 @@ static int text_launch(bool vn, const void* k, int64_t k_ld, int64_t k_b1, int64
   p.T = (int)T;
   p.N = (int)N;
   p.n_steps = (int)((N + BT_STEP - 1) / BT_STEP);
+  p.rowbias = rowbias;
+  p.rb_ld = (int)(rb_ld > 0 ? rb_ld : 1);
   p.vn_lbo = BT_SUB * 128;  // next 64 channels: the next [64 n x 64 c] block
   p.vn_sbo = 1024;          // next 8 image tokens
   if (const char* dbg = getenv("MQDET_VN_DESC_SWAP")) {  // bring-up aid: swap the two strides
@@ -746,15 +759,15 @@ extern "C" int mqdet_biattn_text(const void* k, int64_t k_ld, int64_t k_b1, int6
                                  int64_t q_b1, int64_t q_b2, const void* vvT, int64_t v_ld, int64_t v_b1, int64_t v_b2,
                                  const float* stat, float clamp, void* out, int64_t o_ld, int64_t o_b1, int64_t o_b2,
                                  int64_t nb1, int64_t nb2, int64_t T, int64_t N, int64_t Np, int64_t d, void* stream) {
-  return text_launch(false, k, k_ld, k_b1, k_b2, q, q_ld, q_b1, q_b2, vvT, v_ld, v_b1, v_b2, stat, clamp, out, o_ld, o_b1, o_b2,
+  return text_launch(false, nullptr, 0, k, k_ld, k_b1, k_b2, q, q_ld, q_b1, q_b2, vvT, v_ld, v_b1, v_b2, stat, clamp, out, o_ld, o_b1, o_b2,
                      nb1, nb2, T, N, Np, d, stream);
 }
 
 extern "C" int mqdet_biattn_text_vn(const void* k, int64_t k_ld, int64_t k_b1, int64_t k_b2, const void* q, int64_t q_ld,
                                     int64_t q_b1, int64_t q_b2, const void* vn, int64_t vn_ld, int64_t vn_b1, int64_t vn_b2,
-                                    const float* colmax, float clamp, void* out, int64_t o_ld, int64_t o_b1, int64_t o_b2,
-                                    int64_t nb1, int64_t nb2, int64_t T, int64_t N, void* stream) {
-  return text_launch(true, k, k_ld, k_b1, k_b2, q, q_ld, q_b1, q_b2, vn, vn_ld, vn_b1, vn_b2, colmax, clamp, out, o_ld, o_b1,
+                                    const float* colmax, const float* rowbias, int64_t rb_ld, float clamp, void* out, int64_t o_ld,
+                                    int64_t o_b1, int64_t o_b2, int64_t nb1, int64_t nb2, int64_t T, int64_t N, void* stream) {
+  return text_launch(true, rowbias, rb_ld, k, k_ld, k_b1, k_b2, q, q_ld, q_b1, q_b2, vn, vn_ld, vn_b1, vn_b2, colmax, clamp, out, o_ld, o_b1,
                      o_b2, nb1, nb2, T, N, (N + 7) / 8 * 8, 256, stream);
 }
 
@@ -762,27 +775,26 @@ extern "C" int64_t mqdet_biattn_image_workspace_floats(int64_t B, int64_t H, int
   return B * H * ((N + BM - 1) / BM) * T;
 }
 
-extern "C" int mqdet_biattn_image(const void* q, int64_t q_ld, int64_t q_b, const void* k, int64_t k_ld, int64_t k_b,
-                                  const void* mT, int64_t m_ld, int64_t m_bh, int64_t m_b, const float* bias,
-                                  const float* gamma, const void* res, int64_t res_ld, int64_t res_b, const float* mask,
-                                  float clamp, void* out, int64_t o_ld, int64_t o_b, float* colmax, float* workspace, int64_t B,
-                                  int64_t H, int64_t N, int64_t T, void* stream) {
-  MQ_REQUIRE(q && k && mT && out && colmax && workspace, "biattn_image: null pointer");
-  MQ_REQUIRE(B >= 1 && H >= 1 && H <= 64 && N >= 1 && T >= 8 && T <= 256 && (T % 8) == 0,
-             "biattn_image: need B, H, N >= 1, 8 <= T <= 256, T %% 8 == 0 (got B=%ld H=%ld N=%ld T=%ld)", (long)B, (long)H, (long)N, (long)T);
-  const int64_t lds[] = {q_ld, q_b, k_ld, k_b, m_ld, m_bh, m_b, o_ld, o_b, res ? res_ld : 0, res ? res_b : 0};
+extern "C" int mqdet_biattn_image(const void* vn, int64_t vn_ld, int64_t vn_b, const void* gT, int64_t g_ld, int64_t g_bh,
+                                  int64_t g_b, const float* gbias, int64_t gb_ld, const void* mT, int64_t m_ld, int64_t m_bh,
+                                  int64_t m_b, const float* bias, const float* gamma, const void* res, int64_t res_ld,
+                                  int64_t res_b, const float* mask, float clamp, void* out, int64_t o_ld, int64_t o_b,
+                                  float* colmax, float* workspace, int64_t B, int64_t H, int64_t N, int64_t T, void* stream) {
+  MQ_REQUIRE(vn && gT && mT && out && colmax && workspace, "biattn_image: null pointer");
+  MQ_REQUIRE(B >= 1 && H >= 1 && H <= BiCfg::MAX_HEADS && N >= 1 && T >= 8 && T <= 256 && (T % 8) == 0,
+             "biattn_image: need B, N >= 1, 1 <= H <= 8, 8 <= T <= 256, T %% 8 == 0 (got B=%ld H=%ld N=%ld T=%ld)", (long)B, (long)H, (long)N, (long)T);
+  const int64_t lds[] = {vn_ld, vn_b, g_ld, g_bh, g_b, m_ld, m_bh, m_b, o_ld, o_b, res ? res_ld : 0, res ? res_b : 0};
   for (int64_t x : lds) MQ_REQUIRE((x % 8) == 0, "biattn_image: strides must be multiples of 8 elements");
-  MQ_REQUIRE(((uintptr_t)q % 16) == 0 && ((uintptr_t)k % 16) == 0 && ((uintptr_t)mT % 16) == 0 &&
-                 ((uintptr_t)out % 16) == 0 && ((uintptr_t)res % 16) == 0,
+  MQ_REQUIRE(((uintptr_t)vn % 16) == 0 && ((uintptr_t)gT % 16) == 0 && ((uintptr_t)mT % 16) == 0 && ((uintptr_t)out % 16) == 0 &&
+                 ((uintptr_t)res % 16) == 0 && ((uintptr_t)bias % 16) == 0 && ((uintptr_t)gamma % 16) == 0,
              "biattn_image: operands must be 16-byte aligned");
-  const long E = H * 256;
   CUtensorMap mq, mk, mm, mo;
   int bc1, bc2;
-  int rc = make_operand_map(&mq, q, N, E, q_ld, (int)B, q_b, 1, 0, BM, &bc1, &bc2);
+  int rc = make_operand_map(&mq, vn, N, 256, vn_ld, (int)B, vn_b, 1, 0, BM, &bc1, &bc2);
   if (rc) return rc;
-  rc = make_operand_map(&mk, k, T, E, k_ld, (int)B, k_b, 1, 0, 256, &bc1, &bc2);
+  MQ_REQUIRE((H == 1 || (g_bh != 0 && m_bh != 0)) && (B == 1 || (g_b != 0 && m_b != 0)), "biattn_image: head / image strides must be non-zero");
+  rc = make_operand_map(&mk, gT, T, 256, g_ld, (int)H, g_bh, (int)B, g_b, 256, &bc1, &bc2);  // [B][H][T][256 c]
   if (rc) return rc;
-  MQ_REQUIRE((H == 1 || m_bh != 0) && (B == 1 || m_b != 0), "biattn_image: mT head / image strides must be non-zero");
   rc = make_operand_map(&mm, mT, 256, T, m_ld, (int)H, m_bh, (int)B, m_b, 256, &bc1, &bc2);  // [B][H][256 o][T]
   if (rc) return rc;
   MQ_REQUIRE(B == 1 || o_b != 0, "biattn_image: output batch stride must be non-zero");
@@ -797,6 +809,8 @@ extern "C" int mqdet_biattn_image(const void* q, int64_t q_ld, int64_t q_b, cons
   p.res_ld = res_ld;
   p.res_b = res_b;
   p.colmax_part = workspace;
+  p.gbias = gbias;
+  p.gb_ld = (int)(gb_ld > 0 ? gb_ld : 1);
   p.clamp = clamp;
   p.B = (int)B; p.H = (int)H; p.T = (int)T; p.N = (int)N;
   p.tiles_per_img = (int)((N + BM - 1) / BM);

@@ -244,24 +244,29 @@ def biattn_text(kh, qh, vvT4, stat, clamp, out):
     return out
 
 
-def biattn_image(q, k, mT, bias, gamma, residual, mask, clamp, heads):
-    """Fused image -> text side + out-projection + layer scale + residual (mqdet_biattn_image).
-    q [B,N,E] fp16 (scaled), k [B,T,E], mT [B,H,256,T] fp16 (= W_out,h . V_l,h^T per head); bias/gamma [256] fp32 or None;
-    residual [B,N,256] fp16 or None; mask [B,T] fp32 or None -> (out [B,N,256] fp16, colmax [B*H,T] fp32)."""
+def biattn_image(vn16, gT, gbias, mT, bias, gamma, residual, mask, clamp, heads):
+    """Fused image -> text side with the query / value / output projections folded into per-(image, head) operands, layer
+    scale and residual (mqdet_biattn_image).  vn16 [B,N,256] fp16 (layer-normed tokens), gT [B,H,T,256] fp16, gbias [B,H,T,ld]
+    fp32 (column 0 used) or None, mT [B,H,256,T] fp16; bias/gamma [256] fp32 or None; residual [B,N,256] fp16 or None; mask
+    [B,T] fp32 or None -> (out [B,N,256] fp16, colmax [B*H,T] fp32)."""
     global launch_count
-    _need_cuda(q, k, mT, bias, gamma, residual, mask)
-    B, N, E = q.shape
-    T = k.shape[1]
-    for t in (q, k, mT):
+    _need_cuda(vn16, gT, gbias, mT, bias, gamma, residual, mask)
+    B, N, C = vn16.shape
+    T = gT.shape[2]
+    for t in (vn16, gT, mT):
         if t.dtype != torch.float16 or t.stride(-1) != 1:
             raise _lib.MqdetError("biattn_image: fp16 operands with a contiguous last dimension required")
-    if tuple(mT.shape) != (B, heads, 256, T):
-        raise _lib.MqdetError(f"biattn_image: mT must be [B, H, 256, T], got {tuple(mT.shape)}")
-    out = torch.empty((B, N, 256), dtype=torch.float16, device=q.device)
-    colmax = torch.empty((B * heads, T), dtype=torch.float32, device=q.device)
-    ws = torch.empty((int(load().mqdet_biattn_image_workspace_floats(B, heads, N, T)),), dtype=torch.float32, device=q.device)
-    check(load().mqdet_biattn_image(_ptr(q), q.stride(1), q.stride(0), _ptr(k), k.stride(1), k.stride(0), _ptr(mT), mT.stride(2),
-                                    mT.stride(1), mT.stride(0), _ptr(bias), _ptr(gamma), _ptr(residual),
+    if C != 256 or tuple(gT.shape) != (B, heads, T, 256) or tuple(mT.shape) != (B, heads, 256, T):
+        raise _lib.MqdetError(f"biattn_image: need vn [B,N,256], gT [B,H,T,256], mT [B,H,256,T]; got {tuple(vn16.shape)}, "
+                              f"{tuple(gT.shape)}, {tuple(mT.shape)}")
+    if gbias is not None and (gbias.dtype != torch.float32 or not gbias.is_contiguous() or gbias.shape[:3] != (B, heads, T)):
+        raise _lib.MqdetError("biattn_image: gbias must be contiguous fp32 [B, H, T, ld]")
+    out = torch.empty((B, N, 256), dtype=torch.float16, device=vn16.device)
+    colmax = torch.empty((B * heads, T), dtype=torch.float32, device=vn16.device)
+    ws = torch.empty((int(load().mqdet_biattn_image_workspace_floats(B, heads, N, T)),), dtype=torch.float32, device=vn16.device)
+    check(load().mqdet_biattn_image(_ptr(vn16), vn16.stride(1), vn16.stride(0), _ptr(gT), gT.stride(2), gT.stride(1), gT.stride(0),
+                                    _ptr(gbias), gbias.shape[3] if gbias is not None else 0, _ptr(mT), mT.stride(2), mT.stride(1),
+                                    mT.stride(0), _ptr(bias), _ptr(gamma), _ptr(residual),
                                     residual.stride(1) if residual is not None else 0,
                                     residual.stride(0) if residual is not None else 0, _ptr(mask), float(clamp), _ptr(out),
                                     out.stride(1), out.stride(0), _ptr(colmax), _ptr(ws), B, heads, N, T, _stream()),
@@ -270,20 +275,21 @@ def biattn_image(q, k, mT, bias, gamma, residual, mask, clamp, heads):
     return out, colmax
 
 
-def biattn_text_vn(kh, qh, vn16, colmax, clamp, out):
-    """Fused text -> image attention on the image tokens themselves: kh [B,H,T,d], qh [B,H,N,d] (strided views), vn16 [B,N,256]
-    fp16, colmax [B*H,T] fp32 (from biattn_image), out [B,H,T,256] fp16 view <- softmax_n(scores)^T . vn."""
+def biattn_text_vn(kh, qh, vn16, colmax, clamp, out, rowbias=None):
+    """Fused text -> image attention on the image tokens themselves: kh [B,H,T,d], qh [B,H,N,d] (strided views; a head stride of
+    0 broadcasts), vn16 [B,N,256] fp16, colmax [B*H,T] fp32 (from biattn_image), rowbias [B,H,T,ld] fp32 (column 0) or None,
+    out [B,H,T,256] fp16 view <- softmax_n(scores + rowbias)^T . vn."""
     global launch_count
-    _need_cuda(kh, qh, vn16, colmax, out)
+    _need_cuda(kh, qh, vn16, colmax, out, rowbias)
     B, H, T, d = kh.shape
     N = qh.shape[2]
     for t in (kh, qh, vn16, out):
         if t.stride(-1) != 1 or t.dtype != torch.float16:
             raise _lib.MqdetError("biattn_text_vn: fp16 operands with a contiguous last dimension required")
     check(load().mqdet_biattn_text_vn(_ptr(kh), kh.stride(2), kh.stride(1), kh.stride(0), _ptr(qh), qh.stride(2), qh.stride(1),
-                                      qh.stride(0), _ptr(vn16), vn16.stride(1), 0, vn16.stride(0), _ptr(colmax), float(clamp),
-                                      _ptr(out), out.stride(2), out.stride(1), out.stride(0), H, B, T, N, _stream()),
-          "biattn_text_vn")
+                                      qh.stride(0), _ptr(vn16), vn16.stride(1), 0, vn16.stride(0), _ptr(colmax), _ptr(rowbias),
+                                      rowbias.shape[3] if rowbias is not None else 0, float(clamp), _ptr(out), out.stride(2),
+                                      out.stride(1), out.stride(0), H, B, T, N, _stream()), "biattn_text_vn")
     launch_count += 1
     return out
 

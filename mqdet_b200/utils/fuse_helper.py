@@ -84,11 +84,11 @@ class BiMultiHeadAttention(nn.Module):
         dev = vn16.device
         Np = (N + 7) // 8 * 8
         clamp = 50000.0 if (self.clamp_min_for_underflow or self.clamp_max_for_overflow) else 0.0
+        k = ops.gemm(ln16.view(B * T, -1), w16(self.l_proj.weight), bias=f32(self.l_proj.bias)).view(B, T, H, d)
+        if self.score_precision == "fused" and d == 256 and Cv == 256 and T % 8 == 0 and T <= 256 and H <= 8:
+            return self._attend_fused(vn16, ln16, k, mask_l, clamp, v_epilogue, l_epilogue)
         q = ops.gemm(vn16.view(B * N, Cv), w16(self.v_proj.weight), bias=f32(self.v_proj.bias), alpha=self.scale,
                      scale_after_bias=True).view(B, N, H, d)
-        k = ops.gemm(ln16.view(B * T, -1), w16(self.l_proj.weight), bias=f32(self.l_proj.bias)).view(B, T, H, d)
-        if self.score_precision == "fused" and d == 256 and Cv == 256 and T % 8 == 0 and T <= 256:
-            return self._attend_fused(vn16, ln16, q, k, mask_l, clamp, v_epilogue, l_epilogue)
         vvT = torch.zeros((B, E, Np), dtype=torch.float16, device=dev) if Np != N else \
             torch.empty((B, E, Np), dtype=torch.float16, device=dev)
         ops.gemm(w16(self.values_v_proj.weight), vn16, out=vvT[:, :, :N], bias=f32(self.values_v_proj.bias),
@@ -128,29 +128,50 @@ class BiMultiHeadAttention(nn.Module):
             ops.gemm(Pl, vvT.view(B, H, d, Np), out=ol.permute(0, 2, 1, 3))
         return self._finish(ov, ol, v_epilogue, l_epilogue, B, N, T, Cv)
 
-    def _attend_fused(self, vn16, ln16, q, k, mask_l, clamp, v_epilogue, l_epilogue):
-        """Product path: the score matrix never reaches HBM and stays fp32 until both softmaxes have been taken.
-          image side: ONE kernel = S (TMEM) -> masked row softmax -> P.(V_l W_out^T) accumulated over the heads -> layer scale
-                      + residual; it also emits the column maxima of the scores;
-          text side : ONE kernel = S^T recomputed -> exp(. - column max) -> P^T . vn (the image tokens themselves; the value
-                      projection follows as a small per-head GEMM because sum_n p[n] = 1) with in-kernel column sums."""
+    def _query_fold_weights(self):
+        """(scale * Wq)^T as fp16 [Cv, E] and scale * bq as fp16 [H, 8, d] (row 0 used), cached per parameter version: the B
+        operands that fold the query projection into the keys.  scale = d^-1/2 = 2^-4 for d = 256: exact in fp16."""
+        ps = (self.v_proj.weight, self.v_proj.bias)
+        key = tuple((p.data_ptr(), p._version) for p in ps)
+        if getattr(self, "_qfold", None) is None or self._qfold[0] != key:
+            H, d = self.num_heads, self.head_dim
+            wt = ops.cast_f16((self.v_proj.weight.detach().float() * self.scale).t().contiguous())        # [Cv, E]
+            bq = torch.zeros((H, 8, d), dtype=torch.float32, device=wt.device)
+            bq[:, 0] = (self.v_proj.bias.detach().float() * self.scale).view(H, d)
+            self._qfold = (key, wt, ops.cast_f16(bq))
+        return self._qfold[1], self._qfold[2]
+
+    def _attend_fused(self, vn16, ln16, k, mask_l, clamp, v_epilogue, l_epilogue):
+        """Product path: neither the queries q [B,N,E], the score matrix, its transpose, the per-head contexts nor the image-side
+        value tensor reach HBM, and the scores stay fp32 until both softmaxes have been taken.  Three per-(image, head)
+        operands of [256 x 256] fold the projections into the text side (tiny GEMMs over the T = 256 tokens):
+            gT_h = K_h (d^-1/2 Wq_h)            S = (vn Wq_h^T + bq_h) d^-1/2 K_h^T == vn gT_h^T + gbias_h,  gbias_h = d^-1/2 bq_h . K_h
+            mT_h = Wout_h Vl_h^T                (P Vl_h) Wout_h^T == P mT_h^T
+          image side: ONE kernel = S (TMEM) -> masked row softmax -> P . mT accumulated over the heads -> layer scale + residual;
+                      it also emits the column maxima of the scores;
+          text side : ONE kernel = S^T recomputed from gT and the image tokens -> exp(. - column max) -> P^T . vn (the image
+                      tokens themselves; the value projection follows as a small per-head GEMM because sum_n p[n] = 1) with
+                      in-kernel column sums."""
         B, N, Cv = vn16.shape
         T = ln16.shape[1]
         H, d, E = self.num_heads, self.head_dim, self.embed_dim
         dev = vn16.device
         ve = v_epilogue or {}
         le = l_epilogue or {}
-        # value and output projection of the image side folded per (image, head): mT[b,h,o,t] = sum_d Wout[o,h*d+dd] Vl[b,t,h*d+dd]
-        # ((P Vl_h) Wout_h^T == P (Vl_h Wout_h^T): the per-head context never exists, a head costs two products instead of three)
+        kh = k.permute(0, 2, 1, 3)                                                     # [B,H,T,d]
+        wqT, bq8 = self._query_fold_weights()
+        gT = torch.empty((B, H, T, Cv), dtype=torch.float16, device=dev)
+        ops.gemm(kh, wqT.view(1, Cv, H, d).permute(0, 2, 1, 3), out=gT)                # gT[b,h,t,c] = sum_dd K[b,t,h,dd] scale Wq[h*d+dd, c]
+        gbias = torch.empty((B, H, T, 8), dtype=torch.float32, device=dev)
+        ops.gemm(kh, bq8.view(1, H, 8, d), out=gbias)                                  # column 0 = scale bq_h . K_h[t]
         vl = ops.gemm(ln16.view(B * T, -1), w16(self.values_l_proj.weight), bias=f32(self.values_l_proj.bias)).view(B, T, H, d)
         mT = torch.empty((B, H, Cv, T), dtype=torch.float16, device=dev)
         ops.gemm(w16(self.out_v_proj.weight).view(1, Cv, H, d).permute(0, 2, 1, 3), vl.permute(0, 2, 1, 3), out=mT)
         cm = mask_l.float().contiguous() if mask_l is not None else None
-        dv, colmax = ops.biattn_image(q.view(B, N, E), k.view(B, T, E), mT, f32(self.out_v_proj.bias), ve.get("gate"),
-                                      ve.get("residual"), cm, clamp, H)
-        qh, kh = q.permute(0, 2, 1, 3), k.permute(0, 2, 1, 3)
+        dv, colmax = ops.biattn_image(vn16, gT, gbias, mT, f32(self.out_v_proj.bias), ve.get("gate"), ve.get("residual"), cm,
+                                      clamp, H)
         u = torch.empty((B, H, T, Cv), dtype=torch.float16, device=dev)
-        ops.biattn_text_vn(kh, qh, vn16, colmax, clamp, u)
+        ops.biattn_text_vn(gT, vn16.view(B, 1, N, Cv).expand(B, H, N, Cv), vn16, colmax, clamp, u, rowbias=gbias)
         # out_l[b, t, h, :] = u[b, h, t, :] . Wvv_h^T + b_h   (value projection after the token reduction)
         ol = torch.empty((B, T, H, d), dtype=torch.float16, device=dev)
         ops.gemm(u, w16(self.values_v_proj.weight).view(1, H, d, Cv), out=ol.permute(0, 2, 1, 3),

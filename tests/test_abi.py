@@ -84,9 +84,9 @@ def test_argument_validation_errors_without_gpu():
     expect(lib.mqdet_colsoftmax_transposed(one, 1, 10, 12, one, 16, one, nul), "T%8")          # T % 8 != 0
     expect(lib.mqdet_colstats_rowsoftmax(one, 1, 10, 128, nul, 1, 0.0, 0.0, one, nul), "T must be 256")
     expect(lib.mqdet_swin_window_attn(one, one, one, 1, 14, 14, 3, 8, 0, 1.0, one, nul), "window 7 (Swin-T) or 12 (Swin-L)")
-    expect(lib.mqdet_biattn_image(one, 8, 8, one, 8, 8, one, 8, 8, 8, nul, nul, nul, 0, 0, nul, 0.0, one, 8, 8, one, one,
-                                  1, 8, 100, 100, nul), "T % 8 == 0")
-    expect(lib.mqdet_biattn_text_vn(one, 8, 8, 8, one, 8, 8, 8, one, 8, 0, 8, nul, 0.0, one, 8, 8, 8, 1, 1, 256, 100, nul),
+    expect(lib.mqdet_biattn_image(one, 8, 8, one, 8, 8, 8, nul, 0, one, 8, 8, 8, nul, nul, nul, 0, 0, nul, 0.0, one, 8, 8, one,
+                                  one, 1, 8, 100, 100, nul), "T % 8 == 0")
+    expect(lib.mqdet_biattn_text_vn(one, 8, 8, 8, one, 8, 8, 8, one, 8, 0, 8, nul, nul, 0, 0.0, one, 8, 8, 8, 1, 1, 256, 100, nul),
            "null pointer")
     expect(lib.mqdet_gather_detections(one, one, one, one, one, 1, 256, 128, 64, one, nul), "det_rows")
     expect(lib.mqdet_dcn_cols(one, nul, 0, one, 5, 1, 128, 1, one, nul), "C must be 256")
