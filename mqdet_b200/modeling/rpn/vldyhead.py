@@ -231,6 +231,14 @@ class VLDyHead(nn.Module):
         self.scales = nn.ModuleList([Scale(init_value=1.0) for _ in range(5)])
         torch.nn.init.constant_(self.cls_logits.bias, bias_value)
         self._head = None
+        self.overlap_text_stream = True   # run the text branch of every tower layer on a second stream next to DyConv
+        self._side = {}
+
+    def _side_stream(self, device):
+        s = self._side.get(device)
+        if s is None:
+            s = self._side[device] = torch.cuda.Stream(device=device)
+        return s
 
     def _head_weights(self):
         """[4 bbox + 1 centerness, 256] fused 1x1 head (+ bias); log_scale read once (it is a constant at inference)."""
@@ -251,11 +259,36 @@ class VLDyHead(nn.Module):
         T = lang_hidden32.shape[1]
         cm = lang_masks.float().contiguous()
         h32 = lang_hidden32.float().contiguous()
+        main = torch.cuda.current_stream(v16.device)
         for i in range(0, len(self.dyhead_tower), 3):
             fuse, bert, dyconv = self.dyhead_tower[i], self.dyhead_tower[i + 1], self.dyhead_tower[i + 2]
-            v16, h32 = fuse.b_attn.forward_flat(v16, h32, lang_masks)
-            h32, _ = BertLayer.forward(bert, h32, ops.cast_f16(h32), cm)
-            v16 = dyconv.forward_flat(v16, levels)
+            split = fuse.b_attn.forward_flat_split(v16, h32, lang_masks) if self.overlap_text_stream else None
+            if split is None:
+                v16, h32 = fuse.b_attn.forward_flat(v16, h32, lang_masks)
+                h32, _ = BertLayer.forward(bert, h32, ops.cast_f16(h32), cm)
+                v16 = dyconv.forward_flat(v16, levels)
+                continue
+            # Two branches that do not depend on each other until the next fusion layer:
+            #   text branch  : text->image attention over all image tokens -> value / output projections -> BertEncoderLayer
+            #   visual branch: DyConv on the fused pyramid
+            # The text branch (128 CTAs, then GEMMs with a few dozen tiles) leaves most SMs idle; on a second stream it fills in
+            # next to the DyConv kernels.  Fork / join by events (capturable into the CUDA graph as two branches).  Every tensor
+            # that crosses streams is kept alive until the join, so the caching allocator never hands a block to one stream
+            # while the other may still touch it.
+            v_new, ctx = split
+            side = self._side_stream(v16.device)
+            fork, join = torch.cuda.Event(), torch.cuda.Event()
+            fork.record(main)
+            with torch.cuda.stream(side):
+                side.wait_event(fork)
+                h_new = fuse.b_attn.finish_text(ctx)
+                h_new, _ = BertLayer.forward(bert, h_new, ops.cast_f16(h_new), cm)
+                join.record(side)
+            v16 = dyconv.forward_flat(v_new, levels)
+            main.wait_event(join)
+            keep_alive = (ctx, h32)   # released only now: after the join both streams are done with them
+            h32 = h_new
+            del keep_alive
         # dot-product token head (:806-818, :871-888): tok = Linear(normalize(h)/2), bias = normalize(h).bias_lang + bias0
         e16, _, beta = ops.l2_normalize(h32, f32(self.bias_lang), f32(self.bias0))  # beta [B,T] fp32
         pt = self.dot_product_projection_text

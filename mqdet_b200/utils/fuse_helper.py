@@ -152,12 +152,17 @@ class BiMultiHeadAttention(nn.Module):
           text side : ONE kernel = S^T recomputed from gT and the image tokens -> exp(. - column max) -> P^T . vn (the image
                       tokens themselves; the value projection follows as a small per-head GEMM because sum_n p[n] = 1) with
                       in-kernel column sums."""
+        dv, ctx = self._fused_image(vn16, ln16, k, mask_l, clamp, v_epilogue)
+        return dv, self._fused_text(ctx, l_epilogue)
+
+    def _fused_image(self, vn16, ln16, k, mask_l, clamp, v_epilogue):
+        """Image side of the product path (see _attend_fused) -> (dv [B,N,Cv] fp16, context of the text side).  The text side
+        only needs that context, so a caller may run it on another stream next to the visual branch (VLDyHead.forward_flat)."""
         B, N, Cv = vn16.shape
         T = ln16.shape[1]
         H, d, E = self.num_heads, self.head_dim, self.embed_dim
         dev = vn16.device
         ve = v_epilogue or {}
-        le = l_epilogue or {}
         kh = k.permute(0, 2, 1, 3)                                                     # [B,H,T,d]
         wqT, bq8 = self._query_fold_weights()
         gT = torch.empty((B, H, T, Cv), dtype=torch.float16, device=dev)
@@ -170,6 +175,17 @@ class BiMultiHeadAttention(nn.Module):
         cm = mask_l.float().contiguous() if mask_l is not None else None
         dv, colmax = ops.biattn_image(vn16, gT, gbias, mT, f32(self.out_v_proj.bias), ve.get("gate"), ve.get("residual"), cm,
                                       clamp, H)
+        return dv, dict(gT=gT, gbias=gbias, vn16=vn16, colmax=colmax, clamp=clamp)
+
+    def _fused_text(self, ctx, l_epilogue):
+        """Text side of the product path: S^T recomputed from gT and the image tokens, softmax over all image tokens, value
+        projection after the token reduction, output projection (+ layer scale + residual) -> dl [B,T,l_dim] fp32."""
+        gT, gbias, vn16, colmax, clamp = ctx["gT"], ctx["gbias"], ctx["vn16"], ctx["colmax"], ctx["clamp"]
+        B, N, Cv = vn16.shape
+        H, d, E = self.num_heads, self.head_dim, self.embed_dim
+        T = gT.shape[2]
+        dev = vn16.device
+        le = l_epilogue or {}
         u = torch.empty((B, H, T, Cv), dtype=torch.float16, device=dev)
         ops.biattn_text_vn(gT, vn16.view(B, 1, N, Cv).expand(B, H, N, Cv), vn16, colmax, clamp, u, rowbias=gbias)
         # out_l[b, t, h, :] = u[b, h, t, :] . Wvv_h^T + b_h   (value projection after the token reduction)
@@ -179,7 +195,7 @@ class BiMultiHeadAttention(nn.Module):
         dl = ops.gemm(ol.view(B * T, E), w16(self.out_l_proj.weight), bias=f32(self.out_l_proj.bias),
                       out_dtype=torch.float32, gate=le.get("gate"), gate_mode=VEC_PER_COL if le else 0,
                       residual=le["residual"].view(B * T, -1) if le else None)
-        return dv, dl.view(B, T, -1)
+        return dl.view(B, T, -1)
 
     def _attend_f32_scores(self, qh, kh, vvT, vlT, mask_l, clamp, B, N, T, Np):
         """Diagnostic: both score matrices in fp32 (A and its transpose as two products), softmaxes on the fp32 values."""
@@ -246,6 +262,29 @@ class BiAttentionBlockForCheckpoint(nn.Module):
         return self.attn._attend(vn16, ln16, attention_mask_l,
                                  v_epilogue=dict(gate=f32(self.gamma_v), residual=vn16),
                                  l_epilogue=dict(gate=f32(self.gamma_l), residual=ln32))
+
+    @torch.no_grad()
+    def forward_flat_split(self, v16, l32, attention_mask_l):
+        """forward_flat in two halves for two-stream execution: returns (v' fp16, ctx) after the image side; ``finish_text(ctx)``
+        -> l' fp32 runs the text side (it depends on nothing the visual branch computes afterwards).  None when the product
+        path does not apply (A/B score precisions, unusual shapes)."""
+        a = self.attn
+        B, N, Cv = v16.shape
+        T = l32.shape[1]
+        if not (a.score_precision == "fused" and a.head_dim == 256 and Cv == 256 and T % 8 == 0 and T <= 256 and a.num_heads <= 8):
+            return None
+        nv, nl = self.layer_norm_v, self.layer_norm_l
+        vn16 = ops.layernorm(v16, f32(nv.weight), f32(nv.bias), nv.eps)
+        ln16, ln32 = ops.layernorm(l32, f32(nl.weight), f32(nl.bias), nl.eps, out16=True, out32=True)
+        clamp = 50000.0 if (a.clamp_min_for_underflow or a.clamp_max_for_overflow) else 0.0
+        k = ops.gemm(ln16.view(B * T, -1), w16(a.l_proj.weight), bias=f32(a.l_proj.bias)).view(B, T, a.num_heads, a.head_dim)
+        dv, ctx = a._fused_image(vn16, ln16, k, attention_mask_l, clamp, dict(gate=f32(self.gamma_v), residual=vn16))
+        ctx["ln32"] = ln32
+        return dv.view(B, N, Cv), ctx
+
+    @torch.no_grad()
+    def finish_text(self, ctx):
+        return self.attn._fused_text(ctx, dict(gate=f32(self.gamma_l), residual=ctx["ln32"]))
 
     def single_attention_call(self, v, l, attention_mask_l=None, dummy_tensor=None):
         v2, l2 = self.forward_flat(ops.cast_f16(v.contiguous()), l.float().contiguous(), attention_mask_l)

@@ -28,6 +28,7 @@ model.load_state_dict(sd, strict=True)
 del sd
 model = model.to(dev).eval()
 model.query_selector.set_query_bank(bank)
+model.rpn.head.overlap_text_stream = os.environ.get("MQDET_OVERLAP", "0") == "1"  # stage times: branches one after the other
 caps = {"input_ids": ids, "attention_mask": am}
 x = img.to(dev)
 sizes = [(bench.H_IMG, bench.W_IMG)] * B
