@@ -418,7 +418,7 @@ __device__ __forceinline__ void epilogue_fast(const GemmP& p, const CUtensorMap*
     }
     if (act == MQDET_ACT_GELU) {
 #pragma unroll
-      for (int k = 0; k < 16; ++k) v[k] = gelu_fast(v[k]);
+      for (int k = 0; k < 8; ++k) gelu_fast2(v[2 * k], v[2 * k + 1]);
     } else if (act == MQDET_ACT_RELU) {
 #pragma unroll
       for (int k = 0; k < 16; ++k) v[k] = fmaxf(v[k], 0.f);
