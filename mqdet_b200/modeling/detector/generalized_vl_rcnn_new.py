@@ -58,6 +58,14 @@ class GeneralizedVLRCNN_New(nn.Module):
         self.tokenizer = None  # attach an HF tokenizer to accept string captions
         self.DEBUG = False
         self._prompt = None
+        self.overlap_text_prefix = True   # image-independent BERT layers on a second stream next to the visual backbone
+        self._side = {}
+
+    def _side_stream(self, device):
+        s = self._side.get(device)
+        if s is None:
+            s = self._side[device] = torch.cuda.Stream(device=device)
+        return s
 
     def load_query_bank(self, path):
         self.query_selector.load_query_bank(path)
@@ -210,11 +218,25 @@ class GeneralizedVLRCNN_New(nn.Module):
         if not x.is_cuda:
             raise MqdetError("GeneralizedVLRCNN_New: CUDA images required (no CPU fallback)")
         B = x.shape[0]
+        st = self._prompt_state(captions, positive_map, B, x.device)
+        # The embeddings and the BERT layers before the first GCP block depend on the prompt only: they run on a second
+        # stream next to the visual backbone (fork / join by events; capturable as a second graph branch).
+        prefix = None
+        if self.overlap_text_prefix:
+            main = torch.cuda.current_stream(x.device)
+            side = self._side_stream(x.device)
+            fork, join = torch.cuda.Event(), torch.cuda.Event()
+            fork.record(main)
+            with torch.cuda.stream(side):
+                side.wait_event(fork)
+                prefix = self.language_backbone.body.model.text_prefix(st["ids"], st["am"])
+                join.record(side)
         feats = self.backbone.body.forward_flat(x)
         pyr16, levels = self.backbone.fpn.forward_flat([feats[i] for i in (1, 2, 3)])
-        st = self._prompt_state(captions, positive_map, B, x.device)
+        if prefix is not None:
+            main.wait_event(join)
         pooled = ops.avgpool2_levels(pyr16, levels) if st["vision"] is not None else None  # flatten_fpn_features (:291-293)
-        lang = self.language_backbone.body({"input_ids": st["ids"], "attention_mask": st["am"],
+        lang = self.language_backbone.body({"input_ids": st["ids"], "attention_mask": st["am"], "text_prefix": prefix,
                                             "vision_inputs": {"vision": st["vision"], "images": pooled,
                                                               "vision_attention_mask": st["vmask"],
                                                               "batched_pos_category_map": None}})

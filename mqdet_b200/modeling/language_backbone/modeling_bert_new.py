@@ -394,10 +394,28 @@ class QVBertEncoder(nn.Module):
                                        for _ in range(n - start_qv_layer_index)])
 
     @torch.no_grad()
-    def forward(self, h32, h16, colmask, vision=None, vision_attention_mask=None, batched_pos_category_map=None,
-                output_hidden_states=False):
+    def forward_prefix(self, h32, h16, colmask, output_hidden_states=False):
+        """BERT layers 0 .. start_qv_layer_index-1: they depend on the prompt only, not on the image, so the detector runs them
+        on a second stream next to the visual backbone.  Returns the state ``forward(..., prefix=state)`` continues from."""
         all_h = () if output_hidden_states else None
+        for i in range(self.start_qv_layer_index):
+            if output_hidden_states:
+                all_h = all_h + (h32,)
+            h32, h16 = self.layer[i](h32, h16, colmask)
+        return dict(h32=h32, h16=h16, all_h=all_h, next=self.start_qv_layer_index)
+
+    @torch.no_grad()
+    def forward(self, h32, h16, colmask, vision=None, vision_attention_mask=None, batched_pos_category_map=None,
+                output_hidden_states=False, prefix=None):
+        all_h = () if output_hidden_states else None
+        first = 0
+        if prefix is not None:
+            h32, h16, first = prefix["h32"], prefix["h16"], prefix["next"]
+            if output_hidden_states:
+                all_h = prefix["all_h"]
         for i, layer in enumerate(self.layer):
+            if i < first:
+                continue
             if output_hidden_states:
                 all_h = all_h + (h32,)
             if i >= self.start_qv_layer_index and exists(vision):
@@ -437,9 +455,8 @@ class QVBertModel(nn.Module):
         return {"attn_gates": attn_gates, "ffn_gates": ff_gates}
 
     @torch.no_grad()
-    def forward(self, input_ids=None, attention_mask=None, token_type_ids=None, position_ids=None, head_mask=None,
-                inputs_embeds=None, output_hidden_states=None, return_dict=True, vision=None, images=None,
-                vision_attention_mask=None, batched_pos_category_map=None, **unused):
+    def text_prefix(self, input_ids, attention_mask=None, token_type_ids=None, position_ids=None, output_hidden_states=True):
+        """Embeddings + the BERT layers that precede the first GCP block (image-independent part of ``forward``)."""
         if input_ids is None or not input_ids.is_cuda:
             raise MqdetError("QVBertModel: CUDA input_ids required (no CPU fallback)")
         B, T = input_ids.shape
@@ -447,13 +464,31 @@ class QVBertModel(nn.Module):
             attention_mask = torch.ones((B, T), device=input_ids.device)
         colmask = attention_mask.float().contiguous()
         h32, h16 = self.embeddings(input_ids, token_type_ids, position_ids)
+        st = self.encoder.forward_prefix(h32, h16, colmask, output_hidden_states=bool(output_hidden_states))
+        st["colmask"] = colmask
+        return st
+
+    @torch.no_grad()
+    def forward(self, input_ids=None, attention_mask=None, token_type_ids=None, position_ids=None, head_mask=None,
+                inputs_embeds=None, output_hidden_states=None, return_dict=True, vision=None, images=None,
+                vision_attention_mask=None, batched_pos_category_map=None, text_prefix=None, **unused):
+        if input_ids is None or not input_ids.is_cuda:
+            raise MqdetError("QVBertModel: CUDA input_ids required (no CPU fallback)")
+        B, T = input_ids.shape
+        if attention_mask is None:
+            attention_mask = torch.ones((B, T), device=input_ids.device)
+        if text_prefix is not None:
+            colmask, h32, h16 = text_prefix["colmask"], None, None
+        else:
+            colmask = attention_mask.float().contiguous()
+            h32, h16 = self.embeddings(input_ids, token_type_ids, position_ids)
         augmented_vision = None
         if exists(images) and exists(vision):
             vision = self.pre_select(vision, images)["vision"]
             augmented_vision = vision
         h32, all_h = self.encoder(h32, h16, colmask, vision=vision, vision_attention_mask=vision_attention_mask,
                                   batched_pos_category_map=batched_pos_category_map,
-                                  output_hidden_states=bool(output_hidden_states))
+                                  output_hidden_states=bool(output_hidden_states), prefix=text_prefix)
         out = ModelOutput(last_hidden_state=h32, pooler_output=None, hidden_states=all_h)
         out["vision_query_gates"] = self.get_gate_value()
         if getattr(self.cfg.VISION_QUERY, "QUERY_FUSION", False):
