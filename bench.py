@@ -250,9 +250,27 @@ def run_lvis(args):
                        "global_batch": B, "parallelism": f"prompt chunks sharded over {world} rank(s), 1 NCCL all-gather of [chunks,B,{model.max_out() + 1},6]",
                        "chunk_forwards_per_step": B * len(chunks), "detections_returned_per_step": nd,
                        "l2": "256 MiB buffer written between timed steps"},
-            "gpu_launches": ops.launch_count, "clocks": clk}))
-    if world > 1:
-        dist.destroy_process_group()
+            "gpu_launches": ops.launch_count, "clocks": clk}), flush=True)
+    finish(world)
+
+
+def finish(world):
+    """Leave the process group; the JSON line is already out, so a teardown that does not return within 30 s (seen with
+    communicators that recorded graph-captured collectives) ends the process instead of hanging the launcher."""
+    if world <= 1:
+        return
+    import threading
+    import torch.distributed as dist
+    sys.stdout.flush()
+    guard = threading.Timer(30.0, lambda: os._exit(0))
+    guard.daemon = True
+    guard.start()
+    dist.barrier()
+    dist.destroy_process_group()
+    guard.cancel()
+    sys.stdout.flush()
+    sys.stderr.flush()
+    os._exit(0)  # nothing left to finalise; interpreter teardown with NCCL/graph state alive is the other place this can hang
 
 
 def build_inputs(B, seed):
@@ -492,9 +510,9 @@ def main():
             res["cpu_baseline"] = {"value": 1.0 / (sum(ts) / len(ts)), "unit": "images/s", "cores": cores, "kind": "port",
                                    "sample": f"{len(ts)} forward(s) of ONE 800x1333 image, 80-class prompt, oracle/restate.py "
                                              f"fp32 on {cores} host threads"}
-        print(json.dumps(res))
-    if world > 1:
-        dist.destroy_process_group()
+        print(json.dumps(res), flush=True)
+    engine.close()  # captured NCCL all-gathers must be gone before the communicator is
+    finish(world)
 
 
 if __name__ == "__main__":

@@ -234,6 +234,16 @@ int mqdet_ml_nms(const float* boxes, const float* scores, const float* labels, c
 int mqdet_dcn_cols(const void* x, const float* om, int64_t om_ld, const int32_t* level_hw, int64_t nlev, int64_t B,
                    int64_t C, int branch, void* cols, void* stream);
 
+/* The same DCNv2 convolutions as ONE implicit GEMM on the tensor cores, without the column matrix (replaces
+ * mqdet_dcn_cols + mqdet_gemm_f16 for modulated_deform_conv_cuda_forward, deform_conv_cuda.cu:493-690 inference path):
+ *   y[j][B*rows_j][256] (f16) = sampled_cols_j[B*rows_j][9*256] * weight[j][256][9*256]^T + bias[j]       j < njobs <= 3
+ * branch[j] selects the sampling geometry exactly as in mqdet_dcn_cols; all jobs share x / om and run in one launch.
+ * branch, weight, bias, y: HOST arrays of njobs entries (device pointers inside; bias[j] may be NULL). */
+#define MQDET_DCN_MAX_JOBS 3
+int mqdet_dcn_conv(const void* x, const float* om, int64_t om_ld, const int32_t* level_hw, int64_t nlev, int64_t B,
+                   int64_t C, int64_t njobs, const int32_t* branch, const void* const* weight, const float* const* bias,
+                   void* const* y, void* stream);
+
 /* Plain 3x3 / pad 1 / stride 1 convolution with O <= 32 output channels over all levels at once, no column matrix: the
  * offset/mask conv of DyConv (`self.offset`, vldyhead.py:150-153,207-210).  x [B,N,256] f16 (levels concatenated),
  * w [O][9*256] f16 with k = tap*256 + c (tap = ky*3 + kx), bias [O] f32 -> out [B*N, ld] f32 (columns 0..O-1 written). */

@@ -74,6 +74,8 @@ SIGNATURES = {
     "mqdet_contrastive_mask": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64, c_void_p]),
     "mqdet_argsort_desc": (c_int, [c_void_p, c_int64, c_void_p, c_void_p]),
     "mqdet_ml_nms_workspace_bytes": (c_int64, [c_int64]),
+    "mqdet_dcn_conv": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int64, c_int64, c_void_p, c_void_p,
+                               c_void_p, c_void_p, c_void_p]),
     "mqdet_dcn_cols": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int64, c_int, c_void_p,
                                c_void_p]),
     "mqdet_conv3x3_small": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64, c_void_p,

@@ -29,6 +29,27 @@ int check_launch(const char* what);
 
 static inline int cdiv(long a, long b) { return (int)((a + b - 1) / b); }
 
+// All FPN levels of an image live in one tensor x[B][N][C] (level l at row offset off_l, row-major (h, w)).
+#ifndef MQDET_MAX_LEVELS
+#define MQDET_MAX_LEVELS 8
+#endif
+struct LevelTable {
+  int n;
+  int H[MQDET_MAX_LEVELS], W[MQDET_MAX_LEVELS], off[MQDET_MAX_LEVELS];
+};
+static inline int fill_levels(LevelTable* t, const int32_t* hw, int64_t nlev) {
+  if (nlev < 1 || nlev > MQDET_MAX_LEVELS) return -1;
+  t->n = (int)nlev;
+  int off = 0;
+  for (int l = 0; l < nlev; ++l) {
+    t->H[l] = hw[2 * l];
+    t->W[l] = hw[2 * l + 1];
+    t->off[l] = off;
+    off += t->H[l] * t->W[l];
+  }
+  return off;
+}
+
 // host helpers of the tcgen05 kernels (capi.cu): cached TMA tensor maps, per-device SM count / shared-memory opt-in
 int make_operand_map(CUtensorMap* map, const void* ptr, long rows, long K, long ld, int nb1, long s1, int nb2, long s2,
                      int box_rows, int* bcast1, int* bcast2);

@@ -12,24 +12,6 @@
 
 namespace mqdet {
 
-struct LevelTable {
-  int n;
-  int H[MQDET_MAX_LEVELS], W[MQDET_MAX_LEVELS], off[MQDET_MAX_LEVELS];
-};
-
-static int fill_levels(LevelTable* t, const int32_t* hw, int64_t nlev) {
-  if (nlev < 1 || nlev > MQDET_MAX_LEVELS) return -1;
-  t->n = (int)nlev;
-  int off = 0;
-  for (int l = 0; l < nlev; ++l) {
-    t->H[l] = hw[2 * l];
-    t->W[l] = hw[2 * l + 1];
-    t->off[l] = off;
-    off += t->H[l] * t->W[l];
-  }
-  return off;
-}
-
 __device__ __forceinline__ void ld8h(const __half* p, float (&f)[8]) {
   const uint4 a = *reinterpret_cast<const uint4*>(p);
   const __half2* h = reinterpret_cast<const __half2*>(&a);

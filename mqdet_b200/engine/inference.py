@@ -103,6 +103,18 @@ class InferenceEngine:
             return self.outs[k]
         return self._forward(k)
 
+    def close(self):
+        """Drop the captured graphs (and the NCCL work they hold) before the process group is destroyed: a communicator that
+        still has captured collectives alive does not tear down."""
+        torch.cuda.synchronize(self.dev)
+        for g in self.graphs:
+            if g is not None:
+                g.reset()
+        self.graphs = [None, None]
+        self.outs = [None, None]
+        self.use_graph = False
+        torch.cuda.synchronize(self.dev)
+
     def to_boxlists(self, k=0):
         """BoxLists of the LOCAL images from pinned host buffer k (waits for that step's device->host copy only)."""
         from ..structures.bounding_box import BoxList

@@ -87,6 +87,7 @@ class DyConv(nn.Module):
         self.h_sigmoid = h_sigmoid()
         self.relu = DYReLU(in_channels, out_channels)
         self.offset = nn.Conv2d(in_channels, 27, kernel_size=3, stride=1, padding=1)
+        self.implicit_dcn = True
         self.init_weights()
 
     def init_weights(self):
@@ -109,10 +110,20 @@ class DyConv(nn.Module):
         aw = f32(self.AttnConv[1].weight).view(-1)
         ab = f32(self.AttnConv[1].bias)
 
+        # the three DCNv2 convolutions: one implicit-GEMM launch (no column matrix); implicit_dcn = False keeps the
+        # sampling kernel + GEMM pair (dcn_cols -> gemm), the path the comparison tests check the implicit one against
+        ks = [1, 2, 0] if L > 1 else [1]
+        if self.implicit_dcn:
+            ys = dict(zip(ks, ops.dcn_conv(x16, om3, levels, ks, [_conv_w16(self.DyConv[k].conv.weight) for k in ks],
+                                           [f32(self.DyConv[k].conv.bias) for k in ks])))
+
         def branch(k, rows, seg, weights=None):
             conv, gn = self.DyConv[k].conv, self.DyConv[k].bn
-            c = ops.dcn_cols(x16, om3, levels, k)
-            y = ops.gemm(c, _conv_w16(conv.weight), bias=f32(conv.bias))
+            if self.implicit_dcn:
+                y = ys[k]
+            else:
+                c = ops.dcn_cols(x16, om3, levels, k)
+                y = ops.gemm(c, _conv_w16(conv.weight), bias=f32(conv.bias))
             part = ops.chan_stats(y, seg, B, rows, weights)
             aff, at = ops.gn_attn(part, seg, B, C, gn.num_groups, weights is not None, f32(gn.weight), f32(gn.bias),
                                   gn.eps, aw, ab)

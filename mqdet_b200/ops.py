@@ -501,6 +501,29 @@ def dcn_cols(x16, om, levels, branch):
     return cols
 
 
+def dcn_conv(x16, om, levels, branches, weights, biases):
+    """DyConv's DCNv2 convolutions as one implicit GEMM (no column matrix): x16 [B,N,256] fp16, om [B,N,om_ld] fp32 or None,
+    branches: list of 0/1/2, weights: fp16 [256, 2304] (k = tap*256 + c) each, biases: fp32 [256] or None each
+    -> list of fp16 [B*rows_j, 256]."""
+    global launch_count
+    _need_cuda(x16, om, *weights)
+    B, N, C = x16.shape
+    n = len(branches)
+    ys = [torch.empty((B * (levels.N if k == 1 else levels.N1), 256), dtype=torch.float16, device=x16.device) for k in branches]
+    br = (ctypes.c_int32 * n)(*[int(k) for k in branches])
+    wp = (ctypes.c_void_p * n)(*[w.data_ptr() for w in weights])
+    bp = (ctypes.c_void_p * n)(*[(b.data_ptr() if b is not None else None) for b in biases])
+    yp = (ctypes.c_void_p * n)(*[y.data_ptr() for y in ys])
+    for w in weights:
+        if w.dtype != torch.float16 or tuple(w.shape) != (256, 9 * C) or not w.is_contiguous():
+            raise _lib.MqdetError(f"dcn_conv: weights must be contiguous fp16 [256, {9 * C}] (got {w.dtype} {tuple(w.shape)})")
+    check(load().mqdet_dcn_conv(_ptr(x16), _ptr(om), om.shape[-1] if om is not None else 0, levels.hw_ptr, levels.n, B, C, n,
+                                ctypes.cast(br, ctypes.c_void_p), ctypes.cast(wp, ctypes.c_void_p),
+                                ctypes.cast(bp, ctypes.c_void_p), ctypes.cast(yp, ctypes.c_void_p), _stream()), "dcn_conv")
+    launch_count += 1
+    return ys
+
+
 def conv3x3_small(x16, w16_, bias, levels, ld=32):
     """Plain 3x3 / pad 1 conv with <= 32 output channels over all levels, no column matrix (the DyConv offset/mask conv):
     x16 [B,N,256] fp16, w16_ [O, 2304] fp16 (k = tap*256 + c), bias [O] fp32 -> [B*N, ld] fp32 (columns >= O untouched)."""

@@ -90,6 +90,8 @@ def test_argument_validation_errors_without_gpu():
            "null pointer")
     expect(lib.mqdet_gather_detections(one, one, one, one, one, 1, 256, 128, 64, one, nul), "det_rows")
     expect(lib.mqdet_dcn_cols(one, nul, 0, one, 5, 1, 128, 1, one, nul), "C must be 256")
+    expect(lib.mqdet_dcn_conv(one, nul, 0, one, 5, 1, 128, 1, one, one, one, one, nul), "C must be 256")
+    expect(lib.mqdet_dcn_conv(one, nul, 0, one, 5, 1, 256, 4, one, one, one, one, nul), "1..3 jobs")
     expect(lib.mqdet_conv3x3_small(one, one, one, one, 5, 1, 256, 40, one, 64, nul), "O <= 32")
     expect(lib.mqdet_biattn_text(one, 8, 8, 8, one, 8, 8, 8, one, 8, 8, 8, one, 0.0, one, 8, 8, 8, 1, 1, 256, 100, 104, 128,
                                  nul), "head dim must be 256")

@@ -122,6 +122,38 @@ def test_conv3x3_small_equals_conv2d(dev):
         assert err <= 2e-4 * ref.abs().max().item() + 1e-5, (l, err)     # fp32 accumulation of fp16-exact products
 
 
+@pytest.mark.parametrize("sizes,B,with_om", [([(13, 17), (7, 9), (4, 5), (2, 3), (1, 1)], 3, True),
+                                             ([(40, 56), (20, 28), (10, 14), (5, 7), (3, 4)], 2, True),
+                                             ([(13, 17), (7, 9), (4, 5)], 2, False), ([(9, 11)], 2, True)])
+def test_dcn_conv_implicit_equals_cols_gemm(dev, sizes, B, with_om):
+    """mqdet_dcn_conv (sampling fused into the tcgen05 mainloop, three branches in one launch) against the sampling kernel +
+    GEMM pair it replaces: same fp16 operands, same fp32 accumulation, the mask folded into the corner weights (one fp32
+    rounding apart) -> equal up to an fp16 ulp of the column values.  Sizes make tiles straddle levels, images and the ragged
+    last tile; large offsets push samples outside the maps."""
+    from mqdet_b200 import ops
+    g = torch.Generator().manual_seed(11)
+    lv = ops.Levels(sizes, dev)
+    x16 = torch.randn(B, lv.N, 256, generator=g).half().to(dev)
+    om = None
+    if with_om:
+        om = torch.randn(B, lv.N, 32, generator=g)
+        om[..., :18] *= 2.5
+        om = om.to(dev).contiguous()
+    ks = [1, 2, 0] if len(sizes) > 1 else [1]
+    ws = [(torch.randn(256, 2304, generator=g) * 0.03).half().to(dev) for _ in ks]
+    bs = [torch.randn(256, generator=g).to(dev) for _ in ks]
+    ys = ops.dcn_conv(x16, om, lv, ks, ws, bs)
+    for k, w, b, y in zip(ks, ws, bs, ys):
+        ref = ops.gemm(ops.dcn_cols(x16, om, lv, k), w, bias=b)
+        assert y.shape == ref.shape
+        err = (y.float() - ref.float()).abs().max().item()
+        assert err <= 2e-3 * ref.float().abs().max().item(), (k, err, ref.float().abs().max().item())
+    # no bias pointer
+    y0 = ops.dcn_conv(x16, om, lv, [1], ws[:1], [None])[0]
+    ref0 = ops.gemm(ops.dcn_cols(x16, om, lv, 1), ws[0])
+    assert (y0.float() - ref0.float()).abs().max().item() <= 2e-3 * ref0.float().abs().max().item()
+
+
 def test_dyconv(dev):
     from mqdet_b200 import ops
     from mqdet_b200.modeling.rpn.vldyhead import Conv3x3Norm, DyConv
@@ -137,6 +169,9 @@ def test_dyconv(dev):
     x16 = restate.flatten_levels(feats).half().to(dev).contiguous()
     out = mod.forward_flat(x16, lv)
     assert_close(out, ref, 3e-3, "DyConv (fp16 activations)")
+    mod.implicit_dcn = False   # sampling kernel + GEMM pair instead of the implicit GEMM
+    assert_close(mod.forward_flat(x16, lv), ref, 3e-3, "DyConv (column-matrix path)")
+    mod.implicit_dcn = True
     # the same inputs through the REFERENCE's own DyConv.forward (fixture recorded by oracle/make_golden.py)
     from oracle import make_golden
     fx = torch.load(os.path.join(ROOT, "tests", "golden", "dyconv.pt"))
