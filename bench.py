@@ -403,22 +403,30 @@ def main():
     engine.stage[1].copy_(img_dev)
 
     # ---- device-resident throughput ---------------------------------------------------------------------------------
-    for _ in range(args.warmup):
-        engine.device_step()
+    for i in range(args.warmup):
+        engine.device_step(k=i & 1)
     barrier()
     clocks = ClockSampler(local)  # rank 0 samples its own GPU (one nvidia-smi poller per node is enough)
     if rank == 0:
         clocks.start()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     barrier()
+    main_stream = torch.cuda.current_stream()
     for i in range(args.steps):
         flush.zero_()  # L2 flush between timed iterations (outside the per-step events)
         ev[i][0].record()
-        engine.device_step()
+        engine.device_step(k=i & 1)
         ev[i][1].record()
+    # the all-gather of a step runs on the engine's result stream behind the forward; a step's bracket holds the wait for
+    # the gather issued two steps earlier, and this last bracket holds the two still in flight: every collective is timed
+    tail = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+    tail[0].record()
+    for e in engine.res_done:
+        main_stream.wait_event(e)
+    tail[1].record()
     barrier()
     launches = launches_per_step * args.steps
-    ms = sum(a.elapsed_time(b) for a, b in ev) / args.steps
+    ms = (sum(a.elapsed_time(b) for a, b in ev) + tail[0].elapsed_time(tail[1])) / args.steps
     t = torch.tensor([ms], device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)

@@ -83,6 +83,77 @@ __global__ void __launch_bounds__(256) layernorm_reg_kernel(const T* __restrict_
   }
 }
 
+// Narrow rows (Swin stages 1 / 2: D = 96 / 192 over 537600 / 134400 tokens): R consecutive rows per warp, all R*K loads issued
+// before the first reduction, so a warp keeps R x 384 bytes in flight instead of 384 (the one-row kernel sits at ~30 % of
+// the HBM rate on these shapes).  Same arithmetic per row as layernorm_reg_kernel.
+template <typename T, int K, int R>
+__global__ void __launch_bounds__(256) layernorm_reg_rows_kernel(const T* __restrict__ x, long ldx,
+                                                                 const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                                 float eps, long rows, __half* __restrict__ out16,
+                                                                 float* __restrict__ out32, long ldo, long zero_row_period) {
+  const long row0 = ((long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * R;
+  const int lane = threadIdx.x & 31;
+  if (row0 >= rows) return;
+  constexpr int D = 32 * K;
+  float v[R][K];
+  bool zr[R];
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    const long row = row0 + r;
+    zr[r] = row >= rows || (zero_row_period > 0 && (row % zero_row_period) == zero_row_period - 1);
+#pragma unroll
+    for (int i = 0; i < K; ++i) v[r][i] = zr[r] ? 0.f : ld_as_float(x + row * ldx + lane + 32 * i);
+  }
+  float g[K], bt[K];
+#pragma unroll
+  for (int i = 0; i < K; ++i) {
+    g[i] = gamma[lane + 32 * i];
+    bt[i] = beta[lane + 32 * i];
+  }
+  float mean[R], rstd[R];
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < K; ++i) s += v[r][i];
+    mean[r] = s;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+    for (int r = 0; r < R; ++r) mean[r] += __shfl_xor_sync(0xffffffffu, mean[r], o);
+  }
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    mean[r] = zr[r] ? 0.f : mean[r] / D;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < K; ++i) {
+      const float d = v[r][i] - mean[r];
+      q += d * d;
+    }
+    rstd[r] = q;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+    for (int r = 0; r < R; ++r) rstd[r] += __shfl_xor_sync(0xffffffffu, rstd[r], o);
+  }
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    const long row = row0 + r;
+    if (row >= rows) break;
+    const float rs = zr[r] ? rsqrtf(eps) : rsqrtf(rstd[r] / D + eps);
+#pragma unroll
+    for (int i = 0; i < K; ++i) {
+      const int c = lane + 32 * i;
+      const float y = (v[r][i] - mean[r]) * rs * g[i] + bt[i];
+      if (out16) out16[row * ldo + c] = __float2half_rn(y);
+      if (out32) out32[row * ldo + c] = y;
+    }
+  }
+}
+
 __global__ void __launch_bounds__(256) layernorm_h256_kernel(const __half* __restrict__ x, long ldx,
                                                              const float* __restrict__ gamma, const float* __restrict__ beta,
                                                              float eps, long rows, __half* __restrict__ out16,
@@ -814,6 +885,20 @@ extern "C" int mqdet_layernorm(const void* x, int in_dtype, int64_t ldx, const f
 #define MQ_LN_REG(TT, KK)                                                                                                   \
   layernorm_reg_kernel<TT, KK><<<grid, wpb * 32, 0, st>>>((const TT*)x, ldx, gamma, beta, eps, rows, (__half*)out16,        \
                                                           (float*)out32, ldo, zero_row_period)
+  if ((D == 96 || D == 192) && rows >= 4096) {  // narrow rows: several rows per warp (see layernorm_reg_rows_kernel)
+#define MQ_LN_ROWS(TT, KK, RR)                                                                                               \
+  layernorm_reg_rows_kernel<TT, KK, RR><<<cdiv(rows, wpb * RR), wpb * 32, 0, st>>>(                                         \
+      (const TT*)x, ldx, gamma, beta, eps, rows, (__half*)out16, (float*)out32, ldo, zero_row_period)
+    if (in_dtype == MQDET_F32) {
+      if (D == 96) MQ_LN_ROWS(float, 3, 4);
+      else MQ_LN_ROWS(float, 6, 2);
+    } else {
+      if (D == 96) MQ_LN_ROWS(__half, 3, 4);
+      else MQ_LN_ROWS(__half, 6, 2);
+    }
+#undef MQ_LN_ROWS
+    return check_launch("layernorm_reg_rows_kernel");
+  }
   if ((D % 32) == 0 && D / 32 <= 24) {
     const int k = (int)(D / 32);
     bool done = true;

@@ -243,6 +243,51 @@ __global__ void __launch_bounds__(256) patch_merge_ln_kernel(const float* __rest
   for (int i = lane; i < D4; i += 32) out[row * D4 + i] = __float2half_rn((src(i) - mean) * rstd * gamma[i] + beta[i]);
 }
 
+// The same, register-cached and vectorised for C = 32 * K4 (Swin-T/L stages: 96, 192, 384): the 4C-float row is read ONCE as
+// float4s (lane l owns float4 #(l + 32 i); a float4 never straddles two of the four source pixels because C % 4 == 0) and
+// written as 8-byte fp16 groups.  Same two-pass statistics in fp32.
+template <int K4>
+__global__ void __launch_bounds__(256) patch_merge_ln_vec_kernel(const float* __restrict__ x, int B, int H, int W,
+                                                                 const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                                 float eps, __half* __restrict__ out) {
+  constexpr int C = 32 * K4, C4 = C / 4, D4 = 4 * C;
+  const int H2 = (H + 1) / 2, W2 = (W + 1) / 2;
+  const long row = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= (long)B * H2 * W2) return;
+  const int w2 = (int)(row % W2), h2 = (int)((row / W2) % H2), b = (int)(row / ((long)W2 * H2));
+  float4 v[K4];
+#pragma unroll
+  for (int i = 0; i < K4; ++i) {
+    const int f = lane + 32 * i, q = f / C4, c4 = f - q * C4;
+    const int hh = 2 * h2 + (q & 1), ww = 2 * w2 + (q >> 1);
+    v[i] = (hh < H && ww < W) ? __ldg(reinterpret_cast<const float4*>(x + ((long)b * H * W + (long)hh * W + ww) * C) + c4)
+                              : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < K4; ++i) s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+  const float mean = warp_sum(s) / D4;
+  float qv = 0.f;
+#pragma unroll
+  for (int i = 0; i < K4; ++i) {
+    const float a = v[i].x - mean, bb = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+    qv += (a * a + bb * bb) + (c * c + d * d);
+  }
+  const float rstd = rsqrtf(warp_sum(qv) / D4 + eps);
+#pragma unroll
+  for (int i = 0; i < K4; ++i) {
+    const int f = lane + 32 * i;
+    const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + f), bt = __ldg(reinterpret_cast<const float4*>(beta) + f);
+    const __half2 lo = __floats2half2_rn((v[i].x - mean) * rstd * g.x + bt.x, (v[i].y - mean) * rstd * g.y + bt.y);
+    const __half2 hi = __floats2half2_rn((v[i].z - mean) * rstd * g.z + bt.z, (v[i].w - mean) * rstd * g.w + bt.w);
+    uint2 o;
+    o.x = *reinterpret_cast<const uint32_t*>(&lo);
+    o.y = *reinterpret_cast<const uint32_t*>(&hi);
+    *reinterpret_cast<uint2*>(out + row * D4 + 4 * f) = o;
+  }
+}
+
 // FPN top-down merge (fpn.py:88-95): out = lateral + nearest_upsample(top).  fp16 rows of C=256, warp per pixel.
 __global__ void __launch_bounds__(256) upsample_add_kernel(const __half* __restrict__ lateral, const __half* __restrict__ top,
                                                            int B, int H, int W, int Hs, int Ws, int C,
@@ -368,8 +413,16 @@ extern "C" int mqdet_patch_merge_ln(const float* x, int64_t B, int64_t H, int64_
                                     const float* beta, float eps, void* out, void* stream) {
   MQ_REQUIRE(x && gamma && beta && out, "patch_merge_ln: null pointer");
   const long rows = B * ((H + 1) / 2) * ((W + 1) / 2);
-  patch_merge_ln_kernel<<<cdiv(rows, 8), 256, 0, (cudaStream_t)stream>>>(x, (int)B, (int)H, (int)W, (int)C, gamma, beta, eps,
-                                                                        (__half*)out);
+  const bool al = (((uintptr_t)x | (uintptr_t)gamma | (uintptr_t)beta) & 15) == 0 && ((uintptr_t)out & 7) == 0;
+  cudaStream_t st = (cudaStream_t)stream;
+#define MQ_PM(K4)                                                                                                             \
+  patch_merge_ln_vec_kernel<K4><<<cdiv(rows, 8), 256, 0, st>>>(x, (int)B, (int)H, (int)W, gamma, beta, eps, (__half*)out)
+  if (al && C == 96) MQ_PM(3);
+  else if (al && C == 192) MQ_PM(6);
+  else if (al && C == 384) MQ_PM(12);
+  else
+    patch_merge_ln_kernel<<<cdiv(rows, 8), 256, 0, st>>>(x, (int)B, (int)H, (int)W, (int)C, gamma, beta, eps, (__half*)out);
+#undef MQ_PM
   return check_launch("patch_merge_ln_kernel");
 }
 

@@ -11,7 +11,9 @@ images + one prompt), same outputs (``list[BoxList]`` per batch), but
   * the host->device copy of batch s+1 (pinned memory -> a second device buffer, on a copy stream) overlaps the replay of
     batch s; the packed fixed-shape result ``[B, max_out + 1, 6]`` (detections + count row) is the ONE device->host copy;
   * with ``torch.distributed`` initialised, the ONE collective of the data path (all-gather of the packed result over
-    NCCL / NVLink) is captured inside the graph as well.
+    NCCL / NVLink) and the device->host copy run on a separate RESULT stream behind the forward: the next replay starts
+    without waiting for the slowest rank to reach the collective, so ranks may drift by one step instead of meeting at a
+    barrier every step (the gather of step s only has to finish before the forward of step s+2 reuses its buffers).
 
 Nothing here computes: it is stream / graph / buffer plumbing around ``GeneralizedVLRCNN_New.forward_device``.
 """
@@ -44,14 +46,20 @@ class InferenceEngine:
         self.max_out = model.max_out()
         self.host = [torch.empty((self.world * self.B, self.max_out + 1, 6), dtype=torch.float32).pin_memory() for _ in range(2)]
         self.d2h_done = [torch.cuda.Event(), torch.cuda.Event()]
+        # result stream: all-gather (N > 1) + device->host copy of step s while the main stream already runs step s+1
+        self.result_stream = torch.cuda.Stream(device=self.dev)
+        self.res_done = [torch.cuda.Event(), torch.cuda.Event()]  # gather / D2H that read outs[k]["packed"] finished
+        self.gathered = [torch.empty((self.world * self.B, self.max_out + 1, 6), dtype=torch.float32, device=self.dev)
+                         if self.world > 1 else None for _ in range(2)]
         main = torch.cuda.current_stream(self.dev)
-        for ev in self.fw_done:
+        for ev in self.fw_done + self.res_done:
             ev.record(main)
         # warm-up on the real buffers: fills every per-prompt / per-shape cache (token ids, selected queries, index tables,
         # level tables, fp16 weight copies, tensor maps, shared-memory opt-ins) so that the capture sees launches only
         for _ in range(max(1, warmup)):
             for k in range(2):
-                self._forward(k)
+                self.outs[k] = self._forward(k)
+                self._collect(k, to_host=False)
         torch.cuda.synchronize(self.dev)
         self.use_graph = bool(use_graph)
         if self.use_graph:
@@ -66,24 +74,39 @@ class InferenceEngine:
 
     def _forward(self, k):
         out = self.model.forward_device(ImageList(self.stage[k], self.image_sizes), self.captions, self.positive_map)
-        res = out["det_packed"]
-        if self.world > 1:
-            res = parallel.all_gather_packed(res)   # the ONE collective of the data path
-        return {"packed": res, "raw": out}
+        return {"packed": out["det_packed"], "raw": out}
 
-    # -- one step on staging buffer k: (graph replay | eager forward) -> async D2H of the packed result ------------------
-    def _launch(self, k):
+    def _collect(self, k, to_host=True):
+        """On the result stream, behind the forward of slot k: the ONE collective of the data path (N > 1), then the ONE
+        device->host copy."""
+        main = torch.cuda.current_stream(self.dev)
+        self.fw_done[k].record(main)
+        rs = self.result_stream
+        with torch.cuda.stream(rs):
+            rs.wait_event(self.fw_done[k])
+            res = self.outs[k]["packed"]
+            if self.world > 1:
+                res = parallel.all_gather_packed(res, out=self.gathered[k])
+            if to_host:
+                self.host[k].copy_(res, non_blocking=True)
+                self.d2h_done[k].record(rs)
+            self.res_done[k].record(rs)
+        return res
+
+    # -- one step on staging buffer k: (graph replay | eager forward) -> [all-gather ->] async D2H of the packed result ----
+    def _step(self, k, to_host):
         main = torch.cuda.current_stream(self.dev)
         main.wait_event(self.up_done[k])
+        main.wait_event(self.res_done[k])   # the previous result of this slot has been gathered / copied out
         if self.use_graph:
             self.graphs[k].replay()
-            o = self.outs[k]
         else:
-            o = self._forward(k)
-        self.fw_done[k].record(main)
-        self.host[k].copy_(o["packed"], non_blocking=True)
-        self.d2h_done[k].record(main)
-        return o
+            self.outs[k] = self._forward(k)
+        self._collect(k, to_host)
+        return self.outs[k]
+
+    def _launch(self, k):
+        return self._step(k, True)
 
     def _upload(self, k, images_host):
         with torch.cuda.stream(self.copy_stream):
@@ -92,20 +115,17 @@ class InferenceEngine:
             self.up_done[k].record(self.copy_stream)
 
     def device_step(self, images_dev=None, k=0):
-        """Device-resident step (bench `value`): optional device->device refresh of the input, then one replay; no host
-        traffic, no synchronisation.  Returns the device-side result dict."""
+        """Device-resident step (bench `value`): optional device->device refresh of the input, then one replay and (N > 1)
+        the all-gather on the result stream; no host traffic, no synchronisation.  Returns the device-side result dict
+        (``gathered`` = the rank-major result of all ranks, valid once the result stream has caught up)."""
         if images_dev is not None and images_dev.data_ptr() != self.stage[k].data_ptr():
             self.stage[k].copy_(images_dev, non_blocking=True)
-        main = torch.cuda.current_stream(self.dev)
-        self.up_done[k].record(main)
-        if self.use_graph:
-            self.graphs[k].replay()
-            return self.outs[k]
-        return self._forward(k)
+        self.up_done[k].record(torch.cuda.current_stream(self.dev))
+        o = self._step(k, False)
+        return {"packed": o["packed"], "raw": o["raw"], "gathered": self.gathered[k]}
 
     def close(self):
-        """Drop the captured graphs (and the NCCL work they hold) before the process group is destroyed: a communicator that
-        still has captured collectives alive does not tear down."""
+        """Drain both streams and drop the captured graphs (call before destroying the process group)."""
         torch.cuda.synchronize(self.dev)
         for g in self.graphs:
             if g is not None:

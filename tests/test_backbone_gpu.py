@@ -115,6 +115,24 @@ def test_swin_fpn_vs_oracle_and_golden(dev):
     assert not bad, bad
 
 
+@pytest.mark.parametrize("C,H,W", [(96, 13, 10), (192, 7, 9), (384, 5, 4), (64, 6, 7)])
+def test_patch_merge_ln(dev, C, H, W):
+    """PatchMerging gather + LayerNorm(4C) (swin_transformer.py:256-284) incl. the zero padding of odd H / W; C = 96 / 192 /
+    384 take the vectorised register-cached kernel, other widths the generic one."""
+    from mqdet_b200 import ops
+    g = torch.Generator().manual_seed(C + H)
+    B = 2
+    x = torch.randn(B, H * W, C, generator=g) * 1.5 + 0.3
+    gamma, beta = torch.randn(4 * C, generator=g), torch.randn(4 * C, generator=g)
+    xi = x.view(B, H, W, C)
+    xi = torch.nn.functional.pad(xi, (0, 0, 0, W % 2, 0, H % 2))
+    cat = torch.cat([xi[:, 0::2, 0::2], xi[:, 1::2, 0::2], xi[:, 0::2, 1::2], xi[:, 1::2, 1::2]], -1)
+    ref = torch.nn.functional.layer_norm(cat, (4 * C,), gamma, beta, 1e-5).reshape(-1, 4 * C)
+    out, H2, W2 = ops.patch_merge_ln(x.to(dev).contiguous(), B, H, W, gamma.to(dev), beta.to(dev), 1e-5)
+    assert (H2, W2) == ((H + 1) // 2, (W + 1) // 2)
+    assert_close(out, ref, 1e-3, "patch_merge_ln")
+
+
 def test_avgpool_levels(dev):
     from mqdet_b200 import ops
     g = torch.Generator().manual_seed(4)

@@ -26,6 +26,20 @@ def _inputs(seed, B, ncls, K=5, T=256, D=768, ragged=False):
     return x, vision, mask
 
 
+@pytest.mark.parametrize("D,rows,dt", [(96, 4099, torch.float32), (192, 4097, torch.float32), (96, 5003, torch.float16),
+                                       (192, 4100, torch.float16)])
+def test_layernorm_narrow_rows(dev, D, rows, dt):
+    """Swin stage 1 / 2 widths take the several-rows-per-warp kernel (rows >= 4096): ragged row counts, both input types."""
+    from mqdet_b200 import ops
+    g = torch.Generator().manual_seed(D + rows)
+    x = (torch.randn(rows, D, generator=g) * 2.0 + 0.7).to(dt)
+    w, b = torch.randn(D, generator=g), torch.randn(D, generator=g)
+    ref = torch.nn.functional.layer_norm(x.float(), (D,), w, b, 1e-5)
+    o16, o32 = ops.layernorm(x.to(dev), w.to(dev), b.to(dev), 1e-5, out16=True, out32=True)
+    assert_close(o32, ref, 1e-5, "narrow layernorm fp32 out")
+    assert_close(o16, ref, 1e-3, "narrow layernorm fp16 out")
+
+
 def test_layernorm_and_softmax(dev):
     from mqdet_b200 import ops
     g = torch.Generator().manual_seed(3)

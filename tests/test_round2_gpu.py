@@ -235,13 +235,27 @@ def test_detections_per_img_300_and_packed_result(dev):
     assert torch.equal(num_u.cpu(), out["num"].cpu()) and torch.equal(det_u, out["det"])
     res = model(il, captions=caps, positive_map=pmap)
     for b in range(B):
+        # (1) exact: NMS + top-300 of the DEVICE candidates == the oracle's select_over_all_levels on those very candidates
+        n = int(out["cand_totals"][b])
+        gb, gs, gl = out["cand_boxes"][b, :n].cpu(), out["cand_scores"][b, :n].cpu(), out["cand_labels"][b, :n].cpu()
+        keep_ref = restate.select_over_all_levels(gb, gs, gl, 0.6, 300)
+        num = int(out["num"][b])
+        assert num == keep_ref.numel() and torch.equal(out["keep"][b, :num].cpu(), keep_ref)
+        assert torch.equal(out["det"][b, :num, :4].cpu(), gb[keep_ref]) and torch.equal(out["det"][b, :num, 4].cpu(), gs[keep_ref])
+        assert len(res[b]) == num and torch.equal(res[b].bbox.cpu(), gb[keep_ref])
+        # (2) free-running against the oracle's own forward.  The synthetic weights give every location ten near-identical
+        # class scores and many overlapping boxes within 1e-3 of each other, so the ~1e-3 score noise of the fp16 tower flips
+        # NMS winners (ten detections per flip, measured 3-7 flips per image: tools/dbg_match.py) and moves the top-300 cut;
+        # a flipped winner still overlaps the oracle's winner by more than the NMS threshold.  Hence: same label, score
+        # within 2e-2, IoU > 0.5 for >= 85 % — the strict IoU > 0.9 match is asserted on the 100-detection cases
+        # (test_detector_forward, test_detector_vs_reference_golden) where those ties do not dominate.
         rb, rs, rl = ref["detections"][b]
         assert rb.shape[0] > 128, "the case must keep more than the old hard 128-row limit"
         assert abs(len(res[b]) - rb.shape[0]) <= 8, (len(res[b]), rb.shape[0])
         iou = _iou(rb, res[b].bbox.cpu())
         same = rl[:, None] == res[b].get_field("labels").cpu()[None]
-        matched = ((iou > 0.9) & same & ((rs[:, None] - res[b].get_field("scores").cpu()[None]).abs() < 2e-2)).any(1)
-        assert matched.float().mean().item() >= 0.85
+        matched = ((iou > 0.5) & same & ((rs[:, None] - res[b].get_field("scores").cpu()[None]).abs() < 2e-2)).any(1)
+        assert matched.float().mean().item() >= 0.85, matched.float().mean().item()
     # a too-small result buffer is an error, never a silent truncation
     from mqdet_b200._lib import MqdetError
     small = model.forward_device(il, caps, pmap, max_out=64)
