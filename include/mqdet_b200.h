@@ -355,6 +355,25 @@ int mqdet_ms_deform_attn(const void* value, const float* proj, int64_t proj_ld, 
                          const int32_t* level_hw, int64_t nlev, int64_t B, int64_t Q, int64_t heads, int64_t head_dim,
                          int64_t points, void* out, int out_dtype, void* stream);
 
+/* ---- GroundingDINO variant, small device ops --------------------------------------------------
+ * STABLE_SOFTMAX_2D of BiMultiHeadAttention (groundingdino_new/models/GroundingDINO/fuse_modules.py:177-187): the global
+ * maximum of the score tensor is subtracted before the +-5e4 clamps.
+ *   mqdet_global_max_f32 : out[0] = max_i x[i] (two deterministic launches; workspace: mqdet_global_max_workspace_floats())
+ *   mqdet_shift_clamp_f32: x[i] = clamp(x[i] - *shift, lo, hi) in place, shift a DEVICE scalar (no host sync) */
+int64_t mqdet_global_max_workspace_floats(void);
+int mqdet_global_max_f32(const float* x, int64_t n, float* out, float* workspace, void* stream);
+int mqdet_shift_clamp_f32(float* x, int64_t n, const float* shift, float lo, float hi, void* stream);
+/* Two-stage query selection (transformer.py:288-318): topk_logits = enc_outputs_class.max(-1)[0]; torch.topk(.., 900, dim=1);
+ * torch.gather of the selected rows.
+ *   mqdet_row_max_f32   : out[r] = max_j x[r*ld + j], j < D
+ *   mqdet_topk_desc     : idx_out[b][0..k) = indices of the k largest of keys[b][0..n), by (value descending, index ascending);
+ *                         k <= min(n, 1024); one CTA per image (radix select + ordered tie fill + bitonic sort)
+ *   mqdet_gather_rows_f32: dst[b][i][0..D) = act(src[b][idx[b][i]][0..D)), act = identity (sigmoid == 0) or the logistic sigmoid */
+int mqdet_row_max_f32(const float* x, int64_t rows, int64_t D, int64_t ld, float* out, void* stream);
+int mqdet_topk_desc(const float* keys, int64_t B, int64_t n, int64_t k, int64_t* idx_out, void* stream);
+int mqdet_gather_rows_f32(const float* src, const int64_t* idx, int64_t B, int64_t rows_src, int64_t k, int64_t D, int sigmoid,
+                          float* dst, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

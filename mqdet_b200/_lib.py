@@ -74,6 +74,12 @@ SIGNATURES = {
     "mqdet_contrastive_mask": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64, c_void_p]),
     "mqdet_argsort_desc": (c_int, [c_void_p, c_int64, c_void_p, c_void_p]),
     "mqdet_ml_nms_workspace_bytes": (c_int64, [c_int64]),
+    "mqdet_global_max_workspace_floats": (c_int64, []),
+    "mqdet_global_max_f32": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
+    "mqdet_shift_clamp_f32": (c_int, [c_void_p, c_int64, c_void_p, c_float, c_float, c_void_p]),
+    "mqdet_row_max_f32": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_void_p]),
+    "mqdet_topk_desc": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_void_p]),
+    "mqdet_gather_rows_f32": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64, c_int, c_void_p, c_void_p]),
     "mqdet_dcn_conv": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int64, c_int64, c_void_p, c_void_p,
                                c_void_p, c_void_p, c_void_p]),
     "mqdet_dcn_cols": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int64, c_int, c_void_p,

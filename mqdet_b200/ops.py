@@ -168,6 +168,70 @@ def softmax_rows(x, *, n=None, scale=1.0, colmask=None, rows_per_batch=0, mask_v
     return out
 
 
+def global_max(x32):
+    """max over ALL elements of a contiguous fp32 tensor -> device scalar [1] (no host sync)."""
+    global launch_count
+    _need_cuda(x32)
+    if x32.dtype != torch.float32 or not x32.is_contiguous():
+        raise _lib.MqdetError("global_max: contiguous fp32 tensor required")
+    out = torch.empty((1,), dtype=torch.float32, device=x32.device)
+    ws = torch.empty((int(load().mqdet_global_max_workspace_floats()),), dtype=torch.float32, device=x32.device)
+    check(load().mqdet_global_max_f32(_ptr(x32), x32.numel(), _ptr(out), _ptr(ws), _stream()), "global_max")
+    launch_count += 2
+    return out
+
+
+def shift_clamp_(x32, shift, lo, hi):
+    """x = clamp(x - shift[0], lo, hi) in place over the whole (contiguous fp32) buffer; ``shift`` is a device scalar."""
+    global launch_count
+    _need_cuda(x32, shift)
+    if x32.dtype != torch.float32 or not x32.is_contiguous():
+        raise _lib.MqdetError("shift_clamp_: contiguous fp32 tensor required")
+    check(load().mqdet_shift_clamp_f32(_ptr(x32), x32.numel(), _ptr(shift), float(lo), float(hi), _stream()), "shift_clamp")
+    launch_count += 1
+    return x32
+
+
+def row_max(x32):
+    """max over the last dim of a contiguous fp32 [..., D] tensor -> fp32 [...]."""
+    global launch_count
+    _need_cuda(x32)
+    D = x32.shape[-1]
+    x2 = x32.reshape(-1, D)
+    out = torch.empty(x32.shape[:-1], dtype=torch.float32, device=x32.device)
+    check(load().mqdet_row_max_f32(_ptr(x2), x2.shape[0], D, x2.stride(0), _ptr(out), _stream()), "row_max")
+    launch_count += 1
+    return out
+
+
+def topk_desc(keys32, k):
+    """indices [B, k] (int64) of the k largest entries of each row of fp32 keys [B, n], by (value descending, index ascending)."""
+    global launch_count
+    _need_cuda(keys32)
+    if keys32.dtype != torch.float32 or keys32.dim() != 2 or not keys32.is_contiguous():
+        raise _lib.MqdetError("topk_desc: contiguous fp32 [B, n] required")
+    B, n = keys32.shape
+    idx = torch.empty((B, k), dtype=torch.int64, device=keys32.device)
+    check(load().mqdet_topk_desc(_ptr(keys32), B, n, int(k), _ptr(idx), _stream()), "topk_desc")
+    launch_count += 1
+    return idx
+
+
+def gather_rows(src32, idx, sigmoid=False):
+    """src32 [B, R, D] fp32, idx [B, k] int64 -> [B, k, D] (torch.gather along dim 1 with the index repeated over D), optionally
+    through the logistic sigmoid."""
+    global launch_count
+    _need_cuda(src32, idx)
+    if src32.dtype != torch.float32 or src32.dim() != 3 or not src32.is_contiguous() or idx.dtype != torch.int64 or not idx.is_contiguous():
+        raise _lib.MqdetError("gather_rows: contiguous fp32 [B, R, D] and int64 [B, k] required")
+    B, R, D = src32.shape
+    k = idx.shape[1]
+    out = torch.empty((B, k, D), dtype=torch.float32, device=src32.device)
+    check(load().mqdet_gather_rows_f32(_ptr(src32), _ptr(idx), B, R, k, D, int(bool(sigmoid)), _ptr(out), _stream()), "gather_rows")
+    launch_count += 1
+    return out
+
+
 def l2_normalize(x32, w=None, b0=None, eps=1e-12):
     """e = F.normalize(x, p=2, dim=-1) of a contiguous fp32 tensor -> (e fp16, e fp32, dot) with
     dot[r] = e[r, :] . w + b0 when ``w`` is given (the token bias of the dot-product head, vldyhead.py:818)."""

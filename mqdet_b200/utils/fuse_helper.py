@@ -40,7 +40,11 @@ def _split_levels(v, sizes):
 
 
 class BiMultiHeadAttention(nn.Module):
-    def __init__(self, v_dim, l_dim, embed_dim, num_heads, dropout=0.1, cfg=None):
+    def __init__(self, v_dim, l_dim, embed_dim, num_heads, dropout=0.1, cfg=None, *, stable_softmax_2d=None,
+                 clamp_min_for_underflow=None, clamp_max_for_overflow=None, mask_fill=(-9e15, 1.0)):
+        """``cfg`` supplies the three score flags (MODEL.DYHEAD.FUSE_CONFIG) unless they are given explicitly — the
+        GroundingDINO variant (modeling/groundingdino/fuse_modules.py) hard-codes them.  ``mask_fill`` = (value added at padded
+        text tokens, value added at kept ones): fuse_helper.py:270-283 adds -9e15 / +1, GroundingDINO fills -inf / 0."""
         super().__init__()
         self.embed_dim = embed_dim
         self.num_heads = num_heads
@@ -55,18 +59,20 @@ class BiMultiHeadAttention(nn.Module):
         self.values_l_proj = nn.Linear(l_dim, embed_dim)
         self.out_v_proj = nn.Linear(embed_dim, v_dim)
         self.out_l_proj = nn.Linear(embed_dim, l_dim)
-        fc = cfg.MODEL.DYHEAD.FUSE_CONFIG
+        fc = cfg.MODEL.DYHEAD.FUSE_CONFIG if cfg is not None else None
         self.fused_text_side = True  # False: column-softmax + GEMM path (kept for A/B checks, tests/test_fusion_gpu.py)
         # "fused" (default): the product path; "f16": the score matrix A = q.k^T stored in fp16 (round-1 path, kept for
         # A/B runs); "f32": diagnostic variant that keeps the
         # scores in fp32 until both softmaxes have been taken, like the reference (fuse_helper.py:240-291) — twice the
         # traffic, used by tests/test_parity_experiment_gpu.py to attribute the tower's end-to-end error
         self.score_precision = "fused"
-        self.stable_softmax_2d = fc.STABLE_SOFTMAX_2D
-        self.clamp_min_for_underflow = fc.CLAMP_MIN_FOR_UNDERFLOW
-        self.clamp_max_for_overflow = fc.CLAMP_MAX_FOR_OVERFLOW
-        if self.stable_softmax_2d:
-            raise NotImplementedError("STABLE_SOFTMAX_2D (GroundingDINO fuse_modules.py) is SURVEY.md §8f 'next'")
+        self.stable_softmax_2d = bool(fc.STABLE_SOFTMAX_2D if stable_softmax_2d is None else stable_softmax_2d)
+        self.clamp_min_for_underflow = bool(fc.CLAMP_MIN_FOR_UNDERFLOW if clamp_min_for_underflow is None else clamp_min_for_underflow)
+        self.clamp_max_for_overflow = bool(fc.CLAMP_MAX_FOR_OVERFLOW if clamp_max_for_overflow is None else clamp_max_for_overflow)
+        self.mask_fill = (float(mask_fill[0]), float(mask_fill[1]))
+        # STABLE_SOFTMAX_2D subtracts the GLOBAL maximum of the score tensor before the clamps (fuse_helper.py:240-242,
+        # GroundingDINO fuse_modules.py:177-178): that needs the whole score tensor before either softmax, so it takes the
+        # explicit fp32-score path (global_max + shift_clamp kernels) instead of the fused one
         self._reset_parameters()
 
     def _reset_parameters(self):
@@ -75,9 +81,10 @@ class BiMultiHeadAttention(nn.Module):
             m.bias.data.fill_(0)
 
     @torch.no_grad()
-    def _attend(self, vn16, ln16, mask_l, v_epilogue=None, l_epilogue=None):
-        """vn16 [B,N,256] fp16, ln16 [B,T,768] fp16 (already layer-normed), mask_l [B,T] -> (dv, dl).
-        ``*_epilogue`` = dict(gate=gamma, residual=normed input) fuses the layer-scale + residual into the out-proj."""
+    def _attend(self, vn16, ln16, mask_l, v_epilogue=None, l_epilogue=None, mask_v=None):
+        """vn16 [B,N,256] fp16, ln16 [B,T,768] fp16 (already layer-normed), mask_l [B,T] (1 keep / 0 padding) -> (dv, dl).
+        ``*_epilogue`` = dict(gate=gamma, residual=normed input) fuses the layer-scale + residual into the out-proj.
+        ``mask_v`` [B,N] (1 keep / 0 padding; GroundingDINO's attention_mask_v) only on the explicit fp32-score path."""
         B, N, Cv = vn16.shape
         T = ln16.shape[1]
         H, d, E = self.num_heads, self.head_dim, self.embed_dim
@@ -85,7 +92,8 @@ class BiMultiHeadAttention(nn.Module):
         Np = (N + 7) // 8 * 8
         clamp = 50000.0 if (self.clamp_min_for_underflow or self.clamp_max_for_overflow) else 0.0
         k = ops.gemm(ln16.view(B * T, -1), w16(self.l_proj.weight), bias=f32(self.l_proj.bias)).view(B, T, H, d)
-        if self.score_precision == "fused" and d == 256 and Cv == 256 and T % 8 == 0 and T <= 256 and H <= 8:
+        explicit = self.stable_softmax_2d or mask_v is not None
+        if not explicit and self.score_precision == "fused" and d == 256 and Cv == 256 and T % 8 == 0 and T <= 256 and H <= 8:
             return self._attend_fused(vn16, ln16, k, mask_l, clamp, v_epilogue, l_epilogue)
         q = ops.gemm(vn16.view(B * N, Cv), w16(self.v_proj.weight), bias=f32(self.v_proj.bias), alpha=self.scale,
                      scale_after_bias=True).view(B, N, H, d)
@@ -96,9 +104,9 @@ class BiMultiHeadAttention(nn.Module):
         vlT = ops.gemm(w16(self.values_l_proj.weight), ln16, bias=f32(self.values_l_proj.bias), bias_mode=VEC_PER_ROW)
 
         qh, kh = q.permute(0, 2, 1, 3), k.permute(0, 2, 1, 3)
-        if self.score_precision == "f32":
-            return self._finish(*self._attend_f32_scores(qh, kh, vvT, vlT, mask_l, clamp, B, N, T, Np), v_epilogue, l_epilogue,
-                                B, N, T, Cv)
+        if self.score_precision == "f32" or explicit:
+            return self._finish(*self._attend_f32_scores(qh, kh, vvT, vlT, mask_l, clamp, B, N, T, Np, mask_v), v_epilogue,
+                                l_epilogue, B, N, T, Cv)
         # scores A = clamp(Q_h K_h^T)  [B,H,N,T]  (ONE product serves both directions)
         A = torch.empty((B, H, N, T), dtype=torch.float16, device=dev)
         ops.gemm(qh, kh, out=A, clamp=clamp)
@@ -197,18 +205,33 @@ class BiMultiHeadAttention(nn.Module):
                       residual=le["residual"].view(B * T, -1) if le else None)
         return dl.view(B, T, -1)
 
-    def _attend_f32_scores(self, qh, kh, vvT, vlT, mask_l, clamp, B, N, T, Np):
-        """Diagnostic: both score matrices in fp32 (A and its transpose as two products), softmaxes on the fp32 values."""
+    def _attend_f32_scores(self, qh, kh, vvT, vlT, mask_l, clamp, B, N, T, Np, mask_v=None):
+        """Both score matrices in fp32 (A and its transpose as two products), softmaxes on the fp32 values: the diagnostic
+        variant of the GLIP path and THE path of STABLE_SOFTMAX_2D / an image-token mask (GroundingDINO)."""
         H, d = self.num_heads, self.head_dim
         dev = qh.device
         cm = mask_l.float().contiguous() if mask_l is not None else None
+        stable = self.stable_softmax_2d
+        lim = clamp if clamp > 0 else float("inf")
         A32 = torch.empty((B, H, N, T), dtype=torch.float32, device=dev)
-        ops.gemm(qh, kh, out=A32, clamp=clamp)
-        Pv = ops.softmax_rows(A32, colmask=cm, rows_per_batch=H * N, mask_value=-9e15, keep_add=1.0)
+        ops.gemm(qh, kh, out=A32, clamp=0.0 if stable else clamp)
+        if stable:  # attn_weights - attn_weights.max(), then the clamps; the maximum stays on the device
+            gmax = ops.global_max(A32)
+            ops.shift_clamp_(A32, gmax, -lim, lim)
+        Pv = ops.softmax_rows(A32, colmask=cm, rows_per_batch=H * N, mask_value=self.mask_fill[0], keep_add=self.mask_fill[1])
         del A32
         AT32 = torch.empty((B, H, T, Np), dtype=torch.float32, device=dev)
-        ops.gemm(kh, qh, out=AT32[..., :N], clamp=clamp)
-        Pl = ops.softmax_rows(AT32, n=N)
+        if Np != N:
+            AT32[..., N:].zero_()
+        ops.gemm(kh, qh, out=AT32[..., :N], clamp=0.0 if stable else clamp)
+        if stable:
+            ops.shift_clamp_(AT32, gmax, -lim, lim)
+        if mask_v is not None:  # padded image tokens leave the text side's softmax (fuse_modules.py:201-206)
+            mv = torch.zeros((B, Np), dtype=torch.float32, device=dev)
+            mv[:, :N] = mask_v.float()
+            Pl = ops.softmax_rows(AT32, n=N, colmask=mv, rows_per_batch=H * T, mask_value=float("-inf"), keep_add=0.0)
+        else:
+            Pl = ops.softmax_rows(AT32, n=N)
         del AT32
         ov = torch.empty((B, N, H, d), dtype=torch.float16, device=dev)
         ops.gemm(Pv, vlT.view(B, H, d, T), out=ov.permute(0, 2, 1, 3))
@@ -221,7 +244,7 @@ class BiMultiHeadAttention(nn.Module):
         ve = v_epilogue or {}
         le = l_epilogue or {}
         dv = ops.gemm(ov.view(B * N, E), w16(self.out_v_proj.weight), bias=f32(self.out_v_proj.bias),
-                      gate=ve.get("gate"), gate_mode=VEC_PER_COL if ve else 0,
+                      out_dtype=ve.get("out_dtype", torch.float16), gate=ve.get("gate"), gate_mode=VEC_PER_COL if ve else 0,
                       residual=ve["residual"].view(B * N, Cv) if ve else None)
         dl = ops.gemm(ol.view(B * T, E), w16(self.out_l_proj.weight), bias=f32(self.out_l_proj.bias),
                       out_dtype=torch.float32, gate=le.get("gate"), gate_mode=VEC_PER_COL if le else 0,

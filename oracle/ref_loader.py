@@ -155,6 +155,15 @@ def gdino_ms_deform_attn():
     return _cache["msda"]
 
 
+def gdino_fuse_modules():
+    """groundingdino_new/models/GroundingDINO/fuse_modules.py (BiAttentionBlock / BiMultiHeadAttention; torch + the timm
+    DropPath shim)."""
+    if "gdfuse" not in _cache:
+        _install_shims()
+        _cache["gdfuse"] = _load_file("ref_gdino_fuse", "groundingdino_new/models/GroundingDINO/fuse_modules.py")
+    return _cache["gdfuse"]
+
+
 def query_selector():
     """maskrcnn_benchmark/modeling/query_selector/query_selector.py (pure torch / numpy)."""
     if "qs" not in _cache:

@@ -224,6 +224,55 @@ def bi_attention(v, l, mask_l, sd, p="", heads=8, embed=2048):
     return vn + sd[p + "gamma_v"] * dv, ln + sd[p + "gamma_l"] * dl
 
 
+def gdino_bi_attention(v, l, sd, p="", heads=4, embed=1024, mask_v=None, mask_l=None):
+    """GroundingDINO's BiAttentionBlock.forward (groundingdino_new/models/GroundingDINO/fuse_modules.py:286-296) +
+    BiMultiHeadAttention.forward (:147-254), eval: STABLE_SOFTMAX_2D (the global maximum of the whole score tensor is
+    subtracted before the clamps, :177-178), boolean masks (True = padding) filled with -inf.
+    v [B,N,v_dim], l [B,T,l_dim], mask_v [B,N] / mask_l [B,T] bool or None.  Returns (v', l')."""
+    B, N, _ = v.shape
+    T = l.shape[1]
+    d = embed // heads
+    vn = _ln(v, sd, p + "layer_norm_v")
+    ln = _ln(l, sd, p + "layer_norm_l")
+    q = _lin(vn, sd, p + "attn.v_proj") * (d ** -0.5)
+    k = _lin(ln, sd, p + "attn.l_proj")
+    vv = _lin(vn, sd, p + "attn.values_v_proj")
+    vl = _lin(ln, sd, p + "attn.values_l_proj")
+
+    def sh(t, n):
+        return t.view(B, n, heads, d).transpose(1, 2)  # [B,h,n,d]
+
+    q, k, vv, vl = sh(q, N), sh(k, T), sh(vv, N), sh(vl, T)
+    A = q @ k.transpose(-1, -2)                                   # [B,h,N,T]
+    A = (A - A.max()).clamp(min=-50000, max=50000)                # :177-187
+    At = A.transpose(-1, -2)
+    Al = (At - At.max(dim=-1, keepdim=True)[0]).clamp(min=-50000, max=50000)
+    if mask_v is not None:
+        Al = Al.masked_fill(mask_v[:, None, None, :], float("-inf"))
+    Al = Al.softmax(dim=-1)
+    if mask_l is not None:
+        A = A.masked_fill(mask_l[:, None, None, :], float("-inf"))
+    Av = A.softmax(dim=-1)
+    ov = (Av @ vl).transpose(1, 2).reshape(B, N, embed)
+    ol = (Al @ vv).transpose(1, 2).reshape(B, T, embed)
+    dv = _lin(ov, sd, p + "attn.out_v_proj")
+    dl = _lin(ol, sd, p + "attn.out_l_proj")
+    return vn + sd[p + "gamma_v"] * dv, ln + sd[p + "gamma_l"] * dl
+
+
+def gdino_two_stage_select(class_logits, coord_unsel, output_proposals, output_memory, k=900):
+    """Two-stage query selection of the GroundingDINO transformer (transformer.py:297-318): the k proposals with the largest
+    max-over-tokens class logit; gathers of their boxes (unsigmoid), anchor proposals (sigmoid) and memory rows.
+    class_logits [B,Q,T] (may hold -inf on padded tokens), coord_unsel / output_proposals [B,Q,4], output_memory [B,Q,C]."""
+    topk_logits = class_logits.max(-1)[0]
+    idx = torch.topk(topk_logits, k, dim=1)[1]
+    g4 = idx.unsqueeze(-1).repeat(1, 1, 4)
+    refpoint = torch.gather(coord_unsel, 1, g4)
+    init_box = torch.gather(output_proposals, 1, g4).sigmoid()
+    tgt = torch.gather(output_memory, 1, idx.unsqueeze(-1).repeat(1, 1, output_memory.shape[-1]))
+    return {"topk_logits": topk_logits, "idx": idx, "refpoint_embed": refpoint, "init_box_proposal": init_box, "tgt": tgt}
+
+
 def dot_product_head(feat, hidden, sd, p=""):
     """VLDyHead.forward dot-product section (vldyhead.py:806-818,871-888): feat [B,N,256] (tower output, permuted
     and flattened), hidden [B,T,768] -> logits [B,N,T]."""

@@ -85,3 +85,75 @@ def test_ms_deform_attn_vs_oracle(dev, ref_dim, Q):
         if not batch_first:
             out = out.transpose(0, 1)
         assert_close(out, ref, 2e-3, f"MultiScaleDeformableAttention ref_dim={ref_dim} batch_first={batch_first}")
+
+
+def test_global_max_shift_clamp_row_max(dev):
+    """The three small ops of STABLE_SOFTMAX_2D / the two-stage selection, exactly against torch (sizes off the vector width)."""
+    from mqdet_b200 import ops
+    g = torch.Generator().manual_seed(31)
+    for n in (1, 7, 1024 * 1024 + 3):
+        x = (torch.randn(n, generator=g) * 1000).to(dev)
+        gm = ops.global_max(x)
+        assert gm.item() == x.max().item()
+        y = x.clone()
+        ops.shift_clamp_(y, gm, -500.0, 500.0)
+        assert torch.equal(y, (x - x.max()).clamp(-500.0, 500.0))
+    x = torch.randn(5003, 256, generator=g)
+    x[:, 200:] = float("-inf")
+    x[17] = float("-inf")
+    assert torch.equal(ops.row_max(x.to(dev)).cpu(), x.max(-1)[0])
+
+
+@pytest.mark.parametrize("masks", [False, True])
+def test_gdino_bi_attention_block(dev, masks):
+    """GroundingDINO BiAttentionBlock (fuse_modules.py:257-296; stable_softmax_2d, -inf boolean masks for text AND image tokens)
+    at the MQ-GroundingDINO-T encoder dimensions (256 / 256 / 1024, 4 heads), N not a multiple of 8."""
+    from mqdet_b200.modeling.groundingdino.fuse_modules import BiAttentionBlock
+    from oracle import restate, synth
+    from util import assert_close, load_sd
+    gen = synth.Gen(1410)
+    sd = synth.bi_attention_sd(gen, v_dim=256, l_dim=256, embed=1024)
+    B, N, T = 2, 1003, 64
+    v, l = gen.randn(B, N, 256), gen.randn(B, T, 256)
+    mask_v = mask_l = None
+    if masks:
+        mask_v = torch.zeros(B, N, dtype=torch.bool)
+        mask_v[1, -131:] = True
+        mask_l = torch.zeros(B, T, dtype=torch.bool)
+        mask_l[0, -9:] = True
+    ref_v, ref_l = restate.gdino_bi_attention(v, l, sd, mask_v=mask_v, mask_l=mask_l)
+    mod = load_sd(BiAttentionBlock(v_dim=256, l_dim=256, embed_dim=1024, num_heads=4), sd).to(dev).eval()
+    out_v, out_l = mod(v.to(dev), l.to(dev), attention_mask_v=None if mask_v is None else mask_v.to(dev),
+                       attention_mask_l=None if mask_l is None else mask_l.to(dev))
+    assert out_v.dtype == torch.float32 and out_l.dtype == torch.float32
+    assert_close(out_v, ref_v, 1e-3, "GroundingDINO BiAttentionBlock: image side")
+    assert_close(out_l, ref_l, 1e-3, "GroundingDINO BiAttentionBlock: text side")
+
+
+def test_gdino_two_stage_select(dev):
+    """Two-stage query selection (transformer.py:297-318) at the encoder size of config 4 (22323 positions, 256 text tokens with
+    -inf padding, 900 queries): indices identical to torch.topk, gathers exact; ties resolve towards the lower index."""
+    from mqdet_b200.modeling.groundingdino.two_stage import select_queries
+    from oracle import restate
+    g = torch.Generator().manual_seed(77)
+    B, Q, T, C, k = 2, 22323, 256, 256, 900
+    logits = torch.randn(B, Q, T, generator=g) * 3.0
+    logits[:, :, 40:] = float("-inf")          # padded text tokens (ContrastiveEmbed fills -inf)
+    coord = torch.randn(B, Q, 4, generator=g)
+    prop = torch.randn(B, Q, 4, generator=g) * 2.0
+    mem = torch.randn(B, Q, C, generator=g)
+    ref = restate.gdino_two_stage_select(logits, coord, prop, mem, k)
+    out = select_queries(logits.to(dev), coord.to(dev), prop.to(dev), mem.to(dev), k)
+    assert torch.equal(out["topk_logits"].cpu(), ref["topk_logits"])
+    assert torch.equal(out["topk_proposals"].cpu(), ref["idx"])
+    assert torch.equal(out["refpoint_embed"].cpu(), ref["refpoint_embed"]) and torch.equal(out["tgt"].cpu(), ref["tgt"])
+    assert (out["init_box_proposal"].cpu() - ref["init_box_proposal"]).abs().max().item() <= 2e-7
+    # ties: equal keys come out in index order; k == n; a row of -inf
+    from mqdet_b200 import ops
+    keys = torch.zeros(3, 1500)
+    keys[1, 100:] = -1.0
+    keys[2] = float("-inf")
+    idx = ops.topk_desc(keys.to(dev), 1000).cpu()
+    assert torch.equal(idx[0], torch.arange(1000)) and torch.equal(idx[1], torch.arange(1000)) and torch.equal(idx[2], torch.arange(1000))
+    small = torch.tensor([[3.0, -1.0, 7.0, 7.0, 0.5]])
+    assert ops.topk_desc(small.to(dev), 5).cpu().tolist() == [[2, 3, 0, 4, 1]]

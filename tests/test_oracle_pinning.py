@@ -383,3 +383,42 @@ def test_ms_deform_attn_vs_reference(ref_dim):
         want = mod(query, value=value, key_padding_mask=mask, reference_points=ref_pts, spatial_shapes=ss, level_start_index=lsi)
         got = restate.ms_deform_attn(query, value, ref_pts, shapes, sd, key_padding_mask=mask)
     _close(got, want, 1e-5)
+
+
+@pytest.mark.parametrize("case", ["plain", "masks", "wide"])
+def test_gdino_bi_attention_vs_reference(case):
+    """GroundingDINO BiAttentionBlock (fuse_modules.py:99-297; v_dim = l_dim = 256, embed 1024, 4 heads): the oracle restatement
+    against the reference's own module — stable_softmax_2d (global maximum subtracted before the clamps), boolean -inf masks
+    on both sides, and ("wide") scores spread over more than 5e4 so that the shifted lower clamp is ACTIVE."""
+    import torch
+    from oracle import ref_loader as rl
+    from oracle import synth
+    gen = synth.Gen(1400)
+    sd = synth.bi_attention_sd(gen, v_dim=256, l_dim=256, embed=1024)
+    B, N, T = 2, 203, 24
+    v, l = gen.randn(B, N, 256), gen.randn(B, T, 256)
+    mask_v = mask_l = None
+    if case != "plain":
+        mask_v = torch.zeros(B, N, dtype=torch.bool)
+        mask_v[1, -31:] = True
+        mask_l = torch.zeros(B, T, dtype=torch.bool)
+        mask_l[0, -5:] = True
+    if case == "wide":
+        sd = dict(sd)
+        sd["attn.v_proj.weight"] = sd["attn.v_proj.weight"] * 400.0
+        sd["attn.l_proj.weight"] = sd["attn.l_proj.weight"] * 400.0
+    mod = rl.gdino_fuse_modules().BiAttentionBlock(v_dim=256, l_dim=256, embed_dim=1024, num_heads=4, dropout=0.1, drop_path=0.1)
+    mod.load_state_dict(sd, strict=True)
+    mod.eval()
+    with torch.no_grad():
+        want_v, want_l = mod(v, l, attention_mask_v=mask_v, attention_mask_l=mask_l)
+        got_v, got_l = restate.gdino_bi_attention(v, l, sd, mask_v=mask_v, mask_l=mask_l)
+    if case == "wide":  # the case must really exercise the shifted clamp
+        vn = torch.nn.functional.layer_norm(v, (256,), sd["layer_norm_v.weight"], sd["layer_norm_v.bias"])
+        ln = torch.nn.functional.layer_norm(l, (256,), sd["layer_norm_l.weight"], sd["layer_norm_l.bias"])
+        q = (vn @ sd["attn.v_proj.weight"].t() + sd["attn.v_proj.bias"]) / 16.0
+        k = ln @ sd["attn.l_proj.weight"].t() + sd["attn.l_proj.bias"]
+        A = torch.einsum("bnhd,bthd->bhnt", q.view(B, N, 4, 256), k.view(B, T, 4, 256))
+        assert (A - A.max()).min().item() < -50000.0
+    _close(got_v, want_v, 1e-5)
+    _close(got_l, want_l, 1e-5)
