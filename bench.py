@@ -466,13 +466,38 @@ def main():
         return model.forward_device(ImageList(img_dev, sizes), caps, pmap)
 
     prof = ops.GEMM_PROFILE = []
+    kprof = ops.KERNEL_PROFILE = []
     eager_step()
     torch.cuda.synchronize()
     ops.GEMM_PROFILE = None
+    ops.KERNEL_PROFILE = None
     g_ms = sum(a.elapsed_time(b) for a, b, _, _ in prof)
     g_flops = sum(f for _, _, f, _ in prof)
     pk = peaks()
     achieved = g_flops / (g_ms / 1e3) / 1e12 if g_ms > 0 else 0.0
+    # per tensor-core kernel: measured time against the roofline time of each launch, max(flops / tensor peak, bytes / HBM
+    # peak) with ALGORITHMIC flops and bytes — the family of GEMMs mixes tensor-bound and HBM-bound shapes, so one ratio against
+    # one peak misstates it
+    kern = {}
+    for e0, e1, name, fl, by in kprof:
+        t = e0.elapsed_time(e1)
+        k = kern.setdefault(name, {"launches": 0, "ms": 0.0, "flops": 0.0, "bytes": 0.0, "roof_ms": 0.0, "hbm_bound_ms": 0.0})
+        t_tensor, t_hbm = fl / (pk["tflops"] * 1e12) * 1e3, by / (pk["hbm_gbs"] * 1e9) * 1e3
+        k["launches"] += 1
+        k["ms"] += t
+        k["flops"] += fl
+        k["bytes"] += by
+        k["roof_ms"] += max(t_tensor, t_hbm)
+        if t_hbm > t_tensor:
+            k["hbm_bound_ms"] += t
+    kernels = []
+    for name, k in sorted(kern.items(), key=lambda kv: -kv[1]["ms"]):
+        kernels.append({"kernel": name, "launches": k["launches"], "ms_per_step": round(k["ms"], 3),
+                        "algorithmic_tflops": round(k["flops"] / (k["ms"] / 1e3) / 1e12, 1),
+                        "algorithmic_gbs": round(k["bytes"] / (k["ms"] / 1e3) / 1e9, 1),
+                        "tensor_frac": round(k["flops"] / (k["ms"] / 1e3) / 1e12 / pk["tflops"], 3),
+                        "roofline_frac": round(k["roof_ms"] / k["ms"], 3),
+                        "ms_in_hbm_bound_launches": round(k["hbm_bound_ms"], 3)})
     stages = stage_profile(model, eager_step, B, pk) if rank == 0 else None
 
     if rank == 0:
@@ -492,6 +517,9 @@ def main():
                          "kernel": "gemm_tcp_kernel (persistent tcgen05 GEMM, all shapes of one step)", "launches": len(prof),
                          "kernel_ms_per_step": g_ms, "kernel_share_of_step": g_ms / ms,
                          "algorithmic_tflop_per_step": g_flops / 1e12, "traffic_source": traffic_note()[1],
+                         "kernels": kernels, "kernels_note": "per tensor-core kernel, CUDA events around every launch of one eager "
+                                                             "step: roofline_frac = sum over launches of max(algorithmic flops / "
+                                                             "tensor peak, algorithmic bytes / HBM peak) / measured time",
                          "stages": stages},
             "e2e": {"value": world * B / (e2e_ms / 1e3), "unit": "images/s", "ms_per_step": e2e_ms, "wall_ms_per_step": e2e_wall_ms,
                     "h2d_bytes_per_step": img_host.numel() * 4, "d2h_bytes_per_step": engine.host[0].numel() * 4,

@@ -20,10 +20,10 @@
 //
 // HBM traffic per DyConv layer at B=8, 800x1344 (ncu): 245 MB read + 113 MB written (algorithmic: 92 MB of x, 3.5 MB of weights,
 // 138 MB of y) — against 1.24 GB written + 1.24 GB read for the materialised column matrix.  What bounds it now is the L2 -> SM
-// rate: per k-block an SM takes in the 32 KB weight tile plus ~48 KB of corner rows (64 KB at the measured 25 % L1 hit rate),
-// 6.5 GB per layer at ~11.7 TB/s (ncu lts__t_sectors) = 0.53 ms, 600 TFLOP/s.  Sharing the weight tile between the two CTAs
-// of a cluster by TMA multicast was measured and changes nothing (0.57 ms): the limit is what each SM can take in, not
-// what the L2 slices read.
+// rate: per k-block an SM takes in the 32 KB weight tile plus ~45 KB of corner rows (64 KB at the measured 31 % L1 hit rate):
+// 5.9 GB per layer (ncu lts__t_sectors) in 0.545 ms = 10.7 TB/s, against the ~12 TB/s the L2 delivers chip-wide; 600 TFLOP/s,
+// tensor pipe 31 % active.  Sharing the weight tile between the two CTAs of a cluster by TMA multicast was measured and changes
+// nothing (0.57 ms): the limit is what each SM can take in, not what the L2 slices read.
 #include "common.cuh"
 #include "../../include/mqdet_b200.h"
 

@@ -19,6 +19,30 @@ launch_count = 0
 
 # bench.py sets this to a list to time every GEMM launch with CUDA events on the launching stream (roofline.achieved)
 GEMM_PROFILE = None
+# ... and this one to time every launch of the tensor-core kernels (GEMM, dcn_conv, biattn_image, biattn_text_vn):
+# entries (start event, end event, kernel name, algorithmic flops, algorithmic bytes)
+KERNEL_PROFILE = None
+
+
+class _Timed:
+    """Brackets one launch with CUDA events on the launching stream when KERNEL_PROFILE is a list."""
+
+    def __init__(self, name, flops, nbytes):
+        self.rec = KERNEL_PROFILE is not None
+        if self.rec:
+            self.name, self.flops, self.nbytes = name, float(flops), float(nbytes)
+            self.e0, self.e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+    def __enter__(self):
+        if self.rec:
+            self.e0.record()
+        return self
+
+    def __exit__(self, *exc):
+        if self.rec:
+            self.e1.record()
+            KERNEL_PROFILE.append((self.e0, self.e1, self.name, self.flops, self.nbytes))
+        return False
 
 
 def _stream():
@@ -113,7 +137,14 @@ def gemm(a, b, out=None, *, out_dtype=torch.float16, alpha=1.0, bias=None, bias_
     if GEMM_PROFILE is not None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-    check(load().mqdet_gemm_f16(ctypes.byref(g), DEFAULT_GEMM_IMPL if impl is None else impl, _stream()), "gemm")
+    # algorithmic bytes: every operand once (a broadcast operand once for the whole batch), the output, the residual
+    nb = nb1 * nb2
+    es_o = 2 if out.dtype == torch.float16 else 4
+    gbytes = 2.0 * M * K * (a4.shape[0] * a4.shape[1]) + 2.0 * N * K * (b4.shape[0] * b4.shape[1]) + float(es_o) * M * N * nb
+    if residual is not None:
+        gbytes += (2.0 if residual.dtype == torch.float16 else 4.0) * M * N * nb
+    with _Timed("gemm_tcp_kernel", 2.0 * M * N * K * nb, gbytes):
+        check(load().mqdet_gemm_f16(ctypes.byref(g), DEFAULT_GEMM_IMPL if impl is None else impl, _stream()), "gemm")
     if GEMM_PROFILE is not None:
         e1.record()
         GEMM_PROFILE.append((e0, e1, 2.0 * M * N * K * nb1 * nb2, (M, N, K, nb1 * nb2)))
@@ -328,13 +359,18 @@ def biattn_image(vn16, gT, gbias, mT, bias, gamma, residual, mask, clamp, heads)
     out = torch.empty((B, N, 256), dtype=torch.float16, device=vn16.device)
     colmax = torch.empty((B * heads, T), dtype=torch.float32, device=vn16.device)
     ws = torch.empty((int(load().mqdet_biattn_image_workspace_floats(B, heads, N, T)),), dtype=torch.float32, device=vn16.device)
-    check(load().mqdet_biattn_image(_ptr(vn16), vn16.stride(1), vn16.stride(0), _ptr(gT), gT.stride(2), gT.stride(1), gT.stride(0),
-                                    _ptr(gbias), gbias.shape[3] if gbias is not None else 0, _ptr(mT), mT.stride(2), mT.stride(1),
-                                    mT.stride(0), _ptr(bias), _ptr(gamma), _ptr(residual),
-                                    residual.stride(1) if residual is not None else 0,
-                                    residual.stride(0) if residual is not None else 0, _ptr(mask), float(clamp), _ptr(out),
-                                    out.stride(1), out.stride(0), _ptr(colmax), _ptr(ws), B, heads, N, T, _stream()),
-          "biattn_image")
+    # algorithmic work of the image -> text direction as the reference computes it (fuse_helper.py:218-303): query projection,
+    # scores, P.V_l, output projection (4 products of 2.N.T'.E with T' = 256 or T); bytes: tokens in, tokens out, residual
+    E = heads * 256
+    fl = B * (2.0 * N * 256 * E + 2.0 * 2.0 * N * T * E + 2.0 * N * E * 256)
+    with _Timed("biattn_image_kernel", fl, 2.0 * B * N * 256 * (3 if residual is not None else 2) + 2.0 * 2 * B * heads * T * 256):
+        check(load().mqdet_biattn_image(_ptr(vn16), vn16.stride(1), vn16.stride(0), _ptr(gT), gT.stride(2), gT.stride(1),
+                                        gT.stride(0), _ptr(gbias), gbias.shape[3] if gbias is not None else 0, _ptr(mT),
+                                        mT.stride(2), mT.stride(1), mT.stride(0), _ptr(bias), _ptr(gamma), _ptr(residual),
+                                        residual.stride(1) if residual is not None else 0,
+                                        residual.stride(0) if residual is not None else 0, _ptr(mask), float(clamp), _ptr(out),
+                                        out.stride(1), out.stride(0), _ptr(colmax), _ptr(ws), B, heads, N, T, _stream()),
+              "biattn_image")
     launch_count += 2
     return out, colmax
 
@@ -350,10 +386,14 @@ def biattn_text_vn(kh, qh, vn16, colmax, clamp, out, rowbias=None):
     for t in (kh, qh, vn16, out):
         if t.stride(-1) != 1 or t.dtype != torch.float16:
             raise _lib.MqdetError("biattn_text_vn: fp16 operands with a contiguous last dimension required")
-    check(load().mqdet_biattn_text_vn(_ptr(kh), kh.stride(2), kh.stride(1), kh.stride(0), _ptr(qh), qh.stride(2), qh.stride(1),
-                                      qh.stride(0), _ptr(vn16), vn16.stride(1), 0, vn16.stride(0), _ptr(colmax), _ptr(rowbias),
-                                      rowbias.shape[3] if rowbias is not None else 0, float(clamp), _ptr(out), out.stride(2),
-                                      out.stride(1), out.stride(0), H, B, T, N, _stream()), "biattn_text_vn")
+    # algorithmic work of the text -> image direction (the scores are shared with the other direction in the reference): the
+    # image-side value projection and P^T.V_v; bytes: the image tokens once per image, the small text-side operands
+    fl = B * (2.0 * N * 256 * H * d + 2.0 * T * N * H * d)
+    with _Timed("biattn_text_kernel", fl, 2.0 * B * N * 256 + 2.0 * 2 * B * H * T * 256):
+        check(load().mqdet_biattn_text_vn(_ptr(kh), kh.stride(2), kh.stride(1), kh.stride(0), _ptr(qh), qh.stride(2), qh.stride(1),
+                                          qh.stride(0), _ptr(vn16), vn16.stride(1), 0, vn16.stride(0), _ptr(colmax), _ptr(rowbias),
+                                          rowbias.shape[3] if rowbias is not None else 0, float(clamp), _ptr(out), out.stride(2),
+                                          out.stride(1), out.stride(0), H, B, T, N, _stream()), "biattn_text_vn")
     launch_count += 1
     return out
 
@@ -581,9 +621,11 @@ def dcn_conv(x16, om, levels, branches, weights, biases):
     for w in weights:
         if w.dtype != torch.float16 or tuple(w.shape) != (256, 9 * C) or not w.is_contiguous():
             raise _lib.MqdetError(f"dcn_conv: weights must be contiguous fp16 [256, {9 * C}] (got {w.dtype} {tuple(w.shape)})")
-    check(load().mqdet_dcn_conv(_ptr(x16), _ptr(om), om.shape[-1] if om is not None else 0, levels.hw_ptr, levels.n, B, C, n,
-                                ctypes.cast(br, ctypes.c_void_p), ctypes.cast(wp, ctypes.c_void_p),
-                                ctypes.cast(bp, ctypes.c_void_p), ctypes.cast(yp, ctypes.c_void_p), _stream()), "dcn_conv")
+    rows = sum(y.shape[0] for y in ys)
+    with _Timed("dcn_conv_kernel", 2.0 * rows * 256 * 9 * C, 2.0 * (B * N * C + rows * 256 + n * 256 * 9 * C) + (4.0 * B * N * 27 if om is not None else 0.0)):
+        check(load().mqdet_dcn_conv(_ptr(x16), _ptr(om), om.shape[-1] if om is not None else 0, levels.hw_ptr, levels.n, B, C, n,
+                                    ctypes.cast(br, ctypes.c_void_p), ctypes.cast(wp, ctypes.c_void_p),
+                                    ctypes.cast(bp, ctypes.c_void_p), ctypes.cast(yp, ctypes.c_void_p), _stream()), "dcn_conv")
     launch_count += 1
     return ys
 

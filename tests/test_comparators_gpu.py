@@ -125,10 +125,17 @@ def test_speed_comparators(dev):
         cols = ops.dcn_cols(x16, om_flat, lv, 1)
         return ops.gemm(cols, w16_, bias=bias)
 
+    def ours_implicit():
+        return ops.dcn_conv(x16, om_flat, lv, [1], [w16_], [bias])[0]
+
+    y_i, y_c = ours_implicit().float(), ours().float()
+    assert (y_i - y_c).abs().max().item() <= 2e-3 * y_c.abs().max().item()
     out["dcnv2_3x3_B8_100x168_256ch"] = {"reference_kernel_ms": _time(lambda: _ref_dcn(ref, x, off, msk, w, bias, 1)),
-                                         "mqdet_ms": _time(ours),
+                                         "mqdet_ms": _time(ours_implicit), "mqdet_cols_gemm_ms": _time(ours),
                                          "note": "reference = fp32 im2col + per-image SGEMM (deform_conv_cuda.cu:496-575); "
-                                                 "mqdet = fp16 NHWC sampling kernel + tcgen05 GEMM"}
+                                                 "mqdet = implicit GEMM (mqdet_dcn_conv: sampling fused into the tcgen05 mainloop, "
+                                                 "no column matrix); mqdet_cols_gemm = the fp16 NHWC sampling kernel + tcgen05 GEMM "
+                                                 "pair it replaced"}
     # ---- eager-PyTorch reference algorithm vs the fused kernels: one BiAttention fusion layer, B = 8, N = 22400 ------
     sd = synth.bi_attention_sd(gen)
     blk = load_sd(BiAttentionBlockForCheckpoint(v_dim=256, l_dim=768, embed_dim=2048, num_heads=8, hidden_dim=3072, dropout=0.1,
