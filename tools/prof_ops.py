@@ -50,6 +50,20 @@ elif which == "dcn":
     rows = 8 * (lv.N + 2 * lv.N1)
     byt = 2.0 * (8 * lv.N * 256 + rows * 256) + 3 * 2.0 * 256 * 2304
     flop = 2.0 * rows * 256 * 2304
+elif which == "dyconv":
+    # one whole DyConv layer (offset conv, dcn_conv, chan_stats, gn_attn, combine, DyReLU) for multi-kernel ncu captures
+    from mqdet_b200.modeling.rpn.vldyhead import Conv3x3Norm, DyConv
+    from tools import synth
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from util import load_sd
+    gen = synth.Gen(3)
+    conv_func = lambda i, o, s: Conv3x3Norm(i, o, s, deformable=True, bn_type=["gn", 16])  # noqa: E731
+    mod = load_sd(DyConv(256, 256, conv_func=conv_func, use_dyrelu=True, use_dyfuse=True, use_deform=True), synth.dyconv_sd(gen))
+    mod = mod.to(dev).eval()
+    lv = ops.Levels([(100, 168), (50, 84), (25, 42), (13, 21), (7, 11)], dev)
+    x16 = rnd(8, lv.N, 256)
+    fn = lambda: mod.forward_flat(x16, lv)  # noqa: E731
+    byt, flop = 2.0 * 2 * 8 * lv.N * 256, 2.0 * 8 * (lv.N + 2 * lv.N1) * 256 * 2304
 elif which == "conv_off":
     lv = ops.Levels([(100, 168), (50, 84), (25, 42), (13, 21), (7, 11)], dev)
     x16 = rnd(8, lv.N, 256)
