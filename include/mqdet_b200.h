@@ -262,16 +262,20 @@ int mqdet_gn_attn(const float* partial, const int32_t* seg_off_dev, int64_t nseg
                   int weighted, const float* gn_w, const float* gn_b, float eps, const float* attn_w, const float* attn_b,
                   float* affine, float* attn, void* stream);
 
-/* mid = mean_k attn_k * GN_k(y_k), branch 0 bilinearly upsampled (align_corners=True) from the coarser grid. */
+/* mid = mean_k attn_k * GN_k(y_k), branch 0 bilinearly upsampled (align_corners=True) from the coarser grid.
+ * mid_sums (optional): fp32 [B][nlev][mqdet_dyconv_combine_chunks()][C] per-channel sums of the stored (fp16) output over
+ * the pixel ranges of each (image, level) — the global average pool DyReLU needs, so `mid` is not read again for it. */
+int64_t mqdet_dyconv_combine_chunks(void);
 int mqdet_dyconv_combine(const void* y1, const void* y2, const void* y0, const float* aff1, const float* aff2,
                          const float* aff0, const float* at1, const float* at2, const float* at0, const int32_t* level_hw,
-                         int64_t nlev, int64_t B, int64_t C, void* mid, void* stream);
+                         int64_t nlev, int64_t B, int64_t C, void* mid, float* mid_sums, void* stream);
 
-/* DyReLU (layers/dyrelu.py:80-104): coefficients per (image, level) from the partial sums of `mid`, then
- * out = max(mid*a1 + b1, mid*a2 + b2). */
-int mqdet_dyrelu_coef(const float* partial, const int32_t* seg_off_dev, int64_t nseg, int64_t B, int64_t C,
-                      int64_t squeeze, const float* w1, const float* b1, const float* w2, const float* b2, float* coef,
-                      void* stream);
+/* DyReLU (layers/dyrelu.py:80-104): coefficients per (image, level) from partial channel sums of `mid`
+ * (partial [B*nseg][chunks][stats][C], statistic 0 = the plain sum: mqdet_chan_stats output has chunks = 32, stats = 3;
+ * mqdet_dyconv_combine's mid_sums chunks = mqdet_dyconv_combine_chunks(), stats = 1), then out = max(mid*a1 + b1, mid*a2 + b2). */
+int mqdet_dyrelu_coef(const float* partial, int64_t chunks, int64_t stats, const int32_t* seg_off_dev, int64_t nseg, int64_t B,
+                      int64_t C, int64_t squeeze, const float* w1, const float* b1, const float* w2, const float* b2,
+                      float* coef, void* stream);
 int mqdet_dyrelu_apply(const void* mid, const float* coef, const int32_t* level_hw, int64_t nlev, int64_t B, int64_t C,
                        void* out, void* stream);
 
@@ -320,8 +324,10 @@ int mqdet_anchors(float* out, uint8_t* visibility, int64_t grid_h, int64_t grid_
 /* PatchEmbed input gather (swint.py:393-431): image fp32 NCHW [B,3,H,W] -> fp16 [B*ceil(H/4)*ceil(W/4), 48]. */
 int mqdet_patchify4(const float* img, int64_t B, int64_t H, int64_t W, void* out, void* stream);
 /* (S)W-MSA core (swint.py:111-142,186-242): qkv fp16 [B*H*W, 3C] -> out fp16 [B*H*W, C]; pads to a multiple of the
- * window with qkv_bias rows, cyclic shift + -100 region mask by index math, bias_dense fp32 [heads][49][49]. */
-int mqdet_swin_window_attn(const void* qkv, const float* qkv_bias, const float* bias_dense, int64_t B, int64_t H, int64_t W,
+ * window with qkv_bias rows, cyclic shift + -100 region mask by index math.  bias_pad: fp32 [heads][NP][NP] with
+ * NP = window^2 rounded up to 16 (64 / 144) = log2(e) x the relative position bias inside [N][N], -inf outside (scale, bias
+ * and the padding of keys / queries are then one FFMA per score; the softmax runs in the log2 domain). */
+int mqdet_swin_window_attn(const void* qkv, const float* qkv_bias, const float* bias_pad, int64_t B, int64_t H, int64_t W,
                            int64_t heads, int64_t window, int64_t shift, float scale, void* out, void* stream);
 /* PatchMerging gather + LayerNorm(4C) (swint.py:256-284): x fp32 [B,H*W,C] -> fp16 [B*ceil(H/2)*ceil(W/2), 4C]. */
 int mqdet_patch_merge_ln(const float* x, int64_t B, int64_t H, int64_t W, int64_t C, const float* gamma, const float* beta,

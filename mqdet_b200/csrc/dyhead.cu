@@ -153,9 +153,37 @@ __global__ void __launch_bounds__(256) chan_stats_kernel(const __half* __restric
   float s[8], q[8], w[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) s[i] = q[i] = w[i] = 0.f;
-  for (int r = r0 + chunk * 8 + rl; r < r1; r += STAT_CHUNKS * 8) {
+  // four independent 16-byte loads in flight per thread (level 0 gives each thread ~65 rows: one load at a time left the
+  // kernel latency-bound at ~2.5 TB/s); the order of the additions per accumulator is unchanged
+  constexpr int STEP = STAT_CHUNKS * 8;
+  const __half* yb = y + (long)b * rows_per_img * C + cl * 8;
+  int r = r0 + chunk * 8 + rl;
+  for (; r + 3 * STEP < r1; r += 4 * STEP) {
+    uint4 u[4];
+    float wt[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      u[k] = *reinterpret_cast<const uint4*>(yb + (long)(r + k * STEP) * C);
+      wt[k] = rw ? rw[r + k * STEP] : 1.f;
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const __half2* h = reinterpret_cast<const __half2*>(&u[k]);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float2 f = __half22float2(h[i]);
+        s[2 * i] += f.x;
+        s[2 * i + 1] += f.y;
+        q[2 * i] += f.x * f.x;
+        q[2 * i + 1] += f.y * f.y;
+        w[2 * i] += wt[k] * f.x;
+        w[2 * i + 1] += wt[k] * f.y;
+      }
+    }
+  }
+  for (; r < r1; r += STEP) {
     float v[8];
-    ld8h(y + ((long)b * rows_per_img + r) * C + cl * 8, v);
+    ld8h(yb + (long)r * C, v);
     const float wt = rw ? rw[r] : 1.f;
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
@@ -199,10 +227,11 @@ __global__ void __launch_bounds__(C) gn_attn_kernel(const float* __restrict__ pa
   const int c = threadIdx.x;
   const float* p = partial + (long)sb * STAT_CHUNKS * 3 * C;
   float s = 0.f, q = 0.f, w = 0.f;
-  for (int k = 0; k < STAT_CHUNKS; ++k) {
-    s += p[(k * 3 + 0) * C + c];
-    q += p[(k * 3 + 1) * C + c];
-    w += p[(k * 3 + 2) * C + c];
+#pragma unroll 8
+  for (int k = 0; k < STAT_CHUNKS; ++k) {  // unrolled: 24 independent loads in flight (same addition order)
+    s += __ldg(p + (k * 3 + 0) * C + c);
+    q += __ldg(p + (k * 3 + 1) * C + c);
+    w += __ldg(p + (k * 3 + 2) * C + c);
   }
   const float rows = (float)(seg_off[seg + 1] - seg_off[seg]);
   __shared__ float sh_s[C], sh_q[C], sh_d[C];
@@ -241,39 +270,37 @@ __global__ void __launch_bounds__(C) gn_attn_kernel(const float* __restrict__ pa
 // Scale-aware fusion (vldyhead.py:219-238): mid[p] = mean_k attn_k * GN_k(y_k)[p]; branch 0 is bilinearly upsampled
 // (align_corners=True, F.upsample_bilinear :224) from the next-coarser grid.  One warp per pixel, 8 channels per lane.
 // ---------------------------------------------------------------------------------------------------------------
-constexpr int DC_PPW = 4;
+constexpr int MID_CHUNKS = 128;  // pixel ranges per (image, level) of dyconv_combine == partial-sum rows DyReLU reads
+// grid (MID_CHUNKS, B * L): a block = one contiguous pixel range of ONE (image, level), a warp = a contiguous sub-range
+// (8 channels per lane).  The (attention x GroupNorm affine) rows of the block's (image, level) are folded into one
+// scale/offset pair per branch once per block; row / column advance by increment.  The per-channel sums of the (rounded)
+// output — the global average pool DyReLU needs (layers/dyrelu.py:84-86) — are reduced per block into
+// mid_sums[b][l][chunk][C], so `mid` is not read a second time for them.
 template <int C>
-__global__ void __launch_bounds__(256) dyconv_combine_kernel(const __half* __restrict__ y1, const __half* __restrict__ y2,
+__global__ void __launch_bounds__(256, 3) dyconv_combine_kernel(const __half* __restrict__ y1, const __half* __restrict__ y2,
                                                              const __half* __restrict__ y0, const float* __restrict__ aff1,
                                                              const float* __restrict__ aff2, const float* __restrict__ aff0,
                                                              const float* __restrict__ at1, const float* __restrict__ at2,
                                                              const float* __restrict__ at0, LevelTable lt, int B,
-                                                             __half* __restrict__ mid) {
-  // one warp per run of DC_PPW consecutive pixels; the (attention x GroupNorm affine) rows of the run's (image, level) are
-  // folded into one scale/offset pair per branch and kept in registers across the run
-  const long gw0 = (((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5) * DC_PPW;
-  const int lane = threadIdx.x & 31;
+                                                             __half* __restrict__ mid, float* __restrict__ mid_sums) {
+  const int chunk = blockIdx.x, sb = blockIdx.y;
   const int L = lt.n;
+  const int b = sb / L, l = sb - b * L;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int N = lt.off[L - 1] + lt.H[L - 1] * lt.W[L - 1];
   const int N1 = N - lt.H[0] * lt.W[0];
-  const long total = (long)B * N;
-  if (gw0 >= total) return;
+  const int H = lt.H[l], W = lt.W[l], HW = H * W;
+  const int len = (HW + MID_CHUNKS - 1) / MID_CHUNKS, sub = (len + 7) / 8;
+  const int p0 = chunk * len + warp * sub;
+  const int p1 = min(min(p0 + sub, (chunk + 1) * len), HW);
   const int c0 = lane * 8;
-  int cur = -1;
-  float s1[8], s2[8], s0[8], off[8];  // acc = s1*y1 + s2*y2 + s0*up(y0) + off, already divided by the branch count
-  bool has2 = false, has0 = false;
-#pragma unroll 1
-  for (int j = 0; j < DC_PPW; ++j) {
-    const long gw = gw0 + j;
-    if (gw >= total) break;
-    const int b = (int)(gw / N);
-    const int pn = (int)(gw % N);
-    int l = 0;
-    while (l + 1 < L && pn >= lt.off[l + 1]) ++l;
-    if (b * L + l != cur) {
-      cur = b * L + l;
-      has2 = l > 0;
-      has0 = l < L - 1;
+  const bool has2 = l > 0, has0 = l < L - 1;
+  float sums[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) sums[i] = 0.f;
+  if (p0 < p1) {
+    float s1[8], s2[8], s0[8], off[8];  // acc = s1*y1 + s2*y2 + s0*up(y0) + off, already divided by the branch count
+    {
       const float inv = 1.f / (float)(1 + (has2 ? 1 : 0) + (has0 ? 1 : 0));
       float g[8], o[8];
       {
@@ -285,6 +312,7 @@ __global__ void __launch_bounds__(256) dyconv_combine_kernel(const __half* __res
         for (int i = 0; i < 8; ++i) {
           s1[i] = a * g[i];
           off[i] = a * o[i];
+          s2[i] = s0[i] = 0.f;
         }
       }
       if (has2) {  // branch 2: stride-2 conv of the finer level, already at this resolution; segment index l-1
@@ -310,43 +338,70 @@ __global__ void __launch_bounds__(256) dyconv_combine_kernel(const __half* __res
         }
       }
     }
-    const int q = pn - lt.off[l];
-    const int H = lt.H[l], W = lt.W[l];
-    float acc[8], v[8];
-    ld8h(y1 + ((long)b * N + pn) * C + c0, v);
+    const int Hs = has0 ? lt.H[l + 1] : 1, Ws = has0 ? lt.W[l + 1] : 1;
+    // area_pixel_compute_source_index, align_corners=True (fp32 scale like ATen)
+    const float sh = (H > 1) ? (float)(Hs - 1) / (float)(H - 1) : 0.f;
+    const float sw = (W > 1) ? (float)(Ws - 1) / (float)(W - 1) : 0.f;
+    const __half* y1b = y1 + ((long)b * N + lt.off[l]) * C + c0;
+    const __half* y2b = has2 ? y2 + ((long)b * N1 + (lt.off[l] - lt.off[1])) * C + c0 : nullptr;
+    const __half* y0b = has0 ? y0 + ((long)b * N1 + (lt.off[l + 1] - lt.off[1])) * C + c0 : nullptr;
+    __half* mb = mid + ((long)b * N + lt.off[l]) * C + c0;
+    int h = p0 / W, w = p0 - h * W;
+#pragma unroll 1
+    for (int p = p0; p < p1; ++p) {
+      float acc[8], v[8];
+      ld8h(y1b + (long)p * C, v);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) acc[i] = fmaf(s1[i], v[i], off[i]);
-    if (has2) {
-      ld8h(y2 + ((long)b * N1 + (pn - lt.off[1])) * C + c0, v);
+      for (int i = 0; i < 8; ++i) acc[i] = fmaf(s1[i], v[i], off[i]);
+      if (has2) {
+        ld8h(y2b + (long)p * C, v);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) acc[i] = fmaf(s2[i], v[i], acc[i]);
-    }
-    if (has0) {
-      const int Hs = lt.H[l + 1], Ws = lt.W[l + 1];
-      const int h = q / W, w = q % W;
-      // area_pixel_compute_source_index, align_corners=True (fp32 scale like ATen)
-      const float sh = (H > 1) ? (float)(Hs - 1) / (float)(H - 1) : 0.f;
-      const float sw = (W > 1) ? (float)(Ws - 1) / (float)(W - 1) : 0.f;
-      const float fh = sh * h, fw = sw * w;
-      const int h0 = (int)fh, w0 = (int)fw;
-      const int h1 = h0 + ((h0 < Hs - 1) ? 1 : 0), w1 = w0 + ((w0 < Ws - 1) ? 1 : 0);
-      const float lh = fh - h0, lw = fw - w0;
-      const __half* yb = y0 + ((long)b * N1 + (lt.off[l + 1] - lt.off[1])) * C + c0;
-      float t00[8], t01[8], t10[8], t11[8];
-      ld8h(yb + (long)(h0 * Ws + w0) * C, t00);
-      ld8h(yb + (long)(h0 * Ws + w1) * C, t01);
-      ld8h(yb + (long)(h1 * Ws + w0) * C, t10);
-      ld8h(yb + (long)(h1 * Ws + w1) * C, t11);
+        for (int i = 0; i < 8; ++i) acc[i] = fmaf(s2[i], v[i], acc[i]);
+      }
+      if (has0) {
+        const float fh = sh * h, fw = sw * w;
+        const int h0 = (int)fh, w0 = (int)fw;
+        const int h1 = h0 + ((h0 < Hs - 1) ? 1 : 0), w1 = w0 + ((w0 < Ws - 1) ? 1 : 0);
+        const float lh = fh - h0, lw = fw - w0;
+        float t00[8], t01[8], t10[8], t11[8];
+        ld8h(y0b + (long)(h0 * Ws + w0) * C, t00);
+        ld8h(y0b + (long)(h0 * Ws + w1) * C, t01);
+        ld8h(y0b + (long)(h1 * Ws + w0) * C, t10);
+        ld8h(y0b + (long)(h1 * Ws + w1) * C, t11);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        float u = (1.f - lh) * (1.f - lw) * t00[i];
-        u += (1.f - lh) * lw * t01[i];
-        u += lh * (1.f - lw) * t10[i];
-        u += lh * lw * t11[i];
-        acc[i] = fmaf(s0[i], u, acc[i]);
+        for (int i = 0; i < 8; ++i) {
+          float u = (1.f - lh) * (1.f - lw) * t00[i];
+          u += (1.f - lh) * lw * t01[i];
+          u += lh * (1.f - lw) * t10[i];
+          u += lh * lw * t11[i];
+          acc[i] = fmaf(s0[i], u, acc[i]);
+        }
+      }
+      __half2 hv[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        hv[i] = __floats2half2_rn(acc[2 * i], acc[2 * i + 1]);
+        const float2 r = __half22float2(hv[i]);  // the pooled mean is taken over the STORED (rounded) values
+        sums[2 * i] += r.x;
+        sums[2 * i + 1] += r.y;
+      }
+      *reinterpret_cast<uint4*>(mb + (long)p * C) = *reinterpret_cast<uint4*>(hv);
+      if (++w == W) {
+        w = 0;
+        ++h;
       }
     }
-    st8h(mid + ((long)b * N + pn) * C + c0, acc);
+  }
+  if (mid_sums) {  // block-uniform
+    __shared__ float shs[8][C];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) shs[warp][c0 + i] = sums[i];
+    __syncthreads();
+    const int c = threadIdx.x;  // C == blockDim.x
+    float t = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) t += shs[j][c];
+    mid_sums[((long)sb * MID_CHUNKS + chunk) * C + c] = t;
   }
 }
 
@@ -356,36 +411,85 @@ __global__ void __launch_bounds__(256) dyconv_combine_kernel(const __half* __res
 // One block of C threads per (b, level).  coef[b][l][4][C].
 // ---------------------------------------------------------------------------------------------------------------
 template <int C, int SQ>
-__global__ void __launch_bounds__(C) dyrelu_coef_kernel(const float* __restrict__ partial, const int* __restrict__ seg_off,
-                                                        int nseg, const float* __restrict__ w1,
+__global__ void __launch_bounds__(C) dyrelu_coef_kernel(const float* __restrict__ partial, int chunks, int stats,
+                                                        const int* __restrict__ seg_off, int nseg,
+                                                        const float* __restrict__ w1,
                                                         const float* __restrict__ b1, const float* __restrict__ w2,
                                                         const float* __restrict__ b2, float* __restrict__ coef) {
   const int sb = blockIdx.x, seg = sb % nseg;
   const int c = threadIdx.x;
-  const float* p = partial + (long)sb * STAT_CHUNKS * 3 * C;
+  // partial[sb][chunk][stats][C], statistic 0 = the plain sum (chan_stats: 32 x 3, dyconv_combine: MID_CHUNKS x 1)
+  const float* p = partial + (long)sb * chunks * stats * C + c;
   float s = 0.f;
-  for (int k = 0; k < STAT_CHUNKS; ++k) s += p[(k * 3 + 0) * C + c];
+  for (int k0 = 0; k0 < chunks; k0 += 32) {
+    float v[32];
+#pragma unroll
+    for (int k = 0; k < 32; ++k) v[k] = (k0 + k < chunks) ? __ldg(p + (long)(k0 + k) * stats * C) : 0.f;  // 32 loads in flight
+#pragma unroll
+    for (int k = 0; k < 32; ++k) s += v[k];
+  }
   __shared__ float gap[C], hid[SQ];
   gap[c] = s / (float)(seg_off[seg + 1] - seg_off[seg]);
   __syncthreads();
-  if (c < SQ) {
-    float t = b1[c];
-    for (int i = 0; i < C; ++i) t = fmaf(w1[c * C + i], gap[i], t);
-    hid[c] = fmaxf(t, 0.f);
+  // both mat-vecs read their weight rows coalesced (a thread per output row walked 1 KB / 256 B strides: 50 us of latency)
+  const int warp = c >> 5, lane = c & 31;
+  // hid = relu(W1 gap + b1): W1 [SQ][C]; a warp per output row, 8 floats of the row per lane.  ALL loads of a warp's rows are
+  // issued before the first reduction (a load -> shuffle -> next load chain costs one memory latency per row)
+  {
+    constexpr int RPW = SQ / (C / 32);  // rows per warp (8)
+    float4 wa[RPW], wb[RPW];
+#pragma unroll
+    for (int k = 0; k < RPW; ++k) {
+      const float4* row = reinterpret_cast<const float4*>(w1 + (long)(warp + k * (C / 32)) * C);
+      wa[k] = __ldg(row + 2 * lane);
+      wb[k] = __ldg(row + 2 * lane + 1);
+    }
+    const float* g = gap + 8 * lane;
+#pragma unroll
+    for (int k = 0; k < RPW; ++k) {
+      float t = wa[k].x * g[0];
+      t = fmaf(wa[k].y, g[1], t); t = fmaf(wa[k].z, g[2], t); t = fmaf(wa[k].w, g[3], t);
+      t = fmaf(wb[k].x, g[4], t); t = fmaf(wb[k].y, g[5], t); t = fmaf(wb[k].z, g[6], t); t = fmaf(wb[k].w, g[7], t);
+      t = warp_sum(t);
+      const int o = warp + k * (C / 32);
+      if (lane == 0) hid[o] = fmaxf(t + b1[o], 0.f);
+    }
   }
   __syncthreads();
+  // y = h_sigmoid(W2 hid + b2): W2 [4C][SQ = 64]; half a warp per output row (one float4 per lane), two rows per warp step,
+  // eight steps' loads in flight at a time
+  {
+    const int hl = lane & 15, hw = lane >> 4;
+    const float h0 = hid[4 * hl], h1 = hid[4 * hl + 1], h2 = hid[4 * hl + 2], h3 = hid[4 * hl + 3];
+    constexpr int STRIDE = (C / 32) * 2, STEPS = 4 * C / STRIDE, UN = 8;
+    static_assert(STEPS % UN == 0, "dyrelu_coef: step count must be a multiple of the unroll");
+#pragma unroll 1
+    for (int s0 = 0; s0 < STEPS; s0 += UN) {
+      float4 wv[UN];
 #pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    const int o = k * C + c;
-    float t = b2[o];
-    for (int i = 0; i < SQ; ++i) t = fmaf(w2[o * SQ + i], hid[i], t);
-    t = fminf(fmaxf(t + 3.f, 0.f), 6.f) / 6.f;  // h_sigmoid
-    float r;
-    if (k == 0) r = (t - 0.5f) * 2.f + 1.f;
-    else if (k == 1) r = t - 0.5f;
-    else if (k == 2) r = (t - 0.5f) * 2.f;
-    else r = t - 0.5f;
-    coef[((long)sb * 4 + k) * C + c] = r;
+      for (int u = 0; u < UN; ++u)
+        wv[u] = __ldg(reinterpret_cast<const float4*>(w2 + (long)(warp * 2 + hw + (s0 + u) * STRIDE) * SQ) + hl);
+#pragma unroll
+      for (int u = 0; u < UN; ++u) {
+        const int o = warp * 2 + hw + (s0 + u) * STRIDE;
+        float t = wv[u].x * h0;
+        t = fmaf(wv[u].y, h1, t); t = fmaf(wv[u].z, h2, t); t = fmaf(wv[u].w, h3, t);
+        t += __shfl_xor_sync(0xffffffffu, t, 8);
+        t += __shfl_xor_sync(0xffffffffu, t, 4);
+        t += __shfl_xor_sync(0xffffffffu, t, 2);
+        t += __shfl_xor_sync(0xffffffffu, t, 1);
+        if (hl == 0) {
+          t = fminf(fmaxf(t + b2[o] + 3.f, 0.f), 6.f) / 6.f;  // h_sigmoid
+          const int k = o / C;
+          float r;
+          if (k == 0) r = (t - 0.5f) * 2.f + 1.f;
+          else if (k == 1) r = t - 0.5f;
+          else if (k == 2) r = (t - 0.5f) * 2.f;
+          else r = t - 0.5f;
+          coef[(long)sb * 4 * C + o] = r;
+        }
+      }
+    }
   }
 }
 
@@ -622,28 +726,33 @@ extern "C" int mqdet_gn_attn(const float* partial, const int32_t* seg_off_dev, i
   return check_launch("gn_attn_kernel");
 }
 
+extern "C" int64_t mqdet_dyconv_combine_chunks(void) { return MID_CHUNKS; }
+
 extern "C" int mqdet_dyconv_combine(const void* y1, const void* y2, const void* y0, const float* aff1, const float* aff2,
                                     const float* aff0, const float* at1, const float* at2, const float* at0,
-                                    const int32_t* level_hw, int64_t nlev, int64_t B, int64_t C, void* mid, void* stream) {
+                                    const int32_t* level_hw, int64_t nlev, int64_t B, int64_t C, void* mid, float* mid_sums,
+                                    void* stream) {
   MQ_REQUIRE(y1 && aff1 && at1 && mid && level_hw, "dyconv_combine: null pointer");
   MQ_REQUIRE(C == 256, "dyconv_combine: C must be 256");
   LevelTable lt;
   const int N = fill_levels(&lt, level_hw, nlev);
   MQ_REQUIRE(N > 0, "dyconv_combine: bad level table");
   MQ_REQUIRE(nlev == 1 || (y2 && y0 && aff2 && aff0 && at2 && at0), "dyconv_combine: missing cross-level inputs");
-  const long blocks = (((long)B * N + DC_PPW - 1) / DC_PPW * 32 + 255) / 256;
-  dyconv_combine_kernel<256><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
-      (const __half*)y1, (const __half*)y2, (const __half*)y0, aff1, aff2, aff0, at1, at2, at0, lt, (int)B, (__half*)mid);
+  MQ_REQUIRE(B >= 1 && B * nlev <= 65535, "dyconv_combine: B * levels must be in 1..65535");
+  dyconv_combine_kernel<256><<<dim3(MID_CHUNKS, (unsigned)(B * nlev)), 256, 0, (cudaStream_t)stream>>>(
+      (const __half*)y1, (const __half*)y2, (const __half*)y0, aff1, aff2, aff0, at1, at2, at0, lt, (int)B, (__half*)mid, mid_sums);
   return check_launch("dyconv_combine_kernel");
 }
 
-extern "C" int mqdet_dyrelu_coef(const float* partial, const int32_t* seg_off_dev, int64_t nseg, int64_t B, int64_t C,
-                                 int64_t squeeze, const float* w1, const float* b1, const float* w2, const float* b2,
-                                 float* coef, void* stream) {
+extern "C" int mqdet_dyrelu_coef(const float* partial, int64_t chunks, int64_t stats, const int32_t* seg_off_dev, int64_t nseg,
+                                 int64_t B, int64_t C, int64_t squeeze, const float* w1, const float* b1, const float* w2,
+                                 const float* b2, float* coef, void* stream) {
   MQ_REQUIRE(partial && seg_off_dev && w1 && b1 && w2 && b2 && coef, "dyrelu_coef: null pointer");
+  MQ_REQUIRE(chunks >= 1 && stats >= 1, "dyrelu_coef: chunks / stats must be positive");
+  MQ_REQUIRE((((uintptr_t)w1 | (uintptr_t)w2) & 15) == 0, "dyrelu_coef: weights must be 16-byte aligned");
   MQ_REQUIRE(C == 256 && squeeze == 64, "dyrelu_coef: C=256, squeeze=64 only");
-  dyrelu_coef_kernel<256, 64><<<(unsigned)(B * nseg), 256, 0, (cudaStream_t)stream>>>(partial, seg_off_dev, (int)nseg, w1, b1,
-                                                                                      w2, b2, coef);
+  dyrelu_coef_kernel<256, 64><<<(unsigned)(B * nseg), 256, 0, (cudaStream_t)stream>>>(partial, (int)chunks, (int)stats, seg_off_dev,
+                                                                                      (int)nseg, w1, b1, w2, b2, coef);
   return check_launch("dyrelu_coef_kernel");
 }
 

@@ -14,22 +14,50 @@ namespace mqdet {
 
 // image [B,3,H,W] fp32 NCHW -> patches [B*(H/4)*(W/4), 48] fp16, k = c*16 + i*4 + j (Conv2d(3,96,4,4) weight order);
 // zero padding on the right/bottom when H or W is not a multiple of 4 (swint.py:413-418).
-__global__ void patchify4_kernel(const float* __restrict__ img, int B, int H, int W, int Hp, int Wp, __half* __restrict__ out) {
-  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
-  const long total = (long)B * Hp * Wp * 48;
-  if (i >= total) return;
-  const int k = (int)(i % 48);
-  const long t = i / 48;
-  const int pw = (int)(t % Wp), ph = (int)((t / Wp) % Hp), b = (int)(t / ((long)Wp * Hp));
-  const int c = k / 16, ii = (k % 16) / 4, jj = k % 4;
-  const int y = ph * 4 + ii, x = pw * 4 + jj;
-  float v = 0.f;
-  if (y < H && x < W) v = img[(((long)b * 3 + c) * H + y) * W + x];
-  out[i] = __float2half_rn(v);
+// One CTA per run of PF_TOK consecutive patches of a patch row: the 12 (channel, image row) segments of the run are read as
+// float4s (consecutive threads -> consecutive 16-byte pieces of one image row), converted, transposed through shared memory
+// and written as the run's contiguous [PF_TOK x 48] fp16 block with 16-byte stores.
+constexpr int PF_TOK = 64;
+__global__ void __launch_bounds__(256) patchify4_kernel(const float* __restrict__ img, int B, int H, int W, int Hp, int Wp,
+                                                        __half* __restrict__ out) {
+  __shared__ __align__(16) __half tile[PF_TOK * 48];
+  const int runs = (Wp + PF_TOK - 1) / PF_TOK;
+  const int run = blockIdx.x % runs;
+  const int ph = (blockIdx.x / runs) % Hp, b = blockIdx.x / (runs * Hp);
+  const int pw0 = run * PF_TOK, ntok = min(PF_TOK, Wp - pw0);
+  const bool vec = (W & 3) == 0 && ((uintptr_t)img & 15) == 0;
+  for (int i = threadIdx.x; i < 12 * PF_TOK; i += 256) {
+    const int seg = i / PF_TOK, tkn = i - seg * PF_TOK;  // seg = c * 4 + ii
+    if (tkn >= ntok) continue;
+    const int c = seg >> 2, ii = seg & 3;
+    const int y = ph * 4 + ii, x = (pw0 + tkn) * 4;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (y < H) {
+      const float* src = img + (((long)b * 3 + c) * H + y) * W + x;
+      if (vec && x + 3 < W) {
+        v = __ldg(reinterpret_cast<const float4*>(src));
+      } else {
+        if (x < W) v.x = src[0];
+        if (x + 1 < W) v.y = src[1];
+        if (x + 2 < W) v.z = src[2];
+        if (x + 3 < W) v.w = src[3];
+      }
+    }
+    const __half2 lo = __floats2half2_rn(v.x, v.y), hi = __floats2half2_rn(v.z, v.w);
+    uint2 o;
+    o.x = *reinterpret_cast<const uint32_t*>(&lo);
+    o.y = *reinterpret_cast<const uint32_t*>(&hi);
+    *reinterpret_cast<uint2*>(tile + tkn * 48 + seg * 4) = o;
+  }
+  __syncthreads();
+  uint4* dst = reinterpret_cast<uint4*>(out + (((long)b * Hp + ph) * Wp + pw0) * 48);  // 96 bytes per patch: 16-byte aligned
+  const uint4* srcv = reinterpret_cast<const uint4*>(tile);
+  for (int i = threadIdx.x; i < ntok * 6; i += 256) dst[i] = srcv[i];
 }
 
 // Window attention for one (window, head): head_dim 32, window WS x WS (N = 49 tokens for Swin-T, 144 for Swin-L).
-// qkv [B*H*W, 3*C] fp16 (q | k | v, each C = heads*32 wide); bias_dense [heads][N][N] fp32 (relative position bias);
+// qkv [B*H*W, 3*C] fp16 (q | k | v, each C = heads*32 wide); bias_pad [heads][NP][NP] fp32 = log2(e) x relative position bias
+// inside [N][N] and -inf outside (NP = N rounded up to 16): one FFMA per score applies scale, bias and key/query padding;
 // padded tokens (beyond H/W after padding to a multiple of the window) carry qkv = qkv_bias because the reference
 // pads the NORMALISED input with zeros before the qkv Linear (:200-205); cyclic shift + region mask (-100) are index math.
 //
@@ -61,7 +89,7 @@ struct SwinCfg {
 
 template <int WS>
 __global__ void __launch_bounds__(128) swin_window_attn_kernel(const __half* __restrict__ qkv, const float* __restrict__ qkv_bias,
-                                                               const float* __restrict__ bias_dense, int B, int H, int W,
+                                                               const float* __restrict__ bias_pad, int B, int H, int W,
                                                                int heads, int shift, float scale, __half* __restrict__ out) {
   using Cfg = SwinCfg<WS>;
   constexpr int N = Cfg::N, D = 32, NP = Cfg::NP, NT = Cfg::NT, QLD = Cfg::QLD, VLD = Cfg::VLD;
@@ -80,6 +108,13 @@ __global__ void __launch_bounds__(128) swin_window_attn_kernel(const __half* __r
   __half* vT = ks + NP * QLD;                           // [32][VLD]
   int* tok = reinterpret_cast<int*>(vT + 32 * VLD);     // [NP]
   int* reg = tok + NP;                                  // [NP]
+  // region id of the window's first token (t = 0) — every thread evaluates it, the comparison below is per token
+  int rg_first = 0;
+  if (shift > 0) {
+    const int hs = wi * WS, wsft = wj * WS;
+    rg_first = ((hs < Hp - WS) ? 0 : ((hs < Hp - shift) ? 1 : 2)) * 3 + ((wsft < Wp - WS) ? 0 : ((wsft < Wp - shift) ? 1 : 2));
+  }
+  bool differs = false;
   for (int t = threadIdx.x; t < NP; t += 128) {
     int tk = -2, rg = 0;  // -2: beyond the window's tokens
     if (t < N) {
@@ -95,8 +130,10 @@ __global__ void __launch_bounds__(128) swin_window_attn_kernel(const __half* __r
     }
     tok[t] = tk;
     reg[t] = rg;
+    differs |= (t < N && rg != rg_first);
   }
-  __syncthreads();
+  // (the table is complete after this barrier) does any token of the window lie in another shift region than its first one?
+  const bool masked = __syncthreads_or(differs ? 1 : 0) != 0;
   const __half* base = qkv + (long)b * H * W * 3 * C + head * D;
   // stage q | k | v of the window: 12 x 16-byte pieces per token (which = piece / 4, 8 dims each)
   for (int i = threadIdx.x; i < NP * 12; i += 128) {
@@ -121,7 +158,9 @@ __global__ void __launch_bounds__(128) swin_window_attn_kernel(const __half* __r
   }
   __syncthreads();
   const int g = lane >> 2, t4 = lane & 3;
-  const float* bd = bias_dense + (long)head * N * N;
+  const float* bd = bias_pad + (long)head * NP * NP;
+  constexpr float L2E = 1.4426950408889634f;
+  const float sc = scale * L2E;  // scores are kept in the log2 domain: exp(x) = ex2(x * log2 e)
 #pragma unroll 1
   for (int mi = warp; mi * 16 < N; mi += 4) {
     const int r0 = 16 * mi + g, r1 = r0 + 8;  // the two query rows this lane holds
@@ -146,37 +185,48 @@ __global__ void __launch_bounds__(128) swin_window_attn_kernel(const __half* __r
       mma_16816(sacc[nj], qf[0], kf0);
       mma_16816(sacc[nj], qf[1], kf1);
     }
-    // scale, relative position bias, shift mask, key padding; row max
-    const int rg0 = (r0 < N) ? reg[r0] : 0, rg1 = (r1 < N) ? reg[r1] : 0;
-    float mx0 = -INFINITY, mx1 = -INFINITY;
+    // scale + relative position bias + key / query padding in ONE FFMA per score (padded table entries are -inf); row max
+    const float* b0p = bd + (long)r0 * NP + 2 * t4;
+    const float* b1p = bd + (long)r1 * NP + 2 * t4;
+    float mx0 = -1e30f, mx1 = -1e30f;  // finite floor: a fully padded query row gives exp2(-inf - (-1e30)) = 0, not NaN
 #pragma unroll
-    for (int nj = 0; nj < NT; ++nj)
+    for (int nj = 0; nj < NT; ++nj) {
+      const float2 ba = __ldg(reinterpret_cast<const float2*>(b0p + 8 * nj));
+      const float2 bb = __ldg(reinterpret_cast<const float2*>(b1p + 8 * nj));
+      sacc[nj][0] = fmaf(sacc[nj][0], sc, ba.x);
+      sacc[nj][1] = fmaf(sacc[nj][1], sc, ba.y);
+      sacc[nj][2] = fmaf(sacc[nj][2], sc, bb.x);
+      sacc[nj][3] = fmaf(sacc[nj][3], sc, bb.y);
+    }
+    if (masked) {  // CTA-uniform: only windows that straddle the cyclic-shift seam carry the -100 region mask (:186-199)
+      const int rg0 = reg[r0], rg1 = reg[r1];
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const int j = 8 * nj + 2 * t4 + (e & 1);
-        const int r = (e < 2) ? r0 : r1;
-        float v = -INFINITY;
-        if (j < N && r < N) {
-          v = sacc[nj][e] * scale + bd[r * N + j];
-          if (shift > 0 && reg[j] != ((e < 2) ? rg0 : rg1)) v += -100.0f;
+      for (int nj = 0; nj < NT; ++nj)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int j = 8 * nj + 2 * t4 + (e & 1);
+          if (reg[j] != ((e < 2) ? rg0 : rg1)) sacc[nj][e] += -100.0f * L2E;
         }
-        sacc[nj][e] = v;
-        if (e < 2) mx0 = fmaxf(mx0, v); else mx1 = fmaxf(mx1, v);
-      }
+    }
+#pragma unroll
+    for (int nj = 0; nj < NT; ++nj) {
+      mx0 = fmaxf(mx0, fmaxf(sacc[nj][0], sacc[nj][1]));
+      mx1 = fmaxf(mx1, fmaxf(sacc[nj][2], sacc[nj][3]));
+    }
     mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
     mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
     mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
     mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
     float sum0 = 0.f, sum1 = 0.f;
 #pragma unroll
-    for (int nj = 0; nj < NT; ++nj)
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const float m = (e < 2) ? mx0 : mx1;
-        const float pv = (sacc[nj][e] == -INFINITY) ? 0.f : expf(sacc[nj][e] - m);
-        sacc[nj][e] = pv;
-        if (e < 2) sum0 += pv; else sum1 += pv;
-      }
+    for (int nj = 0; nj < NT; ++nj) {
+      sacc[nj][0] = ex2_approx(sacc[nj][0] - mx0);
+      sacc[nj][1] = ex2_approx(sacc[nj][1] - mx0);
+      sacc[nj][2] = ex2_approx(sacc[nj][2] - mx1);
+      sacc[nj][3] = ex2_approx(sacc[nj][3] - mx1);
+      sum0 += sacc[nj][0] + sacc[nj][1];
+      sum1 += sacc[nj][2] + sacc[nj][3];
+    }
     sum0 += __shfl_xor_sync(0xffffffffu, sum0, 1);
     sum0 += __shfl_xor_sync(0xffffffffu, sum0, 2);
     sum1 += __shfl_xor_sync(0xffffffffu, sum1, 1);
@@ -381,16 +431,17 @@ using namespace mqdet;
 extern "C" int mqdet_patchify4(const float* img, int64_t B, int64_t H, int64_t W, void* out, void* stream) {
   MQ_REQUIRE(img && out && B > 0 && H > 0 && W > 0, "patchify4: bad args");
   const int Hp = (int)((H + 3) / 4), Wp = (int)((W + 3) / 4);
-  const long total = B * Hp * Wp * 48;
-  patchify4_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(img, (int)B, (int)H, (int)W, Hp, Wp,
-                                                                                     (__half*)out);
+  const long blocks = B * Hp * ((Wp + PF_TOK - 1) / PF_TOK);
+  MQ_REQUIRE(blocks < 2147483647L && ((uintptr_t)out & 15) == 0, "patchify4: output must be 16-byte aligned");
+  patchify4_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(img, (int)B, (int)H, (int)W, Hp, Wp, (__half*)out);
   return check_launch("patchify4_kernel");
 }
 
-extern "C" int mqdet_swin_window_attn(const void* qkv, const float* qkv_bias, const float* bias_dense, int64_t B, int64_t H,
+extern "C" int mqdet_swin_window_attn(const void* qkv, const float* qkv_bias, const float* bias_pad, int64_t B, int64_t H,
                                       int64_t W, int64_t heads, int64_t window, int64_t shift, float scale, void* out,
                                       void* stream) {
-  MQ_REQUIRE(qkv && qkv_bias && bias_dense && out, "swin_window_attn: null pointer");
+  MQ_REQUIRE(qkv && qkv_bias && bias_pad && out, "swin_window_attn: null pointer");
+  MQ_REQUIRE(((uintptr_t)bias_pad & 7) == 0, "swin_window_attn: bias_pad must be 8-byte aligned");
   MQ_REQUIRE(window == 7 || window == 12, "swin_window_attn: window 7 (Swin-T) or 12 (Swin-L), got %ld", (long)window);
   MQ_REQUIRE(shift >= 0 && shift < window, "swin_window_attn: bad shift");
   MQ_REQUIRE(((uintptr_t)qkv % 16) == 0 && (heads * 32 * 3) % 8 == 0, "swin_window_attn: qkv must be 16-byte aligned");
@@ -401,10 +452,10 @@ extern "C" int mqdet_swin_window_attn(const void* qkv, const float* qkv_bias, co
   dim3 grid((unsigned)units);
   if (window == 7) {
     swin_window_attn_kernel<7><<<grid, 128, SwinCfg<7>::SMEM, (cudaStream_t)stream>>>(
-        (const __half*)qkv, qkv_bias, bias_dense, (int)B, (int)H, (int)W, (int)heads, (int)shift, scale, (__half*)out);
+        (const __half*)qkv, qkv_bias, bias_pad, (int)B, (int)H, (int)W, (int)heads, (int)shift, scale, (__half*)out);
   } else {
     swin_window_attn_kernel<12><<<grid, 128, SwinCfg<12>::SMEM, (cudaStream_t)stream>>>(
-        (const __half*)qkv, qkv_bias, bias_dense, (int)B, (int)H, (int)W, (int)heads, (int)shift, scale, (__half*)out);
+        (const __half*)qkv, qkv_bias, bias_pad, (int)B, (int)H, (int)W, (int)heads, (int)shift, scale, (__half*)out);
   }
   return check_launch("swin_window_attn_kernel");
 }

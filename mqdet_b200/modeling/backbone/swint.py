@@ -40,13 +40,17 @@ class WindowAttention(nn.Module):
         self._dense = None
 
     def dense_bias(self):
-        """[heads, N, N] fp32 relative position bias (swint.py:124-127), cached per table version."""
+        """Relative position bias (swint.py:124-127) as the padded table ``mqdet_swin_window_attn`` reads: fp32 [heads, NP, NP],
+        NP = N rounded up to 16, = log2(e) * bias inside [N, N] and -inf outside; cached per table version."""
         t = self.relative_position_bias_table
         key = (t.data_ptr(), t._version)
         if self._dense is None or self._dense[0] != key:
             N = self.window_size * self.window_size
-            d = t.detach()[self.relative_position_index.view(-1)].view(N, N, -1).permute(2, 0, 1).float().contiguous()
-            self._dense = (key, d)
+            NP = (N + 15) // 16 * 16
+            d = t.detach()[self.relative_position_index.view(-1)].view(N, N, -1).permute(2, 0, 1).float()
+            pad = torch.full((d.shape[0], NP, NP), float("-inf"), dtype=torch.float32, device=d.device)
+            pad[:, :N, :N] = d * 1.4426950408889634
+            self._dense = (key, pad.contiguous())
         return self._dense[1]
 
 

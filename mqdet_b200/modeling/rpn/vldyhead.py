@@ -135,9 +135,9 @@ class DyConv(nn.Module):
             y0, aff0, at0 = branch(0, levels.N1, levels.seg_tail, levels.up_w)
         else:
             y2 = y0 = aff2 = aff0 = at2 = at0 = None
-        mid = ops.dyconv_combine(y1, y2, y0, aff1, aff2, aff0, at1, at2, at0, levels, B)
+        mid, mid_sums = ops.dyconv_combine(y1, y2, y0, aff1, aff2, aff0, at1, at2, at0, levels, B)
         fc = self.relu.fc
-        return ops.dyrelu(mid, levels, f32(fc[0].weight), f32(fc[0].bias), f32(fc[2].weight), f32(fc[2].bias))
+        return ops.dyrelu(mid, levels, f32(fc[0].weight), f32(fc[0].bias), f32(fc[2].weight), f32(fc[2].bias), mid_sums=mid_sums)
 
     def forward(self, inputs):
         """Reference signature: {"visual": [B,256,h,w] x L, "lang": ...} -> same dict structure."""
@@ -273,9 +273,9 @@ class VLDyHead(nn.Module):
         main = torch.cuda.current_stream(v16.device)
         for i in range(0, len(self.dyhead_tower), 3):
             fuse, bert, dyconv = self.dyhead_tower[i], self.dyhead_tower[i + 1], self.dyhead_tower[i + 2]
-            split = fuse.b_attn.forward_flat_split(v16, h32, lang_masks) if self.overlap_text_stream else None
+            split = fuse.b_attn.forward_flat_split(v16, h32, cm) if self.overlap_text_stream else None
             if split is None:
-                v16, h32 = fuse.b_attn.forward_flat(v16, h32, lang_masks)
+                v16, h32 = fuse.b_attn.forward_flat(v16, h32, cm)
                 h32, _ = BertLayer.forward(bert, h32, ops.cast_f16(h32), cm)
                 v16 = dyconv.forward_flat(v16, levels)
                 continue

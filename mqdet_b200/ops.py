@@ -667,24 +667,30 @@ def gn_attn(partial, seg, B, C, groups, weighted, gn_w, gn_b, eps, attn_w, attn_
 
 
 def dyconv_combine(y1, y2, y0, aff1, aff2, aff0, at1, at2, at0, levels, B):
+    """-> (mid [B,N,C] fp16, mid_sums [B, L, chunks, C] fp32: per-channel sums of `mid` over pixel ranges, for DyReLU's pool)."""
     global launch_count
     C = y1.shape[-1]
     mid = torch.empty((B, levels.N, C), dtype=torch.float16, device=y1.device)
+    sums = torch.empty((B, levels.n, int(load().mqdet_dyconv_combine_chunks()), C), dtype=torch.float32, device=y1.device)
     check(load().mqdet_dyconv_combine(_ptr(y1), _ptr(y2), _ptr(y0), _ptr(aff1), _ptr(aff2), _ptr(aff0), _ptr(at1),
-                                      _ptr(at2), _ptr(at0), levels.hw_ptr, levels.n, B, C, _ptr(mid), _stream()),
+                                      _ptr(at2), _ptr(at0), levels.hw_ptr, levels.n, B, C, _ptr(mid), _ptr(sums), _stream()),
           "dyconv_combine")
     launch_count += 1
-    return mid
+    return mid, sums
 
 
-def dyrelu(mid, levels, w1, b1, w2, b2):
-    """DyReLU over every level of mid [B,N,256] fp16 -> fp16."""
+def dyrelu(mid, levels, w1, b1, w2, b2, mid_sums=None):
+    """DyReLU over every level of mid [B,N,256] fp16 -> fp16.  ``mid_sums`` = the per-range channel sums dyconv_combine
+    produced (else they are taken from `mid` by chan_stats)."""
     global launch_count
     B, N, C = mid.shape
-    partial = chan_stats(mid, levels.seg_all, B, N)
+    if mid_sums is None:
+        partial, chunks, stats = chan_stats(mid, levels.seg_all, B, N), 32, 3
+    else:
+        partial, chunks, stats = mid_sums, mid_sums.shape[2], 1
     coef = torch.empty((B, levels.n, 4, C), dtype=torch.float32, device=mid.device)
-    check(load().mqdet_dyrelu_coef(_ptr(partial), _ptr(levels.seg_all), levels.n, B, C, w1.shape[0], _ptr(w1), _ptr(b1),
-                                   _ptr(w2), _ptr(b2), _ptr(coef), _stream()), "dyrelu_coef")
+    check(load().mqdet_dyrelu_coef(_ptr(partial), chunks, stats, _ptr(levels.seg_all), levels.n, B, C, w1.shape[0], _ptr(w1),
+                                   _ptr(b1), _ptr(w2), _ptr(b2), _ptr(coef), _stream()), "dyrelu_coef")
     out = torch.empty_like(mid)
     check(load().mqdet_dyrelu_apply(_ptr(mid), _ptr(coef), levels.hw_ptr, levels.n, B, C, _ptr(out), _stream()),
           "dyrelu_apply")

@@ -133,6 +133,21 @@ def test_patch_merge_ln(dev, C, H, W):
     assert_close(out, ref, 1e-3, "patch_merge_ln")
 
 
+@pytest.mark.parametrize("H,W", [(32, 448), (30, 301), (7, 5), (64, 1344)])
+def test_patchify4(dev, H, W):
+    """PatchEmbed input gather (swint.py:413-418): [B,3,H,W] fp32 -> fp16 [B*ceil(H/4)*ceil(W/4), 48], k = c*16 + i*4 + j, zero
+    padding on the right / bottom; widths that are / are not multiples of 4 and of the 64-patch run of a CTA."""
+    from mqdet_b200 import ops
+    g = torch.Generator().manual_seed(H * 1000 + W)
+    B = 2
+    img = torch.randn(B, 3, H, W, generator=g)
+    out, Hp, Wp = ops.patchify4(img.to(dev))
+    assert (Hp, Wp) == ((H + 3) // 4, (W + 3) // 4)
+    pad = torch.nn.functional.pad(img, (0, Wp * 4 - W, 0, Hp * 4 - H))
+    ref = pad.view(B, 3, Hp, 4, Wp, 4).permute(0, 2, 4, 1, 3, 5).reshape(B * Hp * Wp, 48).half()
+    assert torch.equal(out.cpu(), ref)
+
+
 def test_avgpool_levels(dev):
     from mqdet_b200 import ops
     g = torch.Generator().manual_seed(4)
