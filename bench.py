@@ -343,6 +343,7 @@ def main():
                          "yields are reported in config.postprocess (-1.5 is a denser stress point: every level hits top-k)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch the kernels eagerly instead of replaying the captured CUDA graph")
+    ap.add_argument("--gather-every", type=int, default=8, help="steps whose packed results one all-gather exchanges (N > 1)")
     ap.add_argument("--cpu-baseline-steps", type=int, default=1)
     ap.add_argument("--config", default="coco", choices=["coco", "lvis"],
                     help="coco: BASELINE config 2 (the headline metric); lvis: BASELINE config 3 (MQ-GLIP-L, chunked 1203-class prompt)")
@@ -402,13 +403,14 @@ def main():
     # (mqdet_b200/engine/inference.py; --no-graph runs the same calls eagerly)
     graph_note = "cuda-graph replay"
     try:
-        engine = InferenceEngine(model, caps, pmap, tuple(img.shape), sizes, use_graph=not args.no_graph, warmup=max(1, args.warmup // 2))
+        engine = InferenceEngine(model, caps, pmap, tuple(img.shape), sizes, use_graph=not args.no_graph, warmup=max(1, args.warmup // 2),
+                                 gather_every=args.gather_every)
     except Exception as e:  # noqa: BLE001 - e.g. a collective that cannot be captured on this stack: fall back to eager launches
         if args.no_graph:
             raise
         graph_note = f"eager (graph capture failed: {type(e).__name__}: {str(e)[:120]})"
         torch.cuda.synchronize()
-        engine = InferenceEngine(model, caps, pmap, tuple(img.shape), sizes, use_graph=False, warmup=1)
+        engine = InferenceEngine(model, caps, pmap, tuple(img.shape), sizes, use_graph=False, warmup=1, gather_every=args.gather_every)
     if args.no_graph:
         graph_note = "eager launches (--no-graph)"
     engine.stage[0].copy_(img_dev)
@@ -429,11 +431,13 @@ def main():
         ev[i][0].record()
         engine.device_step(k=i & 1)
         ev[i][1].record()
-    # the all-gather of a step runs on the engine's result stream behind the forward; a step's bracket holds the wait for
-    # the gather issued two steps earlier, and this last bracket holds the two still in flight: every collective is timed
+    # the exchange ring (one all-gather per `gather_every` steps) runs on the engine's result stream behind the forward; a
+    # step's bracket holds the wait for the result work issued two steps earlier, and this last bracket the flush of the ring
+    # and whatever is still in flight: every collective is timed
     tail = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
     tail[0].record()
-    for e in engine.res_done:
+    engine.flush()  # a partly filled exchange ring is gathered inside the timed region
+    for e in engine.res_done + [engine.gather_done]:
         main_stream.wait_event(e)
     tail[1].record()
     barrier()
@@ -458,6 +462,7 @@ def main():
     e0.record()
     for boxlists in engine.run([img_host] * args.steps):
         n_boxes += sum(len(bl) for bl in boxlists)
+    torch.cuda.current_stream().wait_event(engine.gather_done)  # the run's last exchange (flush) is inside the timed region
     e1.record()
     barrier()
     e2e_wall_ms = 1e3 * (time.time() - t_wall) / args.steps
@@ -527,7 +532,7 @@ def main():
             "config": {"workload": f"MQ-GLIP-T full forward (Swin-T+FPN, BERT+GCP+PreSelect, 6x fusion/DyConv, dot-product "
                                    f"head, ATSS+ml_nms), batch {B}/GPU, 800x1333 (padded 800x1344), 80-class prompt T=256, "
                                    f"K=5 queries/class (BASELINE config 2), random-init weights",
-                       "global_batch": world * B, "parallelism": f"image-sharded dp{world}, 1 NCCL all-gather of [B,{model.max_out() + 1},6] (detections + count row)",
+                       "global_batch": world * B, "parallelism": f"image-sharded dp{world}, 1 NCCL all-gather of [{engine.G},B,{model.max_out() + 1},6] (detections + count row) per {engine.G} steps (+ flush)",
                        "launch": graph_note + ("; tower text branch on a second stream" if model.rpn.head.overlap_text_stream else ""),
                        "l2": "256 MiB buffer written between timed steps", "postprocess": pp,
                        "tokenisation": "pre-tokenised ids (no bert-base-uncased vocabulary offline); prompt state cached per prompt"},
@@ -546,7 +551,7 @@ def main():
                                                              "tensor peak, algorithmic bytes / HBM peak) / measured time",
                          "stages": stages},
             "e2e": {"value": world * B / (e2e_ms / 1e3), "unit": "images/s", "ms_per_step": e2e_ms, "wall_ms_per_step": e2e_wall_ms,
-                    "h2d_bytes_per_step": img_host.numel() * 4, "d2h_bytes_per_step": engine.host[0].numel() * 4,
+                    "h2d_bytes_per_step": img_host.numel() * 4, "d2h_bytes_per_step": engine.host[0].numel() * 4 + (engine.gathered_host.numel() * 4 // engine.G if world > 1 else 0),
                     "api": "mqdet_b200.engine.inference.InferenceEngine.run(host batches) -> list[BoxList] per batch",
                     "boxes_returned": n_boxes},
             "gpu_launches": launches, "clocks": clk,

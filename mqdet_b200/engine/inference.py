@@ -10,10 +10,13 @@ images + one prompt), same outputs (``list[BoxList]`` per batch), but
     are never starved by the launch rate;
   * the host->device copy of batch s+1 (pinned memory -> a second device buffer, on a copy stream) overlaps the replay of
     batch s; the packed fixed-shape result ``[B, max_out + 1, 6]`` (detections + count row) is the ONE device->host copy;
-  * with ``torch.distributed`` initialised, the ONE collective of the data path (all-gather of the packed result over
-    NCCL / NVLink) and the device->host copy run on a separate RESULT stream behind the forward: the next replay starts
-    without waiting for the slowest rank to reach the collective, so ranks may drift by one step instead of meeting at a
-    barrier every step (the gather of step s only has to finish before the forward of step s+2 reuses its buffers).
+  * with ``torch.distributed`` initialised, the ONE collective of the data path (all-gather of the packed results over
+    NCCL / NVLink) and the device->host copies run on a separate RESULT stream behind the forward: the next replay starts
+    without waiting for the slowest rank to reach the collective.  The reference gathers the predictions of all ranks ONCE
+    per evaluation (engine/inference.py:294 -> utils/comm.py:61-102, a pickled variable-length all_gather); here the packed
+    fixed-shape results of ``gather_every`` consecutive steps accumulate in a device ring and are exchanged by one
+    ``all_gather_into_tensor`` (plus a final ``flush()``): an NCCL kernel that sits on an SM waiting for a peer takes that SM
+    away from the persistent one-CTA-per-SM kernels of the next forward, so the collective is kept rare, not per step.
 
 Nothing here computes: it is stream / graph / buffer plumbing around ``GeneralizedVLRCNN_New.forward_device``.
 """
@@ -26,9 +29,11 @@ from ..structures.image_list import ImageList
 
 
 class InferenceEngine:
-    def __init__(self, model, captions, positive_map, batch_shape, image_sizes, *, use_graph=True, gather=True, warmup=2):
+    def __init__(self, model, captions, positive_map, batch_shape, image_sizes, *, use_graph=True, gather=True, warmup=2,
+                 gather_every=8):
         """model: GeneralizedVLRCNN_New (eval, on its CUDA device); captions / positive_map: the prompt of the run;
-        batch_shape: (B, 3, H, W) of the padded batch tensor; image_sizes: [(h, w)] * B un-padded sizes."""
+        batch_shape: (B, 3, H, W) of the padded batch tensor; image_sizes: [(h, w)] * B un-padded sizes;
+        gather_every: steps whose packed results are exchanged by one all-gather (N > 1)."""
         self.model = model
         self.captions, self.positive_map = captions, positive_map
         self.dev = next(model.parameters()).device
@@ -44,15 +49,25 @@ class InferenceEngine:
         self.graphs = [None, None]
         self.outs = [None, None]
         self.max_out = model.max_out()
-        self.host = [torch.empty((self.world * self.B, self.max_out + 1, 6), dtype=torch.float32).pin_memory() for _ in range(2)]
+        # local packed result of a step -> pinned host (the BoxLists of `run`)
+        self.host = [torch.empty((self.B, self.max_out + 1, 6), dtype=torch.float32).pin_memory() for _ in range(2)]
         self.d2h_done = [torch.cuda.Event(), torch.cuda.Event()]
-        # result stream: all-gather (N > 1) + device->host copy of step s while the main stream already runs step s+1
+        # result stream: ring append (+ all-gather every G steps, N > 1) + device->host copies of step s while the main stream
+        # already runs step s+1
         self.result_stream = torch.cuda.Stream(device=self.dev)
-        self.res_done = [torch.cuda.Event(), torch.cuda.Event()]  # gather / D2H that read outs[k]["packed"] finished
-        self.gathered = [torch.empty((self.world * self.B, self.max_out + 1, 6), dtype=torch.float32, device=self.dev)
-                         if self.world > 1 else None for _ in range(2)]
+        self.res_done = [torch.cuda.Event(), torch.cuda.Event()]  # everything that read outs[k]["packed"] finished
+        self.G = max(1, int(gather_every))
+        self.ring_fill = 0            # steps appended since the last exchange
+        self.exchanges = 0            # all-gathers issued
+        self.gather_done = torch.cuda.Event()
+        if self.world > 1:
+            self.ring = torch.zeros((self.G, self.B, self.max_out + 1, 6), dtype=torch.float32, device=self.dev)
+            self.gathered = torch.zeros((self.world, self.G, self.B, self.max_out + 1, 6), dtype=torch.float32, device=self.dev)
+            self.gathered_host = torch.zeros(tuple(self.gathered.shape), dtype=torch.float32).pin_memory()
+        else:
+            self.ring = self.gathered = self.gathered_host = None
         main = torch.cuda.current_stream(self.dev)
-        for ev in self.fw_done + self.res_done:
+        for ev in self.fw_done + self.res_done + [self.gather_done]:
             ev.record(main)
         # warm-up on the real buffers: fills every per-prompt / per-shape cache (token ids, selected queries, index tables,
         # level tables, fp16 weight copies, tensor maps, shared-memory opt-ins) so that the capture sees launches only
@@ -60,6 +75,7 @@ class InferenceEngine:
             for k in range(2):
                 self.outs[k] = self._forward(k)
                 self._collect(k, to_host=False)
+        self.flush()
         torch.cuda.synchronize(self.dev)
         self.use_graph = bool(use_graph)
         if self.use_graph:
@@ -77,8 +93,8 @@ class InferenceEngine:
         return {"packed": out["det_packed"], "raw": out}
 
     def _collect(self, k, to_host=True):
-        """On the result stream, behind the forward of slot k: the ONE collective of the data path (N > 1), then the ONE
-        device->host copy."""
+        """On the result stream, behind the forward of slot k: append the packed result to the exchange ring (N > 1; the ONE
+        collective of the data path runs when the ring is full), and the device->host copy of the local result."""
         main = torch.cuda.current_stream(self.dev)
         self.fw_done[k].record(main)
         rs = self.result_stream
@@ -86,12 +102,38 @@ class InferenceEngine:
             rs.wait_event(self.fw_done[k])
             res = self.outs[k]["packed"]
             if self.world > 1:
-                res = parallel.all_gather_packed(res, out=self.gathered[k])
+                self.ring[self.ring_fill].copy_(res, non_blocking=True)
+                self.ring_fill += 1
+                if self.ring_fill == self.G:
+                    self._exchange(rs)
             if to_host:
                 self.host[k].copy_(res, non_blocking=True)
                 self.d2h_done[k].record(rs)
             self.res_done[k].record(rs)
         return res
+
+    def _exchange(self, rs):
+        """(result stream) all-gather of the ring -> gathered [world, G, B, max_out + 1, 6] -> pinned host copy."""
+        parallel.all_gather_packed(self.ring.view(self.G * self.B, self.max_out + 1, 6),
+                                   out=self.gathered.view(self.world * self.G * self.B, self.max_out + 1, 6))
+        self.gathered_host.copy_(self.gathered, non_blocking=True)
+        self.gather_done.record(rs)
+        self.last_exchange_steps = self.ring_fill
+        self.ring_fill = 0
+        self.exchanges += 1
+
+    def flush(self):
+        """Exchange a partly filled ring (end of an evaluation run; every rank must call it the same number of times)."""
+        if self.world > 1 and self.ring_fill > 0:
+            with torch.cuda.stream(self.result_stream):
+                self._exchange(self.result_stream)
+
+    def gathered_results(self):
+        """Pinned host tensor [world, steps, B, max_out + 1, 6] of the LAST exchange (waits for its copy), rank-major."""
+        if self.world == 1:
+            return None
+        self.gather_done.synchronize()
+        return self.gathered_host[:, :self.last_exchange_steps]
 
     # -- one step on staging buffer k: (graph replay | eager forward) -> [all-gather ->] async D2H of the packed result ----
     def _step(self, k, to_host):
@@ -115,14 +157,13 @@ class InferenceEngine:
             self.up_done[k].record(self.copy_stream)
 
     def device_step(self, images_dev=None, k=0):
-        """Device-resident step (bench `value`): optional device->device refresh of the input, then one replay and (N > 1)
-        the all-gather on the result stream; no host traffic, no synchronisation.  Returns the device-side result dict
-        (``gathered`` = the rank-major result of all ranks, valid once the result stream has caught up)."""
+        """Device-resident step (bench `value`): optional device->device refresh of the input, then one replay; on the result
+        stream the packed result joins the exchange ring (N > 1).  No host traffic, no synchronisation."""
         if images_dev is not None and images_dev.data_ptr() != self.stage[k].data_ptr():
             self.stage[k].copy_(images_dev, non_blocking=True)
         self.up_done[k].record(torch.cuda.current_stream(self.dev))
         o = self._step(k, False)
-        return {"packed": o["packed"], "raw": o["raw"], "gathered": self.gathered[k]}
+        return {"packed": o["packed"], "raw": o["raw"]}
 
     def close(self):
         """Drain both streams and drop the captured graphs (call before destroying the process group)."""
@@ -139,8 +180,7 @@ class InferenceEngine:
         """BoxLists of the LOCAL images from pinned host buffer k (waits for that step's device->host copy only)."""
         from ..structures.bounding_box import BoxList
         self.d2h_done[k].synchronize()
-        rank = dist.get_rank() if self.world > 1 else 0
-        mine = self.host[k][rank * self.B:(rank + 1) * self.B]
+        mine = self.host[k]
         res = []
         for b, (h, w) in enumerate(self.image_sizes):
             n = int(round(float(mine[b, self.max_out, 0])))
@@ -172,6 +212,8 @@ class InferenceEngine:
             if nxt is not None:
                 self._upload(k ^ 1, nxt)
                 self._launch(k ^ 1)
+            if nxt is None:
+                self.flush()  # the tail of the run reaches the other ranks
             yield self.to_boxlists(k)
             if nxt is None:
                 return
