@@ -48,17 +48,19 @@ def cpu_threads():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    """nvidia-smi clocks / power / throttle reasons of every GPU of the job, sampled DURING the timed region (rank 0 polls)."""
 
     def __init__(self, idx):
-        self.idx, self.rows, self.proc = idx, [], None
+        self.idx = list(idx) if isinstance(idx, (list, tuple, range)) else [idx]
+        self.rows, self.proc = [], None
 
     def start(self):
-        q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100",
-                                          "-i", str(self.idx)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "-i", ",".join(str(i) for i in self.idx)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
             self.proc = None
@@ -71,12 +73,19 @@ class ClockSampler:
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
-        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
-        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
+        rows = [r for r in self.rows if len(r) >= 8 and r[1].isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({n for r in self.rows if len(r) >= 7 for n, v in zip(names, r[3:7]) if v.lower().startswith("active")})
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
-                "samples": len(sm)}
+        reasons = sorted({n for r in rows for n, v in zip(names, r[4:8]) if v.lower().startswith("active")})
+        per_gpu = []
+        for g in sorted({r[0] for r in rows}):
+            sm = sorted(int(r[1]) for r in rows if r[0] == g)
+            pw = sorted(float(r[3]) for r in rows if r[0] == g and r[3].replace(".", "", 1).isdigit())
+            per_gpu.append({"gpu": int(g), "sm_mhz": sm[len(sm) // 2], "power_w": pw[len(pw) // 2] if pw else None})
+        sm_all = sorted(int(r[1]) for r in rows)
+        mx = [int(r[2]) for r in rows if r[2].isdigit()]
+        # sm_mhz = the LOWEST per-GPU median under load (the slowest GPU paces a max-over-ranks number)
+        return {"sm_mhz": min(g["sm_mhz"] for g in per_gpu) if per_gpu else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm_all), "per_gpu": per_gpu}
 
 
 def traffic_note():
@@ -226,7 +235,7 @@ def run_lvis(args):
     barrier()
     ops.launch_count = 0
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    clocks = ClockSampler(local)
+    clocks = ClockSampler(range(world))
     if rank == 0:
         clocks.start()
     for i in range(args.steps):
@@ -420,7 +429,7 @@ def main():
     for i in range(args.warmup):
         engine.device_step(k=i & 1)
     barrier()
-    clocks = ClockSampler(local)  # rank 0 samples its own GPU (one nvidia-smi poller per node is enough)
+    clocks = ClockSampler(range(world))  # rank 0 polls every GPU of the job (local ranks 0..N-1 on the one node)
     if rank == 0:
         clocks.start()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
@@ -444,7 +453,11 @@ def main():
     launches = launches_per_step * args.steps
     ms = (sum(a.elapsed_time(b) for a, b in ev) + tail[0].elapsed_time(tail[1])) / args.steps
     t = torch.tensor([ms], device=dev)
+    ms_per_rank = [ms]
     if world > 1:
+        allms = torch.empty((world,), device=dev)
+        dist.all_gather_into_tensor(allms, t)
+        ms_per_rank = [float(x) for x in allms.tolist()]   # reported: tells a slow GPU from a systematic N > 1 cost
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = float(t.item())
     value = world * B / (ms / 1e3)
@@ -554,7 +567,7 @@ def main():
                     "h2d_bytes_per_step": img_host.numel() * 4, "d2h_bytes_per_step": engine.host[0].numel() * 4 + (engine.gathered_host.numel() * 4 // engine.G if world > 1 else 0),
                     "api": "mqdet_b200.engine.inference.InferenceEngine.run(host batches) -> list[BoxList] per batch",
                     "boxes_returned": n_boxes},
-            "gpu_launches": launches, "clocks": clk,
+            "gpu_launches": launches, "clocks": clk, "ms_per_step_per_rank": ms_per_rank,
         }
         if not args.no_cpu_baseline and world == 1:
             import torch as _t
