@@ -380,6 +380,35 @@ int mqdet_topk_desc(const float* keys, int64_t B, int64_t n, int64_t k, int64_t*
 int mqdet_gather_rows_f32(const float* src, const int64_t* idx, int64_t B, int64_t rows_src, int64_t k, int64_t D, int sigmoid,
                           float* dst, void* stream);
 
+/* ---- GroundingDINO encoder / decoder assembly (BASELINE config 4): the device ops that are not GEMMs, LayerNorms,
+ * softmaxes or ms_deform_attn -----------------------------------------------------------------------------------------------
+ *   mqdet_add_cast       : out = (a + b) * rowgate[row]  (b, rowgate optional; a gated-off row is exactly 0) -> f16 and / or f32.
+ *                          with_pos_embed of groundingdino_new/models/GroundingDINO/transformer.py:738,843-870 and the masked
+ *                          memory of gen_encoder_output_proposals (utils.py:110-112).  D % 4 == 0, 16-byte aligned pointers.
+ *   mqdet_groupnorm_rows : nn.GroupNorm(groups, C) over x [B][HW][C] (f16 | f32 rows, channel-contiguous): input_proj =
+ *                          Conv2d + GroupNorm(32, 256) (groundingdino.py:214-236).  workspace: mqdet_groupnorm_rows_workspace_floats.
+ *   mqdet_box_refine_sine: decoder box refinement + conditional-query embedding (transformer.py:636-650,688-700):
+ *                            ref = delta ? sigmoid(delta + (ref_is_logit ? ref_in : inverse_sigmoid(ref_in)))   (util/misc.py:721-725)
+ *                                        : (ref_is_logit ? sigmoid(ref_in) : ref_in)
+ *                            ref_input[b][q][l] = ref * (vr[b][l].x, vr[b][l].y, vr[b][l].x, vr[b][l].y)
+ *                            sine16[b][q][512]  = gen_sineembed_for_position(ref_input[:, :, 0, :])  (utils.py:203-232), optional
+ *                          delta [B*nq][ldd] f32 or NULL; ref_in / ref_out [B*nq][4]; valid_ratios [B][L][2]; ref_out optional.
+ *   mqdet_gdino_detections: convert_groundingdino_to_glip_output (groundingdino.py:291-335) for raw class logits [B][nq][T] f32
+ *                          (-inf on padding): sigmoid, per-class mean over its tokens (tokmap int32 [C][max_tok], -1 padded),
+ *                          best class (lowest index on ties), keep if score > box_threshold, boxes cxcywh (normalised) -> xyxy in
+ *                          pixels of img_wh[b] = (W, H), clipped to [0, W-1] x [0, H-1], boxes with a negative side dropped; kept rows in
+ *                          query order -> out [B][max_out + 1][6] = (x1, y1, x2, y2, score, label), row max_out = (count, 0, ...). */
+int mqdet_add_cast(const float* a, const float* b, const float* rowgate, int64_t rows, int64_t D, void* out16, float* out32,
+                   void* stream);
+int64_t mqdet_groupnorm_rows_workspace_floats(int64_t B, int64_t C);
+int mqdet_groupnorm_rows(const void* x, int x_dtype, int64_t B, int64_t HW, int64_t C, int64_t groups, const float* gamma,
+                         const float* beta, float eps, void* out16, float* out32, float* workspace, void* stream);
+int mqdet_box_refine_sine(const float* delta, int64_t ldd, const float* ref_in, int ref_is_logit, const float* valid_ratios, int64_t B,
+                          int64_t nq, int64_t L, float* ref_out, float* ref_input, void* sine16, void* stream);
+int mqdet_gdino_detections(const float* logits, int64_t T, const float* boxes, const int32_t* tokmap, int64_t C, int64_t max_tok,
+                           const float* img_wh, float box_threshold, int64_t B, int64_t nq, int64_t max_out, float* out,
+                           void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -60,3 +60,26 @@ def mq_glip_l_cfg(**over):
     cfg = mq_glip_t_cfg(**base)
     cfg.TEST.CHUNKED_EVALUATION = 40
     return cfg
+
+
+def mq_groundingdino_t_cfg(**over):
+    """configs/pretrain/mq-groundingdino-t.yaml + the GROUNDINGDINO block of maskrcnn_benchmark/config/defaults.py:944-1001
+    (Swin-T with three outputs + one extra stride-2 level, 6 encoder / 6 decoder layers, 900 queries, two-stage "standard",
+    text enhancer + fusion layers + text cross-attention, box threshold 0.05)."""
+    base = {"INPUT.PIXEL_MEAN": [0.485, 0.456, 0.406], "INPUT.PIXEL_STD": [0.229, 0.224, 0.225],
+            "MODEL.ROI_BOX_HEAD.POOLER_SCALES": (0.125, 0.0625, 0.03125, 0.015625)}
+    base.update(over)
+    cfg = mq_glip_t_cfg(**{k: v for k, v in base.items() if not k.startswith("GROUNDINGDINO.")})
+    cfg.GROUNDINGDINO = NS(
+        enabled=True, modelname="groundingdino", backbone="swin_T_224_1k", position_embedding="sine", pe_temperatureH=20,
+        pe_temperatureW=20, return_interm_indices=[1, 2, 3], enc_layers=6, dec_layers=6, pre_norm=False, dim_feedforward=2048,
+        hidden_dim=256, dropout=0.0, nheads=8, num_queries=900, query_dim=4, num_patterns=0, num_feature_levels=4, enc_n_points=4,
+        dec_n_points=4, two_stage_type="standard", two_stage_bbox_embed_share=False, two_stage_class_embed_share=False,
+        transformer_activation="relu", dec_pred_bbox_embed_share=True, embed_init_tgt=True, max_text_len=256,
+        text_encoder_type="bert-base-uncased", use_text_enhancer=True, use_fusion_layer=True, use_checkpoint=False,
+        use_transformer_ckpt=False, use_text_cross_attention=True, text_dropout=0.0, fusion_dropout=0.0, fusion_droppath=0.1,
+        sub_sentence_present=True, box_threshold=0.05)
+    for k, v in base.items():
+        if k.startswith("GROUNDINGDINO."):
+            setattr(cfg.GROUNDINGDINO, k.split(".", 1)[1], v)
+    return cfg

@@ -52,16 +52,18 @@ class BiAttentionBlock(nn.Module):
         self.gamma_l = nn.Parameter(init_values * torch.ones((l_dim)), requires_grad=True)
 
     @torch.no_grad()
-    def forward(self, v, l, attention_mask_v=None, attention_mask_l=None):
+    def forward(self, v, l, attention_mask_v=None, attention_mask_l=None, keep_v=None, keep_l=None):
         """v [B,N,v_dim], l [B,T,l_dim] fp32 -> (v', l') fp32:  x' = LN(x) + gamma * delta  (residual on the NORMALISED inputs,
-        :286-296)."""
+        :286-296).  ``keep_v`` / ``keep_l``: the masks already as fp32 1 keep / 0 padding (the assembly builds them once)."""
         if not v.is_cuda:
             raise MqdetError("BiAttentionBlock: CUDA tensors required (no CPU fallback)")
         nv, nl = self.layer_norm_v, self.layer_norm_l
         vn16, vn32 = ops.layernorm(v.float().contiguous(), f32(nv.weight), f32(nv.bias), nv.eps, out16=True, out32=True)
         ln16, ln32 = ops.layernorm(l.float().contiguous(), f32(nl.weight), f32(nl.bias), nl.eps, out16=True, out32=True)
         a = self.attn
-        dv, dl = a._attend(vn16, ln16, a._keep(attention_mask_l), mask_v=a._keep(attention_mask_v),
+        keep_l = a._keep(attention_mask_l) if keep_l is None else keep_l
+        keep_v = a._keep(attention_mask_v) if keep_v is None else keep_v
+        dv, dl = a._attend(vn16, ln16, keep_l, mask_v=keep_v,
                            v_epilogue=dict(gate=f32(self.gamma_v), residual=vn32, out_dtype=torch.float32),
                            l_epilogue=dict(gate=f32(self.gamma_l), residual=ln32))
         return dv, dl

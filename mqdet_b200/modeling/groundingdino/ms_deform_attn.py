@@ -68,20 +68,27 @@ class MultiScaleDeformableAttention(nn.Module):
             query = query + query_pos
         if not self.batch_first:
             query, value = query.permute(1, 0, 2), value.permute(1, 0, 2)
-        bs, nq, E = query.shape
-        nv = value.shape[1]
-        sizes = [(int(h), int(w)) for h, w in (spatial_shapes.tolist() if torch.is_tensor(spatial_shapes) else spatial_shapes)]
-        assert sum(h * w for h, w in sizes) == nv
-        levels = ops.get_levels(sizes, query.device)
-        H, L, P = self.num_heads, self.num_levels, self.num_points
         keep = None
         if key_padding_mask is not None:   # value.masked_fill(mask, 0) as a per-row gate of the projection (:282-283)
             keep = (~key_padding_mask.bool()).reshape(-1).float().contiguous()
-        v16 = ops.gemm(ops.cast_f16(value.contiguous()).view(bs * nv, E), w16(self.value_proj.weight), bias=f32(self.value_proj.bias),
+        out = self.core(ops.cast_f16(query.contiguous()), ops.cast_f16(value.contiguous()), keep, reference_points, spatial_shapes)
+        return out if self.batch_first else out.permute(1, 0, 2)
+
+    @torch.no_grad()
+    def core(self, q16, v16_in, keep, reference_points, spatial_shapes, residual=None):
+        """Batch-first fp16 operands: q16 [bs, nq, E] (query + query_pos already added), v16_in [bs, nv, E] (un-projected value),
+        keep fp32 [bs*nv] (1 = valid, 0 = padding) or None -> fp32 [bs, nq, E] (+ ``residual`` fp32 when given)."""
+        bs, nq, E = q16.shape
+        nv = v16_in.shape[1]
+        sizes = [(int(h), int(w)) for h, w in (spatial_shapes.tolist() if torch.is_tensor(spatial_shapes) else spatial_shapes)]
+        assert sum(h * w for h, w in sizes) == nv
+        levels = ops.get_levels(sizes, q16.device)
+        H, L, P = self.num_heads, self.num_levels, self.num_points
+        v16 = ops.gemm(v16_in.view(bs * nv, E), w16(self.value_proj.weight), bias=f32(self.value_proj.bias),
                        gate=keep, gate_mode=VEC_PER_ROW if keep is not None else 0).view(bs, nv, E)
         wc, bc = self._offsets_and_logits_weights()
-        proj = ops.gemm(ops.cast_f16(query.contiguous()).view(bs * nq, E), wc, bias=bc, out_dtype=torch.float32)  # [bs*nq, H*L*P*3]
+        proj = ops.gemm(q16.view(bs * nq, E), wc, bias=bc, out_dtype=torch.float32)  # [bs*nq, H*L*P*3]
         out16 = ops.ms_deform_attn(v16, proj, H * L * P * 2, reference_points.float().contiguous(), levels, H, P)
         out = ops.gemm(out16.view(bs * nq, E), w16(self.output_proj.weight), bias=f32(self.output_proj.bias),
-                       out_dtype=torch.float32).view(bs, nq, E)
-        return out if self.batch_first else out.permute(1, 0, 2)
+                       out_dtype=torch.float32, residual=None if residual is None else residual.view(bs * nq, E))
+        return out.view(bs, nq, E)

@@ -311,7 +311,8 @@ class BertLayer(nn.Module):
 
     @torch.no_grad()
     def forward(self, h32, h16, colmask):
-        """h32 fp32 [B,T,D] (+ its fp16 copy h16), colmask fp32 [B,T] (1 keep / 0 pad) -> (fp32, fp16) outputs."""
+        """h32 fp32 [B,T,D] (+ its fp16 copy h16), colmask fp32 [B,T] (1 keep / 0 pad; or [B,T,T] per query) -> (fp32, fp16)
+        outputs."""
         B, T, D = h32.shape
         H = self.heads
         d = D // H
@@ -321,11 +322,19 @@ class BertLayer(nn.Module):
         q, k = qk[:, :, 0], qk[:, :, 1]
         # V^T[b] = W_v . h[b]^T + b_v  -> [B, H, d, T]: P.V below is then K-major x K-major, no transpose kernel
         vT = ops.gemm(w16(sa.value.weight), h16, bias=f32(sa.value.bias), bias_mode=VEC_PER_ROW).view(B, H, d, T)
-        scores = torch.empty((B, H, T, T), dtype=torch.float32, device=h32.device)
-        ops.gemm(q.permute(0, 2, 1, 3), k.permute(0, 2, 1, 3), out=scores, alpha=d ** -0.5, clamp=self.clamp)
-        p = ops.softmax_rows(scores, colmask=colmask, rows_per_batch=H * T, mask_value=-10000.0)
         ctx = torch.empty((B, T, H, d), dtype=torch.float16, device=h32.device)
-        ops.gemm(p, vT, out=ctx.permute(0, 2, 1, 3))
+        if colmask.dim() == 3:
+            # per-query mask [B, T, T] (GroundingDINO's per-category block-diagonal text mask, bertwarper.py:271-320): scores laid
+            # out [B, T, H, T] so that the H rows of one (image, query) are consecutive and share one mask row
+            scores = torch.empty((B, T, H, T), dtype=torch.float32, device=h32.device)
+            ops.gemm(q.permute(0, 2, 1, 3), k.permute(0, 2, 1, 3), out=scores.permute(0, 2, 1, 3), alpha=d ** -0.5, clamp=self.clamp)
+            p = ops.softmax_rows(scores, colmask=colmask, rows_per_batch=H, mask_value=-10000.0)
+            ops.gemm(p.permute(0, 2, 1, 3), vT, out=ctx.permute(0, 2, 1, 3))
+        else:
+            scores = torch.empty((B, H, T, T), dtype=torch.float32, device=h32.device)
+            ops.gemm(q.permute(0, 2, 1, 3), k.permute(0, 2, 1, 3), out=scores, alpha=d ** -0.5, clamp=self.clamp)
+            p = ops.softmax_rows(scores, colmask=colmask, rows_per_batch=H * T, mask_value=-10000.0)
+            ops.gemm(p, vT, out=ctx.permute(0, 2, 1, 3))
         ao = self.attention.output
         # BertSelfOutput has no clamp_values (rpn/modeling_bert.py:186-190); only the attention scores, BertIntermediate
         # (before and after the GELU: same result as one clamp after it) and BertOutput are clamped (:140-143, 250-271)

@@ -898,3 +898,85 @@ def ms_deform_attn(value16, proj32, aw_col0, ref, levels, heads, points, out_dty
           "ms_deform_attn")
     launch_count += 1
     return out
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# GroundingDINO encoder / decoder assembly (csrc/gdino_asm.cu)
+# ----------------------------------------------------------------------------------------------------------------------
+def add_cast(a32, b32=None, rowgate=None, *, out16=True, out32=False):
+    """(a + b) * rowgate[row] over contiguous fp32 [..., D] tensors -> fp16 and / or fp32 (a gated-off row is exactly 0)."""
+    global launch_count
+    _need_cuda(a32, b32, rowgate)
+    if a32.dtype != torch.float32 or (b32 is not None and (b32.dtype != torch.float32 or b32.shape != a32.shape)):
+        raise TypeError("add_cast: fp32 tensors of one shape expected")
+    a32 = a32.contiguous()
+    b32 = None if b32 is None else b32.contiguous()
+    D = a32.shape[-1]
+    rows = a32.numel() // D
+    if rowgate is not None and (rowgate.dtype != torch.float32 or rowgate.numel() != rows):
+        raise ValueError("add_cast: rowgate must be fp32 with one entry per row")
+    o16 = torch.empty(a32.shape, dtype=torch.float16, device=a32.device) if out16 else None
+    o32 = torch.empty(a32.shape, dtype=torch.float32, device=a32.device) if out32 else None
+    check(load().mqdet_add_cast(_ptr(a32), _ptr(b32), _ptr(rowgate), rows, D, _ptr(o16), _ptr(o32), _stream()), "add_cast")
+    launch_count += 1
+    if out16 and out32:
+        return o16, o32
+    return o16 if out16 else o32
+
+
+def groupnorm_rows(x, groups, gamma, beta, eps=1e-5, *, out16=True, out32=False):
+    """nn.GroupNorm(groups, C) over x [B, HW, C] (fp16 / fp32 rows) -> fp16 and / or fp32 [B, HW, C]."""
+    global launch_count
+    _need_cuda(x, gamma, beta)
+    x = x.contiguous()
+    B, HW, C = x.shape
+    ws = torch.empty((int(load().mqdet_groupnorm_rows_workspace_floats(B, C)),), dtype=torch.float32, device=x.device)
+    o16 = torch.empty(x.shape, dtype=torch.float16, device=x.device) if out16 else None
+    o32 = torch.empty(x.shape, dtype=torch.float32, device=x.device) if out32 else None
+    check(load().mqdet_groupnorm_rows(_ptr(x), _dt(x), B, HW, C, int(groups), _ptr(gamma), _ptr(beta), float(eps), _ptr(o16),
+                                      _ptr(o32), _ptr(ws), _stream()), "groupnorm_rows")
+    launch_count += 2
+    if out16 and out32:
+        return o16, o32
+    return o16 if out16 else o32
+
+
+def box_refine_sine(ref_in, valid_ratios, *, delta=None, ref_is_logit=False, want_sine=True):
+    """Decoder box refinement + conditional query embedding.  ref_in fp32 [B, nq, 4]; valid_ratios fp32 [B, L, 2]; delta fp32
+    [B, nq, >=4] (row stride = its last-dim size) or None -> (ref [B,nq,4], ref_input [B,nq,L,4], sine fp16 [B,nq,512] | None)."""
+    global launch_count
+    _need_cuda(ref_in, valid_ratios, delta)
+    B, nq, _ = ref_in.shape
+    L = valid_ratios.shape[1]
+    ref_in = ref_in.float().contiguous()
+    vr = valid_ratios.float().contiguous()
+    ldd = 0
+    if delta is not None:
+        if delta.dtype != torch.float32 or delta.stride(-1) != 1:
+            raise TypeError("box_refine_sine: delta must be fp32, last dim contiguous")
+        d2 = delta.reshape(B * nq, delta.shape[-1])
+        ldd = d2.stride(0)
+        delta = d2
+    ref = torch.empty((B, nq, 4), dtype=torch.float32, device=ref_in.device)
+    ref_input = torch.empty((B, nq, L, 4), dtype=torch.float32, device=ref_in.device)
+    sine = torch.empty((B, nq, 512), dtype=torch.float16, device=ref_in.device) if want_sine else None
+    check(load().mqdet_box_refine_sine(_ptr(delta), ldd, _ptr(ref_in), int(bool(ref_is_logit)), _ptr(vr), B, nq, L, _ptr(ref),
+                                       _ptr(ref_input), _ptr(sine), _stream()), "box_refine_sine")
+    launch_count += 1
+    return ref, ref_input, sine
+
+
+def gdino_detections(logits, boxes, tokmap, img_wh, box_threshold, max_out=None):
+    """Raw class logits fp32 [B, nq, T] + boxes fp32 [B, nq, 4] (cxcywh, normalised) -> packed [B, max_out + 1, 6]
+    (x1, y1, x2, y2, score, label; last row = count).  tokmap int32 [C, max_tok]; img_wh fp32 [B, 2] = (W, H)."""
+    global launch_count
+    _need_cuda(logits, boxes, tokmap, img_wh)
+    B, nq, T = logits.shape
+    C, max_tok = tokmap.shape
+    max_out = nq if max_out is None else int(max_out)
+    out = torch.empty((B, max_out + 1, 6), dtype=torch.float32, device=logits.device)
+    check(load().mqdet_gdino_detections(_ptr(logits.float().contiguous()), T, _ptr(boxes.float().contiguous()), _ptr(tokmap), C,
+                                        max_tok, _ptr(img_wh.float().contiguous()), float(box_threshold), B, nq, max_out,
+                                        _ptr(out), _stream()), "gdino_detections")
+    launch_count += 1
+    return out

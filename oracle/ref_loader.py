@@ -468,3 +468,32 @@ def fpn():
         _install_shims()
         _cache["fpn"] = _load_file("ref_fpn", "maskrcnn_benchmark/modeling/backbone/fpn.py")
     return _cache["fpn"]
+
+
+def gdino_package():
+    """groundingdino_new/models/GroundingDINO as a pseudo-package ``ref_gdino_pkg`` so that the relative imports of
+    ``transformer.py`` (.fuse_modules, .ms_deform_attn, .transformer_vanilla, .utils) resolve to the reference's own files;
+    ``groundingdino_new.util.misc`` is the reference's own file loaded by path (only ``inverse_sigmoid`` is used)."""
+    if "gdpkg" not in _cache:
+        import warnings
+        _install_shims()
+        if "groundingdino_new" not in sys.modules:
+            top = types.ModuleType("groundingdino_new")
+            top.__path__ = []
+            util = types.ModuleType("groundingdino_new.util")
+            util.__path__ = []
+            sys.modules.update({"groundingdino_new": top, "groundingdino_new.util": util})
+            top.util = util
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                util.misc = _load_file("groundingdino_new.util.misc", "groundingdino_new/util/misc.py")
+        pkg = types.ModuleType("ref_gdino_pkg")
+        pkg.__path__ = [os.path.join(REF, "groundingdino_new", "models", "GroundingDINO")]
+        sys.modules["ref_gdino_pkg"] = pkg
+        import importlib
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            for sub in ("utils", "fuse_modules", "ms_deform_attn", "transformer_vanilla", "transformer"):
+                setattr(pkg, sub, importlib.import_module("ref_gdino_pkg." + sub))
+        _cache["gdpkg"] = pkg
+    return _cache["gdpkg"]

@@ -158,12 +158,13 @@ def extended_mask(attention_mask):
     return (1.0 - attention_mask[:, None, None, :].float()) * -10000.0
 
 
-def bert_embeddings(input_ids, sd, p="embeddings.", eps=1e-12):
-    """QVBertEmbeddings.forward at eval (modeling_bert_new.py:457-519): word + token_type(0) + absolute position, LN."""
+def bert_embeddings(input_ids, sd, p="embeddings.", eps=1e-12, position_ids=None):
+    """QVBertEmbeddings.forward at eval (modeling_bert_new.py:457-519): word + token_type(0) + absolute position, LN.
+    ``position_ids`` [B,T] (GroundingDINO restarts them per category, bertwarper.py:271-320) or None = arange(T)."""
     T = input_ids.shape[1]
     e = sd[p + "word_embeddings.weight"][input_ids]
     e = e + sd[p + "token_type_embeddings.weight"][0][None, None, :]
-    e = e + sd[p + "position_embeddings.weight"][:T][None]
+    e = e + (sd[p + "position_embeddings.weight"][:T][None] if position_ids is None else sd[p + "position_embeddings.weight"][position_ids])
     return _ln(e, sd, p + "LayerNorm", eps)
 
 
@@ -754,3 +755,312 @@ def detector(img, image_size, input_ids, attention_mask, positive_map, bank, sd,
         dets.append((boxes[keep], scores[keep], labs[keep]))
     return {"pyramid": pyr, "hidden": lang["hidden"], "vision": lang["vision"], "logits": head["dot_product_logits"],
             "fused_hidden": head["hidden"], "detections": dets}
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# GroundingDINO transformer and forward — groundingdino_new/models/GroundingDINO/{transformer,transformer_vanilla,utils,
+# groundingdino,bertwarper}.py, backbone/{backbone,position_encoding}.py   (MQ-GroundingDINO-T, BASELINE config 4)
+# ------------------------------------------------------------------------------------------------------------------
+def sine_pos_embed(pos_tensor, num_pos_feats=128, temperature=10000, exchange_xy=True):
+    """get_sine_pos_embed (utils.py:24-56): pos_tensor [B, n, k] -> [B, n, k * num_pos_feats]."""
+    dim_t = torch.arange(num_pos_feats, dtype=torch.float32)
+    dim_t = temperature ** (2 * torch.div(dim_t, 2, rounding_mode="floor") / num_pos_feats)
+    res = []
+    for x in pos_tensor.split([1] * pos_tensor.shape[-1], dim=-1):
+        s = x * (2 * math.pi) / dim_t
+        res.append(torch.stack((s[..., 0::2].sin(), s[..., 1::2].cos()), dim=3).flatten(2))
+    if exchange_xy:
+        res[0], res[1] = res[1], res[0]
+    return torch.cat(res, dim=-1)
+
+
+def sineembed_for_position(pos):
+    """gen_sineembed_for_position (utils.py:203-232) for pos [..., 4] (x, y, w, h) -> [..., 512] ordered (y, x, w, h)."""
+    dim_t = torch.arange(128, dtype=torch.float32)
+    dim_t = 10000 ** (2 * torch.div(dim_t, 2, rounding_mode="floor") / 128)
+    out = []
+    for c in (1, 0, 2, 3):
+        e = pos[..., c, None] * (2 * math.pi) / dim_t
+        out.append(torch.stack((e[..., 0::2].sin(), e[..., 1::2].cos()), dim=-1).flatten(-2))
+    return torch.cat(out, dim=-1)
+
+
+def position_embedding_sine_hw(mask, num_pos_feats=128, temperature_h=20, temperature_w=20):
+    """PositionEmbeddingSineHW.forward with normalize=True (backbone/position_encoding.py:78-128, build at :171-178):
+    mask [B,H,W] bool (True = padding) -> [B, 2*num_pos_feats, H, W]."""
+    not_mask = ~mask
+    y_embed = not_mask.cumsum(1, dtype=torch.float32)
+    x_embed = not_mask.cumsum(2, dtype=torch.float32)
+    eps, scale = 1e-6, 2 * math.pi
+    y_embed = y_embed / (y_embed[:, -1:, :] + eps) * scale
+    x_embed = x_embed / (x_embed[:, :, -1:] + eps) * scale
+    d = torch.arange(num_pos_feats, dtype=torch.float32)
+    dim_tx = temperature_w ** (2 * torch.div(d, 2, rounding_mode="floor") / num_pos_feats)
+    dim_ty = temperature_h ** (2 * torch.div(d, 2, rounding_mode="floor") / num_pos_feats)
+    pos_x = x_embed[:, :, :, None] / dim_tx
+    pos_y = y_embed[:, :, :, None] / dim_ty
+    pos_x = torch.stack((pos_x[..., 0::2].sin(), pos_x[..., 1::2].cos()), dim=4).flatten(3)
+    pos_y = torch.stack((pos_y[..., 0::2].sin(), pos_y[..., 1::2].cos()), dim=4).flatten(3)
+    return torch.cat((pos_y, pos_x), dim=3).permute(0, 3, 1, 2)
+
+
+def mha(q_in, k_in, v_in, sd, p, heads, attn_mask=None, key_padding_mask=None):
+    """torch.nn.MultiheadAttention.forward at eval (third-party: torch; call sites transformer.py:843,851,
+    transformer_vanilla.py:112), batch-first restatement: q_in [B,Lq,E], k_in / v_in [B,Lk,E]; attn_mask bool [B,Lq,Lk]
+    (True = not allowed, shared by the heads), key_padding_mask bool [B,Lk] (True = ignored) -> [B,Lq,E]."""
+    B, Lq, E = q_in.shape
+    Lk = k_in.shape[1]
+    d = E // heads
+    w, b = sd[p + "in_proj_weight"], sd[p + "in_proj_bias"]
+    q = F.linear(q_in, w[:E], b[:E]).view(B, Lq, heads, d).transpose(1, 2) * (d ** -0.5)
+    k = F.linear(k_in, w[E:2 * E], b[E:2 * E]).view(B, Lk, heads, d).transpose(1, 2)
+    v = F.linear(v_in, w[2 * E:], b[2 * E:]).view(B, Lk, heads, d).transpose(1, 2)
+    s = q @ k.transpose(-1, -2)
+    if attn_mask is not None:
+        s = s.masked_fill(attn_mask[:, None], float("-inf"))
+    if key_padding_mask is not None:
+        s = s.masked_fill(key_padding_mask[:, None, None, :], float("-inf"))
+    o = (s.softmax(-1) @ v).transpose(1, 2).reshape(B, Lq, E)
+    return _lin(o, sd, p + "out_proj")
+
+
+def gdino_text_enhancer_layer(src, pos, attn_mask, sd, p, heads=4):
+    """TransformerEncoderLayer.forward (transformer_vanilla.py:96-123), post-norm, relu; the key padding mask is NOT used
+    (:114 is commented out in the reference).  src / pos [B,T,256], attn_mask bool [B,T,T] (True = not allowed)."""
+    q = src + pos
+    src = _ln(src + mha(q, q, src, sd, p + "self_attn.", heads, attn_mask=attn_mask), sd, p + "norm1")
+    ff = _lin(F.relu(_lin(src, sd, p + "linear1")), sd, p + "linear2")
+    return _ln(src + ff, sd, p + "norm2")
+
+
+def gdino_deformable_encoder_layer(src, pos, reference_points, spatial_shapes, key_padding_mask, sd, p, heads=8, points=4):
+    """DeformableTransformerEncoderLayer.forward (transformer.py:729-760)."""
+    src2 = ms_deform_attn(src + pos, src, reference_points, spatial_shapes, sd, p + "self_attn.", heads, points,
+                          key_padding_mask=key_padding_mask)
+    src = _ln(src + src2, sd, p + "norm1")
+    ff = _lin(F.relu(_lin(src, sd, p + "linear1")), sd, p + "linear2")
+    return _ln(src + ff, sd, p + "norm2")
+
+
+def gdino_encoder_reference_points(spatial_shapes, valid_ratios):
+    """TransformerEncoder.get_reference_points (transformer.py:473-489): [B, sum(hw), L, 2]."""
+    refs = []
+    for lvl, (H_, W_) in enumerate(spatial_shapes):
+        ref_y, ref_x = torch.meshgrid(torch.linspace(0.5, H_ - 0.5, H_), torch.linspace(0.5, W_ - 0.5, W_), indexing="ij")
+        ref_y = ref_y.reshape(-1)[None] / (valid_ratios[:, None, lvl, 1] * H_)
+        ref_x = ref_x.reshape(-1)[None] / (valid_ratios[:, None, lvl, 0] * W_)
+        refs.append(torch.stack((ref_x, ref_y), -1))
+    return torch.cat(refs, 1)[:, :, None] * valid_ratios[:, None]
+
+
+def gdino_valid_ratio(mask):
+    """Transformer.get_valid_ratio (transformer.py:194-201): mask [B,H,W] bool -> [B, 2] (w, h)."""
+    _, H, W = mask.shape
+    return torch.stack([(~mask[:, 0, :]).sum(1).float() / W, (~mask[:, :, 0]).sum(1).float() / H], -1)
+
+
+def gdino_encoder_output_proposals(memory, memory_padding_mask, spatial_shapes):
+    """gen_encoder_output_proposals (utils.py:59-118), learnedwh=None."""
+    N_ = memory.shape[0]
+    proposals, cur = [], 0
+    for lvl, (H_, W_) in enumerate(spatial_shapes):
+        m = memory_padding_mask[:, cur:cur + H_ * W_].view(N_, H_, W_, 1)
+        valid_H = torch.sum(~m[:, :, 0, 0], 1)
+        valid_W = torch.sum(~m[:, 0, :, 0], 1)
+        gy, gx = torch.meshgrid(torch.linspace(0, H_ - 1, H_), torch.linspace(0, W_ - 1, W_), indexing="ij")
+        grid = torch.cat([gx.unsqueeze(-1), gy.unsqueeze(-1)], -1)
+        scale = torch.cat([valid_W.unsqueeze(-1), valid_H.unsqueeze(-1)], 1).view(N_, 1, 1, 2)
+        grid = (grid.unsqueeze(0).expand(N_, -1, -1, -1) + 0.5) / scale
+        wh = torch.ones_like(grid) * 0.05 * (2.0 ** lvl)
+        proposals.append(torch.cat((grid, wh), -1).view(N_, -1, 4))
+        cur += H_ * W_
+    prop = torch.cat(proposals, 1)
+    valid = ((prop > 0.01) & (prop < 0.99)).all(-1, keepdim=True)
+    prop = torch.log(prop / (1 - prop))
+    prop = prop.masked_fill(memory_padding_mask.unsqueeze(-1), float("inf")).masked_fill(~valid, float("inf"))
+    mem = memory.masked_fill(memory_padding_mask.unsqueeze(-1), 0.0).masked_fill(~valid, 0.0)
+    return mem, prop
+
+
+def _mlp(x, sd, p, n):
+    """MLP (utils.py:171-185): Linear + relu ... Linear."""
+    for i in range(n):
+        x = _lin(x, sd, f"{p}layers.{i}")
+        if i < n - 1:
+            x = F.relu(x)
+    return x
+
+
+def inverse_sigmoid(x, eps=1e-3):
+    """groundingdino_new/util/misc.py:721-725."""
+    x = x.clamp(min=0, max=1)
+    return torch.log(x.clamp(min=eps) / (1 - x).clamp(min=eps))
+
+
+def gdino_decoder_layer(tgt, query_pos, ref_input, memory, memory_mask, spatial_shapes, memory_text, text_pad_mask, sd, p,
+                        heads=8, points=4):
+    """DeformableTransformerDecoderLayer.forward (transformer.py:823-878), batch-first: self-attention over the queries,
+    text cross-attention, deformable cross-attention into the image memory, FFN — each followed by residual + LayerNorm."""
+    q = tgt + query_pos
+    tgt = _ln(tgt + mha(q, q, tgt, sd, p + "self_attn.", heads), sd, p + "norm2")
+    tgt = _ln(tgt + mha(tgt + query_pos, memory_text, memory_text, sd, p + "ca_text.", heads,
+                        key_padding_mask=text_pad_mask), sd, p + "catext_norm")
+    tgt2 = ms_deform_attn(tgt + query_pos, memory, ref_input, spatial_shapes, sd, p + "cross_attn.", heads, points,
+                          key_padding_mask=memory_mask)
+    tgt = _ln(tgt + tgt2, sd, p + "norm1")
+    ff = _lin(F.relu(_lin(tgt, sd, p + "linear1")), sd, p + "linear2")
+    return _ln(tgt + ff, sd, p + "norm3")
+
+
+def gdino_transformer(srcs, masks, poss, encoded_text, text_token_mask, position_ids, text_self_attention_masks, sd,
+                      num_queries=900, enc_layers=6, dec_layers=6, heads=8, points=4, return_all=False):
+    """Transformer.forward (transformer.py:206-403) with two_stage_type="standard", embed_init_tgt=True, text enhancer,
+    fusion layers and text cross-attention (the shipped MQ-GroundingDINO-T settings, config/defaults.py:944-987), eval.
+    srcs / poss: lists of [B,256,h,w]; masks: list of bool [B,h,w] (True = padding); encoded_text [B,T,256];
+    text_token_mask bool [B,T] (True = token in use); position_ids int64 [B,T]; text_self_attention_masks bool [B,T,T]
+    (True = may attend).  ``sd`` holds the Transformer's state_dict plus ``enc_out_bbox_embed.*`` and
+    ``decoder.bbox_embed.{i}.*`` as the reference registers them (groundingdino.py:255-275).
+    Returns hs (list of [B,nq,256], normed) and references (list of dec_layers+1 sigmoid boxes [B,nq,4])."""
+    spatial_shapes = [tuple(s.shape[-2:]) for s in srcs]
+    B = srcs[0].shape[0]
+    src = torch.cat([s.flatten(2).transpose(1, 2) for s in srcs], 1)
+    mask = torch.cat([m.flatten(1) for m in masks], 1)
+    pos = torch.cat([p_.flatten(2).transpose(1, 2) + sd["level_embed"][l].view(1, 1, -1) for l, p_ in enumerate(poss)], 1)
+    valid_ratios = torch.stack([gdino_valid_ratio(m) for m in masks], 1)
+    # ---- encoder (transformer.py:491-590)
+    ref_enc = gdino_encoder_reference_points(spatial_shapes, valid_ratios)
+    pos_text = sine_pos_embed(position_ids[..., None].float(), num_pos_feats=256, exchange_xy=False)
+    text_pad = ~text_token_mask
+    out, text = src, encoded_text
+    for i in range(enc_layers):
+        out, text = gdino_bi_attention(out, text, sd, f"encoder.fusion_layers.{i}.", heads=heads // 2, embed=1024,
+                                       mask_v=mask, mask_l=text_pad)
+        text = gdino_text_enhancer_layer(text, pos_text, ~text_self_attention_masks, sd, f"encoder.text_layers.{i}.",
+                                         heads=heads // 2)
+        out = gdino_deformable_encoder_layer(out, pos, ref_enc, spatial_shapes, mask, sd, f"encoder.layers.{i}.", heads, points)
+    memory, memory_text = out, text
+    # ---- two-stage query selection (:272-318)
+    output_memory, output_proposals = gdino_encoder_output_proposals(memory, mask, spatial_shapes)
+    output_memory = _ln(_lin(output_memory, sd, "enc_output"), sd, "enc_output_norm")
+    enc_class = contrastive_embed(output_memory, memory_text, text_token_mask)
+    enc_coord = _mlp(output_memory, sd, "enc_out_bbox_embed.", 3) + output_proposals
+    sel = gdino_two_stage_select(enc_class, enc_coord, output_proposals, output_memory, num_queries)
+    refpoint = sel["refpoint_embed"]
+    tgt = sd["tgt_embed.weight"][None].expand(B, -1, -1)
+    # ---- decoder (:636-716)
+    reference_points = refpoint.sigmoid()
+    refs, hs = [reference_points], []
+    vr4 = torch.cat([valid_ratios, valid_ratios], -1)
+    output = tgt
+    for i in range(dec_layers):
+        ref_input = reference_points[:, :, None] * vr4[:, None]
+        sine = sineembed_for_position(ref_input[:, :, 0, :])
+        query_pos = _mlp(sine, sd, "decoder.ref_point_head.", 2)
+        output = gdino_decoder_layer(output, query_pos, ref_input, memory, mask, spatial_shapes, memory_text, text_pad, sd,
+                                     f"decoder.layers.{i}.", heads, points)
+        delta = _mlp(output, sd, f"decoder.bbox_embed.{i}.", 3)
+        reference_points = (delta + inverse_sigmoid(reference_points)).sigmoid()
+        refs.append(reference_points)
+        hs.append(_ln(output, sd, "decoder.norm"))
+    res = {"hs": hs, "references": refs, "memory": memory, "memory_text": memory_text}
+    if return_all:
+        res.update(enc_class=enc_class, topk=sel["idx"], output_memory=output_memory, output_proposals=output_proposals)
+    return res
+
+
+def gdino_text_masks(input_ids, special_tokens=(101, 102, 1012, 1029)):
+    """generate_masks_with_special_tokens_and_transfer_map (bertwarper.py:271-320): per-category block-diagonal self-attention
+    mask bool [B,T,T] (True = may attend) and position ids that restart after every delimiter ([CLS], [SEP], '.', '?')."""
+    bs, T = input_ids.shape
+    special = torch.zeros((bs, T), dtype=torch.bool)
+    for s in special_tokens:
+        special |= input_ids == s
+    mask = torch.eye(T, dtype=torch.bool)[None].repeat(bs, 1, 1)
+    pid = torch.zeros((bs, T), dtype=torch.long)
+    prev = 0
+    for row, col in torch.nonzero(special).tolist():
+        if col == 0 or col == T - 1:
+            mask[row, col, col] = True
+            pid[row, col] = 0
+        else:
+            mask[row, prev + 1:col + 1, prev + 1:col + 1] = True
+            pid[row, prev + 1:col + 1] = torch.arange(0, col - prev)
+        prev = col
+    return mask, pid
+
+
+def gdino_detections(pred_logits, pred_boxes, positive_map, num_classes, image_sizes, box_threshold=0.05):
+    """convert_groundingdino_to_glip_output (groundingdino.py:291-335) on RAW class logits: sigmoid, MEAN score aggregation
+    (rpn/inference.py:772-790), best class above the box threshold, cxcywh -> xyxy pixels, clip_to_image (TO_REMOVE = 1),
+    remove_small_boxes(min_size=0).  Returns per image (boxes [k,4], scores [k], labels [k])."""
+    prob = pred_logits.sigmoid()
+    B, N, _ = prob.shape
+    scores = torch.zeros(B, N, num_classes)
+    for label, toks in positive_map.items():
+        scores[:, :, label - 1] = prob[:, :, torch.as_tensor(list(toks), dtype=torch.long)].mean(-1)
+    out = []
+    for b, (H, W) in enumerate(image_sizes):
+        cand = scores[b].max(-1)[0] > box_threshold
+        s, idx = scores[b][cand].max(-1)
+        box = pred_boxes[b][cand] * torch.tensor([W, H, W, H], dtype=torch.float32)
+        box = torch.cat([box[:, :2] - box[:, 2:] / 2, box[:, 2:] + (box[:, :2] - box[:, 2:] / 2)], -1)
+        box = torch.stack([box[:, 0].clamp(0, W - 1), box[:, 1].clamp(0, H - 1), box[:, 2].clamp(0, W - 1),
+                           box[:, 3].clamp(0, H - 1)], -1)
+        keep = ((box[:, 2] - box[:, 0] + 1) >= 0) & ((box[:, 3] - box[:, 1] + 1) >= 0)
+        out.append((box[keep], s[keep], idx[keep] + 1))
+    return out
+
+
+def gdino_forward(img, image_sizes, input_ids, attention_mask, positive_map, bank, sd, K=5, num_classes=80, num_queries=900,
+                  enc_layers=6, dec_layers=6, box_threshold=0.05):
+    """GroundingDINO.forward at eval (groundingdino.py:447-662) for a batch sharing one prompt: Swin-T (3 outputs) -> input_proj
+    (+ one stride-2 level) -> QuerySelector / flatten_fpn_features -> BertModelWarper(QVBertModel) with the per-category text
+    masks -> feat_map -> Transformer -> last-layer class logits / boxes -> detections.  img [B,3,H,W] normalised and padded;
+    image_sizes list of (h, w); bank {label: [n,1,256]} with n == K."""
+    B, _, Hp, Wp = img.shape
+    T = input_ids.shape[1]
+    feats = swin_transformer(img, _sub(sd, "backbone.0."))[1:]
+    m = torch.zeros(B, Hp, Wp)
+    for b, (h, w) in enumerate(image_sizes):
+        m[b, h:, :] = 1
+        m[b, :, w:] = 1
+    srcs, masks = [], []
+    for l, f in enumerate(feats):
+        y = F.conv2d(f, sd[f"input_proj.{l}.0.weight"], sd[f"input_proj.{l}.0.bias"])
+        srcs.append(F.group_norm(y, 32, sd[f"input_proj.{l}.1.weight"], sd[f"input_proj.{l}.1.bias"]))
+        masks.append(F.interpolate(m[None], size=f.shape[-2:]).to(torch.bool)[0])
+    y = F.conv2d(feats[-1], sd["input_proj.3.0.weight"], sd["input_proj.3.0.bias"], stride=2, padding=1)
+    srcs.append(F.group_norm(y, 32, sd["input_proj.3.1.weight"], sd["input_proj.3.1.bias"]))
+    masks.append(F.interpolate(m[None], size=y.shape[-2:]).to(torch.bool)[0])
+    poss = [position_embedding_sine_hw(mk) for mk in masks]
+    labels = [k for k, v in positive_map.items() if len(v) != 0]
+    vision = torch.cat([bank[l][:K].flatten(0, 1) for l in labels])[None].expand(B, -1, -1)
+    vmask = torch.zeros(1, vision.shape[1], T)
+    r = 0
+    for l in labels:
+        n = bank[l][:K].flatten(0, 1).shape[0]
+        vmask[0, r:r + n, positive_map[l]] = 1.0
+        r += n
+    vmask = vmask.expand(B, -1, -1)
+    pooled = torch.cat([F.avg_pool2d(f, 2).flatten(2) for f in srcs], dim=2).permute(0, 2, 1)
+    ids = input_ids.expand(B, -1) if input_ids.shape[0] == 1 else input_ids
+    am = attention_mask.expand(B, -1) if attention_mask.shape[0] == 1 else attention_mask
+    self_mask, pid = gdino_text_masks(ids)
+    bsd = _sub(sd, "bert.")
+    h = bert_embeddings(ids, bsd, position_ids=pid)
+    ext = (1.0 - self_mask[:, None].float()) * -10000.0
+    vq = preselect(vision, pooled, bsd, "pre_select.")
+    for i in range(12):
+        if i >= 6:
+            h = gcp_block(h, vq, vmask, bsd, f"encoder.qv_layer.{i - 6}.")
+        h = bert_layer(h, ext, bsd, f"encoder.layer.{i}.", 12)
+    enc_text = _lin(h, sd, "feat_map")
+    tsd = _sub(sd, "transformer.")
+    tr = gdino_transformer(srcs, masks, poss, enc_text, am.bool(), pid, self_mask, tsd, num_queries=num_queries,
+                           enc_layers=enc_layers, dec_layers=dec_layers)
+    hs, refs = tr["hs"], tr["references"]
+    boxes = (_mlp(hs[-1], sd, f"bbox_embed.{dec_layers - 1}.", 3) + inverse_sigmoid(refs[-2])).sigmoid()
+    logits = contrastive_embed(hs[-1], tr["memory_text"], am.bool())
+    dets = gdino_detections(logits, boxes, positive_map, num_classes, image_sizes, box_threshold)
+    return {"srcs": srcs, "bert_hidden": h, "encoded_text": enc_text, "memory": tr["memory"], "memory_text": tr["memory_text"],
+            "hs": hs, "references": refs, "pred_logits": logits, "pred_boxes": boxes, "detections": dets}

@@ -317,3 +317,96 @@ def images(gen, B, h, w, size_divisibility=32, mean=(103.530, 116.280, 123.675),
     out = torch.zeros(B, 3, H, W)
     out[:, :, :h, :w] = x
     return out
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# MQ-GroundingDINO-T (BASELINE config 4)
+# ------------------------------------------------------------------------------------------------------------------
+def mha_sd(gen, p, embed=256, sd=None):
+    """torch.nn.MultiheadAttention parameters (in_proj_weight / in_proj_bias / out_proj)."""
+    sd[p + "in_proj_weight"] = gen.randn(3 * embed, embed, scale=1.0 / math.sqrt(embed))
+    sd[p + "in_proj_bias"] = gen.randn(3 * embed, scale=0.05)
+    gen.xavier(embed, embed, sd, p + "out_proj")
+    return sd
+
+
+def mlp_sd(gen, p, dims, sd, last_scale=None):
+    for i, (a, b) in enumerate(zip(dims[:-1], dims[1:])):
+        gen.xavier(b, a, sd, f"{p}layers.{i}")
+    if last_scale is not None:
+        i = len(dims) - 2
+        sd[f"{p}layers.{i}.weight"] = gen.randn(dims[-1], dims[-2], scale=last_scale)
+        sd[f"{p}layers.{i}.bias"] = gen.randn(dims[-1], scale=last_scale)
+    return sd
+
+
+def gdino_transformer_sd(gen, enc_layers=6, dec_layers=6, E=256, ffn=2048, nq=900, levels=4, sd=None, p=""):
+    """Transformer parameters with the reference's key names (transformer.py), plus ``enc_out_bbox_embed`` and the SHARED
+    ``decoder.bbox_embed.{i}`` as GroundingDINO registers them (groundingdino.py:247-275).  Gammas, sampling offsets, attention
+    weights and the box heads are livelier than the reference's (near-)zero initialisation so parity is not vacuous."""
+    sd = {} if sd is None else sd
+    sd[p + "level_embed"] = gen.randn(levels, E, scale=0.5)
+    sd[p + "tgt_embed.weight"] = gen.randn(nq, E)
+    gen.xavier(E, E, sd, p + "enc_output")
+    gen.norm(E, sd, p + "enc_output_norm")
+    for i in range(enc_layers):
+        q = f"{p}encoder.layers.{i}."
+        msda_sd(gen, q + "self_attn.", E, 8, levels, 4, sd)
+        gen.norm(E, sd, q + "norm1")
+        gen.xavier(ffn, E, sd, q + "linear1")
+        gen.xavier(E, ffn, sd, q + "linear2")
+        gen.norm(E, sd, q + "norm2")
+        q = f"{p}encoder.text_layers.{i}."
+        mha_sd(gen, q + "self_attn.", E, sd)
+        gen.xavier(ffn // 2, E, sd, q + "linear1")
+        gen.xavier(E, ffn // 2, sd, q + "linear2")
+        gen.norm(E, sd, q + "norm1")
+        gen.norm(E, sd, q + "norm2")
+        q = f"{p}encoder.fusion_layers.{i}."
+        bi_attention_sd(gen, q, E, E, ffn // 2, enc_layers, sd)
+    for i in range(dec_layers):
+        q = f"{p}decoder.layers.{i}."
+        msda_sd(gen, q + "cross_attn.", E, 8, levels, 4, sd)
+        gen.norm(E, sd, q + "norm1")
+        mha_sd(gen, q + "ca_text.", E, sd)
+        gen.norm(E, sd, q + "catext_norm")
+        mha_sd(gen, q + "self_attn.", E, sd)
+        gen.norm(E, sd, q + "norm2")
+        gen.xavier(ffn, E, sd, q + "linear1")
+        gen.xavier(E, ffn, sd, q + "linear2")
+        gen.norm(E, sd, q + "norm3")
+    gen.norm(E, sd, p + "decoder.norm")
+    mlp_sd(gen, p + "decoder.ref_point_head.", (2 * E, E, E), sd)
+    mlp_sd(gen, p + "enc_out_bbox_embed.", (E, E, E, 4), sd, last_scale=0.02)
+    shared = mlp_sd(gen, "", (E, E, E, 4), {}, last_scale=0.02)
+    for i in range(dec_layers):
+        for k, v in shared.items():
+            sd[f"{p}decoder.bbox_embed.{i}.{k}"] = v
+    return sd
+
+
+def gdino_sd(gen, enc_layers=6, dec_layers=6, nq=900):
+    """Full MQ-GroundingDINO-T parameter set with the reference's key names (groundingdino.py): Swin-T backbone (3 outputs),
+    input projections + GroupNorm, BertModelWarper(QVBertModel) incl. the unused pooler, feat_map, transformer, box heads."""
+    sd = {"backbone.0." + k: v for k, v in swin_sd(gen).items()}
+    for l, c in enumerate((192, 384, 768)):
+        sd[f"input_proj.{l}.0.weight"] = gen.randn(256, c, 1, 1, scale=1.0 / math.sqrt(c))
+        sd[f"input_proj.{l}.0.bias"] = gen.randn(256, scale=0.05)
+        gen.norm(256, sd, f"input_proj.{l}.1")
+    sd["input_proj.3.0.weight"] = gen.randn(256, 768, 3, 3, scale=1.0 / math.sqrt(9 * 768))
+    sd["input_proj.3.0.bias"] = gen.randn(256, scale=0.05)
+    gen.norm(256, sd, "input_proj.3.1")
+    sd.update({"bert." + k: v for k, v in qvbert_sd(gen).items()})
+    gen.xavier(768, 768, sd, "bert.pooler.dense")
+    gen.xavier(256, 768, sd, "feat_map")
+    gdino_transformer_sd(gen, enc_layers, dec_layers, nq=nq, sd=sd, p="transformer.")
+    for i in range(dec_layers):
+        for j in range(3):
+            for t in ("weight", "bias"):
+                sd[f"bbox_embed.{i}.layers.{j}.{t}"] = sd[f"transformer.decoder.bbox_embed.{i}.layers.{j}.{t}"]
+    return sd
+
+
+def rgb_images(gen, B, h, w, size_divisibility=32):
+    """Synthetic RGB [0,1] images normalised like configs/pretrain/mq-groundingdino-t.yaml:45-46, zero-padded to a multiple of 32."""
+    return images(gen, B, h, w, size_divisibility, mean=(0.485 * 255, 0.456 * 255, 0.406 * 255), std=(0.229 * 255, 0.224 * 255, 0.225 * 255))
