@@ -229,7 +229,7 @@ class GroundingDINO(nn.Module):
         return src32, ops.cast_f16(src32), sizes
 
     @torch.no_grad()
-    def forward_device(self, samples, captions, positive_map, all_layers=False):
+    def forward_device(self, samples, captions, positive_map, all_layers=False, proposals=None):
         """-> dict(det_packed [B, nq+1, 6] on the device, pred_logits (raw) [B,nq,T], pred_boxes [B,nq,4], ...)."""
         if self.training:
             raise NotImplementedError("training is SURVEY.md §8(f2)")
@@ -248,7 +248,7 @@ class GroundingDINO(nn.Module):
         T = h.shape[1]
         enc_text = ops.gemm(ops.cast_f16(h).view(B * T, -1), w16(self.feat_map.weight), bias=f32(self.feat_map.bias),
                             out_dtype=torch.float32).view(B, T, self.hidden_dim)
-        tr = self.transformer.forward_flat(src32, geo, enc_text, all_layers=all_layers)
+        tr = self.transformer.forward_flat(src32, geo, enc_text, all_layers=all_layers, proposals=proposals)
         hs, refs = tr["hs"], tr["references"]
         nq = hs[-1].shape[1]
         # deformable-detr-like anchor update of the LAST layer on the normed hidden state (groundingdino.py:618-627)

@@ -337,8 +337,9 @@ class Transformer(nn.Module):
                 "output_proposals": proposals.contiguous()}
 
     @torch.no_grad()
-    def forward_flat(self, src32, geo, text32, all_layers=False):
-        """src32 fp32 [B,N,E] (levels concatenated), text32 fp32 [B,T,E] -> dict(hs, references, memory, memory_text, ...)."""
+    def forward_flat(self, src32, geo, text32, all_layers=False, proposals=None):
+        """src32 fp32 [B,N,E] (levels concatenated), text32 fp32 [B,T,E] -> dict(hs, references, memory, memory_text, ...).
+        ``proposals``: see ``select_queries`` (parity tests only)."""
         B, N, E = src32.shape
         mem16, mem32, text16, text32 = self.encoder.forward_flat(src32, geo, text32)
         # two-stage query selection (:272-318)
@@ -349,7 +350,8 @@ class Transformer(nn.Module):
         text_dict = {"encoded_text": text32, "encoded_text16": text16, "text_token_mask": geo["text_token_mask"]}
         enc_class = self.enc_out_class_embed(o16.view(B, N, E), text_dict)
         coord = self.enc_out_bbox_embed(o16, out_dtype=torch.float32, residual=geo["output_proposals"].view(B * N, 4))
-        sel = select_queries(enc_class, coord.view(B, N, -1)[..., :4], geo["output_proposals"], o32.view(B, N, E), self.num_queries)
+        sel = select_queries(enc_class, coord.view(B, N, -1)[..., :4], geo["output_proposals"], o32.view(B, N, E), self.num_queries,
+                             proposals=proposals)
         tgt = self.tgt_embed.weight.detach().float()[None].expand(B, -1, -1).contiguous()
         hs, refs = self.decoder.forward_flat(tgt, sel["refpoint_embed"], mem16, geo, text16, all_layers=all_layers)
         return {"hs": hs, "references": refs, "memory": mem32, "memory_text": text32, "memory_text16": text16,

@@ -18,7 +18,8 @@ from ..._lib import MqdetError
 
 
 @torch.no_grad()
-def select_queries(enc_outputs_class, enc_outputs_coord_unselected, output_proposals, output_memory, num_queries=900):
+def select_queries(enc_outputs_class, enc_outputs_coord_unselected, output_proposals, output_memory, num_queries=900,
+                   proposals=None):
     """enc_outputs_class [B,Q,T] fp32 (-inf on padded text tokens allowed), enc_outputs_coord_unselected / output_proposals
     [B,Q,4] fp32, output_memory [B,Q,C] fp32 -> dict(topk_proposals int64 [B,k], refpoint_embed [B,k,4], init_box_proposal
     [B,k,4], tgt [B,k,C], topk_logits [B,Q])."""
@@ -26,7 +27,9 @@ def select_queries(enc_outputs_class, enc_outputs_coord_unselected, output_propo
         if not t.is_cuda:
             raise MqdetError("select_queries: CUDA tensors required (no CPU fallback)")
     topk_logits = ops.row_max(enc_outputs_class.float().contiguous())
-    idx = ops.topk_desc(topk_logits, num_queries)
+    # ``proposals`` (int64 [B, k]): a given selection instead of the top-k -- parity tests feed the oracle's selection so that the
+    # decoder can be compared slot by slot although near-tied class logits may rank differently under fp16 operands
+    idx = ops.topk_desc(topk_logits, num_queries) if proposals is None else proposals.to(torch.int64).contiguous()
     ref = ops.gather_rows(enc_outputs_coord_unselected.float().contiguous(), idx)
     prop = ops.gather_rows(output_proposals.float().contiguous(), idx, sigmoid=True)
     tgt = ops.gather_rows(output_memory.float().contiguous(), idx)

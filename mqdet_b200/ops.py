@@ -20,17 +20,20 @@ launch_count = 0
 # bench.py sets this to a list to time every GEMM launch with CUDA events on the launching stream (roofline.achieved)
 GEMM_PROFILE = None
 # ... and this one to time every launch of the tensor-core kernels (GEMM, dcn_conv, biattn_image, biattn_text_vn):
-# entries (start event, end event, kernel name, algorithmic flops, algorithmic bytes)
+# entries (start event, end event, kernel name, algorithmic flops, algorithmic bytes, executed flops)
 KERNEL_PROFILE = None
 
 
 class _Timed:
     """Brackets one launch with CUDA events on the launching stream when KERNEL_PROFILE is a list."""
 
-    def __init__(self, name, flops, nbytes):
+    def __init__(self, name, flops, nbytes, executed=None):
         self.rec = KERNEL_PROFILE is not None
         if self.rec:
+            # ``flops`` = the ALGORITHMIC count (what the reference computes for this piece of work); ``executed`` = what the kernel
+            # issues to the tensor cores when algebraic folding makes that smaller (defaults to the algorithmic count)
             self.name, self.flops, self.nbytes = name, float(flops), float(nbytes)
+            self.executed = float(flops if executed is None else executed)
             self.e0, self.e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 
     def __enter__(self):
@@ -41,7 +44,7 @@ class _Timed:
     def __exit__(self, *exc):
         if self.rec:
             self.e1.record()
-            KERNEL_PROFILE.append((self.e0, self.e1, self.name, self.flops, self.nbytes))
+            KERNEL_PROFILE.append((self.e0, self.e1, self.name, self.flops, self.nbytes, self.executed))
         return False
 
 
@@ -363,7 +366,9 @@ def biattn_image(vn16, gT, gbias, mT, bias, gamma, residual, mask, clamp, heads)
     # scores, P.V_l, output projection (4 products of 2.N.T'.E with T' = 256 or T); bytes: tokens in, tokens out, residual
     E = heads * 256
     fl = B * (2.0 * N * 256 * E + 2.0 * 2.0 * N * T * E + 2.0 * N * E * 256)
-    with _Timed("biattn_image_kernel", fl, 2.0 * B * N * 256 * (3 if residual is not None else 2) + 2.0 * 2 * B * heads * T * 256):
+    # executed: S = vn gT^T and P mT^T per head, 2.N.T.256 each (the query / value / output projections are folded into gT / mT)
+    ex = B * heads * 2.0 * (2.0 * N * T * 256)
+    with _Timed("biattn_image_kernel", fl, 2.0 * B * N * 256 * (3 if residual is not None else 2) + 2.0 * 2 * B * heads * T * 256, ex):
         check(load().mqdet_biattn_image(_ptr(vn16), vn16.stride(1), vn16.stride(0), _ptr(gT), gT.stride(2), gT.stride(1),
                                         gT.stride(0), _ptr(gbias), gbias.shape[3] if gbias is not None else 0, _ptr(mT),
                                         mT.stride(2), mT.stride(1), mT.stride(0), _ptr(bias), _ptr(gamma), _ptr(residual),
@@ -389,7 +394,8 @@ def biattn_text_vn(kh, qh, vn16, colmax, clamp, out, rowbias=None):
     # algorithmic work of the text -> image direction (the scores are shared with the other direction in the reference): the
     # image-side value projection and P^T.V_v; bytes: the image tokens once per image, the small text-side operands
     fl = B * (2.0 * N * 256 * H * d + 2.0 * T * N * H * d)
-    with _Timed("biattn_text_kernel", fl, 2.0 * B * N * 256 + 2.0 * 2 * B * H * T * 256):
+    # executed: S^T recomputed (2.T.N.256 per head) + P^T.vn (2.T.N.256 per head)
+    with _Timed("biattn_text_kernel", fl, 2.0 * B * N * 256 + 2.0 * 2 * B * H * T * 256, B * H * 2.0 * (2.0 * T * N * 256)):
         check(load().mqdet_biattn_text_vn(_ptr(kh), kh.stride(2), kh.stride(1), kh.stride(0), _ptr(qh), qh.stride(2), qh.stride(1),
                                           qh.stride(0), _ptr(vn16), vn16.stride(1), 0, vn16.stride(0), _ptr(colmax), _ptr(rowbias),
                                           rowbias.shape[3] if rowbias is not None else 0, float(clamp), _ptr(out), out.stride(2),

@@ -227,9 +227,9 @@ class BiMultiHeadAttention(nn.Module):
         if stable:
             ops.shift_clamp_(AT32, gmax, -lim, lim)
         if mask_v is not None:  # padded image tokens leave the text side's softmax (fuse_modules.py:201-206)
-            mv = torch.zeros((B, Np), dtype=torch.float32, device=dev)
-            mv[:, :N] = mask_v.float()
-            Pl = ops.softmax_rows(AT32, n=N, colmask=mv, rows_per_batch=H * T, mask_value=float("-inf"), keep_add=0.0)
+            # mask rows are indexed with stride n (= N), not with the padded row length (mqdet_softmax_rows)
+            Pl = ops.softmax_rows(AT32, n=N, colmask=mask_v.float().contiguous(), rows_per_batch=H * T, mask_value=float("-inf"),
+                                  keep_add=0.0)
         else:
             Pl = ops.softmax_rows(AT32, n=N)
         del AT32

@@ -187,6 +187,32 @@ def case_inputs(name):
         mask[0, 150:] = False
         mask[1, 17:] = False
         return dict(x=gen.randn(B, Q, D), y=gen.randn(B, T, D), mask=mask)
+    if name == "gdino_transformer":
+        # GroundingDINO Transformer.forward (BASELINE config 4): 2 encoder + 2 decoder layers, 4 small levels (image 1 padded on
+        # the right / bottom), 20 queries, a prompt of 4-token categories with per-category masks and restarted position ids
+        gen = synth.Gen(1240)
+        nq, el, dl, B, Tt, used = 20, 2, 2, 2, 32, 25
+        sd = synth.gdino_transformer_sd(gen, el, dl, nq=nq)
+        shapes = ((12, 16), (6, 8), (3, 4), (2, 2))
+        srcs = [gen.randn(B, 256, h, w) for h, w in shapes]
+        masks = []
+        for h, w in shapes:
+            m = torch.zeros(B, h, w, dtype=torch.bool)
+            m[1, :, int(w * 0.75):] = True
+            m[1, int(h * 0.8):, :] = True
+            masks.append(m)
+        tmask = torch.ones(B, Tt, dtype=torch.bool)
+        tmask[:, used:] = False
+        pid = torch.zeros(B, Tt, dtype=torch.long)
+        sam = torch.eye(Tt, dtype=torch.bool)[None].repeat(B, 1, 1)
+        st = 1
+        while st < used:
+            e = min(st + 4, used)
+            sam[:, st:e, st:e] = True
+            pid[:, st:e] = torch.arange(e - st)
+            st = e
+        return dict(sd=sd, nq=nq, enc_layers=el, dec_layers=dl, srcs=srcs, masks=masks, enc_text=gen.randn(B, Tt, 256), tmask=tmask,
+                    pid=pid, sam=sam)
     raise KeyError(name)
 
 
@@ -280,6 +306,30 @@ def run_reference(name):
     if name == "contrastive_embed":
         mod = rl.gdino_utils().ContrastiveEmbed(max_text_len=256)
         return dict(logits=mod(c["x"], {"encoded_text": c["y"], "text_token_mask": c["mask"]}))
+    if name == "gdino_transformer":
+        import warnings
+        p = rl.gdino_package()
+        kw = dict(d_model=256, nhead=8, dim_feedforward=2048, dropout=0.0, activation="relu", return_intermediate_dec=True, query_dim=4,
+                  num_feature_levels=4, enc_n_points=4, dec_n_points=4, learnable_tgt_init=True, two_stage_type="standard",
+                  embed_init_tgt=True, use_text_enhancer=True, use_fusion_layer=True, use_checkpoint=False, use_transformer_ckpt=False,
+                  use_text_cross_attention=True, text_dropout=0.0, fusion_dropout=0.0, fusion_droppath=0.1)
+        T = p.transformer.Transformer(num_queries=c["nq"], num_encoder_layers=c["enc_layers"], num_decoder_layers=c["dec_layers"], **kw).eval()
+        be = p.utils.MLP(256, 256, 4, 3)  # shared by the decoder layers (groundingdino.py:247-252)
+        T.decoder.bbox_embed = torch.nn.ModuleList([be for _ in range(c["dec_layers"])])
+        T.decoder.class_embed = torch.nn.ModuleList([p.utils.ContrastiveEmbed() for _ in range(c["dec_layers"])])
+        T.enc_out_bbox_embed = p.utils.MLP(256, 256, 4, 3)
+        T.enc_out_class_embed = p.utils.ContrastiveEmbed()
+        T.load_state_dict({k: c["sd"][k] for k in T.state_dict()}, strict=True)
+        import importlib
+        pe = importlib.import_module("ref_gdino_pkg.backbone.position_encoding").PositionEmbeddingSineHW(128, 20, 20, normalize=True)
+        misc = importlib.import_module("groundingdino_new.util.misc")
+        poss = [pe(misc.NestedTensor(s, m)) for s, m in zip(c["srcs"], c["masks"])]
+        td = {"encoded_text": c["enc_text"].clone(), "text_token_mask": c["tmask"], "position_ids": c["pid"],
+              "text_self_attention_masks": c["sam"]}
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            hs, refs, _, _, _ = T(c["srcs"], c["masks"], None, poss, None, None, td)
+        return dict(hs_last=hs[-1], ref_last=refs[-1], text=td["encoded_text"])
     if name == "swin_fpn":
         sw = rl.swint()
         body = sw.SwinTransformer(embed_dim=96, depths=[2, 2, 6, 2], num_heads=[3, 6, 12, 24], window_size=7,
@@ -305,6 +355,7 @@ def run_reference(name):
 SUBSAMPLE = {"gcp_block": {"y": (4, 8), "s": (4, 8)}, "preselect": {"vision": (1, 8)},
              "bi_attention": {"v": (3, 4), "l": (4, 8)}, "bert_layer": {"h": (4, 8)},
              "contrastive_embed": {"logits": (9, 1)},
+             "gdino_transformer": {"hs_last": (1, 1), "ref_last": (1, 1), "text": (1, 1)},
              "dyconv": {"v": (3, 4)},
              "detector": {"det": (1, 1)},
              "detector_bench": {"det": (1, 1), "lang_hidden": (2, 8), "logits": (32, 2), "pyramid": (32, 4), "bbox": (16, 1),

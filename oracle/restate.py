@@ -1057,10 +1057,11 @@ def gdino_forward(img, image_sizes, input_ids, attention_mask, positive_map, ban
     enc_text = _lin(h, sd, "feat_map")
     tsd = _sub(sd, "transformer.")
     tr = gdino_transformer(srcs, masks, poss, enc_text, am.bool(), pid, self_mask, tsd, num_queries=num_queries,
-                           enc_layers=enc_layers, dec_layers=dec_layers)
+                           enc_layers=enc_layers, dec_layers=dec_layers, return_all=True)
     hs, refs = tr["hs"], tr["references"]
     boxes = (_mlp(hs[-1], sd, f"bbox_embed.{dec_layers - 1}.", 3) + inverse_sigmoid(refs[-2])).sigmoid()
     logits = contrastive_embed(hs[-1], tr["memory_text"], am.bool())
     dets = gdino_detections(logits, boxes, positive_map, num_classes, image_sizes, box_threshold)
     return {"srcs": srcs, "bert_hidden": h, "encoded_text": enc_text, "memory": tr["memory"], "memory_text": tr["memory_text"],
-            "hs": hs, "references": refs, "pred_logits": logits, "pred_boxes": boxes, "detections": dets}
+            "hs": hs, "references": refs, "pred_logits": logits, "pred_boxes": boxes, "detections": dets, "topk": tr["topk"],
+            "enc_class": tr["enc_class"]}

@@ -156,3 +156,14 @@ def test_detector_golden():
     assert have.shape == want.shape
     assert torch.equal(want[:, 5], have[:, 5])
     assert torch.allclose(want[:, 4], have[:, 4], rtol=2e-4, atol=2e-5) and torch.allclose(want[:, :4], have[:, :4], rtol=0, atol=5e-2)
+
+
+def test_gdino_transformer_restatement_vs_golden():
+    """oracle/restate.py::gdino_transformer against the fixture recorded from the reference's own Transformer.forward."""
+    c = make_golden.case_inputs("gdino_transformer")
+    poss = [restate.position_embedding_sine_hw(m) for m in c["masks"]]
+    out = restate.gdino_transformer(c["srcs"], c["masks"], poss, c["enc_text"], c["tmask"], c["pid"], c["sam"], c["sd"],
+                                    num_queries=c["nq"], enc_layers=c["enc_layers"], dec_layers=c["dec_layers"])
+    fx = torch.load(os.path.join(ROOT, "tests", "golden", "gdino_transformer.pt"))
+    for got, key in ((out["hs"][-1], "hs_last"), (out["references"][-1], "ref_last"), (out["memory_text"], "text")):
+        assert (got - fx[key]).abs().max().item() <= 2e-5 * fx[key + "_absmax"] + 1e-6
