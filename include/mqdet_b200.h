@@ -409,6 +409,52 @@ int mqdet_gdino_detections(const float* logits, int64_t T, const float* boxes, c
                            const float* img_wh, float box_threshold, int64_t B, int64_t nq, int64_t max_out, float* out,
                            void* stream);
 
+/* ---- Training side of the modulated pre-training step (BASELINE config 5): backward of the Gated Class-scalable
+ * Perceiver block (modeling_bert_new.py:186-248,298-374; the block's forward is the inference path above), token focal loss,
+ * global-norm clipping + AdamW.  The matrix products of the backward are mqdet_gemm_f16 launches (dX = dY W, dW = dY^T X with both
+ * operands transposed to K-major by mqdet_transpose_cast); SURVEY §8(b2)'s `gcp_block_bwd` is their composition in
+ * mqdet_b200/modeling/language_backbone/gcp_backward.py. --------------------------------------------------------------------
+ *   mqdet_transpose_cast   : out16[c][r] = f16(scale * x[r][c]), x [R][C] (f16 | f32, row stride ld), out row stride ldo >= R; columns
+ *                            R..ldo-1 are zero filled (K padding of the weight-gradient products)
+ *   mqdet_layernorm_bwd    : nn.LayerNorm backward from the saved INPUT x [rows][D] f32 and dy f32: dx (= or +=), dgamma, dbeta (optional);
+ *                            workspace: mqdet_layernorm_bwd_workspace_floats
+ *   mqdet_gelu_bwd         : dz16 = dh * gelu'(z16) (exact erf GELU), dh f16 | f32
+ *   mqdet_gcp_gate_bwd     : x1 = s * g + x with g = tanh(h1 . w2) (modeling_bert_new.py:355-361): ds = dx1 * g, dgpre = (sum_d dx1 * s)(1 - g^2),
+ *                            dh1 = dgpre * w2 (f16 [rows][Dg])
+ *   mqdet_colsum_weighted  : out[j] = sum_r w[r] * h16[r][j]   (d w2 of the gate projection); workspace: mqdet_colsum_weighted_workspace_floats
+ *   mqdet_gcp_sparse_attn_bwd: backward of mqdet_gcp_sparse_attn: dq16 [B][T][512]; dkv f32 [B][V+1][1024] ACCUMULATED with atomics (caller
+ *                            zero-initialises): K / V gradients land once per unique query row
+ *   mqdet_dot_sum          : out[0] = mul * sum_i a[i] * b[i] (b == NULL: a[i]^2), times (1 - tanh(*one_minus_tanh2_of)^2) when given;
+ *                            workspace: mqdet_reduce_workspace_floats
+ *   mqdet_scale_cast       : out = x * alpha * (tanh?)(*scalar_dev) -> f16 and / or f32
+ *   mqdet_token_focal_loss : token_sigmoid_binary_focal_loss (layers/sigmoid_focal_loss.py:127-162) over logits / targets f32 [B][N][T];
+ *                            text_mask f32 [B][T] (> 0 = token in use) or NULL; loss_out[0] = sum; dlogits (optional) = grad_scale * d loss
+ *   mqdet_sqnorm_partials  : partial sums of x^2 (<= 64 floats written, count returned through *partials_written, a HOST pointer)
+ *   mqdet_clip_coef        : coef2[0] = min(1, max_norm / (sqrt(sum partials) + 1e-6)), coef2[1] = the norm (clip_grad_norm_)
+ *   mqdet_adamw_step       : torch.optim.AdamW update of one tensor, gradient scaled by *grad_scale_dev (the clip coefficient) */
+int mqdet_transpose_cast(const void* x, int x_dtype, int64_t R, int64_t C, int64_t ld, float scale, void* out16, int64_t ldo, void* stream);
+int64_t mqdet_layernorm_bwd_workspace_floats(int64_t rows, int64_t D);
+int mqdet_layernorm_bwd(const float* dy, const float* x, const float* gamma, float eps, int64_t rows, int64_t D, float* dx, int accumulate,
+                        float* dgamma, float* dbeta, float* workspace, void* stream);
+int mqdet_gelu_bwd(const void* z16, const void* dh, int dh_dtype, int64_t n, void* dz16, void* stream);
+int mqdet_gcp_gate_bwd(const float* dx1, const float* s, const float* g, const float* w2, int64_t rows, int64_t D, int64_t Dg, float* ds,
+                       float* dgpre, void* dh1_16, void* stream);
+int64_t mqdet_colsum_weighted_workspace_floats(int64_t C);
+int mqdet_colsum_weighted(const void* h16, const float* w, int64_t rows, int64_t C, float* out, float* workspace, void* stream);
+int mqdet_gcp_sparse_attn_bwd(const void* q16, const void* kv16, const int32_t* idx, const void* dout16, int64_t B, int64_t T, int64_t V,
+                              int64_t S, int64_t H, int64_t Dh, void* dq16, float* dkv, void* stream);
+int64_t mqdet_reduce_workspace_floats(void);
+int mqdet_dot_sum(const float* a, const float* b, int64_t n, const float* one_minus_tanh2_of, float mul, float* out, float* workspace,
+                  void* stream);
+int mqdet_scale_cast(const float* x, const float* scalar_dev, int tanh_scalar, float alpha, int64_t n, void* out16, float* out32,
+                     void* stream);
+int mqdet_token_focal_loss(const float* logits, const float* targets, const float* text_mask, float alpha, float gamma, int64_t B, int64_t N,
+                           int64_t T, float grad_scale, float* loss_out, float* dlogits, float* workspace, void* stream);
+int mqdet_sqnorm_partials(const float* x, int64_t n, float* partial_out, int64_t max_partials, int64_t* partials_written, void* stream);
+int mqdet_clip_coef(const float* partials, int64_t count, float max_norm, float* coef2, void* stream);
+int mqdet_adamw_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr, float beta1, float beta2,
+                     float eps, float weight_decay, int64_t step, const float* grad_scale_dev, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -986,3 +986,174 @@ def gdino_detections(logits, boxes, tokmap, img_wh, box_threshold, max_out=None)
                                         _ptr(out), _stream()), "gdino_detections")
     launch_count += 1
     return out
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# Training side (csrc/train.cu): GCP backward pieces, token focal loss, clipping + AdamW
+# ----------------------------------------------------------------------------------------------------------------------
+def transpose_cast(x, scale=1.0):
+    """x [R, C] (fp16 / fp32, contiguous rows) -> fp16 [C, Rp] with Rp = R rounded up to 8, the padding columns zero: the K-major
+    operand of a weight-gradient product dW = dY^T X (K = the row dimension)."""
+    global launch_count
+    _need_cuda(x)
+    if x.dim() != 2 or x.stride(1) != 1:
+        raise _lib.MqdetError("transpose_cast: 2-D tensor with contiguous rows required")
+    R, C = x.shape
+    Rp = (R + 7) // 8 * 8
+    out = torch.empty((C, Rp), dtype=torch.float16, device=x.device)
+    check(load().mqdet_transpose_cast(_ptr(x), _dt(x), R, C, x.stride(0), float(scale), _ptr(out), Rp, _stream()), "transpose_cast")
+    launch_count += 1
+    return out
+
+
+def layernorm_bwd(dy32, x32, gamma, eps, dx=None, want_param_grads=True):
+    """nn.LayerNorm backward from the saved input: dy32 / x32 fp32 [..., D] -> (dx, dgamma, dbeta); ``dx`` given: accumulated into."""
+    global launch_count
+    _need_cuda(dy32, x32, gamma, dx)
+    D = x32.shape[-1]
+    rows = x32.numel() // D
+    if dy32.dtype != torch.float32 or x32.dtype != torch.float32 or not dy32.is_contiguous() or not x32.is_contiguous():
+        raise _lib.MqdetError("layernorm_bwd: contiguous fp32 tensors required")
+    acc = dx is not None
+    if dx is None:
+        dx = torch.empty_like(x32)
+    dg = torch.empty((D,), dtype=torch.float32, device=x32.device) if want_param_grads else None
+    db = torch.empty((D,), dtype=torch.float32, device=x32.device) if want_param_grads else None
+    ws = torch.empty((int(load().mqdet_layernorm_bwd_workspace_floats(rows, D)),), dtype=torch.float32, device=x32.device)
+    check(load().mqdet_layernorm_bwd(_ptr(dy32), _ptr(x32), _ptr(gamma), float(eps), rows, D, _ptr(dx), int(acc), _ptr(dg), _ptr(db),
+                                     _ptr(ws), _stream()), "layernorm_bwd")
+    launch_count += 3
+    return dx, dg, db
+
+
+def gelu_bwd(z16, dh):
+    """dz = dh * gelu'(z) (exact erf GELU): z16 fp16, dh fp16 / fp32 of the same shape -> fp16."""
+    global launch_count
+    _need_cuda(z16, dh)
+    if z16.dtype != torch.float16 or not z16.is_contiguous() or not dh.is_contiguous() or dh.shape != z16.shape:
+        raise _lib.MqdetError("gelu_bwd: contiguous tensors of one shape, z fp16")
+    out = torch.empty_like(z16)
+    check(load().mqdet_gelu_bwd(_ptr(z16), _ptr(dh), _dt(dh), z16.numel(), _ptr(out), _stream()), "gelu_bwd")
+    launch_count += 1
+    return out
+
+
+def gcp_gate_bwd(dx1, s32, g, w2):
+    """Backward of x1 = s * tanh(h1 . w2) + x: dx1 / s32 fp32 [M, D], g fp32 [M] (the gate values), w2 fp32 [Dg] ->
+    (ds fp32 [M, D], dgpre fp32 [M], dh1 fp16 [M, Dg])."""
+    global launch_count
+    _need_cuda(dx1, s32, g, w2)
+    M, D = dx1.shape
+    Dg = w2.numel()
+    ds = torch.empty_like(dx1)
+    dgpre = torch.empty((M,), dtype=torch.float32, device=dx1.device)
+    dh1 = torch.empty((M, Dg), dtype=torch.float16, device=dx1.device)
+    check(load().mqdet_gcp_gate_bwd(_ptr(dx1), _ptr(s32), _ptr(g), _ptr(w2), M, D, Dg, _ptr(ds), _ptr(dgpre), _ptr(dh1), _stream()),
+          "gcp_gate_bwd")
+    launch_count += 1
+    return ds, dgpre, dh1
+
+
+def colsum_weighted(h16, w32):
+    """out[j] = sum_r w32[r] * h16[r, j] -> fp32 [C]."""
+    global launch_count
+    _need_cuda(h16, w32)
+    R, C = h16.shape
+    out = torch.empty((C,), dtype=torch.float32, device=h16.device)
+    ws = torch.empty((int(load().mqdet_colsum_weighted_workspace_floats(C)),), dtype=torch.float32, device=h16.device)
+    check(load().mqdet_colsum_weighted(_ptr(h16.contiguous()), _ptr(w32), R, C, _ptr(out), _ptr(ws), _stream()), "colsum_weighted")
+    launch_count += 2
+    return out
+
+
+def gcp_sparse_attn_bwd(q, kv, idx, dout16, heads, dim_head):
+    """Backward of gcp_sparse_attn: q [B,T,512] fp16, kv [B,V+1,1024] fp16, idx int32 [B,T,S], dout16 [B,T,512] fp16 ->
+    (dq fp16 [B,T,512], dkv fp32 [B,V+1,1024])."""
+    global launch_count
+    _need_cuda(q, kv, idx, dout16)
+    B, T, inner = q.shape
+    V1 = kv.shape[1]
+    S = idx.shape[-1]
+    dq = torch.empty_like(q)
+    dkv = torch.zeros((B, V1, 2 * inner), dtype=torch.float32, device=q.device)
+    check(load().mqdet_gcp_sparse_attn_bwd(_ptr(q.contiguous()), _ptr(kv.contiguous()), _ptr(idx), _ptr(dout16.contiguous()), B, T, V1 - 1,
+                                           S, heads, dim_head, _ptr(dq), _ptr(dkv), _stream()), "gcp_sparse_attn_bwd")
+    launch_count += 1
+    return dq, dkv
+
+
+def dot_sum(a32, b32=None, one_minus_tanh2_of=None, mul=1.0):
+    """mul * sum(a * b) (b None: sum a^2), times 1 - tanh(s)^2 for a device scalar ``one_minus_tanh2_of`` -> device scalar [1]."""
+    global launch_count
+    _need_cuda(a32, b32, one_minus_tanh2_of)
+    out = torch.empty((1,), dtype=torch.float32, device=a32.device)
+    ws = torch.empty((int(load().mqdet_reduce_workspace_floats()),), dtype=torch.float32, device=a32.device)
+    check(load().mqdet_dot_sum(_ptr(a32.contiguous()), _ptr(None if b32 is None else b32.contiguous()), a32.numel(),
+                               _ptr(one_minus_tanh2_of), float(mul), _ptr(out), _ptr(ws), _stream()), "dot_sum")
+    launch_count += 2
+    return out
+
+
+def scale_cast(x32, scalar=None, tanh_scalar=False, alpha=1.0, out16=True, out32=False):
+    """x * alpha * (tanh)(scalar[0]) -> fp16 and / or fp32 (``scalar``: a device scalar, read on the device)."""
+    global launch_count
+    _need_cuda(x32, scalar)
+    x32 = x32.contiguous()
+    o16 = torch.empty(x32.shape, dtype=torch.float16, device=x32.device) if out16 else None
+    o32 = torch.empty(x32.shape, dtype=torch.float32, device=x32.device) if out32 else None
+    check(load().mqdet_scale_cast(_ptr(x32), _ptr(scalar), int(bool(tanh_scalar)), float(alpha), x32.numel(), _ptr(o16), _ptr(o32),
+                                  _stream()), "scale_cast")
+    launch_count += 1
+    if out16 and out32:
+        return o16, o32
+    return o16 if out16 else o32
+
+
+def token_focal_loss(logits, targets, text_mask=None, alpha=0.25, gamma=2.0, want_grad=True, grad_scale=1.0):
+    """token_sigmoid_binary_focal_loss(...).sum() over logits / targets fp32 [B, N, T] with the text mask [B, T] ->
+    (loss device scalar [1], dlogits fp32 [B, N, T] | None)."""
+    global launch_count
+    _need_cuda(logits, targets, text_mask)
+    B, N, T = logits.shape
+    loss = torch.empty((1,), dtype=torch.float32, device=logits.device)
+    dl = torch.empty_like(logits, dtype=torch.float32) if want_grad else None
+    ws = torch.empty((int(load().mqdet_reduce_workspace_floats()),), dtype=torch.float32, device=logits.device)
+    tm = None if text_mask is None else text_mask.float().contiguous()
+    check(load().mqdet_token_focal_loss(_ptr(logits.float().contiguous()), _ptr(targets.float().contiguous()), _ptr(tm), float(alpha),
+                                        float(gamma), B, N, T, float(grad_scale), _ptr(loss), _ptr(dl), _ptr(ws), _stream()),
+          "token_focal_loss")
+    launch_count += 2
+    return loss, dl
+
+
+def clip_coef(grads, max_norm):
+    """Global L2 norm over a list of fp32 gradient tensors and the clip_grad_norm_ coefficient, all on the device ->
+    fp32 [2] = (coefficient, norm)."""
+    global launch_count
+    _need_cuda(*grads)
+    dev = grads[0].device
+    partials = torch.zeros((64 * len(grads),), dtype=torch.float32, device=dev)
+    n_written = ctypes.c_int64(0)
+    off = 0
+    for g in grads:
+        g = g if g.is_contiguous() else g.contiguous()
+        check(load().mqdet_sqnorm_partials(_ptr(g), g.numel(), ctypes.c_void_p(partials.data_ptr() + 4 * off), 64,
+                                           ctypes.byref(n_written), _stream()), "sqnorm_partials")
+        off += int(n_written.value)
+    coef = torch.empty((2,), dtype=torch.float32, device=dev)
+    check(load().mqdet_clip_coef(_ptr(partials), off, float(max_norm), _ptr(coef), _stream()), "clip_coef")
+    launch_count += len(grads) + 1
+    return coef
+
+
+def adamw_step_(param, grad, exp_avg, exp_avg_sq, step, lr, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.01, grad_scale=None):
+    """torch.optim.AdamW update of one fp32 tensor in place; ``grad_scale`` = a device scalar (the clip coefficient) or None."""
+    global launch_count
+    _need_cuda(param, grad, exp_avg, exp_avg_sq, grad_scale)
+    for t in (param, grad, exp_avg, exp_avg_sq):
+        if t.dtype != torch.float32 or not t.is_contiguous():
+            raise _lib.MqdetError("adamw_step_: contiguous fp32 tensors required")
+    check(load().mqdet_adamw_step(_ptr(param), _ptr(grad), _ptr(exp_avg), _ptr(exp_avg_sq), param.numel(), float(lr), float(betas[0]),
+                                  float(betas[1]), float(eps), float(weight_decay), int(step), _ptr(grad_scale), _stream()), "adamw_step")
+    launch_count += 1
+    return param

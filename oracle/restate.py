@@ -1065,3 +1065,21 @@ def gdino_forward(img, image_sizes, input_ids, attention_mask, positive_map, ban
     return {"srcs": srcs, "bert_hidden": h, "encoded_text": enc_text, "memory": tr["memory"], "memory_text": tr["memory_text"],
             "hs": hs, "references": refs, "pred_logits": logits, "pred_boxes": boxes, "detections": dets, "topk": tr["topk"],
             "enc_class": tr["enc_class"]}
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# Training side — the backward oracle of the GCP block is torch.autograd over gcp_block() above
+# ------------------------------------------------------------------------------------------------------------------
+def token_focal_loss(pred_logits, targets, alpha=0.25, gamma=2.0, text_mask=None):
+    """TokenSigmoidFocalLoss.forward(version="binary") = token_sigmoid_binary_focal_loss(...).sum()
+    (maskrcnn_benchmark/layers/sigmoid_focal_loss.py:127-162,173-184): elements of masked text tokens are dropped."""
+    if text_mask is not None:
+        keep = (text_mask > 0).unsqueeze(1).expand_as(pred_logits)
+        pred_logits, targets = pred_logits[keep], targets[keep]
+    p = torch.sigmoid(pred_logits)
+    ce = F.binary_cross_entropy_with_logits(pred_logits, targets, reduction="none")
+    p_t = p * targets + (1 - p) * (1 - targets)
+    loss = ce * ((1 - p_t) ** gamma)
+    if alpha >= 0:
+        loss = (alpha * targets + (1 - alpha) * (1 - targets)) * loss
+    return loss.sum()
