@@ -416,7 +416,8 @@ int mqdet_gdino_detections(const float* logits, int64_t T, const float* boxes, c
  * mqdet_b200/modeling/language_backbone/gcp_backward.py. --------------------------------------------------------------------
  *   mqdet_transpose_cast   : out16[c][r] = f16(scale * x[r][c]), x [R][C] (f16 | f32, row stride ld), out row stride ldo >= R; columns
  *                            R..ldo-1 are zero filled (K padding of the weight-gradient products)
- *   mqdet_layernorm_bwd    : nn.LayerNorm backward from the saved INPUT x [rows][D] f32 and dy f32: dx (= or +=), dgamma, dbeta (optional);
+ *   mqdet_layernorm_bwd    : nn.LayerNorm backward from the saved INPUT x (+ x2 when given: the two addends of a post-norm residual block)
+ *                            [rows][D] f32 and dy f32: dx (= or +=), dgamma, dbeta (optional);
  *                            workspace: mqdet_layernorm_bwd_workspace_floats
  *   mqdet_gelu_bwd         : dz16 = dh * gelu'(z16) (exact erf GELU), dh f16 | f32
  *   mqdet_gcp_gate_bwd     : x1 = s * g + x with g = tanh(h1 . w2) (modeling_bert_new.py:355-361): ds = dx1 * g, dgpre = (sum_d dx1 * s)(1 - g^2),
@@ -434,8 +435,14 @@ int mqdet_gdino_detections(const float* logits, int64_t T, const float* boxes, c
  *   mqdet_adamw_step       : torch.optim.AdamW update of one tensor, gradient scaled by *grad_scale_dev (the clip coefficient) */
 int mqdet_transpose_cast(const void* x, int x_dtype, int64_t R, int64_t C, int64_t ld, float scale, void* out16, int64_t ldo, void* stream);
 int64_t mqdet_layernorm_bwd_workspace_floats(int64_t rows, int64_t D);
-int mqdet_layernorm_bwd(const float* dy, const float* x, const float* gamma, float eps, int64_t rows, int64_t D, float* dx, int accumulate,
-                        float* dgamma, float* dbeta, float* workspace, void* stream);
+int mqdet_layernorm_bwd(const float* dy, const float* x, const float* x2, const float* gamma, float eps, int64_t rows, int64_t D, float* dx,
+                        int accumulate, float* dgamma, float* dbeta, float* workspace, void* stream);
+/* batched form: input z = z1 + nb1 * z2 at x + z1 * x_s1 + z2 * x_s2 (element strides), outputs contiguous [nb2][nb1][C][ldo] */
+int mqdet_transpose_cast_batched(const void* x, int x_dtype, int64_t nb1, int64_t nb2, int64_t x_s1, int64_t x_s2, int64_t R, int64_t C,
+                                 int64_t ld, float scale, void* out16, int64_t ldo, void* stream);
+/* softmax backward over rows: ds16[r][j] = scale * p16[r][j] * (dp[r][j] - sum_k p16[r][k] dp[r][k]), j < n; columns n..n_pad-1 zero */
+int mqdet_softmax_bwd_rows(const void* p16, int64_t ldp, const float* dp, int64_t ldd, int64_t rows, int64_t n, int64_t n_pad, float scale,
+                           void* ds16, int64_t lds, void* stream);
 int mqdet_gelu_bwd(const void* z16, const void* dh, int dh_dtype, int64_t n, void* dz16, void* stream);
 int mqdet_gcp_gate_bwd(const float* dx1, const float* s, const float* g, const float* w2, int64_t rows, int64_t D, int64_t Dg, float* ds,
                        float* dgpre, void* dh1_16, void* stream);

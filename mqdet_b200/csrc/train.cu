@@ -30,9 +30,12 @@ __device__ __forceinline__ float ldf<__half>(const __half* p) { return __half2fl
 
 // ---------------------------------------------------------------------------------------------------------------------
 template <typename T>
-__global__ void __launch_bounds__(256) transpose_cast_kernel(const T* __restrict__ x, int R, int C, long ld, float scale,
-                                                             __half* __restrict__ out, long ldo) {
+__global__ void __launch_bounds__(256) transpose_cast_kernel(const T* __restrict__ x, int R, int C, long ld, long s1, long s2, int nb1,
+                                                             float scale, __half* __restrict__ out, long ldo) {
   __shared__ float tile[32][33];
+  const int z = blockIdx.z, z1 = z % nb1, z2 = z / nb1;
+  x += (long)z1 * s1 + (long)z2 * s2;
+  out += (long)z * C * ldo;
   const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
   for (int j = ty; j < 32; j += 8) {
@@ -50,7 +53,8 @@ __global__ void __launch_bounds__(256) transpose_cast_kernel(const T* __restrict
 // LayerNorm backward, warp per row (grid-stride).  Per-warp partial dgamma / dbeta rows go to the workspace
 // [2][nwarps][D]; ln_bwd_reduce sums them per column.
 __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x,
-                                                            const float* __restrict__ gamma, float eps, long rows, int D,
+                                                            const float* __restrict__ x2, const float* __restrict__ gamma, float eps,
+                                                            long rows, int D,
                                                             float* __restrict__ dx, int accumulate, float* __restrict__ ws) {
   extern __shared__ float lnb_sh[];  // [8 warps][2][D]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -60,19 +64,20 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restr
   for (int i = lane; i < D; i += 32) pg[i] = pb[i] = 0.f;
   for (long r = gw; r < rows; r += nw) {
     const float* xr = x + r * D;
+    const float* x2r = x2 ? x2 + r * D : nullptr;  // LN input = x + x2 (post-norm residual blocks store the two addends)
     const float* dr = dy + r * D;
     float s = 0.f;
-    for (int i = lane; i < D; i += 32) s += xr[i];
+    for (int i = lane; i < D; i += 32) s += xr[i] + (x2r ? x2r[i] : 0.f);
     const float mean = warp_sum(s) / D;
     float v = 0.f;
     for (int i = lane; i < D; i += 32) {
-      const float d = xr[i] - mean;
+      const float d = xr[i] + (x2r ? x2r[i] : 0.f) - mean;
       v = fmaf(d, d, v);
     }
     const float rstd = rsqrtf(warp_sum(v) / D + eps);
     float sg = 0.f, sgx = 0.f;
     for (int i = lane; i < D; i += 32) {
-      const float xh = (xr[i] - mean) * rstd, g = dr[i] * gamma[i];
+      const float xh = (xr[i] + (x2r ? x2r[i] : 0.f) - mean) * rstd, g = dr[i] * gamma[i];
       sg += g;
       sgx = fmaf(g, xh, sgx);
       pg[i] = fmaf(dr[i], xh, pg[i]);
@@ -81,7 +86,7 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restr
     sg = warp_sum(sg) / D;
     sgx = warp_sum(sgx) / D;
     for (int i = lane; i < D; i += 32) {
-      const float xh = (xr[i] - mean) * rstd, g = dr[i] * gamma[i];
+      const float xh = (xr[i] + (x2r ? x2r[i] : 0.f) - mean) * rstd, g = dr[i] * gamma[i];
       const float o = rstd * (g - sg - xh * sgx);
       dx[r * D + i] = accumulate ? dx[r * D + i] + o : o;
     }
@@ -113,6 +118,20 @@ __global__ void __launch_bounds__(256) gelu_bwd_kernel(const __half* __restrict_
     const float pdf = 0.3989422804014327f * expf(-0.5f * x * x);
     dz[i] = __float2half_rn(ldf<T>(dh + i) * (cdf + x * pdf));
   }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// softmax backward, warp per row: ds[j] = scale * p[j] * (dp[j] - sum_k p[k] dp[k]); columns n..n_pad-1 are written as zero
+__global__ void __launch_bounds__(256) softmax_bwd_rows_kernel(const __half* __restrict__ p, long ldp, const float* __restrict__ dp, long ldd,
+                                                               long rows, int n, int n_pad, float scale, __half* __restrict__ ds, long lds) {
+  const long r = (long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (r >= rows) return;
+  const int lane = threadIdx.x & 31;
+  float dot = 0.f;
+  for (int j = lane; j < n; j += 32) dot = fmaf(__half2float(p[r * ldp + j]), dp[r * ldd + j], dot);
+  dot = warp_sum(dot);
+  for (int j = lane; j < n_pad; j += 32)
+    ds[r * lds + j] = __float2half_rn(j < n ? scale * __half2float(p[r * ldp + j]) * (dp[r * ldd + j] - dot) : 0.f);
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -370,28 +389,44 @@ static inline unsigned ew_blocks(long n) {
 
 using namespace mqdet;
 
+extern "C" int mqdet_transpose_cast_batched(const void* x, int x_dtype, int64_t nb1, int64_t nb2, int64_t x_s1, int64_t x_s2, int64_t R,
+                                            int64_t C, int64_t ld, float scale, void* out16, int64_t ldo, void* stream) {
+  MQ_REQUIRE(x && out16 && R > 0 && C > 0 && ldo >= R && nb1 > 0 && nb2 > 0 && nb1 * nb2 <= 65535, "transpose_cast: bad arguments");
+  const dim3 grid((unsigned)((C + 31) / 32), (unsigned)((ldo + 31) / 32), (unsigned)(nb1 * nb2));
+  if (x_dtype == MQDET_F16)
+    transpose_cast_kernel<__half><<<grid, 256, 0, (cudaStream_t)stream>>>((const __half*)x, (int)R, (int)C, ld, x_s1, x_s2, (int)nb1, scale,
+                                                                          (__half*)out16, ldo);
+  else
+    transpose_cast_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>((const float*)x, (int)R, (int)C, ld, x_s1, x_s2, (int)nb1, scale,
+                                                                         (__half*)out16, ldo);
+  return check_launch("transpose_cast_kernel");
+}
+
 extern "C" int mqdet_transpose_cast(const void* x, int x_dtype, int64_t R, int64_t C, int64_t ld, float scale, void* out16,
                                     int64_t ldo, void* stream) {
-  MQ_REQUIRE(x && out16 && R > 0 && C > 0 && ld >= C && ldo >= R, "transpose_cast: bad arguments");
-  const dim3 grid((unsigned)((C + 31) / 32), (unsigned)((ldo + 31) / 32));
-  if (x_dtype == MQDET_F16)
-    transpose_cast_kernel<__half><<<grid, 256, 0, (cudaStream_t)stream>>>((const __half*)x, (int)R, (int)C, ld, scale, (__half*)out16, ldo);
-  else
-    transpose_cast_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>((const float*)x, (int)R, (int)C, ld, scale, (__half*)out16, ldo);
-  return check_launch("transpose_cast_kernel");
+  MQ_REQUIRE(ld >= C, "transpose_cast: ld < C");
+  return mqdet_transpose_cast_batched(x, x_dtype, 1, 1, 0, 0, R, C, ld, scale, out16, ldo, stream);
+}
+
+extern "C" int mqdet_softmax_bwd_rows(const void* p16, int64_t ldp, const float* dp, int64_t ldd, int64_t rows, int64_t n, int64_t n_pad,
+                                      float scale, void* ds16, int64_t lds, void* stream) {
+  MQ_REQUIRE(p16 && dp && ds16 && rows > 0 && n > 0 && n_pad >= n && ldp >= n && ldd >= n && lds >= n_pad, "softmax_bwd_rows: bad arguments");
+  softmax_bwd_rows_kernel<<<cdiv(rows, 8), 256, 0, (cudaStream_t)stream>>>((const __half*)p16, ldp, dp, ldd, rows, (int)n, (int)n_pad, scale,
+                                                                          (__half*)ds16, lds);
+  return check_launch("softmax_bwd_rows_kernel");
 }
 
 extern "C" int64_t mqdet_layernorm_bwd_workspace_floats(int64_t rows, int64_t D) { return 2 * (int64_t)RED_BLOCKS * 8 * D; }
 
-extern "C" int mqdet_layernorm_bwd(const float* dy, const float* x, const float* gamma, float eps, int64_t rows, int64_t D, float* dx,
-                                   int accumulate, float* dgamma, float* dbeta, float* workspace, void* stream) {
+extern "C" int mqdet_layernorm_bwd(const float* dy, const float* x, const float* x2, const float* gamma, float eps, int64_t rows, int64_t D,
+                                   float* dx, int accumulate, float* dgamma, float* dbeta, float* workspace, void* stream) {
   MQ_REQUIRE(dy && x && gamma && dx && workspace && rows > 0 && D > 0, "layernorm_bwd: bad arguments");
   MQ_REQUIRE(D <= 2048, "layernorm_bwd: D <= 2048");
   const size_t sh = (size_t)8 * 2 * D * sizeof(float);
   int rc = ensure_dyn_smem((const void*)layernorm_bwd_kernel, (int)sh);
   if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
-  layernorm_bwd_kernel<<<RED_BLOCKS, 256, sh, st>>>(dy, x, gamma, eps, rows, (int)D, dx, accumulate, workspace);
+  layernorm_bwd_kernel<<<RED_BLOCKS, 256, sh, st>>>(dy, x, x2, gamma, eps, rows, (int)D, dx, accumulate, workspace);
   const int nw = RED_BLOCKS * 8;
   if (dgamma) colsum_partials_kernel<<<cdiv(D, 256), 256, 0, st>>>(workspace, nw, (int)D, dgamma);
   if (dbeta) colsum_partials_kernel<<<cdiv(D, 256), 256, 0, st>>>(workspace + (long)nw * D, nw, (int)D, dbeta);

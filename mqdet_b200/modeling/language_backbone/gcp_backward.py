@@ -120,3 +120,69 @@ class GCPBlockTrain:
         dvision = dvis.view(B, V + 1, D)[:, :V].contiguous()   # the zero padding row is a constant
         self.ctx = None
         return dx.view(B, T, D), dvision, grads
+
+
+class QVBertEncoderTrain:
+    """Training forward / backward of the vision-conditioned half of ``QVBertEncoder`` (modeling_bert_new.py:566-610): for
+    i = start_qv .. last:  h <- GCP_{i-start}(h, vision, mask);  h <- BertLayer_i(h).  ``backward(dh)`` runs the chain in reverse and
+    returns dL/dh at the entry of the first GCP block, dL/d(vision) summed over the blocks (the gradient PreSelect receives) and the
+    gradients of every ``qv_layer.N.*`` parameter.  BERT layers are frozen (activation backward only); the layers before the first GCP
+    block see no trainable parameter and are not differentiated."""
+
+    def __init__(self, encoder):
+        from .bert_backward import BertLayerTrain
+        self.encoder = encoder
+        s = encoder.start_qv_layer_index
+        self.gcp = [GCPBlockTrain(b) for b in encoder.qv_layer]
+        self.bert = [BertLayerTrain(encoder.layer[i]) for i in range(s, len(encoder.layer))]
+
+    @torch.no_grad()
+    def forward(self, h32, colmask, vision, vision_attention_mask):
+        """h32 fp32 [B,T,D] = output of BERT layer start_qv-1; vision fp32 [B,V,D] (PreSelect output) -> final hidden state."""
+        for g, b in zip(self.gcp, self.bert):
+            h32 = g.forward(h32, vision, vision_attention_mask)
+            h32, _ = b.forward(h32, ops.cast_f16(h32.contiguous()), colmask)
+        return h32
+
+    @torch.no_grad()
+    def backward(self, dh):
+        grads, dvision = {}, None
+        for i in range(len(self.gcp) - 1, -1, -1):
+            dh = self.bert[i].backward(dh)
+            dh, dv, g = self.gcp[i].backward(dh)
+            dvision = dv if dvision is None else dvision.add_(dv)   # plain accumulation of six [B,V,D] tensors (torch add)
+            grads.update({f"qv_layer.{i}.{k}": v for k, v in g.items()})
+        return dh, dvision, grads
+
+
+class QVBertModelTrain:
+    """Training forward / backward of ``QVBertModel`` (modeling_bert_new.py:690-848) restricted to what the modulated pre-training
+    updates: every ``encoder.qv_layer.N.*`` and ``pre_select.*`` parameter (45.66 M parameters; BERT, embeddings frozen).
+
+        hidden = forward(input_ids, attention_mask, vision, images, vision_attention_mask)     fp32 [B,T,768]
+        grads  = backward(d_hidden)     {"encoder.qv_layer.N...": g, "pre_select.layers.N...": g}, names as in model.state_dict()
+
+    The embeddings and the BERT layers before the first GCP block run on the inference path (no trainable parameter upstream of them);
+    PreSelect, the GCP blocks and the BERT layers between them run their training forwards.  ``backward`` is the complete gradient of
+    the trainable half of the language backbone GIVEN dL/d(hidden) — producing that input gradient from the detection loss needs the
+    backward of the frozen fusion tower, which is not built."""
+
+    def __init__(self, model):
+        from .preselect_backward import PreSelectTrain
+        self.model = model
+        self.pre = PreSelectTrain(model.pre_select)
+        self.enc = QVBertEncoderTrain(model.encoder)
+
+    @torch.no_grad()
+    def forward(self, input_ids, attention_mask, vision, images, vision_attention_mask):
+        st = self.model.text_prefix(input_ids, attention_mask, output_hidden_states=False)
+        vq = self.pre.forward(vision, images)
+        return self.enc.forward(st["h32"], st["colmask"], vq, vision_attention_mask)
+
+    @torch.no_grad()
+    def backward(self, d_hidden):
+        _, dvq, g = self.enc.backward(d_hidden)
+        _, gp = self.pre.backward(dvq)
+        grads = {"encoder." + k: v for k, v in g.items()}
+        grads.update({"pre_select." + k: v for k, v in gp.items()})
+        return grads

@@ -1006,10 +1006,44 @@ def transpose_cast(x, scale=1.0):
     return out
 
 
-def layernorm_bwd(dy32, x32, gamma, eps, dx=None, want_param_grads=True):
-    """nn.LayerNorm backward from the saved input: dy32 / x32 fp32 [..., D] -> (dx, dgamma, dbeta); ``dx`` given: accumulated into."""
+def transpose_cast_batched(x):
+    """x [nb2, nb1, R, C] (fp16 / fp32, arbitrary batch / row strides, contiguous last dim) -> fp16 [nb2, nb1, C, Rp] contiguous,
+    Rp = R rounded up to 8 with zero padding."""
     global launch_count
-    _need_cuda(dy32, x32, gamma, dx)
+    _need_cuda(x)
+    if x.dim() != 4 or x.stride(3) != 1:
+        raise _lib.MqdetError("transpose_cast_batched: 4-D tensor with a contiguous last dimension required")
+    nb2, nb1, R, C = x.shape
+    Rp = (R + 7) // 8 * 8
+    out = torch.empty((nb2, nb1, C, Rp), dtype=torch.float16, device=x.device)
+    check(load().mqdet_transpose_cast_batched(_ptr(x), _dt(x), nb1, nb2, x.stride(1), x.stride(0), R, C, x.stride(2), 1.0, _ptr(out), Rp,
+                                              _stream()), "transpose_cast_batched")
+    launch_count += 1
+    return out
+
+
+def softmax_bwd_rows(p16, dp32, scale=1.0):
+    """ds = scale * p * (dp - sum(p * dp)) over the last dim: p16 fp16 / dp32 fp32 [..., n] contiguous -> fp16 [..., n]."""
+    global launch_count
+    _need_cuda(p16, dp32)
+    if p16.dtype != torch.float16 or dp32.dtype != torch.float32 or not p16.is_contiguous() or not dp32.is_contiguous() or \
+            p16.shape != dp32.shape:
+        raise _lib.MqdetError("softmax_bwd_rows: contiguous p fp16 / dp fp32 of one shape")
+    n = p16.shape[-1]
+    rows = p16.numel() // n
+    out = torch.empty_like(p16)
+    check(load().mqdet_softmax_bwd_rows(_ptr(p16), n, _ptr(dp32), n, rows, n, n, float(scale), _ptr(out), n, _stream()), "softmax_bwd_rows")
+    launch_count += 1
+    return out
+
+
+def layernorm_bwd(dy32, x32, gamma, eps, dx=None, want_param_grads=True, x2=None):
+    """nn.LayerNorm backward from the saved input (``x32 + x2`` when ``x2`` is given): dy32 / x32 fp32 [..., D] -> (dx, dgamma,
+    dbeta); ``dx`` given: accumulated into."""
+    global launch_count
+    _need_cuda(dy32, x32, gamma, dx, x2)
+    if x2 is not None and (x2.dtype != torch.float32 or not x2.is_contiguous() or x2.numel() != x32.numel()):
+        raise _lib.MqdetError("layernorm_bwd: x2 must be contiguous fp32 of x's size")
     D = x32.shape[-1]
     rows = x32.numel() // D
     if dy32.dtype != torch.float32 or x32.dtype != torch.float32 or not dy32.is_contiguous() or not x32.is_contiguous():
@@ -1020,7 +1054,7 @@ def layernorm_bwd(dy32, x32, gamma, eps, dx=None, want_param_grads=True):
     dg = torch.empty((D,), dtype=torch.float32, device=x32.device) if want_param_grads else None
     db = torch.empty((D,), dtype=torch.float32, device=x32.device) if want_param_grads else None
     ws = torch.empty((int(load().mqdet_layernorm_bwd_workspace_floats(rows, D)),), dtype=torch.float32, device=x32.device)
-    check(load().mqdet_layernorm_bwd(_ptr(dy32), _ptr(x32), _ptr(gamma), float(eps), rows, D, _ptr(dx), int(acc), _ptr(dg), _ptr(db),
+    check(load().mqdet_layernorm_bwd(_ptr(dy32), _ptr(x32), _ptr(x2), _ptr(gamma), float(eps), rows, D, _ptr(dx), int(acc), _ptr(dg), _ptr(db),
                                      _ptr(ws), _stream()), "layernorm_bwd")
     launch_count += 3
     return dx, dg, db

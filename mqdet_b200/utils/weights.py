@@ -43,3 +43,20 @@ def f32(param):
 
 def clear():
     _cache.clear()
+
+
+_cache_t = {}
+
+
+def wT16(param):
+    """fp16 TRANSPOSE of a 2-D parameter [out, in] -> [in, out rounded up to 8] (zero padded): the B operand of an activation
+    gradient dX = dY W (K = out).  Cached per parameter version like ``w16`` (frozen weights are transposed once)."""
+    key = id(param)
+    ent = _cache_t.get(key)
+    ver = (param.data_ptr(), param._version, param.device)
+    if ent is not None and ent[0] == ver and ent[2]() is param:
+        return ent[1]
+    src = param.detach()
+    h = ops.transpose_cast(src if src.dtype in (torch.float16, torch.float32) and src.is_contiguous() else src.float().contiguous())
+    _cache_t[key] = (ver, h, weakref.ref(param, lambda _r, k=key: _cache_t.pop(k, None)))
+    return h

@@ -158,3 +158,192 @@ def test_gcp_training_step_reduces_loss(dev):
         _, _, grads = tr.backward(dy * 1000.0)
         opt.step(grads)
     assert all(b < a for a, b in zip(losses, losses[1:])) and losses[-1] < losses[0] * 0.97, losses
+
+
+def test_batched_transpose_softmax_bwd_lnbwd_x2(dev):
+    from mqdet_b200 import ops
+    g = torch.Generator().manual_seed(11)
+    x = torch.randn(2, 3, 50, 36, generator=g).half()
+    xv = x.permute(0, 2, 1, 3)                                   # strided view [2, 50, 3, 36] -> batch dims (0, 2)
+    o = ops.transpose_cast_batched(xv.permute(0, 2, 1, 3).to(dev)).cpu()
+    assert o.shape == (2, 3, 36, 56) and torch.equal(o[..., :50], x.transpose(-1, -2)) and (o[..., 50:] == 0).all()
+    base = torch.randn(2, 50, 3 * 36, generator=g).half().to(dev)  # [B, T, H*d] read as [B, H, T, d] through strides
+    o2 = ops.transpose_cast_batched(base.view(2, 50, 3, 36).permute(0, 2, 1, 3)).cpu()
+    assert torch.equal(o2[..., :50], base.cpu().view(2, 50, 3, 36).permute(0, 2, 3, 1))
+    s = torch.randn(4, 6, 64, 64, generator=g)
+    pr = s.clone().requires_grad_(True)
+    p = pr.softmax(-1)
+    dp = torch.randn(4, 6, 64, 64, generator=g)
+    p.backward(dp)
+    ds = ops.softmax_bwd_rows(p.detach().half().to(dev), dp.to(dev), scale=0.5)
+    assert_close(ds, 0.5 * pr.grad, 2e-3, "softmax_bwd_rows")
+    a, b = torch.randn(300, 768, generator=g), torch.randn(300, 768, generator=g)
+    w = torch.randn(768, generator=g)
+    dy = torch.randn(300, 768, generator=g)
+    ar = (a + b).requires_grad_(True)
+    torch.nn.functional.layer_norm(ar, (768,), w, torch.zeros(768), 1e-12).backward(dy)
+    dx, _, _ = ops.layernorm_bwd(dy.to(dev), a.to(dev), w.to(dev), 1e-12, want_param_grads=False, x2=b.to(dev))
+    assert_close(dx, ar.grad, 1e-5, "layernorm_bwd with two addends")
+
+
+def test_bert_layer_backward_vs_autograd(dev):
+    from mqdet_b200 import ops
+    from mqdet_b200.modeling.language_backbone.bert_backward import BertLayerTrain
+    from mqdet_b200.modeling.language_backbone.modeling_bert_new import BertLayer
+    from oracle import restate, synth
+    gen = synth.Gen(8)
+    sd = synth.bert_layer_sd(gen, "")
+    B, T = 8, 256
+    h, dy = gen.randn(B, T, 768), gen.randn(B, T, 768)
+    am = torch.ones(B, T)
+    am[0, 200:] = 0
+    hr = h.clone().requires_grad_(True)
+    y = restate.bert_layer(hr, restate.extended_mask(am), sd, "", 12)
+    y.backward(dy)
+    tr = BertLayerTrain(load_sd(BertLayer(768, 12, 3072), sd).to(dev))
+    o32, _ = tr.forward(h.to(dev), ops.cast_f16(h.to(dev)), am.to(dev))
+    assert_close(o32, y.detach(), FP16_TOL, "bert train forward")
+    assert_close(tr.backward(dy.to(dev)), hr.grad, 3e-3, "bert layer backward: dh")
+
+
+def test_qvbert_encoder_backward_vs_autograd(dev):
+    """Two [GCP block, BERT layer] pairs chained: dL/dh at the entry, dL/d(vision) summed over the blocks and every qv_layer gradient
+    against autograd over the oracle — the complete backward of the trainable half of the language backbone, given dL/d(hidden)."""
+    from mqdet_b200.modeling.language_backbone.gcp_backward import QVBertEncoderTrain
+    from mqdet_b200.modeling.language_backbone.modeling_bert_new import QVBertEncoder
+    from oracle import restate, synth
+    from types import SimpleNamespace
+    gen = synth.Gen(12)
+    cfgb = SimpleNamespace(hidden_size=768, num_hidden_layers=3, num_attention_heads=12, intermediate_size=3072, layer_norm_eps=1e-12)
+    sd = {}
+    for i in range(3):
+        synth.bert_layer_sd(gen, f"layer.{i}.", sd=sd)
+    for i in range(2):
+        synth.gcp_block_sd(gen, f"qv_layer.{i}.", sd=sd)
+    B, T = 2, 256
+    _, _, pmap = synth.prompt(10, 2, T, gen)
+    _, m = synth.vision_queries(pmap, 5, T, 768, gen)
+    mask = m.expand(B, -1, -1).clone()
+    vision, h, dy = gen.randn(B, mask.shape[1], 768), gen.randn(B, T, 768), gen.randn(B, T, 768)
+    am = torch.ones(B, T)
+    am[1, 220:] = 0
+    p = {k: v.clone().requires_grad_(k.startswith("qv_layer")) for k, v in sd.items()}
+    hr, vr = h.clone().requires_grad_(True), vision.clone().requires_grad_(True)
+    x = hr
+    for i in (1, 2):
+        x = restate.gcp_block(x, vr, mask, p, f"qv_layer.{i - 1}.")
+        x = restate.bert_layer(x, restate.extended_mask(am), p, f"layer.{i}.", 12)
+    x.backward(dy)
+    enc = load_sd(QVBertEncoder(cfgb, dim=768, start_qv_layer_index=1, cfg=vq_cfg()), sd).to(dev)
+    tr = QVBertEncoderTrain(enc)
+    out = tr.forward(h.to(dev), am.to(dev), vision.to(dev), mask.to(dev))
+    assert_close(out, x.detach(), 2e-3, "encoder train forward")
+    dh, dvis, grads = tr.backward(dy.to(dev))
+    errs = []
+    assert_close(dh, hr.grad, 5e-3, "encoder backward: dh", defer=errs)
+    assert_close(dvis, vr.grad, 5e-3, "encoder backward: dvision", defer=errs)
+    for k, g in grads.items():
+        # ff_gate is ONE scalar = a sum of B*T*D signed products: fp16 rounding of the operands does not average out against max|ref|
+        assert_close(g.view(p[k].shape), p[k].grad, 3e-2 if k.endswith("ff_gate") else 5e-3, f"encoder backward: d {k}", defer=errs)
+    assert len(grads) == 32 and not errs, errs
+
+
+@pytest.mark.parametrize("B,V,I", [(2, 50, 237), (8, 400, 5577)])
+def test_preselect_backward_vs_autograd(dev, B, V, I):
+    """Gradient of all 23 PreSelect parameter tensors (and of the incoming vision queries) against autograd over the oracle;
+    (8, 400, 5577) is the per-GPU shape of BASELINE configs 2 / 5 (80 classes x 5 queries, the pooled 800x1333 pyramid)."""
+    from mqdet_b200.modeling.language_backbone.modeling_bert_new import PreSelectModule
+    from mqdet_b200.modeling.language_backbone.preselect_backward import PreSelectTrain
+    from oracle import restate, synth
+    gen = synth.Gen(21)
+    sd = synth.preselect_sd(gen)
+    vision, image, dy = gen.randn(B, V, 256), gen.randn(B, I, 256), gen.randn(B, V, 768)
+    p = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    vr = vision.clone().requires_grad_(True)
+    y = restate.preselect(vr, image, p, "")
+    y.backward(dy)
+    tr = PreSelectTrain(load_sd(PreSelectModule(dim=256, out_dim=768, cfg=vq_cfg()), sd).to(dev))
+    out = tr.forward(vision.to(dev), image.to(dev))
+    assert_close(out, y.detach(), FP16_TOL, "preselect train forward")
+    dvin, grads = tr.backward(dy.to(dev))
+    errs = []
+    assert_close(dvin, vr.grad, 3e-3, "preselect backward: d vision", defer=errs)
+    assert set(grads) == set(sd)
+    for k in sd:
+        assert_close(grads[k].view(p[k].shape), p[k].grad, 3e-3, f"preselect backward: d {k}", defer=errs)
+    assert not errs, errs
+
+
+def test_qvbert_model_backward_and_optimizer_step(dev):
+    """The whole trainable half of the language backbone: QVBertModel forward (12 BERT layers, PreSelect, 6 GCP blocks) -> a token focal
+    loss on a linear read-out of the hidden state -> backward to all 119 trainable tensors (encoder.qv_layer.*, pre_select.*) against
+    autograd over the oracle, then one FusedAdamW step with the reference's parameter-group rules against torch.optim.AdamW."""
+    from types import SimpleNamespace as NS
+    from mqdet_b200 import ops
+    from mqdet_b200.modeling.language_backbone.bert_model_new import bert_base_config
+    from mqdet_b200.modeling.language_backbone.gcp_backward import QVBertModelTrain
+    from mqdet_b200.modeling.language_backbone.modeling_bert_new import QVBertModel
+    from mqdet_b200.solver.build import FusedAdamW, param_group_options
+    from oracle import restate, synth
+    gen = synth.Gen(31)
+    sd = synth.qvbert_sd(gen)
+    B, T, I = 2, 256, 301
+    ids, am, pmap = synth.prompt(10, 2, T, gen)
+    ids, am = ids.expand(B, -1).contiguous(), am.expand(B, -1).contiguous()
+    vision, vmask = synth.vision_queries(pmap, 5, T, 256, gen)
+    vision, vmask = vision.expand(B, -1, -1).contiguous(), vmask.expand(B, -1, -1).contiguous()
+    images = gen.randn(B, I, 256)
+    readout = gen.randn(T, 768, scale=0.05)                       # logits[b, n, t] = hidden[b, n] . readout[t]
+    targets = (torch.rand(B, T, T, generator=gen.g) > 0.98).float()
+    train_keys = [k for k in sd if k.startswith(("encoder.qv_layer", "pre_select"))]
+    p = {k: (v.clone().requires_grad_(True) if k in train_keys else v) for k, v in sd.items()}
+    out = restate.qvbert_model(ids, am, vision, images, vmask, p)
+    logits = out["hidden"] @ readout.t()
+    loss = restate.token_focal_loss(logits, targets, 0.25, 2.0, am.float()) / 16.0
+    loss.backward()
+    model = load_sd(QVBertModel(bert_base_config(), dim_t=768, dim_v=256, cfg=vq_cfg()), sd).to(dev)
+    tr = QVBertModelTrain(model)
+    hid = tr.forward(ids.to(dev), am.to(dev), vision.to(dev), images.to(dev), vmask.to(dev))
+    assert_close(hid, out["hidden"].detach(), 5e-3, "qvbert train forward")
+    r16 = ops.cast_f16(readout.to(dev))
+    lg = ops.gemm(ops.cast_f16(hid.contiguous()).view(B * T, 768), r16, out_dtype=torch.float32).view(B, T, T)
+    l, dl = ops.token_focal_loss(lg, targets.to(dev), am.float().to(dev), 0.25, 2.0, grad_scale=1.0 / 16.0)
+    assert abs(l.item() / 16.0 - loss.item()) <= 2e-2 * abs(loss.item())
+    dh = ops.gemm(ops.cast_f16(dl).view(B * T, T), ops.transpose_cast(readout.to(dev)), out_dtype=torch.float32).view(B, T, 768)
+    grads = tr.backward(dh)
+    assert set(grads) == set(train_keys)
+    errs = []
+    for k in train_keys:
+        tol = 1e-1 if k.endswith("ff_gate") else 2e-2   # up to 6 GCP blocks + 6 BERT layers of fp16-operand products between loss and parameter
+        assert_close(grads[k].view(p[k].shape), p[k].grad, tol, f"qvbert backward: d {k}", defer=errs)
+    assert not errs, errs[:10]
+    # one optimizer step, reference parameter groups
+    cfg = NS(SOLVER=NS(BASE_LR=1e-4, WEIGHT_DECAY=1e-4, LANG_LR=1e-5, BACKBONE_BODY_LR_FACTOR=1.0, BIAS_LR_FACTOR=2.0, WEIGHT_DECAY_BIAS=0.0,
+                       WEIGHT_DECAY_NORM_FACTOR=1.0, GATE_LR=5e-3, QUERY_LR=1e-5, OPTIMIZER="ADAMW",
+                       CLIP_GRADIENTS=NS(ENABLED=True, CLIP_TYPE="full_model", CLIP_VALUE=1.0, NORM_TYPE=2.0)))
+    named = [("language_backbone.body.model." + k, q) for k, q in model.named_parameters() if k in train_keys]
+    for _, q in named:
+        q.requires_grad_(True)
+    opt = FusedAdamW(named, cfg=cfg)
+    ref_params = [torch.nn.Parameter(p[k].detach().clone()) for k in train_keys]
+    groups = []
+    for k, q in zip(train_keys, ref_params):
+        lr, wd = param_group_options(cfg, "language_backbone.body.model." + k)
+        groups.append({"params": [q], "lr": lr, "weight_decay": wd})
+        q.grad = p[k].grad.clone()
+    ref_opt = torch.optim.AdamW(groups)
+    norm = torch.nn.utils.clip_grad_norm_(ref_params, 1.0)
+    ref_opt.step()
+    coef = opt.step({"language_backbone.body.model." + k: grads[k] for k in train_keys}).cpu()
+    assert abs(coef[1].item() - norm.item()) <= 2e-2 * norm.item()
+    # AdamW's first update is lr * g / (|g| + eps), i.e. sign-like: elements whose gradient is below the fp16 noise may flip, so the
+    # updates are compared as vectors (cosine per tensor) and by their size (= the group's learning rate)
+    name_to_param = dict(model.named_parameters())
+    worst_cos, worst_size = 1.0, 0.0
+    for k, q in zip(train_keys, ref_params):
+        u_ref = (q.detach() - sd[k]).flatten()
+        u = (name_to_param[k].detach().cpu() - sd[k]).flatten()
+        if u.numel() >= 64:
+            worst_cos = min(worst_cos, torch.nn.functional.cosine_similarity(u, u_ref, dim=0).item())
+        worst_size = max(worst_size, abs(u.abs().max().item() / (u_ref.abs().max().item() + 1e-20) - 1.0))
+    assert worst_cos > 0.9 and worst_size < 0.05, (worst_cos, worst_size)
