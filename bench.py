@@ -272,7 +272,7 @@ def run_gdino(args):
     scaling) and ONE NCCL all-gather returns the fixed-shape detections [B, 901, 6] of every rank."""
     import torch
     import torch.distributed as dist
-    from mqdet_b200 import _lib, ops
+    from mqdet_b200 import _lib, ops, parallel
     from mqdet_b200.config import mq_groundingdino_t_cfg
     from mqdet_b200.modeling.groundingdino.groundingdino import GroundingDINO
     from mqdet_b200.structures.image_list import ImageList
@@ -337,9 +337,8 @@ def run_gdino(args):
             det = static_out
         else:
             det = model.forward_device(il if x is None else ImageList(x, [(H_IMG, W_IMG)] * B), caps, pmap)["det_packed"]
-        if world > 1:
-            dist.all_gather_into_tensor(gathered, det.contiguous())
-            return gathered
+        if world > 1:   # the ONE collective of the step (mqdet_b200.parallel; gloo world-2 test in tests/test_parallel_cpu.py)
+            return parallel.all_gather_packed(det.contiguous(), out=gathered.view(world * B, 901, 6)).view(world, B, 901, 6)
         return det
 
     def barrier():

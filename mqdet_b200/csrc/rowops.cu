@@ -377,6 +377,52 @@ __global__ void __launch_bounds__(256) softmax_rows256_f32_kernel(const float* _
   }
 }
 
+// Long fp32 rows (the text -> image side of the explicit BiAttention path: n = 22323 image tokens per (image, head, text token)): one
+// CTA per row instead of one warp, so a few thousand rows still fill the machine; three passes (max, sum, write) over a row that
+// stays in L2 (89 KB), float4 loads where the row is 16-byte aligned.
+__global__ void __launch_bounds__(256) softmax_longrows_f32_kernel(const float* __restrict__ x, long ldx, __half* __restrict__ y, long ldy,
+                                                                   int n, int n_pad, float scale, const float* __restrict__ colmask,
+                                                                   long rows_per_batch, float mask_value, float keep_add) {
+  __shared__ float red[8];
+  __shared__ float bcast;
+  const long row = blockIdx.x;
+  const float* xr = x + row * ldx;
+  __half* yr = y + row * ldy;
+  const float* cm = colmask ? colmask + (row / rows_per_batch) * n : nullptr;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  auto val = [&](int i) {
+    float v = xr[i] * scale;
+    if (cm) v += (cm[i] == 0.f) ? mask_value : keep_add;
+    return v;
+  };
+  float mx = -INFINITY;
+  for (int i = tid; i < n; i += 256) mx = fmaxf(mx, val(i));
+  mx = warp_max(mx);
+  if (lane == 0) red[warp] = mx;
+  __syncthreads();
+  if (tid < 32) {
+    float m = tid < 8 ? red[tid] : -INFINITY;
+    m = warp_max(m);
+    if (tid == 0) bcast = m;
+  }
+  __syncthreads();
+  mx = bcast;
+  __syncthreads();
+  float sum = 0.f;
+  for (int i = tid; i < n; i += 256) sum += expf(val(i) - mx);
+  sum = warp_sum(sum);
+  if (lane == 0) red[warp] = sum;
+  __syncthreads();
+  if (tid < 32) {
+    float t = tid < 8 ? red[tid] : 0.f;
+    t = warp_sum(t);
+    if (tid == 0) bcast = t;
+  }
+  __syncthreads();
+  const float inv = 1.f / bcast;
+  for (int i = tid; i < n_pad; i += 256) yr[i] = __float2half_rn(i < n ? expf(val(i) - mx) * inv : 0.f);
+}
+
 // Vectorised fp16 row softmax (rows 16-byte aligned, n % 8 == 0): one warp per row, 8 halfs per lane per step.
 //   ITERS > 0 : the whole row (n <= ITERS*256) lives in registers -> one read, one write      (A: n = 256 tokens)
 //   ITERS == 0: two passes, online max/sum then normalise                                     (At: n = 22400 locations)
@@ -976,6 +1022,11 @@ extern "C" int mqdet_softmax_rows(const void* x, int in_dtype, int64_t ldx, void
     softmax_rows256_f32_kernel<RW><<<(unsigned)cdiv(rows, (long)wpb * RW), wpb * 32, 0, st>>>(
         (const float*)x, ldx, (__half*)y, ldy, rows, scale, colmask, rows_per_batch, mask_value, keep_add);
     return check_launch("softmax_rows256_f32_kernel");
+  }
+  if (in_dtype == MQDET_F32 && n >= 4096 && rows <= 0x7fffffffL) {
+    softmax_longrows_f32_kernel<<<(unsigned)rows, 256, 0, st>>>((const float*)x, ldx, (__half*)y, ldy, (int)n, (int)n_pad, scale, colmask,
+                                                                rows_per_batch, mask_value, keep_add);
+    return check_launch("softmax_longrows_f32_kernel");
   }
   if (in_dtype == MQDET_F32)
     softmax_rows_kernel<float><<<grid, wpb * 32, 0, st>>>((const float*)x, ldx, (__half*)y, ldy, rows, (int)n, (int)n_pad,

@@ -290,3 +290,20 @@ def test_groundingdino_full_depth_runs_at_benchmark_shape(dev):
     one = model.forward_device(ImageList(img[1:].to(dev), [(h, w)]), caps, pmap, proposals=out["transformer"]["topk_proposals"][1:])
     e = assert_close(out["pred_boxes"][1:], one["pred_boxes"].cpu(), 2e-3, "gdino: image 1 of B=2 vs its B=1 run")
     _record("full_depth", {"batch_vs_single_box_err": e, "detections": [int(v) for v in out["num"].cpu()]})
+
+
+def test_softmax_long_fp32_rows_with_mask(dev):
+    """CTA-per-row softmax (n >= 4096 fp32: the text -> image side of the explicit BiAttention path, PreSelect's training forward)."""
+    from mqdet_b200 import ops
+    g = torch.Generator().manual_seed(9)
+    B, H, T, N = 2, 4, 16, 5003
+    Np = (N + 7) // 8 * 8
+    x = torch.zeros(B, H, T, Np)
+    x[..., :N] = torch.randn(B, H, T, N, generator=g) * 3
+    keep = (torch.rand(B, N, generator=g) > 0.2).float()
+    ref = (x[..., :N] + torch.where(keep == 0, float("-inf"), 0.0)[:, None, None, :]).softmax(-1)
+    out = ops.softmax_rows(x.to(dev), n=N, colmask=keep.to(dev).contiguous(), rows_per_batch=H * T, mask_value=float("-inf")).cpu()
+    assert (out[..., N:] == 0).all()
+    assert_close(out[..., :N], ref, FP16_TOL, "softmax_rows long fp32 rows, masked")
+    out2 = ops.softmax_rows(x.to(dev), n=N, scale=0.5).cpu()
+    assert_close(out2[..., :N], (0.5 * x[..., :N]).softmax(-1), FP16_TOL, "softmax_rows long fp32 rows, scaled")
