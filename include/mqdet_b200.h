@@ -368,6 +368,12 @@ int mqdet_ms_deform_attn(const void* value, const float* proj, int64_t proj_ld, 
  *   mqdet_shift_clamp_f32: x[i] = clamp(x[i] - *shift, lo, hi) in place, shift a DEVICE scalar (no host sync) */
 int64_t mqdet_global_max_workspace_floats(void);
 int mqdet_global_max_f32(const float* x, int64_t n, float* out, float* workspace, void* stream);
+/* the same shift + clamps fused into the row softmax (one pass less over the scores): y = softmax_j(clamp(x - *shift_dev, lo, hi) + mask),
+ * fp32 rows of n == n_pad == 256 (image -> text side) or n >= 4096 (text -> image side); mask arguments as mqdet_softmax_rows */
+int mqdet_softmax_rows_shifted_supported(int64_t n, int64_t n_pad);
+int mqdet_softmax_rows_shifted(const float* x, int64_t ldx, void* y, int64_t ldy, int64_t rows, int64_t n, int64_t n_pad,
+                               const float* shift_dev, float lo, float hi, const float* colmask, int64_t rows_per_batch, float mask_value,
+                               float keep_add, void* stream);
 int mqdet_shift_clamp_f32(float* x, int64_t n, const float* shift, float lo, float hi, void* stream);
 /* Two-stage query selection (transformer.py:288-318): topk_logits = enc_outputs_class.max(-1)[0]; torch.topk(.., 900, dim=1);
  * torch.gather of the selected rows.
@@ -397,7 +403,8 @@ int mqdet_gather_rows_f32(const float* src, const int64_t* idx, int64_t B, int64
  *                          (-inf on padding): sigmoid, per-class mean over its tokens (tokmap int32 [C][max_tok], -1 padded),
  *                          best class (lowest index on ties), keep if score > box_threshold, boxes cxcywh (normalised) -> xyxy in
  *                          pixels of img_wh[b] = (W, H), clipped to [0, W-1] x [0, H-1], boxes with a negative side dropped; kept rows in
- *                          query order -> out [B][max_out + 1][6] = (x1, y1, x2, y2, score, label), row max_out = (count, 0, ...). */
+ *                          query order -> out [B][max_out + 1][6] = (x1, y1, x2, y2, score, label), row max_out = (count, 0, ...);
+ *                          workspace: mqdet_gdino_detections_workspace_floats. */
 int mqdet_add_cast(const float* a, const float* b, const float* rowgate, int64_t rows, int64_t D, void* out16, float* out32,
                    void* stream);
 int64_t mqdet_groupnorm_rows_workspace_floats(int64_t B, int64_t C);
@@ -405,9 +412,10 @@ int mqdet_groupnorm_rows(const void* x, int x_dtype, int64_t B, int64_t HW, int6
                          const float* beta, float eps, void* out16, float* out32, float* workspace, void* stream);
 int mqdet_box_refine_sine(const float* delta, int64_t ldd, const float* ref_in, int ref_is_logit, const float* valid_ratios, int64_t B,
                           int64_t nq, int64_t L, float* ref_out, float* ref_input, void* sine16, void* stream);
+int64_t mqdet_gdino_detections_workspace_floats(int64_t B, int64_t nq);
 int mqdet_gdino_detections(const float* logits, int64_t T, const float* boxes, const int32_t* tokmap, int64_t C, int64_t max_tok,
                            const float* img_wh, float box_threshold, int64_t B, int64_t nq, int64_t max_out, float* out,
-                           void* stream);
+                           float* workspace, void* stream);
 
 /* ---- Training side of the modulated pre-training step (BASELINE config 5): backward of the Gated Class-scalable
  * Perceiver block (modeling_bert_new.py:186-248,298-374; the block's forward is the inference path above), token focal loss,

@@ -164,83 +164,81 @@ __global__ void __launch_bounds__(256) box_refine_sine_kernel(const float* __res
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
-// one CTA per image, 16 warps; warp per query (strided).  Shared memory: probabilities of the 16 queries in flight, the
-// per-query result rows and keep flags.
+// Pass 1: warp per (image, query), 16 queries per CTA -> scratch rows [B][nq][7] = (x1, y1, x2, y2, score, label, keep).
+// Pass 2: one warp per image compacts the kept rows in query order (boolean-mask indexing) into the packed result.
 constexpr int GD_WARPS = 16;
 constexpr int GD_MAX_T = 256;
 
-__global__ void __launch_bounds__(GD_WARPS * 32) gdino_detections_kernel(const float* __restrict__ logits, int T, const float* __restrict__ boxes,
-                                                                         const int* __restrict__ tokmap, int C, int max_tok,
-                                                                         const float* __restrict__ img_wh, float thr, int nq,
-                                                                         int max_out, float* __restrict__ out) {
-  extern __shared__ float gd_sh[];
-  float* prob = gd_sh;                             // [GD_WARPS][GD_MAX_T]
-  float* rows = gd_sh + GD_WARPS * GD_MAX_T;       // [nq][6]
-  int* keep = reinterpret_cast<int*>(rows + (long)nq * 6);  // [nq]
-  __shared__ int s_total;
-  const int b = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+__global__ void __launch_bounds__(GD_WARPS * 32) gdino_score_kernel(const float* __restrict__ logits, int T, const float* __restrict__ boxes,
+                                                                    const int* __restrict__ tokmap, int C, int max_tok,
+                                                                    const float* __restrict__ img_wh, float thr, int nq,
+                                                                    float* __restrict__ scratch) {
+  __shared__ float prob[GD_WARPS][GD_MAX_T];
+  const int b = blockIdx.y, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q = blockIdx.x * GD_WARPS + warp;
+  if (q >= nq) return;
   const float W = img_wh[b * 2], H = img_wh[b * 2 + 1];
-  float* pw = prob + warp * GD_MAX_T;
-  for (int q = warp; q < nq; q += GD_WARPS) {
-    const float* lg = logits + ((long)b * nq + q) * T;
-    for (int t = lane; t < T; t += 32) pw[t] = sigmoidf_(__ldg(lg + t));  // sigmoid(-inf) = 0
-    __syncwarp();
-    float best = -1.f;
-    int best_c = 0x7fffffff;
-    for (int c = lane; c < C; c += 32) {
-      const int* tm = tokmap + (long)c * max_tok;
-      float s = 0.f;
-      int n = 0;
-      for (int j = 0; j < max_tok; ++j) {
-        const int t = tm[j];
-        if (t < 0) break;
-        s += pw[t];
-        ++n;
-      }
-      const float sc = n ? s / (float)n : 0.f;
-      if (sc > best) { best = sc; best_c = c; }  // ascending c within a lane: the first maximum stays
+  float* pw = prob[warp];
+  const float* lg = logits + ((long)b * nq + q) * T;
+  for (int t = lane; t < T; t += 32) pw[t] = sigmoidf_(__ldg(lg + t));  // sigmoid(-inf) = 0
+  __syncwarp();
+  float best = -1.f;
+  int best_c = 0x7fffffff;
+  for (int c = lane; c < C; c += 32) {
+    const int* tm = tokmap + (long)c * max_tok;
+    float s = 0.f;
+    int n = 0;
+    for (int j = 0; j < max_tok; ++j) {
+      const int t = tm[j];
+      if (t < 0) break;
+      s += pw[t];
+      ++n;
     }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      const float ob = __shfl_xor_sync(0xffffffffu, best, o);
-      const int oc = __shfl_xor_sync(0xffffffffu, best_c, o);
-      if (ob > best || (ob == best && oc < best_c)) { best = ob; best_c = oc; }
-    }
-    if (lane == 0) {
-      const float* bx = boxes + ((long)b * nq + q) * 4;
-      const float cx = bx[0] * W, cy = bx[1] * H, bw = bx[2] * W, bh = bx[3] * H;
-      float x1 = cx - bw / 2.f, y1 = cy - bh / 2.f;
-      float x2 = bw + x1, y2 = bh + y1;
-      x1 = fminf(fmaxf(x1, 0.f), W - 1.f);
-      y1 = fminf(fmaxf(y1, 0.f), H - 1.f);
-      x2 = fminf(fmaxf(x2, 0.f), W - 1.f);
-      y2 = fminf(fmaxf(y2, 0.f), H - 1.f);
-      float* r = rows + q * 6;
-      r[0] = x1; r[1] = y1; r[2] = x2; r[3] = y2; r[4] = best; r[5] = (float)(best_c + 1);
-      // candidate_inds = max > box_threshold; remove_small_boxes(min_size=0): w = x2 - x1 + 1 >= 0 (boxlist_ops.py:78-92)
-      keep[q] = (best > thr) && (x2 - x1 + 1.f >= 0.f) && (y2 - y1 + 1.f >= 0.f);
-    }
-    __syncwarp();
+    const float sc = n ? s / (float)n : 0.f;
+    if (sc > best) { best = sc; best_c = c; }  // ascending c within a lane: the first maximum stays
   }
-  __syncthreads();
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oc = __shfl_xor_sync(0xffffffffu, best_c, o);
+    if (ob > best || (ob == best && oc < best_c)) { best = ob; best_c = oc; }
+  }
+  if (lane == 0) {
+    const float* bx = boxes + ((long)b * nq + q) * 4;
+    const float cx = bx[0] * W, cy = bx[1] * H, bw = bx[2] * W, bh = bx[3] * H;
+    float x1 = cx - bw / 2.f, y1 = cy - bh / 2.f;
+    float x2 = bw + x1, y2 = bh + y1;
+    x1 = fminf(fmaxf(x1, 0.f), W - 1.f);
+    y1 = fminf(fmaxf(y1, 0.f), H - 1.f);
+    x2 = fminf(fmaxf(x2, 0.f), W - 1.f);
+    y2 = fminf(fmaxf(y2, 0.f), H - 1.f);
+    float* r = scratch + ((long)b * nq + q) * 7;
+    r[0] = x1; r[1] = y1; r[2] = x2; r[3] = y2; r[4] = best; r[5] = (float)(best_c + 1);
+    // candidate_inds = max > box_threshold; remove_small_boxes(min_size=0): w = x2 - x1 + 1 >= 0 (boxlist_ops.py:78-92)
+    r[6] = ((best > thr) && (x2 - x1 + 1.f >= 0.f) && (y2 - y1 + 1.f >= 0.f)) ? 1.f : 0.f;
+  }
+}
+
+__global__ void __launch_bounds__(256) gdino_compact_kernel(const float* __restrict__ scratch, int nq, int max_out, float* __restrict__ out) {
+  const int b = blockIdx.x, lane = threadIdx.x & 31;
   float* o = out + (long)b * (max_out + 1) * 6;
   for (int i = threadIdx.x; i < (max_out + 1) * 6; i += blockDim.x) o[i] = 0.f;
   __syncthreads();
-  if (warp == 0) {  // ordered compaction (query order, like boolean-mask indexing)
-    int base = 0;
-    for (int q0 = 0; q0 < nq; q0 += 32) {
-      const int q = q0 + lane;
-      const bool k = q < nq && keep[q];
-      const unsigned bal = __ballot_sync(0xffffffffu, k);
-      const int pos = base + __popc(bal & ((1u << lane) - 1u));
-      if (k && pos < max_out) {
+  if (threadIdx.x >= 32) return;
+  const float* sc = scratch + (long)b * nq * 7;
+  int base = 0;
+  for (int q0 = 0; q0 < nq; q0 += 32) {
+    const int q = q0 + lane;
+    const bool k = q < nq && sc[q * 7 + 6] != 0.f;
+    const unsigned bal = __ballot_sync(0xffffffffu, k);
+    const int pos = base + __popc(bal & ((1u << lane) - 1u));
+    if (k && pos < max_out) {
 #pragma unroll
-        for (int c = 0; c < 6; ++c) o[pos * 6 + c] = rows[q * 6 + c];
-      }
-      base += __popc(bal);
+      for (int c = 0; c < 6; ++c) o[pos * 6 + c] = sc[q * 7 + c];
     }
-    if (lane == 0) o[max_out * 6] = (float)base;
+    base += __popc(bal);
   }
+  if (lane == 0) o[max_out * 6] = (float)base;
 }
 
 }  // namespace mqdet
@@ -294,16 +292,17 @@ extern "C" int mqdet_box_refine_sine(const float* delta, int64_t ldd, const floa
   return check_launch("box_refine_sine_kernel");
 }
 
+extern "C" int64_t mqdet_gdino_detections_workspace_floats(int64_t B, int64_t nq) { return B * nq * 7; }
+
 extern "C" int mqdet_gdino_detections(const float* logits, int64_t T, const float* boxes, const int32_t* tokmap, int64_t C,
                                       int64_t max_tok, const float* img_wh, float box_threshold, int64_t B, int64_t nq,
-                                      int64_t max_out, float* out, void* stream) {
-  MQ_REQUIRE(logits && boxes && tokmap && img_wh && out, "gdino_detections: null pointer");
-  MQ_REQUIRE(B > 0 && nq > 0 && nq <= 4096 && T > 0 && T <= GD_MAX_T && C > 0 && max_tok > 0 && max_out > 0,
-             "gdino_detections: bad shape (T <= 256, nq <= 4096)");
-  const size_t sh = (size_t)GD_WARPS * GD_MAX_T * 4 + (size_t)nq * 7 * 4;
-  int rc = ensure_dyn_smem((const void*)gdino_detections_kernel, (int)sh);
-  if (rc) return rc;
-  gdino_detections_kernel<<<(unsigned)B, GD_WARPS * 32, sh, (cudaStream_t)stream>>>(logits, (int)T, boxes, tokmap, (int)C, (int)max_tok,
-                                                                                 img_wh, box_threshold, (int)nq, (int)max_out, out);
-  return check_launch("gdino_detections_kernel");
+                                      int64_t max_out, float* out, float* workspace, void* stream) {
+  MQ_REQUIRE(logits && boxes && tokmap && img_wh && out && workspace, "gdino_detections: null pointer");
+  MQ_REQUIRE(B > 0 && B <= 65535 && nq > 0 && T > 0 && T <= GD_MAX_T && C > 0 && max_tok > 0 && max_out > 0,
+             "gdino_detections: bad shape (T <= 256)");
+  cudaStream_t st = (cudaStream_t)stream;
+  gdino_score_kernel<<<dim3((unsigned)((nq + GD_WARPS - 1) / GD_WARPS), (unsigned)B), GD_WARPS * 32, 0, st>>>(
+      logits, (int)T, boxes, tokmap, (int)C, (int)max_tok, img_wh, box_threshold, (int)nq, workspace);
+  gdino_compact_kernel<<<(unsigned)B, 256, 0, st>>>(workspace, (int)nq, (int)max_out, out);
+  return check_launch("gdino_detections");
 }

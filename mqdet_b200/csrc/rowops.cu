@@ -328,7 +328,9 @@ template <int RW>
 __global__ void __launch_bounds__(256) softmax_rows256_f32_kernel(const float* __restrict__ x, long ldx, __half* __restrict__ y,
                                                                   long ldy, long rows, float scale,
                                                                   const float* __restrict__ colmask, long rows_per_batch,
-                                                                  float mask_value, float keep_add) {
+                                                                  float mask_value, float keep_add,
+                                                                  const float* __restrict__ shift = nullptr, float lo = -INFINITY,
+                                                                  float hi = INFINITY) {
   const int lane = threadIdx.x & 31;
   const long r0 = ((long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * RW;
   if (r0 >= rows) return;
@@ -350,6 +352,11 @@ __global__ void __launch_bounds__(256) softmax_rows256_f32_kernel(const float* _
     if (row >= rows) break;
     float v[8] = {u[j][0].x * scale, u[j][0].y * scale, u[j][0].z * scale, u[j][0].w * scale,
                   u[j][1].x * scale, u[j][1].y * scale, u[j][1].z * scale, u[j][1].w * scale};
+    if (shift) {  // STABLE_SOFTMAX_2D: v = clamp(v - global max, lo, hi) fused here instead of a pass of its own over the scores
+      const float sh = __ldg(shift);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] = fminf(fmaxf(v[i] - sh, lo), hi);
+    }
     if (colmask) {
       const float* cm = colmask + (row / rows_per_batch) * 256 + lane * 8;
       const float4 m0 = *reinterpret_cast<const float4*>(cm);
@@ -382,7 +389,9 @@ __global__ void __launch_bounds__(256) softmax_rows256_f32_kernel(const float* _
 // stays in L2 (89 KB), float4 loads where the row is 16-byte aligned.
 __global__ void __launch_bounds__(256) softmax_longrows_f32_kernel(const float* __restrict__ x, long ldx, __half* __restrict__ y, long ldy,
                                                                    int n, int n_pad, float scale, const float* __restrict__ colmask,
-                                                                   long rows_per_batch, float mask_value, float keep_add) {
+                                                                   long rows_per_batch, float mask_value, float keep_add,
+                                                                   const float* __restrict__ shift = nullptr, float lo = -INFINITY,
+                                                                   float hi = INFINITY) {
   __shared__ float red[8];
   __shared__ float bcast;
   const long row = blockIdx.x;
@@ -390,8 +399,10 @@ __global__ void __launch_bounds__(256) softmax_longrows_f32_kernel(const float* 
   __half* yr = y + row * ldy;
   const float* cm = colmask ? colmask + (row / rows_per_batch) * n : nullptr;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const float sh = shift ? __ldg(shift) : 0.f;
   auto val = [&](int i) {
     float v = xr[i] * scale;
+    if (shift) v = fminf(fmaxf(v - sh, lo), hi);
     if (cm) v += (cm[i] == 0.f) ? mask_value : keep_add;
     return v;
   };
@@ -1036,6 +1047,29 @@ extern "C" int mqdet_softmax_rows(const void* x, int in_dtype, int64_t ldx, void
                                                           (int)n_pad, scale, colmask, rows_per_batch, mask_value,
                                                           keep_add);
   return check_launch("softmax_rows_kernel");
+}
+
+extern "C" int mqdet_softmax_rows_shifted_supported(int64_t n, int64_t n_pad) { return (n == 256 && n_pad == 256) || n >= 4096; }
+
+extern "C" int mqdet_softmax_rows_shifted(const float* x, int64_t ldx, void* y, int64_t ldy, int64_t rows, int64_t n, int64_t n_pad,
+                                          const float* shift_dev, float lo, float hi, const float* colmask, int64_t rows_per_batch,
+                                          float mask_value, float keep_add, void* stream) {
+  MQ_REQUIRE(x && y && shift_dev && rows > 0 && n > 0 && n_pad >= n, "softmax_rows_shifted: bad args");
+  MQ_REQUIRE(mqdet_softmax_rows_shifted_supported(n, n_pad), "softmax_rows_shifted: n == n_pad == 256 or n >= 4096 only");
+  if (rows_per_batch <= 0) rows_per_batch = rows;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (n == 256) {
+    MQ_REQUIRE((ldx % 4) == 0 && (ldy % 8) == 0 && ((uintptr_t)x % 16) == 0 && ((uintptr_t)y % 16) == 0 &&
+                   (!colmask || ((uintptr_t)colmask % 16) == 0), "softmax_rows_shifted: 16-byte aligned rows required for n = 256");
+    constexpr int RW = 2;
+    softmax_rows256_f32_kernel<RW><<<(unsigned)cdiv(rows, 8L * RW), 256, 0, st>>>(x, ldx, (__half*)y, ldy, rows, 1.f, colmask,
+                                                                                  rows_per_batch, mask_value, keep_add, shift_dev, lo, hi);
+    return check_launch("softmax_rows256_f32_kernel");
+  }
+  MQ_REQUIRE(rows <= 0x7fffffffL, "softmax_rows_shifted: too many rows");
+  softmax_longrows_f32_kernel<<<(unsigned)rows, 256, 0, st>>>(x, ldx, (__half*)y, ldy, (int)n, (int)n_pad, 1.f, colmask, rows_per_batch,
+                                                              mask_value, keep_add, shift_dev, lo, hi);
+  return check_launch("softmax_longrows_f32_kernel");
 }
 
 extern "C" int mqdet_cast_f32_f16(const float* x, void* y, int64_t n, void* stream) {

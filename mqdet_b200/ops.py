@@ -202,6 +202,27 @@ def softmax_rows(x, *, n=None, scale=1.0, colmask=None, rows_per_batch=0, mask_v
     return out
 
 
+def softmax_rows_shifted(x32, shift, lo, hi, *, n=None, colmask=None, rows_per_batch=0, mask_value=0.0, keep_add=0.0):
+    """softmax over the last dim of clamp(x - shift[0], lo, hi) (+ mask) for contiguous fp32 [..., n_pad] -> fp16; ``shift`` is a device
+    scalar.  Fused where the kernel supports the row length, else ``shift_clamp_`` (in place!) followed by ``softmax_rows``."""
+    global launch_count
+    _need_cuda(x32, shift, colmask)
+    n_pad = x32.shape[-1]
+    n = n_pad if n is None else n
+    if x32.dtype != torch.float32 or not x32.is_contiguous():
+        raise _lib.MqdetError("softmax_rows_shifted: contiguous fp32 tensor required")
+    if not load().mqdet_softmax_rows_shifted_supported(n, n_pad):
+        shift_clamp_(x32, shift, lo, hi)
+        return softmax_rows(x32, n=n, colmask=colmask, rows_per_batch=rows_per_batch, mask_value=mask_value, keep_add=keep_add)
+    rows = x32.numel() // n_pad
+    out = torch.empty(x32.shape, dtype=torch.float16, device=x32.device)
+    check(load().mqdet_softmax_rows_shifted(_ptr(x32), n_pad, _ptr(out), n_pad, rows, n, n_pad, _ptr(shift), float(lo), float(hi),
+                                            _ptr(colmask), int(rows_per_batch), float(mask_value), float(keep_add), _stream()),
+          "softmax_rows_shifted")
+    launch_count += 1
+    return out
+
+
 def global_max(x32):
     """max over ALL elements of a contiguous fp32 tensor -> device scalar [1] (no host sync)."""
     global launch_count
@@ -981,10 +1002,11 @@ def gdino_detections(logits, boxes, tokmap, img_wh, box_threshold, max_out=None)
     C, max_tok = tokmap.shape
     max_out = nq if max_out is None else int(max_out)
     out = torch.empty((B, max_out + 1, 6), dtype=torch.float32, device=logits.device)
+    ws = torch.empty((int(load().mqdet_gdino_detections_workspace_floats(B, nq)),), dtype=torch.float32, device=logits.device)
     check(load().mqdet_gdino_detections(_ptr(logits.float().contiguous()), T, _ptr(boxes.float().contiguous()), _ptr(tokmap), C,
                                         max_tok, _ptr(img_wh.float().contiguous()), float(box_threshold), B, nq, max_out,
-                                        _ptr(out), _stream()), "gdino_detections")
-    launch_count += 1
+                                        _ptr(out), _ptr(ws), _stream()), "gdino_detections")
+    launch_count += 2
     return out
 
 

@@ -97,8 +97,9 @@ class BiMultiHeadAttention(nn.Module):
             return self._attend_fused(vn16, ln16, k, mask_l, clamp, v_epilogue, l_epilogue)
         q = ops.gemm(vn16.view(B * N, Cv), w16(self.v_proj.weight), bias=f32(self.v_proj.bias), alpha=self.scale,
                      scale_after_bias=True).view(B, N, H, d)
-        vvT = torch.zeros((B, E, Np), dtype=torch.float16, device=dev) if Np != N else \
-            torch.empty((B, E, Np), dtype=torch.float16, device=dev)
+        vvT = torch.empty((B, E, Np), dtype=torch.float16, device=dev)
+        if Np != N:
+            vvT[:, :, N:].zero_()   # only the K-padding columns (a full memset is 91 MB per layer at N = 22323)
         ops.gemm(w16(self.values_v_proj.weight), vn16, out=vvT[:, :, :N], bias=f32(self.values_v_proj.bias),
                  bias_mode=VEC_PER_ROW)
         vlT = ops.gemm(w16(self.values_l_proj.weight), ln16, bias=f32(self.values_l_proj.bias), bias_mode=VEC_PER_ROW)
@@ -215,23 +216,25 @@ class BiMultiHeadAttention(nn.Module):
         lim = clamp if clamp > 0 else float("inf")
         A32 = torch.empty((B, H, N, T), dtype=torch.float32, device=dev)
         ops.gemm(qh, kh, out=A32, clamp=0.0 if stable else clamp)
-        if stable:  # attn_weights - attn_weights.max(), then the clamps; the maximum stays on the device
-            gmax = ops.global_max(A32)
-            ops.shift_clamp_(A32, gmax, -lim, lim)
-        Pv = ops.softmax_rows(A32, colmask=cm, rows_per_batch=H * N, mask_value=self.mask_fill[0], keep_add=self.mask_fill[1])
+        if stable:  # attn_weights - attn_weights.max(), then the clamps; the maximum stays on the device, the shift + clamps ride in
+            gmax = ops.global_max(A32)  # the softmax kernels (no pass of their own over the 183 MB score tensors)
+            Pv = ops.softmax_rows_shifted(A32, gmax, -lim, lim, colmask=cm, rows_per_batch=H * N, mask_value=self.mask_fill[0],
+                                          keep_add=self.mask_fill[1])
+        else:
+            Pv = ops.softmax_rows(A32, colmask=cm, rows_per_batch=H * N, mask_value=self.mask_fill[0], keep_add=self.mask_fill[1])
         del A32
         AT32 = torch.empty((B, H, T, Np), dtype=torch.float32, device=dev)
         if Np != N:
             AT32[..., N:].zero_()
         ops.gemm(kh, qh, out=AT32[..., :N], clamp=0.0 if stable else clamp)
+        # padded image tokens leave the text side's softmax (fuse_modules.py:201-206); mask rows are indexed with stride n (= N), not
+        # with the padded row length (mqdet_softmax_rows)
+        mv = mask_v.float().contiguous() if mask_v is not None else None
+        mkw = dict(colmask=mv, rows_per_batch=H * T, mask_value=float("-inf"), keep_add=0.0) if mv is not None else {}
         if stable:
-            ops.shift_clamp_(AT32, gmax, -lim, lim)
-        if mask_v is not None:  # padded image tokens leave the text side's softmax (fuse_modules.py:201-206)
-            # mask rows are indexed with stride n (= N), not with the padded row length (mqdet_softmax_rows)
-            Pl = ops.softmax_rows(AT32, n=N, colmask=mask_v.float().contiguous(), rows_per_batch=H * T, mask_value=float("-inf"),
-                                  keep_add=0.0)
+            Pl = ops.softmax_rows_shifted(AT32, gmax, -lim, lim, n=N, **mkw)
         else:
-            Pl = ops.softmax_rows(AT32, n=N)
+            Pl = ops.softmax_rows(AT32, n=N, **mkw)
         del AT32
         ov = torch.empty((B, N, H, d), dtype=torch.float16, device=dev)
         ops.gemm(Pv, vlT.view(B, H, d, T), out=ov.permute(0, 2, 1, 3))

@@ -307,3 +307,27 @@ def test_softmax_long_fp32_rows_with_mask(dev):
     assert_close(out[..., :N], ref, FP16_TOL, "softmax_rows long fp32 rows, masked")
     out2 = ops.softmax_rows(x.to(dev), n=N, scale=0.5).cpu()
     assert_close(out2[..., :N], (0.5 * x[..., :N]).softmax(-1), FP16_TOL, "softmax_rows long fp32 rows, scaled")
+
+
+def test_softmax_rows_shifted(dev):
+    """STABLE_SOFTMAX_2D's global shift + clamps fused into the softmax kernels (fuse_modules.py:177-187): both supported row lengths,
+    with the clamp ACTIVE on part of the scores, against the unfused formula."""
+    from mqdet_b200 import ops
+    g = torch.Generator().manual_seed(10)
+    for shape, n in (((2, 4, 300, 256), 256), ((2, 4, 16, 5008), 5003)):
+        x = torch.randn(*shape, generator=g) * 4.0
+        x[..., 7] += 30.0
+        rows_per_batch = shape[1] * shape[2]
+        keep = (torch.rand(shape[0], n, generator=g) > 0.2).float()
+        shift = x[..., :n].max().view(1)
+        lo, hi = -25.0, 25.0
+        ref = ((x[..., :n] - shift).clamp(lo, hi) + torch.where(keep == 0, float("-inf"), 0.0)[:, None, None, :]).softmax(-1)
+        out = ops.softmax_rows_shifted(x.to(dev).contiguous(), shift.to(dev), lo, hi, n=n, colmask=keep.to(dev).contiguous(),
+                                       rows_per_batch=rows_per_batch, mask_value=float("-inf")).cpu()
+        assert (out[..., n:] == 0).all()
+        assert_close(out[..., :n], ref, FP16_TOL, f"softmax_rows_shifted n={n}")
+    # unsupported row length: falls back to shift_clamp_ + softmax_rows
+    x = torch.randn(3, 40, 120, generator=g) * 4.0
+    shift = x.max().view(1)
+    out = ops.softmax_rows_shifted(x.to(dev).contiguous(), shift.to(dev), -5.0, 5.0).cpu()
+    assert_close(out, (x - shift).clamp(-5.0, 5.0).softmax(-1), FP16_TOL, "softmax_rows_shifted fallback")
