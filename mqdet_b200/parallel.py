@@ -85,3 +85,26 @@ def all_gather_chunks(packed_local, num_chunks, group=None):
     dist.all_gather_into_tensor(out, buf.contiguous(), group=group)
     idx = torch.tensor([(c % world) * per + c // world for c in range(num_chunks)], dtype=torch.long, device=out.device)
     return out.index_select(0, idx)
+
+
+def all_reduce_gradients(grads, group=None, average=True):
+    """Data-parallel gradient exchange of the modulated pre-training (the reference wraps the model in DistributedDataParallel,
+    tools/train_net.py:96-103; only the ~45.7 M GCP / PreSelect parameters carry gradients): ALL gradient tensors of a step are packed
+    into ONE flat fp32 buffer and reduced by ONE collective (NCCL all-reduce over NVLink; 183 MB), then averaged over the ranks like
+    DDP does and scattered back into the given tensors in place.  ``grads``: {name: fp32 tensor}; iteration order = key order, which
+    must be the same on every rank (it is: ``QVBertModelTrain.backward`` builds the dict deterministically).  Identity when no
+    process group is initialised."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return grads
+    world = dist.get_world_size(group)
+    keys = sorted(grads)
+    flat = torch.cat([grads[k].reshape(-1).float() for k in keys])
+    dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+    if average:
+        flat.div_(world)
+    off = 0
+    for k in keys:
+        n = grads[k].numel()
+        grads[k].copy_(flat[off:off + n].view_as(grads[k]))
+        off += n
+    return grads

@@ -79,3 +79,30 @@ def test_single_process_is_identity():
     assert parallel.shard_indices(10, 1, 4) == [1, 5, 9]
     d2, n2 = parallel.unpack(parallel.pack(det, num))
     assert torch.equal(d2, det) and torch.equal(n2, num)
+
+
+def _grad_worker(rank, world, port, ret):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    sys.path.insert(0, ROOT)
+    from mqdet_b200 import parallel
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    g = torch.Generator().manual_seed(100 + rank)
+    shapes = {"encoder.qv_layer.0.ff_gate": (1,), "encoder.qv_layer.0.attn.to_q.weight": (512, 768), "pre_select.layers.0.ff.norm.bias": (256,)}
+    grads = {k: torch.randn(*s, generator=g) for k, s in shapes.items()}
+    mine = {k: v.clone() for k, v in grads.items()}
+    parallel.all_reduce_gradients(grads)
+    other = torch.Generator().manual_seed(100 + (1 - rank))
+    exp = {k: (mine[k] + torch.randn(*s, generator=other)) / 2 for k, s in shapes.items()}
+    ret[rank] = all(torch.allclose(grads[k], exp[k], atol=1e-6) for k in shapes)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_gradient_all_reduce_world2_one_collective():
+    """Training side: every gradient of a step in ONE flat all-reduce, averaged over the ranks (DDP semantics)."""
+    world = 2
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    port = 31500 + (os.getpid() % 2000)
+    mp.spawn(_grad_worker, args=(world, port, ret), nprocs=world, join=True)
+    assert dict(ret) == {0: True, 1: True}
