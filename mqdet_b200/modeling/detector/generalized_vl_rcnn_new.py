@@ -38,6 +38,26 @@ def build_backbone(cfg):
     return nn.Sequential(OrderedDict([("body", body), ("fpn", fpn)]))
 
 
+def append_to_bank(query_images, labels, query_feats, cfg, exclude_similar=False, max_query_number=None):
+    """The bank bookkeeping shared by ``GeneralizedVLRCNN_New.extract_query`` (generalized_vl_rcnn_new.py:268-288) and
+    ``GroundingDINO.extract_query`` (groundingdino.py:411-430): append each box's pooled feature [n_scales, C] to ``query_images[label]``
+    up to MAX_QUERY_NUMBER per label, optionally skipping near-duplicates (cosine similarity above SIMILARITY_THRESHOLD).  Host-side
+    list handling on a handful of ground-truth boxes."""
+    import torch.nn.functional as F
+    max_query_number = cfg.VISION_QUERY.MAX_QUERY_NUMBER if max_query_number is None else max_query_number
+    for label, feat in zip(labels.tolist(), query_feats):
+        n = len(query_images[label])
+        if n >= max_query_number:
+            continue
+        if exclude_similar and n > 0:
+            bank = F.normalize(query_images[label], p=2, dim=-1)                    # [n, 1, C]
+            new = F.normalize(feat, p=2, dim=-1)                                     # [1, C]
+            if ((bank * new[None]).sum(-1) > cfg.VISION_QUERY.SIMILARITY_THRESHOLD).sum() > 0:
+                continue
+        query_images[label] = feat[None] if n == 0 else torch.cat([query_images[label], feat[None]])
+    return query_images
+
+
 class GeneralizedVLRCNN_New(nn.Module):
     def __init__(self, cfg):
         super().__init__()
@@ -117,18 +137,7 @@ class GeneralizedVLRCNN_New(nn.Module):
         query_feats = feats[:, None, :].cpu()                                            # [num_boxes, 1 scale, C]
         labels = torch.cat([t.get_field("labels") for t in targets]) if targets else torch.zeros(0, dtype=torch.long)
         assert len(labels) == len(query_feats)
-        max_query_number = self.cfg.VISION_QUERY.MAX_QUERY_NUMBER if max_query_number is None else max_query_number
-        for label, feat in zip(labels.tolist(), query_feats):
-            n = len(query_images[label])
-            if n >= max_query_number:
-                continue
-            if exclude_similar and n > 0:
-                bank = F.normalize(query_images[label], p=2, dim=-1)                    # [n, 1, C]
-                new = F.normalize(feat, p=2, dim=-1)                                     # [1, C]
-                if ((bank * new[None]).sum(-1) > self.cfg.VISION_QUERY.SIMILARITY_THRESHOLD).sum() > 0:
-                    continue
-            query_images[label] = feat[None] if n == 0 else torch.cat([query_images[label], feat[None]])
-        return query_images
+        return append_to_bank(query_images, labels, query_feats, self.cfg, exclude_similar, max_query_number)
 
     def invalidate_prompt_cache(self):
         """Drop everything cached per prompt (token ids, selected queries, masks, the head's token map)."""

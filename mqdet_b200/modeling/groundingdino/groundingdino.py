@@ -126,8 +126,48 @@ class GroundingDINO(nn.Module):
         import copy
         self.transformer.enc_out_bbox_embed = copy.deepcopy(_bbox_embed)                       # two_stage_bbox_embed_share False
         self.transformer.enc_out_class_embed = ContrastiveEmbed(self.max_text_len)
+        rb = getattr(cfg.MODEL, "ROI_BOX_HEAD", None)
+        self.pooler = None
+        if rb is not None:
+            from ..poolers import Pooler
+            self.pooler = Pooler(output_size=(rb.POOLER_RESOLUTION, rb.POOLER_RESOLUTION), scales=rb.POOLER_SCALES,
+                                 sampling_ratio=rb.POOLER_SAMPLING_RATIO, use_v2=True)
         self._prompt = None
         self._geo = None
+
+    # ---- vision-query bank extraction (groundingdino.py:340-430) ------------------------------------------------------
+    @torch.no_grad()
+    def extract_query(self, samples=None, targets=None, query_images=None, visual_features=None, exclude_similar=False, device=None,
+                      max_query_number=None):
+        """Expand every ground-truth box x EXPAND_RATIO, pool it from its level of the 4-level ``input_proj`` pyramid (aligned ROIAlign
+        POOLER_RESOLUTION^2, mean over the bins) and append it to ``query_images[label]`` ([n, 1, C]) — the GroundingDINO flavour of
+        ``GeneralizedVLRCNN_New.extract_query`` (same ``mqdet_roi_align_levels`` kernel, same bank bookkeeping)."""
+        from collections import defaultdict
+        from ..detector.generalized_vl_rcnn_new import GeneralizedVLRCNN_New, append_to_bank
+        if self.pooler is None:
+            raise MqdetError("extract_query needs cfg.MODEL.ROI_BOX_HEAD (POOLER_RESOLUTION / POOLER_SCALES / POOLER_SAMPLING_RATIO)")
+        if not getattr(self.cfg.VISION_QUERY, "SELECT_FPN_LEVEL", True):
+            raise NotImplementedError("VISION_QUERY.SELECT_FPN_LEVEL is True in every MQ config (CustomPooler over all levels is unused)")
+        query_images = defaultdict(list) if query_images is None else query_images
+        targets = GeneralizedVLRCNN_New.expand_bbox([t for t in targets if t is not None], self.cfg.VISION_QUERY.EXPAND_RATIO)
+        if visual_features is None:
+            images = to_image_list(samples, self.cfg.DATALOADER.SIZE_DIVISIBILITY)
+            if not images.tensors.is_cuda:
+                raise MqdetError("GroundingDINO.extract_query: CUDA images required (no CPU fallback)")
+            _, pyr16, sizes = self.visual_features(images.tensors)
+            levels = ops.get_levels(sizes, images.tensors.device)
+        else:
+            levels = ops.get_levels([(f.shape[2], f.shape[3]) for f in visual_features], visual_features[0].device)
+            pyr16 = ops.cast_f16(torch.cat([f.flatten(2).transpose(1, 2) for f in visual_features], dim=1).float().contiguous())
+        feats, _ = self.pooler.forward_flat(pyr16, levels, targets, mean_only=True)      # [num_boxes, C]
+        query_feats = feats[:, None, :].cpu()
+        labels = torch.cat([t.get_field("labels") for t in targets]) if targets else torch.zeros(0, dtype=torch.long)
+        assert len(labels) == len(query_feats)
+        return append_to_bank(query_images, labels, query_feats, self.cfg, exclude_similar, max_query_number)
+
+    def save_query_bank(self, query_images, path):
+        """The on-disk bank format of tools/extract_vision_query.py: torch.save of {label: FloatTensor[n, n_scales, C]}."""
+        torch.save({int(k): v.detach().cpu() for k, v in query_images.items()}, path)
 
     # ---- prompt / geometry state ------------------------------------------------------------------------------------
     def load_query_bank(self, query_path):

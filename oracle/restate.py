@@ -1011,14 +1011,11 @@ def gdino_detections(pred_logits, pred_boxes, positive_map, num_classes, image_s
     return out
 
 
-def gdino_forward(img, image_sizes, input_ids, attention_mask, positive_map, bank, sd, K=5, num_classes=80, num_queries=900,
-                  enc_layers=6, dec_layers=6, box_threshold=0.05):
-    """GroundingDINO.forward at eval (groundingdino.py:447-662) for a batch sharing one prompt: Swin-T (3 outputs) -> input_proj
-    (+ one stride-2 level) -> QuerySelector / flatten_fpn_features -> BertModelWarper(QVBertModel) with the per-category text
-    masks -> feat_map -> Transformer -> last-layer class logits / boxes -> detections.  img [B,3,H,W] normalised and padded;
-    image_sizes list of (h, w); bank {label: [n,1,256]} with n == K."""
+def gdino_visual_features(img, image_sizes, sd):
+    """Backbone + input projections of GroundingDINO.forward (groundingdino.py:486-516): Swin-T outputs 1..3 -> 1x1 conv + GroupNorm(32),
+    plus one 3x3 stride-2 conv + GroupNorm level from the last Swin output; padding masks interpolated per level.
+    Returns (srcs: 4 x [B,256,h,w], masks: 4 x bool [B,h,w])."""
     B, _, Hp, Wp = img.shape
-    T = input_ids.shape[1]
     feats = swin_transformer(img, _sub(sd, "backbone.0."))[1:]
     m = torch.zeros(B, Hp, Wp)
     for b, (h, w) in enumerate(image_sizes):
@@ -1032,6 +1029,18 @@ def gdino_forward(img, image_sizes, input_ids, attention_mask, positive_map, ban
     y = F.conv2d(feats[-1], sd["input_proj.3.0.weight"], sd["input_proj.3.0.bias"], stride=2, padding=1)
     srcs.append(F.group_norm(y, 32, sd["input_proj.3.1.weight"], sd["input_proj.3.1.bias"]))
     masks.append(F.interpolate(m[None], size=y.shape[-2:]).to(torch.bool)[0])
+    return srcs, masks
+
+
+def gdino_forward(img, image_sizes, input_ids, attention_mask, positive_map, bank, sd, K=5, num_classes=80, num_queries=900,
+                  enc_layers=6, dec_layers=6, box_threshold=0.05):
+    """GroundingDINO.forward at eval (groundingdino.py:447-662) for a batch sharing one prompt: Swin-T (3 outputs) -> input_proj
+    (+ one stride-2 level) -> QuerySelector / flatten_fpn_features -> BertModelWarper(QVBertModel) with the per-category text
+    masks -> feat_map -> Transformer -> last-layer class logits / boxes -> detections.  img [B,3,H,W] normalised and padded;
+    image_sizes list of (h, w); bank {label: [n,1,256]} with n == K."""
+    B = img.shape[0]
+    T = input_ids.shape[1]
+    srcs, masks = gdino_visual_features(img, image_sizes, sd)
     poss = [position_embedding_sine_hw(mk) for mk in masks]
     labels = [k for k, v in positive_map.items() if len(v) != 0]
     vision = torch.cat([bank[l][:K].flatten(0, 1) for l in labels])[None].expand(B, -1, -1)

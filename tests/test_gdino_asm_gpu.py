@@ -331,3 +331,40 @@ def test_softmax_rows_shifted(dev):
     shift = x.max().view(1)
     out = ops.softmax_rows_shifted(x.to(dev).contiguous(), shift.to(dev), -5.0, 5.0).cpu()
     assert_close(out, (x - shift).clamp(-5.0, 5.0).softmax(-1), FP16_TOL, "softmax_rows_shifted fallback")
+
+
+def test_groundingdino_extract_query_vs_oracle(dev):
+    """GroundingDINO.extract_query (groundingdino.py:340-430): boxes expanded x1.5, pooled from their level of the 4-level input_proj
+    pyramid (POOLER_SCALES 1/8 .. 1/64), bank appended per label — against the oracle's pooling of the oracle's pyramid."""
+    from collections import defaultdict
+    from mqdet_b200.structures.bounding_box import BoxList
+    from mqdet_b200.structures.image_list import ImageList
+    from oracle import restate, synth
+    sd, ids, am, pmap, bank, _ = _gdino_case(2040, 1, 32, 32, 5, 1, 1, 20)
+    model = _build_model(sd, 1, 1, 20, dev)
+    gen = synth.Gen(557)
+    W_, H_ = 640, 480
+    img = synth.rgb_images(gen, 2, H_, W_)
+    boxes = [torch.tensor([[10., 12., 40., 50.], [100., 60., 330., 300.], [0., 0., 639., 479.], [300., 200., 620., 460.]]),
+             torch.tensor([[30., 30., 190., 200.], [5., 200., 80., 318.]])]
+    labels = [torch.tensor([3, 1, 2, 3]), torch.tensor([1, 4])]
+    targets = []
+    for b, l in zip(boxes, labels):
+        t = BoxList(b.clone(), (W_, H_), mode="xyxy")
+        t.add_field("labels", l)
+        targets.append(t)
+    got = model.extract_query(samples=ImageList(img.to(dev), [(H_, W_)] * 2), targets=targets, query_images=defaultdict(list))
+    srcs, _ = restate.gdino_visual_features(img, [(H_, W_)] * 2, sd)
+    ex, lab = [], []
+    for b, l in zip(boxes, labels):
+        nb, keep = restate.expand_boxes(b.clone(), (W_, H_), 1.5)
+        ex.append(nb)
+        lab.append(l[keep])
+    feats, lvls = restate.pool_query_features(srcs, ex, scales=(0.125, 0.0625, 0.03125, 0.015625))
+    assert len(set(lvls.tolist())) >= 2
+    lab = torch.cat(lab)
+    assert sorted(got) == sorted(set(lab.tolist()))
+    for label in got:
+        want = feats[lab == label][:, None, :]
+        assert got[label].shape == want.shape
+        assert_close(got[label], want, 4e-3, f"gdino extract_query label {label}")
