@@ -370,6 +370,10 @@ int64_t mqdet_global_max_workspace_floats(void);
 int mqdet_global_max_f32(const float* x, int64_t n, float* out, float* workspace, void* stream);
 /* the same shift + clamps fused into the row softmax (one pass less over the scores): y = softmax_j(clamp(x - *shift_dev, lo, hi) + mask),
  * fp32 rows of n == n_pad == 256 (image -> text side) or n >= 4096 (text -> image side); mask arguments as mqdet_softmax_rows */
+/* reduction of a split-K product whose K slices ran as an extra batch dimension of mqdet_gemm_f16: part f32 [nb2][nb1][S][R][C] ->
+ * out16[z2 * o_s2 + z1 * o_s1 + r * ldo + c] = f16(sum_s part[z2][z1][s][r][c]); C % 4 == 0 */
+int mqdet_sum_splits_cast(const float* part, int64_t nb2, int64_t nb1, int64_t S, int64_t R, int64_t C, void* out16, int64_t o_s2, int64_t o_s1,
+                          int64_t ldo, void* stream);
 int mqdet_softmax_rows_shifted_supported(int64_t n, int64_t n_pad);
 int mqdet_softmax_rows_shifted(const float* x, int64_t ldx, void* y, int64_t ldy, int64_t rows, int64_t n, int64_t n_pad,
                                const float* shift_dev, float lo, float hi, const float* colmask, int64_t rows_per_batch, float mask_value,

@@ -76,6 +76,7 @@ SIGNATURES = {
     "mqdet_ml_nms_workspace_bytes": (c_int64, [c_int64]),
     "mqdet_global_max_workspace_floats": (c_int64, []),
     "mqdet_global_max_f32": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
+    "mqdet_sum_splits_cast": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_int64, c_int64, c_void_p, c_int64, c_int64, c_int64, c_void_p]),
     "mqdet_softmax_rows_shifted_supported": (c_int, [c_int64, c_int64]),
     "mqdet_softmax_rows_shifted": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int64, c_int64, c_void_p, c_float, c_float,
                                            c_void_p, c_int64, c_float, c_float, c_void_p]),

@@ -434,6 +434,30 @@ __global__ void __launch_bounds__(256) softmax_longrows_f32_kernel(const float* 
   for (int i = tid; i < n_pad; i += 256) yr[i] = __float2half_rn(i < n ? expf(val(i) - mx) * inv : 0.f);
 }
 
+// out16[z2][z1][r][c] (strides o_s2, o_s1, ldo) = sum_s part[z2][z1][s][r][c]: the reduction of a split-K product whose K slices ran as an
+// extra batch dimension of mqdet_gemm_f16 (fp32 partials).  One thread per 4 output columns.
+__global__ void __launch_bounds__(256) sum_splits_cast_kernel(const float4* __restrict__ part, int S, int R, int C4, int nb1, long o_s1, long o_s2,
+                                                              long ldo, long total, __half* __restrict__ out) {
+  const long i = (long)blockIdx.x * 256 + threadIdx.x;
+  if (i >= total) return;
+  const int c4 = (int)(i % C4);
+  const int r = (int)((i / C4) % R);
+  const long z = i / ((long)C4 * R);
+  const float4* p = part + (z * S * R + r) * C4 + c4;
+  float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int s = 0; s < S; ++s) {
+    const float4 v = p[(long)s * R * C4];
+    a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+  }
+  const long z1 = z % nb1, z2 = z / nb1;
+  __half* o = out + z2 * o_s2 + z1 * o_s1 + (long)r * ldo + c4 * 4;
+  const __half2 h0 = __floats2half2_rn(a.x, a.y), h1 = __floats2half2_rn(a.z, a.w);
+  uint2 u;
+  u.x = *reinterpret_cast<const uint32_t*>(&h0);
+  u.y = *reinterpret_cast<const uint32_t*>(&h1);
+  *reinterpret_cast<uint2*>(o) = u;
+}
+
 // Vectorised fp16 row softmax (rows 16-byte aligned, n % 8 == 0): one warp per row, 8 halfs per lane per step.
 //   ITERS > 0 : the whole row (n <= ITERS*256) lives in registers -> one read, one write      (A: n = 256 tokens)
 //   ITERS == 0: two passes, online max/sum then normalise                                     (At: n = 22400 locations)
@@ -1070,6 +1094,17 @@ extern "C" int mqdet_softmax_rows_shifted(const float* x, int64_t ldx, void* y, 
   softmax_longrows_f32_kernel<<<(unsigned)rows, 256, 0, st>>>(x, ldx, (__half*)y, ldy, (int)n, (int)n_pad, 1.f, colmask, rows_per_batch,
                                                               mask_value, keep_add, shift_dev, lo, hi);
   return check_launch("softmax_longrows_f32_kernel");
+}
+
+extern "C" int mqdet_sum_splits_cast(const float* part, int64_t nb2, int64_t nb1, int64_t S, int64_t R, int64_t C, void* out16, int64_t o_s2,
+                                     int64_t o_s1, int64_t ldo, void* stream) {
+  MQ_REQUIRE(part && out16 && nb1 > 0 && nb2 > 0 && S > 0 && R > 0 && C > 0 && (C % 4) == 0, "sum_splits_cast: bad args (C %% 4 == 0)");
+  MQ_REQUIRE(((uintptr_t)part & 15) == 0 && ((uintptr_t)out16 & 7) == 0 && (ldo % 4) == 0 && (o_s1 % 4) == 0 && (o_s2 % 4) == 0,
+             "sum_splits_cast: 16-byte aligned partials, 8-byte aligned output rows required");
+  const long total = nb1 * nb2 * R * (C / 4);
+  sum_splits_cast_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>((const float4*)part, (int)S, (int)R, (int)(C / 4),
+                                                                                          (int)nb1, o_s1, o_s2, ldo, total, (__half*)out16);
+  return check_launch("sum_splits_cast_kernel");
 }
 
 extern "C" int mqdet_cast_f32_f16(const float* x, void* y, int64_t n, void* stream) {

@@ -202,6 +202,21 @@ def softmax_rows(x, *, n=None, scale=1.0, colmask=None, rows_per_batch=0, mask_v
     return out
 
 
+def sum_splits_cast(part32, out16):
+    """part32 fp32 [nb2, nb1, S, R, C] contiguous (the fp32 partial products of a K-split GEMM) -> out16 [nb2, nb1, R, C] fp16 (a view with
+    arbitrary nb / row strides, contiguous last dim) = the sum over S."""
+    global launch_count
+    _need_cuda(part32, out16)
+    nb2, nb1, S, R, C = part32.shape
+    if part32.dtype != torch.float32 or not part32.is_contiguous() or out16.dtype != torch.float16 or tuple(out16.shape) != (nb2, nb1, R, C) \
+            or out16.stride(3) != 1:
+        raise _lib.MqdetError("sum_splits_cast: part fp32 [nb2,nb1,S,R,C] contiguous, out fp16 [nb2,nb1,R,C] with a contiguous last dim")
+    check(load().mqdet_sum_splits_cast(_ptr(part32), nb2, nb1, S, R, C, _ptr(out16), out16.stride(0), out16.stride(1), out16.stride(2),
+                                       _stream()), "sum_splits_cast")
+    launch_count += 1
+    return out16
+
+
 def softmax_rows_shifted(x32, shift, lo, hi, *, n=None, colmask=None, rows_per_batch=0, mask_value=0.0, keep_add=0.0):
     """softmax over the last dim of clamp(x - shift[0], lo, hi) (+ mask) for contiguous fp32 [..., n_pad] -> fp16; ``shift`` is a device
     scalar.  Fused where the kernel supports the row length, else ``shift_clamp_`` (in place!) followed by ``softmax_rows``."""

@@ -80,6 +80,8 @@ class BiMultiHeadAttention(nn.Module):
             nn.init.xavier_uniform_(m.weight)
             m.bias.data.fill_(0)
 
+    SPLIT_K = 8
+
     @torch.no_grad()
     def _attend(self, vn16, ln16, mask_l, v_epilogue=None, l_epilogue=None, mask_v=None):
         """vn16 [B,N,256] fp16, ln16 [B,T,768] fp16 (already layer-normed), mask_l [B,T] (1 keep / 0 padding) -> (dv, dl).
@@ -89,10 +91,13 @@ class BiMultiHeadAttention(nn.Module):
         T = ln16.shape[1]
         H, d, E = self.num_heads, self.head_dim, self.embed_dim
         dev = vn16.device
-        Np = (N + 7) // 8 * 8
         clamp = 50000.0 if (self.clamp_min_for_underflow or self.clamp_max_for_overflow) else 0.0
         k = ops.gemm(ln16.view(B * T, -1), w16(self.l_proj.weight), bias=f32(self.l_proj.bias)).view(B, T, H, d)
         explicit = self.stable_softmax_2d or mask_v is not None
+        # explicit path with many image tokens: the text-side P^T.V contracts over N with only B*H*T/128 output tiles, so it runs as
+        # SPLIT_K K-slices (an extra GEMM batch dimension) -> N is padded to a multiple of 64 * SPLIT_K instead of 8
+        split = self.SPLIT_K if (explicit and N >= 8192) else 1
+        Np = (N + 64 * split - 1) // (64 * split) * (64 * split) if split > 1 else (N + 7) // 8 * 8
         if not explicit and self.score_precision == "fused" and d == 256 and Cv == 256 and T % 8 == 0 and T <= 256 and H <= 8:
             return self._attend_fused(vn16, ln16, k, mask_l, clamp, v_epilogue, l_epilogue)
         q = ops.gemm(vn16.view(B * N, Cv), w16(self.v_proj.weight), bias=f32(self.v_proj.bias), alpha=self.scale,
@@ -239,7 +244,14 @@ class BiMultiHeadAttention(nn.Module):
         ov = torch.empty((B, N, H, d), dtype=torch.float16, device=dev)
         ops.gemm(Pv, vlT.view(B, H, d, T), out=ov.permute(0, 2, 1, 3))
         ol = torch.empty((B, T, H, d), dtype=torch.float16, device=dev)
-        ops.gemm(Pl, vvT.view(B, H, d, Np), out=ol.permute(0, 2, 1, 3))
+        S = self.SPLIT_K if (N >= 8192 and Np % (64 * self.SPLIT_K) == 0) else 1
+        if S > 1:   # K = Np in S slices as a batch dimension (16 output tiles would leave most SMs idle), fp32 partials, one reduction
+            ch = Np // S
+            part = torch.empty((B * H, S, T, d), dtype=torch.float32, device=dev)
+            ops.gemm(Pl.view(B * H, T, S, ch).permute(0, 2, 1, 3), vvT.view(B * H, d, S, ch).permute(0, 2, 1, 3), out=part)
+            ops.sum_splits_cast(part.view(B, H, S, T, d), ol.permute(0, 2, 1, 3))
+        else:
+            ops.gemm(Pl, vvT.view(B, H, d, Np), out=ol.permute(0, 2, 1, 3))
         return ov, ol
 
     def _finish(self, ov, ol, v_epilogue, l_epilogue, B, N, T, Cv):
