@@ -302,44 +302,18 @@ def run_gdino(args):
     caps = {"input_ids": ids, "attention_mask": am}
     il = ImageList(img.to(dev), [(H_IMG, W_IMG)] * B)
     host = img.pin_memory()
-    stage = torch.empty_like(img, device=dev)
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
-    gathered = torch.empty((world, B, 901, 6), dtype=torch.float32, device=dev) if world > 1 else None
 
-    # the forward has a fixed shape and no host synchronisation once the prompt / geometry state is cached: captured as ONE CUDA
-    # graph over a static input buffer (--no-graph: ~780 eager launches per step, launch-bound at 2 images)
-    static_in = il.tensors.clone()
-    sil = ImageList(static_in, [(H_IMG, W_IMG)] * B)
-    graph, static_out, graph_note = None, None, "eager launches"
-    if not args.no_graph:
-        try:
-            for _ in range(2):
-                model.forward_device(sil, caps, pmap)
-            torch.cuda.synchronize()
-            side = torch.cuda.Stream(device=dev)
-            side.wait_stream(torch.cuda.current_stream(dev))
-            with torch.cuda.stream(side):
-                model.forward_device(sil, caps, pmap)
-            torch.cuda.current_stream(dev).wait_stream(side)
-            g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
-                static_out = model.forward_device(sil, caps, pmap)["det_packed"]
-            graph, graph_note = g, "cuda-graph replay of the whole forward"
-        except Exception as e:  # noqa: BLE001
-            graph, graph_note = None, f"eager launches (graph capture failed: {type(e).__name__}: {str(e)[:120]})"
-            torch.cuda.synchronize()
+    # the public API: mqdet_b200.engine.inference.GroundingDINOEngine — the forward has a fixed shape and no host synchronisation once
+    # the prompt / geometry state is cached, so it is captured as ONE CUDA graph over a static input buffer (--no-graph: ~780 eager
+    # launches per step, launch-bound at 2 images) and replayed per batch; N > 1: one all-gather of the packed result per step
+    from mqdet_b200.engine.inference import GroundingDINOEngine
+    engine = GroundingDINOEngine(model, caps, pmap, tuple(img.shape), [(H_IMG, W_IMG)] * B, use_graph=not args.no_graph)
+    graph, graph_note = engine.graph, engine.note
+    engine.static_in.copy_(il.tensors)
 
     def step(x=None):
-        if graph is not None:
-            if x is not None:
-                static_in.copy_(x, non_blocking=True)
-            graph.replay()
-            det = static_out
-        else:
-            det = model.forward_device(il if x is None else ImageList(x, [(H_IMG, W_IMG)] * B), caps, pmap)["det_packed"]
-        if world > 1:   # the ONE collective of the step (mqdet_b200.parallel; gloo world-2 test in tests/test_parallel_cpu.py)
-            return parallel.all_gather_packed(det.contiguous(), out=gathered.view(world * B, 901, 6)).view(world, B, 901, 6)
-        return det
+        return engine.step_device(x)
 
     def barrier():
         if world > 1:
@@ -363,7 +337,7 @@ def run_gdino(args):
     launches = ops.launch_count
     if graph is not None:  # launches replayed per step = the launches recorded while capturing
         ops.launch_count = 0
-        model.forward_device(sil, caps, pmap)
+        model.forward_device(il, caps, pmap)
         launches = ops.launch_count * args.steps
     clk = clocks.stop() if rank == 0 else None
     ms = sum(a.elapsed_time(b) for a, b in ev) / args.steps
@@ -371,14 +345,7 @@ def run_gdino(args):
     barrier()
     t0 = time.time()
     nd = 0
-    for i in range(args.steps):
-        if graph is not None:
-            static_in.copy_(host, non_blocking=True)   # pinned host -> the graph's input buffer
-            r = step()
-        else:
-            stage.copy_(host, non_blocking=True)
-            r = step(stage)
-        boxlists = GroundingDINO.to_boxlists(r.reshape(-1, 901, 6)[rank * B:(rank + 1) * B] if world > 1 else r, [(H_IMG, W_IMG)] * B)
+    for boxlists in engine.run([host] * args.steps):   # pinned host -> input buffer -> replay (-> all-gather) -> D2H -> list[BoxList]
         nd += sum(len(b) for b in boxlists)
     barrier()
     e2e_ms = (time.time() - t0) * 1e3 / args.steps
@@ -400,6 +367,7 @@ def run_gdino(args):
                        "tokenisation": "pre-tokenised ids (no bert-base-uncased vocabulary offline)"},
             "e2e": {"value": world * B / (e2e_ms / 1e3), "unit": "images/s", "h2d_bytes_per_step": int(img.numel() * 4),
                     "d2h_bytes_per_step": int(B * 901 * 6 * 4), "detections_per_step": nd / args.steps,
+                    "api": "mqdet_b200.engine.inference.GroundingDINOEngine.run(host batches) -> list[BoxList] per batch",
                     "timing": "host wall clock around K steps incl. H2D, forward, D2H, BoxList construction"},
             "gpu_launches": launches, "clocks": clk}), flush=True)
     finish(world)

@@ -218,3 +218,67 @@ class InferenceEngine:
             if nxt is None:
                 return
             k ^= 1
+
+
+class GroundingDINOEngine:
+    """The same idea for ``mqdet_b200.modeling.groundingdino.groundingdino.GroundingDINO`` (BASELINE config 4): the whole forward
+    (≈ 780 kernels at 2 images) recorded once as a CUDA graph over a static input buffer and replayed per batch; pinned host images in,
+    ``list[BoxList]`` out, and — with ``torch.distributed`` initialised — ONE all-gather of the packed ``[B, num_queries + 1, 6]`` result
+    per step (``parallel.all_gather_packed``), issued after the replay, outside the graph.
+
+        eng = GroundingDINOEngine(model, captions, positive_map, batch_shape=(2, 3, 800, 1344), image_sizes=[(800, 1333)] * 2)
+        for boxlists in eng.run(host_batches): ...
+    """
+
+    def __init__(self, model, captions, positive_map, batch_shape, image_sizes, *, use_graph=True, gather=True, warmup=2):
+        self.model, self.captions, self.positive_map = model, captions, positive_map
+        self.dev = next(model.parameters()).device
+        if self.dev.type != "cuda":
+            raise MqdetError("GroundingDINOEngine: the model must live on a CUDA device (no CPU fallback)")
+        self.image_sizes = [tuple(s) for s in image_sizes]
+        self.B, self.nq = int(batch_shape[0]), int(model.num_queries)
+        self.world = dist.get_world_size() if (gather and dist.is_available() and dist.is_initialized()) else 1
+        self.static_in = torch.zeros(tuple(batch_shape), dtype=torch.float32, device=self.dev)
+        self.images = ImageList(self.static_in, self.image_sizes)
+        self.host = torch.empty((self.B, self.nq + 1, 6), dtype=torch.float32).pin_memory()
+        self.gathered = torch.empty((self.world * self.B, self.nq + 1, 6), dtype=torch.float32, device=self.dev) if self.world > 1 else None
+        self.graph, self.static_out, self.note = None, None, "eager launches"
+        for _ in range(max(1, warmup)):          # fills the per-prompt / per-geometry caches, fp16 weight copies, tensor maps
+            model.forward_device(self.images, captions, positive_map)
+        torch.cuda.synchronize(self.dev)
+        if use_graph:
+            try:
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    self.static_out = model.forward_device(self.images, captions, positive_map)["det_packed"]
+                self.graph, self.note = g, "cuda-graph replay of the whole forward"
+            except Exception as e:  # noqa: BLE001 - capture is an optimisation; the eager path is the same arithmetic
+                self.graph, self.note = None, f"eager launches (graph capture failed: {type(e).__name__}: {str(e)[:120]})"
+                torch.cuda.synchronize(self.dev)
+
+    @torch.no_grad()
+    def step_device(self, x=None):
+        """One forward over ``x`` (a device or pinned-host batch; None = whatever the input buffer holds) -> the device-resident
+        packed result of THIS rank ([B, nq + 1, 6]) or, N > 1, of all ranks ([world * B, nq + 1, 6], rank-major)."""
+        if x is not None:
+            self.static_in.copy_(x, non_blocking=True)
+        if self.graph is not None:
+            self.graph.replay()
+            det = self.static_out
+        else:
+            det = self.model.forward_device(self.images, self.captions, self.positive_map)["det_packed"]
+        if self.world > 1:
+            return parallel.all_gather_packed(det.contiguous(), out=self.gathered)
+        return det
+
+    @torch.no_grad()
+    def run(self, host_batches):
+        """host_batches: iterable of pinned fp32 [B,3,H,W] tensors -> yields ``list[BoxList]`` of the LOCAL images per batch."""
+        from ..modeling.groundingdino.groundingdino import GroundingDINO
+        rank = dist.get_rank() if self.world > 1 else 0
+        for hb in host_batches:
+            det = self.step_device(hb)
+            local = det[rank * self.B:(rank + 1) * self.B] if self.world > 1 else det
+            self.host.copy_(local, non_blocking=True)
+            torch.cuda.current_stream(self.dev).synchronize()
+            yield GroundingDINO.to_boxlists(self.host, self.image_sizes)
