@@ -381,6 +381,10 @@ def init_nccl(dev):
     os.environ.setdefault("NCCL_MAX_CTAS", "1")
     os.environ.setdefault("NCCL_MIN_CTAS", "1")
     dist.init_process_group("nccl", device_id=dev)
+    # ... and the persistent kernels leave that one SM to it (before any launch / graph capture): an NCCL CTA that waits for a
+    # peer (ranks drift by up to a step) otherwise delays one CTA of every persistent kernel it overlaps with
+    from mqdet_b200 import _lib
+    _lib.check(_lib.load().mqdet_reserve_sms(int(os.environ.get("MQDET_RESERVED_SMS", "1"))), "reserve_sms")
 
 
 def finish(world):

@@ -45,6 +45,10 @@ extern "C" {
 
 const char* mqdet_last_error(void);
 int mqdet_version(void);
+/* Leave n SMs free of the persistent one-CTA-per-SM kernels (GEMM, dcn_conv, biattn_*): call once per process BEFORE the first launch /
+ * graph capture when a collective kernel runs next to the forward (N > 1: one NCCL CTA waiting for a peer would otherwise hold the SM
+ * of one persistent CTA for the whole wait).  Process-wide; 0 (default) = use every SM. */
+int mqdet_reserve_sms(int n);
 
 /* D[z] = epilogue( A[z] (M x K, fp16, K contiguous) * B[z]^T (N x K, fp16, K contiguous) ), fp32 accumulate.
  *   v = alpha*acc + bias            (scale_after_bias == 0)

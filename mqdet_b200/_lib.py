@@ -40,6 +40,7 @@ class GemmArgs(ctypes.Structure):
 SIGNATURES = {
     "mqdet_last_error": (c_char_p, []),
     "mqdet_version": (c_int, []),
+    "mqdet_reserve_sms": (c_int, [c_int]),
     "mqdet_gemm_f16": (c_int, [POINTER(GemmArgs), c_int, c_void_p]),
     "mqdet_layernorm": (c_int, [c_void_p, c_int, c_int64, c_void_p, c_void_p, c_float, c_int64, c_int64, c_void_p,
                                 c_void_p, c_int64, c_int64, c_void_p]),

@@ -142,6 +142,20 @@ int make_store_map(CUtensorMap* map, void* C, int c_dtype, long M, long N, long 
 
 static const int kMaxDev = 64;
 
+// SMs the persistent one-CTA-per-SM kernels leave free (process-wide, set once before the first launch / graph capture):
+// a collective that runs next to the forward (one NCCL CTA spinning on a peer) otherwise takes the SM of one persistent CTA, whose
+// tiles then wait behind it in every kernel of the step.
+static std::atomic<int> g_reserved_sms{0};
+
+extern "C" int mqdet_reserve_sms(int n) {
+  if (n < 0 || n > 64) {
+    mqdet::set_error("mqdet_reserve_sms: 0 <= n <= 64 (got %d)", n);
+    return MQDET_ERR_ARG;
+  }
+  g_reserved_sms.store(n, std::memory_order_relaxed);
+  return MQDET_OK;
+}
+
 int num_sms() {
   static std::atomic<int> n[kMaxDev];
   int dev = 0;
@@ -153,7 +167,8 @@ int num_sms() {
     if (v <= 0) v = 148;
     n[slot].store(v, std::memory_order_relaxed);
   }
-  return v;
+  const int r = g_reserved_sms.load(std::memory_order_relaxed);
+  return v - r > 8 ? v - r : v;
 }
 
 // cudaFuncAttributeMaxDynamicSharedMemorySize is per (function, device): remember which pairs have been set.
