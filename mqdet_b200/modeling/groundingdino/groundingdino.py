@@ -197,13 +197,15 @@ class GroundingDINO(nn.Module):
     def _prompt_state(self, captions, positive_map, B, dev):
         """Token ids, per-category text masks / position ids (bertwarper.py:271-320), selected vision queries and the class ->
         token table: everything that depends on the prompt only, rebuilt when its CONTENT (or the query bank) changes."""
-        ids, am = self._tokenize(captions)
+        from ..detector.generalized_vl_rcnn_new import GeneralizedVLRCNN_New
         bank_version = self.query_selector.bank_version if self.query_selector is not None else 0
-        pk = tuple((int(k), tuple(int(t) for t in v)) for k, v in sorted(positive_map.items()))
-        key = (ids.detach().cpu().numpy().tobytes(), am.detach().cpu().numpy().tobytes(), pk, int(B), int(bank_version))
+        # content key (token ids / strings, positive map entries, batch size, bank version); device-resident ids are keyed by storage
+        # identity + version counter, so the hot path never synchronises to compare prompts
+        key = GeneralizedVLRCNN_New._prompt_key(captions, positive_map, B, bank_version)
         st = self._prompt
         if st is not None and st["key"] == key:
             return st
+        ids, am = self._tokenize(captions)
         ids, am = ids[:, : self.max_text_len].cpu(), am[:, : self.max_text_len].cpu()
         sam, pid, _ = generate_masks_with_special_tokens_and_transfer_map({"input_ids": ids}, self.specical_tokens, self.tokenizer)
         if ids.shape[0] == 1 and B > 1:
@@ -224,7 +226,8 @@ class GroundingDINO(nn.Module):
     def _geometry(self, image_sizes, padded_hw, level_hw, B, dev, st):
         """Padding masks per level (backbone.py:103-111, groundingdino.py:513-516), position embeddings, encoder reference points,
         valid ratios, anchor proposals, text position embeddings: functions of the image sizes and the prompt only."""
-        key = (tuple(tuple(int(v) for v in s) for s in image_sizes), tuple(padded_hw), tuple(level_hw), st["key"])
+        le = self.transformer.level_embed   # folded into the cached level position embeddings: a reloaded checkpoint invalidates them
+        key = (tuple(tuple(int(v) for v in s) for s in image_sizes), tuple(padded_hw), tuple(level_hw), st["key"], le.data_ptr(), le._version)
         if self._geo is not None and self._geo["key"] == key:
             return self._geo
         Hp, Wp = padded_hw
