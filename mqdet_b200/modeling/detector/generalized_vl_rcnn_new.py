@@ -184,9 +184,9 @@ class GeneralizedVLRCNN_New(nn.Module):
             raise MqdetError("string captions need a tokenizer (bert-base-uncased vocabulary is not available offline): "
                              "pass {'input_ids', 'attention_mask'} or set model.tokenizer")
         L = self.cfg.MODEL.LANGUAGE_BACKBONE
-        tok = self.tokenizer.batch_encode_plus(captions, max_length=L.MAX_QUERY_LEN,
-                                               padding="max_length" if L.PAD_MAX else "longest",
-                                               return_special_tokens_mask=True, return_tensors="pt", truncation=True)
+        encode = getattr(self.tokenizer, "batch_encode_plus", None) or self.tokenizer   # transformers >= 5 dropped the alias of __call__
+        tok = encode(captions, max_length=L.MAX_QUERY_LEN, padding="max_length" if L.PAD_MAX else "longest",
+                     return_special_tokens_mask=True, return_tensors="pt", truncation=True)
         return tok.input_ids.to(device), tok.attention_mask.to(device)
 
     @torch.no_grad()
