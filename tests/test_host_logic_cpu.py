@@ -10,7 +10,7 @@ import pytest
 
 from util import ROOT
 
-CASES = ["transformer", "biattn_split", "gcp_bwd", "bert_bwd", "preselect_bwd", "lang_train", "extract_query", "model"]
+CASES = ["transformer", "ref_signatures", "biattn_split", "gcp_bwd", "bert_bwd", "preselect_bwd", "lang_train", "extract_query", "model"]
 
 
 @pytest.mark.parametrize("case", CASES)
